@@ -1,0 +1,328 @@
+// C-ABI layer: argument validation, TMA tensor-map encoding, kernel launches. No torch types, no allocation.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "kernels.h"
+
+namespace vp3d {
+cudaError_t launch_project_points(const float* X, float* out3, float* out2, long long n_pts, const float* q,
+                                  const float* t, const float* cam, long long pts_per_q, long long pts_per_cam,
+                                  int mode, int sm_count, cudaStream_t stream);
+cudaError_t launch_mpjpe_fwd(const float* pred, const float* tgt, long long n_joints, const float* w, long long T,
+                             long long J, long long s_n, long long s_t, long long s_j, double* partial, float* out,
+                             int sm_count, cudaStream_t stream);
+cudaError_t launch_mpjpe_bwd(const float* pred, const float* tgt, const float* grad_out, long long n_joints,
+                             const float* w, long long T, long long J, long long s_n, long long s_t, long long s_j,
+                             float* grad_pred, int sm_count, cudaStream_t stream);
+cudaError_t launch_n_mpjpe_fwd(const float* pred, const float* tgt, long long n_poses, int J, double* partial,
+                               float* out, int sm_count, cudaStream_t stream);
+cudaError_t launch_pack_rows(int dtype, const float* src, void* dst, long long rows, int c, int c_pad, int sm_count,
+                             cudaStream_t stream);
+cudaError_t launch_pack_weight(int dtype, const float* w, void* dst, int c_out, int c_in, int taps, int rows_pad,
+                               int k_pad_per_tap, int transpose, int sm_count, cudaStream_t stream);
+cudaError_t launch_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                           float* scale, float* shift, int c, int c_pad, cudaStream_t stream);
+}  // namespace vp3d
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(VP3D_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+// Immutable per-device facts, resolved once (no other global state).
+struct DeviceInfo {
+  int sm_count = 0, cc_major = 0, cc_minor = 0;
+  bool ok = false;
+};
+constexpr int kMaxDevices = 64;
+DeviceInfo g_dev[kMaxDevices];
+std::mutex g_dev_mu;
+
+int device_info(DeviceInfo** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev < 0 || dev >= kMaxDevices) return fail(VP3D_ERR_INVALID, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lock(g_dev_mu);
+  DeviceInfo& d = g_dev[dev];
+  if (!d.ok) {
+    if ((e = cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess ||
+        (e = cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev)) != cudaSuccess ||
+        (e = cudaDeviceGetAttribute(&d.cc_minor, cudaDevAttrComputeCapabilityMinor, dev)) != cudaSuccess)
+      return cuda_fail(e, "cudaDeviceGetAttribute");
+    d.ok = true;
+  }
+  if (d.cc_major != 10)
+    return fail(VP3D_ERR_UNSUPPORTED, "vp3d_b200 kernels are built for sm_100a only; device is sm_%d%d", d.cc_major,
+                d.cc_minor);
+  *out = &d;
+  return VP3D_OK;
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::once_flag g_encode_once;
+
+EncodeTiledFn get_encode() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  });
+  return g_encode;
+}
+
+int elem_bytes(int dtype) { return dtype == VP3D_TF32 ? 4 : 2; }
+CUtensorMapDataType tm_dtype(int dtype) {
+  switch (dtype) {
+    case VP3D_F16: return CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    case VP3D_BF16: return CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    default: return CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  }
+}
+
+// Tiled map with a 128-byte inner box and SWIZZLE_128B; out-of-range elements read as zero.
+int encode_map(CUtensorMap* tm, int dtype, int rank, const void* base, const cuuint64_t* dims,
+               const cuuint64_t* strides_bytes, const cuuint32_t* box, const char* what) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) return fail(VP3D_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, tm_dtype(dtype), (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(VP3D_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d (dims %llu,%llu,%llu)", what, (int)r,
+                (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                (unsigned long long)(rank > 2 ? dims[2] : 0));
+  return VP3D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vp3d_version(void) { return 100; }
+
+const char* vp3d_last_error(void) { return g_err; }
+
+int vp3d_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  int sm = 0, maj = 0, min = 0;
+  if ((e = cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess ||
+      (e = cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev)) != cudaSuccess ||
+      (e = cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, dev)) != cudaSuccess)
+    return cuda_fail(e, "cudaDeviceGetAttribute");
+  if (sm_count) *sm_count = sm;
+  if (cc_major) *cc_major = maj;
+  if (cc_minor) *cc_minor = min;
+  if (maj != 10) return fail(VP3D_ERR_UNSUPPORTED, "device is sm_%d%d, need sm_100", maj, min);
+  return VP3D_OK;
+}
+
+int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
+  if (a == nullptr) return fail(VP3D_ERR_INVALID, "args is NULL");
+  if (a->dtype != VP3D_F16 && a->dtype != VP3D_BF16 && a->dtype != VP3D_TF32)
+    return fail(VP3D_ERR_INVALID, "unknown dtype %d", a->dtype);
+  if (a->block_n != 256 && a->block_n != 64) return fail(VP3D_ERR_INVALID, "block_n must be 256 or 64");
+  const int eb = elem_bytes(a->dtype);
+  const long long kblk = 128 / eb;  // elements of K per pipeline stage
+  if (a->a == nullptr || a->w == nullptr || a->out == nullptr) return fail(VP3D_ERR_INVALID, "null a / w / out");
+  if (a->a_seqs <= 0 || a->a_rows <= 0 || a->rows_out <= 0) return fail(VP3D_ERR_INVALID, "empty problem");
+  if (a->taps < 1 || a->k_per_tap <= 0 || a->k_per_tap % kblk != 0)
+    return fail(VP3D_ERR_INVALID, "k_per_tap (%lld) must be a positive multiple of %lld", a->k_per_tap, kblk);
+  if (a->k_total != (long long)a->taps * a->k_per_tap) return fail(VP3D_ERR_INVALID, "k_total != taps * k_per_tap");
+  if (a->a_kdim < a->k_per_tap) return fail(VP3D_ERR_INVALID, "a_kdim (%lld) < k_per_tap", a->a_kdim);
+  if (a->n_pad <= 0 || a->n_pad % a->block_n != 0) return fail(VP3D_ERR_INVALID, "n_pad must be a multiple of block_n");
+  if ((reinterpret_cast<uintptr_t>(a->a) & 15) || (reinterpret_cast<uintptr_t>(a->w) & 15) ||
+      (reinterpret_cast<uintptr_t>(a->out) & 15))
+    return fail(VP3D_ERR_INVALID, "a / w / out must be 16-byte aligned");
+  if ((a->a_row_stride * eb) % 16 != 0 || (a->a_seq_stride * eb) % 16 != 0)
+    return fail(VP3D_ERR_INVALID, "activation strides must be multiples of 16 bytes");
+  if (a->scale != nullptr && a->shift == nullptr) return fail(VP3D_ERR_INVALID, "scale without shift");
+  if (a->scale == nullptr && a->shift != nullptr) return fail(VP3D_ERR_INVALID, "shift without scale");
+  if ((a->stat_sum == nullptr) != (a->stat_sqsum == nullptr)) return fail(VP3D_ERR_INVALID, "stat_sum / stat_sqsum");
+  if (a->dtype == VP3D_TF32 && !a->out_f32) return fail(VP3D_ERR_INVALID, "TF32 activations are fp32: set out_f32");
+  if (!a->out_f32 && ((a->out_row_stride * 2) % 16 != 0 || (a->out_seq_stride * 2) % 16 != 0))
+    return fail(VP3D_ERR_INVALID, "16-bit output strides must be multiples of 16 bytes");
+  if (a->res != nullptr) {
+    if ((reinterpret_cast<uintptr_t>(a->res) & 15) || (a->res_row_stride * eb) % 16 != 0 ||
+        (a->res_seq_stride * eb) % 16 != 0)
+      return fail(VP3D_ERR_INVALID, "residual must be 16-byte aligned with 16-byte strides");
+  }
+  if (a->out_f32 && (a->n_valid <= 0 || a->n_valid > a->n_pad)) return fail(VP3D_ERR_INVALID, "bad n_valid");
+
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)a->a_kdim, (cuuint64_t)a->a_rows, (cuuint64_t)a->a_seqs};
+    cuuint64_t strides[2] = {(cuuint64_t)(a->a_row_stride * eb), (cuuint64_t)(a->a_seq_stride * eb)};
+    if (a->a_seqs == 1) strides[1] = (cuuint64_t)(a->a_rows * a->a_row_stride * eb);  // unused extent, keep it legal
+    cuuint32_t box[3] = {(cuuint32_t)kblk, 128, 1};
+    if (int rc = encode_map(&tmA, a->dtype, 3, a->a, dims, strides, box, "activations")) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)a->k_total, (cuuint64_t)a->n_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)(a->k_total * eb)};
+    cuuint32_t box[2] = {(cuuint32_t)kblk, (cuuint32_t)a->block_n};
+    if (int rc = encode_map(&tmB, a->dtype, 2, a->w, dims, strides, box, "weights")) return rc;
+  }
+
+  vp3d::ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.a_seqs = (int)a->a_seqs;
+  p.rows_out = (int)a->rows_out;
+  p.m_tiles_per_seq = (int)((a->rows_out + 127) / 128);
+  p.n_tiles = (int)(a->n_pad / a->block_n);
+  p.taps = a->taps;
+  p.kblocks_per_tap = (int)(a->k_per_tap / kblk);
+  p.tap_row_step = a->tap_row_step;
+  p.a_row_off = (int)a->a_row_off;
+  p.scale = a->scale;
+  p.shift = a->shift;
+  p.relu = a->relu;
+  p.res = a->res;
+  p.res_seq_stride = a->res_seq_stride;
+  p.res_row_stride = a->res_row_stride;
+  p.res_row_mul = a->res_row_mul;
+  p.res_row_off = a->res_row_off;
+  p.out = a->out;
+  p.out_seq_stride = a->out_seq_stride;
+  p.out_row_stride = a->out_row_stride;
+  p.out_f32 = a->out_f32;
+  p.n_valid = (int)(a->out_f32 ? a->n_valid : a->n_pad);
+  p.stat_sum = a->stat_sum;
+  p.stat_sqsum = a->stat_sqsum;
+
+  const long long total_tiles = (long long)p.a_seqs * p.m_tiles_per_seq * p.n_tiles;
+  if (total_tiles > 0x7fffffffLL) return fail(VP3D_ERR_INVALID, "too many tiles");
+  const int grid = (int)(total_tiles < dev->sm_count ? total_tiles : dev->sm_count);
+  cudaError_t e = vp3d::launch_conv_gemm(a->dtype, a->block_n, tmA, tmB, p, grid, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "conv_gemm launch");
+  return VP3D_OK;
+}
+
+int vp3d_pack_rows(int dtype, const float* src, void* dst, long long rows, int c, int c_pad, void* stream) {
+  if (src == nullptr || dst == nullptr || rows < 0 || c <= 0 || c_pad < c) return fail(VP3D_ERR_INVALID, "pack_rows args");
+  if (rows == 0) return VP3D_OK;
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_pack_rows(dtype, src, dst, rows, c, c_pad, dev->sm_count, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "pack_rows launch");
+  return VP3D_OK;
+}
+
+int vp3d_pack_conv_weight(int dtype, const float* w, void* dst, int c_out, int c_in, int taps, int rows_pad,
+                          int k_pad_per_tap, int transpose, void* stream) {
+  if (w == nullptr || dst == nullptr || c_out <= 0 || c_in <= 0 || taps <= 0)
+    return fail(VP3D_ERR_INVALID, "pack_conv_weight args");
+  if (!transpose && (rows_pad < c_out || k_pad_per_tap < c_in)) return fail(VP3D_ERR_INVALID, "pack_conv_weight padding");
+  if (transpose && (rows_pad < taps * c_in || k_pad_per_tap < c_out))
+    return fail(VP3D_ERR_INVALID, "pack_conv_weight (transposed) padding");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_pack_weight(dtype, w, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap, transpose,
+                                           dev->sm_count, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "pack_weight launch");
+  return VP3D_OK;
+}
+
+int vp3d_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps,
+                 float* scale, float* shift, int c, int c_pad, void* stream) {
+  if (!gamma || !beta || !running_mean || !running_var || !scale || !shift || c <= 0 || c_pad < c)
+    return fail(VP3D_ERR_INVALID, "bn_fold args");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_bn_fold(gamma, beta, running_mean, running_var, eps, scale, shift, c, c_pad,
+                                       static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "bn_fold launch");
+  return VP3D_OK;
+}
+
+int vp3d_project_points(const float* x, float* out3, float* out2, long long n_pts, const float* q, const float* t,
+                        const float* cam, long long pts_per_q, long long pts_per_cam, int mode, void* stream) {
+  if (n_pts < 0) return fail(VP3D_ERR_INVALID, "n_pts < 0");
+  if (n_pts == 0) return VP3D_OK;
+  if (x == nullptr) return fail(VP3D_ERR_INVALID, "x is NULL");
+  const int xf = mode & (VP3D_PT_WORLD_TO_CAMERA | VP3D_PT_CAMERA_TO_WORLD | VP3D_PT_ROTATE);
+  if (xf != 0 && (xf & (xf - 1)) != 0) return fail(VP3D_ERR_INVALID, "choose one rigid transform");
+  if (xf && q == nullptr) return fail(VP3D_ERR_INVALID, "q is NULL");
+  if ((mode & (VP3D_PT_WORLD_TO_CAMERA | VP3D_PT_CAMERA_TO_WORLD)) && t == nullptr)
+    return fail(VP3D_ERR_INVALID, "t is NULL");
+  if (xf && pts_per_q <= 0) return fail(VP3D_ERR_INVALID, "pts_per_q <= 0");
+  if (mode & VP3D_PT_PROJECT) {
+    if (cam == nullptr || out2 == nullptr) return fail(VP3D_ERR_INVALID, "projection needs cam and out2");
+    if (pts_per_cam <= 0) return fail(VP3D_ERR_INVALID, "pts_per_cam <= 0");
+  } else if (out2 != nullptr) {
+    return fail(VP3D_ERR_INVALID, "out2 given without VP3D_PT_PROJECT");
+  }
+  if (out3 == nullptr && out2 == nullptr) return fail(VP3D_ERR_INVALID, "no output");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_project_points(x, out3, out2, n_pts, q, t, cam, pts_per_q, pts_per_cam, mode,
+                                              dev->sm_count, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "project_points launch");
+  return VP3D_OK;
+}
+
+long long vp3d_loss_workspace_bytes(void) { return 8LL * 8 * 1024; }  // up to 8192 per-CTA partial sums (double)
+
+int vp3d_mpjpe_fwd(const float* pred, const float* target, long long n_joints, const float* w, long long T, long long J,
+                   long long w_stride_n, long long w_stride_t, long long w_stride_j, void* workspace, float* out,
+                   void* stream) {
+  if (!pred || !target || !workspace || !out || n_joints <= 0) return fail(VP3D_ERR_INVALID, "mpjpe_fwd args");
+  if (w != nullptr && (T <= 0 || J <= 0 || n_joints % (T * J) != 0)) return fail(VP3D_ERR_INVALID, "mpjpe_fwd weight grid");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  if (dev->sm_count * 8 > 8192) return fail(VP3D_ERR_UNSUPPORTED, "workspace too small for this device");
+  cudaError_t e = vp3d::launch_mpjpe_fwd(pred, target, n_joints, w, T, J, w_stride_n, w_stride_t, w_stride_j,
+                                         static_cast<double*>(workspace), out, dev->sm_count,
+                                         static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "mpjpe_fwd launch");
+  return VP3D_OK;
+}
+
+int vp3d_mpjpe_bwd(const float* pred, const float* target, const float* grad_out, long long n_joints, const float* w,
+                   long long T, long long J, long long w_stride_n, long long w_stride_t, long long w_stride_j,
+                   float* grad_pred, void* stream) {
+  if (!pred || !target || !grad_out || !grad_pred || n_joints <= 0) return fail(VP3D_ERR_INVALID, "mpjpe_bwd args");
+  if (w != nullptr && (T <= 0 || J <= 0 || n_joints % (T * J) != 0)) return fail(VP3D_ERR_INVALID, "mpjpe_bwd weight grid");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_mpjpe_bwd(pred, target, grad_out, n_joints, w, T, J, w_stride_n, w_stride_t, w_stride_j,
+                                         grad_pred, dev->sm_count, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "mpjpe_bwd launch");
+  return VP3D_OK;
+}
+
+int vp3d_n_mpjpe_fwd(const float* pred, const float* target, long long n_poses, int J, void* workspace, float* out,
+                     void* stream) {
+  if (!pred || !target || !workspace || !out || n_poses <= 0 || J <= 0) return fail(VP3D_ERR_INVALID, "n_mpjpe_fwd args");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_n_mpjpe_fwd(pred, target, n_poses, J, static_cast<double*>(workspace), out, dev->sm_count,
+                                           static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "n_mpjpe_fwd launch");
+  return VP3D_OK;
+}
+
+}  // extern "C"

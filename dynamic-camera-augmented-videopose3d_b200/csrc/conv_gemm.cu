@@ -1,0 +1,351 @@
+// K1: temporal-convolution block as a tcgen05 / TMEM implicit GEMM (sm_100a).
+//
+// What it replaces in the reference: every nn.Conv1d of the TemporalModel stack together with the BatchNorm
+// (eval: folded scale/shift), ReLU and residual slice-add that follow it
+// (common/models/TemporalModel.py:126-138 for the dilated model, :188-198 for the strided 1f model).
+//
+// Data layout: activations are channels-last [seq][frame][channel] in HBM, so an output tile of 128 frames
+// times one tap of a dilated (or strided) convolution is a plain 2-D box of the input: TMA fetches
+// [128 frames, 128 bytes of channels] at frame offset  t0 + tap * dilation  straight into a SWIZZLE_128B
+// shared-memory tile that tcgen05.mma consumes as a K-major operand. Frames past the end of a sequence are
+// zero-filled by TMA, so ragged tails need no masking on the load side.
+//
+// Pipeline (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer   : ring of STAGES {A 16 KB, B BN*128 B} stages, full/empty mbarriers
+//   warp 1      MMA issuer     : one thread issues 4 x tcgen05.mma (128 x BN x 32 bytes-of-K) per stage into one
+//                                of two TMEM accumulator buffers, tcgen05.commit frees the stage / publishes the tile
+//   warps 2..5  epilogue       : tcgen05.ld 32 lanes x 32 columns, y = acc*scale[c] + shift[c], ReLU, + residual,
+//                                convert, 16-byte stores; overlaps the next tile's MMAs through the 2nd TMEM buffer
+#include "ptx.cuh"
+#include "kernels.h"
+
+namespace vp3d {
+
+constexpr int kBlockM = 128;
+constexpr int kTileKBytes = 128;  // one swizzle span of K per stage row
+constexpr int kNumThreads = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = kBlockM * kTileKBytes;
+  static constexpr int kBBytes = BN * kTileKBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : 8;
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual alignment slack
+};
+
+template <int DT>
+struct ElemTraits;
+template <>
+struct ElemTraits<VP3D_F16> {
+  static constexpr int kBytes = 2;
+  static constexpr uint32_t kFormat = 0;
+};
+template <>
+struct ElemTraits<VP3D_BF16> {
+  static constexpr int kBytes = 2;
+  static constexpr uint32_t kFormat = 1;
+};
+template <>
+struct ElemTraits<VP3D_TF32> {
+  static constexpr int kBytes = 4;
+  static constexpr uint32_t kFormat = 2;
+};
+
+__device__ __forceinline__ uint32_t pack2(float a, float b, std::integral_constant<int, VP3D_F16>) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b, std::integral_constant<int, VP3D_BF16>) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack2(uint32_t u, std::integral_constant<int, VP3D_F16>) {
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+__device__ __forceinline__ float2 unpack2(uint32_t u, std::integral_constant<int, VP3D_BF16>) {
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+}
+
+struct TileCoord {
+  int seq, t0, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(int tile, const ConvGemmParams& p) {
+  TileCoord c;
+  const int n_tile = tile % p.n_tiles;
+  const int m_tile = tile / p.n_tiles;
+  c.seq = m_tile / p.m_tiles_per_seq;
+  c.t0 = (m_tile - c.seq * p.m_tiles_per_seq) * kBlockM;
+  c.n0 = n_tile;
+  return c;
+}
+
+template <int DT, int BN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const ConvGemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  using ET = ElemTraits<DT>;
+  constexpr int kElemsPerKBlock = kTileKBytes / ET::kBytes;  // 64 (16-bit) or 32 (tf32)
+  constexpr int kMmasPerStage = 4;                           // 32 bytes of K per tcgen05.mma
+  constexpr uint32_t kIdesc = make_instr_desc(ET::kFormat, kBlockM, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.a_seqs * p.m_tiles_per_seq * p.n_tiles;
+  const int num_kb = p.taps * p.kblocks_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_base_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(tile, p);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / p.kblocks_per_tap;
+          const int kc = kb - tap * p.kblocks_per_tap;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          tma_load_3d(sa, &tmA, &full_bar[stage], kc * kElemsPerKBlock,
+                      tc.t0 + p.a_row_off + tap * p.tap_row_step, tc.seq);
+          tma_load_2d(sa + Cfg::kABytes, &tmB, &full_bar[stage], kb * kElemsPerKBlock, tc.n0 * BN);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t adesc = make_kmajor_sw128_desc(sa);
+          const uint64_t bdesc = make_kmajor_sw128_desc(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < kMmasPerStage; ++k) {
+            // advance 32 bytes of K inside the swizzle span: +2 in the (address >> 4) field
+            if (ET::kBytes == 2)
+              umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0);
+            else
+              umma_tf32_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(tile, p);
+      const int t = tc.t0 + row;
+      const bool row_ok = t < p.rows_out;
+      const long long out_off = (long long)tc.seq * p.out_seq_stride + (long long)t * p.out_row_stride;
+      const long long res_off =
+          (long long)tc.seq * p.res_seq_stride + ((long long)t * p.res_row_mul + p.res_row_off) * p.res_row_stride;
+
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + acc * BN + c * 32 + (static_cast<uint32_t>(quad * 32) << 16), v);
+        tmem_wait_ld();
+        const int col0 = tc.n0 * BN + c * 32;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+
+        if (p.stat_sum != nullptr) {
+          // per-channel sum / sum of squares of the raw convolution output over the valid rows of this warp
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float s = row_ok ? f[j] : 0.f;
+            float q = s * s;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              s += __shfl_xor_sync(0xffffffffu, s, o);
+              q += __shfl_xor_sync(0xffffffffu, q, o);
+            }
+            if (lane == j) {
+              atomicAdd(p.stat_sum + col0 + j, s);
+              atomicAdd(p.stat_sqsum + col0 + j, q);
+            }
+          }
+        }
+        if (p.scale != nullptr) {
+          const float4* sc4 = reinterpret_cast<const float4*>(p.scale + col0);
+          const float4* sh4 = reinterpret_cast<const float4*>(p.shift + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 sc = __ldg(sc4 + j);
+            const float4 sh = __ldg(sh4 + j);
+            f[4 * j + 0] = fmaf(f[4 * j + 0], sc.x, sh.x);
+            f[4 * j + 1] = fmaf(f[4 * j + 1], sc.y, sh.y);
+            f[4 * j + 2] = fmaf(f[4 * j + 2], sc.z, sh.z);
+            f[4 * j + 3] = fmaf(f[4 * j + 3], sc.w, sh.w);
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (row_ok) {
+          if (p.res != nullptr) {
+            if (ET::kBytes == 2) {
+              const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.res) + res_off + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 r = __ldg(r4 + j);
+                const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 x = unpack2(rr[e], std::integral_constant < int, DT == VP3D_TF32 ? VP3D_F16 : DT > {});
+                  f[8 * j + 2 * e + 0] += x.x;
+                  f[8 * j + 2 * e + 1] += x.y;
+                }
+              }
+            } else {
+              const float4* r4 = reinterpret_cast<const float4*>(static_cast<const float*>(p.res) + res_off + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 r = __ldg(r4 + j);
+                f[4 * j + 0] += r.x;
+                f[4 * j + 1] += r.y;
+                f[4 * j + 2] += r.z;
+                f[4 * j + 3] += r.w;
+              }
+            }
+          }
+          if (p.out_f32) {
+            float* o = static_cast<float*>(p.out) + out_off + col0;
+            if (col0 + 32 <= p.n_valid && (p.out_row_stride & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                reinterpret_cast<float4*>(o)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.n_valid) o[j] = f[j];
+            }
+          } else {
+            // element-typed output (fp16 / bf16); activation buffers are always padded to the tile width
+            uint4* o = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + out_off + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 w;
+              constexpr int D16 = (DT == VP3D_TF32) ? VP3D_F16 : DT;
+              w.x = pack2(f[8 * j + 0], f[8 * j + 1], std::integral_constant<int, D16>{});
+              w.y = pack2(f[8 * j + 2], f[8 * j + 3], std::integral_constant<int, D16>{});
+              w.z = pack2(f[8 * j + 4], f[8 * j + 5], std::integral_constant<int, D16>{});
+              w.w = pack2(f[8 * j + 6], f[8 * j + 7], std::integral_constant<int, D16>{});
+              o[j] = w;
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int DT, int BN>
+static cudaError_t launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid,
+                              cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;  // per-process; idempotent, so a benign race at worst repeats the call
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<DT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  conv_gemm_kernel<DT, BN><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv_gemm(int dtype, int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                             const ConvGemmParams& p, int grid, cudaStream_t stream) {
+  if (block_n == 256) {
+    if (dtype == VP3D_F16) return launch_one<VP3D_F16, 256>(tmA, tmB, p, grid, stream);
+    if (dtype == VP3D_BF16) return launch_one<VP3D_BF16, 256>(tmA, tmB, p, grid, stream);
+    if (dtype == VP3D_TF32) return launch_one<VP3D_TF32, 256>(tmA, tmB, p, grid, stream);
+  } else if (block_n == 64) {
+    if (dtype == VP3D_F16) return launch_one<VP3D_F16, 64>(tmA, tmB, p, grid, stream);
+    if (dtype == VP3D_BF16) return launch_one<VP3D_BF16, 64>(tmA, tmB, p, grid, stream);
+    if (dtype == VP3D_TF32) return launch_one<VP3D_TF32, 64>(tmA, tmB, p, grid, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace vp3d

@@ -1,0 +1,121 @@
+// Layout / bookkeeping kernels around the conv GEMM (all HBM-bound, tiny next to the GEMMs):
+//   pack_rows      fp32 [rows][c]  ->  operand type [rows][c_pad]   (model input (N,T,J*F) -> padded channels-last)
+//   pack_weight    nn.Conv1d weight (c_out, c_in, taps) fp32 -> K-major packed operand [n_pad][taps][c_in_pad]
+//                  (or its transpose for data-gradient GEMMs)
+//   bn_fold        eval-mode BatchNorm1d -> per-channel scale/shift (TemporalModel.py:32,117,119 in eval())
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "kernels.h"
+
+namespace vp3d {
+
+template <int DT>
+__device__ __forceinline__ void store_elem(void* dst, long long i, float v);
+template <>
+__device__ __forceinline__ void store_elem<VP3D_F16>(void* dst, long long i, float v) {
+  static_cast<__half*>(dst)[i] = __float2half_rn(v);
+}
+template <>
+__device__ __forceinline__ void store_elem<VP3D_BF16>(void* dst, long long i, float v) {
+  static_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16_rn(v);
+}
+template <>
+__device__ __forceinline__ void store_elem<VP3D_TF32>(void* dst, long long i, float v) {
+  static_cast<float*>(dst)[i] = v;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const float* __restrict__ src, void* __restrict__ dst, long long rows, int c, int c_pad) {
+  const long long total = rows * c_pad;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / c_pad;
+    const int k = (int)(i - r * c_pad);
+    store_elem<DT>(dst, i, k < c ? __ldg(src + r * c + k) : 0.f);
+  }
+}
+
+// dst[n][tap][ci] = w[n][ci][tap]             (transpose == 0; rows = output channels, K = tap*c_in_pad + ci)
+// dst[tap*c_in + ci][co] = w[co][ci][tap]     (transpose == 1; rows = (tap, ci), K = output channel)
+template <int DT>
+__global__ void __launch_bounds__(256)
+pack_weight_kernel(const float* __restrict__ w, void* __restrict__ dst, int c_out, int c_in, int taps, int rows_pad,
+                   int k_pad_per_tap, int transpose) {
+  const long long k_total = transpose ? k_pad_per_tap : (long long)taps * k_pad_per_tap;
+  const long long total = (long long)rows_pad * k_total;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / k_total;
+    const long long k = i - r * k_total;
+    float v = 0.f;
+    if (!transpose) {
+      const int tap = (int)(k / k_pad_per_tap);
+      const int ci = (int)(k - (long long)tap * k_pad_per_tap);
+      if (r < c_out && ci < c_in) v = __ldg(w + ((long long)r * c_in + ci) * taps + tap);
+    } else {
+      const int tap = (int)(r / c_in);
+      const int ci = (int)(r - (long long)tap * c_in);
+      if (tap < taps && k < c_out) v = __ldg(w + ((long long)k * c_in + ci) * taps + tap);
+    }
+    store_elem<DT>(dst, i, v);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+               const float* __restrict__ var, float eps, float* __restrict__ scale, float* __restrict__ shift, int c,
+               int c_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c_pad) return;
+  if (i < c) {
+    const float s = gamma[i] / sqrtf(var[i] + eps);
+    scale[i] = s;
+    shift[i] = beta[i] - mean[i] * s;
+  } else {
+    scale[i] = 0.f;
+    shift[i] = 0.f;
+  }
+}
+
+static int ew_grid(long long total, int sm_count) {
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+cudaError_t launch_pack_rows(int dtype, const float* src, void* dst, long long rows, int c, int c_pad, int sm_count,
+                             cudaStream_t stream) {
+  const int grid = ew_grid(rows * c_pad, sm_count);
+  if (dtype == VP3D_F16) pack_rows_kernel<VP3D_F16><<<grid, 256, 0, stream>>>(src, dst, rows, c, c_pad);
+  else if (dtype == VP3D_BF16) pack_rows_kernel<VP3D_BF16><<<grid, 256, 0, stream>>>(src, dst, rows, c, c_pad);
+  else if (dtype == VP3D_TF32) pack_rows_kernel<VP3D_TF32><<<grid, 256, 0, stream>>>(src, dst, rows, c, c_pad);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_weight(int dtype, const float* w, void* dst, int c_out, int c_in, int taps, int rows_pad,
+                               int k_pad_per_tap, int transpose, int sm_count, cudaStream_t stream) {
+  const long long k_total = transpose ? k_pad_per_tap : (long long)taps * k_pad_per_tap;
+  const int grid = ew_grid((long long)rows_pad * k_total, sm_count);
+  if (dtype == VP3D_F16)
+    pack_weight_kernel<VP3D_F16><<<grid, 256, 0, stream>>>(w, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap, transpose);
+  else if (dtype == VP3D_BF16)
+    pack_weight_kernel<VP3D_BF16><<<grid, 256, 0, stream>>>(w, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap, transpose);
+  else if (dtype == VP3D_TF32)
+    pack_weight_kernel<VP3D_TF32><<<grid, 256, 0, stream>>>(w, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap, transpose);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                           float* scale, float* shift, int c, int c_pad, cudaStream_t stream) {
+  bn_fold_kernel<<<(c_pad + 255) / 256, 256, 0, stream>>>(gamma, beta, mean, var, eps, scale, shift, c, c_pad);
+  return cudaGetLastError();
+}
+
+}  // namespace vp3d

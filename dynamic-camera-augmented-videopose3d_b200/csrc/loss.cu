@@ -1,0 +1,203 @@
+// K6: fused joint-error losses (HBM-bandwidth bound, 24 B per joint forward, +12 B backward).
+//
+// Replaces, for CUDA tensors, the sub / norm / mean chains of
+//   common/loss.py:11-17  mpjpe            mean_{n,t,j} || pred - target ||_2
+//   common/loss.py:21-27  weighted_mpjpe   mean_{n,t,j} w * || pred - target ||_2   (w broadcast over the joint grid)
+//   common/loss.py:70-80  n_mpjpe          mpjpe(scale * pred, target), scale = mean_j<target,pred> / mean_j<pred,pred>
+// Forward is a two-stage deterministic reduction (per-CTA partial sums in double, one finishing CTA), so the value
+// does not depend on atomics ordering. Backward writes d loss / d pred = g/n * w * (pred - target) / ||pred - target||
+// (zero where the distance is zero, as torch.linalg.norm's backward does).
+#include "kernels.h"
+
+namespace vp3d {
+
+constexpr int kLossThreads = 256;
+
+struct WeightView {
+  const float* w;  // nullptr = unweighted
+  long long T, J;  // joint grid (n, t, j) of the loss
+  long long s_n, s_t, s_j;  // element strides of w over that grid (0 = broadcast)
+};
+
+__device__ __forceinline__ float weight_at(const WeightView& wv, long long idx) {
+  if (wv.w == nullptr) return 1.f;
+  const long long j = idx % wv.J;
+  const long long nt = idx / wv.J;
+  const long long t = nt % wv.T;
+  const long long n = nt / wv.T;
+  return __ldg(wv.w + n * wv.s_n + t * wv.s_t + j * wv.s_j);
+}
+
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double warp_part[kLossThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x < 32) {
+    r = (threadIdx.x < kLossThreads / 32) ? warp_part[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  return r;  // valid in thread 0
+}
+
+__device__ __forceinline__ float dist3(float px, float py, float pz, float tx, float ty, float tz) {
+  const float dx = px - tx, dy = py - ty, dz = pz - tz;
+  return sqrtf(dx * dx + dy * dy + dz * dz);
+}
+
+__global__ void __launch_bounds__(kLossThreads)
+mpjpe_partial_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, long long n_joints, WeightView wv,
+                     int vec_ok, double* __restrict__ partial) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n_quads = vec_ok ? (n_joints >> 2) : 0;
+  double acc = 0.0;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_quads; g += stride) {
+    const float4* p4 = reinterpret_cast<const float4*>(pred) + 3 * g;
+    const float4* t4 = reinterpret_cast<const float4*>(tgt) + 3 * g;
+    const float4 a = __ldg(p4), b = __ldg(p4 + 1), c = __ldg(p4 + 2);
+    const float4 d = __ldg(t4), e = __ldg(t4 + 1), f = __ldg(t4 + 2);
+    const float e0 = dist3(a.x, a.y, a.z, d.x, d.y, d.z);
+    const float e1 = dist3(a.w, b.x, b.y, d.w, e.x, e.y);
+    const float e2 = dist3(b.z, b.w, c.x, e.z, e.w, f.x);
+    const float e3 = dist3(c.y, c.z, c.w, f.y, f.z, f.w);
+    if (wv.w == nullptr) {
+      acc += (double)((e0 + e1) + (e2 + e3));
+    } else {
+      acc += (double)(weight_at(wv, 4 * g) * e0) + (double)(weight_at(wv, 4 * g + 1) * e1) +
+             (double)(weight_at(wv, 4 * g + 2) * e2) + (double)(weight_at(wv, 4 * g + 3) * e3);
+    }
+  }
+  for (long long i = 4 * n_quads + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_joints; i += stride) {
+    const float e0 = dist3(pred[3 * i], pred[3 * i + 1], pred[3 * i + 2], tgt[3 * i], tgt[3 * i + 1], tgt[3 * i + 2]);
+    acc += (double)(weight_at(wv, i) * e0);
+  }
+  const double s = block_sum(acc);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(kLossThreads)
+mean_finish_kernel(const double* __restrict__ partial, int n_partial, double inv_count, float* __restrict__ out) {
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n_partial; i += blockDim.x) acc += partial[i];
+  const double s = block_sum(acc);
+  if (threadIdx.x == 0) out[0] = (float)(s * inv_count);
+}
+
+__global__ void __launch_bounds__(kLossThreads)
+mpjpe_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, const float* __restrict__ grad_out,
+                 float inv_count, long long n_joints, WeightView wv, int vec_ok, float* __restrict__ grad_pred) {
+  const float g0 = __ldg(grad_out) * inv_count;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n_quads = vec_ok ? (n_joints >> 2) : 0;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_quads; g += stride) {
+    const float4* p4 = reinterpret_cast<const float4*>(pred) + 3 * g;
+    const float4* t4 = reinterpret_cast<const float4*>(tgt) + 3 * g;
+    const float4 a = __ldg(p4), b = __ldg(p4 + 1), c = __ldg(p4 + 2);
+    const float4 d = __ldg(t4), e = __ldg(t4 + 1), f = __ldg(t4 + 2);
+    float v[12] = {a.x - d.x, a.y - d.y, a.z - d.z, a.w - d.w, b.x - e.x, b.y - e.y,
+                   b.z - e.z, b.w - e.w, c.x - f.x, c.y - f.y, c.z - f.z, c.w - f.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float nrm = sqrtf(v[3 * i] * v[3 * i] + v[3 * i + 1] * v[3 * i + 1] + v[3 * i + 2] * v[3 * i + 2]);
+      const float s = nrm > 0.f ? g0 * weight_at(wv, 4 * g + i) / nrm : 0.f;
+      v[3 * i] *= s;
+      v[3 * i + 1] *= s;
+      v[3 * i + 2] *= s;
+    }
+    float4* o = reinterpret_cast<float4*>(grad_pred) + 3 * g;
+    o[0] = make_float4(v[0], v[1], v[2], v[3]);
+    o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    o[2] = make_float4(v[8], v[9], v[10], v[11]);
+  }
+  for (long long i = 4 * n_quads + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_joints; i += stride) {
+    const float dx = pred[3 * i] - tgt[3 * i], dy = pred[3 * i + 1] - tgt[3 * i + 1], dz = pred[3 * i + 2] - tgt[3 * i + 2];
+    const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float s = nrm > 0.f ? g0 * weight_at(wv, i) / nrm : 0.f;
+    grad_pred[3 * i] = dx * s;
+    grad_pred[3 * i + 1] = dy * s;
+    grad_pred[3 * i + 2] = dz * s;
+  }
+}
+
+// n_mpjpe: one warp per (n, t) pose; lanes stride over the J joints of the pose.
+__global__ void __launch_bounds__(kLossThreads)
+n_mpjpe_partial_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, long long n_poses, int J,
+                       double* __restrict__ partial) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  double acc = 0.0;
+  for (long long pose = warp_global; pose < n_poses; pose += n_warps) {
+    const float* p = pred + pose * J * 3;
+    const float* t = tgt + pose * J * 3;
+    float pp = 0.f, tp = 0.f;
+    for (int j = lane; j < J; j += 32) {
+      const float px = p[3 * j], py = p[3 * j + 1], pz = p[3 * j + 2];
+      const float tx = t[3 * j], ty = t[3 * j + 1], tz = t[3 * j + 2];
+      pp += px * px + py * py + pz * pz;
+      tp += tx * px + ty * py + tz * pz;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      pp += __shfl_xor_sync(0xffffffffu, pp, o);
+      tp += __shfl_xor_sync(0xffffffffu, tp, o);
+    }
+    const float scale = (tp / (float)J) / (pp / (float)J);
+    float e = 0.f;
+    for (int j = lane; j < J; j += 32)
+      e += dist3(scale * p[3 * j], scale * p[3 * j + 1], scale * p[3 * j + 2], t[3 * j], t[3 * j + 1], t[3 * j + 2]);
+    acc += (double)e;
+  }
+  const double s = block_sum(acc);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int loss_grid(long long n_joints, int sm_count) {
+  long long blocks = ((n_joints + 3) / 4 + kLossThreads - 1) / kLossThreads;
+  const long long cap = (long long)sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+cudaError_t launch_mpjpe_fwd(const float* pred, const float* tgt, long long n_joints, const float* w, long long T,
+                             long long J, long long s_n, long long s_t, long long s_j, double* partial, float* out,
+                             int sm_count, cudaStream_t stream) {
+  WeightView wv{w, T > 0 ? T : 1, J > 0 ? J : 1, s_n, s_t, s_j};
+  const int grid = loss_grid(n_joints, sm_count);
+  const int vec_ok = aligned16(pred) && aligned16(tgt);
+  mpjpe_partial_kernel<<<grid, kLossThreads, 0, stream>>>(pred, tgt, n_joints, wv, vec_ok, partial);
+  mean_finish_kernel<<<1, kLossThreads, 0, stream>>>(partial, grid, n_joints > 0 ? 1.0 / (double)n_joints : 0.0, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mpjpe_bwd(const float* pred, const float* tgt, const float* grad_out, long long n_joints,
+                             const float* w, long long T, long long J, long long s_n, long long s_t, long long s_j,
+                             float* grad_pred, int sm_count, cudaStream_t stream) {
+  if (n_joints <= 0) return cudaSuccess;
+  WeightView wv{w, T > 0 ? T : 1, J > 0 ? J : 1, s_n, s_t, s_j};
+  const int grid = loss_grid(n_joints, sm_count);
+  const int vec_ok = aligned16(pred) && aligned16(tgt) && aligned16(grad_pred);
+  mpjpe_bwd_kernel<<<grid, kLossThreads, 0, stream>>>(pred, tgt, grad_out, 1.f / (float)n_joints, n_joints, wv, vec_ok,
+                                                      grad_pred);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_n_mpjpe_fwd(const float* pred, const float* tgt, long long n_poses, int J, double* partial,
+                               float* out, int sm_count, cudaStream_t stream) {
+  long long blocks = (n_poses * 32 + kLossThreads - 1) / kLossThreads;
+  const long long cap = (long long)sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  n_mpjpe_partial_kernel<<<(int)blocks, kLossThreads, 0, stream>>>(pred, tgt, n_poses, J, partial);
+  const double cnt = (double)n_poses * (double)J;
+  mean_finish_kernel<<<1, kLossThreads, 0, stream>>>(partial, (int)blocks, cnt > 0 ? 1.0 / cnt : 0.0, out);
+  return cudaGetLastError();
+}
+
+}  // namespace vp3d

@@ -1,0 +1,182 @@
+// K5: per-frame camera projection (HBM-bandwidth bound).
+//
+// Replaces, for CUDA tensors, the ATen elementwise chains behind
+//   common/quaternion.py:10-24  qrot        v + 2*(w*(q x v) + q x (q x v))
+//   common/quaternion.py:27-35  qinverse    conjugate of a unit quaternion
+//   common/camera.py:28-34      world_to_camera / camera_to_world
+//   common/camera.py:37-67      project_to_2d         (3 radial + 2 tangential distortion terms)
+//   common/camera.py:69-90      project_to_2d_linear
+// and fuses world -> camera -> image plane for the dynamic-camera case (one quaternion + translation per frame).
+//
+// Arithmetic follows the reference operation by operation in fp32 with contraction disabled (explicit
+// __fmul_rn/__fadd_rn), so results agree with the unfused PyTorch/NumPy evaluation to the last bit or two,
+// including the clamp saturation for z -> 0 and NaN propagation for 0/0.
+//
+// Access pattern: each thread owns 4 consecutive points = three aligned float4 loads (48 B) and writes two float4
+// of 2-D output; the per-frame camera record (quaternion 4 + translation 3 + intrinsics 9 floats) is read through the
+// read-only path and is shared by the J joints of a frame. A scalar path covers tails and unaligned views.
+#include "kernels.h"
+
+namespace vp3d {
+
+struct Quat {
+  float w, x, y, z;
+};
+
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+
+// quaternion.py:21-24
+__device__ __forceinline__ float3 qrot_dev(const Quat q, const float3 v) {
+  float3 uv, uuv, r;
+  uv.x = sub(mul(q.y, v.z), mul(q.z, v.y));
+  uv.y = sub(mul(q.z, v.x), mul(q.x, v.z));
+  uv.z = sub(mul(q.x, v.y), mul(q.y, v.x));
+  uuv.x = sub(mul(q.y, uv.z), mul(q.z, uv.y));
+  uuv.y = sub(mul(q.z, uv.x), mul(q.x, uv.z));
+  uuv.z = sub(mul(q.x, uv.y), mul(q.y, uv.x));
+  r.x = add(v.x, mul(2.f, add(mul(q.w, uv.x), uuv.x)));
+  r.y = add(v.y, mul(2.f, add(mul(q.w, uv.y), uuv.y)));
+  r.z = add(v.z, mul(2.f, add(mul(q.w, uv.z), uuv.z)));
+  return r;
+}
+
+// torch.clamp semantics: NaN stays NaN (fminf/fmaxf would drop it)
+__device__ __forceinline__ float clamp_unit(float x) {
+  if (x != x) return x;
+  return fminf(fmaxf(x, -1.f), 1.f);
+}
+
+// camera.py:54-67 (linear != 0: camera.py:85-90)
+__device__ __forceinline__ float2 project_dev(const float3 X, const float* __restrict__ cam, int linear) {
+  const float fx = __ldg(cam + 0), fy = __ldg(cam + 1), cx = __ldg(cam + 2), cy = __ldg(cam + 3);
+  const float xx = clamp_unit(__fdiv_rn(X.x, X.z));
+  const float yy = clamp_unit(__fdiv_rn(X.y, X.z));
+  float2 o;
+  if (linear) {
+    o.x = add(mul(fx, xx), cx);
+    o.y = add(mul(fy, yy), cy);
+    return o;
+  }
+  const float k1 = __ldg(cam + 4), k2 = __ldg(cam + 5), k3 = __ldg(cam + 6), p1 = __ldg(cam + 7), p2 = __ldg(cam + 8);
+  const float r2 = add(mul(xx, xx), mul(yy, yy));
+  const float r4 = mul(r2, r2);
+  const float r6 = mul(r4, r2);
+  const float radial = add(1.f, add(add(mul(k1, r2), mul(k2, r4)), mul(k3, r6)));
+  const float tan = add(mul(p1, xx), mul(p2, yy));
+  const float s = add(radial, tan);
+  o.x = add(mul(fx, add(mul(xx, s), mul(p1, r2))), cx);
+  o.y = add(mul(fy, add(mul(yy, s), mul(p2, r2))), cy);
+  return o;
+}
+
+// One point through the selected stages.
+//   mode bit 0: subtract translation then rotate by the conjugate quaternion (world -> camera)
+//   mode bit 1: rotate by the quaternion then add translation (camera -> world)
+//   mode bit 2: rotate only (qrot); bit 3 with it: use the conjugate
+//   mode bit 4: project to 2-D; bit 5: linear projection
+struct PointOps {
+  const float* q;      // [n_q][4] (w,x,y,z)
+  const float* t;      // [n_q][3]
+  const float* cam;    // [n_cam][9]
+  long long pts_per_q;    // consecutive points sharing one quaternion/translation record
+  long long pts_per_cam;  // consecutive points sharing one intrinsics record
+  int mode;
+};
+
+__device__ __forceinline__ float3 transform_point(const PointOps& o, long long idx, float3 X) {
+  if (o.mode & 7) {
+    const long long qi = idx / o.pts_per_q;
+    const float* qp = o.q + 4 * qi;
+    Quat q{__ldg(qp + 0), __ldg(qp + 1), __ldg(qp + 2), __ldg(qp + 3)};
+    if (o.mode & 1) {
+      const float* tt = o.t + 3 * qi;
+      X.x = sub(X.x, __ldg(tt + 0));
+      X.y = sub(X.y, __ldg(tt + 1));
+      X.z = sub(X.z, __ldg(tt + 2));
+      q.x = -q.x;
+      q.y = -q.y;
+      q.z = -q.z;
+      X = qrot_dev(q, X);
+    } else if (o.mode & 2) {
+      const float* tt = o.t + 3 * qi;
+      X = qrot_dev(q, X);
+      X.x = add(X.x, __ldg(tt + 0));
+      X.y = add(X.y, __ldg(tt + 1));
+      X.z = add(X.z, __ldg(tt + 2));
+    } else {
+      if (o.mode & 8) {
+        q.x = -q.x;
+        q.y = -q.y;
+        q.z = -q.z;
+      }
+      X = qrot_dev(q, X);
+    }
+  }
+  return X;
+}
+
+__global__ void __launch_bounds__(256)
+project_points_kernel(const float* __restrict__ X, float* __restrict__ out3, float* __restrict__ out2, long long n_pts,
+                      PointOps o, int vec_ok) {
+  const long long n_quads = vec_ok ? (n_pts >> 2) : 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_quads; g += stride) {
+    const float4* src = reinterpret_cast<const float4*>(X) + 3 * g;
+    const float4 a = __ldg(src + 0), b = __ldg(src + 1), c = __ldg(src + 2);
+    float3 P[4] = {{a.x, a.y, a.z}, {a.w, b.x, b.y}, {b.z, b.w, c.x}, {c.y, c.z, c.w}};
+    float2 Q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long idx = 4 * g + i;
+      P[i] = transform_point(o, idx, P[i]);
+      if (o.mode & 16) Q[i] = project_dev(P[i], o.cam + 9 * (idx / o.pts_per_cam), o.mode & 32);
+    }
+    if (out3 != nullptr) {
+      float4* d = reinterpret_cast<float4*>(out3) + 3 * g;
+      d[0] = make_float4(P[0].x, P[0].y, P[0].z, P[1].x);
+      d[1] = make_float4(P[1].y, P[1].z, P[2].x, P[2].y);
+      d[2] = make_float4(P[2].z, P[3].x, P[3].y, P[3].z);
+    }
+    if (out2 != nullptr) {
+      float4* d = reinterpret_cast<float4*>(out2) + 2 * g;
+      d[0] = make_float4(Q[0].x, Q[0].y, Q[1].x, Q[1].y);
+      d[1] = make_float4(Q[2].x, Q[2].y, Q[3].x, Q[3].y);
+    }
+  }
+  // scalar tail (and the whole range when the buffers are not 16-byte aligned)
+  for (long long idx = 4 * n_quads + (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n_pts; idx += stride) {
+    float3 P = {X[3 * idx], X[3 * idx + 1], X[3 * idx + 2]};
+    P = transform_point(o, idx, P);
+    if (out3 != nullptr) {
+      out3[3 * idx] = P.x;
+      out3[3 * idx + 1] = P.y;
+      out3[3 * idx + 2] = P.z;
+    }
+    if (out2 != nullptr) {
+      const float2 Q = project_dev(P, o.cam + 9 * (idx / o.pts_per_cam), o.mode & 32);
+      out2[2 * idx] = Q.x;
+      out2[2 * idx + 1] = Q.y;
+    }
+  }
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+cudaError_t launch_project_points(const float* X, float* out3, float* out2, long long n_pts, const float* q,
+                                  const float* t, const float* cam, long long pts_per_q, long long pts_per_cam,
+                                  int mode, int sm_count, cudaStream_t stream) {
+  if (n_pts <= 0) return cudaSuccess;
+  PointOps o{q, t, cam, pts_per_q > 0 ? pts_per_q : 1, pts_per_cam > 0 ? pts_per_cam : 1, mode};
+  const int vec_ok = aligned16(X) && (out3 == nullptr || aligned16(out3)) && (out2 == nullptr || aligned16(out2));
+  const long long work = vec_ok ? ((n_pts + 3) >> 2) : n_pts;
+  long long blocks = (work + 255) / 256;
+  const long long cap = (long long)sm_count * 8;  // 8 resident CTAs of 256 threads per SM, grid-stride beyond
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  project_points_kernel<<<(unsigned)blocks, 256, 0, stream>>>(X, out3, out2, n_pts, o, vec_ok);
+  return cudaGetLastError();
+}
+
+}  // namespace vp3d

@@ -1,0 +1,126 @@
+"""The CPU oracle (oracle/) against golden outputs of the real reference (tests/golden/make_golden.py).
+This pins the oracle; the GPU tests then compare the CUDA path with the oracle."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, state_from_npz
+from oracle import camera as ocam
+from oracle import loss as oloss
+from oracle import temporal_model as otm
+
+
+def _checksum(sd):
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(sd[k].detach().cpu().numpy().tobytes())
+    return h.hexdigest()
+
+
+def test_small_models_eval():
+    z = load_golden('temporal_small.npz')
+    sd = state_from_npz(z, 'sd/')
+    x = torch.from_numpy(z['x'])
+    fw = [3, 3, 3]
+    with torch.no_grad():
+        np.testing.assert_allclose(otm.forward(sd, x, fw).numpy(), z['y_full'], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(otm.forward(sd, x, fw, causal=True).numpy(), z['y_causal'], rtol=0, atol=1e-6)
+        xw = x[:, :27].contiguous()
+        np.testing.assert_allclose(otm.forward(sd, xw, fw, strided=True).numpy(), z['y_1f'], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(otm.forward(sd, xw, fw, strided=True, causal=True).numpy(), z['y_1f_causal'],
+                                   rtol=0, atol=1e-6)
+        sdd = state_from_npz(z, 'sdd/')
+        np.testing.assert_allclose(otm.forward(sdd, x, fw, dense=True).numpy(), z['y_dense'], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize('name,strided', [('1f', True), ('full', False)])
+def test_small_models_train_step(name, strided):
+    z = load_golden('temporal_small.npz')
+    sd = state_from_npz(z, 'sd/')
+    x = torch.from_numpy(z['x'])
+    if strided:
+        x = x[:, :27].contiguous()
+    tgt = torch.from_numpy(z['train_%s/target' % name])
+    loss, pred, grads, stats = otm.train_step_grads(sd, x, tgt, [3, 3, 3], strided=strided)
+    np.testing.assert_allclose(pred.numpy(), z['train_%s/pred' % name], atol=2e-6)
+    np.testing.assert_allclose(loss.numpy(), z['train_%s/loss' % name], atol=1e-6)
+    for k, g in grads.items():
+        np.testing.assert_allclose(g.numpy(), z['train_%s/grad/%s' % (name, k)], atol=1e-6, err_msg=k)
+    for k, v in stats.items():
+        np.testing.assert_allclose(v.numpy(), z['train_%s/buf/%s' % (name, k)], atol=1e-6, err_msg=k)
+
+
+def test_api_helpers():
+    z = load_golden('temporal_small.npz')
+    assert otm.receptive_field(otm.make_plan([3, 3, 3])) == int(z['api/receptive_field']) == 27
+    assert otm.receptive_field(otm.make_plan([3, 3, 3, 3, 3])) == 243
+
+
+@pytest.mark.parametrize('fname', ['temporal_27f_1024.npz', 'temporal_243f_1024.npz',
+                                   'temporal_243f_1024_causal.npz', 'temporal_243f_j31.npz'])
+def test_seeded_1024_channel_models(fname):
+    z = load_golden(fname)
+    fw = [int(v) for v in z['filter_widths']]
+    sd = otm.init_state(int(z['j_in']), 2, int(z['j_out']), fw, channels=1024, seed=int(z['seed']))
+    assert _checksum(sd) == str(z['checksum']), 'seeded state_dict drifted from the one the golden was made with'
+    x = torch.from_numpy(z['x'])
+    causal = bool(z['causal'])
+    with torch.no_grad():
+        y = otm.forward(sd, x, fw, causal=causal).numpy()
+        rf = otm.receptive_field(otm.make_plan(fw))
+        y1f = otm.forward(sd, x[:, :rf].contiguous(), fw, causal=causal, strided=True).numpy()
+    np.testing.assert_allclose(y, z['y'], atol=2e-6)
+    np.testing.assert_allclose(y1f, z['y_1f'], atol=2e-6)
+    # reference property (TemporalModel.py:147-149): the 1f model equals the full model on an RF-long window
+    np.testing.assert_allclose(y1f, z['y'][:, :1], atol=2e-6)
+
+
+def test_camera_oracle():
+    z = load_golden('camera.npz')
+    X, q, t = z['X'], z['q'], z['t']
+    np.testing.assert_allclose(ocam.world_to_camera(X, q, t), z['w2c'], rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(ocam.camera_to_world(X, q, t), z['c2w'], rtol=2e-6, atol=1e-6)
+    qf, tf = z['qf'], z['tf']
+    qb = np.ascontiguousarray(np.broadcast_to(qf[:, None, :], (*X.shape[:-1], 4)))
+    np.testing.assert_allclose(ocam.qrot(qb, X), z['qrot_f'], rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(ocam.world_to_camera(X, qf, tf), z['w2c_f'], rtol=2e-6, atol=1e-6)
+    np.testing.assert_array_equal(ocam.qinverse(qf), z['qinv_f'])
+    np.testing.assert_allclose(ocam.project_to_2d(z['Xc'], z['cams']), z['proj'], rtol=2e-6, atol=1e-6, equal_nan=True)
+    np.testing.assert_allclose(ocam.project_to_2d_linear(z['Xc'], z['cams']), z['proj_linear'], rtol=2e-6, atol=1e-6,
+                               equal_nan=True)
+    assert np.isnan(z['proj'][0, 0, 1]).all(), 'golden must contain the 0/0 -> NaN case'
+    ns = ocam.normalize_screen_coordinates(z['px'], w=1000, h=1002)
+    assert ns.dtype == z['norm_sc'].dtype == np.float64  # NumPy-2 promotion quirk of camera.py:18
+    np.testing.assert_allclose(ns, z['norm_sc'], atol=0)
+    np.testing.assert_allclose(ocam.image_coordinates(ns, w=1000, h=1002), z['img_sc'], atol=0)
+    # round trip (camera.py:28-34) and the 3x4-extrinsic einsum form (prepare_data_cmu_camera.py:61-66)
+    np.testing.assert_allclose(ocam.camera_to_world(ocam.world_to_camera(X, q, t), q, t), X, atol=5e-6)
+    Rm = ocam.quat_to_matrix(ocam.qinverse(qf).astype(np.float64))
+    E = np.concatenate((Rm, -(Rm @ tf[..., None].astype(np.float64))), axis=-1)
+    np.testing.assert_allclose(ocam.extrinsic_einsum(X.astype(np.float64), E), z['w2c_f'], atol=1e-5)
+
+
+def test_loss_oracle():
+    z = load_golden('loss.npz')
+    pred, tgt = torch.from_numpy(z['pred']), torch.from_numpy(z['tgt'])
+    p = pred.clone().requires_grad_(True)
+    l = oloss.mpjpe(p, tgt)
+    l.backward()
+    np.testing.assert_allclose(l.detach().numpy(), z['mpjpe'], atol=1e-7)
+    np.testing.assert_allclose(p.grad.numpy(), z['mpjpe_grad'], atol=1e-8)
+    assert np.all(z['mpjpe_grad'][0, 0, 0] == 0)
+    for wname in ('w_n', 'w_nt1', 'w_ntj'):
+        w = torch.from_numpy(z[wname])
+        p = pred.clone().requires_grad_(True)
+        l = oloss.weighted_mpjpe(p, tgt, w)
+        l.backward()
+        np.testing.assert_allclose(l.detach().numpy(), z['wmpjpe_' + wname], atol=1e-7)
+        np.testing.assert_allclose(p.grad.numpy(), z['wmpjpe_grad_' + wname], atol=1e-8)
+    np.testing.assert_allclose(oloss.n_mpjpe(pred, tgt).numpy(), z['n_mpjpe'], atol=1e-7)
+    J = pred.shape[2]
+    P, T = z['pred'].reshape(-1, J, 3), z['tgt'].reshape(-1, J, 3)
+    np.testing.assert_allclose(oloss.p_mpjpe(P.copy(), T.copy()), float(z['p_mpjpe']), rtol=1e-6)
+    np.testing.assert_allclose(oloss.mean_velocity_error(P[:, 0], T[:, 0]), float(z['mve']), rtol=1e-6)
