@@ -1,0 +1,93 @@
+"""ctypes binding of lib/libvp3d_b200.so (the C ABI declared in include/vp3d_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+import threading
+
+_PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG_DIR, 'lib', 'libvp3d_b200.so')
+
+F16, BF16, TF32 = 0, 1, 2
+DTYPE_NAMES = {'fp16': F16, 'float16': F16, 'half': F16, 'bf16': BF16, 'bfloat16': BF16, 'tf32': TF32}
+
+PT_WORLD_TO_CAMERA, PT_CAMERA_TO_WORLD, PT_ROTATE, PT_CONJ, PT_PROJECT, PT_LINEAR = 1, 2, 4, 8, 16, 32
+
+
+class ConvArgs(C.Structure):
+    """struct vp3d_conv_args (include/vp3d_b200.h)"""
+    _fields_ = [
+        ('dtype', C.c_int), ('block_n', C.c_int),
+        ('a', C.c_void_p), ('a_seqs', C.c_longlong), ('a_rows', C.c_longlong), ('a_kdim', C.c_longlong),
+        ('a_row_stride', C.c_longlong), ('a_seq_stride', C.c_longlong), ('a_row_off', C.c_longlong),
+        ('w', C.c_void_p), ('n_pad', C.c_longlong), ('k_total', C.c_longlong), ('taps', C.c_int),
+        ('tap_row_step', C.c_int), ('k_per_tap', C.c_longlong),
+        ('rows_out', C.c_longlong), ('out', C.c_void_p), ('out_f32', C.c_int), ('out_row_stride', C.c_longlong),
+        ('out_seq_stride', C.c_longlong), ('n_valid', C.c_longlong),
+        ('scale', C.c_void_p), ('shift', C.c_void_p), ('relu', C.c_int),
+        ('res', C.c_void_p), ('res_row_stride', C.c_longlong), ('res_seq_stride', C.c_longlong),
+        ('res_row_mul', C.c_int), ('res_row_off', C.c_int),
+        ('stat_sum', C.c_void_p), ('stat_sqsum', C.c_void_p),
+    ]
+
+
+_SIGNATURES = {
+    'vp3d_version': (C.c_int, []),
+    'vp3d_last_error': (C.c_char_p, []),
+    'vp3d_device_info': (C.c_int, [C.POINTER(C.c_int)] * 3),
+    'vp3d_conv_block_fwd': (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    'vp3d_pack_rows': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
+    'vp3d_pack_conv_weight': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_void_p]),
+    'vp3d_bn_fold': (C.c_int, [C.c_void_p] * 4 + [C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    'vp3d_project_points': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p]),
+    'vp3d_loss_workspace_bytes': (C.c_longlong, []),
+    'vp3d_mpjpe_fwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p] + [C.c_longlong] * 5 +
+                       [C.c_void_p, C.c_void_p, C.c_void_p]),
+    'vp3d_mpjpe_bwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p] + [C.c_longlong] * 5 +
+                       [C.c_void_p, C.c_void_p]),
+    'vp3d_n_mpjpe_fwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def declared_symbols():
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    """The loaded library. Raises RuntimeError (loudly, no fallback) when it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        'vp3d_b200: %s not found -- build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                        'or `make -C dynamic-camera-augmented-videopose3d_b200/csrc`. There is no CPU fallback.'
+                        % LIB_PATH)
+                handle = C.CDLL(LIB_PATH)
+                for name, (res, args) in _SIGNATURES.items():
+                    fn = getattr(handle, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = handle
+    return _lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = lib().vp3d_last_error().decode('utf-8', 'replace')
+        if rc == 1:
+            raise AssertionError('vp3d_b200 %s: %s' % (what, msg))  # the reference signals bad shapes with assert
+        raise RuntimeError('vp3d_b200 %s failed (status %d): %s' % (what, rc, msg))
+
+
+def device_info():
+    sm, maj, mnr = C.c_int(), C.c_int(), C.c_int()
+    check(lib().vp3d_device_info(C.byref(sm), C.byref(maj), C.byref(mnr)), 'device_info')
+    return sm.value, maj.value, mnr.value

@@ -1,0 +1,209 @@
+"""torch-facing wrappers over the C ABI: tensors in, tensors out, raw pointers + current stream underneath.
+
+PyTorch is plumbing here (device memory from the caching allocator, the current CUDA stream, autograd graph
+bookkeeping); every arithmetic operation on the hot path runs in libvp3d_b200.so.
+"""
+import ctypes as C
+
+import torch
+
+from . import native
+from .native import ConvArgs, check, lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('vp3d_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback '
+                               '(got a %s tensor)' % t.device)
+
+
+def f32c(t):
+    """fp32 contiguous view/copy (layout plumbing only)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def torch_dtype(dt):
+    return {native.F16: torch.float16, native.BF16: torch.bfloat16, native.TF32: torch.float32}[dt]
+
+
+# ------------------------------------------------------------------------------------------------ K5 geometry
+def project_points(x, q=None, t=None, cam=None, pts_per_q=1, pts_per_cam=1, mode=0, want3=False, want2=False):
+    """x (..., 3) fp32 CUDA -> (out3 or None, out2 or None). See vp3d_project_points in include/vp3d_b200.h."""
+    require_cuda(x, q, t, cam)
+    x = f32c(x)
+    n_pts = x.numel() // 3
+    out3 = torch.empty_like(x) if want3 else None
+    out2 = torch.empty(x.shape[:-1] + (2,), dtype=torch.float32, device=x.device) if want2 else None
+    q = None if q is None else f32c(q)
+    t = None if t is None else f32c(t)
+    cam = None if cam is None else f32c(cam)
+    with torch.cuda.device(x.device):
+        check(lib().vp3d_project_points(_ptr(x), _ptr(out3), _ptr(out2), n_pts, _ptr(q), _ptr(t), _ptr(cam),
+                                        int(pts_per_q), int(pts_per_cam), int(mode), _stream()), 'project_points')
+    return out3, out2
+
+
+# ------------------------------------------------------------------------------------------------ K6 losses
+_ws_cache = {}
+
+
+def _loss_workspace(device):
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None:
+        ws = torch.empty(int(lib().vp3d_loss_workspace_bytes()), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def _weight_view(w, lead):
+    """w broadcast over the joint grid `lead` = pred.shape[:-1] (loss.py:27 `w * norm`), described to the kernel as
+    element strides over an (N, T, J) grid; broadcast dimensions get stride 0, nothing is materialised for rank 3."""
+    wb = torch.broadcast_to(f32c(w), lead)
+    if len(lead) == 3:
+        s = wb.stride()
+        return wb, lead[1], lead[2], s[0], s[1], s[2]
+    wb = wb.contiguous().reshape(-1)
+    return wb, 1, 1, 1, 0, 0
+
+
+class _MpjpeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, tgt, w):
+        require_cuda(pred, tgt, w)
+        assert pred.shape == tgt.shape  # loss.py:16
+        assert pred.shape[-1] == 3, 'joint coordinates must be 3-D'
+        p, g = f32c(pred), f32c(tgt)
+        n_joints = p.numel() // 3
+        if w is not None:
+            assert w.shape[0] == pred.shape[0]  # loss.py:26
+            wt, T, J, sn, st, sj = _weight_view(w, tuple(pred.shape[:-1]))
+        else:
+            wt, T, J, sn, st, sj = None, 1, 1, 0, 0, 0
+        out = torch.empty((), dtype=torch.float32, device=p.device)
+        with torch.cuda.device(p.device):
+            check(lib().vp3d_mpjpe_fwd(_ptr(p), _ptr(g), n_joints, _ptr(wt), T, J, sn, st, sj,
+                                       _ptr(_loss_workspace(p.device)), _ptr(out), _stream()), 'mpjpe_fwd')
+        ctx.save_for_backward(p, g, wt if wt is not None else torch.empty(0, device=p.device))
+        ctx.meta = (n_joints, wt is not None, T, J, sn, st, sj, pred.shape, pred.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        p, g, wt = ctx.saved_tensors
+        n_joints, has_w, T, J, sn, st, sj, shape, dtype = ctx.meta
+        grad_pred = None
+        if ctx.needs_input_grad[0]:
+            go = f32c(grad_out).reshape(1)
+            grad_pred = torch.empty_like(p)
+            with torch.cuda.device(p.device):
+                check(lib().vp3d_mpjpe_bwd(_ptr(p), _ptr(g), _ptr(go), n_joints, _ptr(wt) if has_w else None, T, J,
+                                           sn, st, sj, _ptr(grad_pred), _stream()), 'mpjpe_bwd')
+            grad_pred = grad_pred.reshape(shape).to(dtype)
+        grad_tgt = None
+        if ctx.needs_input_grad[1]:
+            grad_tgt = -grad_pred if grad_pred is not None else None
+            if grad_tgt is None:
+                go = f32c(grad_out).reshape(1)
+                gp = torch.empty_like(p)
+                with torch.cuda.device(p.device):
+                    check(lib().vp3d_mpjpe_bwd(_ptr(p), _ptr(g), _ptr(go), n_joints, _ptr(wt) if has_w else None, T,
+                                               J, sn, st, sj, _ptr(gp), _stream()), 'mpjpe_bwd')
+                grad_tgt = (-gp).reshape(shape).to(dtype)
+        return grad_pred, grad_tgt, None
+
+
+def mpjpe(pred, tgt, w=None):
+    return _MpjpeFn.apply(pred, tgt, w)
+
+
+def n_mpjpe(pred, tgt):
+    require_cuda(pred, tgt)
+    assert pred.shape == tgt.shape  # loss.py:75
+    assert pred.dim() == 4 and pred.shape[-1] == 3, 'n_mpjpe expects (N, T, J, 3) (loss.py:77 reduces dims 3 and 2)'
+    p, g = f32c(pred), f32c(tgt)
+    J = p.shape[2]
+    n_poses = p.shape[0] * p.shape[1]
+    out = torch.empty((), dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        check(lib().vp3d_n_mpjpe_fwd(_ptr(p), _ptr(g), n_poses, J, _ptr(_loss_workspace(p.device)), _ptr(out),
+                                     _stream()), 'n_mpjpe_fwd')
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ K1 plumbing
+def pack_rows(dt, src, c_pad):
+    """fp32 (rows, c) -> operand type (rows, c_pad) zero padded."""
+    src = f32c(src)
+    rows, c = src.shape
+    dst = torch.empty((rows, c_pad), dtype=torch_dtype(dt), device=src.device)
+    with torch.cuda.device(src.device):
+        check(lib().vp3d_pack_rows(dt, _ptr(src), _ptr(dst), rows, c, c_pad, _stream()), 'pack_rows')
+    return dst
+
+
+def pack_conv_weight(dt, w, rows_pad, k_pad_per_tap, transpose=False):
+    w = f32c(w.detach())
+    c_out, c_in, taps = w.shape
+    k_total = k_pad_per_tap if transpose else taps * k_pad_per_tap
+    dst = torch.empty((rows_pad, k_total), dtype=torch_dtype(dt), device=w.device)
+    with torch.cuda.device(w.device):
+        check(lib().vp3d_pack_conv_weight(dt, _ptr(w), _ptr(dst), c_out, c_in, taps, rows_pad, k_pad_per_tap,
+                                          1 if transpose else 0, _stream()), 'pack_conv_weight')
+    return dst
+
+
+def bn_fold(bn, c_pad):
+    """nn.BatchNorm1d container (eval statistics) -> (scale, shift) fp32 [c_pad]."""
+    c = bn.num_features
+    dev = bn.weight.device
+    scale = torch.empty(c_pad, dtype=torch.float32, device=dev)
+    shift = torch.empty(c_pad, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().vp3d_bn_fold(_ptr(f32c(bn.weight.detach())), _ptr(f32c(bn.bias.detach())),
+                                 _ptr(f32c(bn.running_mean)), _ptr(f32c(bn.running_var)), float(bn.eps),
+                                 _ptr(scale), _ptr(shift), c, c_pad, _stream()), 'bn_fold')
+    return scale, shift
+
+
+def conv_block(dt, a, a_view, w, taps, tap_row_step, k_per_tap, rows_out, out, out_view, block_n=256, a_row_off=0,
+               scale=None, shift=None, relu=False, res=None, res_view=None, out_f32=False, n_valid=None,
+               stat_sum=None, stat_sqsum=None):
+    """One vp3d_conv_block_fwd launch.
+    a_view   = (seqs, rows, kdim, row_stride, seq_stride)    out_view = (row_stride, seq_stride)
+    res_view = (row_stride, seq_stride, row_mul, row_off)"""
+    args = ConvArgs()
+    args.dtype, args.block_n = dt, block_n
+    args.a = a.data_ptr()
+    args.a_seqs, args.a_rows, args.a_kdim, args.a_row_stride, args.a_seq_stride = a_view
+    args.a_row_off = a_row_off
+    args.w = w.data_ptr()
+    args.n_pad, args.k_total = w.shape[0], w.shape[1]
+    args.taps, args.tap_row_step, args.k_per_tap = taps, tap_row_step, k_per_tap
+    args.rows_out = rows_out
+    args.out = out.data_ptr()
+    args.out_f32 = 1 if out_f32 else 0
+    args.out_row_stride, args.out_seq_stride = out_view
+    args.n_valid = n_valid if n_valid is not None else w.shape[0]
+    args.scale = None if scale is None else scale.data_ptr()
+    args.shift = None if shift is None else shift.data_ptr()
+    args.relu = 1 if relu else 0
+    if res is not None:
+        args.res = res.data_ptr()
+        args.res_row_stride, args.res_seq_stride, args.res_row_mul, args.res_row_off = res_view
+    args.stat_sum = None if stat_sum is None else stat_sum.data_ptr()
+    args.stat_sqsum = None if stat_sqsum is None else stat_sqsum.data_ptr()
+    with torch.cuda.device(a.device):
+        check(lib().vp3d_conv_block_fwd(C.byref(args), _stream()), 'conv_block_fwd')
+    return out

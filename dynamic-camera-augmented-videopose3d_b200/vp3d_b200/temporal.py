@@ -1,0 +1,151 @@
+"""Host-side driver of the temporal-convolution stack: turns a TemporalModel / TemporalModelOptimized1f module
+(parameters under the reference's names) into a sequence of vp3d_conv_block_fwd launches.
+
+Layout in HBM: activations are channels-last [sequence][frame][channel] in the operand type (fp16 / bf16 / fp32-as-tf32),
+channels padded to the 256-wide output tile; weights are re-packed once per parameter version into K-major
+[c_out_pad][tap][c_in_pad] operands; eval-mode BatchNorm is folded into per-channel scale/shift (fp32).
+Nothing here does arithmetic on activations: every FLOP runs in the CUDA library.
+"""
+import os
+
+import torch
+
+from . import native, ops
+
+K_ALIGN = 64     # input channels are padded to one 128-byte K block of 16-bit elements (two blocks of tf32)
+N_TILE = 256     # output-channel tile of the wide layers
+N_TILE_NARROW = 64
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def resolve_dtype(name=None):
+    name = name or os.environ.get('VP3D_DTYPE', 'fp16')
+    if name not in native.DTYPE_NAMES:
+        raise ValueError('unknown operand dtype %r (choose fp16, bf16 or tf32)' % (name,))
+    return native.DTYPE_NAMES[name]
+
+
+class LayerPlan:
+    """Geometry of one convolution of the stack (taps, dilation or stride, residual placement)."""
+    __slots__ = ('taps', 'dilation', 'stride', 'res_mul', 'res_off')
+
+    def __init__(self, taps, dilation=1, stride=1, res_mul=0, res_off=0):
+        self.taps, self.dilation, self.stride, self.res_mul, self.res_off = taps, dilation, stride, res_mul, res_off
+
+
+class PackedStack:
+    """Operand-typed copies of a module's parameters, valid for one (dtype, parameter version) pair."""
+
+    def __init__(self, model, dt):
+        self.dt = dt
+        ch = model.expand_conv.out_channels
+        self.c_in = model.expand_conv.in_channels
+        self.c_in_pad = _round_up(self.c_in, K_ALIGN)
+        self.c_pad = _round_up(ch, N_TILE)
+        self.n_out = model.shrink.out_channels
+        self.n_out_pad = _round_up(self.n_out, N_TILE_NARROW)
+        dev = model.expand_conv.weight.device
+        self.w_expand = ops.pack_conv_weight(dt, model.expand_conv.weight, self.c_pad, self.c_in_pad)
+        self.bn_expand = ops.bn_fold(model.expand_bn, self.c_pad)
+        self.w_layers = [ops.pack_conv_weight(dt, conv.weight, self.c_pad, self.c_pad) for conv in model.layers_conv]
+        self.bn_layers = [ops.bn_fold(bn, self.c_pad) for bn in model.layers_bn]
+        self.w_shrink = ops.pack_conv_weight(dt, model.shrink.weight, self.n_out_pad, self.c_pad)
+        self.shrink_scale = torch.ones(self.n_out_pad, dtype=torch.float32, device=dev)
+        self.shrink_shift = torch.zeros(self.n_out_pad, dtype=torch.float32, device=dev)
+        self.shrink_shift[:self.n_out] = model.shrink.bias.detach().float()
+
+
+def _param_versions(model):
+    return tuple((p.data_ptr(), p._version) for p in list(model.parameters()) + list(model.buffers()))
+
+
+def packed_for(model, dt):
+    key = (dt, _param_versions(model))
+    cache = model.__dict__.setdefault('_vp3d_pack_cache', {})
+    hit = cache.get('eval')
+    if hit is None or hit[0] != key:
+        hit = (key, PackedStack(model, dt))
+        cache['eval'] = hit
+    return hit[1]
+
+
+def _run_layer(dt, x, n, t_in, c_in_pad, w, plan, scale, shift, relu, res=None, res_t=0, out_f32=False, n_valid=None,
+               block_n=N_TILE):
+    """x: [n][t_in][c_in_pad] operand-typed, contiguous. Returns (y [n][t_out][cols], t_out).
+
+    View selection. A stride==width convolution reads `taps` consecutive frames per output frame, i.e. it is a plain
+    GEMM on the reshaped view [t_out][taps*c]; when t_in == taps*t_out the sequences concatenate seamlessly and the
+    whole batch is one flat row range (no per-sequence tile padding -- essential for the 1f model whose last layers
+    have 3 or 1 frames per sequence). Dilated convolutions tile per sequence; TMA zero-fills the ragged tails."""
+    taps, d, s = plan.taps, plan.dilation, plan.stride
+    t_out = (t_in - d * (taps - 1) - 1) // s + 1
+    assert t_out >= 1, 'sequence shorter than the receptive field'
+    n_pad = w.shape[0]
+    out_dtype = torch.float32 if out_f32 else ops.torch_dtype(dt)
+    cols = n_valid if out_f32 else n_pad
+    y = torch.empty((n, t_out, cols), dtype=out_dtype, device=x.device)
+    res_c = 0 if res is None else res.shape[-1]
+
+    if s > 1:
+        assert s == taps and d == 1, 'strided layers of the 1f model have stride == width'
+        g_taps, g_step, k_per_tap = 1, 0, taps * c_in_pad
+        flat = (t_in == taps * t_out) and res is None
+        seq_rows = t_out
+    else:
+        g_taps, g_step, k_per_tap = taps, d, c_in_pad
+        flat = taps == 1 and (res is None or res_t == plan.res_mul * t_out)
+        seq_rows = t_in
+    if flat:
+        a_view = (1, n * seq_rows, k_per_tap, k_per_tap, n * t_in * c_in_pad)
+        rows_out = n * t_out
+        out_view = (cols, n * t_out * cols)
+        res_view = None if res is None else (res_c, n * res_t * res_c, plan.res_mul, plan.res_off)
+    else:
+        a_view = (n, seq_rows, k_per_tap, k_per_tap, t_in * c_in_pad)
+        rows_out = t_out
+        out_view = (cols, t_out * cols)
+        res_view = None if res is None else (res_c, res_t * res_c, plan.res_mul, plan.res_off)
+    ops.conv_block(dt, x, a_view, w, g_taps, g_step, k_per_tap, rows_out, y, out_view, block_n=block_n,
+                   scale=scale, shift=shift, relu=relu, res=res, res_view=res_view, out_f32=out_f32, n_valid=n_valid)
+    return y, t_out
+
+
+def forward_eval(model, x, dt=None):
+    """Eval-mode forward of TemporalModel._forward_blocks (TemporalModel.py:126-138) or
+    TemporalModelOptimized1f._forward_blocks (:188-198): (N, T, J*F) fp32 -> (N, T', 3*J_out) fp32."""
+    ops.require_cuda(x)
+    dt = resolve_dtype(getattr(model, 'operand_dtype', None)) if dt is None else dt
+    pk = packed_for(model, dt)
+    n, t_in, c = x.shape
+    assert c == pk.c_in
+    strided = model._strided
+    fw = model.filter_widths
+
+    h = ops.pack_rows(dt, x.reshape(n * t_in, c), pk.c_in_pad).view(n, t_in, pk.c_in_pad)
+    plan = LayerPlan(fw[0], 1, fw[0] if strided else 1)
+    h, t = _run_layer(dt, h, n, t_in, pk.c_in_pad, pk.w_expand, plan, pk.bn_expand[0], pk.bn_expand[1], True)
+
+    dilation = fw[0]
+    for i in range(len(fw) - 1):
+        w3, w1 = pk.w_layers[2 * i], pk.w_layers[2 * i + 1]
+        taps = model.layers_conv[2 * i].kernel_size[0]
+        shift = model.causal_shift[i + 1]
+        if strided:
+            p3 = LayerPlan(taps, 1, taps)
+            p1 = LayerPlan(1, 1, 1, res_mul=taps, res_off=shift + taps // 2)  # x[:, :, shift + fw//2 :: fw]
+        else:
+            d = model.layers_conv[2 * i].dilation[0]
+            p3 = LayerPlan(taps, d, 1)
+            p1 = LayerPlan(1, 1, 1, res_mul=1, res_off=model.pad[i + 1] + shift)  # x[:, :, pad+shift : T-pad+shift]
+        res, res_t = h, t
+        h, t = _run_layer(dt, h, n, t, pk.c_pad, w3, p3, pk.bn_layers[2 * i][0], pk.bn_layers[2 * i][1], True)
+        h, t = _run_layer(dt, h, n, t, pk.c_pad, w1, p1, pk.bn_layers[2 * i + 1][0], pk.bn_layers[2 * i + 1][1], True,
+                          res=res, res_t=res_t)
+        dilation *= fw[i + 1]
+
+    y, t = _run_layer(dt, h, n, t, pk.c_pad, pk.w_shrink, LayerPlan(1), pk.shrink_scale, pk.shrink_shift, False,
+                      out_f32=True, n_valid=pk.n_out, block_n=N_TILE_NARROW)
+    return y

@@ -1,0 +1,113 @@
+"""K5 (projection) and K6 (losses) on the GPU against the reference golden vectors and the NumPy/torch oracle.
+2-D projections must match fp32 to 1e-5 (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from conftest import load_golden  # noqa: E402
+from common import camera as cam  # noqa: E402
+from common import loss as closs  # noqa: E402
+from common.quaternion import qinverse, qrot  # noqa: E402
+from oracle import camera as ocam  # noqa: E402
+from oracle import loss as oloss  # noqa: E402
+
+PROJ_TOL = 1e-5
+
+
+def test_rigid_transforms_against_golden():
+    z = load_golden('camera.npz')
+    X, q, t = z['X'], z['q'], z['t']
+    np.testing.assert_allclose(cam.world_to_camera(X, q, t), z['w2c'], atol=PROJ_TOL)
+    np.testing.assert_allclose(cam.camera_to_world(X, q, t), z['c2w'], atol=PROJ_TOL)
+    assert cam.world_to_camera(X, q, t).dtype == np.float32
+    Xc, qf, tf = torch.from_numpy(X).cuda(), torch.from_numpy(z['qf']).cuda(), torch.from_numpy(z['tf']).cuda()
+    qb = qf[:, None, :].expand(-1, X.shape[1], -1).contiguous()
+    np.testing.assert_allclose(qrot(qb, Xc).cpu().numpy(), z['qrot_f'], atol=PROJ_TOL)
+    np.testing.assert_allclose(cam.world_to_camera(Xc, qf, tf).cpu().numpy(), z['w2c_f'], atol=PROJ_TOL)
+    np.testing.assert_array_equal(qinverse(qf).cpu().numpy(), z['qinv_f'])
+    rt = cam.camera_to_world(cam.world_to_camera(Xc, qf, tf), qf, tf)
+    np.testing.assert_allclose(rt.cpu().numpy(), X, atol=1e-5)
+    with pytest.raises(AssertionError):
+        qrot(qb[:, :3], Xc)
+
+
+def test_projection_against_golden_including_edge_cases():
+    z = load_golden('camera.npz')
+    Xc, cams = torch.from_numpy(z['Xc']).cuda(), torch.from_numpy(z['cams']).cuda()
+    p = cam.project_to_2d(Xc, cams).cpu().numpy()
+    pl = cam.project_to_2d_linear(Xc, cams).cpu().numpy()
+    np.testing.assert_allclose(p, z['proj'], atol=PROJ_TOL, equal_nan=True)
+    np.testing.assert_allclose(pl, z['proj_linear'], atol=PROJ_TOL, equal_nan=True)
+    assert np.isnan(p[0, 0, 1]).all() and np.isfinite(p[0, 0, 0]).all()   # 0/0 -> NaN, x/0 -> clamp(+-inf)
+    with pytest.raises(AssertionError):
+        cam.project_to_2d(Xc, cams[:2])
+    with pytest.raises(AssertionError):
+        cam.project_to_2d(Xc, cams[:, :8])
+    # NumPy path through wrap(..., unsqueeze=True) as data/prepare_data_h36m.py:161 calls it
+    from common.utils import wrap
+    one = wrap(cam.project_to_2d, z['Xc'][0], z['cams'][0], unsqueeze=True)
+    np.testing.assert_allclose(one, z['proj'][0], atol=PROJ_TOL, equal_nan=True)
+
+
+@pytest.mark.parametrize('per_frame_intrinsics', [False, True])
+def test_fused_dynamic_camera_projection(per_frame_intrinsics):
+    rng = np.random.default_rng(4)
+    S, T, J = 5, 243, 17
+    X = (rng.standard_normal((S, T, J, 3)) * 0.4 + np.array([0, 0, 4.0])).astype(np.float32)
+    q = rng.standard_normal((S, T, 4)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=-1, keepdims=True)
+    q = q * 0.05 + np.array([1, 0, 0, 0], dtype=np.float32)
+    q = (q / np.linalg.norm(q, axis=-1, keepdims=True)).astype(np.float32)
+    t = (rng.standard_normal((S, T, 3)) * 0.2).astype(np.float32)
+    base = np.array([2.2900989, 2.2875624, 0.025083065, 0.028902981, -0.20709892, 0.24777518, -0.0030751503,
+                     -0.00097569887, -0.0014244716], dtype=np.float32)
+    if per_frame_intrinsics:
+        cams = (base * (1 + 0.01 * rng.standard_normal((S, T, 1)))).astype(np.float32)
+    else:
+        cams = (base * (1 + 0.01 * rng.standard_normal((S, 1)))).astype(np.float32)
+    Xc_ref = ocam.world_to_camera(X.reshape(S * T, J, 3), q.reshape(S * T, 4), t.reshape(S * T, 3))
+    if per_frame_intrinsics:
+        p_ref = ocam.project_to_2d(Xc_ref, cams.reshape(S * T, 9)).reshape(S, T, J, 2)
+    else:
+        p_ref = ocam.project_to_2d(Xc_ref.reshape(S, T, J, 3), cams)
+    x3, x2 = cam.world_to_image(*(torch.from_numpy(v).cuda() for v in (X, q, t, cams)))
+    np.testing.assert_allclose(x3.cpu().numpy().reshape(S * T, J, 3), Xc_ref, atol=PROJ_TOL)
+    np.testing.assert_allclose(x2.cpu().numpy(), p_ref, atol=PROJ_TOL)
+    # odd point counts / unaligned views take the scalar path and must agree bit for bit
+    x3b, x2b = cam.world_to_image(*(torch.from_numpy(v).cuda() for v in (X[:, :3, :], q[:, :3], t[:, :3],
+                                                                          cams[:, :3] if per_frame_intrinsics else cams)))
+    assert torch.equal(x2b, x2[:, :3]) and torch.equal(x3b, x3[:, :3])
+
+
+def test_losses_against_golden_values_and_gradients():
+    z = load_golden('loss.npz')
+    pred, tgt = torch.from_numpy(z['pred']).cuda(), torch.from_numpy(z['tgt']).cuda()
+    p = pred.clone().requires_grad_(True)
+    l = closs.mpjpe(p, tgt)
+    l.backward()
+    np.testing.assert_allclose(l.item(), z['mpjpe'], rtol=1e-6)
+    np.testing.assert_allclose(p.grad.cpu().numpy(), z['mpjpe_grad'], atol=1e-8, rtol=1e-5)
+    assert (p.grad[0, 0, 0] == 0).all()
+    for wname in ('w_n', 'w_nt1', 'w_ntj'):
+        w = torch.from_numpy(z[wname]).cuda()
+        p = pred.clone().requires_grad_(True)
+        l = closs.weighted_mpjpe(p, tgt, w)
+        l.backward()
+        np.testing.assert_allclose(l.item(), z['wmpjpe_' + wname], rtol=1e-6)
+        np.testing.assert_allclose(p.grad.cpu().numpy(), z['wmpjpe_grad_' + wname], atol=1e-8, rtol=1e-5)
+    np.testing.assert_allclose(closs.n_mpjpe(pred, tgt).item(), z['n_mpjpe'], rtol=1e-5)
+    with pytest.raises(AssertionError):
+        closs.mpjpe(pred, tgt[:, :2])
+    with pytest.raises(RuntimeError):
+        closs.mpjpe(pred.cpu(), tgt.cpu())
+
+
+def test_mpjpe_large_and_ragged_sizes_against_oracle():
+    g = torch.Generator().manual_seed(3)
+    for shape in [(1, 1, 1, 3), (7, 3, 17, 3), (1024, 1, 17, 3), (33, 243, 31, 3)]:
+        pred, tgt = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+        ref = oloss.mpjpe(pred.double(), tgt.double()).item()
+        got = closs.mpjpe(pred.cuda(), tgt.cuda()).item()
+        assert abs(got - ref) < 1e-6 * max(1.0, abs(ref)), shape

@@ -1,0 +1,149 @@
+"""The drop-in TemporalModel / TemporalModelOptimized1f (CUDA path) against the CPU oracle and the golden outputs of
+the reference. Tolerances come from BASELINE.json: <= 1e-3 relative on outputs, <= 1e-2 mm MPJPE delta (outputs are
+in metres -> 1e-5)."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from conftest import load_golden, state_from_npz  # noqa: E402
+from common.models.TemporalModel import TemporalModel, TemporalModelOptimized1f  # noqa: E402
+from oracle import loss as oloss  # noqa: E402
+from oracle import temporal_model as otm  # noqa: E402
+
+REL_TOL = 1e-3           # relative Frobenius error on outputs (north_star)
+MPJPE_TOL = 1e-5         # 1e-2 mm in metres
+
+
+def rel_err(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return ((a - b).norm() / b.norm()).item()
+
+
+def mpjpe_delta(pred, ref, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    tgt = torch.as_tensor(ref) + torch.randn(ref.shape, generator=g) * 0.05
+    return abs(oloss.mpjpe(torch.as_tensor(pred), tgt).item() - oloss.mpjpe(torch.as_tensor(ref), tgt).item())
+
+
+def build(cls, sd, j_in, j_out, fw, channels, **kw):
+    m = cls(j_in, 2, j_out, fw, dropout=0.0, channels=channels, **kw)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize('dtype', ['fp16', 'tf32'])
+def test_small_models_against_reference_golden(dtype):
+    z = load_golden('temporal_small.npz')
+    sd = state_from_npz(z, 'sd/')
+    x = torch.from_numpy(z['x']).cuda()
+    fw, ch = [3, 3, 3], 32
+    cases = [(TemporalModel, {}, x, 'y_full'), (TemporalModel, {'causal': True}, x, 'y_causal'),
+             (TemporalModelOptimized1f, {}, x[:, :27].contiguous(), 'y_1f'),
+             (TemporalModelOptimized1f, {'causal': True}, x[:, :27].contiguous(), 'y_1f_causal')]
+    for cls, kw, xin, key in cases:
+        m = build(cls, sd, 17, 17, fw, ch, **kw)
+        m.operand_dtype = dtype
+        with torch.no_grad():
+            y = m(xin)
+        assert y.shape == z[key].shape
+        assert rel_err(y.cpu(), z[key]) < REL_TOL, key
+    sdd = state_from_npz(z, 'sdd/')
+    m = build(TemporalModel, sdd, 17, 17, fw, ch, dense=True)
+    m.operand_dtype = dtype
+    with torch.no_grad():
+        assert rel_err(m(x).cpu(), z['y_dense']) < REL_TOL
+
+
+@pytest.mark.parametrize('fname', ['temporal_27f_1024.npz', 'temporal_243f_1024.npz',
+                                   'temporal_243f_1024_causal.npz', 'temporal_243f_j31.npz'])
+def test_1024_channel_models_against_reference_golden(fname):
+    z = load_golden(fname)
+    fw = [int(v) for v in z['filter_widths']]
+    j_in, j_out, causal = int(z['j_in']), int(z['j_out']), bool(z['causal'])
+    sd = otm.init_state(j_in, 2, j_out, fw, channels=1024, seed=int(z['seed']))
+    x = torch.from_numpy(z['x']).cuda()
+    m = build(TemporalModel, sd, j_in, j_out, fw, 1024, causal=causal)
+    m1 = build(TemporalModelOptimized1f, sd, j_in, j_out, fw, 1024, causal=causal)
+    with torch.no_grad():
+        y = m(x).cpu()
+        y1 = m1(x[:, :m.receptive_field()].contiguous()).cpu()
+    assert y.shape == z['y'].shape and y1.shape == z['y_1f'].shape
+    assert rel_err(y, z['y']) < REL_TOL
+    assert rel_err(y1, z['y_1f']) < REL_TOL
+    assert mpjpe_delta(y, z['y']) < MPJPE_TOL
+    # 1f model == full model on an RF-long window (TemporalModel.py:147-149); both run the same rounded operands
+    assert rel_err(y1, y[:, :1]) < REL_TOL
+
+
+def test_batched_long_sequences_against_oracle():
+    """Config-2 shape at oracle-friendly size: batch of sequences, ragged tile tails, window == full-sequence."""
+    fw = [3, 3, 3, 3, 3]
+    sd = otm.init_state(17, 2, 17, fw, channels=1024, seed=21)
+    g = torch.Generator().manual_seed(22)
+    x = torch.rand(3, 243 + 300, 17, 2, generator=g) * 2 - 1
+    with torch.no_grad():
+        ref = otm.forward(sd, x, fw)
+    m = build(TemporalModel, sd, 17, 17, fw, 1024)
+    with torch.no_grad():
+        y = m(x.cuda())
+        yw = m(x[:, 100:100 + 243].contiguous().cuda())
+    assert rel_err(y.cpu(), ref) < REL_TOL
+    assert mpjpe_delta(y.cpu(), ref) < MPJPE_TOL
+    assert rel_err(yw.cpu(), ref[:, 100:101]) < REL_TOL
+    # bf16 is the documented lower-precision speed path: looser bound, still close
+    m.operand_dtype = 'bf16'
+    with torch.no_grad():
+        assert rel_err(m(x.cuda()).cpu(), ref) < 1e-2
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 at full size (64 x 4338 frames): size-independent properties instead of the CPU oracle.
+    (i) every sequence of a batch equals the same sequence run alone; (ii) a time-shifted input gives the
+    time-shifted output (translation equivariance of valid convolutions); (iii) outputs are finite."""
+    fw = [3, 3, 3, 3, 3]
+    sd = otm.init_state(17, 2, 17, fw, channels=1024, seed=31)
+    m = build(TemporalModel, sd, 17, 17, fw, 1024)
+    g = torch.Generator().manual_seed(32)
+    x = (torch.rand(64, 4096 + 242, 17, 2, generator=g) * 2 - 1).cuda()
+    with torch.no_grad():
+        y = m(x)
+        assert y.shape == (64, 4096, 17, 3)
+        assert torch.isfinite(y).all()
+        y7 = m(x[7:8].contiguous())
+        assert torch.equal(y7, y[7:8]), 'batched and single-sequence results must be bit-identical'
+        ys = m(x[:4, 128:].contiguous())
+        assert torch.equal(ys, y[:4, 128:]), 'shift by one M tile must reproduce the same values'
+        ys = m(x[:2, 5:].contiguous())
+        assert rel_err(ys.cpu(), y[:2, 5:].cpu()) < 1e-6 or torch.equal(ys, y[:2, 5:])
+
+
+def test_state_dict_roundtrip_and_api():
+    fw = [3, 3, 3]
+    m = TemporalModel(17, 2, 17, fw, channels=64)
+    sd = otm.init_state(17, 2, 17, fw, channels=64, seed=1)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    for k, v in m.state_dict().items():
+        assert v.shape == sd[k].shape and v.dtype == sd[k].dtype, k
+    m.load_state_dict(sd)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v.cpu(), sd[k])
+    with pytest.raises(RuntimeError):
+        m.eval()(torch.zeros(1, 27, 17, 2))      # CPU tensor: no fallback
+    with pytest.raises(AssertionError):
+        m.cuda().eval()(torch.zeros(1, 27, 16, 2, device='cuda'))
+
+
+def test_repack_after_parameter_update():
+    fw = [3, 3, 3]
+    sd = otm.init_state(17, 2, 17, fw, channels=64, seed=2)
+    m = build(TemporalModel, sd, 17, 17, fw, 64)
+    x = torch.rand(1, 40, 17, 2, device='cuda')
+    with torch.no_grad():
+        y0 = m(x).clone()
+        m.shrink.bias.add_(1.0)
+        y1 = m(x)
+    assert torch.allclose(y1, y0 + 1.0, atol=1e-6)
