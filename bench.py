@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: 243-frame TemporalModel batched inference (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one eval forward of TemporalModel(17, 2, 17, [3,3,3,3,3], channels=1024) over a batch of 64 synthetic
+sequences of 4096+242 frames (262,144 output frames) per GPU. Prints ONE JSON line (rank 0):
+  value      frames/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through the public module API with HOST (pinned) inputs and outputs inside the timed region
+  roofline   tensor-core roofline of the dominant kernel (conv_gemm_kernel), measured live with CUDA events
+  cpu_baseline  the CPU oracle (a torch-CPU port of the reference stack) timed on this box's host cores
+With --impl reference the CPU port itself is the thing measured (the reference is Python and cannot travel to the GPU
+box; oracle/ is its restatement, pinned to the reference by tests/golden).
+Multi-GPU: sequences are sharded over ranks, no collective on the data path (weak scaling: 64 sequences per GPU).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, 'dynamic-camera-augmented-videopose3d_b200')
+for _p in (PKG, ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+FLOP_PER_FRAME = 33867776          # useful MACs x 2 per output frame, 243-frame model, J = 17
+FW = [3, 3, 3, 3, 3]
+SEQS_PER_GPU = 64
+OUT_FRAMES = 4096
+RF = 243
+METRIC = '243f TemporalModel inference throughput'
+UNIT = 'frames/s'
+
+
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p['hbm_gbs'], burst=p['bf16_tflops'], sustained=p.get('bf16_tflops_sustained', p['bf16_tflops']),
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm_gbs=6650.0, burst=1590.0, sustained=1400.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for line in self.lines:
+            f = [v.strip() for v in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        sm_sorted = sorted(sm)
+        return {'sm_mhz': sm_sorted[len(sm_sorted) // 2], 'sm_max_mhz': max(smax), 'power_w_max': max(power),
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def make_inputs(rank, seqs, t_in):
+    g = torch.Generator().manual_seed(1234 + rank)
+    return torch.rand(seqs, t_in, 17, 2, generator=g) * 2 - 1      # normalised screen coordinates in [-1, 1]
+
+
+def oracle_state():
+    from oracle import temporal_model as otm
+    return otm.init_state(17, 2, 17, FW, channels=1024, seed=1234)
+
+
+def cpu_port_frames_per_s(seqs=4, out_frames=4096, repeats=3):
+    """The CPU oracle (torch-CPU port of the reference eval forward) on all host threads; bounded sample."""
+    from oracle import temporal_model as otm
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = oracle_state()
+    x = make_inputs(0, seqs, out_frames + RF - 1)
+    with torch.no_grad():
+        otm.forward(sd, x, FW)
+        times = []
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            otm.forward(sd, x, FW)
+            times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return seqs * out_frames / med, cores, '%d seq x %d output frames, median of %d, torch %s CPU' % (
+        seqs, out_frames, repeats, torch.__version__)
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    steps, warm = max(args.steps, 1), max(args.warmup, 0)
+    from oracle import temporal_model as otm
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = oracle_state()
+    seqs, out_frames = 1, 2048
+    x = make_inputs(0, seqs, out_frames + RF - 1)
+    with torch.no_grad():
+        for _ in range(warm):
+            otm.forward(sd, x, FW)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            otm.forward(sd, x, FW)
+        dt = time.perf_counter() - t0
+    value = steps * seqs * out_frames / dt
+    sample = '%d seq x %d output frames per step (bounded sample of the 64 x 4096 workload)' % (seqs, out_frames)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps,
+            'warmup': warm, 'ms_per_step': dt / steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'TemporalModel 3,3,3,3,3 (243f) eval, J=17, 1024 ch; CPU port of the reference '
+                                   '(oracle/temporal_model.py, torch CPU conv1d/batch_norm), ' + sample},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--dtype', default=os.environ.get('VP3D_DTYPE', 'fp16'), choices=['fp16', 'bf16', 'tf32'])
+    ap.add_argument('--seqs', type=int, default=SEQS_PER_GPU)
+    ap.add_argument('--frames', type=int, default=OUT_FRAMES)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+
+    if args.impl == 'reference':
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from common.models.TemporalModel import TemporalModel
+    from vp3d_b200 import native
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    warm = max(args.warmup, 3)
+    steps = max(args.steps, 1)
+    seqs, out_frames = args.seqs, args.frames
+    t_in = out_frames + RF - 1
+
+    model = TemporalModel(17, 2, 17, FW, dropout=0.25, channels=1024)
+    model.load_state_dict(oracle_state())      # same random-init weights as the CPU arm
+    model = model.to(dev).eval()
+    model.operand_dtype = args.dtype
+
+    x_host = make_inputs(rank, seqs, t_in).pin_memory()
+    x_dev = x_host.to(dev, non_blocking=True)
+    y_host = torch.empty(seqs, out_frames, 17, 3).pin_memory()
+    torch.cuda.synchronize()
+
+    # count our launches per step by instrumenting the ctypes entry points (this is the claim `gpu_launches` makes)
+    lib = native.lib()
+    launches = {'n': 0}
+    names = ('vp3d_conv_block_fwd', 'vp3d_pack_rows')
+    orig = {n: getattr(lib, n) for n in names}
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        with torch.no_grad():
+            return model(x_dev)
+
+    def step_e2e():
+        with torch.no_grad():
+            xd = x_host.to(dev, non_blocking=True)
+            y = model(xd)
+            y_host.copy_(y, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller holds the result on the host
+        return y_host
+
+    for _ in range(warm):
+        step_resident()
+    barrier()
+
+    # ---- value: inputs resident, K steps between two events ------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        step_resident()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- launch count + per-launch timing of the dominant kernel (separate, instrumented pass) ---------------
+    conv_ms = []
+
+    def wrap_conv(*a):
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        rc = orig['vp3d_conv_block_fwd'](*a)
+        s1.record()
+        conv_ms.append((s0, s1))
+        launches['n'] += 1
+        return rc
+
+    def wrap_pack(*a):
+        launches['n'] += 1
+        return orig['vp3d_pack_rows'](*a)
+
+    lib.vp3d_conv_block_fwd, lib.vp3d_pack_rows = wrap_conv, wrap_pack
+    try:
+        inst_steps = min(steps, 3)
+        for _ in range(inst_steps):
+            step_resident()
+        torch.cuda.synchronize()
+    finally:
+        lib.vp3d_conv_block_fwd, lib.vp3d_pack_rows = orig['vp3d_conv_block_fwd'], orig['vp3d_pack_rows']
+    launches_per_step = launches['n'] // inst_steps
+    conv_launches_per_step = len(conv_ms) // inst_steps
+    conv_ms_per_step = sum(a.elapsed_time(b) for a, b in conv_ms) / inst_steps
+
+    # ---- e2e: host buffers in, host buffers out, copies inside the timed region --------------------------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(steps):
+        step_e2e()
+    e3.record()
+    barrier()
+    ms_e2e = max(e2.elapsed_time(e3), 0.0)
+    del t0
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e, conv_ms_per_step], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e, conv_ms_per_step = [float(v) for v in t.tolist()]
+
+    frames_per_step_gpu = seqs * out_frames
+    total_frames = frames_per_step_gpu * world * steps
+    value = total_frames / (ms * 1e-3)
+    e2e_value = total_frames / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        peaks = load_peaks()
+        achieved = FLOP_PER_FRAME * frames_per_step_gpu / (conv_ms_per_step * 1e-3) / 1e12
+        peak = peaks['sustained']
+        if args.dtype == 'tf32':
+            peak = peak / 2
+        roofline = {'bound': 'tensor', 'kernel': 'conv_gemm_kernel (tcgen05 implicit GEMM)', 'achieved': achieved,
+                    'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+                    'frac_of_burst_peak': achieved / (peaks['burst'] / (2 if args.dtype == 'tf32' else 1)),
+                    'peak_source': peaks['source'] + ', sustained dense bf16 (x0.5 for tf32)', 'traffic': None,
+                    'launches_per_step': conv_launches_per_step, 'avg_launch_ms': conv_ms_per_step / conv_launches_per_step,
+                    'algorithmic_flop_per_frame': FLOP_PER_FRAME,
+                    'kernel_share_of_step': conv_ms_per_step / (ms / steps)}
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': warm,
+                'ms_per_step': ms / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': args.dtype, 'data': 'synthetic',
+                'config': {'workload': 'TemporalModel 3,3,3,3,3 (243f RF) eval forward, J=17, 1024 ch, %d sequences x '
+                                       '%d output frames per GPU (BASELINE configs[1])' % (seqs, out_frames),
+                           'sharding': 'sequences over ranks, no collective', 'l2': 'activations (%.0f MB per layer) '
+                           'exceed the 126 MB L2, no flush needed' % (seqs * t_in * 1024 * 2 / 1e6),
+                           'weights': 'random init (seed 1234), BN statistics randomised'},
+                'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': x_host.numel() * 4,
+                        'd2h_bytes_per_step': y_host.numel() * 4, 'ms_per_step': ms_e2e / steps},
+                'gpu_launches': launches_per_step * steps,
+                'roofline': roofline, 'clocks': clocks}
+        if not args.no_cpu_baseline:
+            v, cores, sample = cpu_port_frames_per_s()
+            line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -210,6 +210,7 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
   p.out_row_stride = a->out_row_stride;
   p.out_f32 = a->out_f32;
   p.n_valid = (int)(a->out_f32 ? a->n_valid : a->n_pad);
+  p.out_round_tf32 = a->out_round_tf32;
   p.stat_sum = a->stat_sum;
   p.stat_sqsum = a->stat_sqsum;
 

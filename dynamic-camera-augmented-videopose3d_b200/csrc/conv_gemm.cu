@@ -69,6 +69,13 @@ __device__ __forceinline__ float2 unpack2(uint32_t u, std::integral_constant<int
   return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
 }
 
+// round-to-nearest onto the TF32 grid, so that a following kind::tf32 MMA (which truncates) consumes it exactly
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
 struct TileCoord {
   int seq, t0, n0;
 };
@@ -278,6 +285,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           if (p.out_f32) {
+            if (p.out_round_tf32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = round_tf32(f[j]);
+            }
             float* o = static_cast<float*>(p.out) + out_off + col0;
             if (col0 + 32 <= p.n_valid && (p.out_row_stride & 3) == 0) {
 #pragma unroll

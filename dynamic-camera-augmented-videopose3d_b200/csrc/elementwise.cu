@@ -22,7 +22,9 @@ __device__ __forceinline__ void store_elem<VP3D_BF16>(void* dst, long long i, fl
 }
 template <>
 __device__ __forceinline__ void store_elem<VP3D_TF32>(void* dst, long long i, float v) {
-  static_cast<float*>(dst)[i] = v;
+  uint32_t u;  // fp32 container holding a TF32-representable value (round to nearest; the MMA would truncate)
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  static_cast<float*>(dst)[i] = __uint_as_float(u);
 }
 
 template <int DT>

@@ -35,6 +35,7 @@ struct ConvGemmParams {
   long long out_row_stride;
   int out_f32;          // 1: fp32 output (shrink layer / tf32 activations), 0: activation element type
   int n_valid;          // real output channels (<= n_pad); only consulted on the fp32 path
+  int out_round_tf32;   // fp32 outputs are rounded (RN) to TF32 precision for a following TF32 layer
 
   float* stat_sum;      // optional per-channel sum / sum-of-squares of the raw accumulator (train-mode BN)
   float* stat_sqsum;

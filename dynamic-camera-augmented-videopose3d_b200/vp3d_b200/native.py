@@ -24,7 +24,7 @@ class ConvArgs(C.Structure):
         ('w', C.c_void_p), ('n_pad', C.c_longlong), ('k_total', C.c_longlong), ('taps', C.c_int),
         ('tap_row_step', C.c_int), ('k_per_tap', C.c_longlong),
         ('rows_out', C.c_longlong), ('out', C.c_void_p), ('out_f32', C.c_int), ('out_row_stride', C.c_longlong),
-        ('out_seq_stride', C.c_longlong), ('n_valid', C.c_longlong),
+        ('out_seq_stride', C.c_longlong), ('n_valid', C.c_longlong), ('out_round_tf32', C.c_int),
         ('scale', C.c_void_p), ('shift', C.c_void_p), ('relu', C.c_int),
         ('res', C.c_void_p), ('res_row_stride', C.c_longlong), ('res_seq_stride', C.c_longlong),
         ('res_row_mul', C.c_int), ('res_row_off', C.c_int),

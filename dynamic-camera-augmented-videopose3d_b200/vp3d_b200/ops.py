@@ -179,7 +179,7 @@ def bn_fold(bn, c_pad):
 
 def conv_block(dt, a, a_view, w, taps, tap_row_step, k_per_tap, rows_out, out, out_view, block_n=256, a_row_off=0,
                scale=None, shift=None, relu=False, res=None, res_view=None, out_f32=False, n_valid=None,
-               stat_sum=None, stat_sqsum=None):
+               stat_sum=None, stat_sqsum=None, out_round_tf32=False):
     """One vp3d_conv_block_fwd launch.
     a_view   = (seqs, rows, kdim, row_stride, seq_stride)    out_view = (row_stride, seq_stride)
     res_view = (row_stride, seq_stride, row_mul, row_off)"""
@@ -196,6 +196,7 @@ def conv_block(dt, a, a_view, w, taps, tap_row_step, k_per_tap, rows_out, out, o
     args.out_f32 = 1 if out_f32 else 0
     args.out_row_stride, args.out_seq_stride = out_view
     args.n_valid = n_valid if n_valid is not None else w.shape[0]
+    args.out_round_tf32 = 1 if out_round_tf32 else 0
     args.scale = None if scale is None else scale.data_ptr()
     args.shift = None if shift is None else shift.data_ptr()
     args.relu = 1 if relu else 0

@@ -84,8 +84,10 @@ def _run_layer(dt, x, n, t_in, c_in_pad, w, plan, scale, shift, relu, res=None, 
     t_out = (t_in - d * (taps - 1) - 1) // s + 1
     assert t_out >= 1, 'sequence shorter than the receptive field'
     n_pad = w.shape[0]
+    final = out_f32                      # only the shrink layer asks for fp32 explicitly
+    out_f32 = out_f32 or dt == native.TF32
     out_dtype = torch.float32 if out_f32 else ops.torch_dtype(dt)
-    cols = n_valid if out_f32 else n_pad
+    cols = n_valid if n_valid is not None else n_pad
     y = torch.empty((n, t_out, cols), dtype=out_dtype, device=x.device)
     res_c = 0 if res is None else res.shape[-1]
 
@@ -109,7 +111,8 @@ def _run_layer(dt, x, n, t_in, c_in_pad, w, plan, scale, shift, relu, res=None, 
         out_view = (cols, t_out * cols)
         res_view = None if res is None else (res_c, res_t * res_c, plan.res_mul, plan.res_off)
     ops.conv_block(dt, x, a_view, w, g_taps, g_step, k_per_tap, rows_out, y, out_view, block_n=block_n,
-                   scale=scale, shift=shift, relu=relu, res=res, res_view=res_view, out_f32=out_f32, n_valid=n_valid)
+                   scale=scale, shift=shift, relu=relu, res=res, res_view=res_view, out_f32=out_f32, n_valid=cols,
+                   out_round_tf32=(dt == native.TF32 and not final))
     return y, t_out
 
 
@@ -128,7 +131,6 @@ def forward_eval(model, x, dt=None):
     plan = LayerPlan(fw[0], 1, fw[0] if strided else 1)
     h, t = _run_layer(dt, h, n, t_in, pk.c_in_pad, pk.w_expand, plan, pk.bn_expand[0], pk.bn_expand[1], True)
 
-    dilation = fw[0]
     for i in range(len(fw) - 1):
         w3, w1 = pk.w_layers[2 * i], pk.w_layers[2 * i + 1]
         taps = model.layers_conv[2 * i].kernel_size[0]
@@ -144,7 +146,6 @@ def forward_eval(model, x, dt=None):
         h, t = _run_layer(dt, h, n, t, pk.c_pad, w3, p3, pk.bn_layers[2 * i][0], pk.bn_layers[2 * i][1], True)
         h, t = _run_layer(dt, h, n, t, pk.c_pad, w1, p1, pk.bn_layers[2 * i + 1][0], pk.bn_layers[2 * i + 1][1], True,
                           res=res, res_t=res_t)
-        dilation *= fw[i + 1]
 
     y, t = _run_layer(dt, h, n, t, pk.c_pad, pk.w_shrink, LayerPlan(1), pk.shrink_scale, pk.shrink_shift, False,
                       out_f32=True, n_valid=pk.n_out, block_n=N_TILE_NARROW)

@@ -70,6 +70,7 @@ typedef struct vp3d_conv_args {
   long long out_row_stride;
   long long out_seq_stride;
   long long n_valid;
+  int out_round_tf32;      /* fp32 output rounded (nearest) to TF32 so a following TF32 layer reads exact operands */
 
   const float* scale;      /* [n_pad] or NULL */
   const float* shift;      /* [n_pad]; required when scale is given */
