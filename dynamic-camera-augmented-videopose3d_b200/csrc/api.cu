@@ -168,6 +168,9 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
       return fail(VP3D_ERR_INVALID, "residual must be 16-byte aligned with 16-byte strides");
   }
   if (a->out_f32 && (a->n_valid <= 0 || a->n_valid > a->n_pad)) return fail(VP3D_ERR_INVALID, "bad n_valid");
+  if (a->res_cols < 0 || a->res_col_off < 0 || a->res_cols % 32 != 0 || a->res_col_off % 32 != 0 ||
+      a->res_col_off + a->res_cols > a->n_pad)
+    return fail(VP3D_ERR_INVALID, "residual column window must be 32-aligned and inside n_pad");
 
   DeviceInfo* dev = nullptr;
   if (int rc = device_info(&dev)) return rc;
@@ -205,6 +208,9 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
   p.res_row_stride = a->res_row_stride;
   p.res_row_mul = a->res_row_mul;
   p.res_row_off = a->res_row_off;
+  p.res_rows = a->res_rows;
+  p.res_col_off = (int)a->res_col_off;
+  p.res_cols = (int)a->res_cols;
   p.out = a->out;
   p.out_seq_stride = a->out_seq_stride;
   p.out_row_stride = a->out_row_stride;
@@ -216,7 +222,9 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
 
   const long long total_tiles = (long long)p.a_seqs * p.m_tiles_per_seq * p.n_tiles;
   if (total_tiles > 0x7fffffffLL) return fail(VP3D_ERR_INVALID, "too many tiles");
-  const int grid = (int)(total_tiles < dev->sm_count ? total_tiles : dev->sm_count);
+  int grid = (int)(total_tiles < dev->sm_count ? total_tiles : dev->sm_count);
+  // a grid that is a multiple of n_tiles keeps every CTA on one column tile (weights and BN statistics stay put)
+  if (grid > p.n_tiles && grid % p.n_tiles != 0) grid -= grid % p.n_tiles;
   cudaError_t e = vp3d::launch_conv_gemm(a->dtype, a->block_n, tmA, tmB, p, grid, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "conv_gemm launch");
   return VP3D_OK;
@@ -236,9 +244,12 @@ int vp3d_pack_conv_weight(int dtype, const float* w, void* dst, int c_out, int c
                           int k_pad_per_tap, int transpose, void* stream) {
   if (w == nullptr || dst == nullptr || c_out <= 0 || c_in <= 0 || taps <= 0)
     return fail(VP3D_ERR_INVALID, "pack_conv_weight args");
-  if (!transpose && (rows_pad < c_out || k_pad_per_tap < c_in)) return fail(VP3D_ERR_INVALID, "pack_conv_weight padding");
-  if (transpose && (rows_pad < taps * c_in || k_pad_per_tap < c_out))
-    return fail(VP3D_ERR_INVALID, "pack_conv_weight (transposed) padding");
+  if (transpose < 0 || transpose > 2) return fail(VP3D_ERR_INVALID, "pack_conv_weight transpose must be 0, 1 or 2");
+  if (transpose == 0 && (rows_pad < c_out || k_pad_per_tap < c_in)) return fail(VP3D_ERR_INVALID, "pack_conv_weight padding");
+  if (transpose == 1 && (rows_pad % taps != 0 || rows_pad / taps < c_in || k_pad_per_tap < c_out))
+    return fail(VP3D_ERR_INVALID, "pack_conv_weight (transpose 1) padding");
+  if (transpose == 2 && (rows_pad < c_in || k_pad_per_tap < c_out))
+    return fail(VP3D_ERR_INVALID, "pack_conv_weight (transpose 2) padding");
   DeviceInfo* dev = nullptr;
   if (int rc = device_info(&dev)) return rc;
   cudaError_t e = vp3d::launch_pack_weight(dtype, w, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap, transpose,
@@ -323,6 +334,175 @@ int vp3d_n_mpjpe_fwd(const float* pred, const float* target, long long n_poses, 
   cudaError_t e = vp3d::launch_n_mpjpe_fwd(pred, target, n_poses, J, static_cast<double*>(workspace), out, dev->sm_count,
                                            static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "n_mpjpe_fwd launch");
+  return VP3D_OK;
+}
+
+int vp3d_wgrad(const vp3d_wgrad_args* a, void* stream) {
+  if (a == nullptr) return fail(VP3D_ERR_INVALID, "args is NULL");
+  if (a->dtype != VP3D_F16 && a->dtype != VP3D_BF16) return fail(VP3D_ERR_INVALID, "wgrad: dtype must be F16 or BF16");
+  if (a->block_n != 256 && a->block_n != 64) return fail(VP3D_ERR_INVALID, "wgrad: block_n must be 256 or 64");
+  if (!a->dz || !a->a || !a->dw_packed) return fail(VP3D_ERR_INVALID, "wgrad: null dz / a / dw_packed");
+  if (a->dz_seqs <= 0 || a->dz_rows <= 0 || a->a_rows <= 0 || a->taps < 1) return fail(VP3D_ERR_INVALID, "wgrad: empty problem");
+  if (a->co_pad <= 0 || a->co_pad % 128 != 0) return fail(VP3D_ERR_INVALID, "wgrad: co_pad must be a multiple of 128");
+  if (a->ci_pad <= 0 || a->ci_pad % a->block_n != 0) return fail(VP3D_ERR_INVALID, "wgrad: ci_pad must be a multiple of block_n");
+  if ((reinterpret_cast<uintptr_t>(a->dz) & 15) || (reinterpret_cast<uintptr_t>(a->a) & 15) ||
+      (reinterpret_cast<uintptr_t>(a->dw_packed) & 15))
+    return fail(VP3D_ERR_INVALID, "wgrad: pointers must be 16-byte aligned");
+  if ((a->dz_row_stride * 2) % 16 || (a->dz_seq_stride * 2) % 16 || (a->a_row_stride * 2) % 16 || (a->a_seq_stride * 2) % 16)
+    return fail(VP3D_ERR_INVALID, "wgrad: strides must be multiples of 16 bytes");
+  if (a->a_cols < a->ci_pad + (long long)(a->taps - 1) * a->b_tap_col_step)
+    return fail(VP3D_ERR_INVALID, "wgrad: a_cols too small for taps * column step");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)a->co_pad, (cuuint64_t)a->dz_rows, (cuuint64_t)a->dz_seqs};
+    cuuint64_t strides[2] = {(cuuint64_t)(a->dz_row_stride * 2), (cuuint64_t)(a->dz_seq_stride * 2)};
+    if (a->dz_seqs == 1) strides[1] = (cuuint64_t)(a->dz_rows * a->dz_row_stride * 2);
+    cuuint32_t box[3] = {64, 64, 1};
+    if (int rc = encode_map(&tmA, a->dtype, 3, a->dz, dims, strides, box, "wgrad dz")) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)a->a_cols, (cuuint64_t)a->a_rows, (cuuint64_t)a->dz_seqs};
+    cuuint64_t strides[2] = {(cuuint64_t)(a->a_row_stride * 2), (cuuint64_t)(a->a_seq_stride * 2)};
+    if (a->dz_seqs == 1) strides[1] = (cuuint64_t)(a->a_rows * a->a_row_stride * 2);
+    cuuint32_t box[3] = {64, 64, 1};
+    if (int rc = encode_map(&tmB, a->dtype, 3, a->a, dims, strides, box, "wgrad a")) return rc;
+  }
+  vp3d::WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.co_tiles = (int)(a->co_pad / 128);
+  p.ci_tiles = (int)(a->ci_pad / a->block_n);
+  p.num_tiles = a->taps * p.co_tiles * p.ci_tiles;
+  p.seqs = (int)a->dz_seqs;
+  p.kb_per_seq = (int)((a->dz_rows + 63) / 64);
+  p.b_row_off = (int)a->b_row_off;
+  p.b_tap_row_step = a->b_tap_row_step;
+  p.b_tap_col_step = (int)a->b_tap_col_step;
+  p.out = a->dw_packed;
+  p.out_tap_stride = a->co_pad * a->ci_pad;
+  p.out_row_stride = a->ci_pad;
+  const long long units = (long long)p.num_tiles * p.seqs * p.kb_per_seq;
+  const int grid = (int)(units < dev->sm_count ? units : dev->sm_count);
+  cudaError_t e = vp3d::launch_wgrad(a->dtype, a->block_n, tmA, tmB, p, grid, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "wgrad launch");
+  return VP3D_OK;
+}
+
+int vp3d_wgrad_finish(const float* dw_packed, float* dw, int c_out, int c_in, int taps, int co_pad, int ci_pad,
+                      const float* gscale_buf, void* stream) {
+  if (!dw_packed || !dw || c_out <= 0 || c_in <= 0 || taps <= 0 || co_pad < c_out || ci_pad < c_in)
+    return fail(VP3D_ERR_INVALID, "wgrad_finish args");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_wgrad_finish(dw_packed, dw, c_out, c_in, taps, co_pad, ci_pad, gscale_buf, dev->sm_count,
+                                            static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "wgrad_finish launch");
+  return VP3D_OK;
+}
+
+int vp3d_bn_finalize(const double* stat_sum, const double* stat_sqsum, long long count, const float* gamma,
+                     const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                     long long* num_batches_tracked, float* scale, float* shift, float* mean, float* invstd, int c,
+                     int c_pad, void* stream) {
+  if (!stat_sum || !stat_sqsum || !gamma || !beta || !scale || !shift || !mean || !invstd || c <= 0 || c_pad < c)
+    return fail(VP3D_ERR_INVALID, "bn_finalize args");
+  if ((running_mean == nullptr) != (running_var == nullptr)) return fail(VP3D_ERR_INVALID, "bn_finalize running stats");
+  if (count <= 1)
+    return fail(VP3D_ERR_INVALID, "Expected more than 1 value per channel when training (got %lld)", count);
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_bn_finalize(stat_sum, stat_sqsum, count, gamma, beta, eps, momentum, running_mean,
+                                           running_var, num_batches_tracked, scale, shift, mean, invstd, c, c_pad,
+                                           static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "bn_finalize launch");
+  return VP3D_OK;
+}
+
+namespace {
+int check_ew(int dtype, int c_pad, const char* what) {
+  if (dtype != VP3D_F16 && dtype != VP3D_BF16) return fail(VP3D_ERR_INVALID, "%s: dtype must be F16 or BF16", what);
+  if (c_pad <= 0 || c_pad % 8 != 0) return fail(VP3D_ERR_INVALID, "%s: c_pad must be a positive multiple of 8", what);
+  return VP3D_OK;
+}
+vp3d::DropoutParams drop_of(const vp3d_dropout* d) {
+  vp3d::DropoutParams dp;
+  dp.p = d ? d->p : 0.f;
+  dp.seed = d ? d->seed : 0ull;
+  dp.stream = d ? d->stream : 0ull;
+  return dp;
+}
+}  // namespace
+
+int vp3d_bn_act_fwd(int dtype, const void* z, const float* scale, const float* shift, const void* res,
+                    long long seqs, long long rows_per_seq, long long res_seq_rows, int res_row_mul, int res_row_off,
+                    int c_pad, const vp3d_dropout* drop, void* a, void* stream) {
+  if (int rc = check_ew(dtype, c_pad, "bn_act_fwd")) return rc;
+  if (!z || !scale || !shift || !a || seqs <= 0 || rows_per_seq <= 0) return fail(VP3D_ERR_INVALID, "bn_act_fwd args");
+  if (drop && (drop->p < 0.f || drop->p >= 1.f)) return fail(VP3D_ERR_INVALID, "dropout p must be in [0, 1)");
+  if (res != nullptr &&
+      (res_row_off < 0 || (rows_per_seq - 1) * (long long)res_row_mul + res_row_off >= res_seq_rows))
+    return fail(VP3D_ERR_INVALID, "bn_act_fwd: residual rows out of range");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_bn_act_fwd(dtype, z, scale, shift, res, seqs, rows_per_seq, res_seq_rows, res_row_mul,
+                                          res_row_off, c_pad, drop_of(drop), a, dev->sm_count,
+                                          static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "bn_act_fwd launch");
+  return VP3D_OK;
+}
+
+int vp3d_bn_act_bwd_reduce(int dtype, const void* g, const void* z, const float* scale, const float* shift,
+                           const float* mean, const float* invstd, long long rows, int c_pad,
+                           const vp3d_dropout* drop, double* sum_dy, double* sum_dy_xhat, void* stream) {
+  if (int rc = check_ew(dtype, c_pad, "bn_act_bwd_reduce")) return rc;
+  if (!g || !z || !scale || !shift || !mean || !invstd || !sum_dy || !sum_dy_xhat || rows <= 0)
+    return fail(VP3D_ERR_INVALID, "bn_act_bwd_reduce args");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_bn_act_bwd_reduce(dtype, g, z, scale, shift, mean, invstd, rows, c_pad, drop_of(drop),
+                                                 sum_dy, sum_dy_xhat, dev->sm_count, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "bn_act_bwd_reduce launch");
+  return VP3D_OK;
+}
+
+int vp3d_bn_act_bwd_apply(int dtype, const void* g, const void* z, const float* scale, const float* shift,
+                          const float* mean, const float* invstd, long long rows, int c, int c_pad,
+                          const vp3d_dropout* drop, const double* sum_dy, const double* sum_dy_xhat,
+                          const float* gscale_buf, void* dz, float* d_gamma, float* d_beta, void* stream) {
+  if (int rc = check_ew(dtype, c_pad, "bn_act_bwd_apply")) return rc;
+  if (!g || !z || !scale || !shift || !mean || !invstd || !sum_dy || !sum_dy_xhat || !dz || rows <= 0 || c <= 0 ||
+      c > c_pad)
+    return fail(VP3D_ERR_INVALID, "bn_act_bwd_apply args");
+  if ((d_gamma == nullptr) != (d_beta == nullptr)) return fail(VP3D_ERR_INVALID, "bn_act_bwd_apply d_gamma / d_beta");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_bn_act_bwd_apply(dtype, g, z, scale, shift, mean, invstd, rows, c, c_pad, drop_of(drop),
+                                                sum_dy, sum_dy_xhat, gscale_buf, dz, d_gamma, d_beta, dev->sm_count,
+                                                static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "bn_act_bwd_apply launch");
+  return VP3D_OK;
+}
+
+int vp3d_grad_scale(const float* dy, long long n, float* gscale_buf, void* stream) {
+  if (!dy || !gscale_buf || n <= 0) return fail(VP3D_ERR_INVALID, "grad_scale args");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_grad_scale(dy, n, gscale_buf, dev->sm_count, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "grad_scale launch");
+  return VP3D_OK;
+}
+
+int vp3d_grad_pack_rows(int dtype, const float* src, void* dst, long long rows, int c, int c_pad,
+                        const float* gscale_buf, float* col_sum, void* stream) {
+  if (dtype != VP3D_F16 && dtype != VP3D_BF16) return fail(VP3D_ERR_INVALID, "grad_pack_rows: dtype must be F16 or BF16");
+  if (!src || !dst || rows <= 0 || c <= 0 || c_pad < c) return fail(VP3D_ERR_INVALID, "grad_pack_rows args");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_grad_pack_rows(dtype, src, dst, rows, c, c_pad, gscale_buf, col_sum, dev->sm_count,
+                                              static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "grad_pack_rows launch");
   return VP3D_OK;
 }
 

@@ -33,7 +33,8 @@ struct GemmCfg {
   static constexpr int kStages = (BN == 256) ? 4 : 8;
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual alignment slack
+  static constexpr int kStatBytes = 4 * BN * 2 * 4;  // per epilogue warp: BN x {sum, sum of squares} fp32
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kStatBytes + 1024;  // +1024: alignment slack
 };
 
 template <int DT>
@@ -107,6 +108,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* stat_smem = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -202,13 +204,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row = quad * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
+    // per-warp fp32 statistics accumulators in shared memory, flushed (double atomics) when the CTA moves to another
+    // column tile -- with gridDim.x a multiple of n_tiles a CTA keeps one column tile for the whole launch
+    float* stat_warp = stat_smem + quad * BN * 2;
+    int stat_n0 = -1;
+    auto stat_flush = [&]() {
+      if (stat_n0 >= 0) {
+        for (int j = lane; j < BN; j += 32) {
+          atomicAdd(p.stat_sum + stat_n0 * BN + j, (double)stat_warp[2 * j]);
+          atomicAdd(p.stat_sqsum + stat_n0 * BN + j, (double)stat_warp[2 * j + 1]);
+        }
+      }
+      for (int j = lane; j < 2 * BN; j += 32) stat_warp[j] = 0.f;
+      __syncwarp();
+    };
+    if (p.stat_sum != nullptr) stat_flush();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(tile, p);
+      if (p.stat_sum != nullptr && tc.n0 != stat_n0) {
+        stat_flush();
+        stat_n0 = tc.n0;
+      }
       const int t = tc.t0 + row;
       const bool row_ok = t < p.rows_out;
       const long long out_off = (long long)tc.seq * p.out_seq_stride + (long long)t * p.out_row_stride;
+      const long long res_row = (long long)t * p.res_row_mul + p.res_row_off;
+      const bool res_row_ok = p.res_rows <= 0 || (res_row >= 0 && res_row < p.res_rows);
       const long long res_off =
-          (long long)tc.seq * p.res_seq_stride + ((long long)t * p.res_row_mul + p.res_row_off) * p.res_row_stride;
+          (long long)tc.seq * p.res_seq_stride + res_row * p.res_row_stride - p.res_col_off;
 
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
@@ -224,21 +247,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
 
         if (p.stat_sum != nullptr) {
-          // per-channel sum / sum of squares of the raw convolution output over the valid rows of this warp
+          // Train-mode BatchNorm statistics of the raw convolution output. Thread = row, so a per-channel sum over
+          // the warp's 32 rows is a transposing butterfly: after the 5 exchange steps lane j holds column j.
+          float s[32], q[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float s = row_ok ? f[j] : 0.f;
-            float q = s * s;
+            s[j] = row_ok ? f[j] : 0.f;
+            q[j] = s[j] * s[j];
+          }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              s += __shfl_xor_sync(0xffffffffu, s, o);
-              q += __shfl_xor_sync(0xffffffffu, q, o);
-            }
-            if (lane == j) {
-              atomicAdd(p.stat_sum + col0 + j, s);
-              atomicAdd(p.stat_sqsum + col0 + j, q);
+          for (int o = 16; o > 0; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int i = 0; i < o; ++i) {
+              const float ks = up ? s[i + o] : s[i], ss = up ? s[i] : s[i + o];
+              const float kq = up ? q[i + o] : q[i], sq = up ? q[i] : q[i + o];
+              s[i] = ks + __shfl_xor_sync(0xffffffffu, ss, o);
+              q[i] = kq + __shfl_xor_sync(0xffffffffu, sq, o);
             }
           }
+          float* acc_s = stat_warp + (c * 32 + lane) * 2;  // owned by exactly this lane: no atomics in smem
+          acc_s[0] += s[0];
+          acc_s[1] += q[0];
         }
         if (p.scale != nullptr) {
           const float4* sc4 = reinterpret_cast<const float4*>(p.scale + col0);
@@ -258,7 +288,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
         if (row_ok) {
-          if (p.res != nullptr) {
+          if (p.res != nullptr && res_row_ok &&
+              (p.res_cols <= 0 || (col0 >= p.res_col_off && col0 < p.res_col_off + p.res_cols))) {
             if (ET::kBytes == 2) {
               const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.res) + res_off + col0);
 #pragma unroll
@@ -319,6 +350,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_arrive(&tmem_empty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+    }
+    if (p.stat_sum != nullptr) {
+      __syncwarp();
+      stat_flush();
     }
   }
 

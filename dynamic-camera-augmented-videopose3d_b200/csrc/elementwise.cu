@@ -39,27 +39,33 @@ pack_rows_kernel(const float* __restrict__ src, void* __restrict__ dst, long lon
   }
 }
 
-// dst[n][tap][ci] = w[n][ci][tap]             (transpose == 0; rows = output channels, K = tap*c_in_pad + ci)
-// dst[tap*c_in + ci][co] = w[co][ci][tap]     (transpose == 1; rows = (tap, ci), K = output channel)
+// dst[n][tap][ci] = w[n][ci][tap]                  (transpose == 0; rows = output channels, K = tap*c_in_pad + ci)
+// dst[tap*c_in_pad + ci][co] = w[co][ci][tap]      (transpose == 1; rows = (tap, ci) with c_in_pad = rows_pad / taps)
+// dst[ci][tap*k_pad_per_tap + co] = w[co][ci][tap] (transpose == 2; rows = input channels, K = (tap, output channel))
 template <int DT>
 __global__ void __launch_bounds__(256)
 pack_weight_kernel(const float* __restrict__ w, void* __restrict__ dst, int c_out, int c_in, int taps, int rows_pad,
                    int k_pad_per_tap, int transpose) {
-  const long long k_total = transpose ? k_pad_per_tap : (long long)taps * k_pad_per_tap;
+  const long long k_total = transpose == 1 ? k_pad_per_tap : (long long)taps * k_pad_per_tap;
   const long long total = (long long)rows_pad * k_total;
   const long long stride = (long long)gridDim.x * blockDim.x;
+  const int c_in_pad = rows_pad / taps;  // transpose == 1 only
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const long long r = i / k_total;
     const long long k = i - r * k_total;
     float v = 0.f;
-    if (!transpose) {
+    if (transpose == 0) {
       const int tap = (int)(k / k_pad_per_tap);
       const int ci = (int)(k - (long long)tap * k_pad_per_tap);
       if (r < c_out && ci < c_in) v = __ldg(w + ((long long)r * c_in + ci) * taps + tap);
+    } else if (transpose == 1) {
+      const int tap = (int)(r / c_in_pad);
+      const int ci = (int)(r - (long long)tap * c_in_pad);
+      if (tap < taps && ci < c_in && k < c_out) v = __ldg(w + ((long long)k * c_in + ci) * taps + tap);
     } else {
-      const int tap = (int)(r / c_in);
-      const int ci = (int)(r - (long long)tap * c_in);
-      if (tap < taps && k < c_out) v = __ldg(w + ((long long)k * c_in + ci) * taps + tap);
+      const int tap = (int)(k / k_pad_per_tap);
+      const int co = (int)(k - (long long)tap * k_pad_per_tap);
+      if (r < c_in && co < c_out) v = __ldg(w + ((long long)co * c_in + r) * taps + tap);
     }
     store_elem<DT>(dst, i, v);
   }
@@ -101,7 +107,7 @@ cudaError_t launch_pack_rows(int dtype, const float* src, void* dst, long long r
 
 cudaError_t launch_pack_weight(int dtype, const float* w, void* dst, int c_out, int c_in, int taps, int rows_pad,
                                int k_pad_per_tap, int transpose, int sm_count, cudaStream_t stream) {
-  const long long k_total = transpose ? k_pad_per_tap : (long long)taps * k_pad_per_tap;
+  const long long k_total = transpose == 1 ? k_pad_per_tap : (long long)taps * k_pad_per_tap;
   const int grid = ew_grid((long long)rows_pad * k_total, sm_count);
   if (dtype == VP3D_F16)
     pack_weight_kernel<VP3D_F16><<<grid, 256, 0, stream>>>(w, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap, transpose);

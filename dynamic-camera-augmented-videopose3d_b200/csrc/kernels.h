@@ -29,6 +29,9 @@ struct ConvGemmParams {
   long long res_row_stride;
   int res_row_mul;      // residual row = out_row * res_row_mul + res_row_off
   int res_row_off;
+  long long res_rows;   // > 0: rows outside [0, res_rows) add nothing
+  int res_col_off;      // residual applies to output columns [res_col_off, res_col_off + res_cols), reading column
+  int res_cols;         // col - res_col_off; res_cols == 0: all columns
 
   void* out;
   long long out_seq_stride;
@@ -37,11 +40,57 @@ struct ConvGemmParams {
   int n_valid;          // real output channels (<= n_pad); only consulted on the fp32 path
   int out_round_tf32;   // fp32 outputs are rounded (RN) to TF32 precision for a following TF32 layer
 
-  float* stat_sum;      // optional per-channel sum / sum-of-squares of the raw accumulator (train-mode BN)
-  float* stat_sqsum;
+  double* stat_sum;     // optional per-channel sum / sum-of-squares of the raw accumulator (train-mode BN)
+  double* stat_sqsum;
 };
 
 cudaError_t launch_conv_gemm(int dtype, int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB,
                              const ConvGemmParams& p, int grid, cudaStream_t stream);
+
+// Launch parameters of wgrad_gemm_kernel (see wgrad.cu).
+struct WgradParams {
+  int num_tiles;        // taps * co_tiles * ci_tiles
+  int co_tiles;         // co_pad / 128
+  int ci_tiles;         // ci_pad / BLOCK_N
+  int seqs;
+  int kb_per_seq;       // ceil(rows per sequence / 64)
+  int b_row_off;        // input row read against gradient row 0 by tap 0
+  int b_tap_row_step;   // extra input rows per tap (dilation)
+  int b_tap_col_step;   // extra input columns per tap (stride == width layers on the reshaped view)
+  float* out;           // packed fp32 [taps][co_pad][ci_pad]
+  long long out_tap_stride;
+  long long out_row_stride;
+};
+cudaError_t launch_wgrad(int dtype, int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const WgradParams& p,
+                         int grid, cudaStream_t stream);
+cudaError_t launch_wgrad_finish(const float* packed, float* dw, int c_out, int c_in, int taps, int co_pad, int ci_pad,
+                                const float* gscale_buf, int sm_count, cudaStream_t stream);
+
+// Counter-based dropout description (train.cu).
+struct DropoutParams {
+  float p;
+  unsigned long long seed;
+  unsigned long long stream;
+};
+cudaError_t launch_bn_finalize(const double* sum, const double* sqsum, long long count, const float* gamma,
+                               const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                               long long* nbt, float* scale, float* shift, float* mean, float* invstd, int c, int c_pad,
+                               cudaStream_t stream);
+cudaError_t launch_bn_act_fwd(int dtype, const void* z, const float* scale, const float* shift, const void* res,
+                              long long seqs, long long rows_per_seq, long long res_seq_rows, int res_row_mul,
+                              int res_row_off, int c_pad, const DropoutParams& dp, void* a, int sm_count,
+                              cudaStream_t stream);
+cudaError_t launch_bn_act_bwd_reduce(int dtype, const void* g, const void* z, const float* scale, const float* shift,
+                                     const float* mean, const float* invstd, long long rows, int c_pad,
+                                     const DropoutParams& dp, double* sum_dy, double* sum_dy_xhat, int sm_count,
+                                     cudaStream_t stream);
+cudaError_t launch_bn_act_bwd_apply(int dtype, const void* g, const void* z, const float* scale, const float* shift,
+                                    const float* mean, const float* invstd, long long rows, int c, int c_pad,
+                                    const DropoutParams& dp, const double* sum_dy, const double* sum_dy_xhat,
+                                    const float* gscale_buf, void* dz, float* d_gamma, float* d_beta, int sm_count,
+                                    cudaStream_t stream);
+cudaError_t launch_grad_scale(const float* dy, long long n, float* gscale_buf, int sm_count, cudaStream_t stream);
+cudaError_t launch_grad_pack_rows(int dtype, const float* src, void* dst, long long rows, int c, int c_pad,
+                                  const float* gscale_buf, float* col_sum, int sm_count, cudaStream_t stream);
 
 }  // namespace vp3d

@@ -1,1 +1,448 @@
+// Train-mode BatchNorm / ReLU / Dropout / residual kernels around the convolution GEMMs (all HBM-bandwidth bound).
+//
+// What they replace in the reference (common/models/TemporalModel.py in train() mode, backward at run.py:485):
+//   forward   x = drop(relu(bn(conv(x))))            :127,134 / :189,194     bn_finalize + bn_act_fwd
+//             x = res + drop(relu(bn(conv(x))))      :135 / :195             (residual rows res[t * mul + off])
+//   backward  the autograd chain of the same ops                              bn_act_bwd_reduce + bn_act_bwd_apply
+// The per-channel sum / sum of squares of the raw convolution output comes from the GEMM epilogue (conv_gemm.cu), so
+// the forward touches each activation matrix twice (read z, write a) and the backward three times (2 x read g,z;
+// write dz). Matrices are channels-last [rows][c_pad] in the 16-bit operand type; a thread owns 8 consecutive channels
+// (one 16-byte vector) and walks rows, so every access is a full coalesced 16-byte lane.
+//
+// Dropout is counter based: the keep decision of (row, 8-channel group) is 8 x 16 bits of one Philox4x32-10 block keyed
+// by (seed, stream), so the backward recomputes the forward mask instead of storing it.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "kernels.h"
+
+namespace vp3d {
+
+constexpr int kEwThreads = 256;
+
+// ---------------------------------------------------------------------------------------------- helpers
+template <int DT>
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 v;
+    if (DT == VP3D_F16) v = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    else v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+    f[2 * i] = v.x;
+    f[2 * i + 1] = v.y;
+  }
+}
+template <int DT>
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (DT == VP3D_F16) {
+      __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    } else {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// Philox4x32-10 (Salmon et al., SC'11): counter (c0..c3), key (k0, k1).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+    const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += W0;
+    k.y += W1;
+  }
+  return c;
+}
+
+struct DropCtx {
+  float p;
+  uint32_t thresh;  // keep iff 16-bit draw >= thresh
+  float keep_scale;
+  uint2 key;
+  uint32_t s_lo, s_hi;
+};
+__device__ __forceinline__ DropCtx make_drop(const DropoutParams& d) {
+  DropCtx c;
+  c.p = d.p;
+  c.thresh = (uint32_t)(d.p * 65536.f + 0.5f);
+  c.keep_scale = d.p > 0.f ? 1.f / (1.f - d.p) : 1.f;
+  c.key = make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32));
+  c.s_lo = (uint32_t)d.stream;
+  c.s_hi = (uint32_t)(d.stream >> 32);
+  return c;
+}
+// multipliers (0 or 1/(1-p)) of the 8 channels of group `grp` in row `row`
+__device__ __forceinline__ void drop_mult8(const DropCtx& d, long long row, int grp, float (&m)[8]) {
+  if (d.p <= 0.f) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = 1.f;
+    return;
+  }
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)((unsigned long long)row >> 32) ^ (grp * 0x9E3779B1u),
+                                           d.s_lo, d.s_hi), d.key);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m[2 * i] = (w[i] & 0xFFFFu) >= d.thresh ? d.keep_scale : 0.f;
+    m[2 * i + 1] = (w[i] >> 16) >= d.thresh ? d.keep_scale : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- bn_finalize
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sqsum, long long count,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
+                   float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ nbt,
+                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                   float* __restrict__ invstd_out, int c, int c_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && nbt != nullptr) *nbt += 1;
+  if (i >= c_pad) return;
+  if (i >= c) {
+    scale[i] = 0.f;
+    shift[i] = 0.f;
+    mean_out[i] = 0.f;
+    invstd_out[i] = 0.f;
+    return;
+  }
+  const double n = (double)count;
+  const double m = sum[i] / n;
+  double var = sqsum[i] / n - m * m;  // biased, as F.batch_norm normalises with
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[i] * invstd;
+  scale[i] = sc;
+  shift[i] = beta[i] - (float)m * sc;
+  mean_out[i] = (float)m;
+  invstd_out[i] = invstd;
+  if (running_mean != nullptr) {
+    const double unbiased = count > 1 ? var * n / (n - 1.0) : var;
+    running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * (float)m;
+    running_var[i] = (1.f - momentum) * running_var[i] + momentum * (float)unbiased;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- forward apply
+// grid-stride over (row, channel group); groups = c_pad / 8
+template <int DT>
+__global__ void __launch_bounds__(kEwThreads)
+bn_act_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
+                  const uint4* __restrict__ res, long long rows, long long rows_per_seq, long long res_seq_rows,
+                  int res_row_mul, int res_row_off, int groups, DropoutParams dp, uint4* __restrict__ a) {
+  const DropCtx drop = make_drop(dp);
+  const long long total = rows * groups;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long row = i / groups;
+    const int grp = (int)(i - row * groups);
+    float v[8], m[8];
+    unpack8<DT>(__ldg(z + i), v);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale) + 2 * grp);
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale) + 2 * grp + 1);
+    const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift) + 2 * grp);
+    const float4 h1 = __ldg(reinterpret_cast<const float4*>(shift) + 2 * grp + 1);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    drop_mult8(drop, row, grp, m);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f) * m[k];
+    if (res != nullptr) {
+      const long long seq = row / rows_per_seq;
+      const long long t = row - seq * rows_per_seq;
+      const long long rrow = seq * res_seq_rows + t * res_row_mul + res_row_off;
+      float r[8];
+      unpack8<DT>(__ldg(res + rrow * groups + grp), r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += r[k];
+    }
+    a[i] = pack8<DT>(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- backward
+// dy = g * dropout multiplier * [z * scale + shift > 0];  xhat = (z - mean) * invstd
+template <int DT>
+__device__ __forceinline__ void load_dy_xhat(const uint4* g, const uint4* z, long long i, long long row, int grp,
+                                             const float (&sc)[8], const float (&sh)[8], const float (&mu)[8],
+                                             const float (&is)[8], const DropCtx& drop, float (&dy)[8],
+                                             float (&xh)[8]) {
+  float gv[8], zv[8], m[8];
+  unpack8<DT>(__ldg(g + i), gv);
+  unpack8<DT>(__ldg(z + i), zv);
+  drop_mult8(drop, row, grp, m);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const bool on = fmaf(zv[k], sc[k], sh[k]) > 0.f;
+    dy[k] = on ? gv[k] * m[k] : 0.f;
+    xh[k] = (zv[k] - mu[k]) * is[k];
+  }
+}
+
+__device__ __forceinline__ void load8(const float* p, int grp, float (&o)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p) + 2 * grp);
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 2 * grp + 1);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+
+// Block = kEwThreads threads = (kEwThreads / groups_per_block) row lanes x groups_per_block channel groups. A block
+// owns a fixed slab of channel groups (blockIdx.y) and strides over rows (blockIdx.x), so each thread keeps its 8
+// channels' partial sums in registers; one shared-memory combine and one double atomic per channel per block.
+template <int DT>
+__global__ void __launch_bounds__(kEwThreads)
+bn_act_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z, const float* __restrict__ scale,
+                         const float* __restrict__ shift, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, long long rows, int groups, DropoutParams dp,
+                         double* __restrict__ sum_dy, double* __restrict__ sum_dy_xhat) {
+  constexpr int kGroupsPerBlock = 32;               // 256 channels per block
+  constexpr int kRowLanes = kEwThreads / kGroupsPerBlock;
+  __shared__ float part[2][kRowLanes][kGroupsPerBlock * 8 + 8];
+  const DropCtx drop = make_drop(dp);
+  const int gl = threadIdx.x % kGroupsPerBlock;
+  const int rl = threadIdx.x / kGroupsPerBlock;
+  const int grp = blockIdx.y * kGroupsPerBlock + gl;
+  float a1[8], a2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a1[k] = a2[k] = 0.f;
+  if (grp < groups) {
+    float sc[8], sh[8], mu[8], is[8];
+    load8(scale, grp, sc);
+    load8(shift, grp, sh);
+    load8(mean, grp, mu);
+    load8(invstd, grp, is);
+    for (long long row = (long long)blockIdx.x * kRowLanes + rl; row < rows; row += (long long)gridDim.x * kRowLanes) {
+      float dy[8], xh[8];
+      load_dy_xhat<DT>(g, z, row * groups + grp, row, grp, sc, sh, mu, is, drop, dy, xh);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        a1[k] += dy[k];
+        a2[k] = fmaf(dy[k], xh[k], a2[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    part[0][rl][gl * 8 + k] = a1[k];
+    part[1][rl][gl * 8 + k] = a2[k];
+  }
+  __syncthreads();
+  // 256 channels x 2 quantities, one thread each for the first 256 threads (two quantities per thread)
+  const int ch = threadIdx.x;
+  if (ch < kGroupsPerBlock * 8) {
+    const int cg = blockIdx.y * kGroupsPerBlock * 8 + ch;
+    if (cg < groups * 8) {
+      double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int r = 0; r < kRowLanes; ++r) {
+        s1 += (double)part[0][r][ch];
+        s2 += (double)part[1][r][ch];
+      }
+      atomicAdd(sum_dy + cg, s1);
+      atomicAdd(sum_dy_xhat + cg, s2);
+    }
+  }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kEwThreads)
+bn_act_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z, const float* __restrict__ scale,
+                        const float* __restrict__ shift, const float* __restrict__ mean,
+                        const float* __restrict__ invstd, long long rows, int c, int groups, DropoutParams dp,
+                        const double* __restrict__ sum_dy, const double* __restrict__ sum_dy_xhat,
+                        const float* __restrict__ gscale_buf, uint4* __restrict__ dz, float* __restrict__ d_gamma,
+                        float* __restrict__ d_beta) {
+  const DropCtx drop = make_drop(dp);
+  const float inv_n = 1.f / (float)rows;
+  // BatchNorm parameter gradients: one block writes them (un-scaled)
+  if (blockIdx.x == 0 && d_gamma != nullptr) {
+    const float inv = gscale_buf != nullptr ? gscale_buf[1] : 1.f;
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+      d_gamma[ch] = (float)(sum_dy_xhat[ch] * (double)inv);
+      d_beta[ch] = (float)(sum_dy[ch] * (double)inv);
+    }
+  }
+  const long long total = rows * groups;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long row = i / groups;
+    const int grp = (int)(i - row * groups);
+    float sc[8], sh[8], mu[8], is[8], dy[8], xh[8], o[8];
+    load8(scale, grp, sc);
+    load8(shift, grp, sh);
+    load8(mean, grp, mu);
+    load8(invstd, grp, is);
+    load_dy_xhat<DT>(g, z, i, row, grp, sc, sh, mu, is, drop, dy, xh);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float m1 = (float)sum_dy[grp * 8 + k] * inv_n;
+      const float m2 = (float)sum_dy_xhat[grp * 8 + k] * inv_n;
+      o[k] = sc[k] * (dy[k] - m1 - xh[k] * m2);
+    }
+    dz[i] = pack8<DT>(o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- gradient scale
+__global__ void __launch_bounds__(256)
+grad_absmax_kernel(const float* __restrict__ dy, long long n, float* __restrict__ gscale_buf) {
+  float m = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = fabsf(dy[i]);
+    if (v == v) m = fmaxf(m, v);  // NaN-safe: a NaN gradient stays a NaN downstream, it must not poison the scale
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(gscale_buf + 2), __float_as_uint(m));
+}
+__global__ void grad_scale_finish_kernel(float* __restrict__ gscale_buf) {
+  const float m = gscale_buf[2];
+  float s = 1.f;
+  if (m > 0.f && m < 3.0e38f) {
+    int e;
+    frexpf(64.f / m, &e);  // 64 / m = f * 2^e, f in [0.5, 1)  ->  floor(log2) = e - 1
+    e -= 1;
+    if (e > 60) e = 60;
+    if (e < -60) e = -60;
+    s = ldexpf(1.f, e);
+  }
+  gscale_buf[0] = s;
+  gscale_buf[1] = 1.f / s;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256)
+grad_pack_rows_kernel(const float* __restrict__ src, void* __restrict__ dst, long long rows, int c, int c_pad,
+                      const float* __restrict__ gscale_buf, float* __restrict__ col_sum) {
+  const float gs = gscale_buf != nullptr ? gscale_buf[0] : 1.f;
+  // thread = column (blockDim.x >= c_pad handled by stride), rows strided over blocks: coalesced in both src and dst
+  for (int k = threadIdx.x; k < c_pad; k += blockDim.x) {
+    float acc = 0.f;
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+      const float v = k < c ? __ldg(src + r * c + k) : 0.f;
+      acc += v;
+      if (DT == VP3D_F16) static_cast<__half*>(dst)[r * c_pad + k] = __float2half_rn(v * gs);
+      else static_cast<__nv_bfloat16*>(dst)[r * c_pad + k] = __float2bfloat16_rn(v * gs);
+    }
+    if (col_sum != nullptr && k < c) atomicAdd(col_sum + k, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- launchers
+static int rows_grid(long long total, int sm_count, int per_sm) {
+  long long blocks = (total + kEwThreads - 1) / kEwThreads;
+  const long long cap = (long long)sm_count * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+cudaError_t launch_bn_finalize(const double* sum, const double* sqsum, long long count, const float* gamma,
+                               const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                               long long* nbt, float* scale, float* shift, float* mean, float* invstd, int c, int c_pad,
+                               cudaStream_t stream) {
+  bn_finalize_kernel<<<(c_pad + 255) / 256, 256, 0, stream>>>(sum, sqsum, count, gamma, beta, eps, momentum,
+                                                              running_mean, running_var, nbt, scale, shift, mean,
+                                                              invstd, c, c_pad);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bn_act_fwd(int dtype, const void* z, const float* scale, const float* shift, const void* res,
+                              long long seqs, long long rows_per_seq, long long res_seq_rows, int res_row_mul,
+                              int res_row_off, int c_pad, const DropoutParams& dp, void* a, int sm_count,
+                              cudaStream_t stream) {
+  const long long rows = seqs * rows_per_seq;
+  const int groups = c_pad / 8;
+  const int grid = rows_grid(rows * groups, sm_count, 8);
+  if (dtype == VP3D_F16)
+    bn_act_fwd_kernel<VP3D_F16><<<grid, kEwThreads, 0, stream>>>(
+        static_cast<const uint4*>(z), scale, shift, static_cast<const uint4*>(res), rows, rows_per_seq, res_seq_rows,
+        res_row_mul, res_row_off, groups, dp, static_cast<uint4*>(a));
+  else if (dtype == VP3D_BF16)
+    bn_act_fwd_kernel<VP3D_BF16><<<grid, kEwThreads, 0, stream>>>(
+        static_cast<const uint4*>(z), scale, shift, static_cast<const uint4*>(res), rows, rows_per_seq, res_seq_rows,
+        res_row_mul, res_row_off, groups, dp, static_cast<uint4*>(a));
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bn_act_bwd_reduce(int dtype, const void* g, const void* z, const float* scale, const float* shift,
+                                     const float* mean, const float* invstd, long long rows, int c_pad,
+                                     const DropoutParams& dp, double* sum_dy, double* sum_dy_xhat, int sm_count,
+                                     cudaStream_t stream) {
+  const int groups = c_pad / 8;
+  const int gy = (groups + 31) / 32;
+  long long gx = (rows + 7) / 8;  // 8 row lanes per block
+  const long long cap = ((long long)sm_count * 8 + gy - 1) / gy;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)gy);
+  if (dtype == VP3D_F16)
+    bn_act_bwd_reduce_kernel<VP3D_F16><<<grid, kEwThreads, 0, stream>>>(
+        static_cast<const uint4*>(g), static_cast<const uint4*>(z), scale, shift, mean, invstd, rows, groups, dp,
+        sum_dy, sum_dy_xhat);
+  else if (dtype == VP3D_BF16)
+    bn_act_bwd_reduce_kernel<VP3D_BF16><<<grid, kEwThreads, 0, stream>>>(
+        static_cast<const uint4*>(g), static_cast<const uint4*>(z), scale, shift, mean, invstd, rows, groups, dp,
+        sum_dy, sum_dy_xhat);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bn_act_bwd_apply(int dtype, const void* g, const void* z, const float* scale, const float* shift,
+                                    const float* mean, const float* invstd, long long rows, int c, int c_pad,
+                                    const DropoutParams& dp, const double* sum_dy, const double* sum_dy_xhat,
+                                    const float* gscale_buf, void* dz, float* d_gamma, float* d_beta, int sm_count,
+                                    cudaStream_t stream) {
+  const int groups = c_pad / 8;
+  const int grid = rows_grid(rows * groups, sm_count, 8);
+  if (dtype == VP3D_F16)
+    bn_act_bwd_apply_kernel<VP3D_F16><<<grid, kEwThreads, 0, stream>>>(
+        static_cast<const uint4*>(g), static_cast<const uint4*>(z), scale, shift, mean, invstd, rows, c, groups, dp,
+        sum_dy, sum_dy_xhat, gscale_buf, static_cast<uint4*>(dz), d_gamma, d_beta);
+  else if (dtype == VP3D_BF16)
+    bn_act_bwd_apply_kernel<VP3D_BF16><<<grid, kEwThreads, 0, stream>>>(
+        static_cast<const uint4*>(g), static_cast<const uint4*>(z), scale, shift, mean, invstd, rows, c, groups, dp,
+        sum_dy, sum_dy_xhat, gscale_buf, static_cast<uint4*>(dz), d_gamma, d_beta);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_grad_scale(const float* dy, long long n, float* gscale_buf, int sm_count, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(gscale_buf, 0, 3 * sizeof(float), stream);
+  if (e != cudaSuccess) return e;
+  long long blocks = (n + 255) / 256;
+  if (blocks > sm_count * 4) blocks = sm_count * 4;
+  if (blocks < 1) blocks = 1;
+  grad_absmax_kernel<<<(int)blocks, 256, 0, stream>>>(dy, n, gscale_buf);
+  grad_scale_finish_kernel<<<1, 1, 0, stream>>>(gscale_buf);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_grad_pack_rows(int dtype, const float* src, void* dst, long long rows, int c, int c_pad,
+                                  const float* gscale_buf, float* col_sum, int sm_count, cudaStream_t stream) {
+  long long blocks = rows;
+  if (blocks > sm_count * 8) blocks = sm_count * 8;
+  if (blocks < 1) blocks = 1;
+  const int threads = c_pad < 256 ? ((c_pad + 31) / 32) * 32 : 256;
+  if (dtype == VP3D_F16)
+    grad_pack_rows_kernel<VP3D_F16><<<(int)blocks, threads, 0, stream>>>(src, dst, rows, c, c_pad, gscale_buf, col_sum);
+  else if (dtype == VP3D_BF16)
+    grad_pack_rows_kernel<VP3D_BF16><<<(int)blocks, threads, 0, stream>>>(src, dst, rows, c, c_pad, gscale_buf, col_sum);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+}  // namespace vp3d

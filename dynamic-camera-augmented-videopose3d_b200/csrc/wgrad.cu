@@ -1,0 +1,283 @@
+// K4: weight gradient of the temporal convolutions as a tcgen05 / TMEM GEMM whose reduction runs over frames (sm_100a).
+//
+// What it replaces in the reference: the autograd weight gradient of every nn.Conv1d of the stack
+// (common/models/TemporalModel.py:102,113-118 dilated, :168-181 strided; backward triggered at run.py:485):
+//
+//   dW[tap][co][ci] = sum_{seq, r}  dz[seq][r][co] * a[seq][r + tap * dilation][ci]          (dilated model)
+//   dW[tap][co][ci] = sum_{r}       dz[r][co]      * a_view[r][tap * c_in + ci]              (stride == width, 1f model)
+//
+// Both operands live channels-last in HBM, i.e. the reduction index (the frame) is the *slow* index of both: they are
+// "MN-major" tcgen05 operands. TMA fetches [64 frames x 128 bytes of channels] boxes with SWIZZLE_128B; the shared
+// memory descriptor walks them with LBO = one box (next 64-channel group) and SBO = 1024 B (next 8 frames), so no
+// transpose pass over HBM is needed.
+//
+// Work decomposition ("stream-K"): a work unit is (output tile 128 co x BN ci of one tap, block of 64 frames). The
+// units are split evenly over the persistent CTAs (one per SM); a CTA accumulates a run of units of one tile in TMEM
+// and combines its partial tile into the fp32 result with vector reductions (red.global.add.v4.f32). Every SM gets the
+// same number of MMAs whatever the layer shape -- the 1f model's layers range from 82,944 frames down to 1,024.
+//
+// Pipeline per CTA (192 threads), as in conv_gemm.cu: warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue with
+// two TMEM accumulator buffers so that the reduction of run i overlaps the MMAs of run i + 1.
+#include "ptx.cuh"
+#include "kernels.h"
+
+namespace vp3d {
+
+constexpr int kWgBlockM = 128;    // output channels per tile
+constexpr int kWgRows = 64;       // frames (reduction depth) per pipeline stage
+constexpr int kWgThreads = 192;
+
+template <int BN>
+struct WgradCfg {
+  static constexpr int kABytes = kWgBlockM * kWgRows * 2;  // 16 KB: 2 boxes of [64 frames][64 channels]
+  static constexpr int kBBytes = BN * kWgRows * 2;         // BN / 64 boxes
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : 8;
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
+};
+
+// MN-major SWIZZLE_128B operand: 64-element (128-byte) channel groups `lbo` bytes apart, 8-frame groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+struct WgUnit {
+  int tap, co0, ci0, seq, r0;
+};
+__device__ __forceinline__ void decode_tile(int tile, const WgradParams& p, int& tap, int& co0, int& ci0) {
+  const int ci_t = tile % p.ci_tiles;
+  const int rest = tile / p.ci_tiles;
+  const int co_t = rest % p.co_tiles;
+  tap = rest / p.co_tiles;
+  co0 = co_t * kWgBlockM;
+  ci0 = ci_t;
+}
+
+template <int DT, int BN>
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const WgradParams p) {
+  using Cfg = WgradCfg<BN>;
+  constexpr uint32_t kFormat = (DT == VP3D_BF16) ? 1u : 0u;
+  // instruction descriptor: fp32 accumulate, A and B both MN-major (bits 15, 16)
+  constexpr uint32_t kIdesc = make_instr_desc(kFormat, kWgBlockM, BN) | (1u << 15) | (1u << 16);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // this CTA's run of work units; unit = tile * kb_total + kb, kb = seq * kb_per_seq + row block
+  const long long kb_total = (long long)p.seqs * p.kb_per_seq;
+  const long long total_units = (long long)p.num_tiles * kb_total;
+  const long long u_begin = total_units * blockIdx.x / gridDim.x;
+  const long long u_end = total_units * (blockIdx.x + 1) / gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_base_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long u = u_begin; u < u_end; ++u) {
+        const int tile = (int)(u / kb_total);
+        const long long kb = u - (long long)tile * kb_total;
+        const int seq = (int)(kb / p.kb_per_seq);
+        const int r0 = (int)(kb - (long long)seq * p.kb_per_seq) * kWgRows;
+        int tap, co0, ci_t;
+        decode_tile(tile, p, tap, co0, ci_t);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+        uint8_t* sa = smem + stage * Cfg::kStageBytes;
+#pragma unroll
+        for (int g = 0; g < kWgBlockM / 64; ++g)
+          tma_load_3d(sa + g * (kWgRows * 128), &tmA, &full_bar[stage], co0 + g * 64, r0, seq);
+        uint8_t* sb = sa + Cfg::kABytes;
+        const int b_col = ci_t * BN + tap * p.b_tap_col_step;
+        const int b_row = r0 + p.b_row_off + tap * p.b_tap_row_step;
+#pragma unroll
+        for (int g = 0; g < BN / 64; ++g)
+          tma_load_3d(sb + g * (kWgRows * 128), &tmB, &full_bar[stage], b_col + g * 64, b_row, seq);
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      long long u = u_begin;
+      while (u < u_end) {
+        const long long tile = u / kb_total;
+        long long run_end = (tile + 1) * kb_total;
+        if (run_end > u_end) run_end = u_end;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        bool first = true;
+        for (; u < run_end; ++u) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t adesc = make_mnmajor_sw128_desc(sa, kWgRows * 128);
+          const uint64_t bdesc = make_mnmajor_sw128_desc(sa + Cfg::kABytes, kWgRows * 128);
+#pragma unroll
+          for (int k = 0; k < kWgRows / 16; ++k) {
+            // 16 frames of reduction per MMA = two 8-frame groups = 2048 bytes further into every box
+            umma_f16_ss(d_tmem, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), kIdesc, !(first && k == 0));
+          }
+          first = false;
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5): TMEM -> red.add
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    long long u = u_begin;
+    while (u < u_end) {
+      const long long tile = u / kb_total;
+      long long run_end = (tile + 1) * kb_total;
+      if (run_end > u_end) run_end = u_end;
+      int tap, co0, ci_t;
+      decode_tile((int)tile, p, tap, co0, ci_t);
+      float* out_row = p.out + (long long)tap * p.out_tap_stride + (long long)(co0 + row) * p.out_row_stride +
+                       (long long)ci_t * BN;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + acc * BN + c * 32 + (static_cast<uint32_t>(quad * 32) << 16), v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          red_add_v4(out_row + c * 32 + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                     __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+      u = run_end;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int DT, int BN>
+static cudaError_t launch_wg(const CUtensorMap& tmA, const CUtensorMap& tmB, const WgradParams& p, int grid,
+                             cudaStream_t stream) {
+  using Cfg = WgradCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel<DT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  wgrad_gemm_kernel<DT, BN><<<grid, kWgThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wgrad(int dtype, int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const WgradParams& p,
+                         int grid, cudaStream_t stream) {
+  if (block_n == 256) {
+    if (dtype == VP3D_F16) return launch_wg<VP3D_F16, 256>(tmA, tmB, p, grid, stream);
+    if (dtype == VP3D_BF16) return launch_wg<VP3D_BF16, 256>(tmA, tmB, p, grid, stream);
+  } else if (block_n == 64) {
+    if (dtype == VP3D_F16) return launch_wg<VP3D_F16, 64>(tmA, tmB, p, grid, stream);
+    if (dtype == VP3D_BF16) return launch_wg<VP3D_BF16, 64>(tmA, tmB, p, grid, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// dw[co][ci][tap] = packed[tap][co][ci] * inv_gscale   (nn.Conv1d weight layout)
+__global__ void __launch_bounds__(256)
+wgrad_finish_kernel(const float* __restrict__ packed, float* __restrict__ dw, int c_out, int c_in, int taps, int co_pad,
+                    int ci_pad, const float* __restrict__ gscale_buf) {
+  const float inv = gscale_buf != nullptr ? gscale_buf[1] : 1.f;
+  const long long total = (long long)c_out * c_in * taps;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int tap = (int)(i % taps);
+    const long long r = i / taps;
+    const int ci = (int)(r % c_in);
+    const int co = (int)(r / c_in);
+    dw[i] = __ldg(packed + ((long long)tap * co_pad + co) * ci_pad + ci) * inv;
+  }
+}
+
+cudaError_t launch_wgrad_finish(const float* packed, float* dw, int c_out, int c_in, int taps, int co_pad, int ci_pad,
+                                const float* gscale_buf, int sm_count, cudaStream_t stream) {
+  const long long total = (long long)c_out * c_in * taps;
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
+  if (blocks < 1) blocks = 1;
+  wgrad_finish_kernel<<<(int)blocks, 256, 0, stream>>>(packed, dw, c_out, c_in, taps, co_pad, ci_pad, gscale_buf);
+  return cudaGetLastError();
+}
+
+}  // namespace vp3d

@@ -28,8 +28,27 @@ class ConvArgs(C.Structure):
         ('scale', C.c_void_p), ('shift', C.c_void_p), ('relu', C.c_int),
         ('res', C.c_void_p), ('res_row_stride', C.c_longlong), ('res_seq_stride', C.c_longlong),
         ('res_row_mul', C.c_int), ('res_row_off', C.c_int),
+        ('res_rows', C.c_longlong), ('res_col_off', C.c_longlong), ('res_cols', C.c_longlong),
         ('stat_sum', C.c_void_p), ('stat_sqsum', C.c_void_p),
     ]
+
+
+class WgradArgs(C.Structure):
+    """struct vp3d_wgrad_args (include/vp3d_b200.h)"""
+    _fields_ = [
+        ('dtype', C.c_int), ('block_n', C.c_int),
+        ('dz', C.c_void_p), ('dz_seqs', C.c_longlong), ('dz_rows', C.c_longlong), ('dz_row_stride', C.c_longlong),
+        ('dz_seq_stride', C.c_longlong), ('co_pad', C.c_longlong),
+        ('a', C.c_void_p), ('a_rows', C.c_longlong), ('a_cols', C.c_longlong), ('a_row_stride', C.c_longlong),
+        ('a_seq_stride', C.c_longlong), ('ci_pad', C.c_longlong),
+        ('taps', C.c_int), ('b_row_off', C.c_longlong), ('b_tap_row_step', C.c_int), ('b_tap_col_step', C.c_longlong),
+        ('dw_packed', C.c_void_p),
+    ]
+
+
+class Dropout(C.Structure):
+    """struct vp3d_dropout (include/vp3d_b200.h)"""
+    _fields_ = [('p', C.c_float), ('seed', C.c_ulonglong), ('stream', C.c_ulonglong)]
 
 
 _SIGNATURES = {
@@ -49,6 +68,19 @@ _SIGNATURES = {
     'vp3d_mpjpe_bwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p] + [C.c_longlong] * 5 +
                        [C.c_void_p, C.c_void_p]),
     'vp3d_n_mpjpe_fwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'vp3d_wgrad': (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
+    'vp3d_wgrad_finish': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
+    'vp3d_bn_finalize': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_float, C.c_float] +
+                         [C.c_void_p] * 7 + [C.c_int, C.c_int, C.c_void_p]),
+    'vp3d_bn_act_fwd': (C.c_int, [C.c_int] + [C.c_void_p] * 4 + [C.c_longlong] * 3 + [C.c_int] * 3 +
+                        [C.POINTER(Dropout), C.c_void_p, C.c_void_p]),
+    'vp3d_bn_act_bwd_reduce': (C.c_int, [C.c_int] + [C.c_void_p] * 6 + [C.c_longlong, C.c_int, C.POINTER(Dropout),
+                                                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    'vp3d_bn_act_bwd_apply': (C.c_int, [C.c_int] + [C.c_void_p] * 6 + [C.c_longlong, C.c_int, C.c_int,
+                                                                      C.POINTER(Dropout)] + [C.c_void_p] * 7),
+    'vp3d_grad_scale': (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
+    'vp3d_grad_pack_rows': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import native
-from .native import ConvArgs, check, lib
+from .native import ConvArgs, Dropout, WgradArgs, check, lib
 
 
 def _stream():
@@ -179,7 +179,7 @@ def bn_fold(bn, c_pad):
 
 def conv_block(dt, a, a_view, w, taps, tap_row_step, k_per_tap, rows_out, out, out_view, block_n=256, a_row_off=0,
                scale=None, shift=None, relu=False, res=None, res_view=None, out_f32=False, n_valid=None,
-               stat_sum=None, stat_sqsum=None, out_round_tf32=False):
+               stat_sum=None, stat_sqsum=None, out_round_tf32=False, res_rows=0, res_col_off=0, res_cols=0):
     """One vp3d_conv_block_fwd launch.
     a_view   = (seqs, rows, kdim, row_stride, seq_stride)    out_view = (row_stride, seq_stride)
     res_view = (row_stride, seq_stride, row_mul, row_off)"""
@@ -203,8 +203,106 @@ def conv_block(dt, a, a_view, w, taps, tap_row_step, k_per_tap, rows_out, out, o
     if res is not None:
         args.res = res.data_ptr()
         args.res_row_stride, args.res_seq_stride, args.res_row_mul, args.res_row_off = res_view
+        args.res_rows, args.res_col_off, args.res_cols = res_rows, res_col_off, res_cols
     args.stat_sum = None if stat_sum is None else stat_sum.data_ptr()
     args.stat_sqsum = None if stat_sqsum is None else stat_sqsum.data_ptr()
     with torch.cuda.device(a.device):
         check(lib().vp3d_conv_block_fwd(C.byref(args), _stream()), 'conv_block_fwd')
     return out
+
+
+# ------------------------------------------------------------------------------------------------ training path
+def make_dropout(p, seed, stream):
+    d = Dropout()
+    d.p, d.seed, d.stream = float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream) & 0xFFFFFFFFFFFFFFFF
+    return d
+
+
+def wgrad(dt, dz, dz_view, a, a_view, co_pad, ci_pad, taps, dw_packed, b_row_off=0, b_tap_row_step=0,
+          b_tap_col_step=0, block_n=256):
+    """One vp3d_wgrad launch. dz_view = (seqs, rows, row_stride, seq_stride); a_view = (rows, cols, row_stride,
+    seq_stride). dw_packed: zero-filled fp32 [taps][co_pad][ci_pad]."""
+    args = WgradArgs()
+    args.dtype, args.block_n = dt, block_n
+    args.dz = dz.data_ptr()
+    args.dz_seqs, args.dz_rows, args.dz_row_stride, args.dz_seq_stride = dz_view
+    args.co_pad = co_pad
+    args.a = a.data_ptr()
+    args.a_rows, args.a_cols, args.a_row_stride, args.a_seq_stride = a_view
+    args.ci_pad = ci_pad
+    args.taps, args.b_row_off, args.b_tap_row_step, args.b_tap_col_step = taps, b_row_off, b_tap_row_step, b_tap_col_step
+    args.dw_packed = dw_packed.data_ptr()
+    with torch.cuda.device(dz.device):
+        check(lib().vp3d_wgrad(C.byref(args), _stream()), 'wgrad')
+    return dw_packed
+
+
+def wgrad_finish(dw_packed, c_out, c_in, taps, co_pad, ci_pad, gscale_buf):
+    dw = torch.empty((c_out, c_in, taps), dtype=torch.float32, device=dw_packed.device)
+    with torch.cuda.device(dw.device):
+        check(lib().vp3d_wgrad_finish(_ptr(dw_packed), _ptr(dw), c_out, c_in, taps, co_pad, ci_pad, _ptr(gscale_buf),
+                                      _stream()), 'wgrad_finish')
+    return dw
+
+
+def bn_finalize(stat, count, bn, c_pad, update_running=True):
+    """stat: double [2][c_pad] (sum, sum of squares) -> (scale, shift, mean, invstd) fp32 [c_pad]; updates the
+    nn.BatchNorm1d container's running statistics in place like F.batch_norm(training=True)."""
+    c = bn.num_features
+    dev = stat.device
+    out = torch.empty((4, c_pad), dtype=torch.float32, device=dev)
+    track = update_running and bn.track_running_stats and bn.running_mean is not None
+    momentum = 0.0 if bn.momentum is None else float(bn.momentum)
+    with torch.cuda.device(dev):
+        check(lib().vp3d_bn_finalize(_ptr(stat[0]), _ptr(stat[1]), int(count), _ptr(f32c(bn.weight.detach())),
+                                     _ptr(f32c(bn.bias.detach())), float(bn.eps), momentum,
+                                     _ptr(bn.running_mean) if track else None, _ptr(bn.running_var) if track else None,
+                                     _ptr(bn.num_batches_tracked) if track else None,
+                                     _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), c, c_pad, _stream()),
+              'bn_finalize')
+    return out[0], out[1], out[2], out[3]
+
+
+def bn_act_fwd(dt, z, scale, shift, seqs, rows_per_seq, drop, res=None, res_seq_rows=0, res_row_mul=1, res_row_off=0):
+    c_pad = z.shape[-1]
+    a = torch.empty_like(z)
+    with torch.cuda.device(z.device):
+        check(lib().vp3d_bn_act_fwd(dt, _ptr(z), _ptr(scale), _ptr(shift), _ptr(res), seqs, rows_per_seq, res_seq_rows,
+                                    res_row_mul, res_row_off, c_pad, C.byref(drop), _ptr(a), _stream()), 'bn_act_fwd')
+    return a
+
+
+def bn_act_bwd(dt, g, z, scale, shift, mean, invstd, rows, c, drop, gscale_buf):
+    """-> (dz operand-typed [rows][c_pad], d_gamma [c], d_beta [c])."""
+    c_pad = z.shape[-1]
+    dev = z.device
+    sums = torch.zeros((2, c_pad), dtype=torch.float64, device=dev)
+    dz = torch.empty_like(z)
+    dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().vp3d_bn_act_bwd_reduce(dt, _ptr(g), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd),
+                                           rows, c_pad, C.byref(drop), _ptr(sums[0]), _ptr(sums[1]), _stream()),
+              'bn_act_bwd_reduce')
+        check(lib().vp3d_bn_act_bwd_apply(dt, _ptr(g), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd),
+                                          rows, c, c_pad, C.byref(drop), _ptr(sums[0]), _ptr(sums[1]),
+                                          _ptr(gscale_buf), _ptr(dz), _ptr(dgb[0]), _ptr(dgb[1]), _stream()),
+              'bn_act_bwd_apply')
+    return dz, dgb[0], dgb[1]
+
+
+def grad_scale(dy):
+    """dy fp32 contiguous -> device buffer {gscale, 1 / gscale, max|dy|}."""
+    buf = torch.empty(4, dtype=torch.float32, device=dy.device)
+    with torch.cuda.device(dy.device):
+        check(lib().vp3d_grad_scale(_ptr(dy), dy.numel(), _ptr(buf), _stream()), 'grad_scale')
+    return buf
+
+
+def grad_pack_rows(dt, src, c_pad, gscale_buf, want_col_sum=False):
+    rows, c = src.shape
+    dst = torch.empty((rows, c_pad), dtype=torch_dtype(dt), device=src.device)
+    col_sum = torch.zeros(c, dtype=torch.float32, device=src.device) if want_col_sum else None
+    with torch.cuda.device(src.device):
+        check(lib().vp3d_grad_pack_rows(dt, _ptr(src), _ptr(dst), rows, c, c_pad, _ptr(gscale_buf), _ptr(col_sum),
+                                        _stream()), 'grad_pack_rows')
+    return dst, col_sum

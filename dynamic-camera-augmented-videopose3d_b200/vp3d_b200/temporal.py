@@ -73,7 +73,7 @@ def packed_for(model, dt):
 
 
 def _run_layer(dt, x, n, t_in, c_in_pad, w, plan, scale, shift, relu, res=None, res_t=0, out_f32=False, n_valid=None,
-               block_n=N_TILE):
+               block_n=N_TILE, stats=None):
     """x: [n][t_in][c_in_pad] operand-typed, contiguous. Returns (y [n][t_out][cols], t_out).
 
     View selection. A stride==width convolution reads `taps` consecutive frames per output frame, i.e. it is a plain
@@ -112,7 +112,8 @@ def _run_layer(dt, x, n, t_in, c_in_pad, w, plan, scale, shift, relu, res=None, 
         res_view = None if res is None else (res_c, res_t * res_c, plan.res_mul, plan.res_off)
     ops.conv_block(dt, x, a_view, w, g_taps, g_step, k_per_tap, rows_out, y, out_view, block_n=block_n,
                    scale=scale, shift=shift, relu=relu, res=res, res_view=res_view, out_f32=out_f32, n_valid=cols,
-                   out_round_tf32=(dt == native.TF32 and not final))
+                   out_round_tf32=(dt == native.TF32 and not final),
+                   stat_sum=None if stats is None else stats[0], stat_sqsum=None if stats is None else stats[1])
     return y, t_out
 
 

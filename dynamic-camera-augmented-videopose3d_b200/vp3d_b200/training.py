@@ -1,0 +1,243 @@
+"""Train-mode forward and backward of the temporal-convolution stack (TemporalModel.py:126-138 / :188-198 in train()
+mode and the autograd backward run.py:485 triggers), as one torch.autograd.Function over the whole stack.
+
+Every FLOP runs in libvp3d_b200.so:
+  forward   conv GEMM (raw output z + per-channel sum / sum of squares in the epilogue)  vp3d_conv_block_fwd
+            batch statistics -> scale/shift, running statistics                          vp3d_bn_finalize
+            a = dropout(relu(z * scale + shift)) [+ residual rows]                       vp3d_bn_act_fwd
+  backward  dz = BN/ReLU/dropout backward of the incoming gradient (two passes)           vp3d_bn_act_bwd_*
+            dW = dz^T a_in (stream-K tcgen05 GEMM, MN-major operands)                    vp3d_wgrad (+ _finish)
+            g_in = dz W (same kernel as the forward, transposed weights, residual fan-in) vp3d_conv_block_fwd
+PyTorch only allocates the buffers and records the graph edge. Gradients travel in the 16-bit operand type multiplied
+by a power-of-two scale chosen on the device from max|dL/dy| (no host synchronisation); parameter gradients come out
+as unscaled fp32 in the nn.Conv1d / nn.BatchNorm1d layouts, so torch.optim and load/state_dict work unchanged.
+"""
+import torch
+
+from . import native, ops
+from .temporal import K_ALIGN, N_TILE, LayerPlan, _round_up, _run_layer, resolve_dtype
+
+SHRINK_PAD = 128      # shrink-layer output channels are padded to one 128-row MMA tile for its weight gradient
+_step_counter = [0]
+grad_ready_hook = None  # set by vp3d_b200.ddp: called as hook(parameter, gradient) as soon as a gradient is complete
+
+
+class _Layer:
+    """Everything the backward needs about one convolution + BatchNorm + activation of the stack."""
+    __slots__ = ('conv', 'bn', 'taps', 'dilation', 'stride', 't_in', 't_out', 'c_in', 'c_in_pad', 'a_in', 'z', 'scale',
+                 'shift', 'mean', 'invstd', 'drop', 'res_of', 'res_mul', 'res_off', 'res_t', 'w_fwd')
+
+
+def _conv_w(dt, conv, rows_pad, k_pad, transpose=0):
+    return ops.pack_conv_weight(dt, conv.weight, rows_pad, k_pad, transpose=transpose)
+
+
+def _dropout_for(model, layer_idx, step):
+    p = float(model.drop.p) if model.training else 0.0
+    return ops.make_dropout(p, torch.initial_seed(), step * 64 + layer_idx)
+
+
+def _forward_stack(model, x, dt):
+    """-> (y fp32 (N, T', 3*J_out), saved layers). x: (N, T, C_in) fp32 CUDA."""
+    n, t_in, c_in = x.shape
+    strided = model._strided
+    fw = model.filter_widths
+    ch = model.expand_conv.out_channels
+    c_pad = _round_up(ch, N_TILE)
+    c_in_pad = _round_up(c_in, K_ALIGN)
+    dev = x.device
+    _step_counter[0] += 1
+    step = _step_counter[0]
+    layers = []
+
+    def conv_bn_act(idx, conv, bn, a_in, t, cin, cin_pad, plan, res=None, res_t=0, res_mul=1, res_off=0):
+        L = _Layer()
+        L.conv, L.bn = conv, bn
+        L.taps, L.dilation, L.stride = plan.taps, plan.dilation, plan.stride
+        L.c_in, L.c_in_pad, L.t_in, L.a_in = cin, cin_pad, t, a_in
+        w = _conv_w(dt, conv, c_pad, cin_pad)
+        L.w_fwd = None
+        stats = torch.zeros((2, c_pad), dtype=torch.float64, device=dev)
+        z, t_out = _run_layer(dt, a_in, n, t, cin_pad, w, plan, None, None, False, stats=stats)
+        L.z, L.t_out = z, t_out
+        L.scale, L.shift, L.mean, L.invstd = ops.bn_finalize(stats, n * t_out, bn, c_pad)
+        L.drop = _dropout_for(model, idx, step)
+        L.res_of, L.res_t, L.res_mul, L.res_off = res, res_t, res_mul, res_off
+        a = ops.bn_act_fwd(dt, z, L.scale, L.shift, n, t_out, L.drop, res=res, res_seq_rows=res_t,
+                           res_row_mul=res_mul, res_row_off=res_off)
+        layers.append(L)
+        return a, t_out
+
+    h = ops.pack_rows(dt, x.reshape(n * t_in, c_in), c_in_pad).view(n, t_in, c_in_pad)
+    plan = LayerPlan(fw[0], 1, fw[0] if strided else 1)
+    h, t = conv_bn_act(0, model.expand_conv, model.expand_bn, h, t_in, c_in, c_in_pad, plan)
+    for i in range(len(fw) - 1):
+        conv3, conv1 = model.layers_conv[2 * i], model.layers_conv[2 * i + 1]
+        taps = conv3.kernel_size[0]
+        shift = model.causal_shift[i + 1]
+        if strided:
+            p3 = LayerPlan(taps, 1, taps)
+            res_mul, res_off = taps, shift + taps // 2            # x[:, :, shift + fw//2 :: fw]   (:192)
+        else:
+            p3 = LayerPlan(taps, conv3.dilation[0], 1)
+            res_mul, res_off = 1, model.pad[i + 1] + shift        # x[:, :, pad+shift : T-pad+shift] (:132)
+        res, res_t = h, t
+        h, t = conv_bn_act(2 * i + 1, conv3, model.layers_bn[2 * i], h, t, ch, c_pad, p3)
+        h, t = conv_bn_act(2 * i + 2, conv1, model.layers_bn[2 * i + 1], h, t, ch, c_pad, LayerPlan(1), res=res,
+                           res_t=res_t, res_mul=res_mul, res_off=res_off)
+
+    n_out = model.shrink.out_channels
+    n_out_pad = _round_up(n_out, 64)
+    w_shrink = _conv_w(dt, model.shrink, n_out_pad, c_pad)
+    bias = torch.zeros(n_out_pad, dtype=torch.float32, device=dev)
+    bias[:n_out] = model.shrink.bias.detach().float()
+    ones = torch.ones(n_out_pad, dtype=torch.float32, device=dev)
+    y, t = _run_layer(dt, h, n, t, c_pad, w_shrink, LayerPlan(1), ones, bias, False, out_f32=True, n_valid=n_out,
+                      block_n=64)
+    return y, layers, h, t, c_pad
+
+
+def _views(L, n, c_pad):
+    """(dz view, input view, flat?) of one layer for the weight-gradient GEMM (vp3d_wgrad)."""
+    taps, d, s = L.taps, L.dilation, L.stride
+    if s > 1:
+        flat = L.t_in == taps * L.t_out
+        k = taps * L.c_in_pad
+        if flat:
+            return ((1, n * L.t_out, c_pad, n * L.t_out * c_pad), (n * L.t_out, k, k, n * L.t_in * L.c_in_pad), 0,
+                    L.c_in_pad)
+        return ((n, L.t_out, c_pad, L.t_out * c_pad), (L.t_out, k, k, L.t_in * L.c_in_pad), 0, L.c_in_pad)
+    if taps == 1:
+        return ((1, n * L.t_out, c_pad, n * L.t_out * c_pad), (n * L.t_in, L.c_in_pad, L.c_in_pad,
+                                                              n * L.t_in * L.c_in_pad), 0, 0)
+    return ((n, L.t_out, c_pad, L.t_out * c_pad), (L.t_in, L.c_in_pad, L.c_in_pad, L.t_in * L.c_in_pad), d, 0)
+
+
+def _weight_grad(dt, L, dz, n, c_pad, gscale):
+    dzv, av, row_step, col_step = _views(L, n, c_pad)
+    block_n = 256 if L.c_in_pad % 256 == 0 else 64
+    c_out = L.conv.out_channels
+    packed = torch.zeros((L.taps, c_pad, L.c_in_pad), dtype=torch.float32, device=dz.device)
+    ops.wgrad(dt, dz, dzv, L.a_in, av, c_pad, L.c_in_pad, L.taps, packed, b_tap_row_step=row_step,
+              b_tap_col_step=col_step, block_n=block_n)
+    return ops.wgrad_finish(packed, c_out, L.c_in, L.taps, c_pad, L.c_in_pad, gscale)
+
+
+def _data_grad(dt, L, dz, n, c_pad, fan_in=None, fan_rows=0, fan_off=0, fan_mul=1):
+    """Gradient wrt the layer input: g_in[s][t'][ci]; `fan_in` is the block-output gradient that also reaches this
+    input through the residual slice (rows t * fan_mul + fan_off of the input)."""
+    taps, d, s = L.taps, L.dilation, L.stride
+    cin_pad = L.c_in_pad
+    dev = dz.device
+    g_in = torch.empty((n, L.t_in, cin_pad), dtype=dz.dtype, device=dev)
+    if s > 1:
+        if L.t_in != taps * L.t_out:
+            raise RuntimeError('vp3d_b200: training a strided (1f) block needs t_in == %d * t_out (got %d -> %d)'
+                               % (taps, L.t_in, L.t_out))
+        wt = _conv_w(dt, L.conv, taps * cin_pad, c_pad, transpose=1)   # [(tap, ci)][co]
+        rows = n * L.t_out
+        kw = {}
+        if fan_in is not None:
+            # residual x[:, :, off::taps]: in the [rows][taps * C] view that is the column block [off*C, (off+1)*C)
+            kw = dict(res=fan_in, res_view=(c_pad, rows * c_pad, 1, 0), res_col_off=fan_off * cin_pad, res_cols=cin_pad)
+        ops.conv_block(dt, dz, (1, rows, c_pad, c_pad, rows * c_pad), wt, 1, 0, c_pad, rows, g_in,
+                       (taps * cin_pad, rows * taps * cin_pad), **kw)
+        return g_in
+    if taps == 1:
+        wt = _conv_w(dt, L.conv, cin_pad, c_pad, transpose=1)
+        rows = n * L.t_out
+        assert fan_in is None
+        ops.conv_block(dt, dz, (1, rows, c_pad, c_pad, rows * c_pad), wt, 1, 0, c_pad, rows, g_in,
+                       (cin_pad, rows * cin_pad))
+        return g_in
+    # dilated: g_in[t'] = sum_k W_k^T dz[t' - k d]; rows of dz outside [0, t_out) read as zero through TMA
+    wt = _conv_w(dt, L.conv, cin_pad, c_pad, transpose=2)               # [ci][(tap, co)]
+    kw = {}
+    if fan_in is not None:
+        # residual x[:, :, off : off + fan_rows]: input row t' receives block-output row t' - off
+        kw = dict(res=fan_in, res_view=(c_pad, fan_rows * c_pad, 1, -fan_off), res_rows=fan_rows)
+    ops.conv_block(dt, dz, (n, L.t_out, c_pad, c_pad, L.t_out * c_pad), wt, taps, -d, c_pad, L.t_in, g_in,
+                   (cin_pad, L.t_in * cin_pad), **kw)
+    return g_in
+
+
+class _StackTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, dt, x, *params):
+        y, layers, a_last, t_last, c_pad = _forward_stack(model, x, dt)
+        ctx.model, ctx.dt, ctx.layers, ctx.a_last, ctx.t_last, ctx.c_pad = model, dt, layers, a_last, t_last, c_pad
+        ctx.n = x.shape[0]
+        ctx.params = params
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        model, dt, layers, n, c_pad = ctx.model, ctx.dt, ctx.layers, ctx.n, ctx.c_pad
+        hook = grad_ready_hook
+        grads = {}
+
+        def done(param, g):
+            grads[id(param)] = g
+            if hook is not None:
+                hook(param, g)
+
+        # ---- shrink layer: y = a_last W^T + b
+        n_out = model.shrink.out_channels
+        dy2 = ops.f32c(dy).reshape(n * ctx.t_last, n_out)
+        gscale = ops.grad_scale(dy2)
+        dzs, dbias = ops.grad_pack_rows(dt, dy2, SHRINK_PAD, gscale, want_col_sum=True)
+        done(model.shrink.bias, dbias)
+        rows = n * ctx.t_last
+        packed = torch.zeros((1, SHRINK_PAD, c_pad), dtype=torch.float32, device=dy.device)
+        ops.wgrad(dt, dzs, (1, rows, SHRINK_PAD, rows * SHRINK_PAD), ctx.a_last, (rows, c_pad, c_pad, rows * c_pad),
+                  SHRINK_PAD, c_pad, 1, packed)
+        done(model.shrink.weight, ops.wgrad_finish(packed, n_out, model.shrink.in_channels, 1, SHRINK_PAD, c_pad, gscale))
+        wt = ops.pack_conv_weight(dt, model.shrink.weight, c_pad, SHRINK_PAD, transpose=1)   # [ci][co]
+        g = torch.empty((n, ctx.t_last, c_pad), dtype=dzs.dtype, device=dy.device)
+        ops.conv_block(dt, dzs, (1, rows, SHRINK_PAD, SHRINK_PAD, rows * SHRINK_PAD), wt, 1, 0, SHRINK_PAD, rows, g,
+                       (c_pad, rows * c_pad))
+
+        # ---- blocks and the expand layer, last to first. `g` is the gradient wrt the current layer's output.
+        for idx in range(len(layers) - 1, -1, -1):
+            L = layers[idx]
+            rows = n * L.t_out
+            dz, dgamma, dbeta = ops.bn_act_bwd(dt, g, L.z, L.scale, L.shift, L.mean, L.invstd, rows, L.bn.num_features,
+                                               L.drop, gscale)
+            done(L.bn.weight, dgamma)
+            done(L.bn.bias, dbeta)
+            done(L.conv.weight, _weight_grad(dt, L, dz, n, c_pad, gscale))
+            if idx == 0:
+                break  # no gradient wrt the 2-D keypoints (the reference never asks for one, run.py:458-485)
+            if L.res_of is not None:
+                # second convolution of a block: its output gradient g also feeds the residual source; that fan-in is
+                # added by the data-gradient epilogue of the block's first convolution (next iteration)
+                fan = (g, L.t_out, L.res_off, L.res_mul)
+                g = _data_grad(dt, L, dz, n, c_pad)
+            else:
+                g_block, fan_rows, fan_off, fan_mul = fan
+                g = _data_grad(dt, L, dz, n, c_pad, fan_in=g_block, fan_rows=fan_rows, fan_off=fan_off, fan_mul=fan_mul)
+        out = [grads.get(id(p)) for p in ctx.params]
+        ctx.layers = ctx.a_last = None
+        return (None, None, None) + tuple(out)
+
+
+def stack_parameters(model):
+    ps = [model.expand_conv.weight, model.expand_bn.weight, model.expand_bn.bias]
+    for conv, bn in zip(model.layers_conv, model.layers_bn):
+        ps += [conv.weight, bn.weight, bn.bias]
+    ps += [model.shrink.weight, model.shrink.bias]
+    return ps
+
+
+def forward_train(model, x):
+    """Train-mode _forward_blocks: (N, T, J*F) fp32 CUDA -> (N, T', 3*J_out) fp32 with a grad_fn."""
+    ops.require_cuda(x)
+    dt = resolve_dtype(getattr(model, 'operand_dtype', None))
+    if dt == native.TF32:
+        raise RuntimeError('vp3d_b200: the training path runs fp16 or bf16 operands (fp32 accumulation); '
+                           'set model.operand_dtype / VP3D_DTYPE to fp16 or bf16')
+    x = ops.f32c(x)
+    if not torch.is_grad_enabled():
+        with torch.no_grad():
+            return _forward_stack(model, x, dt)[0]
+    return _StackTrainFn.apply(model, dt, x, *stack_parameters(model))

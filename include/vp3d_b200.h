@@ -78,11 +78,14 @@ typedef struct vp3d_conv_args {
   const void* res;         /* residual source, element type = dtype (fp32 for TF32), or NULL */
   long long res_row_stride;
   long long res_seq_stride;
-  int res_row_mul;
+  int res_row_mul;         /* residual row = out_row * res_row_mul + res_row_off */
   int res_row_off;
+  long long res_rows;      /* > 0: residual rows outside [0, res_rows) contribute nothing (data-gradient fan-in) */
+  long long res_col_off;   /* the residual is added to output columns [res_col_off, res_col_off + res_cols) only, */
+  long long res_cols;      /* reading residual column (col - res_col_off); res_cols == 0: every column, offset 0  */
 
-  float* stat_sum;         /* optional [n_pad] accumulators (+=) of the raw output and its square over valid rows */
-  float* stat_sqsum;
+  double* stat_sum;        /* optional [n_pad] accumulators (+=) of the raw output and its square over valid rows */
+  double* stat_sqsum;      /* (train-mode BatchNorm statistics, fp32 per CTA, double across CTAs) */
 } vp3d_conv_args;
 
 int vp3d_conv_block_fwd(const vp3d_conv_args* args, void* stream);
@@ -92,7 +95,10 @@ int vp3d_pack_rows(int dtype, const float* src, void* dst, long long rows, int c
 
 /* nn.Conv1d weight (c_out, c_in, taps) fp32 (TemporalModel.py:33,102,113-118) -> packed GEMM operand.
  * transpose == 0: dst[rows_pad][taps * k_pad_per_tap], dst[n][tap * k_pad_per_tap + ci] = w[n][ci][tap]
- * transpose == 1: dst[rows_pad][k_pad_per_tap],        dst[tap * c_in + ci][co]          = w[co][ci][tap]  */
+ * transpose == 1: dst[rows_pad][k_pad_per_tap],        dst[tap * c_in_pad + ci][co]      = w[co][ci][tap]
+ *                 (c_in_pad = rows_pad / taps: data-gradient operand of a stride == width convolution)
+ * transpose == 2: dst[rows_pad][taps * k_pad_per_tap], dst[ci][tap * k_pad_per_tap + co] = w[co][ci][tap]
+ *                 (data-gradient operand of a dilated convolution, taps walked with a negative row step) */
 int vp3d_pack_conv_weight(int dtype, const float* w, void* dst, int c_out, int c_in, int taps, int rows_pad,
                           int k_pad_per_tap, int transpose, void* stream);
 
@@ -138,6 +144,81 @@ int vp3d_mpjpe_bwd(const float* pred, const float* target, const float* grad_out
                    float* grad_pred, void* stream);
 int vp3d_n_mpjpe_fwd(const float* pred, const float* target, long long n_poses, int J, void* workspace, float* out,
                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Training path (TemporalModel.py:126-138 / :188-198 in train() mode and their autograd backward, run.py:473-485).
+ * Layout: every activation / gradient matrix is channels-last [rows][c] in the 16-bit operand type (fp16 / bf16),
+ * rows = sequences * frames. Gradients travel multiplied by a power-of-two `gscale` chosen on the device from
+ * max|dL/dy| (vp3d_grad_scale) so that fp16 keeps its precision; parameter gradients are un-scaled when they are
+ * written as fp32. VP3D_TF32 is not available on the training path.
+ */
+
+/* K4  weight gradient of a convolution: dW[tap][co][ci] += sum_{s, r} dz[s][r][co] * a[s][r + b_row_off + tap *
+ * b_tap_row_step][ci + tap * b_tap_col_step]  (the autograd weight gradient of nn.Conv1d, TemporalModel.py:102,
+ * 113-118,168-181). Both operands are read MN-major (reduction over rows) straight from the channels-last matrices;
+ * work is split over (tile, row-block) units evenly across the SMs and combined with fp32 reductions into
+ * `dw_packed` [taps][co_pad][ci_pad] fp32, which the caller zero-fills. block_n (ci tile) is 256 or 64. */
+typedef struct vp3d_wgrad_args {
+  int dtype;               /* VP3D_F16 or VP3D_BF16 */
+  int block_n;
+  const void* dz;          /* [seqs][rows][co_pad] gradient wrt the convolution output */
+  long long dz_seqs, dz_rows, dz_row_stride, dz_seq_stride;
+  long long co_pad;        /* multiple of 128 */
+  const void* a;           /* layer input, viewed [seqs][a_rows][a_cols] */
+  long long a_rows, a_cols, a_row_stride, a_seq_stride;
+  long long ci_pad;        /* input channels per tap (multiple of block_n) */
+  int taps;
+  long long b_row_off;
+  int b_tap_row_step;      /* dilated convolution: tap k reads input row r + k * dilation */
+  long long b_tap_col_step;/* stride == width convolution on the reshaped view: tap k reads columns k * c_in_pad + ci */
+  float* dw_packed;        /* [taps][co_pad][ci_pad] fp32, accumulated with red.add */
+} vp3d_wgrad_args;
+int vp3d_wgrad(const vp3d_wgrad_args* args, void* stream);
+
+/* dw[co][ci][tap] = dw_packed[tap][co][ci] * gscale_buf[1]  (nn.Conv1d weight layout, fp32; gscale_buf = {gscale,
+ * 1 / gscale} on the device, NULL = 1). */
+int vp3d_wgrad_finish(const float* dw_packed, float* dw, int c_out, int c_in, int taps, int co_pad, int ci_pad,
+                      const float* gscale_buf, void* stream);
+
+/* Train-mode nn.BatchNorm1d statistics (TemporalModel.py:32,117,119 in train()): from the per-channel sum / sum of
+ * squares over `count` rows (accumulated by vp3d_conv_block_fwd) produce the forward affine scale = gamma * invstd,
+ * shift = beta - mean * scale (entries [c, c_pad) zero), save mean / invstd for the backward, and update
+ * running_mean / running_var (unbiased variance, `momentum`) and num_batches_tracked (int64, += 1) in place. */
+int vp3d_bn_finalize(const double* stat_sum, const double* stat_sqsum, long long count, const float* gamma,
+                     const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                     long long* num_batches_tracked, float* scale, float* shift, float* mean, float* invstd, int c,
+                     int c_pad, void* stream);
+
+/* Dropout description shared by forward and backward: keep-mask = Philox4x32-10(seed, stream, row, channel group)
+ * >= p; kept values are multiplied by 1 / (1 - p) (nn.Dropout, TemporalModel.py:28,127,134-135). p == 0: off. */
+typedef struct vp3d_dropout { float p; unsigned long long seed; unsigned long long stream; } vp3d_dropout;
+
+/* a[s][t][c] = dropout(relu(z[s][t][c] * scale[c] + shift[c])) + res[s][t * res_row_mul + res_row_off][c]
+ * (TemporalModel.py:127,134-135 / :189,194-195). z, a: [seqs * rows_per_seq][c_pad]; res: [seqs][res_seq_rows][c_pad]
+ * or NULL. */
+int vp3d_bn_act_fwd(int dtype, const void* z, const float* scale, const float* shift, const void* res,
+                    long long seqs, long long rows_per_seq, long long res_seq_rows, int res_row_mul, int res_row_off,
+                    int c_pad, const vp3d_dropout* drop, void* a, void* stream);
+
+/* Backward of the same chain, phase 1: with dy = g * dropout-mask / (1 - p) * [z * scale + shift > 0] and
+ * xhat = (z - mean) * invstd, accumulate sum_dy[c] += sum_rows dy, sum_dy_xhat[c] += sum_rows dy * xhat (double). */
+int vp3d_bn_act_bwd_reduce(int dtype, const void* g, const void* z, const float* scale, const float* shift,
+                           const float* mean, const float* invstd, long long rows, int c_pad,
+                           const vp3d_dropout* drop, double* sum_dy, double* sum_dy_xhat, void* stream);
+/* phase 2: dz = scale * (dy - sum_dy / rows - xhat * sum_dy_xhat / rows) in the operand type; also writes the
+ * BatchNorm parameter gradients d_gamma[c] = sum_dy_xhat * gscale_buf[1], d_beta[c] = sum_dy * gscale_buf[1]. */
+int vp3d_bn_act_bwd_apply(int dtype, const void* g, const void* z, const float* scale, const float* shift,
+                          const float* mean, const float* invstd, long long rows, int c, int c_pad,
+                          const vp3d_dropout* drop, const double* sum_dy, const double* sum_dy_xhat,
+                          const float* gscale_buf, void* dz, float* d_gamma, float* d_beta, void* stream);
+
+/* gscale_buf[0] = 2^floor(log2(64 / max|dy|)) (1 if dy == 0), gscale_buf[1] = 1 / gscale_buf[0]; gscale_buf[2] is
+ * scratch (max|dy|). dy: n fp32 values. */
+int vp3d_grad_scale(const float* dy, long long n, float* gscale_buf, void* stream);
+/* dst[r][k] = (k < c ? src[r][k] * gscale_buf[0] : 0) in the operand type; col_sum[k] += sum_r src[r][k] (fp32,
+ * unscaled: the bias gradient of the shrink layer, TemporalModel.py:33), col_sum may be NULL. */
+int vp3d_grad_pack_rows(int dtype, const float* src, void* dst, long long rows, int c, int c_pad,
+                        const float* gscale_buf, float* col_sum, void* stream);
 
 #ifdef __cplusplus
 }

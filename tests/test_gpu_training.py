@@ -1,0 +1,245 @@
+"""Training path (train-mode forward + backward of the temporal stack) on the GPU, through the C ABI, against
+ * exact fp64 contractions of the same rounded operands (K4 weight-gradient GEMM, data-gradient fan-in),
+ * the reference's own training step stored in tests/golden/temporal_small.npz (loss, prediction, every parameter
+   gradient, BatchNorm running statistics), and
+ * the CPU oracle on 1024-channel models.
+Tolerances: outputs <= 1e-3 relative (BASELINE.json); gradients are compared as relative Frobenius error per parameter
+with the bound written next to each assert (16-bit operand rounding of activations *and* gradients, fp32 accumulate).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from conftest import load_golden, state_from_npz  # noqa: E402
+from common.loss import mpjpe  # noqa: E402
+from common.models.TemporalModel import TemporalModel, TemporalModelOptimized1f  # noqa: E402
+from oracle import temporal_model as otm  # noqa: E402
+from vp3d_b200 import native, ops  # noqa: E402
+
+DT = {'fp16': native.F16, 'bf16': native.BF16}
+
+
+def rel_err(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+# ----------------------------------------------------------------------------------------------- K4 unit parity
+@pytest.mark.parametrize('dtype', ['fp16', 'bf16'])
+@pytest.mark.parametrize('seqs,rows,co,ci,taps,mode,step', [
+    (1, 64, 128, 256, 1, 'plain', 0),        # one unit
+    (1, 1000, 256, 256, 1, 'plain', 0),      # ragged row tail, several tiles
+    (1, 777, 256, 256, 3, 'strided', 0),     # stride == width layer on the reshaped view
+    (5, 150, 128, 256, 3, 'dilated', 9),     # dilated, per-sequence rows
+    (1, 5000, 1024, 64, 3, 'strided', 0),    # expand-layer geometry (narrow input tile)
+    (1, 300, 128, 1024, 1, 'plain', 0),      # shrink-layer geometry
+])
+def test_wgrad_matches_fp64(dtype, seqs, rows, co, ci, taps, mode, step):
+    dt = DT[dtype]
+    td = ops.torch_dtype(dt)
+    g = torch.Generator().manual_seed(rows + co)
+    dz = (torch.randn(seqs, rows, co, generator=g) * 0.5).to(td).cuda()
+    if mode == 'strided':
+        a = (torch.randn(seqs, rows, taps * ci, generator=g) * 0.5).to(td).cuda()
+        a_view = (rows, taps * ci, taps * ci, rows * taps * ci)
+        kw = dict(b_tap_col_step=ci)
+    elif mode == 'dilated':
+        a_rows = rows + step * (taps - 1)
+        a = (torch.randn(seqs, a_rows, ci, generator=g) * 0.5).to(td).cuda()
+        a_view = (a_rows, ci, ci, a_rows * ci)
+        kw = dict(b_tap_row_step=step)
+    else:
+        a = (torch.randn(seqs, rows, ci, generator=g) * 0.5).to(td).cuda()
+        a_view = (rows, ci, ci, rows * ci)
+        kw = {}
+    packed = torch.zeros(taps, co, ci, dtype=torch.float32, device='cuda')
+    ops.wgrad(dt, dz, (seqs, rows, co, rows * co), a, a_view, co, ci, taps, packed, block_n=256 if ci % 256 == 0 else 64,
+              **kw)
+    torch.cuda.synchronize()
+    dz64, a64 = dz.double().cpu(), a.double().cpu()
+    ref = torch.zeros(taps, co, ci, dtype=torch.float64)
+    for k in range(taps):
+        if mode == 'strided':
+            ak = a64[:, :, k * ci:(k + 1) * ci]
+        elif mode == 'dilated':
+            ak = a64[:, k * step:k * step + rows]
+        else:
+            ak = a64
+        ref[k] = torch.einsum('src,srd->cd', dz64, ak)
+    err = (packed.double().cpu() - ref).abs().max().item()
+    assert err < 2e-3 * (seqs * rows) ** 0.5, err   # fp32 accumulation / reduction order only: operands are exact
+    # nn.Conv1d layout + unscale
+    gs = torch.tensor([4.0, 0.25, 0.0, 0.0], device='cuda')
+    dw = ops.wgrad_finish(packed, co - 3, ci - 5, taps, co, ci, gs)
+    want = (ref[:, :co - 3, :ci - 5] * 0.25).permute(1, 2, 0)
+    assert dw.shape == (co - 3, ci - 5, taps)
+    assert (dw.double().cpu() - want).abs().max().item() < 1e-3 * (seqs * rows) ** 0.5
+
+
+def test_grad_scale_and_pack():
+    g = torch.Generator().manual_seed(5)
+    dy = (torch.randn(300, 51, generator=g) * 3e-5).cuda()
+    buf = ops.grad_scale(dy)
+    mx = dy.abs().max().item()
+    s = buf[0].item()
+    assert s == 2.0 ** np.floor(np.log2(64.0 / mx)) and buf[1].item() == 1.0 / s and abs(buf[2].item() - mx) < 1e-12
+    packed, colsum = ops.grad_pack_rows(native.F16, dy, 128, buf, want_col_sum=True)
+    assert packed.shape == (300, 128) and packed[:, 51:].abs().max().item() == 0
+    assert rel_err(packed[:, :51].float() / s, dy) < 1e-3
+    assert rel_err(colsum, dy.sum(0)) < 1e-5
+    zero = ops.grad_scale(torch.zeros(10, device='cuda'))
+    assert zero[0].item() == 1.0
+
+
+# ----------------------------------------------------------------------------------------------- model-level parity
+def _build(cls, sd, fw, ch, dtype, j=17, dropout=0.0, **kw):
+    m = cls(j, 2, j, fw, dropout=dropout, channels=ch, **kw)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().train()
+    m.operand_dtype = dtype
+    return m
+
+
+# bounds on the relative Frobenius error of one parameter's gradient
+GRAD_TOL = {'fp16': 1e-2, 'bf16': 6e-2}
+OUT_TOL = {'fp16': 1e-3, 'bf16': 8e-3}
+
+
+@pytest.mark.parametrize('dtype', ['fp16', 'bf16'])
+@pytest.mark.parametrize('name,cls', [('1f', TemporalModelOptimized1f), ('full', TemporalModel)])
+def test_small_train_step_against_reference_golden(name, cls, dtype):
+    z = load_golden('temporal_small.npz')
+    sd = state_from_npz(z, 'sd/')
+    x = torch.from_numpy(z['x'])
+    if name == '1f':
+        x = x[:, :27].contiguous()
+    tgt = torch.from_numpy(z['train_%s/target' % name]).cuda()
+    m = _build(cls, sd, [3, 3, 3], 32, dtype)
+    pred = m(x.cuda())
+    loss = mpjpe(pred, tgt)
+    loss.backward()
+    assert pred.shape == z['train_%s/pred' % name].shape
+    assert rel_err(pred.detach(), z['train_%s/pred' % name]) < OUT_TOL[dtype] * 3   # batch of 2: BN over 2..18 rows
+    assert abs(loss.item() - float(z['train_%s/loss' % name])) < 3e-3 * float(z['train_%s/loss' % name])
+    worst = {}
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        want = z['train_%s/grad/%s' % (name, k)]
+        assert tuple(p.grad.shape) == want.shape, k
+        worst[k] = rel_err(p.grad, want)
+    print(name, dtype, 'grad rel errs', {k: '%.2e' % v for k, v in worst.items()})
+    # BN over as few as 2 rows amplifies operand rounding (invstd ~ 1 / |z0 - z1|): looser bound than the 1024-ch test
+    assert max(worst.values()) < GRAD_TOL[dtype] * 5, worst
+    for k, b in m.named_buffers():
+        want = z['train_%s/buf/%s' % (name, k)]
+        if 'num_batches' in k:
+            assert int(b.item()) == int(want) == 1
+        else:
+            assert np.abs(b.cpu().numpy() - want).max() < (3e-3 if dtype == 'fp16' else 2e-2), k
+
+
+@pytest.mark.parametrize('causal', [False, True])
+def test_1f_243_train_step_against_oracle(causal):
+    """TemporalModelOptimized1f, 243 frames, 1024 channels, batch 64, dropout 0: loss, prediction, every gradient and
+    the running statistics against the fp32 CPU oracle (the reference's ops in the reference's order)."""
+    fw = [3, 3, 3, 3, 3]
+    sd = otm.init_state(17, 2, 17, fw, channels=1024, seed=11)
+    g = torch.Generator().manual_seed(12)
+    x = torch.rand(64, 243, 17, 2, generator=g) * 2 - 1
+    tgt = torch.randn(64, 1, 17, 3, generator=g) * 0.3
+    loss_o, pred_o, grads_o, stats_o = otm.train_step_grads(sd, x, tgt, fw, causal=causal, strided=True)
+    m = _build(TemporalModelOptimized1f, sd, fw, 1024, 'fp16', causal=causal)
+    pred = m(x.cuda())
+    loss = mpjpe(pred, tgt.cuda())
+    loss.backward()
+    assert rel_err(pred.detach(), pred_o) < 2e-3
+    assert abs(loss.item() - loss_o.item()) < 1e-3 * loss_o.item()
+    worst = {k: rel_err(p.grad, grads_o[k]) for k, p in m.named_parameters()}
+    print('1f 243 causal=%s grad rel errs' % causal, {k: '%.2e' % v for k, v in worst.items()})
+    assert max(worst.values()) < GRAD_TOL['fp16'], worst
+    for k, v in stats_o.items():
+        got = dict(m.named_buffers())[k]
+        if 'num_batches' in k:
+            assert int(got.item()) == int(v)
+        else:
+            assert (got.cpu() - v).abs().max().item() < 2e-3, k
+
+
+def test_full_model_train_step_against_oracle():
+    """The fork trains plain TemporalModel on 243-frame chunks (run.py:294-296): dilated train-mode path."""
+    fw = [3, 3, 3, 3, 3]
+    sd = otm.init_state(17, 2, 17, fw, channels=1024, seed=21)
+    g = torch.Generator().manual_seed(22)
+    x = torch.rand(6, 243 + 5, 17, 2, generator=g) * 2 - 1
+    tgt = torch.randn(6, 6, 17, 3, generator=g) * 0.3
+    loss_o, pred_o, grads_o, stats_o = otm.train_step_grads(sd, x, tgt, fw, strided=False)
+    m = _build(TemporalModel, sd, fw, 1024, 'fp16')
+    pred = m(x.cuda())
+    loss = mpjpe(pred, tgt.cuda())
+    loss.backward()
+    assert rel_err(pred.detach(), pred_o) < 2e-3
+    worst = {k: rel_err(p.grad, grads_o[k]) for k, p in m.named_parameters()}
+    print('full 243 grad rel errs', {k: '%.2e' % v for k, v in worst.items()})
+    assert max(worst.values()) < GRAD_TOL['fp16'], worst
+    for k, v in stats_o.items():
+        if 'num_batches' not in k:
+            assert (dict(m.named_buffers())[k].cpu() - v).abs().max().item() < 2e-3, k
+
+
+def test_dropout_mask_statistics_and_consistency():
+    """Dropout cannot match torch's Philox stream bit for bit: check the keep rate, the 1/(1-p) scaling,
+    determinism per (seed, step) and that the backward uses the forward's mask."""
+    dt = native.F16
+    rows, c = 4096, 1024
+    z = torch.ones(rows, c, dtype=torch.float16, device='cuda')
+    one = torch.ones(c, device='cuda')
+    zero = torch.zeros(c, device='cuda')
+    d = ops.make_dropout(0.25, 1234, 7)
+    a = ops.bn_act_fwd(dt, z, one, zero, 1, rows, d)
+    kept = (a > 0).float().mean().item()
+    assert abs(kept - 0.75) < 2e-3, kept
+    assert torch.all((a == 0) | ((a.float() - 1 / 0.75).abs() < 1e-3))
+    assert torch.equal(a, ops.bn_act_fwd(dt, z, one, zero, 1, rows, d))
+    a2 = ops.bn_act_fwd(dt, z, one, zero, 1, rows, ops.make_dropout(0.25, 1234, 8))
+    assert not torch.equal(a, a2)
+    # per-channel and per-row keep rates are unbiased too
+    assert (a > 0).float().mean(0).sub(0.75).abs().max().item() < 0.04
+    assert (a > 0).float().mean(1).sub(0.75).abs().max().item() < 0.07
+    g = torch.ones(rows, c, dtype=torch.float16, device='cuda')
+    gs = torch.tensor([1.0, 1.0, 0, 0], device='cuda')
+    # mean = 0, invstd = 0 -> xhat = 0: dz = scale * (dy - mean(dy)); dy must be nonzero exactly where a is
+    sums = torch.zeros(2, c, dtype=torch.float64, device='cuda')
+    import ctypes as C
+    native.check(native.lib().vp3d_bn_act_bwd_reduce(dt, g.data_ptr(), z.data_ptr(), one.data_ptr(), zero.data_ptr(),
+                                                    zero.data_ptr(), zero.data_ptr(), rows, c, C.byref(d),
+                                                    sums[0].data_ptr(), sums[1].data_ptr(), None), 'reduce')
+    torch.cuda.synchronize()
+    assert rel_err(sums[0], a.float().sum(0)) < 1e-3
+    assert sums[1].abs().max().item() == 0
+
+
+def test_train_step_with_dropout_runs_and_learns():
+    fw = [3, 3, 3]
+    torch.manual_seed(0)
+    m = TemporalModelOptimized1f(17, 2, 17, fw, dropout=0.25, channels=1024).cuda().train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3, amsgrad=True)
+    g = torch.Generator().manual_seed(1)
+    x = (torch.rand(256, 27, 17, 2, generator=g) * 2 - 1).cuda()
+    tgt = (torch.randn(256, 1, 17, 3, generator=g) * 0.2).cuda()
+    losses = []
+    for _ in range(12):
+        opt.zero_grad()
+        loss = mpjpe(m(x), tgt)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(np.isfinite(losses)), losses
+    assert losses[-1] < 0.7 * losses[0], losses
+    assert int(m.expand_bn.num_batches_tracked.item()) == 12
+    # eval after training uses the running statistics through the folded kernels
+    m.eval()
+    with torch.no_grad():
+        y = m(x)
+    assert torch.isfinite(y).all()
