@@ -12,6 +12,11 @@ sequences of 4096+242 frames (262,144 output frames) per GPU. Prints ONE JSON li
 With --impl reference the CPU port itself is the thing measured (the reference is Python and cannot travel to the GPU
 box; oracle/ is its restatement, pinned to the reference by tests/golden).
 Multi-GPU: sequences are sharded over ranks, no collective on the data path (weak scaling: 64 sequences per GPU).
+
+The same line carries a `train` object: BASELINE.json configs[2], one TemporalModelOptimized1f 243-frame training step
+(per-frame dynamic-camera projection of world-space joints -> forward -> mpjpe -> backward -> Adam amsgrad), batch
+1024 per GPU, gradients averaged over ranks with NCCL when N > 1 (vp3d_b200.ddp). `--mode train` prints that as the
+headline instead (metric "1f 243f training throughput", samples/s).
 """
 import argparse
 import json
@@ -36,6 +41,11 @@ OUT_FRAMES = 4096
 RF = 243
 METRIC = '243f TemporalModel inference throughput'
 UNIT = 'frames/s'
+TRAIN_FLOP_PER_SAMPLE = 1040787456  # fwd 352,569,344 + dgrad 335,648,768 + wgrad 352,569,344 (1f, J = 17)
+TRAIN_BATCH = 1024
+PROJ_BYTES_PER_FRAME = 17 * 20 + 64  # 12 B read + 8 B write per joint, 64 B camera record per frame
+H36M_CAM0 = [2.2900989, 2.2875624, 0.025083065, 0.028902981, -0.20709892, 0.24777518, -0.0030751503, -0.00097569887,
+             -0.0014244716]          # h36m_dataset.py:19-29 camera 0, normalised, with lens distortion
 
 
 def load_peaks():
@@ -60,7 +70,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                          '-lms', '100', '-i', str(self.gpu)], stdout=subprocess.PIPE,
+                                          '-lms', '20', '-i', str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -130,6 +140,26 @@ def cpu_port_frames_per_s(seqs=4, out_frames=4096, repeats=3):
         seqs, out_frames, repeats, torch.__version__)
 
 
+def cpu_port_train_samples_per_s(batch=32, repeats=2):
+    """The CPU oracle's training step (forward + mpjpe + autograd backward of the 1f model, dropout 0, no optimiser)
+    on all host threads; bounded sample."""
+    from oracle import temporal_model as otm
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = oracle_state()
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand(batch, RF, 17, 2, generator=g) * 2 - 1
+    tgt = torch.randn(batch, 1, 17, 3, generator=g) * 0.3
+    otm.train_step_grads(sd, x, tgt, FW, strided=True)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        otm.train_step_grads(sd, x, tgt, FW, strided=True)
+        times.append(time.perf_counter() - t0)
+    return batch / min(times), cores, 'batch %d, forward + mpjpe + backward, best of %d, torch %s CPU' % (
+        batch, repeats, torch.__version__)
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -160,16 +190,213 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
+class LaunchTimer:
+    """Wraps C-ABI entry points with CUDA events (on torch's current stream, which is the stream the library launches
+    on) to count our launches and time kernel families during a separate, instrumented pass."""
+
+    def __init__(self, lib, names):
+        self.lib, self.names = lib, names
+        self.orig = {n: getattr(lib, n) for n in names}
+        self.events = {n: [] for n in names}
+
+    def __enter__(self):
+        for n in self.names:
+            setattr(self.lib, n, self._wrap(n))
+        return self
+
+    def _wrap(self, n):
+        fn, ev = self.orig[n], self.events[n]
+
+        def call(*a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*a)
+            e1.record()
+            ev.append((e0, e1))
+            return rc
+        return call
+
+    def __exit__(self, *exc):
+        for n in self.names:
+            setattr(self.lib, n, self.orig[n])
+
+    def ms(self, *names):
+        return sum(a.elapsed_time(b) for n in names for a, b in self.events[n])
+
+    def count(self, *names):
+        return sum(len(self.events[n]) for n in (names or self.names))
+
+
+def synthetic_training_batch(rank, batch):
+    """World-space joints of `batch` 243-frame windows with one camera pose per frame: root =
+    smooth random walk 2-6 m in front of the camera, joints = root + low-pass N(0, 0.25 m) offsets; camera = unit
+    quaternion near identity with smooth drift, smooth translation; H36M camera-0 intrinsics with distortion."""
+    g = torch.Generator().manual_seed(4321 + rank)
+    T, J = RF, 17
+
+    def smooth(shape, scale, k=31):
+        v = torch.randn(shape, generator=g) * scale
+        flat = v.reshape(shape[0], shape[1], -1).permute(0, 2, 1)
+        ker = torch.ones(flat.shape[1], 1, k) / k
+        out = torch.nn.functional.conv1d(torch.nn.functional.pad(flat, (k // 2, k // 2), mode='replicate'), ker,
+                                         groups=flat.shape[1])
+        return out.permute(0, 2, 1).reshape(shape)
+
+    root = torch.zeros(batch, T, 1, 3)
+    root[..., 2] = 4.0 + smooth((batch, T, 1), 3.0).clamp(-2, 2)
+    root[..., :2] = smooth((batch, T, 1, 2), 1.5)
+    world = root + smooth((batch, T, J, 3), 0.8)
+    q = torch.tensor([1.0, 0, 0, 0]).view(1, 1, 4) + smooth((batch, T, 4), 0.3)
+    q = q / q.norm(dim=-1, keepdim=True)
+    t = smooth((batch, T, 3), 0.5)
+    cam = torch.tensor(H36M_CAM0).repeat(batch, 1)
+    return world.contiguous(), q.contiguous(), t.contiguous(), cam.contiguous()
+
+
+def bench_train(args, rank, world, dev, steps, warm):
+    """One training step of BASELINE configs[2] per iteration. Returns a dict (rank 0) with samples/s resident and e2e,
+    the tensor-core roofline over the GEMM launches and the HBM roofline of the projection kernel."""
+    import torch.distributed as dist
+    from common.camera import world_to_camera, world_to_image
+    from common.loss import mpjpe
+    from common.models.TemporalModel import TemporalModelOptimized1f
+    from vp3d_b200 import ddp, native
+
+    batch = args.batch
+    torch.manual_seed(1234)
+    model = TemporalModelOptimized1f(17, 2, 17, FW, dropout=0.25, channels=1024)
+    model.load_state_dict(oracle_state())
+    model = model.to(dev).train()
+    model.operand_dtype = args.dtype if args.dtype != 'tf32' else 'fp16'
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, amsgrad=True)       # run.py:662
+    sync = None
+    if world > 1:
+        ddp.broadcast_parameters(model)
+        sync = ddp.enable_grad_sync()
+
+    Wh, qh, th, camh = [v.pin_memory() for v in synthetic_training_batch(rank, batch)]
+    Wd, qd, td, camd = [v.to(dev) for v in (Wh, qh, th, camh)]
+    mid = RF // 2
+    with torch.no_grad():   # target: camera-space pose of the centre frame, root-relative (run.py:72-74)
+        Xc = world_to_camera(Wd[:, mid:mid + 1].contiguous(), qd[:, mid:mid + 1].contiguous(),
+                             td[:, mid:mid + 1].contiguous())
+        tgt = (Xc - Xc[:, :, :1]).contiguous()
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def step(W, q, t, cam):
+        _, x2d = world_to_image(W, q, t, cam, return_camera_space=False)
+        opt.zero_grad(set_to_none=True)
+        loss = mpjpe(model(x2d), tgt)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def step_resident():
+        return step(Wd, qd, td, camd)
+
+    def step_e2e():
+        W, q, t, cam = [v.to(dev, non_blocking=True) for v in (Wh, qh, th, camh)]
+        loss = step(W, q, t, cam)
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_host)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warm):
+        first_loss = step_resident()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        last_loss = step_resident()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+
+    lib = native.lib()
+    gemm = ('vp3d_conv_block_fwd', 'vp3d_wgrad')
+    bn = ('vp3d_bn_finalize', 'vp3d_bn_act_fwd', 'vp3d_bn_act_bwd_reduce', 'vp3d_bn_act_bwd_apply')
+    other = ('vp3d_project_points', 'vp3d_mpjpe_fwd', 'vp3d_mpjpe_bwd', 'vp3d_pack_rows', 'vp3d_pack_conv_weight',
+             'vp3d_wgrad_finish', 'vp3d_grad_scale', 'vp3d_grad_pack_rows')
+    inst = min(steps, 3)
+    with LaunchTimer(lib, gemm + bn + other) as lt:
+        for _ in range(inst):
+            step_resident()
+        torch.cuda.synchronize()
+    gemm_ms, bn_ms, proj_ms = lt.ms(*gemm) / inst, lt.ms(*bn) / inst, lt.ms('vp3d_project_points') / inst
+    conv_ms, wgrad_ms = lt.ms('vp3d_conv_block_fwd') / inst, lt.ms('vp3d_wgrad') / inst
+    mpjpe_ms = lt.ms('vp3d_mpjpe_fwd', 'vp3d_mpjpe_bwd') / inst
+    n_launch, n_gemm = lt.count() // inst, lt.count(*gemm) // inst
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(steps):
+        step_e2e()
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+
+    if world > 1:
+        tt = torch.tensor([ms, ms_e2e, gemm_ms, proj_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, ms_e2e, gemm_ms, proj_ms = [float(v) for v in tt.tolist()]
+        ddp.disable_grad_sync()
+    if rank != 0:
+        return None
+    peaks = load_peaks()
+    total = batch * world * steps
+    achieved = TRAIN_FLOP_PER_SAMPLE * batch / (gemm_ms * 1e-3) / 1e12
+    proj_gbs = PROJ_BYTES_PER_FRAME * batch * RF / (proj_ms * 1e-3) / 1e9
+    return {
+        'metric': '1f 243f training throughput', 'value': total / (ms * 1e-3), 'unit': 'samples/s',
+        'ms_per_step': ms / steps, 'scaling': 'weak', 'dtype': model.operand_dtype,
+        'config': {'workload': 'TemporalModelOptimized1f 3,3,3,3,3 training step, batch %d per GPU, dropout 0.25, '
+                               'per-frame camera projection (H36M cam-0 distortion) -> fwd -> mpjpe -> bwd -> Adam '
+                               'amsgrad (BASELINE configs[2])' % batch,
+                   'grad_exchange': 'none (1 GPU)' if world == 1 else 'NCCL all-reduce (avg) of fp32 gradients, large '
+                                    'tensors overlapped with backward, %d collectives, %.1f MB per step'
+                                    % (sync.collectives // max(1, warm + steps + inst + 2 + steps),
+                                       sync.bytes_reduced / max(1, warm + steps + inst + 2 + steps) / 1e6),
+                   'bn': 'per-replica batch statistics'},
+        'e2e': {'value': total / (ms_e2e * 1e-3), 'unit': 'samples/s', 'ms_per_step': ms_e2e / steps,
+                'h2d_bytes_per_step': sum(v.numel() * 4 for v in (Wh, qh, th, camh)), 'd2h_bytes_per_step': 4},
+        'gpu_launches': n_launch * steps,
+        'loss_first_last': [float(first_loss), float(last_loss)],
+        'roofline': {'bound': 'tensor', 'kernel': 'conv_gemm_kernel + wgrad_gemm_kernel (%d launches per step)' % n_gemm,
+                     'achieved': achieved, 'peak': peaks['sustained'], 'unit': 'TFLOP/s',
+                     'frac': achieved / peaks['sustained'], 'peak_source': peaks['source'] + ', sustained dense bf16',
+                     'traffic': None, 'algorithmic_flop_per_sample': TRAIN_FLOP_PER_SAMPLE,
+                     'gemm_ms_per_step': gemm_ms, 'conv_fwd_dgrad_ms': conv_ms, 'wgrad_ms': wgrad_ms,
+                     'bn_act_ms_per_step': bn_ms, 'kernel_share_of_step': gemm_ms / (ms / steps)},
+        'projection_roofline': {'bound': 'hbm', 'kernel': 'project_points_kernel', 'achieved': proj_gbs,
+                                'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': proj_gbs / peaks['hbm_gbs'],
+                                'ms_per_launch': proj_ms, 'algorithmic_bytes_per_frame': PROJ_BYTES_PER_FRAME,
+                                'frames_per_launch': batch * RF},
+        'mpjpe_ms_per_step': mpjpe_ms,
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--dtype', default=os.environ.get('VP3D_DTYPE', 'fp16'), choices=['fp16', 'bf16', 'tf32'])
     ap.add_argument('--seqs', type=int, default=SEQS_PER_GPU)
     ap.add_argument('--frames', type=int, default=OUT_FRAMES)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--mode', default='all', choices=['all', 'infer', 'train'],
+                    help='all: inference headline + train object; train: training headline only')
+    ap.add_argument('--batch', type=int, default=TRAIN_BATCH, help='training samples per GPU per step')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
@@ -192,6 +419,19 @@ def main():
 
     warm = max(args.warmup, 3)
     steps = max(args.steps, 1)
+    if args.mode == 'train':
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        tr = bench_train(args, rank, world, dev, steps, warm)
+        if rank == 0:
+            tr.update({'n_gpus': world, 'steps': steps, 'warmup': warm, 'higher_is_better': True, 'vs_baseline': None,
+                       'data': 'synthetic', 'clocks': sampler.stop()})
+            print(json.dumps(tr))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     seqs, out_frames = args.seqs, args.frames
     t_in = out_frames + RF - 1
 
@@ -327,6 +567,18 @@ def main():
         if not args.no_cpu_baseline:
             v, cores, sample = cpu_port_frames_per_s()
             line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
+    train = None
+    if args.mode == 'all':
+        del x_dev, x_host, y_host
+        torch.cuda.empty_cache()
+        train = bench_train(args, rank, world, dev, max(steps, 10), warm)
+    if rank == 0:
+        if train is not None:
+            if not args.no_cpu_baseline:
+                v, cores, sample = cpu_port_train_samples_per_s()
+                train['cpu_baseline'] = {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+                                         'sample': sample}
+            line['train'] = train
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -468,17 +468,17 @@ int vp3d_bn_act_bwd_reduce(int dtype, const void* g, const void* z, const float*
 }
 
 int vp3d_bn_act_bwd_apply(int dtype, const void* g, const void* z, const float* scale, const float* shift,
-                          const float* mean, const float* invstd, long long rows, int c, int c_pad,
+                          const float* mean, const float* invstd, long long rows, long long count, int c, int c_pad,
                           const vp3d_dropout* drop, const double* sum_dy, const double* sum_dy_xhat,
                           const float* gscale_buf, void* dz, float* d_gamma, float* d_beta, void* stream) {
   if (int rc = check_ew(dtype, c_pad, "bn_act_bwd_apply")) return rc;
   if (!g || !z || !scale || !shift || !mean || !invstd || !sum_dy || !sum_dy_xhat || !dz || rows <= 0 || c <= 0 ||
-      c > c_pad)
+      c > c_pad || count < rows)
     return fail(VP3D_ERR_INVALID, "bn_act_bwd_apply args");
   if ((d_gamma == nullptr) != (d_beta == nullptr)) return fail(VP3D_ERR_INVALID, "bn_act_bwd_apply d_gamma / d_beta");
   DeviceInfo* dev = nullptr;
   if (int rc = device_info(&dev)) return rc;
-  cudaError_t e = vp3d::launch_bn_act_bwd_apply(dtype, g, z, scale, shift, mean, invstd, rows, c, c_pad, drop_of(drop),
+  cudaError_t e = vp3d::launch_bn_act_bwd_apply(dtype, g, z, scale, shift, mean, invstd, rows, count, c, c_pad, drop_of(drop),
                                                 sum_dy, sum_dy_xhat, gscale_buf, dz, d_gamma, d_beta, dev->sm_count,
                                                 static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "bn_act_bwd_apply launch");

@@ -85,8 +85,8 @@ cudaError_t launch_bn_act_bwd_reduce(int dtype, const void* g, const void* z, co
                                      const DropoutParams& dp, double* sum_dy, double* sum_dy_xhat, int sm_count,
                                      cudaStream_t stream);
 cudaError_t launch_bn_act_bwd_apply(int dtype, const void* g, const void* z, const float* scale, const float* shift,
-                                    const float* mean, const float* invstd, long long rows, int c, int c_pad,
-                                    const DropoutParams& dp, const double* sum_dy, const double* sum_dy_xhat,
+                                    const float* mean, const float* invstd, long long rows, long long count, int c,
+                                    int c_pad, const DropoutParams& dp, const double* sum_dy, const double* sum_dy_xhat,
                                     const float* gscale_buf, void* dz, float* d_gamma, float* d_beta, int sm_count,
                                     cudaStream_t stream);
 cudaError_t launch_grad_scale(const float* dy, long long n, float* gscale_buf, int sm_count, cudaStream_t stream);

@@ -255,12 +255,12 @@ template <int DT>
 __global__ void __launch_bounds__(kEwThreads)
 bn_act_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z, const float* __restrict__ scale,
                         const float* __restrict__ shift, const float* __restrict__ mean,
-                        const float* __restrict__ invstd, long long rows, int c, int groups, DropoutParams dp,
-                        const double* __restrict__ sum_dy, const double* __restrict__ sum_dy_xhat,
+                        const float* __restrict__ invstd, long long rows, long long count, int c, int groups,
+                        DropoutParams dp, const double* __restrict__ sum_dy, const double* __restrict__ sum_dy_xhat,
                         const float* __restrict__ gscale_buf, uint4* __restrict__ dz, float* __restrict__ d_gamma,
                         float* __restrict__ d_beta) {
   const DropCtx drop = make_drop(dp);
-  const float inv_n = 1.f / (float)rows;
+  const float inv_n = 1.f / (float)count;
   // BatchNorm parameter gradients: one block writes them (un-scaled)
   if (blockIdx.x == 0 && d_gamma != nullptr) {
     const float inv = gscale_buf != nullptr ? gscale_buf[1] : 1.f;
@@ -400,20 +400,20 @@ cudaError_t launch_bn_act_bwd_reduce(int dtype, const void* g, const void* z, co
 }
 
 cudaError_t launch_bn_act_bwd_apply(int dtype, const void* g, const void* z, const float* scale, const float* shift,
-                                    const float* mean, const float* invstd, long long rows, int c, int c_pad,
-                                    const DropoutParams& dp, const double* sum_dy, const double* sum_dy_xhat,
+                                    const float* mean, const float* invstd, long long rows, long long count, int c,
+                                    int c_pad, const DropoutParams& dp, const double* sum_dy, const double* sum_dy_xhat,
                                     const float* gscale_buf, void* dz, float* d_gamma, float* d_beta, int sm_count,
                                     cudaStream_t stream) {
   const int groups = c_pad / 8;
   const int grid = rows_grid(rows * groups, sm_count, 8);
   if (dtype == VP3D_F16)
     bn_act_bwd_apply_kernel<VP3D_F16><<<grid, kEwThreads, 0, stream>>>(
-        static_cast<const uint4*>(g), static_cast<const uint4*>(z), scale, shift, mean, invstd, rows, c, groups, dp,
-        sum_dy, sum_dy_xhat, gscale_buf, static_cast<uint4*>(dz), d_gamma, d_beta);
+        static_cast<const uint4*>(g), static_cast<const uint4*>(z), scale, shift, mean, invstd, rows, count, c, groups,
+        dp, sum_dy, sum_dy_xhat, gscale_buf, static_cast<uint4*>(dz), d_gamma, d_beta);
   else if (dtype == VP3D_BF16)
     bn_act_bwd_apply_kernel<VP3D_BF16><<<grid, kEwThreads, 0, stream>>>(
-        static_cast<const uint4*>(g), static_cast<const uint4*>(z), scale, shift, mean, invstd, rows, c, groups, dp,
-        sum_dy, sum_dy_xhat, gscale_buf, static_cast<uint4*>(dz), d_gamma, d_beta);
+        static_cast<const uint4*>(g), static_cast<const uint4*>(z), scale, shift, mean, invstd, rows, count, c, groups,
+        dp, sum_dy, sum_dy_xhat, gscale_buf, static_cast<uint4*>(dz), d_gamma, d_beta);
   else
     return cudaErrorInvalidValue;
   return cudaGetLastError();

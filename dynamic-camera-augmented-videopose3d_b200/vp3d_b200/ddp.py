@@ -1,0 +1,112 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), torch.distributed over NCCL / NVLink.
+
+The reference is single-process; this is new capability along the two axes the path shards on:
+
+* inference -- sequences are independent: `shard_range` gives each rank a contiguous slice, there is NO collective on
+  the data path;
+* training -- the batch is sharded; the one exchange per step is the average of the fp32 parameter gradients.
+  `GradSync` hooks the backward of vp3d_b200.training: every large gradient (a convolution weight, 4-12 MB) is
+  all-reduced asynchronously on NCCL's stream the moment its weight-gradient GEMM has been issued, so the transfer
+  overlaps the remaining backward GEMMs of the earlier layers; the ~30 small tensors (BatchNorm affine parameters,
+  shrink layer) travel as one flat bucket at the end. BatchNorm batch statistics stay per replica by default (like
+  torch DDP without SyncBatchNorm); `enable_sync_bn` all-reduces the per-channel sums instead (18 tiny latency-bound
+  exchanges per step). `broadcast_buffers` makes running statistics identical before a checkpoint.
+"""
+import torch
+import torch.distributed as dist
+
+from . import training
+
+LARGE_BYTES = 1 << 20
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous, balanced [lo, hi) slice of n_items for `rank` (first n_items % world ranks get one extra)."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class GradSync:
+    """Averages parameter gradients over the ranks of `group`, overlapped with the backward pass."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        backend = dist.get_backend(group)
+        self._avg = dist.ReduceOp.AVG if backend == 'nccl' else None   # gloo has no AVG: SUM then scale
+        self._pending = []
+        self._small = []
+        self.bytes_reduced = 0
+        self.collectives = 0
+
+    # -- hook protocol used by training._StackTrainFn.backward ---------------------------------------------------
+    def __call__(self, param, grad):
+        if self.world == 1:
+            return
+        if grad.numel() * grad.element_size() >= LARGE_BYTES:
+            self._launch(grad)
+        else:
+            self._small.append(grad)
+
+    def _launch(self, t):
+        op = self._avg if self._avg is not None else dist.ReduceOp.SUM
+        work = dist.all_reduce(t, op=op, group=self.group, async_op=True)
+        self._pending.append((work, t))
+        self.bytes_reduced += t.numel() * t.element_size()
+        self.collectives += 1
+
+    def finish(self):
+        """Flushes the small-tensor bucket and makes the current stream wait for every outstanding all-reduce."""
+        if self.world == 1:
+            return
+        flat = None
+        if self._small:
+            flat = torch.cat([g.reshape(-1) for g in self._small])
+            self._launch(flat)
+        for work, t in self._pending:
+            work.wait()
+            if self._avg is None:
+                t.div_(self.world)
+        if flat is not None:
+            off = 0
+            for g in self._small:
+                n = g.numel()
+                g.copy_(flat[off:off + n].view_as(g))
+                off += n
+        self._pending, self._small = [], []
+
+
+_active = None
+
+
+def enable_grad_sync(group=None):
+    """Install gradient averaging for every vp3d_b200 training backward of this process. Returns the GradSync."""
+    global _active
+    _active = GradSync(group)
+    training.grad_ready_hook = _active
+    training.grad_finish_hook = _active.finish
+    return _active
+
+
+def disable_grad_sync():
+    global _active
+    _active = None
+    training.grad_ready_hook = None
+    training.grad_finish_hook = None
+
+
+def enable_sync_bn(group=None, on=True):
+    """Train-mode BatchNorm statistics over the global batch (all ranks) instead of per replica."""
+    training.sync_bn_group = (group if group is not None else dist.group.WORLD) if on else None
+
+
+def broadcast_buffers(model, src=0, group=None):
+    """Running statistics / num_batches_tracked of rank `src` to every rank (call before saving a checkpoint)."""
+    for b in model.buffers():
+        dist.broadcast(b, src=src, group=group)
+
+
+def broadcast_parameters(model, src=0, group=None):
+    for p in model.parameters():
+        dist.broadcast(p.data, src=src, group=group)

@@ -76,7 +76,7 @@ _SIGNATURES = {
                         [C.POINTER(Dropout), C.c_void_p, C.c_void_p]),
     'vp3d_bn_act_bwd_reduce': (C.c_int, [C.c_int] + [C.c_void_p] * 6 + [C.c_longlong, C.c_int, C.POINTER(Dropout),
                                                                        C.c_void_p, C.c_void_p, C.c_void_p]),
-    'vp3d_bn_act_bwd_apply': (C.c_int, [C.c_int] + [C.c_void_p] * 6 + [C.c_longlong, C.c_int, C.c_int,
+    'vp3d_bn_act_bwd_apply': (C.c_int, [C.c_int] + [C.c_void_p] * 6 + [C.c_longlong, C.c_longlong, C.c_int, C.c_int,
                                                                       C.POINTER(Dropout)] + [C.c_void_p] * 7),
     'vp3d_grad_scale': (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     'vp3d_grad_pack_rows': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p,

@@ -153,14 +153,16 @@ def pack_rows(dt, src, c_pad):
     return dst
 
 
-def pack_conv_weight(dt, w, rows_pad, k_pad_per_tap, transpose=False):
+def pack_conv_weight(dt, w, rows_pad, k_pad_per_tap, transpose=0):
+    """transpose: 0 forward operand, 1 / 2 data-gradient operands (see vp3d_pack_conv_weight)."""
     w = f32c(w.detach())
     c_out, c_in, taps = w.shape
-    k_total = k_pad_per_tap if transpose else taps * k_pad_per_tap
+    transpose = int(transpose)
+    k_total = k_pad_per_tap if transpose == 1 else taps * k_pad_per_tap
     dst = torch.empty((rows_pad, k_total), dtype=torch_dtype(dt), device=w.device)
     with torch.cuda.device(w.device):
         check(lib().vp3d_pack_conv_weight(dt, _ptr(w), _ptr(dst), c_out, c_in, taps, rows_pad, k_pad_per_tap,
-                                          1 if transpose else 0, _stream()), 'pack_conv_weight')
+                                          transpose, _stream()), 'pack_conv_weight')
     return dst
 
 
@@ -272,8 +274,10 @@ def bn_act_fwd(dt, z, scale, shift, seqs, rows_per_seq, drop, res=None, res_seq_
     return a
 
 
-def bn_act_bwd(dt, g, z, scale, shift, mean, invstd, rows, c, drop, gscale_buf):
-    """-> (dz operand-typed [rows][c_pad], d_gamma [c], d_beta [c])."""
+def bn_act_bwd(dt, g, z, scale, shift, mean, invstd, rows, c, drop, gscale_buf, count=None, group=None):
+    """-> (dz operand-typed [rows][c_pad], d_gamma [c], d_beta [c]). `count` (>= rows) is the number of rows the
+    batch statistics were taken over; with `group` the per-channel sums are all-reduced first (SyncBN: the parameter
+    gradients that come out are then already summed over the group)."""
     c_pad = z.shape[-1]
     dev = z.device
     sums = torch.zeros((2, c_pad), dtype=torch.float64, device=dev)
@@ -283,8 +287,11 @@ def bn_act_bwd(dt, g, z, scale, shift, mean, invstd, rows, c, drop, gscale_buf):
         check(lib().vp3d_bn_act_bwd_reduce(dt, _ptr(g), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd),
                                            rows, c_pad, C.byref(drop), _ptr(sums[0]), _ptr(sums[1]), _stream()),
               'bn_act_bwd_reduce')
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(sums, group=group)
         check(lib().vp3d_bn_act_bwd_apply(dt, _ptr(g), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd),
-                                          rows, c, c_pad, C.byref(drop), _ptr(sums[0]), _ptr(sums[1]),
+                                          rows, int(count or rows), c, c_pad, C.byref(drop), _ptr(sums[0]), _ptr(sums[1]),
                                           _ptr(gscale_buf), _ptr(dz), _ptr(dgb[0]), _ptr(dgb[1]), _stream()),
               'bn_act_bwd_apply')
     return dz, dgb[0], dgb[1]

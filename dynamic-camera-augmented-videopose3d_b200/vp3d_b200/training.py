@@ -19,13 +19,17 @@ from .temporal import K_ALIGN, N_TILE, LayerPlan, _round_up, _run_layer, resolve
 
 SHRINK_PAD = 128      # shrink-layer output channels are padded to one 128-row MMA tile for its weight gradient
 _step_counter = [0]
-grad_ready_hook = None  # set by vp3d_b200.ddp: called as hook(parameter, gradient) as soon as a gradient is complete
+grad_ready_hook = None   # set by vp3d_b200.ddp: called as hook(parameter, gradient) as soon as a gradient is issued
+grad_finish_hook = None  # ... and once at the end of the backward (waits for the outstanding all-reduces)
+sync_bn_group = None     # process group over which train-mode BatchNorm statistics are summed (None: per replica)
+debug_keep_saved = False  # tests: keep the last forward's saved per-layer tensors in `debug_last_saved`
+debug_last_saved = None
 
 
 class _Layer:
     """Everything the backward needs about one convolution + BatchNorm + activation of the stack."""
     __slots__ = ('conv', 'bn', 'taps', 'dilation', 'stride', 't_in', 't_out', 'c_in', 'c_in_pad', 'a_in', 'z', 'scale',
-                 'shift', 'mean', 'invstd', 'drop', 'res_of', 'res_mul', 'res_off', 'res_t', 'w_fwd')
+                 'shift', 'mean', 'invstd', 'drop', 'res_of', 'res_mul', 'res_off', 'res_t', 'w_fwd', 'count')
 
 
 def _conv_w(dt, conv, rows_pad, k_pad, transpose=0):
@@ -60,7 +64,13 @@ def _forward_stack(model, x, dt):
         stats = torch.zeros((2, c_pad), dtype=torch.float64, device=dev)
         z, t_out = _run_layer(dt, a_in, n, t, cin_pad, w, plan, None, None, False, stats=stats)
         L.z, L.t_out = z, t_out
-        L.scale, L.shift, L.mean, L.invstd = ops.bn_finalize(stats, n * t_out, bn, c_pad)
+        count = n * t_out
+        if sync_bn_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(stats, group=sync_bn_group)
+            count *= dist.get_world_size(sync_bn_group)
+        L.count = count
+        L.scale, L.shift, L.mean, L.invstd = ops.bn_finalize(stats, count, bn, c_pad)
         L.drop = _dropout_for(model, idx, step)
         L.res_of, L.res_t, L.res_mul, L.res_off = res, res_t, res_mul, res_off
         a = ops.bn_act_fwd(dt, z, L.scale, L.shift, n, t_out, L.drop, res=res, res_seq_rows=res_t,
@@ -165,6 +175,9 @@ class _StackTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, dt, x, *params):
         y, layers, a_last, t_last, c_pad = _forward_stack(model, x, dt)
+        if debug_keep_saved:
+            global debug_last_saved
+            debug_last_saved = layers
         ctx.model, ctx.dt, ctx.layers, ctx.a_last, ctx.t_last, ctx.c_pad = model, dt, layers, a_last, t_last, c_pad
         ctx.n = x.shape[0]
         ctx.params = params
@@ -202,7 +215,7 @@ class _StackTrainFn(torch.autograd.Function):
             L = layers[idx]
             rows = n * L.t_out
             dz, dgamma, dbeta = ops.bn_act_bwd(dt, g, L.z, L.scale, L.shift, L.mean, L.invstd, rows, L.bn.num_features,
-                                               L.drop, gscale)
+                                               L.drop, gscale, count=L.count, group=sync_bn_group)
             done(L.bn.weight, dgamma)
             done(L.bn.bias, dbeta)
             done(L.conv.weight, _weight_grad(dt, L, dz, n, c_pad, gscale))
@@ -216,6 +229,8 @@ class _StackTrainFn(torch.autograd.Function):
             else:
                 g_block, fan_rows, fan_off, fan_mul = fan
                 g = _data_grad(dt, L, dz, n, c_pad, fan_in=g_block, fan_rows=fan_rows, fan_off=fan_off, fan_mul=fan_mul)
+        if grad_finish_hook is not None:
+            grad_finish_hook()
         out = [grads.get(id(p)) for p in ctx.params]
         ctx.layers = ctx.a_last = None
         return (None, None, None) + tuple(out)

@@ -205,10 +205,12 @@ int vp3d_bn_act_fwd(int dtype, const void* z, const float* scale, const float* s
 int vp3d_bn_act_bwd_reduce(int dtype, const void* g, const void* z, const float* scale, const float* shift,
                            const float* mean, const float* invstd, long long rows, int c_pad,
                            const vp3d_dropout* drop, double* sum_dy, double* sum_dy_xhat, void* stream);
-/* phase 2: dz = scale * (dy - sum_dy / rows - xhat * sum_dy_xhat / rows) in the operand type; also writes the
- * BatchNorm parameter gradients d_gamma[c] = sum_dy_xhat * gscale_buf[1], d_beta[c] = sum_dy * gscale_buf[1]. */
+/* phase 2: dz = scale * (dy - sum_dy / count - xhat * sum_dy_xhat / count) in the operand type (count = rows the
+ * statistics were taken over: `rows`, or the global row count under SyncBN after the caller all-reduced the sums);
+ * also writes the BatchNorm parameter gradients d_gamma[c] = sum_dy_xhat * gscale_buf[1], d_beta[c] = sum_dy *
+ * gscale_buf[1]. */
 int vp3d_bn_act_bwd_apply(int dtype, const void* g, const void* z, const float* scale, const float* shift,
-                          const float* mean, const float* invstd, long long rows, int c, int c_pad,
+                          const float* mean, const float* invstd, long long rows, long long count, int c, int c_pad,
                           const vp3d_dropout* drop, const double* sum_dy, const double* sum_dy_xhat,
                           const float* gscale_buf, void* dz, float* d_gamma, float* d_beta, void* stream);
 

@@ -174,3 +174,58 @@ def train_step_grads(sd, x, target, filter_widths, causal=False, strided=True, m
     loss.backward()
     grads = {k: v.grad.detach() for k, v in params.items()}
     return loss.detach(), pred.detach(), grads, new_stats
+
+
+def _ste_round(v, dtype):
+    """Value rounded to `dtype`, gradient passed straight through (the GPU backward treats operand rounding the same
+    way: it differentiates the fp32 formulas and only rounds what it stores)."""
+    return v + (v.to(dtype).to(torch.float32) - v).detach()
+
+
+def train_step_grads_lowp(sd, x, target, filter_widths, causal=False, strided=True, dtype=torch.float16, masks=None):
+    """train_step_grads with the *forward* rounding points of the CUDA training path emulated on the CPU: GEMM
+    operands (input, weights) and every stored matrix (raw convolution output z, activation a) rounded to `dtype`,
+    batch statistics taken from the unrounded fp32 accumulators, fp32 everywhere else. Gradients of a ReLU network
+    are discontinuous in the activations -- a pre-activation that rounding moves across zero flips a mask bit -- so
+    the fp32 oracle is only a loose bound for low-precision gradients. Even this emulation differs from the GPU in
+    fp32 summation order, which moves a few stored values by one 16-bit ulp and flips a few more bits; `masks` (one
+    bool tensor (N, C, T') per BatchNorm layer, in forward order, taken from the GPU's own saved pre-activations) pins
+    the ReLU pattern so that the comparison isolates the backward arithmetic. Used by tests/ only."""
+    from . import loss as oloss
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
+              if v.dtype.is_floating_point and 'running_' not in k}
+    plan = make_plan(filter_widths, causal, False, strided)
+    rnd = lambda v: _ste_round(v, dtype)
+
+    mask_iter = iter(masks) if masks is not None else None
+
+    def bn_act(z, prefix, res=None):
+        mean = z.mean(dim=(0, 2), keepdim=True)
+        var = z.var(dim=(0, 2), unbiased=False, keepdim=True)
+        scale = params[prefix + '.weight'].view(1, -1, 1) / torch.sqrt(var + BN_EPS)
+        shift = params[prefix + '.bias'].view(1, -1, 1) - mean * scale
+        pre = rnd(z) * scale + shift
+        y = F.relu(pre) if mask_iter is None else pre * next(mask_iter).to(pre.dtype)
+        return rnd(y if res is None else y + res)
+
+    n, t = x.shape[0], x.shape[1]
+    h = rnd(x.reshape(n, t, -1).permute(0, 2, 1))
+    h = bn_act(F.conv1d(h, rnd(params['expand_conv.weight']), None, stride=plan['expand_stride']), 'expand_bn')
+    for i, blk in enumerate(plan['blocks']):
+        pad, shift = plan['pad'][i + 1], plan['causal_shift'][i + 1]
+        if strided:
+            fw = plan['filter_widths'][i + 1]
+            res = h[:, :, shift + fw // 2::fw]
+        else:
+            res = h[:, :, pad + shift: h.shape[2] - pad + shift]
+        h = bn_act(F.conv1d(h, rnd(params['layers_conv.%d.weight' % (2 * i)]), None, stride=blk['stride'],
+                            dilation=blk['dilation']), 'layers_bn.%d' % (2 * i))
+        h = bn_act(F.conv1d(h, rnd(params['layers_conv.%d.weight' % (2 * i + 1)]), None), 'layers_bn.%d' % (2 * i + 1),
+                   res=res)
+    h = F.conv1d(h, rnd(params['shrink.weight']), params['shrink.bias'])
+    j_out = sd['shrink.weight'].shape[0] // 3
+    pred = h.permute(0, 2, 1).reshape(n, -1, j_out, 3)
+    loss = oloss.mpjpe(pred, target)
+    loss.backward()
+    grads = {k: v.grad.detach() for k, v in params.items()}
+    return loss.detach(), pred.detach(), grads
