@@ -289,7 +289,7 @@ def bench_train(args, rank, world, dev, steps, warm):
         loss = mpjpe(model(x2d), tgt)
         loss.backward()
         opt.step()
-        return loss
+        return loss.detach()
 
     def step_resident():
         return step(Wd, qd, td, camd)
@@ -297,7 +297,7 @@ def bench_train(args, rank, world, dev, steps, warm):
     def step_e2e():
         W, q, t, cam = [v.to(dev, non_blocking=True) for v in (Wh, qh, th, camh)]
         loss = step(W, q, t, cam)
-        loss_host.copy_(loss.detach(), non_blocking=True)
+        loss_host.copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(loss_host)
 

@@ -148,7 +148,13 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
   if (a->a_seqs <= 0 || a->a_rows <= 0 || a->rows_out <= 0) return fail(VP3D_ERR_INVALID, "empty problem");
   if (a->taps < 1 || a->k_per_tap <= 0 || a->k_per_tap % kblk != 0)
     return fail(VP3D_ERR_INVALID, "k_per_tap (%lld) must be a positive multiple of %lld", a->k_per_tap, kblk);
-  if (a->k_total != (long long)a->taps * a->k_per_tap) return fail(VP3D_ERR_INVALID, "k_total != taps * k_per_tap");
+  if (!a->w_mn_major && a->k_total != (long long)a->taps * a->k_per_tap)
+    return fail(VP3D_ERR_INVALID, "k_total != taps * k_per_tap");
+  if (a->w_mn_major) {
+    if (a->dtype == VP3D_TF32) return fail(VP3D_ERR_INVALID, "w_mn_major needs fp16 / bf16 operands");
+    if (a->w_row_stride < a->n_pad + (long long)(a->taps - 1) * a->w_tap_col_step || (a->w_row_stride * 2) % 16 != 0)
+      return fail(VP3D_ERR_INVALID, "w_mn_major: bad w_row_stride");
+  }
   if (a->a_kdim < a->k_per_tap) return fail(VP3D_ERR_INVALID, "a_kdim (%lld) < k_per_tap", a->a_kdim);
   if (a->n_pad <= 0 || a->n_pad % a->block_n != 0) return fail(VP3D_ERR_INVALID, "n_pad must be a multiple of block_n");
   if ((reinterpret_cast<uintptr_t>(a->a) & 15) || (reinterpret_cast<uintptr_t>(a->w) & 15) ||
@@ -183,11 +189,27 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
     cuuint32_t box[3] = {(cuuint32_t)kblk, 128, 1};
     if (int rc = encode_map(&tmA, a->dtype, 3, a->a, dims, strides, box, "activations")) return rc;
   }
-  {
+  if (a->w_mn_major) {
+    cuuint64_t dims[2] = {(cuuint64_t)a->w_row_stride, (cuuint64_t)a->k_per_tap};
+    cuuint64_t strides[1] = {(cuuint64_t)(a->w_row_stride * eb)};
+    cuuint32_t box[2] = {64, 64};
+    if (int rc = encode_map(&tmB, a->dtype, 2, a->w, dims, strides, box, "weights (MN-major)")) return rc;
+  } else {
     cuuint64_t dims[2] = {(cuuint64_t)a->k_total, (cuuint64_t)a->n_pad};
     cuuint64_t strides[1] = {(cuuint64_t)(a->k_total * eb)};
     cuuint32_t box[2] = {(cuuint32_t)kblk, (cuuint32_t)a->block_n};
     if (int rc = encode_map(&tmB, a->dtype, 2, a->w, dims, strides, box, "weights")) return rc;
+  }
+
+  CUtensorMap tmC;
+  memset(&tmC, 0, sizeof(tmC));
+  if (!a->out_f32) {
+    // output view [n_pad columns][rows_out][sequences]; one store = 64 columns x 32 rows (one epilogue warp)
+    cuuint64_t dims[3] = {(cuuint64_t)a->n_pad, (cuuint64_t)a->rows_out, (cuuint64_t)a->a_seqs};
+    cuuint64_t strides[2] = {(cuuint64_t)(a->out_row_stride * 2), (cuuint64_t)(a->out_seq_stride * 2)};
+    if (a->a_seqs == 1) strides[1] = (cuuint64_t)(a->rows_out * a->out_row_stride * 2);
+    cuuint32_t box[3] = {64, 32, 1};
+    if (int rc = encode_map(&tmC, a->dtype, 3, a->out, dims, strides, box, "output")) return rc;
   }
 
   vp3d::ConvGemmParams p;
@@ -200,6 +222,7 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
   p.kblocks_per_tap = (int)(a->k_per_tap / kblk);
   p.tap_row_step = a->tap_row_step;
   p.a_row_off = (int)a->a_row_off;
+  p.b_tap_col_step = (int)a->w_tap_col_step;
   p.scale = a->scale;
   p.shift = a->shift;
   p.relu = a->relu;
@@ -215,6 +238,7 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
   p.out_seq_stride = a->out_seq_stride;
   p.out_row_stride = a->out_row_stride;
   p.out_f32 = a->out_f32;
+  p.out_tma = a->out_f32 ? 0 : 1;
   p.n_valid = (int)(a->out_f32 ? a->n_valid : a->n_pad);
   p.out_round_tf32 = a->out_round_tf32;
   p.stat_sum = a->stat_sum;
@@ -225,7 +249,7 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
   int grid = (int)(total_tiles < dev->sm_count ? total_tiles : dev->sm_count);
   // a grid that is a multiple of n_tiles keeps every CTA on one column tile (weights and BN statistics stay put)
   if (grid > p.n_tiles && grid % p.n_tiles != 0) grid -= grid % p.n_tiles;
-  cudaError_t e = vp3d::launch_conv_gemm(a->dtype, a->block_n, tmA, tmB, p, grid, static_cast<cudaStream_t>(stream));
+  cudaError_t e = vp3d::launch_conv_gemm(a->dtype, a->block_n, a->w_mn_major, tmA, tmB, tmC, p, grid, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "conv_gemm launch");
   return VP3D_OK;
 }
@@ -350,8 +374,7 @@ int vp3d_wgrad(const vp3d_wgrad_args* a, void* stream) {
     return fail(VP3D_ERR_INVALID, "wgrad: pointers must be 16-byte aligned");
   if ((a->dz_row_stride * 2) % 16 || (a->dz_seq_stride * 2) % 16 || (a->a_row_stride * 2) % 16 || (a->a_seq_stride * 2) % 16)
     return fail(VP3D_ERR_INVALID, "wgrad: strides must be multiples of 16 bytes");
-  if (a->a_cols < a->ci_pad + (long long)(a->taps - 1) * a->b_tap_col_step)
-    return fail(VP3D_ERR_INVALID, "wgrad: a_cols too small for taps * column step");
+  /* a_cols may be smaller than ci_pad (+ tap offsets): TMA zero-fills the missing input columns */
   DeviceInfo* dev = nullptr;
   if (int rc = device_info(&dev)) return rc;
 
@@ -377,27 +400,45 @@ int vp3d_wgrad(const vp3d_wgrad_args* a, void* stream) {
   p.num_tiles = a->taps * p.co_tiles * p.ci_tiles;
   p.seqs = (int)a->dz_seqs;
   p.kb_per_seq = (int)((a->dz_rows + 63) / 64);
+  {
+    // Number of row slices S: items = tiles * S are dealt round-robin to one CTA per SM. Cost model in units of one
+    // 64-row block of MMAs: waves(S) * (rows blocks per slice + flush), flush ~ 8 blocks (one 128 x BN fp32 reduction).
+    const long long kb_all = (long long)p.seqs * p.kb_per_seq;
+    const long long flush = 8;
+    long long best = -1;
+    int best_s = 1;
+    for (int s_try = 1; s_try <= 64 && s_try <= kb_all; ++s_try) {
+      const long long items = (long long)p.num_tiles * s_try;
+      const long long waves = (items + dev->sm_count - 1) / dev->sm_count;
+      const long long cost = waves * ((kb_all + s_try - 1) / s_try + flush);
+      if (best < 0 || cost < best) {
+        best = cost;
+        best_s = s_try;
+      }
+    }
+    p.num_slices = best_s;
+  }
   p.b_row_off = (int)a->b_row_off;
   p.b_tap_row_step = a->b_tap_row_step;
   p.b_tap_col_step = (int)a->b_tap_col_step;
   p.out = a->dw_packed;
   p.out_tap_stride = a->co_pad * a->ci_pad;
   p.out_row_stride = a->ci_pad;
-  const long long units = (long long)p.num_tiles * p.seqs * p.kb_per_seq;
-  const int grid = (int)(units < dev->sm_count ? units : dev->sm_count);
+  const long long items = (long long)p.num_tiles * p.num_slices;
+  const int grid = (int)(items < dev->sm_count ? items : dev->sm_count);
   cudaError_t e = vp3d::launch_wgrad(a->dtype, a->block_n, tmA, tmB, p, grid, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "wgrad launch");
   return VP3D_OK;
 }
 
-int vp3d_wgrad_finish(const float* dw_packed, float* dw, int c_out, int c_in, int taps, int co_pad, int ci_pad,
-                      const float* gscale_buf, void* stream) {
-  if (!dw_packed || !dw || c_out <= 0 || c_in <= 0 || taps <= 0 || co_pad < c_out || ci_pad < c_in)
+int vp3d_wgrad_finish(const float* dw_packed, float* dw, int c_out, int c_in, int taps, long long tap_stride,
+                      long long row_stride, const float* gscale_buf, void* stream) {
+  if (!dw_packed || !dw || c_out <= 0 || c_in <= 0 || taps <= 0 || row_stride < c_in || tap_stride < 0)
     return fail(VP3D_ERR_INVALID, "wgrad_finish args");
   DeviceInfo* dev = nullptr;
   if (int rc = device_info(&dev)) return rc;
-  cudaError_t e = vp3d::launch_wgrad_finish(dw_packed, dw, c_out, c_in, taps, co_pad, ci_pad, gscale_buf, dev->sm_count,
-                                            static_cast<cudaStream_t>(stream));
+  cudaError_t e = vp3d::launch_wgrad_finish(dw_packed, dw, c_out, c_in, taps, tap_stride, row_stride, gscale_buf,
+                                            dev->sm_count, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "wgrad_finish launch");
   return VP3D_OK;
 }
@@ -450,6 +491,17 @@ int vp3d_bn_act_fwd(int dtype, const void* z, const float* scale, const float* s
                                           res_row_off, c_pad, drop_of(drop), a, dev->sm_count,
                                           static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "bn_act_fwd launch");
+  return VP3D_OK;
+}
+
+int vp3d_col_stats(int dtype, const void* z, long long rows, int c_pad, double* sum, double* sqsum, void* stream) {
+  if (int rc = check_ew(dtype, c_pad, "col_stats")) return rc;
+  if (!z || !sum || !sqsum || rows <= 0) return fail(VP3D_ERR_INVALID, "col_stats args");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_col_stats(dtype, z, rows, c_pad, sum, sqsum, dev->sm_count,
+                                         static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "col_stats launch");
   return VP3D_OK;
 }
 

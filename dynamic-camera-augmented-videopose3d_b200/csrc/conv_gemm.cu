@@ -32,9 +32,11 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : 8;
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int kOutStageBytes = 4 * 32 * 128;  // per epilogue warp: 32 rows x 128 B staging for the TMA store
   static constexpr int kBarBytes = 256;
   static constexpr int kStatBytes = 4 * BN * 2 * 4;  // per epilogue warp: BN x {sum, sum of squares} fp32
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kStatBytes + 1024;  // +1024: alignment slack
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kOutStageBytes + kBarBytes + kStatBytes + 1024;  // +1024: alignment slack
 };
 
 template <int DT>
@@ -90,25 +92,41 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, const ConvGemmParams&
   return c;
 }
 
-template <int DT, int BN>
+// MN-major SWIZZLE_128B operand (weights read as [k rows][n columns], n contiguous): 64-column groups `lbo` bytes
+// apart, 8-row groups 1024 B apart -- what BN / 64 TMA boxes of [64 k-rows][64 columns] produce.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc_b(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// BMN = true: the weight operand is MN-major, i.e. the *forward-packed* weights [c_out][taps * c_in] are consumed as
+// W^T by the data-gradient GEMM without a transposed copy (16-bit operand types only).
+template <int DT, int BN, bool BMN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const ConvGemmParams p) {
+                 const __grid_constant__ CUtensorMap tmC, const ConvGemmParams p) {
   using Cfg = GemmCfg<BN>;
   using ET = ElemTraits<DT>;
+  static_assert(!BMN || ET::kBytes == 2, "MN-major weights: fp16 / bf16 only");
   constexpr int kElemsPerKBlock = kTileKBytes / ET::kBytes;  // 64 (16-bit) or 32 (tf32)
   constexpr int kMmasPerStage = 4;                           // 32 bytes of K per tcgen05.mma
-  constexpr uint32_t kIdesc = make_instr_desc(ET::kFormat, kBlockM, BN);
+  constexpr uint32_t kIdesc = make_instr_desc(ET::kFormat, kBlockM, BN) | (BMN ? (1u << 16) : 0u);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* out_stage = smem + Cfg::kStages * Cfg::kStageBytes;  // 1024-aligned: stages are multiples of 1 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + Cfg::kOutStageBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + Cfg::kStages;
   uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  float* stat_smem = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes);
+  float* stat_smem = reinterpret_cast<float*>(out_stage + Cfg::kOutStageBytes + Cfg::kBarBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -118,6 +136,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.out_tma) tma_prefetch_desc(&tmC);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -152,7 +171,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           tma_load_3d(sa, &tmA, &full_bar[stage], kc * kElemsPerKBlock,
                       tc.t0 + p.a_row_off + tap * p.tap_row_step, tc.seq);
-          tma_load_2d(sa + Cfg::kABytes, &tmB, &full_bar[stage], kb * kElemsPerKBlock, tc.n0 * BN);
+          if (BMN) {
+            // rows kc*64.. of the [c_out][taps * c_in] weights, columns of this tap's N tile, 64 at a time
+#pragma unroll
+            for (int g = 0; g < BN / 64; ++g)
+              tma_load_2d(sa + Cfg::kABytes + g * 8192, &tmB, &full_bar[stage],
+                          tap * p.b_tap_col_step + tc.n0 * BN + g * 64, kc * kElemsPerKBlock);
+          } else {
+            tma_load_2d(sa + Cfg::kABytes, &tmB, &full_bar[stage], kb * kElemsPerKBlock, tc.n0 * BN);
+          }
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -177,14 +204,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t adesc = make_kmajor_sw128_desc(sa);
-          const uint64_t bdesc = make_kmajor_sw128_desc(sa + Cfg::kABytes);
+          const uint64_t bdesc = BMN ? make_mnmajor_sw128_desc_b(sa + Cfg::kABytes, 8192)
+                                     : make_kmajor_sw128_desc(sa + Cfg::kABytes);
 #pragma unroll
           for (int k = 0; k < kMmasPerStage; ++k) {
-            // advance 32 bytes of K inside the swizzle span: +2 in the (address >> 4) field
+            // advance 32 bytes of K inside the swizzle span: +2 in the (address >> 4) field; an MN-major operand
+            // advances 16 k-rows = two 8-row groups = 2048 bytes
+            const uint64_t bk = BMN ? (uint64_t)(128 * k) : (uint64_t)(2 * k);
             if (ET::kBytes == 2)
-              umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0);
+              umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + bk, kIdesc, (kb | k) != 0);
             else
-              umma_tf32_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0);
+              umma_tf32_ss(d_tmem, adesc + 2 * k, bdesc + bk, kIdesc, (kb | k) != 0);
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) {
@@ -330,18 +360,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int j = 0; j < 32; ++j)
                 if (col0 + j < p.n_valid) o[j] = f[j];
             }
-          } else {
-            // element-typed output (fp16 / bf16); activation buffers are always padded to the tile width
-            uint4* o = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + out_off + col0);
+          }
+        }
+        if (!p.out_f32) {
+          // element-typed output (fp16 / bf16): the warp's 32 rows x 64 columns are staged in shared memory in the
+          // SWIZZLE_128B layout (conflict-free 16-byte stores) and leave as ONE coalesced TMA store per 64 columns;
+          // TMA clips rows past the end of the sequence, so no row mask is needed here
+          constexpr int D16 = (DT == VP3D_TF32) ? VP3D_F16 : DT;
+          uint8_t* my_stage = out_stage + quad * (32 * 128);
+          if ((c & 1) == 0) {
+            if (lane == 0) tma_store_wait_read<0>();  // the previous store of this warp has drained the buffer
+            __syncwarp();
+          }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 w;
-              constexpr int D16 = (DT == VP3D_TF32) ? VP3D_F16 : DT;
-              w.x = pack2(f[8 * j + 0], f[8 * j + 1], std::integral_constant<int, D16>{});
-              w.y = pack2(f[8 * j + 2], f[8 * j + 3], std::integral_constant<int, D16>{});
-              w.z = pack2(f[8 * j + 4], f[8 * j + 5], std::integral_constant<int, D16>{});
-              w.w = pack2(f[8 * j + 6], f[8 * j + 7], std::integral_constant<int, D16>{});
-              o[j] = w;
+          for (int j = 0; j < 4; ++j) {
+            const int chunk = (c & 1) * 4 + j;
+            st_shared_v4(my_stage + lane * 128 + ((chunk ^ (lane & 7)) << 4),
+                         pack2(f[8 * j + 0], f[8 * j + 1], std::integral_constant<int, D16>{}),
+                         pack2(f[8 * j + 2], f[8 * j + 3], std::integral_constant<int, D16>{}),
+                         pack2(f[8 * j + 4], f[8 * j + 5], std::integral_constant<int, D16>{}),
+                         pack2(f[8 * j + 6], f[8 * j + 7], std::integral_constant<int, D16>{}));
+          }
+          if ((c & 1) == 1) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&tmC, my_stage, tc.n0 * BN + (c >> 1) * 64, tc.t0 + quad * 32, tc.seq);
+              tma_store_commit();
             }
           }
         }
@@ -355,6 +400,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       stat_flush();
     }
+    if (lane == 0) tma_store_wait_all<0>();  // every output tile of this warp has reached global memory
   }
 
   tcgen05_fence_before();
@@ -365,31 +411,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int DT, int BN>
-static cudaError_t launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int grid,
-                              cudaStream_t stream) {
+template <int DT, int BN, bool BMN>
+static cudaError_t launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                              const ConvGemmParams& p, int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;  // per-process; idempotent, so a benign race at worst repeats the call
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<DT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<DT, BN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  conv_gemm_kernel<DT, BN><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  conv_gemm_kernel<DT, BN, BMN><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
   return cudaGetLastError();
 }
 
-cudaError_t launch_conv_gemm(int dtype, int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                             const ConvGemmParams& p, int grid, cudaStream_t stream) {
+cudaError_t launch_conv_gemm(int dtype, int block_n, int w_mn_major, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                             const CUtensorMap& tmC, const ConvGemmParams& p, int grid, cudaStream_t stream) {
+  if (w_mn_major) {
+    if (block_n == 256 && dtype == VP3D_F16) return launch_one<VP3D_F16, 256, true>(tmA, tmB, tmC, p, grid, stream);
+    if (block_n == 256 && dtype == VP3D_BF16) return launch_one<VP3D_BF16, 256, true>(tmA, tmB, tmC, p, grid, stream);
+    if (block_n == 64 && dtype == VP3D_F16) return launch_one<VP3D_F16, 64, true>(tmA, tmB, tmC, p, grid, stream);
+    if (block_n == 64 && dtype == VP3D_BF16) return launch_one<VP3D_BF16, 64, true>(tmA, tmB, tmC, p, grid, stream);
+    return cudaErrorInvalidValue;
+  }
   if (block_n == 256) {
-    if (dtype == VP3D_F16) return launch_one<VP3D_F16, 256>(tmA, tmB, p, grid, stream);
-    if (dtype == VP3D_BF16) return launch_one<VP3D_BF16, 256>(tmA, tmB, p, grid, stream);
-    if (dtype == VP3D_TF32) return launch_one<VP3D_TF32, 256>(tmA, tmB, p, grid, stream);
+    if (dtype == VP3D_F16) return launch_one<VP3D_F16, 256, false>(tmA, tmB, tmC, p, grid, stream);
+    if (dtype == VP3D_BF16) return launch_one<VP3D_BF16, 256, false>(tmA, tmB, tmC, p, grid, stream);
+    if (dtype == VP3D_TF32) return launch_one<VP3D_TF32, 256, false>(tmA, tmB, tmC, p, grid, stream);
   } else if (block_n == 64) {
-    if (dtype == VP3D_F16) return launch_one<VP3D_F16, 64>(tmA, tmB, p, grid, stream);
-    if (dtype == VP3D_BF16) return launch_one<VP3D_BF16, 64>(tmA, tmB, p, grid, stream);
-    if (dtype == VP3D_TF32) return launch_one<VP3D_TF32, 64>(tmA, tmB, p, grid, stream);
+    if (dtype == VP3D_F16) return launch_one<VP3D_F16, 64, false>(tmA, tmB, tmC, p, grid, stream);
+    if (dtype == VP3D_BF16) return launch_one<VP3D_BF16, 64, false>(tmA, tmB, tmC, p, grid, stream);
+    if (dtype == VP3D_TF32) return launch_one<VP3D_TF32, 64, false>(tmA, tmB, tmC, p, grid, stream);
   }
   return cudaErrorInvalidValue;
 }

@@ -87,6 +87,23 @@ bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, 
   }
 }
 
+// transpose == 0 fast path: thread = (n, ci_pad index); reads the `taps` adjacent fp32 of w[n][ci][:] (a warp reads one
+// contiguous span) and writes one element into each tap's K block (contiguous across the warp)
+template <int DT>
+__global__ void __launch_bounds__(256)
+pack_weight_fwd_kernel(const float* __restrict__ w, void* __restrict__ dst, int c_out, int c_in, int taps, int rows_pad,
+                       int k_pad_per_tap) {
+  const int total = rows_pad * k_pad_per_tap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n = i / k_pad_per_tap;
+    const int ci = i - n * k_pad_per_tap;
+    const bool ok = n < c_out && ci < c_in;
+    const float* src = w + ((long long)n * c_in + ci) * taps;
+    const long long d0 = (long long)n * taps * k_pad_per_tap + ci;
+    for (int tap = 0; tap < taps; ++tap) store_elem<DT>(dst, d0 + (long long)tap * k_pad_per_tap, ok ? __ldg(src + tap) : 0.f);
+  }
+}
+
 static int ew_grid(long long total, int sm_count) {
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)sm_count * 8;
@@ -108,6 +125,18 @@ cudaError_t launch_pack_rows(int dtype, const float* src, void* dst, long long r
 cudaError_t launch_pack_weight(int dtype, const float* w, void* dst, int c_out, int c_in, int taps, int rows_pad,
                                int k_pad_per_tap, int transpose, int sm_count, cudaStream_t stream) {
   const long long k_total = transpose == 1 ? k_pad_per_tap : (long long)taps * k_pad_per_tap;
+  if (transpose == 0 && (long long)rows_pad * k_pad_per_tap < (1LL << 31)) {
+    const int g = ew_grid((long long)rows_pad * k_pad_per_tap, sm_count);
+    if (dtype == VP3D_F16)
+      pack_weight_fwd_kernel<VP3D_F16><<<g, 256, 0, stream>>>(w, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap);
+    else if (dtype == VP3D_BF16)
+      pack_weight_fwd_kernel<VP3D_BF16><<<g, 256, 0, stream>>>(w, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap);
+    else if (dtype == VP3D_TF32)
+      pack_weight_fwd_kernel<VP3D_TF32><<<g, 256, 0, stream>>>(w, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap);
+    else
+      return cudaErrorInvalidValue;
+    return cudaGetLastError();
+  }
   const int grid = ew_grid((long long)rows_pad * k_total, sm_count);
   if (dtype == VP3D_F16)
     pack_weight_kernel<VP3D_F16><<<grid, 256, 0, stream>>>(w, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap, transpose);

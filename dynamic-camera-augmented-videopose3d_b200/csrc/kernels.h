@@ -19,6 +19,7 @@ struct ConvGemmParams {
   int kblocks_per_tap;  // 128-byte K blocks per tap
   int tap_row_step;     // input-row distance between consecutive taps (dilation)
   int a_row_off;        // input row of tap 0 for output row 0 (may be negative: TMA zero-fills)
+  int b_tap_col_step;   // MN-major weights only: weight columns per tap (c_in_pad of the forward layer)
 
   const float* scale;   // per output channel, nullptr = identity
   const float* shift;
@@ -37,6 +38,7 @@ struct ConvGemmParams {
   long long out_seq_stride;
   long long out_row_stride;
   int out_f32;          // 1: fp32 output (shrink layer / tf32 activations), 0: activation element type
+  int out_tma;          // 16-bit outputs leave through TMA stores (tmC); fp32 outputs use direct stores
   int n_valid;          // real output channels (<= n_pad); only consulted on the fp32 path
   int out_round_tf32;   // fp32 outputs are rounded (RN) to TF32 precision for a following TF32 layer
 
@@ -44,8 +46,8 @@ struct ConvGemmParams {
   double* stat_sqsum;
 };
 
-cudaError_t launch_conv_gemm(int dtype, int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                             const ConvGemmParams& p, int grid, cudaStream_t stream);
+cudaError_t launch_conv_gemm(int dtype, int block_n, int w_mn_major, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                             const CUtensorMap& tmC, const ConvGemmParams& p, int grid, cudaStream_t stream);
 
 // Launch parameters of wgrad_gemm_kernel (see wgrad.cu).
 struct WgradParams {
@@ -54,6 +56,7 @@ struct WgradParams {
   int ci_tiles;         // ci_pad / BLOCK_N
   int seqs;
   int kb_per_seq;       // ceil(rows per sequence / 64)
+  int num_slices;       // split of the row axis; items = tiles x slices, dealt round-robin to the CTAs
   int b_row_off;        // input row read against gradient row 0 by tap 0
   int b_tap_row_step;   // extra input rows per tap (dilation)
   int b_tap_col_step;   // extra input columns per tap (stride == width layers on the reshaped view)
@@ -63,8 +66,8 @@ struct WgradParams {
 };
 cudaError_t launch_wgrad(int dtype, int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const WgradParams& p,
                          int grid, cudaStream_t stream);
-cudaError_t launch_wgrad_finish(const float* packed, float* dw, int c_out, int c_in, int taps, int co_pad, int ci_pad,
-                                const float* gscale_buf, int sm_count, cudaStream_t stream);
+cudaError_t launch_wgrad_finish(const float* packed, float* dw, int c_out, int c_in, int taps, long long tap_stride,
+                                long long row_stride, const float* gscale_buf, int sm_count, cudaStream_t stream);
 
 // Counter-based dropout description (train.cu).
 struct DropoutParams {
@@ -80,6 +83,8 @@ cudaError_t launch_bn_act_fwd(int dtype, const void* z, const float* scale, cons
                               long long seqs, long long rows_per_seq, long long res_seq_rows, int res_row_mul,
                               int res_row_off, int c_pad, const DropoutParams& dp, void* a, int sm_count,
                               cudaStream_t stream);
+cudaError_t launch_col_stats(int dtype, const void* z, long long rows, int c_pad, double* sum, double* sqsum,
+                             int sm_count, cudaStream_t stream);
 cudaError_t launch_bn_act_bwd_reduce(int dtype, const void* g, const void* z, const float* scale, const float* shift,
                                      const float* mean, const float* invstd, long long rows, int c_pad,
                                      const DropoutParams& dp, double* sum_dy, double* sum_dy_xhat, int sm_count,

@@ -131,53 +131,141 @@ bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sq
   }
 }
 
-// ---------------------------------------------------------------------------------------------- forward apply
-// grid-stride over (row, channel group); groups = c_pad / 8
+// ---------------------------------------------------------------------------------------------- row-walking kernels
+// Shared shape of the four HBM-bound kernels below: blockDim.x = kEwThreads threads, thread i of a block owns channel
+// group (blockIdx.y * kEwThreads + i) -- 8 consecutive channels, one 16-byte vector -- keeps that group's per-channel
+// constants in registers and walks rows blockIdx.x, blockIdx.x + gridDim.x, ... four at a time (all loads of the
+// four rows are issued before the first use). A warp reads 512 contiguous bytes per row.
+constexpr int kRowUnroll = 4;
+
+__device__ __forceinline__ void load8(const float* p, int grp, float (&o)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p) + 2 * grp);
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 2 * grp + 1);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+
 template <int DT>
 __global__ void __launch_bounds__(kEwThreads)
 bn_act_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                   const uint4* __restrict__ res, long long rows, long long rows_per_seq, long long res_seq_rows,
                   int res_row_mul, int res_row_off, int groups, DropoutParams dp, uint4* __restrict__ a) {
+  const int grp = blockIdx.y * kEwThreads + threadIdx.x;
+  if (grp >= groups) return;
   const DropCtx drop = make_drop(dp);
-  const long long total = rows * groups;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const long long row = i / groups;
-    const int grp = (int)(i - row * groups);
-    float v[8], m[8];
-    unpack8<DT>(__ldg(z + i), v);
-    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale) + 2 * grp);
-    const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale) + 2 * grp + 1);
-    const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift) + 2 * grp);
-    const float4 h1 = __ldg(reinterpret_cast<const float4*>(shift) + 2 * grp + 1);
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-    drop_mult8(drop, row, grp, m);
+  float sc[8], sh[8];
+  load8(scale, grp, sc);
+  load8(shift, grp, sh);
+  const long long step = gridDim.x;
+  for (long long r0 = blockIdx.x; r0 < rows; r0 += step * kRowUnroll) {
+    uint4 zv[kRowUnroll], rv[kRowUnroll];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f) * m[k];
-    if (res != nullptr) {
-      const long long seq = row / rows_per_seq;
-      const long long t = row - seq * rows_per_seq;
-      const long long rrow = seq * res_seq_rows + t * res_row_mul + res_row_off;
-      float r[8];
-      unpack8<DT>(__ldg(res + rrow * groups + grp), r);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] += r[k];
+    for (int u = 0; u < kRowUnroll; ++u) {
+      const long long row = r0 + u * step;
+      if (row < rows) {
+        zv[u] = __ldg(z + row * groups + grp);
+        if (res != nullptr) {
+          const long long seq = row / rows_per_seq;
+          const long long t = row - seq * rows_per_seq;
+          rv[u] = __ldg(res + (seq * res_seq_rows + t * res_row_mul + res_row_off) * groups + grp);
+        }
+      }
     }
-    a[i] = pack8<DT>(v);
+#pragma unroll
+    for (int u = 0; u < kRowUnroll; ++u) {
+      const long long row = r0 + u * step;
+      if (row < rows) {
+        float v[8], m[8];
+        unpack8<DT>(zv[u], v);
+        drop_mult8(drop, row, grp, m);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f) * m[k];
+        if (res != nullptr) {
+          float r[8];
+          unpack8<DT>(rv[u], r);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] += r[k];
+        }
+        a[row * groups + grp] = pack8<DT>(v);
+      }
+    }
   }
+}
+
+// Reduction kernels (col_stats, bn_act_bwd_reduce) use blocks of kRedLanes row lanes x kRedGroups channel groups: the
+// lanes of a block are combined in shared memory, so one double atomic per channel per block reaches L2, and the grid
+// is capped at 2 blocks per SM (same-address atomics serialise: thousands of blocks would cost more than the reads).
+constexpr int kRedGroups = 64;
+constexpr int kRedLanes = 4;
+constexpr int kRedUnroll = 8;
+
+__device__ __forceinline__ void block_combine_and_add(const float (&a1)[8], const float (&a2)[8], int gl, int rl, int grp,
+                                                      int groups, double* __restrict__ out1, double* __restrict__ out2) {
+  __shared__ float part[2][kRedLanes][kRedGroups * 8 + 4];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    part[0][rl][gl * 8 + k] = a1[k];
+    part[1][rl][gl * 8 + k] = a2[k];
+  }
+  __syncthreads();
+  if (rl == 0 && grp < groups) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int r = 0; r < kRedLanes; ++r) {
+        s1 += (double)part[0][r][gl * 8 + k];
+        s2 += (double)part[1][r][gl * 8 + k];
+      }
+      atomicAdd(out1 + grp * 8 + k, s1);
+      atomicAdd(out2 + grp * 8 + k, s2);
+    }
+  }
+}
+
+// per-channel sum / sum of squares of a stored matrix (train-mode BatchNorm statistics of layers whose GEMM is too
+// short to hide the in-epilogue reduction): one double atomic per channel per block
+template <int DT>
+__global__ void __launch_bounds__(kRedGroups * kRedLanes)
+col_stats_kernel(const uint4* __restrict__ z, long long rows, int groups, double* __restrict__ sum,
+                 double* __restrict__ sqsum) {
+  const int gl = threadIdx.x % kRedGroups, rl = threadIdx.x / kRedGroups;
+  const int grp = blockIdx.y * kRedGroups + gl;
+  float a1[8], a2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a1[k] = a2[k] = 0.f;
+  if (grp < groups) {
+    const long long step = (long long)gridDim.x * kRedLanes;
+    for (long long r0 = (long long)blockIdx.x * kRedLanes + rl; r0 < rows; r0 += step * kRedUnroll) {
+      uint4 zv[kRedUnroll];
+#pragma unroll
+      for (int u = 0; u < kRedUnroll; ++u) {
+        const long long row = r0 + u * step;
+        zv[u] = row < rows ? __ldg(z + row * groups + grp) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < kRedUnroll; ++u) {
+        float v[8];
+        unpack8<DT>(zv[u], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          a1[k] += v[k];
+          a2[k] = fmaf(v[k], v[k], a2[k]);
+        }
+      }
+    }
+  }
+  block_combine_and_add(a1, a2, gl, rl, grp, groups, sum, sqsum);
 }
 
 // ---------------------------------------------------------------------------------------------- backward
 // dy = g * dropout multiplier * [z * scale + shift > 0];  xhat = (z - mean) * invstd
 template <int DT>
-__device__ __forceinline__ void load_dy_xhat(const uint4* g, const uint4* z, long long i, long long row, int grp,
-                                             const float (&sc)[8], const float (&sh)[8], const float (&mu)[8],
-                                             const float (&is)[8], const DropCtx& drop, float (&dy)[8],
-                                             float (&xh)[8]) {
+__device__ __forceinline__ void dy_xhat(const uint4& gu, const uint4& zu, long long row, int grp, const float (&sc)[8],
+                                        const float (&sh)[8], const float (&mu)[8], const float (&is)[8],
+                                        const DropCtx& drop, float (&dy)[8], float (&xh)[8]) {
   float gv[8], zv[8], m[8];
-  unpack8<DT>(__ldg(g + i), gv);
-  unpack8<DT>(__ldg(z + i), zv);
+  unpack8<DT>(gu, gv);
+  unpack8<DT>(zu, zv);
   drop_mult8(drop, row, grp, m);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -187,68 +275,52 @@ __device__ __forceinline__ void load_dy_xhat(const uint4* g, const uint4* z, lon
   }
 }
 
-__device__ __forceinline__ void load8(const float* p, int grp, float (&o)[8]) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p) + 2 * grp);
-  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 2 * grp + 1);
-  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
-}
-
-// Block = kEwThreads threads = (kEwThreads / groups_per_block) row lanes x groups_per_block channel groups. A block
-// owns a fixed slab of channel groups (blockIdx.y) and strides over rows (blockIdx.x), so each thread keeps its 8
-// channels' partial sums in registers; one shared-memory combine and one double atomic per channel per block.
 template <int DT>
-__global__ void __launch_bounds__(kEwThreads)
+__global__ void __launch_bounds__(kRedGroups * kRedLanes)
 bn_act_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z, const float* __restrict__ scale,
                          const float* __restrict__ shift, const float* __restrict__ mean,
                          const float* __restrict__ invstd, long long rows, int groups, DropoutParams dp,
                          double* __restrict__ sum_dy, double* __restrict__ sum_dy_xhat) {
-  constexpr int kGroupsPerBlock = 32;               // 256 channels per block
-  constexpr int kRowLanes = kEwThreads / kGroupsPerBlock;
-  __shared__ float part[2][kRowLanes][kGroupsPerBlock * 8 + 8];
-  const DropCtx drop = make_drop(dp);
-  const int gl = threadIdx.x % kGroupsPerBlock;
-  const int rl = threadIdx.x / kGroupsPerBlock;
-  const int grp = blockIdx.y * kGroupsPerBlock + gl;
+  const int gl = threadIdx.x % kRedGroups, rl = threadIdx.x / kRedGroups;
+  const int grp = blockIdx.y * kRedGroups + gl;
   float a1[8], a2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) a1[k] = a2[k] = 0.f;
   if (grp < groups) {
+    const DropCtx drop = make_drop(dp);
     float sc[8], sh[8], mu[8], is[8];
     load8(scale, grp, sc);
     load8(shift, grp, sh);
     load8(mean, grp, mu);
     load8(invstd, grp, is);
-    for (long long row = (long long)blockIdx.x * kRowLanes + rl; row < rows; row += (long long)gridDim.x * kRowLanes) {
-      float dy[8], xh[8];
-      load_dy_xhat<DT>(g, z, row * groups + grp, row, grp, sc, sh, mu, is, drop, dy, xh);
+    constexpr int kU = 4;
+    const long long step = (long long)gridDim.x * kRedLanes;
+    for (long long r0 = (long long)blockIdx.x * kRedLanes + rl; r0 < rows; r0 += step * kU) {
+      uint4 gv[kU], zv[kU];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        a1[k] += dy[k];
-        a2[k] = fmaf(dy[k], xh[k], a2[k]);
+      for (int u = 0; u < kU; ++u) {
+        const long long row = r0 + u * step;
+        if (row < rows) {
+          gv[u] = __ldg(g + row * groups + grp);
+          zv[u] = __ldg(z + row * groups + grp);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const long long row = r0 + u * step;
+        if (row < rows) {
+          float dy[8], xh[8];
+          dy_xhat<DT>(gv[u], zv[u], row, grp, sc, sh, mu, is, drop, dy, xh);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            a1[k] += dy[k];
+            a2[k] = fmaf(dy[k], xh[k], a2[k]);
+          }
+        }
       }
     }
   }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    part[0][rl][gl * 8 + k] = a1[k];
-    part[1][rl][gl * 8 + k] = a2[k];
-  }
-  __syncthreads();
-  // 256 channels x 2 quantities, one thread each for the first 256 threads (two quantities per thread)
-  const int ch = threadIdx.x;
-  if (ch < kGroupsPerBlock * 8) {
-    const int cg = blockIdx.y * kGroupsPerBlock * 8 + ch;
-    if (cg < groups * 8) {
-      double s1 = 0.0, s2 = 0.0;
-#pragma unroll
-      for (int r = 0; r < kRowLanes; ++r) {
-        s1 += (double)part[0][r][ch];
-        s2 += (double)part[1][r][ch];
-      }
-      atomicAdd(sum_dy + cg, s1);
-      atomicAdd(sum_dy_xhat + cg, s2);
-    }
-  }
+  block_combine_and_add(a1, a2, gl, rl, grp, groups, sum_dy, sum_dy_xhat);
 }
 
 template <int DT>
@@ -259,34 +331,54 @@ bn_act_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z
                         DropoutParams dp, const double* __restrict__ sum_dy, const double* __restrict__ sum_dy_xhat,
                         const float* __restrict__ gscale_buf, uint4* __restrict__ dz, float* __restrict__ d_gamma,
                         float* __restrict__ d_beta) {
+  const int grp = blockIdx.y * kEwThreads + threadIdx.x;
+  if (grp >= groups) return;
   const DropCtx drop = make_drop(dp);
-  const float inv_n = 1.f / (float)count;
-  // BatchNorm parameter gradients: one block writes them (un-scaled)
-  if (blockIdx.x == 0 && d_gamma != nullptr) {
-    const float inv = gscale_buf != nullptr ? gscale_buf[1] : 1.f;
-    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-      d_gamma[ch] = (float)(sum_dy_xhat[ch] * (double)inv);
-      d_beta[ch] = (float)(sum_dy[ch] * (double)inv);
-    }
+  const double inv_n = 1.0 / (double)count;
+  float sc[8], sh[8], mu[8], is[8], m1[8], m2[8];
+  load8(scale, grp, sc);
+  load8(shift, grp, sh);
+  load8(mean, grp, mu);
+  load8(invstd, grp, is);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    m1[k] = (float)(sum_dy[grp * 8 + k] * inv_n);
+    m2[k] = (float)(sum_dy_xhat[grp * 8 + k] * inv_n);
   }
-  const long long total = rows * groups;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const long long row = i / groups;
-    const int grp = (int)(i - row * groups);
-    float sc[8], sh[8], mu[8], is[8], dy[8], xh[8], o[8];
-    load8(scale, grp, sc);
-    load8(shift, grp, sh);
-    load8(mean, grp, mu);
-    load8(invstd, grp, is);
-    load_dy_xhat<DT>(g, z, i, row, grp, sc, sh, mu, is, drop, dy, xh);
+  // BatchNorm parameter gradients (un-scaled): written once, by the blocks of row 0
+  if (blockIdx.x == 0 && d_gamma != nullptr) {
+    const double inv = gscale_buf != nullptr ? (double)gscale_buf[1] : 1.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float m1 = (float)sum_dy[grp * 8 + k] * inv_n;
-      const float m2 = (float)sum_dy_xhat[grp * 8 + k] * inv_n;
-      o[k] = sc[k] * (dy[k] - m1 - xh[k] * m2);
+      const int ch = grp * 8 + k;
+      if (ch < c) {
+        d_gamma[ch] = (float)(sum_dy_xhat[ch] * inv);
+        d_beta[ch] = (float)(sum_dy[ch] * inv);
+      }
     }
-    dz[i] = pack8<DT>(o);
+  }
+  const long long step = gridDim.x;
+  for (long long r0 = blockIdx.x; r0 < rows; r0 += step * kRowUnroll) {
+    uint4 gv[kRowUnroll], zv[kRowUnroll];
+#pragma unroll
+    for (int u = 0; u < kRowUnroll; ++u) {
+      const long long row = r0 + u * step;
+      if (row < rows) {
+        gv[u] = __ldg(g + row * groups + grp);
+        zv[u] = __ldg(z + row * groups + grp);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kRowUnroll; ++u) {
+      const long long row = r0 + u * step;
+      if (row < rows) {
+        float dy[8], xh[8], o[8];
+        dy_xhat<DT>(gv[u], zv[u], row, grp, sc, sh, mu, is, drop, dy, xh);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = sc[k] * (dy[k] - m1[k] - xh[k] * m2[k]);
+        dz[row * groups + grp] = pack8<DT>(o);
+      }
+    }
   }
 }
 
@@ -337,13 +429,25 @@ grad_pack_rows_kernel(const float* __restrict__ src, void* __restrict__ dst, lon
 }
 
 // ---------------------------------------------------------------------------------------------- launchers
-static int rows_grid(long long total, int sm_count, int per_sm) {
-  long long blocks = (total + kEwThreads - 1) / kEwThreads;
-  const long long cap = (long long)sm_count * per_sm;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  return (int)blocks;
+// grid for the row-walking kernels: y covers the channel groups, x strides over rows with ~8 blocks per SM in total
+static dim3 row_walk_grid(long long rows, int groups, int sm_count) {
+  const int gy = (groups + kEwThreads - 1) / kEwThreads;
+  long long gx = (rows + kRowUnroll - 1) / kRowUnroll;
+  const int per_sm = groups <= 128 ? 16 : 8;  // ~2048 resident threads per SM
+  const long long cap = ((long long)sm_count * per_sm + gy - 1) / gy;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  return dim3((unsigned)gx, (unsigned)gy);
 }
+static dim3 reduce_grid(long long rows, int groups, int sm_count) {
+  const int gy = (groups + kRedGroups - 1) / kRedGroups;
+  long long gx = (rows + kRedLanes * 4 - 1) / (kRedLanes * 4);
+  const long long cap = ((long long)sm_count * 4 + gy - 1) / gy;  // ~4 blocks of 256 threads per SM in total
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  return dim3((unsigned)gx, (unsigned)gy);
+}
+static int ew_block(int groups) { return groups < kEwThreads ? ((groups + 31) / 32) * 32 : kEwThreads; }
 
 cudaError_t launch_bn_finalize(const double* sum, const double* sqsum, long long count, const float* gamma,
                                const float* beta, float eps, float momentum, float* running_mean, float* running_var,
@@ -355,24 +459,30 @@ cudaError_t launch_bn_finalize(const double* sum, const double* sqsum, long long
   return cudaGetLastError();
 }
 
+#define VP3D_DISPATCH_16(KERNEL, ...)                                                              \
+  if (dtype == VP3D_F16) KERNEL<VP3D_F16><<<grid, block, 0, stream>>>(__VA_ARGS__);                 \
+  else if (dtype == VP3D_BF16) KERNEL<VP3D_BF16><<<grid, block, 0, stream>>>(__VA_ARGS__);          \
+  else return cudaErrorInvalidValue;                                                                \
+  return cudaGetLastError();
+
 cudaError_t launch_bn_act_fwd(int dtype, const void* z, const float* scale, const float* shift, const void* res,
                               long long seqs, long long rows_per_seq, long long res_seq_rows, int res_row_mul,
                               int res_row_off, int c_pad, const DropoutParams& dp, void* a, int sm_count,
                               cudaStream_t stream) {
   const long long rows = seqs * rows_per_seq;
   const int groups = c_pad / 8;
-  const int grid = rows_grid(rows * groups, sm_count, 8);
-  if (dtype == VP3D_F16)
-    bn_act_fwd_kernel<VP3D_F16><<<grid, kEwThreads, 0, stream>>>(
-        static_cast<const uint4*>(z), scale, shift, static_cast<const uint4*>(res), rows, rows_per_seq, res_seq_rows,
-        res_row_mul, res_row_off, groups, dp, static_cast<uint4*>(a));
-  else if (dtype == VP3D_BF16)
-    bn_act_fwd_kernel<VP3D_BF16><<<grid, kEwThreads, 0, stream>>>(
-        static_cast<const uint4*>(z), scale, shift, static_cast<const uint4*>(res), rows, rows_per_seq, res_seq_rows,
-        res_row_mul, res_row_off, groups, dp, static_cast<uint4*>(a));
-  else
-    return cudaErrorInvalidValue;
-  return cudaGetLastError();
+  const dim3 grid = row_walk_grid(rows, groups, sm_count);
+  const int block = ew_block(groups);
+  VP3D_DISPATCH_16(bn_act_fwd_kernel, static_cast<const uint4*>(z), scale, shift, static_cast<const uint4*>(res), rows,
+                   rows_per_seq, res_seq_rows, res_row_mul, res_row_off, groups, dp, static_cast<uint4*>(a))
+}
+
+cudaError_t launch_col_stats(int dtype, const void* z, long long rows, int c_pad, double* sum, double* sqsum,
+                             int sm_count, cudaStream_t stream) {
+  const int groups = c_pad / 8;
+  const dim3 grid = reduce_grid(rows, groups, sm_count);
+  const int block = kRedGroups * kRedLanes;
+  VP3D_DISPATCH_16(col_stats_kernel, static_cast<const uint4*>(z), rows, groups, sum, sqsum)
 }
 
 cudaError_t launch_bn_act_bwd_reduce(int dtype, const void* g, const void* z, const float* scale, const float* shift,
@@ -380,23 +490,10 @@ cudaError_t launch_bn_act_bwd_reduce(int dtype, const void* g, const void* z, co
                                      const DropoutParams& dp, double* sum_dy, double* sum_dy_xhat, int sm_count,
                                      cudaStream_t stream) {
   const int groups = c_pad / 8;
-  const int gy = (groups + 31) / 32;
-  long long gx = (rows + 7) / 8;  // 8 row lanes per block
-  const long long cap = ((long long)sm_count * 8 + gy - 1) / gy;
-  if (gx > cap) gx = cap;
-  if (gx < 1) gx = 1;
-  dim3 grid((unsigned)gx, (unsigned)gy);
-  if (dtype == VP3D_F16)
-    bn_act_bwd_reduce_kernel<VP3D_F16><<<grid, kEwThreads, 0, stream>>>(
-        static_cast<const uint4*>(g), static_cast<const uint4*>(z), scale, shift, mean, invstd, rows, groups, dp,
-        sum_dy, sum_dy_xhat);
-  else if (dtype == VP3D_BF16)
-    bn_act_bwd_reduce_kernel<VP3D_BF16><<<grid, kEwThreads, 0, stream>>>(
-        static_cast<const uint4*>(g), static_cast<const uint4*>(z), scale, shift, mean, invstd, rows, groups, dp,
-        sum_dy, sum_dy_xhat);
-  else
-    return cudaErrorInvalidValue;
-  return cudaGetLastError();
+  const dim3 grid = reduce_grid(rows, groups, sm_count);
+  const int block = kRedGroups * kRedLanes;
+  VP3D_DISPATCH_16(bn_act_bwd_reduce_kernel, static_cast<const uint4*>(g), static_cast<const uint4*>(z), scale, shift,
+                   mean, invstd, rows, groups, dp, sum_dy, sum_dy_xhat)
 }
 
 cudaError_t launch_bn_act_bwd_apply(int dtype, const void* g, const void* z, const float* scale, const float* shift,
@@ -405,18 +502,11 @@ cudaError_t launch_bn_act_bwd_apply(int dtype, const void* g, const void* z, con
                                     const float* gscale_buf, void* dz, float* d_gamma, float* d_beta, int sm_count,
                                     cudaStream_t stream) {
   const int groups = c_pad / 8;
-  const int grid = rows_grid(rows * groups, sm_count, 8);
-  if (dtype == VP3D_F16)
-    bn_act_bwd_apply_kernel<VP3D_F16><<<grid, kEwThreads, 0, stream>>>(
-        static_cast<const uint4*>(g), static_cast<const uint4*>(z), scale, shift, mean, invstd, rows, count, c, groups,
-        dp, sum_dy, sum_dy_xhat, gscale_buf, static_cast<uint4*>(dz), d_gamma, d_beta);
-  else if (dtype == VP3D_BF16)
-    bn_act_bwd_apply_kernel<VP3D_BF16><<<grid, kEwThreads, 0, stream>>>(
-        static_cast<const uint4*>(g), static_cast<const uint4*>(z), scale, shift, mean, invstd, rows, count, c, groups,
-        dp, sum_dy, sum_dy_xhat, gscale_buf, static_cast<uint4*>(dz), d_gamma, d_beta);
-  else
-    return cudaErrorInvalidValue;
-  return cudaGetLastError();
+  const dim3 grid = row_walk_grid(rows, groups, sm_count);
+  const int block = ew_block(groups);
+  VP3D_DISPATCH_16(bn_act_bwd_apply_kernel, static_cast<const uint4*>(g), static_cast<const uint4*>(z), scale, shift,
+                   mean, invstd, rows, count, c, groups, dp, sum_dy, sum_dy_xhat, gscale_buf, static_cast<uint4*>(dz),
+                   d_gamma, d_beta)
 }
 
 cudaError_t launch_grad_scale(const float* dy, long long n, float* gscale_buf, int sm_count, cudaStream_t stream) {

@@ -11,10 +11,12 @@
 // memory descriptor walks them with LBO = one box (next 64-channel group) and SBO = 1024 B (next 8 frames), so no
 // transpose pass over HBM is needed.
 //
-// Work decomposition ("stream-K"): a work unit is (output tile 128 co x BN ci of one tap, block of 64 frames). The
-// units are split evenly over the persistent CTAs (one per SM); a CTA accumulates a run of units of one tile in TMEM
-// and combines its partial tile into the fp32 result with vector reductions (red.global.add.v4.f32). Every SM gets the
-// same number of MMAs whatever the layer shape -- the 1f model's layers range from 82,944 frames down to 1,024.
+// Work decomposition (split-K in lockstep): a work item is (row slice s, output tile 128 co x BN ci of one tap). The
+// host picks the number of slices S so that tiles * S fills a whole number of waves of the persistent grid (one CTA
+// per SM); item i = s * tiles + t goes to CTA i mod grid. All CTAs of a wave walk the same row range at the same
+// pace, so every dz / a box that 8-12 tiles need is fetched from HBM once and hit in L2 by the others. A CTA
+// accumulates its item in TMEM and adds the partial tile to the fp32 result with vector reductions
+// (red.global.add.v4.f32); with S slices each output element receives S reductions.
 //
 // Pipeline per CTA (192 threads), as in conv_gemm.cu: warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue with
 // two TMEM accumulator buffers so that the reduction of run i overlaps the MMAs of run i + 1.
@@ -85,11 +87,9 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // this CTA's run of work units; unit = tile * kb_total + kb, kb = seq * kb_per_seq + row block
-  const long long kb_total = (long long)p.seqs * p.kb_per_seq;
-  const long long total_units = (long long)p.num_tiles * kb_total;
-  const long long u_begin = total_units * blockIdx.x / gridDim.x;
-  const long long u_end = total_units * (blockIdx.x + 1) / gridDim.x;
+  // row blocks kb = seq * kb_per_seq + block-in-sequence; slice s owns kb in [s * kb_all / S, (s + 1) * kb_all / S)
+  const long long kb_all = (long long)p.seqs * p.kb_per_seq;
+  const int num_items = p.num_tiles * p.num_slices;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -118,28 +118,32 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long u = u_begin; u < u_end; ++u) {
-        const int tile = (int)(u / kb_total);
-        const long long kb = u - (long long)tile * kb_total;
-        const int seq = (int)(kb / p.kb_per_seq);
-        const int r0 = (int)(kb - (long long)seq * p.kb_per_seq) * kWgRows;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int sl = item / p.num_tiles;
+        const int tile = item - sl * p.num_tiles;
+        const long long kb_lo = kb_all * sl / p.num_slices;
+        const long long kb_hi = kb_all * (sl + 1) / p.num_slices;
         int tap, co0, ci_t;
         decode_tile(tile, p, tap, co0, ci_t);
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-        uint8_t* sa = smem + stage * Cfg::kStageBytes;
+        for (long long kb = kb_lo; kb < kb_hi; ++kb) {
+          const int seq = (int)(kb / p.kb_per_seq);
+          const int r0 = (int)(kb - (long long)seq * p.kb_per_seq) * kWgRows;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
 #pragma unroll
-        for (int g = 0; g < kWgBlockM / 64; ++g)
-          tma_load_3d(sa + g * (kWgRows * 128), &tmA, &full_bar[stage], co0 + g * 64, r0, seq);
-        uint8_t* sb = sa + Cfg::kABytes;
-        const int b_col = ci_t * BN + tap * p.b_tap_col_step;
-        const int b_row = r0 + p.b_row_off + tap * p.b_tap_row_step;
+          for (int g = 0; g < kWgBlockM / 64; ++g)
+            tma_load_3d(sa + g * (kWgRows * 128), &tmA, &full_bar[stage], co0 + g * 64, r0, seq);
+          uint8_t* sb = sa + Cfg::kABytes;
+          const int b_col = ci_t * BN + tap * p.b_tap_col_step;
+          const int b_row = r0 + p.b_row_off + tap * p.b_tap_row_step;
 #pragma unroll
-        for (int g = 0; g < BN / 64; ++g)
-          tma_load_3d(sb + g * (kWgRows * 128), &tmB, &full_bar[stage], b_col + g * 64, b_row, seq);
-        if (++stage == Cfg::kStages) {
-          stage = 0;
-          phase ^= 1;
+          for (int g = 0; g < BN / 64; ++g)
+            tma_load_3d(sb + g * (kWgRows * 128), &tmB, &full_bar[stage], b_col + g * 64, b_row, seq);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -151,16 +155,14 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      long long u = u_begin;
-      while (u < u_end) {
-        const long long tile = u / kb_total;
-        long long run_end = (tile + 1) * kb_total;
-        if (run_end > u_end) run_end = u_end;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int sl = item / p.num_tiles;
+        const long long kb_lo = kb_all * sl / p.num_slices;
+        const long long kb_hi = kb_all * (sl + 1) / p.num_slices;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        bool first = true;
-        for (; u < run_end; ++u) {
+        for (long long kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -169,9 +171,9 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int k = 0; k < kWgRows / 16; ++k) {
             // 16 frames of reduction per MMA = two 8-frame groups = 2048 bytes further into every box
-            umma_f16_ss(d_tmem, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), kIdesc, !(first && k == 0));
+            umma_f16_ss(d_tmem, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), kIdesc,
+                        !(kb == kb_lo && k == 0));
           }
-          first = false;
           umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) {
             stage = 0;
@@ -190,13 +192,11 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int row = quad * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    long long u = u_begin;
-    while (u < u_end) {
-      const long long tile = u / kb_total;
-      long long run_end = (tile + 1) * kb_total;
-      if (run_end > u_end) run_end = u_end;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int sl = item / p.num_tiles;
+      const int tile = item - sl * p.num_tiles;
       int tap, co0, ci_t;
-      decode_tile((int)tile, p, tap, co0, ci_t);
+      decode_tile(tile, p, tap, co0, ci_t);
       float* out_row = p.out + (long long)tap * p.out_tap_stride + (long long)(co0 + row) * p.out_row_stride +
                        (long long)ci_t * BN;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -215,7 +215,6 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_arrive(&tmem_empty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
-      u = run_end;
     }
   }
 
@@ -254,29 +253,30 @@ cudaError_t launch_wgrad(int dtype, int block_n, const CUtensorMap& tmA, const C
   return cudaErrorInvalidValue;
 }
 
-// dw[co][ci][tap] = packed[tap][co][ci] * inv_gscale   (nn.Conv1d weight layout)
+// dw[co][ci][tap] = packed[tap * tap_stride + co * row_stride + ci] * inv_gscale   (nn.Conv1d weight layout).
+// Thread = (co, ci); the taps of one (co, ci) are adjacent in dw, so a warp writes one contiguous span.
 __global__ void __launch_bounds__(256)
-wgrad_finish_kernel(const float* __restrict__ packed, float* __restrict__ dw, int c_out, int c_in, int taps, int co_pad,
-                    int ci_pad, const float* __restrict__ gscale_buf) {
+wgrad_finish_kernel(const float* __restrict__ packed, float* __restrict__ dw, int c_out, int c_in, int taps,
+                    long long tap_stride, long long row_stride, const float* __restrict__ gscale_buf) {
   const float inv = gscale_buf != nullptr ? gscale_buf[1] : 1.f;
-  const long long total = (long long)c_out * c_in * taps;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int tap = (int)(i % taps);
-    const long long r = i / taps;
-    const int ci = (int)(r % c_in);
-    const int co = (int)(r / c_in);
-    dw[i] = __ldg(packed + ((long long)tap * co_pad + co) * ci_pad + ci) * inv;
+  const int total = c_out * c_in;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i / c_in;
+    const int ci = i - co * c_in;
+    const float* src = packed + (long long)co * row_stride + ci;
+    float* dst = dw + (long long)i * taps;
+    for (int tap = 0; tap < taps; ++tap) dst[tap] = __ldg(src + tap * tap_stride) * inv;
   }
 }
 
-cudaError_t launch_wgrad_finish(const float* packed, float* dw, int c_out, int c_in, int taps, int co_pad, int ci_pad,
-                                const float* gscale_buf, int sm_count, cudaStream_t stream) {
-  const long long total = (long long)c_out * c_in * taps;
+cudaError_t launch_wgrad_finish(const float* packed, float* dw, int c_out, int c_in, int taps, long long tap_stride,
+                                long long row_stride, const float* gscale_buf, int sm_count, cudaStream_t stream) {
+  const long long total = (long long)c_out * c_in;
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
   if (blocks < 1) blocks = 1;
-  wgrad_finish_kernel<<<(int)blocks, 256, 0, stream>>>(packed, dw, c_out, c_in, taps, co_pad, ci_pad, gscale_buf);
+  wgrad_finish_kernel<<<(int)blocks, 256, 0, stream>>>(packed, dw, c_out, c_in, taps, tap_stride, row_stride,
+                                                       gscale_buf);
   return cudaGetLastError();
 }
 

@@ -23,6 +23,7 @@ class ConvArgs(C.Structure):
         ('a_row_stride', C.c_longlong), ('a_seq_stride', C.c_longlong), ('a_row_off', C.c_longlong),
         ('w', C.c_void_p), ('n_pad', C.c_longlong), ('k_total', C.c_longlong), ('taps', C.c_int),
         ('tap_row_step', C.c_int), ('k_per_tap', C.c_longlong),
+        ('w_mn_major', C.c_int), ('w_row_stride', C.c_longlong), ('w_tap_col_step', C.c_longlong),
         ('rows_out', C.c_longlong), ('out', C.c_void_p), ('out_f32', C.c_int), ('out_row_stride', C.c_longlong),
         ('out_seq_stride', C.c_longlong), ('n_valid', C.c_longlong), ('out_round_tf32', C.c_int),
         ('scale', C.c_void_p), ('shift', C.c_void_p), ('relu', C.c_int),
@@ -69,11 +70,12 @@ _SIGNATURES = {
                        [C.c_void_p, C.c_void_p]),
     'vp3d_n_mpjpe_fwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     'vp3d_wgrad': (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
-    'vp3d_wgrad_finish': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
+    'vp3d_wgrad_finish': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 3 + [C.c_longlong] * 2 + [C.c_void_p, C.c_void_p]),
     'vp3d_bn_finalize': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_float, C.c_float] +
                          [C.c_void_p] * 7 + [C.c_int, C.c_int, C.c_void_p]),
     'vp3d_bn_act_fwd': (C.c_int, [C.c_int] + [C.c_void_p] * 4 + [C.c_longlong] * 3 + [C.c_int] * 3 +
                         [C.POINTER(Dropout), C.c_void_p, C.c_void_p]),
+    'vp3d_col_stats': (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     'vp3d_bn_act_bwd_reduce': (C.c_int, [C.c_int] + [C.c_void_p] * 6 + [C.c_longlong, C.c_int, C.POINTER(Dropout),
                                                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     'vp3d_bn_act_bwd_apply': (C.c_int, [C.c_int] + [C.c_void_p] * 6 + [C.c_longlong, C.c_longlong, C.c_int, C.c_int,

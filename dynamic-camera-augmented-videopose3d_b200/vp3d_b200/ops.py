@@ -181,7 +181,8 @@ def bn_fold(bn, c_pad):
 
 def conv_block(dt, a, a_view, w, taps, tap_row_step, k_per_tap, rows_out, out, out_view, block_n=256, a_row_off=0,
                scale=None, shift=None, relu=False, res=None, res_view=None, out_f32=False, n_valid=None,
-               stat_sum=None, stat_sqsum=None, out_round_tf32=False, res_rows=0, res_col_off=0, res_cols=0):
+               stat_sum=None, stat_sqsum=None, out_round_tf32=False, res_rows=0, res_col_off=0, res_cols=0,
+               w_mn_major=None):
     """One vp3d_conv_block_fwd launch.
     a_view   = (seqs, rows, kdim, row_stride, seq_stride)    out_view = (row_stride, seq_stride)
     res_view = (row_stride, seq_stride, row_mul, row_off)"""
@@ -191,13 +192,18 @@ def conv_block(dt, a, a_view, w, taps, tap_row_step, k_per_tap, rows_out, out, o
     args.a_seqs, args.a_rows, args.a_kdim, args.a_row_stride, args.a_seq_stride = a_view
     args.a_row_off = a_row_off
     args.w = w.data_ptr()
-    args.n_pad, args.k_total = w.shape[0], w.shape[1]
     args.taps, args.tap_row_step, args.k_per_tap = taps, tap_row_step, k_per_tap
+    if w_mn_major is None:
+        args.n_pad, args.k_total = w.shape[0], w.shape[1]
+    else:
+        # w is the forward-packed [k rows][row_stride columns] matrix read as W^T: (n_pad, tap column step)
+        args.n_pad, args.w_tap_col_step = w_mn_major
+        args.w_mn_major, args.w_row_stride, args.k_total = 1, w.shape[1], 0
     args.rows_out = rows_out
     args.out = out.data_ptr()
     args.out_f32 = 1 if out_f32 else 0
     args.out_row_stride, args.out_seq_stride = out_view
-    args.n_valid = n_valid if n_valid is not None else w.shape[0]
+    args.n_valid = n_valid if n_valid is not None else args.n_pad
     args.out_round_tf32 = 1 if out_round_tf32 else 0
     args.scale = None if scale is None else scale.data_ptr()
     args.shift = None if shift is None else shift.data_ptr()
@@ -239,12 +245,24 @@ def wgrad(dt, dz, dz_view, a, a_view, co_pad, ci_pad, taps, dw_packed, b_row_off
     return dw_packed
 
 
-def wgrad_finish(dw_packed, c_out, c_in, taps, co_pad, ci_pad, gscale_buf):
+def wgrad_finish(dw_packed, c_out, c_in, taps, co_pad, ci_pad, gscale_buf, tap_stride=None, row_stride=None):
+    """packed [taps][co_pad][ci_pad] (or the strides given) -> nn.Conv1d layout (c_out, c_in, taps), un-scaled."""
     dw = torch.empty((c_out, c_in, taps), dtype=torch.float32, device=dw_packed.device)
+    tap_stride = co_pad * ci_pad if tap_stride is None else tap_stride
+    row_stride = ci_pad if row_stride is None else row_stride
     with torch.cuda.device(dw.device):
-        check(lib().vp3d_wgrad_finish(_ptr(dw_packed), _ptr(dw), c_out, c_in, taps, co_pad, ci_pad, _ptr(gscale_buf),
-                                      _stream()), 'wgrad_finish')
+        check(lib().vp3d_wgrad_finish(_ptr(dw_packed), _ptr(dw), c_out, c_in, taps, tap_stride, row_stride,
+                                      _ptr(gscale_buf), _stream()), 'wgrad_finish')
     return dw
+
+
+def col_stats(dt, z, stats):
+    """stats (double [2][c_pad]) += per-channel sum / sum of squares of the stored matrix z [rows][c_pad]."""
+    c_pad = z.shape[-1]
+    rows = z.numel() // c_pad
+    with torch.cuda.device(z.device):
+        check(lib().vp3d_col_stats(dt, _ptr(z), rows, c_pad, _ptr(stats[0]), _ptr(stats[1]), _stream()), 'col_stats')
+    return stats
 
 
 def bn_finalize(stat, count, bn, c_pad, update_running=True):

@@ -18,6 +18,7 @@ from . import native, ops
 from .temporal import K_ALIGN, N_TILE, LayerPlan, _round_up, _run_layer, resolve_dtype
 
 SHRINK_PAD = 128      # shrink-layer output channels are padded to one 128-row MMA tile for its weight gradient
+STATS_IN_EPILOGUE_MIN_K = 2048
 _step_counter = [0]
 grad_ready_hook = None   # set by vp3d_b200.ddp: called as hook(parameter, gradient) as soon as a gradient is issued
 grad_finish_hook = None  # ... and once at the end of the backward (waits for the outstanding all-reduces)
@@ -60,9 +61,14 @@ def _forward_stack(model, x, dt):
         L.taps, L.dilation, L.stride = plan.taps, plan.dilation, plan.stride
         L.c_in, L.c_in_pad, L.t_in, L.a_in = cin, cin_pad, t, a_in
         w = _conv_w(dt, conv, c_pad, cin_pad)
-        L.w_fwd = None
+        L.w_fwd = w   # [c_out_pad][taps * c_in_pad]; the data-gradient GEMM reads it again as W^T (MN-major operand)
         stats = torch.zeros((2, c_pad), dtype=torch.float64, device=dev)
-        z, t_out = _run_layer(dt, a_in, n, t, cin_pad, w, plan, None, None, False, stats=stats)
+        # per-channel sum / sum of squares: in the GEMM epilogue when the contraction is long enough to hide it
+        # (3-tap 1024-channel layers), otherwise one extra read of the stored matrix (mostly L2 hits)
+        fused_stats = plan.taps * cin_pad >= STATS_IN_EPILOGUE_MIN_K
+        z, t_out = _run_layer(dt, a_in, n, t, cin_pad, w, plan, None, None, False, stats=stats if fused_stats else None)
+        if not fused_stats:
+            ops.col_stats(dt, z, stats)
         L.z, L.t_out = z, t_out
         count = n * t_out
         if sync_bn_group is not None:
@@ -104,7 +110,7 @@ def _forward_stack(model, x, dt):
     ones = torch.ones(n_out_pad, dtype=torch.float32, device=dev)
     y, t = _run_layer(dt, h, n, t, c_pad, w_shrink, LayerPlan(1), ones, bias, False, out_f32=True, n_valid=n_out,
                       block_n=64)
-    return y, layers, h, t, c_pad
+    return y, layers, h, t, c_pad, w_shrink
 
 
 def _views(L, n, c_pad):
@@ -125,8 +131,14 @@ def _views(L, n, c_pad):
 
 def _weight_grad(dt, L, dz, n, c_pad, gscale):
     dzv, av, row_step, col_step = _views(L, n, c_pad)
-    block_n = 256 if L.c_in_pad % 256 == 0 else 64
     c_out = L.conv.out_channels
+    if L.stride > 1 and L.taps * L.c_in_pad <= 256:
+        # narrow strided layer (expand: 3 x 64 input columns): all taps are adjacent columns of the reshaped view, so
+        # they form ONE 256-wide tile (columns past taps * c_in_pad are zero-filled by TMA) and dz is read once
+        packed = torch.zeros((1, c_pad, 256), dtype=torch.float32, device=dz.device)
+        ops.wgrad(dt, dz, dzv, L.a_in, av, c_pad, 256, 1, packed, block_n=256)
+        return ops.wgrad_finish(packed, c_out, L.c_in, L.taps, c_pad, 256, gscale, tap_stride=L.c_in_pad, row_stride=256)
+    block_n = 256 if L.c_in_pad % 256 == 0 else 64
     packed = torch.zeros((L.taps, c_pad, L.c_in_pad), dtype=torch.float32, device=dz.device)
     ops.wgrad(dt, dz, dzv, L.a_in, av, c_pad, L.c_in_pad, L.taps, packed, b_tap_row_step=row_step,
               b_tap_col_step=col_step, block_n=block_n)
@@ -134,47 +146,41 @@ def _weight_grad(dt, L, dz, n, c_pad, gscale):
 
 
 def _data_grad(dt, L, dz, n, c_pad, fan_in=None, fan_rows=0, fan_off=0, fan_mul=1):
-    """Gradient wrt the layer input: g_in[s][t'][ci]; `fan_in` is the block-output gradient that also reaches this
-    input through the residual slice (rows t * fan_mul + fan_off of the input)."""
+    """Gradient wrt the layer input: g_in[s][t'][ci] = sum_{tap, co} dz[s][t' - tap * d][co] * W[co][tap][ci]. The
+    forward-packed weights [co][tap * c_in_pad + ci] are the W^T operand as they are (MN-major), no transposed copy.
+    `fan_in` is the block-output gradient that also reaches this input through the residual slice."""
     taps, d, s = L.taps, L.dilation, L.stride
     cin_pad = L.c_in_pad
-    dev = dz.device
-    g_in = torch.empty((n, L.t_in, cin_pad), dtype=dz.dtype, device=dev)
-    if s > 1:
-        if L.t_in != taps * L.t_out:
+    g_in = torch.empty((n, L.t_in, cin_pad), dtype=dz.dtype, device=dz.device)
+    block_n = 256 if cin_pad % 256 == 0 else 64
+    if s > 1 or taps == 1:
+        if s > 1 and L.t_in != taps * L.t_out:
             raise RuntimeError('vp3d_b200: training a strided (1f) block needs t_in == %d * t_out (got %d -> %d)'
                                % (taps, L.t_in, L.t_out))
-        wt = _conv_w(dt, L.conv, taps * cin_pad, c_pad, transpose=1)   # [(tap, ci)][co]
         rows = n * L.t_out
+        n_cols = taps * cin_pad          # stride == width: the [rows][taps * C] view of g_in is one plain GEMM
         kw = {}
         if fan_in is not None:
-            # residual x[:, :, off::taps]: in the [rows][taps * C] view that is the column block [off*C, (off+1)*C)
+            # residual x[:, :, off::taps]: in that view it is the column block [off*C, (off+1)*C)
             kw = dict(res=fan_in, res_view=(c_pad, rows * c_pad, 1, 0), res_col_off=fan_off * cin_pad, res_cols=cin_pad)
-        ops.conv_block(dt, dz, (1, rows, c_pad, c_pad, rows * c_pad), wt, 1, 0, c_pad, rows, g_in,
-                       (taps * cin_pad, rows * taps * cin_pad), **kw)
+        ops.conv_block(dt, dz, (1, rows, c_pad, c_pad, rows * c_pad), L.w_fwd, 1, 0, c_pad, rows, g_in,
+                       (n_cols, rows * n_cols), block_n=block_n, w_mn_major=(n_cols, 0), **kw)
         return g_in
-    if taps == 1:
-        wt = _conv_w(dt, L.conv, cin_pad, c_pad, transpose=1)
-        rows = n * L.t_out
-        assert fan_in is None
-        ops.conv_block(dt, dz, (1, rows, c_pad, c_pad, rows * c_pad), wt, 1, 0, c_pad, rows, g_in,
-                       (cin_pad, rows * cin_pad))
-        return g_in
-    # dilated: g_in[t'] = sum_k W_k^T dz[t' - k d]; rows of dz outside [0, t_out) read as zero through TMA
-    wt = _conv_w(dt, L.conv, cin_pad, c_pad, transpose=2)               # [ci][(tap, co)]
+    # dilated: rows of dz outside [0, t_out) read as zero through TMA
     kw = {}
     if fan_in is not None:
         # residual x[:, :, off : off + fan_rows]: input row t' receives block-output row t' - off
         kw = dict(res=fan_in, res_view=(c_pad, fan_rows * c_pad, 1, -fan_off), res_rows=fan_rows)
-    ops.conv_block(dt, dz, (n, L.t_out, c_pad, c_pad, L.t_out * c_pad), wt, taps, -d, c_pad, L.t_in, g_in,
-                   (cin_pad, L.t_in * cin_pad), **kw)
+    ops.conv_block(dt, dz, (n, L.t_out, c_pad, c_pad, L.t_out * c_pad), L.w_fwd, taps, -d, c_pad, L.t_in, g_in,
+                   (cin_pad, L.t_in * cin_pad), block_n=block_n, w_mn_major=(cin_pad, cin_pad), **kw)
     return g_in
 
 
 class _StackTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, dt, x, *params):
-        y, layers, a_last, t_last, c_pad = _forward_stack(model, x, dt)
+        y, layers, a_last, t_last, c_pad, w_shrink = _forward_stack(model, x, dt)
+        ctx.w_shrink = w_shrink
         if debug_keep_saved:
             global debug_last_saved
             debug_last_saved = layers
@@ -205,10 +211,10 @@ class _StackTrainFn(torch.autograd.Function):
         ops.wgrad(dt, dzs, (1, rows, SHRINK_PAD, rows * SHRINK_PAD), ctx.a_last, (rows, c_pad, c_pad, rows * c_pad),
                   SHRINK_PAD, c_pad, 1, packed)
         done(model.shrink.weight, ops.wgrad_finish(packed, n_out, model.shrink.in_channels, 1, SHRINK_PAD, c_pad, gscale))
-        wt = ops.pack_conv_weight(dt, model.shrink.weight, c_pad, SHRINK_PAD, transpose=1)   # [ci][co]
         g = torch.empty((n, ctx.t_last, c_pad), dtype=dzs.dtype, device=dy.device)
-        ops.conv_block(dt, dzs, (1, rows, SHRINK_PAD, SHRINK_PAD, rows * SHRINK_PAD), wt, 1, 0, SHRINK_PAD, rows, g,
-                       (c_pad, rows * c_pad))
+        k_shrink = ctx.w_shrink.shape[0]      # forward-packed [n_out_pad][c_pad], read as W^T
+        ops.conv_block(dt, dzs, (1, rows, SHRINK_PAD, SHRINK_PAD, rows * SHRINK_PAD), ctx.w_shrink, 1, 0, k_shrink, rows,
+                       g, (c_pad, rows * c_pad), w_mn_major=(c_pad, 0))
 
         # ---- blocks and the expand layer, last to first. `g` is the gradient wrt the current layer's output.
         for idx in range(len(layers) - 1, -1, -1):

@@ -63,6 +63,12 @@ typedef struct vp3d_conv_args {
   int taps;
   int tap_row_step;        /* dilation, in rows */
   long long k_per_tap;     /* multiple of 128 bytes of K */
+  int w_mn_major;          /* 1 (fp16 / bf16 only): `w` is [k_per_tap rows][w_row_stride columns] with the OUTPUT column
+                              contiguous -- the forward-packed weights [c_out][taps * c_in_pad] read as W^T by the
+                              data-gradient GEMM: out[.][n] += a[.][k] * w[k][tap * w_tap_col_step + n]. n_pad is then
+                              the number of output columns and k_total is ignored. */
+  long long w_row_stride;
+  long long w_tap_col_step;
 
   long long rows_out;      /* output rows per sequence */
   void* out;
@@ -165,7 +171,7 @@ typedef struct vp3d_wgrad_args {
   long long dz_seqs, dz_rows, dz_row_stride, dz_seq_stride;
   long long co_pad;        /* multiple of 128 */
   const void* a;           /* layer input, viewed [seqs][a_rows][a_cols] */
-  long long a_rows, a_cols, a_row_stride, a_seq_stride;
+  long long a_rows, a_cols, a_row_stride, a_seq_stride;  /* columns past a_cols read as zero */
   long long ci_pad;        /* input channels per tap (multiple of block_n) */
   int taps;
   long long b_row_off;
@@ -175,10 +181,12 @@ typedef struct vp3d_wgrad_args {
 } vp3d_wgrad_args;
 int vp3d_wgrad(const vp3d_wgrad_args* args, void* stream);
 
-/* dw[co][ci][tap] = dw_packed[tap][co][ci] * gscale_buf[1]  (nn.Conv1d weight layout, fp32; gscale_buf = {gscale,
- * 1 / gscale} on the device, NULL = 1). */
-int vp3d_wgrad_finish(const float* dw_packed, float* dw, int c_out, int c_in, int taps, int co_pad, int ci_pad,
-                      const float* gscale_buf, void* stream);
+/* dw[co][ci][tap] = dw_packed[tap * tap_stride + co * row_stride + ci] * gscale_buf[1]  (nn.Conv1d weight layout,
+ * fp32; gscale_buf = {gscale, 1 / gscale} on the device, NULL = 1). For vp3d_wgrad's [taps][co_pad][ci_pad] result
+ * tap_stride = co_pad * ci_pad, row_stride = ci_pad; a narrow layer whose taps were contracted as ONE 256-wide tile
+ * (taps = 1, b_tap_col_step = 0 on the [rows][taps * c_in_pad] view) has tap_stride = c_in_pad, row_stride = 256. */
+int vp3d_wgrad_finish(const float* dw_packed, float* dw, int c_out, int c_in, int taps, long long tap_stride,
+                      long long row_stride, const float* gscale_buf, void* stream);
 
 /* Train-mode nn.BatchNorm1d statistics (TemporalModel.py:32,117,119 in train()): from the per-channel sum / sum of
  * squares over `count` rows (accumulated by vp3d_conv_block_fwd) produce the forward affine scale = gamma * invstd,
@@ -188,6 +196,10 @@ int vp3d_bn_finalize(const double* stat_sum, const double* stat_sqsum, long long
                      const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                      long long* num_batches_tracked, float* scale, float* shift, float* mean, float* invstd, int c,
                      int c_pad, void* stream);
+
+/* sum[c] += sum_rows z[r][c], sqsum[c] += sum_rows z[r][c]^2 over a stored [rows][c_pad] matrix: the same statistics
+ * as the GEMM epilogue's stat_sum / stat_sqsum, for layers whose contraction is too short to hide that reduction. */
+int vp3d_col_stats(int dtype, const void* z, long long rows, int c_pad, double* sum, double* sqsum, void* stream);
 
 /* Dropout description shared by forward and backward: keep-mask = Philox4x32-10(seed, stream, row, channel group)
  * >= p; kept values are multiplied by 1 / (1 - p) (nn.Dropout, TemporalModel.py:28,127,134-135). p == 0: off. */
