@@ -268,7 +268,8 @@ def bench_train(args, rank, world, dev, steps, warm):
     model.load_state_dict(oracle_state())
     model = model.to(dev).train()
     model.operand_dtype = args.dtype if args.dtype != 'tf32' else 'fp16'
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, amsgrad=True)       # run.py:662
+    use_graph = world == 1 and not args.no_graph
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, amsgrad=True, capturable=use_graph)       # run.py:662
     sync = None
     if world > 1:
         ddp.broadcast_parameters(model)
@@ -291,12 +292,31 @@ def bench_train(args, rank, world, dev, steps, warm):
         opt.step()
         return loss.detach()
 
+    graphed = None
+    if use_graph:
+        # the whole step (projection -> forward -> loss -> backward -> Adam) as one CUDA graph (vp3d_b200.graphs)
+        from vp3d_b200.graphs import GraphedTrainStep
+        graphed = GraphedTrainStep(model, opt, mpjpe, (Wd, qd, td, camd), tgt,
+                                   preprocess=lambda W, q, t, cam: world_to_image(W, q, t, cam,
+                                                                                  return_camera_space=False)[1])
+        Wd, qd, td, camd = graphed.static_inputs
+
     def step_resident():
+        if graphed is not None:
+            return graphed((Wd, qd, td, camd))
         return step(Wd, qd, td, camd)
 
+    from vp3d_b200.pipeline import HostPrefetcher
+    pre = HostPrefetcher((Wh, qh, th, camh), dev)
+    pre.put((Wh, qh, th, camh))
+
     def step_e2e():
-        W, q, t, cam = [v.to(dev, non_blocking=True) for v in (Wh, qh, th, camh)]
-        loss = step(W, q, t, cam)
+        # this step's batch was uploaded (pinned host -> device, side stream) while the previous step computed; the
+        # next one starts travelling now. Every step still moves its own 57.8 MB and reads its loss back.
+        b, bufs = pre.get()
+        pre.put((Wh, qh, th, camh))
+        loss = graphed(bufs) if graphed is not None else step(*bufs)
+        pre.release(b)
         loss_host.copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(loss_host)
@@ -307,8 +327,10 @@ def bench_train(args, rank, world, dev, steps, warm):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(warm):
-        first_loss = step_resident()
+    for i in range(warm):
+        loss = step_resident()
+        if i == 0:
+            first_loss = float(loss)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -316,6 +338,7 @@ def bench_train(args, rank, world, dev, steps, warm):
         last_loss = step_resident()
     e1.record()
     barrier()
+    last_loss = float(last_loss)
     ms = e0.elapsed_time(e1)
 
     lib = native.lib()
@@ -324,9 +347,9 @@ def bench_train(args, rank, world, dev, steps, warm):
     other = ('vp3d_project_points', 'vp3d_mpjpe_fwd', 'vp3d_mpjpe_bwd', 'vp3d_pack_rows', 'vp3d_pack_conv_weight',
              'vp3d_wgrad_finish', 'vp3d_grad_scale', 'vp3d_grad_pack_rows')
     inst = min(steps, 3)
-    with LaunchTimer(lib, gemm + bn + other) as lt:
+    with LaunchTimer(lib, gemm + bn + other) as lt:   # per-kernel-family timing needs the eager path
         for _ in range(inst):
-            step_resident()
+            step(Wd, qd, td, camd)
         torch.cuda.synchronize()
     gemm_ms, bn_ms, proj_ms = lt.ms(*gemm) / inst, lt.ms(*bn) / inst, lt.ms('vp3d_project_points') / inst
     conv_ms, wgrad_ms = lt.ms('vp3d_conv_block_fwd') / inst, lt.ms('vp3d_wgrad') / inst
@@ -365,7 +388,8 @@ def bench_train(args, rank, world, dev, steps, warm):
                                     'tensors overlapped with backward, %d collectives, %.1f MB per step'
                                     % (sync.collectives // max(1, warm + steps + inst + 2 + steps),
                                        sync.bytes_reduced / max(1, warm + steps + inst + 2 + steps) / 1e6),
-                   'bn': 'per-replica batch statistics'},
+                   'bn': 'per-replica batch statistics',
+                   'launch': 'one CUDA graph per step (vp3d_b200.graphs.GraphedTrainStep)' if use_graph else 'eager'},
         'e2e': {'value': total / (ms_e2e * 1e-3), 'unit': 'samples/s', 'ms_per_step': ms_e2e / steps,
                 'h2d_bytes_per_step': sum(v.numel() * 4 for v in (Wh, qh, th, camh)), 'd2h_bytes_per_step': 4},
         'gpu_launches': n_launch * steps,
@@ -397,6 +421,7 @@ def main():
     ap.add_argument('--mode', default='all', choices=['all', 'infer', 'train'],
                     help='all: inference headline + train object; train: training headline only')
     ap.add_argument('--batch', type=int, default=TRAIN_BATCH, help='training samples per GPU per step')
+    ap.add_argument('--no-graph', action='store_true', help='training: launch kernels eagerly instead of one CUDA graph')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
@@ -461,13 +486,12 @@ def main():
         with torch.no_grad():
             return model(x_dev)
 
+    from vp3d_b200 import pipeline
+
     def step_e2e():
-        with torch.no_grad():
-            xd = x_host.to(dev, non_blocking=True)
-            y = model(xd)
-            y_host.copy_(y, non_blocking=True)
-        torch.cuda.current_stream().synchronize()   # the caller holds the result on the host
-        return y_host
+        # public host-buffer entry point: chunks of sequences, upload / compute / download overlapped on 3 streams;
+        # returns after the last result byte is in y_host
+        return pipeline.infer_host(model, x_host, y_host, chunk_seqs=max(1, seqs // 8))
 
     for _ in range(warm):
         step_resident()

@@ -472,6 +472,7 @@ vp3d::DropoutParams drop_of(const vp3d_dropout* d) {
   dp.p = d ? d->p : 0.f;
   dp.seed = d ? d->seed : 0ull;
   dp.stream = d ? d->stream : 0ull;
+  dp.step_counter = d ? d->step_counter : nullptr;
   return dp;
 }
 }  // namespace
@@ -534,6 +535,13 @@ int vp3d_bn_act_bwd_apply(int dtype, const void* g, const void* z, const float* 
                                                 sum_dy, sum_dy_xhat, gscale_buf, dz, d_gamma, d_beta, dev->sm_count,
                                                 static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "bn_act_bwd_apply launch");
+  return VP3D_OK;
+}
+
+int vp3d_counter_add(unsigned long long* counter, unsigned long long inc, void* stream) {
+  if (!counter) return fail(VP3D_ERR_INVALID, "counter_add: null counter");
+  cudaError_t e = vp3d::launch_counter_add(counter, inc, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "counter_add launch");
   return VP3D_OK;
 }
 

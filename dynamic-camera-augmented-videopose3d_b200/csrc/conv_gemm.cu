@@ -35,8 +35,9 @@ struct GemmCfg {
   static constexpr int kOutStageBytes = 4 * 32 * 128;  // per epilogue warp: 32 rows x 128 B staging for the TMA store
   static constexpr int kBarBytes = 256;
   static constexpr int kStatBytes = 4 * BN * 2 * 4;  // per epilogue warp: BN x {sum, sum of squares} fp32
+  static constexpr int kAffineBytes = 2 * BN * 4;    // scale / shift of the CTA's current column tile
   static constexpr int kSmemBytes =
-      kStages * kStageBytes + kOutStageBytes + kBarBytes + kStatBytes + 1024;  // +1024: alignment slack
+      kStages * kStageBytes + kOutStageBytes + kBarBytes + kStatBytes + kAffineBytes + 1024;  // +1024: alignment slack
 };
 
 template <int DT>
@@ -127,6 +128,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   float* stat_smem = reinterpret_cast<float*>(out_stage + Cfg::kOutStageBytes + Cfg::kBarBytes);
+  float* affine_smem = stat_smem + Cfg::kStatBytes / 4;  // [0, BN) scale, [BN, 2 BN) shift
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -249,11 +251,25 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
     };
     if (p.stat_sum != nullptr) stat_flush();
+    int affine_n0 = -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(tile, p);
       if (p.stat_sum != nullptr && tc.n0 != stat_n0) {
         stat_flush();
         stat_n0 = tc.n0;
+      }
+      if (p.scale != nullptr && tc.n0 != affine_n0) {
+        // per-channel scale / shift of this column tile -> shared memory (once per launch when the grid is a multiple
+        // of n_tiles). Named barrier 1 over the 128 epilogue threads on both sides: nobody still reads the old tile's
+        // values, everybody sees the new ones.
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int e = threadIdx.x - 64;
+        for (int j = e; j < BN; j += 128) {
+          affine_smem[j] = __ldg(p.scale + tc.n0 * BN + j);
+          affine_smem[BN + j] = __ldg(p.shift + tc.n0 * BN + j);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        affine_n0 = tc.n0;
       }
       const int t = tc.t0 + row;
       const bool row_ok = t < p.rows_out;
@@ -262,6 +278,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool res_row_ok = p.res_rows <= 0 || (res_row >= 0 && res_row < p.res_rows);
       const long long res_off =
           (long long)tc.seq * p.res_seq_stride + res_row * p.res_row_stride - p.res_col_off;
+      // 16-bit residual rows are prefetched one 32-column chunk ahead (the loads of chunk 0 go out before the wait for
+      // the accumulator): their HBM / L2 latency was the dominant epilogue stall
+      const bool res_any = ET::kBytes == 2 && p.res != nullptr && row_ok && res_row_ok;
+      auto res_in_window = [&](int c) {
+        const int col0 = tc.n0 * BN + c * 32;
+        return p.res_cols <= 0 || (col0 >= p.res_col_off && col0 < p.res_col_off + p.res_cols);
+      };
+      auto res_load = [&](int c, uint4 (&r)[4]) {
+        if (res_any && res_in_window(c)) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.res) + res_off +
+                                                           tc.n0 * BN + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) r[j] = __ldg(r4 + j);
+        }
+      };
+      uint4 rcur[4], rnext[4];
+      res_load(0, rcur);
 
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
@@ -270,6 +303,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + acc * BN + c * 32 + (static_cast<uint32_t>(quad * 32) << 16), v);
+        if (c + 1 < BN / 32) res_load(c + 1, rnext);
         tmem_wait_ld();
         const int col0 = tc.n0 * BN + c * 32;
         float f[32];
@@ -301,12 +335,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           acc_s[1] += q[0];
         }
         if (p.scale != nullptr) {
-          const float4* sc4 = reinterpret_cast<const float4*>(p.scale + col0);
-          const float4* sh4 = reinterpret_cast<const float4*>(p.shift + col0);
+          const float4* sc4 = reinterpret_cast<const float4*>(affine_smem + c * 32);
+          const float4* sh4 = reinterpret_cast<const float4*>(affine_smem + BN + c * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 sc = __ldg(sc4 + j);
-            const float4 sh = __ldg(sh4 + j);
+            const float4 sc = sc4[j];
+            const float4 sh = sh4[j];
             f[4 * j + 0] = fmaf(f[4 * j + 0], sc.x, sh.x);
             f[4 * j + 1] = fmaf(f[4 * j + 1], sc.y, sh.y);
             f[4 * j + 2] = fmaf(f[4 * j + 2], sc.z, sh.z);
@@ -321,10 +355,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (p.res != nullptr && res_row_ok &&
               (p.res_cols <= 0 || (col0 >= p.res_col_off && col0 < p.res_col_off + p.res_cols))) {
             if (ET::kBytes == 2) {
-              const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.res) + res_off + col0);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const uint4 r = __ldg(r4 + j);
+                const uint4 r = rcur[j];
                 const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -390,6 +423,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
       }
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);

@@ -74,7 +74,9 @@ struct DropoutParams {
   float p;
   unsigned long long seed;
   unsigned long long stream;
+  const unsigned long long* step_counter;
 };
+cudaError_t launch_counter_add(unsigned long long* counter, unsigned long long inc, cudaStream_t stream);
 cudaError_t launch_bn_finalize(const double* sum, const double* sqsum, long long count, const float* gamma,
                                const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                                long long* nbt, float* scale, float* shift, float* mean, float* invstd, int c, int c_pad,

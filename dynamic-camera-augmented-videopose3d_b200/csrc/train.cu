@@ -76,8 +76,10 @@ __device__ __forceinline__ DropCtx make_drop(const DropoutParams& d) {
   c.thresh = (uint32_t)(d.p * 65536.f + 0.5f);
   c.keep_scale = d.p > 0.f ? 1.f / (1.f - d.p) : 1.f;
   c.key = make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32));
-  c.s_lo = (uint32_t)d.stream;
-  c.s_hi = (uint32_t)(d.stream >> 32);
+  // counter words 2, 3: layer stream and the training step (device counter, so graph replays differ)
+  const unsigned long long step = d.step_counter != nullptr ? *d.step_counter : 0ull;
+  c.s_lo = (uint32_t)d.stream ^ (uint32_t)(step >> 32);
+  c.s_hi = (uint32_t)step;
   return c;
 }
 // multipliers (0 or 1/(1-p)) of the 8 channels of group `grp` in row `row`
@@ -426,6 +428,12 @@ grad_pack_rows_kernel(const float* __restrict__ src, void* __restrict__ dst, lon
     }
     if (col_sum != nullptr && k < c) atomicAdd(col_sum + k, acc);
   }
+}
+
+__global__ void counter_add_kernel(unsigned long long* counter, unsigned long long inc) { *counter += inc; }
+cudaError_t launch_counter_add(unsigned long long* counter, unsigned long long inc, cudaStream_t stream) {
+  counter_add_kernel<<<1, 1, 0, stream>>>(counter, inc);
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------- launchers

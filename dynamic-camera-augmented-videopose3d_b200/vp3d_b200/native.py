@@ -49,7 +49,7 @@ class WgradArgs(C.Structure):
 
 class Dropout(C.Structure):
     """struct vp3d_dropout (include/vp3d_b200.h)"""
-    _fields_ = [('p', C.c_float), ('seed', C.c_ulonglong), ('stream', C.c_ulonglong)]
+    _fields_ = [('p', C.c_float), ('seed', C.c_ulonglong), ('stream', C.c_ulonglong), ('step_counter', C.c_void_p)]
 
 
 _SIGNATURES = {
@@ -80,6 +80,7 @@ _SIGNATURES = {
                                                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     'vp3d_bn_act_bwd_apply': (C.c_int, [C.c_int] + [C.c_void_p] * 6 + [C.c_longlong, C.c_longlong, C.c_int, C.c_int,
                                                                       C.POINTER(Dropout)] + [C.c_void_p] * 7),
+    'vp3d_counter_add': (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_void_p]),
     'vp3d_grad_scale': (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     'vp3d_grad_pack_rows': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),

@@ -220,10 +220,17 @@ def conv_block(dt, a, a_view, w, taps, tap_row_step, k_per_tap, rows_out, out, o
 
 
 # ------------------------------------------------------------------------------------------------ training path
-def make_dropout(p, seed, stream):
+def make_dropout(p, seed, stream, step_counter=None):
+    """step_counter: optional int64 device tensor (one element) the kernels read as the training-step number."""
     d = Dropout()
     d.p, d.seed, d.stream = float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream) & 0xFFFFFFFFFFFFFFFF
+    d.step_counter = None if step_counter is None else step_counter.data_ptr()
     return d
+
+
+def counter_add(counter, inc=1):
+    with torch.cuda.device(counter.device):
+        check(lib().vp3d_counter_add(_ptr(counter), int(inc), _stream()), 'counter_add')
 
 
 def wgrad(dt, dz, dz_view, a, a_view, co_pad, ci_pad, taps, dw_packed, b_row_off=0, b_tap_row_step=0,

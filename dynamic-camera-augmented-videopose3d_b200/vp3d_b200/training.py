@@ -19,7 +19,6 @@ from .temporal import K_ALIGN, N_TILE, LayerPlan, _round_up, _run_layer, resolve
 
 SHRINK_PAD = 128      # shrink-layer output channels are padded to one 128-row MMA tile for its weight gradient
 STATS_IN_EPILOGUE_MIN_K = 2048
-_step_counter = [0]
 grad_ready_hook = None   # set by vp3d_b200.ddp: called as hook(parameter, gradient) as soon as a gradient is issued
 grad_finish_hook = None  # ... and once at the end of the backward (waits for the outstanding all-reduces)
 sync_bn_group = None     # process group over which train-mode BatchNorm statistics are summed (None: per replica)
@@ -37,9 +36,19 @@ def _conv_w(dt, conv, rows_pad, k_pad, transpose=0):
     return ops.pack_conv_weight(dt, conv.weight, rows_pad, k_pad, transpose=transpose)
 
 
-def _dropout_for(model, layer_idx, step):
+def _step_counter(model, dev):
+    """Per-model training-step counter on the device (int64), ticked once per training forward by a kernel so that a
+    captured CUDA graph of the step draws new dropout masks on every replay."""
+    c = model.__dict__.get('_vp3d_step_counter')
+    if c is None or c.device != dev:
+        c = torch.zeros(1, dtype=torch.int64, device=dev)
+        model.__dict__['_vp3d_step_counter'] = c
+    return c
+
+
+def _dropout_for(model, layer_idx, counter):
     p = float(model.drop.p) if model.training else 0.0
-    return ops.make_dropout(p, torch.initial_seed(), step * 64 + layer_idx)
+    return ops.make_dropout(p, torch.initial_seed(), layer_idx, counter)
 
 
 def _forward_stack(model, x, dt):
@@ -51,8 +60,9 @@ def _forward_stack(model, x, dt):
     c_pad = _round_up(ch, N_TILE)
     c_in_pad = _round_up(c_in, K_ALIGN)
     dev = x.device
-    _step_counter[0] += 1
-    step = _step_counter[0]
+    counter = _step_counter(model, dev)
+    ops.counter_add(counter, 1)
+    step = counter.clone()   # this call's own copy: its backward sees the same value even if another forward runs first
     layers = []
 
     def conv_bn_act(idx, conv, bn, a_in, t, cin, cin_pad, plan, res=None, res_t=0, res_mul=1, res_off=0):

@@ -203,7 +203,15 @@ int vp3d_col_stats(int dtype, const void* z, long long rows, int c_pad, double* 
 
 /* Dropout description shared by forward and backward: keep-mask = Philox4x32-10(seed, stream, row, channel group)
  * >= p; kept values are multiplied by 1 / (1 - p) (nn.Dropout, TemporalModel.py:28,127,134-135). p == 0: off. */
-typedef struct vp3d_dropout { float p; unsigned long long seed; unsigned long long stream; } vp3d_dropout;
+typedef struct vp3d_dropout {
+  float p;
+  unsigned long long seed;
+  unsigned long long stream;              /* distinguishes layers */
+  const unsigned long long* step_counter; /* optional device counter read by the kernel and mixed into the Philox
+                                             counter: a captured CUDA graph draws a fresh mask on every replay */
+} vp3d_dropout;
+/* *counter += inc on the stream (one thread): the per-step tick of step_counter, capturable in a CUDA graph. */
+int vp3d_counter_add(unsigned long long* counter, unsigned long long inc, void* stream);
 
 /* a[s][t][c] = dropout(relu(z[s][t][c] * scale[c] + shift[c])) + res[s][t * res_row_mul + res_row_off][c]
  * (TemporalModel.py:127,134-135 / :189,194-195). z, a: [seqs * rows_per_seq][c_pad]; res: [seqs][res_seq_rows][c_pad]
