@@ -491,7 +491,7 @@ def main():
     def step_e2e():
         # public host-buffer entry point: chunks of sequences, upload / compute / download overlapped on 3 streams;
         # returns after the last result byte is in y_host
-        return pipeline.infer_host(model, x_host, y_host, chunk_seqs=max(1, seqs // 8))
+        return pipeline.infer_host(model, x_host, y_host, chunk_seqs=max(1, seqs // 4))
 
     for _ in range(warm):
         step_resident()
