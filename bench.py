@@ -268,7 +268,7 @@ def bench_train(args, rank, world, dev, steps, warm):
     model.load_state_dict(oracle_state())
     model = model.to(dev).train()
     model.operand_dtype = args.dtype if args.dtype != 'tf32' else 'fp16'
-    use_graph = world == 1 and not args.no_graph
+    use_graph = not args.no_graph      # N > 1: the NCCL all-reduces are captured in the graph as well
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, amsgrad=True, capturable=use_graph)       # run.py:662
     sync = None
     if world > 1:
@@ -347,10 +347,12 @@ def bench_train(args, rank, world, dev, steps, warm):
     other = ('vp3d_project_points', 'vp3d_mpjpe_fwd', 'vp3d_mpjpe_bwd', 'vp3d_pack_rows', 'vp3d_pack_conv_weight',
              'vp3d_wgrad_finish', 'vp3d_grad_scale', 'vp3d_grad_pack_rows')
     inst = min(steps, 3)
+    coll0 = (sync.collectives, sync.bytes_reduced) if sync is not None else (0, 0)
     with LaunchTimer(lib, gemm + bn + other) as lt:   # per-kernel-family timing needs the eager path
         for _ in range(inst):
             step(Wd, qd, td, camd)
         torch.cuda.synchronize()
+    coll_per_step = ((sync.collectives - coll0[0]) // inst, (sync.bytes_reduced - coll0[1]) / inst) if sync else (0, 0)
     gemm_ms, bn_ms, proj_ms = lt.ms(*gemm) / inst, lt.ms(*bn) / inst, lt.ms('vp3d_project_points') / inst
     conv_ms, wgrad_ms = lt.ms('vp3d_conv_block_fwd') / inst, lt.ms('vp3d_wgrad') / inst
     mpjpe_ms = lt.ms('vp3d_mpjpe_fwd', 'vp3d_mpjpe_bwd') / inst
@@ -386,8 +388,7 @@ def bench_train(args, rank, world, dev, steps, warm):
                                'amsgrad (BASELINE configs[2])' % batch,
                    'grad_exchange': 'none (1 GPU)' if world == 1 else 'NCCL all-reduce (avg) of fp32 gradients, large '
                                     'tensors overlapped with backward, %d collectives, %.1f MB per step'
-                                    % (sync.collectives // max(1, warm + steps + inst + 2 + steps),
-                                       sync.bytes_reduced / max(1, warm + steps + inst + 2 + steps) / 1e6),
+                                    % (coll_per_step[0], coll_per_step[1] / 1e6),
                    'bn': 'per-replica batch statistics',
                    'launch': 'one CUDA graph per step (vp3d_b200.graphs.GraphedTrainStep)' if use_graph else 'eager'},
         'e2e': {'value': total / (ms_e2e * 1e-3), 'unit': 'samples/s', 'ms_per_step': ms_e2e / steps,
