@@ -150,3 +150,60 @@ def test_repack_after_parameter_update():
         m.shrink.bias.add_(1.0)
         y1 = m(x)
     assert torch.allclose(y1, y0 + 1.0, atol=1e-6)
+
+
+@pytest.mark.parametrize('fw,ch', [([3, 3, 3], 1024), ([3, 3, 3, 3, 3], 1024)])
+def test_streaming_equals_full_causal_forward(fw, ch):
+    """BASELINE configs[3]: per-layer ring buffers, one frame per step, against the full causal forward on the
+    left-padded sequence (generators.py:193-195 replicates the first frame) and against the CPU oracle."""
+    from vp3d_b200.streaming import CausalStream
+    sd = otm.init_state(17, 2, 17, fw, channels=ch, seed=5)
+    m = build(TemporalModel, sd, 17, 17, fw, ch, causal=True)
+    rf = m.receptive_field()
+    S, T = 5, 40
+    g = torch.Generator().manual_seed(6)
+    x = torch.rand(S, T, 17, 2, generator=g) * 2 - 1
+    xpad = torch.cat([x[:, :1].expand(S, rf - 1, 17, 2), x], dim=1).contiguous()
+    with torch.no_grad():
+        full = m(xpad.cuda()).cpu()                                  # (S, T, 17, 3)
+        ref = otm.forward(sd, xpad, fw, causal=True)
+    assert rel_err(full, ref) < REL_TOL
+    st = CausalStream(m, S)
+    xc = x.cuda()
+    st.prime(xc[:, 0])
+    outs = []
+    with torch.no_grad():
+        for t in range(T):
+            outs.append(st.step(xc[:, t]).cpu())
+    stream = torch.stack(outs, dim=1)
+    assert stream.shape == full.shape
+    assert rel_err(stream, ref) < REL_TOL
+    assert rel_err(stream, full) < 5e-4      # same kernels, same operands: only tile shapes / summation order differ
+
+
+def test_streaming_with_per_frame_camera():
+    from vp3d_b200.streaming import CausalStream
+    from common.camera import world_to_image
+    fw = [3, 3, 3]
+    sd = otm.init_state(17, 2, 17, fw, channels=1024, seed=7)
+    m = build(TemporalModel, sd, 17, 17, fw, 1024, causal=True)
+    S, T = 4, 30
+    g = torch.Generator().manual_seed(8)
+    X = torch.randn(S, T, 17, 3, generator=g) * 0.3
+    X[..., 2] += 4.0
+    q = torch.tensor([1.0, 0, 0, 0]) + torch.randn(S, T, 4, generator=g) * 0.05
+    q = q / q.norm(dim=-1, keepdim=True)
+    tr = torch.randn(S, T, 3, generator=g) * 0.1
+    cam = torch.tensor([2.29, 2.2876, 0.0251, 0.0289, -0.2071, 0.2478, -0.0031, -0.00098, -0.0014]).repeat(S, 1)
+    Xd, qd, td, camd = X.cuda(), q.cuda(), tr.cuda(), cam.cuda()
+    _, x2d = world_to_image(Xd, qd, td, camd, return_camera_space=False)
+    rf = m.receptive_field()
+    xpad = torch.cat([x2d[:, :1].expand(S, rf - 1, 17, 2), x2d], dim=1).contiguous()
+    with torch.no_grad():
+        full = m(xpad).cpu()
+    st = CausalStream(m, S)
+    st.prime(x2d[:, 0].contiguous())
+    with torch.no_grad():
+        outs = [st.step_world(Xd[:, t].contiguous(), qd[:, t].contiguous(), td[:, t].contiguous(), camd).cpu()
+                for t in range(T)]
+    assert rel_err(torch.stack(outs, dim=1), full) < 5e-4
