@@ -346,7 +346,7 @@ def bench_train(args, rank, world, dev, steps, warm):
     bn = ('vp3d_bn_finalize', 'vp3d_bn_act_fwd', 'vp3d_bn_act_bwd_reduce', 'vp3d_bn_act_bwd_apply')
     other = ('vp3d_project_points', 'vp3d_mpjpe_fwd', 'vp3d_mpjpe_bwd', 'vp3d_pack_rows', 'vp3d_pack_conv_weight',
              'vp3d_wgrad_finish', 'vp3d_grad_scale', 'vp3d_grad_pack_rows')
-    inst = min(steps, 3)
+    inst = min(steps, 10)
     coll0 = (sync.collectives, sync.bytes_reduced) if sync is not None else (0, 0)
     with LaunchTimer(lib, gemm + bn + other) as lt:   # per-kernel-family timing needs the eager path
         for _ in range(inst):
@@ -407,6 +407,40 @@ def bench_train(args, rank, world, dev, steps, warm):
                                 'frames_per_launch': batch * RF},
         'mpjpe_ms_per_step': mpjpe_ms,
     }
+
+
+def bench_stream(args, rank, world, dev):
+    """BASELINE configs[3]: causal 243-frame model, S concurrent streams advancing one frame per step with this
+    frame's camera (quaternion, translation, distortion intrinsics) per stream; plus single-stream latency."""
+    from common.models.TemporalModel import TemporalModel
+    from vp3d_b200.streaming import CausalStream
+    model = TemporalModel(17, 2, 17, FW, causal=True, dropout=0.25, channels=1024)
+    model.load_state_dict(oracle_state())
+    model = model.to(dev).eval()
+    model.operand_dtype = args.dtype if args.dtype != 'tf32' else 'fp16'
+    out = {}
+    for S, steps in ((1024, 200), (1, 200)):
+        g = torch.Generator().manual_seed(99 + rank)
+        X = (torch.randn(S, 17, 3, generator=g) * 0.3 + torch.tensor([0.0, 0.0, 4.0])).to(dev)
+        q = torch.tensor([1.0, 0, 0, 0]).repeat(S, 1).to(dev)
+        t = torch.zeros(S, 3, device=dev)
+        cam = torch.tensor(H36M_CAM0).repeat(S, 1).to(dev)
+        st = CausalStream(model, S)
+        with torch.no_grad():
+            for _ in range(20):
+                st.step_world(X, q, t, cam)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                st.step_world(X, q, t, cam)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out['streams_%d' % S] = {'ms_per_step': ms, 'frames_per_s': S / (ms * 1e-3)}
+    out['config'] = ('TemporalModel(causal=True) 3,3,3,3,3, per-layer ring buffers, one frame per step, per-frame camera '
+                     'projection with distortion on the device (BASELINE configs[3]); eager launches (17 per step)')
+    return out
 
 
 def main():
@@ -530,7 +564,7 @@ def main():
 
     lib.vp3d_conv_block_fwd, lib.vp3d_pack_rows = wrap_conv, wrap_pack
     try:
-        inst_steps = min(steps, 3)
+        inst_steps = min(steps, 10)
         for _ in range(inst_steps):
             step_resident()
         torch.cuda.synchronize()
@@ -597,7 +631,10 @@ def main():
         del x_dev, x_host, y_host
         torch.cuda.empty_cache()
         train = bench_train(args, rank, world, dev, max(steps, 10), warm)
+    stream = bench_stream(args, rank, world, dev) if args.mode == 'all' and rank == 0 else None
     if rank == 0:
+        if stream is not None:
+            line['stream'] = stream
         if train is not None:
             if not args.no_cpu_baseline:
                 v, cores, sample = cpu_port_train_samples_per_s()

@@ -117,21 +117,114 @@ __device__ __forceinline__ float3 transform_point(const PointOps& o, long long i
   return X;
 }
 
-__global__ void __launch_bounds__(256)
+// Camera records in registers: consecutive points mostly share their frame's quaternion / translation / intrinsics, so
+// a thread divides once per 4-point group (32-bit when the point count allows) and afterwards only counts up,
+// reloading a record when its index changes. (The first version divided twice per point in 64 bits and re-read the
+// 16 camera floats per point: the kernel was instruction-bound at 37 % of HBM peak.)
+struct CamRegs {
+  Quat q;
+  float3 t;
+  float cam[9];
+};
+
+template <typename IndexT>
+struct RecordCursor {
+  IndexT idx, rem, per;
+  __device__ __forceinline__ RecordCursor(IndexT point, IndexT per_) : per(per_) {
+    idx = point / per_;
+    rem = point - idx * per_;
+  }
+  // advances to the next point; true when the record index changed
+  __device__ __forceinline__ bool next() {
+    if (++rem == per) {
+      rem = 0;
+      ++idx;
+      return true;
+    }
+    return false;
+  }
+};
+
+__device__ __forceinline__ void load_pose(const PointOps& o, long long qi, CamRegs& r) {
+  const float4 qq = __ldg(reinterpret_cast<const float4*>(o.q) + qi);   // rows of 4 floats: always 16-byte aligned
+  // world -> camera and ROTATE|CONJ rotate by the conjugate: negate once per record, not once per point
+  const bool conj = (o.mode & 1) || ((o.mode & 4) && (o.mode & 8));
+  r.q = conj ? Quat{qq.x, -qq.y, -qq.z, -qq.w} : Quat{qq.x, qq.y, qq.z, qq.w};
+  if (o.mode & 3) {
+    const float* tt = o.t + 3 * qi;
+    r.t = make_float3(__ldg(tt + 0), __ldg(tt + 1), __ldg(tt + 2));
+  }
+}
+__device__ __forceinline__ void load_intrinsics(const PointOps& o, long long ci, CamRegs& r) {
+  const float* c = o.cam + 9 * ci;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) r.cam[k] = __ldg(c + k);
+}
+
+__device__ __forceinline__ float3 transform_regs(const PointOps& o, const CamRegs& r, float3 X) {
+  if (o.mode & 7) {
+    if (o.mode & 1) {
+      X.x = sub(X.x, r.t.x);
+      X.y = sub(X.y, r.t.y);
+      X.z = sub(X.z, r.t.z);
+      X = qrot_dev(r.q, X);
+    } else if (o.mode & 2) {
+      X = qrot_dev(r.q, X);
+      X.x = add(X.x, r.t.x);
+      X.y = add(X.y, r.t.y);
+      X.z = add(X.z, r.t.z);
+    } else {
+      X = qrot_dev(r.q, X);
+    }
+  }
+  return X;
+}
+
+// camera.py:54-67 with the intrinsics already in registers
+__device__ __forceinline__ float2 project_regs(const float3 X, const float (&cam)[9], int linear) {
+  const float xx = clamp_unit(__fdiv_rn(X.x, X.z));
+  const float yy = clamp_unit(__fdiv_rn(X.y, X.z));
+  float2 o;
+  if (linear) {
+    o.x = add(mul(cam[0], xx), cam[2]);
+    o.y = add(mul(cam[1], yy), cam[3]);
+    return o;
+  }
+  const float r2 = add(mul(xx, xx), mul(yy, yy));
+  const float r4 = mul(r2, r2);
+  const float r6 = mul(r4, r2);
+  const float radial = add(1.f, add(add(mul(cam[4], r2), mul(cam[5], r4)), mul(cam[6], r6)));
+  const float tan = add(mul(cam[7], xx), mul(cam[8], yy));
+  const float s = add(radial, tan);
+  o.x = add(mul(cam[0], add(mul(xx, s), mul(cam[7], r2))), cam[2]);
+  o.y = add(mul(cam[1], add(mul(yy, s), mul(cam[8], r2))), cam[3]);
+  return o;
+}
+
+template <typename IndexT>
+__global__ void __launch_bounds__(256, 4)
 project_points_kernel(const float* __restrict__ X, float* __restrict__ out3, float* __restrict__ out2, long long n_pts,
                       PointOps o, int vec_ok) {
   const long long n_quads = vec_ok ? (n_pts >> 2) : 0;
   const long long stride = (long long)gridDim.x * blockDim.x;
+  const bool has_pose = (o.mode & 7) != 0, has_proj = (o.mode & 16) != 0;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_quads; g += stride) {
     const float4* src = reinterpret_cast<const float4*>(X) + 3 * g;
     const float4 a = __ldg(src + 0), b = __ldg(src + 1), c = __ldg(src + 2);
     float3 P[4] = {{a.x, a.y, a.z}, {a.w, b.x, b.y}, {b.z, b.w, c.x}, {c.y, c.z, c.w}};
     float2 Q[4];
+    CamRegs r;
+    RecordCursor<IndexT> qc((IndexT)(4 * g), (IndexT)o.pts_per_q), cc((IndexT)(4 * g), (IndexT)o.pts_per_cam);
+    if (has_pose) load_pose(o, (long long)qc.idx, r);
+    if (has_proj) load_intrinsics(o, (long long)cc.idx, r);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const long long idx = 4 * g + i;
-      P[i] = transform_point(o, idx, P[i]);
-      if (o.mode & 16) Q[i] = project_dev(P[i], o.cam + 9 * (idx / o.pts_per_cam), o.mode & 32);
+      P[i] = transform_regs(o, r, P[i]);
+      if (has_proj) Q[i] = project_regs(P[i], r.cam, o.mode & 32);
+      if (i < 3) {
+        if (has_pose && qc.next()) load_pose(o, (long long)qc.idx, r);
+        if (has_proj && cc.next()) load_intrinsics(o, (long long)cc.idx, r);
+      }
     }
     if (out3 != nullptr) {
       float4* d = reinterpret_cast<float4*>(out3) + 3 * g;
@@ -175,7 +268,10 @@ cudaError_t launch_project_points(const float* X, float* out3, float* out2, long
   const long long cap = (long long)sm_count * 8;  // 8 resident CTAs of 256 threads per SM, grid-stride beyond
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  project_points_kernel<<<(unsigned)blocks, 256, 0, stream>>>(X, out3, out2, n_pts, o, vec_ok);
+  if (n_pts < (1LL << 31))
+    project_points_kernel<unsigned int><<<(unsigned)blocks, 256, 0, stream>>>(X, out3, out2, n_pts, o, vec_ok);
+  else
+    project_points_kernel<long long><<<(unsigned)blocks, 256, 0, stream>>>(X, out3, out2, n_pts, o, vec_ok);
   return cudaGetLastError();
 }
 

@@ -49,11 +49,11 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-// Philox4x32-10 (Salmon et al., SC'11): counter (c0..c3), key (k0, k1).
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+// Philox4x32-7 (Salmon et al., SC'11; 7 rounds is the fastest variant that passes BigCrush): counter (c0..c3), key.
+__device__ __forceinline__ uint4 philox4x32_7(uint4 c, uint2 k) {
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < 7; ++r) {
     const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
     const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
     c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
@@ -63,18 +63,21 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
+// One Philox block = 16 random bytes = the keep decisions of 2 adjacent rows x 8 channels (rows 2P and 2P+1 of channel
+// group grp): keep iff byte >= thresh, thresh = round(p * 256). The drop probability is therefore p quantised to
+// 1/256 (exact for the reference default 0.25) and kept values are scaled by 256 / (256 - thresh), so E[mask] = 1.
 struct DropCtx {
-  float p;
-  uint32_t thresh;  // keep iff 16-bit draw >= thresh
+  bool on;
+  uint32_t thresh;
   float keep_scale;
   uint2 key;
   uint32_t s_lo, s_hi;
 };
 __device__ __forceinline__ DropCtx make_drop(const DropoutParams& d) {
   DropCtx c;
-  c.p = d.p;
-  c.thresh = (uint32_t)(d.p * 65536.f + 0.5f);
-  c.keep_scale = d.p > 0.f ? 1.f / (1.f - d.p) : 1.f;
+  c.thresh = (uint32_t)(d.p * 256.f + 0.5f);
+  c.on = c.thresh > 0;
+  c.keep_scale = 256.f / (256.f - (float)c.thresh);
   c.key = make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32));
   // counter words 2, 3: layer stream and the training step (device counter, so graph replays differ)
   const unsigned long long step = d.step_counter != nullptr ? *d.step_counter : 0ull;
@@ -82,20 +85,16 @@ __device__ __forceinline__ DropCtx make_drop(const DropoutParams& d) {
   c.s_hi = (uint32_t)step;
   return c;
 }
-// multipliers (0 or 1/(1-p)) of the 8 channels of group `grp` in row `row`
-__device__ __forceinline__ void drop_mult8(const DropCtx& d, long long row, int grp, float (&m)[8]) {
-  if (d.p <= 0.f) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) m[i] = 1.f;
-    return;
-  }
-  const uint4 r = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)((unsigned long long)row >> 32) ^ (grp * 0x9E3779B1u),
-                                           d.s_lo, d.s_hi), d.key);
-  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+// random bytes of row pair `pair` (rows 2*pair, 2*pair + 1), channel group grp: .x,.y -> even row, .z,.w -> odd row
+__device__ __forceinline__ uint4 drop_bits(const DropCtx& d, long long pair, int grp) {
+  return philox4x32_7(make_uint4((uint32_t)pair, (uint32_t)((unsigned long long)pair >> 32) ^ (grp * 0x9E3779B1u),
+                                 d.s_lo, d.s_hi), d.key);
+}
+__device__ __forceinline__ void drop_mult8(const DropCtx& d, uint32_t w0, uint32_t w1, float (&m)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    m[2 * i] = (w[i] & 0xFFFFu) >= d.thresh ? d.keep_scale : 0.f;
-    m[2 * i + 1] = (w[i] >> 16) >= d.thresh ? d.keep_scale : 0.f;
+    m[i] = ((w0 >> (8 * i)) & 0xFFu) >= d.thresh ? d.keep_scale : 0.f;
+    m[4 + i] = ((w1 >> (8 * i)) & 0xFFu) >= d.thresh ? d.keep_scale : 0.f;
   }
 }
 
@@ -134,11 +133,16 @@ bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sq
 }
 
 // ---------------------------------------------------------------------------------------------- row-walking kernels
-// Shared shape of the four HBM-bound kernels below: blockDim.x = kEwThreads threads, thread i of a block owns channel
-// group (blockIdx.y * kEwThreads + i) -- 8 consecutive channels, one 16-byte vector -- keeps that group's per-channel
-// constants in registers and walks rows blockIdx.x, blockIdx.x + gridDim.x, ... four at a time (all loads of the
-// four rows are issued before the first use). A warp reads 512 contiguous bytes per row.
-constexpr int kRowUnroll = 4;
+// Shared shape of the HBM-bound kernels below: a thread owns one channel group (8 consecutive channels = one 16-byte
+// vector), keeps that group's per-channel constants in registers and processes row PAIRS (rows 2P, 2P+1: one Philox
+// block covers a pair), kPairUnroll pairs at a time with all loads issued before the first use. A block covers
+// kEwGroups channel groups x kEwLanes pair lanes; in one iteration it touches 2 * kEwLanes * kPairUnroll ADJACENT rows,
+// i.e. one contiguous span of HBM per channel slab.
+constexpr int kEwGroups = 128;   // 1024 channels per block slab
+constexpr int kEwLanes = 2;
+constexpr int kRedLanes = 4;     // reductions: 512-thread blocks, ~1 per SM, so few double atomics reach L2
+constexpr int kPairUnroll = 2;   // 4 rows in flight per thread
+constexpr int kRowsPerIter = 2 * kEwLanes * kPairUnroll;
 
 __device__ __forceinline__ void load8(const float* p, int grp, float (&o)[8]) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p) + 2 * grp);
@@ -146,70 +150,93 @@ __device__ __forceinline__ void load8(const float* p, int grp, float (&o)[8]) {
   o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
 }
 
+// rows handled by this thread in iteration `it`: pair P = (it * gridDim.x + blockIdx.x) * kEwLanes * kPairUnroll +
+// u * kEwLanes + lane, rows 2P and 2P + 1
+template <int LANES>
+struct RowWalkT {
+  int gl, lane, grp;
+  __device__ __forceinline__ RowWalkT() {
+    gl = threadIdx.x % kEwGroups;
+    lane = threadIdx.x / kEwGroups;
+    grp = blockIdx.y * kEwGroups + gl;
+  }
+  __device__ __forceinline__ long long pair(long long it, int u) const {
+    return (it * gridDim.x + blockIdx.x) * (LANES * kPairUnroll) + u * LANES + lane;
+  }
+};
+using RowWalk = RowWalkT<kEwLanes>;
+
 template <int DT>
-__global__ void __launch_bounds__(kEwThreads)
+__global__ void __launch_bounds__(kEwGroups * kEwLanes, 3)
 bn_act_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                   const uint4* __restrict__ res, long long rows, long long rows_per_seq, long long res_seq_rows,
                   int res_row_mul, int res_row_off, int groups, DropoutParams dp, uint4* __restrict__ a) {
-  const int grp = blockIdx.y * kEwThreads + threadIdx.x;
-  if (grp >= groups) return;
+  const RowWalk w;
+  if (w.grp >= groups) return;
   const DropCtx drop = make_drop(dp);
   float sc[8], sh[8];
-  load8(scale, grp, sc);
-  load8(shift, grp, sh);
-  const long long step = gridDim.x;
-  for (long long r0 = blockIdx.x; r0 < rows; r0 += step * kRowUnroll) {
-    uint4 zv[kRowUnroll], rv[kRowUnroll];
+  load8(scale, w.grp, sc);
+  load8(shift, w.grp, sh);
+  const long long iters = (rows + (long long)gridDim.x * kRowsPerIter - 1) / ((long long)gridDim.x * kRowsPerIter);
+  for (long long it = 0; it < iters; ++it) {
+    uint4 zv[2 * kPairUnroll], rv[2 * kPairUnroll];
 #pragma unroll
-    for (int u = 0; u < kRowUnroll; ++u) {
-      const long long row = r0 + u * step;
+    for (int u = 0; u < 2 * kPairUnroll; ++u) {
+      const long long row = 2 * w.pair(it, u >> 1) + (u & 1);
       if (row < rows) {
-        zv[u] = __ldg(z + row * groups + grp);
+        zv[u] = __ldg(z + row * groups + w.grp);
         if (res != nullptr) {
           const long long seq = row / rows_per_seq;
           const long long t = row - seq * rows_per_seq;
-          rv[u] = __ldg(res + (seq * res_seq_rows + t * res_row_mul + res_row_off) * groups + grp);
+          rv[u] = __ldg(res + (seq * res_seq_rows + t * res_row_mul + res_row_off) * groups + w.grp);
         }
       }
     }
 #pragma unroll
-    for (int u = 0; u < kRowUnroll; ++u) {
-      const long long row = r0 + u * step;
-      if (row < rows) {
-        float v[8], m[8];
-        unpack8<DT>(zv[u], v);
-        drop_mult8(drop, row, grp, m);
+    for (int pu = 0; pu < kPairUnroll; ++pu) {
+      const long long P = w.pair(it, pu);
+      if (2 * P >= rows) continue;
+      uint4 bits = make_uint4(0, 0, 0, 0);
+      if (drop.on) bits = drop_bits(drop, P, w.grp);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f) * m[k];
-        if (res != nullptr) {
-          float r[8];
-          unpack8<DT>(rv[u], r);
+      for (int h = 0; h < 2; ++h) {
+        const long long row = 2 * P + h;
+        if (row < rows) {
+          float v[8], m[8];
+          unpack8<DT>(zv[2 * pu + h], v);
+          if (drop.on) {
+            drop_mult8(drop, h ? bits.z : bits.x, h ? bits.w : bits.y, m);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] += r[k];
+            for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f) * m[k];
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f);
+          }
+          if (res != nullptr) {
+            float r[8];
+            unpack8<DT>(rv[2 * pu + h], r);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] += r[k];
+          }
+          a[row * groups + w.grp] = pack8<DT>(v);
         }
-        a[row * groups + grp] = pack8<DT>(v);
       }
     }
   }
 }
 
-// Reduction kernels (col_stats, bn_act_bwd_reduce) use blocks of kRedLanes row lanes x kRedGroups channel groups: the
-// lanes of a block are combined in shared memory, so one double atomic per channel per block reaches L2, and the grid
-// is capped at 2 blocks per SM (same-address atomics serialise: thousands of blocks would cost more than the reads).
-constexpr int kRedGroups = 64;
-constexpr int kRedLanes = 4;
-constexpr int kRedUnroll = 8;
-
-__device__ __forceinline__ void block_combine_and_add(const float (&a1)[8], const float (&a2)[8], int gl, int rl, int grp,
+// Reductions: the pair lanes of a block are combined in shared memory, then one double atomic per channel per block
+// reaches L2; the grid is capped (reduce_grid) because same-address atomics serialise.
+__device__ __forceinline__ void block_combine_and_add(const float (&a1)[8], const float (&a2)[8], int gl, int lane, int grp,
                                                       int groups, double* __restrict__ out1, double* __restrict__ out2) {
-  __shared__ float part[2][kRedLanes][kRedGroups * 8 + 4];
+  __shared__ float part[2][kRedLanes][kEwGroups * 8 + 4];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    part[0][rl][gl * 8 + k] = a1[k];
-    part[1][rl][gl * 8 + k] = a2[k];
+    part[0][lane][gl * 8 + k] = a1[k];
+    part[1][lane][gl * 8 + k] = a2[k];
   }
   __syncthreads();
-  if (rl == 0 && grp < groups) {
+  if (lane == 0 && grp < groups) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       double s1 = 0.0, s2 = 0.0;
@@ -225,27 +252,28 @@ __device__ __forceinline__ void block_combine_and_add(const float (&a1)[8], cons
 }
 
 // per-channel sum / sum of squares of a stored matrix (train-mode BatchNorm statistics of layers whose GEMM is too
-// short to hide the in-epilogue reduction): one double atomic per channel per block
+// short to hide the in-epilogue reduction)
 template <int DT>
-__global__ void __launch_bounds__(kRedGroups * kRedLanes)
+__global__ void __launch_bounds__(kEwGroups * kRedLanes)
 col_stats_kernel(const uint4* __restrict__ z, long long rows, int groups, double* __restrict__ sum,
                  double* __restrict__ sqsum) {
-  const int gl = threadIdx.x % kRedGroups, rl = threadIdx.x / kRedGroups;
-  const int grp = blockIdx.y * kRedGroups + gl;
+  constexpr int kU = 8;  // rows in flight per thread; a block reads kRedLanes * kU adjacent rows per iteration
+  const int gl = threadIdx.x % kEwGroups, lane = threadIdx.x / kEwGroups;
+  const int grp = blockIdx.y * kEwGroups + gl;
   float a1[8], a2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) a1[k] = a2[k] = 0.f;
   if (grp < groups) {
-    const long long step = (long long)gridDim.x * kRedLanes;
-    for (long long r0 = (long long)blockIdx.x * kRedLanes + rl; r0 < rows; r0 += step * kRedUnroll) {
-      uint4 zv[kRedUnroll];
+    for (long long base = (long long)blockIdx.x * (kRedLanes * kU); base < rows;
+         base += (long long)gridDim.x * (kRedLanes * kU)) {
+      uint4 zv[kU];
 #pragma unroll
-      for (int u = 0; u < kRedUnroll; ++u) {
-        const long long row = r0 + u * step;
+      for (int u = 0; u < kU; ++u) {
+        const long long row = base + u * kRedLanes + lane;
         zv[u] = row < rows ? __ldg(z + row * groups + grp) : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
-      for (int u = 0; u < kRedUnroll; ++u) {
+      for (int u = 0; u < kU; ++u) {
         float v[8];
         unpack8<DT>(zv[u], v);
 #pragma unroll
@@ -256,19 +284,24 @@ col_stats_kernel(const uint4* __restrict__ z, long long rows, int groups, double
       }
     }
   }
-  block_combine_and_add(a1, a2, gl, rl, grp, groups, sum, sqsum);
+  block_combine_and_add(a1, a2, gl, lane, grp, groups, sum, sqsum);
 }
 
 // ---------------------------------------------------------------------------------------------- backward
 // dy = g * dropout multiplier * [z * scale + shift > 0];  xhat = (z - mean) * invstd
 template <int DT>
-__device__ __forceinline__ void dy_xhat(const uint4& gu, const uint4& zu, long long row, int grp, const float (&sc)[8],
-                                        const float (&sh)[8], const float (&mu)[8], const float (&is)[8],
-                                        const DropCtx& drop, float (&dy)[8], float (&xh)[8]) {
+__device__ __forceinline__ void dy_xhat(const uint4& gu, const uint4& zu, const DropCtx& drop, uint32_t w0, uint32_t w1,
+                                        const float (&sc)[8], const float (&sh)[8], const float (&mu)[8],
+                                        const float (&is)[8], float (&dy)[8], float (&xh)[8]) {
   float gv[8], zv[8], m[8];
   unpack8<DT>(gu, gv);
   unpack8<DT>(zu, zv);
-  drop_mult8(drop, row, grp, m);
+  if (drop.on) {
+    drop_mult8(drop, w0, w1, m);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = 1.f;
+  }
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const bool on = fmaf(zv[k], sc[k], sh[k]) > 0.f;
@@ -278,107 +311,120 @@ __device__ __forceinline__ void dy_xhat(const uint4& gu, const uint4& zu, long l
 }
 
 template <int DT>
-__global__ void __launch_bounds__(kRedGroups * kRedLanes)
+__global__ void __launch_bounds__(kEwGroups * kRedLanes, 1)
 bn_act_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z, const float* __restrict__ scale,
                          const float* __restrict__ shift, const float* __restrict__ mean,
                          const float* __restrict__ invstd, long long rows, int groups, DropoutParams dp,
                          double* __restrict__ sum_dy, double* __restrict__ sum_dy_xhat) {
-  const int gl = threadIdx.x % kRedGroups, rl = threadIdx.x / kRedGroups;
-  const int grp = blockIdx.y * kRedGroups + gl;
+  const RowWalkT<kRedLanes> w;
   float a1[8], a2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) a1[k] = a2[k] = 0.f;
-  if (grp < groups) {
+  if (w.grp < groups) {
     const DropCtx drop = make_drop(dp);
     float sc[8], sh[8], mu[8], is[8];
-    load8(scale, grp, sc);
-    load8(shift, grp, sh);
-    load8(mean, grp, mu);
-    load8(invstd, grp, is);
-    constexpr int kU = 4;
-    const long long step = (long long)gridDim.x * kRedLanes;
-    for (long long r0 = (long long)blockIdx.x * kRedLanes + rl; r0 < rows; r0 += step * kU) {
-      uint4 gv[kU], zv[kU];
+    load8(scale, w.grp, sc);
+    load8(shift, w.grp, sh);
+    load8(mean, w.grp, mu);
+    load8(invstd, w.grp, is);
+    const long long iters = (rows + (long long)gridDim.x * (2 * kRedLanes * kPairUnroll) - 1) / ((long long)gridDim.x * (2 * kRedLanes * kPairUnroll));
+    for (long long it = 0; it < iters; ++it) {
+      uint4 gv[2 * kPairUnroll], zv[2 * kPairUnroll];
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const long long row = r0 + u * step;
+      for (int u = 0; u < 2 * kPairUnroll; ++u) {
+        const long long row = 2 * w.pair(it, u >> 1) + (u & 1);
         if (row < rows) {
-          gv[u] = __ldg(g + row * groups + grp);
-          zv[u] = __ldg(z + row * groups + grp);
+          gv[u] = __ldg(g + row * groups + w.grp);
+          zv[u] = __ldg(z + row * groups + w.grp);
         }
       }
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const long long row = r0 + u * step;
-        if (row < rows) {
-          float dy[8], xh[8];
-          dy_xhat<DT>(gv[u], zv[u], row, grp, sc, sh, mu, is, drop, dy, xh);
+      for (int pu = 0; pu < kPairUnroll; ++pu) {
+        const long long P = w.pair(it, pu);
+        if (2 * P >= rows) continue;
+        uint4 bits = make_uint4(0, 0, 0, 0);
+        if (drop.on) bits = drop_bits(drop, P, w.grp);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            a1[k] += dy[k];
-            a2[k] = fmaf(dy[k], xh[k], a2[k]);
+        for (int h = 0; h < 2; ++h) {
+          if (2 * P + h < rows) {
+            float dy[8], xh[8];
+            dy_xhat<DT>(gv[2 * pu + h], zv[2 * pu + h], drop, h ? bits.z : bits.x, h ? bits.w : bits.y, sc, sh, mu, is,
+                        dy, xh);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              a1[k] += dy[k];
+              a2[k] = fmaf(dy[k], xh[k], a2[k]);
+            }
           }
         }
       }
     }
   }
-  block_combine_and_add(a1, a2, gl, rl, grp, groups, sum_dy, sum_dy_xhat);
+  block_combine_and_add(a1, a2, w.gl, w.lane, w.grp, groups, sum_dy, sum_dy_xhat);
 }
 
 template <int DT>
-__global__ void __launch_bounds__(kEwThreads)
+__global__ void __launch_bounds__(kEwGroups * kEwLanes, 2)
 bn_act_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z, const float* __restrict__ scale,
                         const float* __restrict__ shift, const float* __restrict__ mean,
                         const float* __restrict__ invstd, long long rows, long long count, int c, int groups,
                         DropoutParams dp, const double* __restrict__ sum_dy, const double* __restrict__ sum_dy_xhat,
                         const float* __restrict__ gscale_buf, uint4* __restrict__ dz, float* __restrict__ d_gamma,
                         float* __restrict__ d_beta) {
-  const int grp = blockIdx.y * kEwThreads + threadIdx.x;
-  if (grp >= groups) return;
+  const RowWalk w;
+  if (w.grp >= groups) return;
   const DropCtx drop = make_drop(dp);
   const double inv_n = 1.0 / (double)count;
   float sc[8], sh[8], mu[8], is[8], m1[8], m2[8];
-  load8(scale, grp, sc);
-  load8(shift, grp, sh);
-  load8(mean, grp, mu);
-  load8(invstd, grp, is);
+  load8(scale, w.grp, sc);
+  load8(shift, w.grp, sh);
+  load8(mean, w.grp, mu);
+  load8(invstd, w.grp, is);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    m1[k] = (float)(sum_dy[grp * 8 + k] * inv_n);
-    m2[k] = (float)(sum_dy_xhat[grp * 8 + k] * inv_n);
+    m1[k] = (float)(sum_dy[w.grp * 8 + k] * inv_n);
+    m2[k] = (float)(sum_dy_xhat[w.grp * 8 + k] * inv_n);
   }
-  // BatchNorm parameter gradients (un-scaled): written once, by the blocks of row 0
-  if (blockIdx.x == 0 && d_gamma != nullptr) {
+  // BatchNorm parameter gradients (un-scaled): written once, by pair lane 0 of the blocks of grid row 0
+  if (blockIdx.x == 0 && w.lane == 0 && d_gamma != nullptr) {
     const double inv = gscale_buf != nullptr ? (double)gscale_buf[1] : 1.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int ch = grp * 8 + k;
+      const int ch = w.grp * 8 + k;
       if (ch < c) {
         d_gamma[ch] = (float)(sum_dy_xhat[ch] * inv);
         d_beta[ch] = (float)(sum_dy[ch] * inv);
       }
     }
   }
-  const long long step = gridDim.x;
-  for (long long r0 = blockIdx.x; r0 < rows; r0 += step * kRowUnroll) {
-    uint4 gv[kRowUnroll], zv[kRowUnroll];
+  const long long iters = (rows + (long long)gridDim.x * kRowsPerIter - 1) / ((long long)gridDim.x * kRowsPerIter);
+  for (long long it = 0; it < iters; ++it) {
+    uint4 gv[2 * kPairUnroll], zv[2 * kPairUnroll];
 #pragma unroll
-    for (int u = 0; u < kRowUnroll; ++u) {
-      const long long row = r0 + u * step;
+    for (int u = 0; u < 2 * kPairUnroll; ++u) {
+      const long long row = 2 * w.pair(it, u >> 1) + (u & 1);
       if (row < rows) {
-        gv[u] = __ldg(g + row * groups + grp);
-        zv[u] = __ldg(z + row * groups + grp);
+        gv[u] = __ldg(g + row * groups + w.grp);
+        zv[u] = __ldg(z + row * groups + w.grp);
       }
     }
 #pragma unroll
-    for (int u = 0; u < kRowUnroll; ++u) {
-      const long long row = r0 + u * step;
-      if (row < rows) {
-        float dy[8], xh[8], o[8];
-        dy_xhat<DT>(gv[u], zv[u], row, grp, sc, sh, mu, is, drop, dy, xh);
+    for (int pu = 0; pu < kPairUnroll; ++pu) {
+      const long long P = w.pair(it, pu);
+      if (2 * P >= rows) continue;
+      uint4 bits = make_uint4(0, 0, 0, 0);
+      if (drop.on) bits = drop_bits(drop, P, w.grp);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = sc[k] * (dy[k] - m1[k] - xh[k] * m2[k]);
-        dz[row * groups + grp] = pack8<DT>(o);
+      for (int h = 0; h < 2; ++h) {
+        const long long row = 2 * P + h;
+        if (row < rows) {
+          float dy[8], xh[8], o[8];
+          dy_xhat<DT>(gv[2 * pu + h], zv[2 * pu + h], drop, h ? bits.z : bits.x, h ? bits.w : bits.y, sc, sh, mu, is, dy,
+                      xh);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = sc[k] * (dy[k] - m1[k] - xh[k] * m2[k]);
+          dz[row * groups + w.grp] = pack8<DT>(o);
+        }
       }
     }
   }
@@ -437,25 +483,25 @@ cudaError_t launch_counter_add(unsigned long long* counter, unsigned long long i
 }
 
 // ---------------------------------------------------------------------------------------------- launchers
-// grid for the row-walking kernels: y covers the channel groups, x strides over rows with ~8 blocks per SM in total
-static dim3 row_walk_grid(long long rows, int groups, int sm_count) {
-  const int gy = (groups + kEwThreads - 1) / kEwThreads;
-  long long gx = (rows + kRowUnroll - 1) / kRowUnroll;
-  const int per_sm = groups <= 128 ? 16 : 8;  // ~2048 resident threads per SM
+// grid for the row-walking kernels: y covers the channel slabs, x strides over spans of kRowsPerIter adjacent rows
+static dim3 row_walk_grid(long long rows, int groups, int sm_count, int per_sm) {
+  const int gy = (groups + kEwGroups - 1) / kEwGroups;
+  long long gx = (rows + kRowsPerIter - 1) / kRowsPerIter;
   const long long cap = ((long long)sm_count * per_sm + gy - 1) / gy;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   return dim3((unsigned)gx, (unsigned)gy);
 }
-static dim3 reduce_grid(long long rows, int groups, int sm_count) {
-  const int gy = (groups + kRedGroups - 1) / kRedGroups;
-  long long gx = (rows + kRedLanes * 4 - 1) / (kRedLanes * 4);
-  const long long cap = ((long long)sm_count * 4 + gy - 1) / gy;  // ~4 blocks of 256 threads per SM in total
+
+// reductions: 512-thread blocks, at most ~1 per SM over all channel slabs
+static dim3 reduce_grid(long long rows, int rows_per_iter, int groups, int sm_count) {
+  const int gy = (groups + kEwGroups - 1) / kEwGroups;
+  long long gx = (rows + rows_per_iter - 1) / rows_per_iter;
+  const long long cap = (sm_count + gy - 1) / gy;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   return dim3((unsigned)gx, (unsigned)gy);
 }
-static int ew_block(int groups) { return groups < kEwThreads ? ((groups + 31) / 32) * 32 : kEwThreads; }
 
 cudaError_t launch_bn_finalize(const double* sum, const double* sqsum, long long count, const float* gamma,
                                const float* beta, float eps, float momentum, float* running_mean, float* running_var,
@@ -479,8 +525,8 @@ cudaError_t launch_bn_act_fwd(int dtype, const void* z, const float* scale, cons
                               cudaStream_t stream) {
   const long long rows = seqs * rows_per_seq;
   const int groups = c_pad / 8;
-  const dim3 grid = row_walk_grid(rows, groups, sm_count);
-  const int block = ew_block(groups);
+  const dim3 grid = row_walk_grid(rows, groups, sm_count, 8);
+  const int block = kEwGroups * kEwLanes;
   VP3D_DISPATCH_16(bn_act_fwd_kernel, static_cast<const uint4*>(z), scale, shift, static_cast<const uint4*>(res), rows,
                    rows_per_seq, res_seq_rows, res_row_mul, res_row_off, groups, dp, static_cast<uint4*>(a))
 }
@@ -488,8 +534,8 @@ cudaError_t launch_bn_act_fwd(int dtype, const void* z, const float* scale, cons
 cudaError_t launch_col_stats(int dtype, const void* z, long long rows, int c_pad, double* sum, double* sqsum,
                              int sm_count, cudaStream_t stream) {
   const int groups = c_pad / 8;
-  const dim3 grid = reduce_grid(rows, groups, sm_count);
-  const int block = kRedGroups * kRedLanes;
+  const dim3 grid = reduce_grid(rows, kRedLanes * 8, groups, sm_count);
+  const int block = kEwGroups * kRedLanes;
   VP3D_DISPATCH_16(col_stats_kernel, static_cast<const uint4*>(z), rows, groups, sum, sqsum)
 }
 
@@ -498,8 +544,8 @@ cudaError_t launch_bn_act_bwd_reduce(int dtype, const void* g, const void* z, co
                                      const DropoutParams& dp, double* sum_dy, double* sum_dy_xhat, int sm_count,
                                      cudaStream_t stream) {
   const int groups = c_pad / 8;
-  const dim3 grid = reduce_grid(rows, groups, sm_count);
-  const int block = kRedGroups * kRedLanes;
+  const dim3 grid = reduce_grid(rows, 2 * kRedLanes * kPairUnroll, groups, sm_count);
+  const int block = kEwGroups * kRedLanes;
   VP3D_DISPATCH_16(bn_act_bwd_reduce_kernel, static_cast<const uint4*>(g), static_cast<const uint4*>(z), scale, shift,
                    mean, invstd, rows, groups, dp, sum_dy, sum_dy_xhat)
 }
@@ -510,8 +556,8 @@ cudaError_t launch_bn_act_bwd_apply(int dtype, const void* g, const void* z, con
                                     const float* gscale_buf, void* dz, float* d_gamma, float* d_beta, int sm_count,
                                     cudaStream_t stream) {
   const int groups = c_pad / 8;
-  const dim3 grid = row_walk_grid(rows, groups, sm_count);
-  const int block = ew_block(groups);
+  const dim3 grid = row_walk_grid(rows, groups, sm_count, 8);
+  const int block = kEwGroups * kEwLanes;
   VP3D_DISPATCH_16(bn_act_bwd_apply_kernel, static_cast<const uint4*>(g), static_cast<const uint4*>(z), scale, shift,
                    mean, invstd, rows, count, c, groups, dp, sum_dy, sum_dy_xhat, gscale_buf, static_cast<uint4*>(dz),
                    d_gamma, d_beta)
