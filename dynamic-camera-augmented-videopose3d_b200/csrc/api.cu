@@ -99,12 +99,13 @@ CUtensorMapDataType tm_dtype(int dtype) {
 
 // Tiled map with a 128-byte inner box and SWIZZLE_128B; out-of-range elements read as zero.
 int encode_map(CUtensorMap* tm, int dtype, int rank, const void* base, const cuuint64_t* dims,
-               const cuuint64_t* strides_bytes, const cuuint32_t* box, const char* what) {
+               const cuuint64_t* strides_bytes, const cuuint32_t* box, const char* what,
+               CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (enc == nullptr) return fail(VP3D_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(tm, tm_dtype(dtype), (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(VP3D_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d (dims %llu,%llu,%llu)", what, (int)r,
@@ -204,12 +205,12 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
   CUtensorMap tmC;
   memset(&tmC, 0, sizeof(tmC));
   if (!a->out_f32) {
-    // output view [n_pad columns][rows_out][sequences]; one store = 64 columns x 32 rows (one epilogue warp)
+    // output view [n_pad columns][rows_out][sequences]; one store = 32 columns x 32 rows (one epilogue warp, 64 B rows)
     cuuint64_t dims[3] = {(cuuint64_t)a->n_pad, (cuuint64_t)a->rows_out, (cuuint64_t)a->a_seqs};
     cuuint64_t strides[2] = {(cuuint64_t)(a->out_row_stride * 2), (cuuint64_t)(a->out_seq_stride * 2)};
     if (a->a_seqs == 1) strides[1] = (cuuint64_t)(a->rows_out * a->out_row_stride * 2);
-    cuuint32_t box[3] = {64, 32, 1};
-    if (int rc = encode_map(&tmC, a->dtype, 3, a->out, dims, strides, box, "output")) return rc;
+    cuuint32_t box[3] = {32, 32, 1};
+    if (int rc = encode_map(&tmC, a->dtype, 3, a->out, dims, strides, box, "output", CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
   }
 
   vp3d::ConvGemmParams p;

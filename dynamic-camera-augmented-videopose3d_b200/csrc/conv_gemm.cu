@@ -23,7 +23,8 @@ namespace vp3d {
 
 constexpr int kBlockM = 128;
 constexpr int kTileKBytes = 128;  // one swizzle span of K per stage row
-constexpr int kNumThreads = 192;
+constexpr int kEpiWarps = 8;                        // two per TMEM lane quadrant, each takes half of the columns
+constexpr int kNumThreads = 64 + 32 * kEpiWarps;    // + TMA producer warp + MMA issuer warp
 
 template <int BN>
 struct GemmCfg {
@@ -32,7 +33,7 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : 8;
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int kOutStageBytes = 4 * 32 * 128;  // per epilogue warp: 32 rows x 128 B staging for the TMA store
+  static constexpr int kOutStageBytes = kEpiWarps * 32 * 64;  // per epilogue warp: 32 rows x 64 B staging for a TMA store
   static constexpr int kBarBytes = 256;
   static constexpr int kStatBytes = 4 * BN * 2 * 4;  // per epilogue warp: BN x {sum, sum of squares} fp32
   static constexpr int kAffineBytes = 2 * BN * 4;    // scale / shift of the CTA's current column tile
@@ -145,7 +146,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 128);
+      mbar_init(&tmem_empty_bar[s], 32 * kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -231,23 +232,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    // The epilogue of a 128 x BN tile is latency bound (TMEM load -> math -> residual / store), so two warps share
+    // each TMEM lane quadrant and split the columns: warp `epi` handles chunks [half * kChunks, (half + 1) * kChunks).
+    constexpr int kChunks = BN / 64;              // 32-column chunks per epilogue warp
+    const int quad = warp & 3;                    // TMEM lane quadrant this warp may access (hardware: warp id % 4)
+    const int epi = warp - 2;
+    const int half = epi >> 2;
     const int row = quad * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
     // per-warp fp32 statistics accumulators in shared memory, flushed (double atomics) when the CTA moves to another
     // column tile -- with gridDim.x a multiple of n_tiles a CTA keeps one column tile for the whole launch
-    float* stat_warp = stat_smem + quad * BN * 2;
+    float* stat_warp = stat_smem + epi * (BN / 2) * 2;   // this warp's BN/2 columns x {sum, sum of squares}
     int stat_n0 = -1;
     auto stat_flush = [&]() {
       if (stat_n0 >= 0) {
-        for (int j = lane; j < BN; j += 32) {
-          atomicAdd(p.stat_sum + stat_n0 * BN + j, (double)stat_warp[2 * j]);
-          atomicAdd(p.stat_sqsum + stat_n0 * BN + j, (double)stat_warp[2 * j + 1]);
+        for (int j = lane; j < BN / 2; j += 32) {
+          atomicAdd(p.stat_sum + stat_n0 * BN + half * (BN / 2) + j, (double)stat_warp[2 * j]);
+          atomicAdd(p.stat_sqsum + stat_n0 * BN + half * (BN / 2) + j, (double)stat_warp[2 * j + 1]);
         }
       }
-      for (int j = lane; j < 2 * BN; j += 32) stat_warp[j] = 0.f;
+      for (int j = lane; j < BN; j += 32) stat_warp[j] = 0.f;
       __syncwarp();
     };
     if (p.stat_sum != nullptr) stat_flush();
@@ -260,15 +266,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (p.scale != nullptr && tc.n0 != affine_n0) {
         // per-channel scale / shift of this column tile -> shared memory (once per launch when the grid is a multiple
-        // of n_tiles). Named barrier 1 over the 128 epilogue threads on both sides: nobody still reads the old tile's
+        // of n_tiles). Named barrier 1 over the epilogue threads on both sides: nobody still reads the old tile's
         // values, everybody sees the new ones.
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
         const int e = threadIdx.x - 64;
-        for (int j = e; j < BN; j += 128) {
+        for (int j = e; j < BN; j += 32 * kEpiWarps) {
           affine_smem[j] = __ldg(p.scale + tc.n0 * BN + j);
           affine_smem[BN + j] = __ldg(p.shift + tc.n0 * BN + j);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
         affine_n0 = tc.n0;
       }
       const int t = tc.t0 + row;
@@ -294,16 +300,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       };
       uint4 rcur[4], rnext[4];
-      res_load(0, rcur);
+      res_load(half * kChunks, rcur);
 
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
 
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half * kChunks; c < (half + 1) * kChunks; ++c) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + acc * BN + c * 32 + (static_cast<uint32_t>(quad * 32) << 16), v);
-        if (c + 1 < BN / 32) res_load(c + 1, rnext);
+        if (c + 1 < (half + 1) * kChunks) res_load(c + 1, rnext);
         tmem_wait_ld();
         const int col0 = tc.n0 * BN + c * 32;
         float f[32];
@@ -330,7 +336,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               q[i] = kq + __shfl_xor_sync(0xffffffffu, sq, o);
             }
           }
-          float* acc_s = stat_warp + (c * 32 + lane) * 2;  // owned by exactly this lane: no atomics in smem
+          float* acc_s = stat_warp + ((c - half * kChunks) * 32 + lane) * 2;  // owned by this lane: no smem atomics
           acc_s[0] += s[0];
           acc_s[1] += q[0];
         }
@@ -396,31 +402,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         if (!p.out_f32) {
-          // element-typed output (fp16 / bf16): the warp's 32 rows x 64 columns are staged in shared memory in the
-          // SWIZZLE_128B layout (conflict-free 16-byte stores) and leave as ONE coalesced TMA store per 64 columns;
+          // element-typed output (fp16 / bf16): the warp's 32 rows x 32 columns (64 B per row) are staged in shared
+          // memory in the SWIZZLE_64B layout (conflict-free 16-byte stores) and leave as ONE coalesced TMA store;
           // TMA clips rows past the end of the sequence, so no row mask is needed here
           constexpr int D16 = (DT == VP3D_TF32) ? VP3D_F16 : DT;
-          uint8_t* my_stage = out_stage + quad * (32 * 128);
-          if ((c & 1) == 0) {
-            if (lane == 0) tma_store_wait_read<0>();  // the previous store of this warp has drained the buffer
-            __syncwarp();
-          }
+          uint8_t* my_stage = out_stage + epi * (32 * 64);
+          if (lane == 0) tma_store_wait_read<0>();  // the previous store of this warp has drained the buffer
+          __syncwarp();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int chunk = (c & 1) * 4 + j;
-            st_shared_v4(my_stage + lane * 128 + ((chunk ^ (lane & 7)) << 4),
+            st_shared_v4(my_stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4),
                          pack2(f[8 * j + 0], f[8 * j + 1], std::integral_constant<int, D16>{}),
                          pack2(f[8 * j + 2], f[8 * j + 3], std::integral_constant<int, D16>{}),
                          pack2(f[8 * j + 4], f[8 * j + 5], std::integral_constant<int, D16>{}),
                          pack2(f[8 * j + 6], f[8 * j + 7], std::integral_constant<int, D16>{}));
           }
-          if ((c & 1) == 1) {
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_3d(&tmC, my_stage, tc.n0 * BN + (c >> 1) * 64, tc.t0 + quad * 32, tc.seq);
-              tma_store_commit();
-            }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmC, my_stage, tc.n0 * BN + c * 32, tc.t0 + quad * 32, tc.seq);
+            tma_store_commit();
           }
         }
 #pragma unroll
