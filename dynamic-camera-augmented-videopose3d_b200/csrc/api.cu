@@ -10,6 +10,11 @@ namespace vp3d {
 cudaError_t launch_project_points(const float* X, float* out3, float* out2, long long n_pts, const float* q,
                                   const float* t, const float* cam, long long pts_per_q, long long pts_per_cam,
                                   int mode, int sm_count, cudaStream_t stream);
+cudaError_t launch_project_windows(const float* x, const float* q, const float* t, const float* cam,
+                                   const long long* seq_start, const long long* seq_len, const int* sample_seq,
+                                   const long long* sample_start, int batch, int joints, int chunk, int pad, int shift,
+                                   int root_relative, int linear, float* out2, float* target3, float* cam3x4,
+                                   int sm_count, cudaStream_t stream);
 cudaError_t launch_mpjpe_fwd(const float* pred, const float* tgt, long long n_joints, const float* w, long long T,
                              long long J, long long s_n, long long s_t, long long s_j, double* partial, float* out,
                              int sm_count, cudaStream_t stream);
@@ -318,6 +323,26 @@ int vp3d_project_points(const float* x, float* out3, float* out2, long long n_pt
   cudaError_t e = vp3d::launch_project_points(x, out3, out2, n_pts, q, t, cam, pts_per_q, pts_per_cam, mode,
                                               dev->sm_count, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "project_points launch");
+  return VP3D_OK;
+}
+
+int vp3d_project_windows(const vp3d_window_args* a, void* stream) {
+  if (a == nullptr) return fail(VP3D_ERR_INVALID, "args is NULL");
+  if (!a->x_world || !a->q || !a->t || !a->cam || !a->seq_start || !a->seq_len || !a->sample_seq || !a->sample_start ||
+      !a->out2)
+    return fail(VP3D_ERR_INVALID, "project_windows: null pointer");
+  if (a->batch <= 0 || a->joints <= 0 || a->chunk_length <= 0 || a->pad < 0)
+    return fail(VP3D_ERR_INVALID, "project_windows: bad sizes");
+  if ((long long)a->batch * (a->chunk_length + 2 * a->pad) * a->joints >= (1LL << 32))
+    return fail(VP3D_ERR_INVALID, "project_windows: batch too large for 32-bit point indices");
+  if (reinterpret_cast<uintptr_t>(a->q) & 15) return fail(VP3D_ERR_INVALID, "project_windows: q must be 16-byte aligned");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_project_windows(a->x_world, a->q, a->t, a->cam, a->seq_start, a->seq_len, a->sample_seq,
+                                               a->sample_start, a->batch, a->joints, a->chunk_length, a->pad,
+                                               a->causal_shift, a->root_relative, a->linear, a->out2, a->target3,
+                                               a->cam3x4, dev->sm_count, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "project_windows launch");
   return VP3D_OK;
 }
 

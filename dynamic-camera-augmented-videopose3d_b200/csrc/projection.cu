@@ -255,6 +255,126 @@ project_points_kernel(const float* __restrict__ X, float* __restrict__ out3, flo
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Window feeder: the batch assembly of common/generators.py:102-132 (ChunkedGenerator.next_epoch) fused with the
+// dynamic-camera projection. Sequences stay resident on the device as concatenated world-space joints with one camera
+// pose per frame; for sample b and window frame k the source frame is
+//     f = seq_start[s] + clamp(start_3d[b] - pad - causal_shift + k, 0, len[s] - 1)      (np.pad 'edge', :92-100)
+// and the kernel writes project_to_2d(world_to_camera(X[f], q[f], t[f]), cam[s]) straight into the (B, window, J, 2)
+// batch -- no (B, 243, J, 3) intermediate, no host loop. Optionally the camera-space target of the chunk frames
+// (root-relative like run.py:72-74) and the per-frame K @ [R|t] matrices the sibling models consume (:119-125).
+struct WindowParams {
+  const float* x;        // [frames][J][3]
+  const float* q;        // [frames][4]
+  const float* t;        // [frames][3]
+  const float* cam;      // [n_seq][9]
+  const long long* seq_start;
+  const long long* seq_len;
+  const int* sample_seq;
+  const long long* sample_start;
+  int batch, joints, chunk, pad, shift, root_relative, linear, window;
+};
+
+__device__ __forceinline__ long long window_frame(const WindowParams& w, int s, long long local) {
+  const long long len = w.seq_len[s];
+  local = local < 0 ? 0 : (local >= len ? len - 1 : local);
+  return w.seq_start[s] + local;
+}
+
+__device__ __forceinline__ float3 to_camera(const WindowParams& w, long long f, int j) {
+  const float4 qq = __ldg(reinterpret_cast<const float4*>(w.q) + f);
+  const Quat qc{qq.x, -qq.y, -qq.z, -qq.w};
+  const float* xp = w.x + (f * w.joints + j) * 3;
+  const float* tp = w.t + f * 3;
+  float3 X = make_float3(sub(__ldg(xp), __ldg(tp)), sub(__ldg(xp + 1), __ldg(tp + 1)), sub(__ldg(xp + 2), __ldg(tp + 2)));
+  return qrot_dev(qc, X);
+}
+
+__global__ void __launch_bounds__(256)
+project_windows_kernel(WindowParams w, float* __restrict__ out2) {
+  const unsigned total = (unsigned)w.batch * w.window * w.joints;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned j = i % w.joints;
+    const unsigned bk = i / w.joints;
+    const unsigned k = bk % w.window;
+    const unsigned b = bk / w.window;
+    const int s = w.sample_seq[b];
+    const long long f = window_frame(w, s, w.sample_start[b] - w.pad - w.shift + (long long)k);
+    const float3 Xc = to_camera(w, f, (int)j);
+    const float2 P = project_dev(Xc, w.cam + 9 * s, w.linear);
+    reinterpret_cast<float2*>(out2)[i] = P;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+window_targets_kernel(WindowParams w, float* __restrict__ target3) {
+  const unsigned total = (unsigned)w.batch * w.chunk * w.joints;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned j = i % w.joints;
+    const unsigned bc = i / w.joints;
+    const unsigned c = bc % w.chunk;
+    const unsigned b = bc / w.chunk;
+    const int s = w.sample_seq[b];
+    const long long f = window_frame(w, s, w.sample_start[b] + (long long)c);
+    float3 X = to_camera(w, f, (int)j);
+    if (w.root_relative) {
+      const float3 R = to_camera(w, f, 0);
+      X = make_float3(sub(X.x, R.x), sub(X.y, R.y), sub(X.z, R.z));
+    }
+    target3[3 * i] = X.x;
+    target3[3 * i + 1] = X.y;
+    target3[3 * i + 2] = X.z;
+  }
+}
+
+// K @ [R | -R c] per window frame: R = rotation of conj(q) (world -> camera), c = camera position t
+__global__ void __launch_bounds__(256)
+window_cameras_kernel(WindowParams w, float* __restrict__ cam3x4) {
+  const unsigned total = (unsigned)w.batch * w.window;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned k = i % w.window;
+    const unsigned b = i / w.window;
+    const int s = w.sample_seq[b];
+    const long long f = window_frame(w, s, w.sample_start[b] - w.pad - w.shift + (long long)k);
+    const float4 qq = __ldg(reinterpret_cast<const float4*>(w.q) + f);
+    const Quat qc{qq.x, -qq.y, -qq.z, -qq.w};
+    const float3 e0 = qrot_dev(qc, make_float3(1.f, 0.f, 0.f));   // columns of R
+    const float3 e1 = qrot_dev(qc, make_float3(0.f, 1.f, 0.f));
+    const float3 e2 = qrot_dev(qc, make_float3(0.f, 0.f, 1.f));
+    const float* tp = w.t + f * 3;
+    const float3 tc = qrot_dev(qc, make_float3(-__ldg(tp), -__ldg(tp + 1), -__ldg(tp + 2)));
+    const float* cm = w.cam + 9 * s;
+    const float fx = __ldg(cm), fy = __ldg(cm + 1), cx = __ldg(cm + 2), cy = __ldg(cm + 3);
+    const float E[3][4] = {{e0.x, e1.x, e2.x, tc.x}, {e0.y, e1.y, e2.y, tc.y}, {e0.z, e1.z, e2.z, tc.z}};
+    float* o = cam3x4 + (long long)i * 12;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      o[c] = add(mul(fx, E[0][c]), mul(cx, E[2][c]));
+      o[4 + c] = add(mul(fy, E[1][c]), mul(cy, E[2][c]));
+      o[8 + c] = E[2][c];
+    }
+  }
+}
+
+cudaError_t launch_project_windows(const float* x, const float* q, const float* t, const float* cam,
+                                   const long long* seq_start, const long long* seq_len, const int* sample_seq,
+                                   const long long* sample_start, int batch, int joints, int chunk, int pad, int shift,
+                                   int root_relative, int linear, float* out2, float* target3, float* cam3x4,
+                                   int sm_count, cudaStream_t stream) {
+  WindowParams w{x, q, t, cam, seq_start, seq_len, sample_seq, sample_start, batch, joints, chunk, pad, shift,
+                 root_relative, linear, chunk + 2 * pad};
+  auto grid_for = [&](long long total) {
+    long long blocks = (total + 255) / 256;
+    if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
+    return (unsigned)(blocks < 1 ? 1 : blocks);
+  };
+  project_windows_kernel<<<grid_for((long long)batch * w.window * joints), 256, 0, stream>>>(w, out2);
+  if (target3 != nullptr)
+    window_targets_kernel<<<grid_for((long long)batch * chunk * joints), 256, 0, stream>>>(w, target3);
+  if (cam3x4 != nullptr) window_cameras_kernel<<<grid_for((long long)batch * w.window), 256, 0, stream>>>(w, cam3x4);
+  return cudaGetLastError();
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 cudaError_t launch_project_points(const float* X, float* out3, float* out2, long long n_pts, const float* q,

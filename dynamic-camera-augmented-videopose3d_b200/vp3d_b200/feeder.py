@@ -1,0 +1,123 @@
+"""GPU-resident batch feeder: ChunkedGenerator's batch assembly (common/generators.py:11-137) fused with
+the dynamic-camera projection, on the device.
+
+The reference assembles every training batch on the host: a Python loop over the 1024 samples, np.pad edge padding,
+a 3x3 @ (243,3,4) matmul per sample, float64 staging buffers, then a blocking .cuda() (generators.py:102-132,
+run.py:458-464) -- 78 ms per batch, the real bottleneck of its training step. Here all sequences live on
+the device once (world-space joints + one camera pose per frame), an epoch is the reference's own permutation of
+(sequence, frame) pairs, and a batch costs one 12 KB index upload plus one kernel (vp3d_project_windows) that gathers
+the padded windows, applies world -> camera -> image per frame and writes the (B, window, J, 2) batch, the
+camera-space target and (optionally) the K @ [R|t] matrices directly.
+
+Epoch order: `np.random.RandomState(seed).permutation(pairs)` exactly as generators.py:56,85, so sample order is
+reproducible against the reference generator. Deviation (deliberate): the last, partial batch of an epoch contains
+only its own samples -- the reference yields its full-size buffers with stale rows from the previous batch.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import native, ops
+
+
+class DeviceWindowFeeder:
+    def __init__(self, world_3d, quats, trans, intrinsics, batch_size, chunk_length=1, pad=0, causal_shift=0,
+                 shuffle=True, random_seed=1234, root_relative=True, linear=False, want_cameras=False, device='cuda',
+                 endless=False):
+        """world_3d: list of (T_i, J, 3) arrays/tensors; quats (T_i, 4) and trans (T_i, 3): one camera pose per frame;
+        intrinsics: (n_seq, 9) [fx, fy, cx, cy, k1, k2, k3, p1, p2] per sequence."""
+        assert len(world_3d) == len(quats) == len(trans) == len(intrinsics)
+        dev = torch.device(device)
+        as_t = lambda a: torch.as_tensor(np.asarray(a.cpu() if isinstance(a, torch.Tensor) else a), dtype=torch.float32)
+        self.joints = int(world_3d[0].shape[-2])
+        lens = [int(x.shape[0]) for x in world_3d]
+        for x, q, t in zip(world_3d, quats, trans):
+            assert x.shape[0] == q.shape[0] == t.shape[0] and x.shape[-1] == 3 and q.shape[-1] == 4 and t.shape[-1] == 3
+        self.x = torch.cat([as_t(x) for x in world_3d]).contiguous().to(dev)
+        self.q = torch.cat([as_t(q) for q in quats]).contiguous().to(dev)
+        self.t = torch.cat([as_t(t) for t in trans]).contiguous().to(dev)
+        self.cam = as_t(intrinsics).reshape(len(lens), 9).contiguous().to(dev)
+        starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+        self.seq_start = torch.from_numpy(starts).to(dev)
+        self.seq_len = torch.tensor(lens, dtype=torch.int64, device=dev)
+        # lineage info, as generators.py:39-45
+        pairs = []
+        for i, n in enumerate(lens):
+            n_chunks = (n + chunk_length - 1) // chunk_length
+            offset = (n_chunks * chunk_length - n) // 2
+            bounds = np.arange(n_chunks + 1) * chunk_length - offset
+            pairs += zip(np.repeat(i, len(bounds) - 1), bounds[:-1], bounds[1:])
+        self.pairs = pairs
+        self.batch_size, self.chunk_length, self.pad, self.causal_shift = batch_size, chunk_length, pad, causal_shift
+        self.num_batches = (len(pairs) + batch_size - 1) // batch_size
+        self.random = np.random.RandomState(random_seed)
+        self.shuffle, self.endless, self.state = shuffle, endless, None
+        self.root_relative, self.linear, self.want_cameras = root_relative, linear, want_cameras
+        self.dev = dev
+        self.window = chunk_length + 2 * pad
+        # pinned staging for the per-batch index upload (two buffers: the copy of batch i+1 may overlap batch i)
+        self._idx_host = [torch.empty((batch_size, 2), dtype=torch.int64).pin_memory() for _ in range(2)]
+        self._idx_dev = [torch.empty((batch_size, 2), dtype=torch.int64, device=dev) for _ in range(2)]
+        self._flip = 0
+
+    # -- generator protocol of the reference ------------------------------------------------------------------
+    def num_frames(self):
+        return self.num_batches * self.batch_size
+
+    def random_state(self):
+        return self.random
+
+    def set_random_state(self, random):
+        self.random = random
+
+    def next_pairs(self):
+        if self.state is None:
+            pairs = self.random.permutation(self.pairs) if self.shuffle else np.asarray(self.pairs)
+            return 0, pairs
+        return self.state
+
+    def assemble(self, chunks):
+        """chunks: (n, 3) int array of (seq_i, start_3d, end_3d) -> (cams or None, batch_3d, batch_2d) on the device."""
+        chunks = np.asarray(chunks)
+        n = len(chunks)
+        b = self._flip
+        self._flip ^= 1
+        host = self._idx_host[b]
+        host[:n, 0] = torch.from_numpy(chunks[:, 0].astype(np.int64))
+        host[:n, 1] = torch.from_numpy(chunks[:, 1].astype(np.int64))
+        idx = self._idx_dev[b]
+        idx[:n].copy_(host[:n], non_blocking=True)
+        seq32 = idx[:n, 0].to(torch.int32).contiguous()
+        start = idx[:n, 1].contiguous()
+        J = self.joints
+        x2d = torch.empty((n, self.window, J, 2), dtype=torch.float32, device=self.dev)
+        tgt = torch.empty((n, self.chunk_length, J, 3), dtype=torch.float32, device=self.dev)
+        cams = torch.empty((n, self.window, 3, 4), dtype=torch.float32, device=self.dev) if self.want_cameras else None
+        a = native.WindowArgs()
+        a.x_world, a.q, a.t, a.cam = self.x.data_ptr(), self.q.data_ptr(), self.t.data_ptr(), self.cam.data_ptr()
+        a.seq_start, a.seq_len = self.seq_start.data_ptr(), self.seq_len.data_ptr()
+        a.sample_seq, a.sample_start = seq32.data_ptr(), start.data_ptr()
+        a.batch, a.joints, a.chunk_length, a.pad, a.causal_shift = n, J, self.chunk_length, self.pad, self.causal_shift
+        a.root_relative, a.linear = int(self.root_relative), int(self.linear)
+        a.out2, a.target3 = x2d.data_ptr(), tgt.data_ptr()
+        a.cam3x4 = None if cams is None else cams.data_ptr()
+        with torch.cuda.device(self.dev):
+            native.check(native.lib().vp3d_project_windows(C.byref(a), ops._stream()), 'project_windows')
+        return cams, tgt, x2d
+
+    def next_epoch(self):
+        """Yields (batch_cam, batch_3d, batch_2d) like ChunkedGenerator.next_epoch (generators.py:102-132), as fp32 CUDA
+        tensors (batch_cam is None unless want_cameras)."""
+        enabled = True
+        while enabled:
+            start_idx, pairs = self.next_pairs()
+            for b_i in range(start_idx, self.num_batches):
+                chunks = pairs[b_i * self.batch_size:(b_i + 1) * self.batch_size]
+                if self.endless:
+                    self.state = (b_i + 1, pairs)
+                yield self.assemble(chunks)
+            if self.endless:
+                self.state = None
+            else:
+                enabled = False

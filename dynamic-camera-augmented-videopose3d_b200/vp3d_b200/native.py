@@ -47,6 +47,16 @@ class WgradArgs(C.Structure):
     ]
 
 
+class WindowArgs(C.Structure):
+    """struct vp3d_window_args (include/vp3d_b200.h)"""
+    _fields_ = [('x_world', C.c_void_p), ('q', C.c_void_p), ('t', C.c_void_p), ('cam', C.c_void_p),
+                ('seq_start', C.c_void_p), ('seq_len', C.c_void_p), ('sample_seq', C.c_void_p),
+                ('sample_start', C.c_void_p),
+                ('batch', C.c_int), ('joints', C.c_int), ('chunk_length', C.c_int), ('pad', C.c_int),
+                ('causal_shift', C.c_int), ('root_relative', C.c_int), ('linear', C.c_int),
+                ('out2', C.c_void_p), ('target3', C.c_void_p), ('cam3x4', C.c_void_p)]
+
+
 class Dropout(C.Structure):
     """struct vp3d_dropout (include/vp3d_b200.h)"""
     _fields_ = [('p', C.c_float), ('seed', C.c_ulonglong), ('stream', C.c_ulonglong), ('step_counter', C.c_void_p)]
@@ -63,6 +73,7 @@ _SIGNATURES = {
     'vp3d_bn_fold': (C.c_int, [C.c_void_p] * 4 + [C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     'vp3d_project_points': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p]),
+    'vp3d_project_windows': (C.c_int, [C.POINTER(WindowArgs), C.c_void_p]),
     'vp3d_loss_workspace_bytes': (C.c_longlong, []),
     'vp3d_mpjpe_fwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p] + [C.c_longlong] * 5 +
                        [C.c_void_p, C.c_void_p, C.c_void_p]),

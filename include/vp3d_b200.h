@@ -135,6 +135,24 @@ enum {
 int vp3d_project_points(const float* x, float* out3, float* out2, long long n_pts, const float* q, const float* t,
                         const float* cam, long long pts_per_q, long long pts_per_cam, int mode, void* stream);
 
+/* Window feeder: the batch assembly of common/generators.py:102-132 fused with the dynamic-camera
+ * projection. All sequences are resident on the device, concatenated: x_world[frames][joints][3], one camera pose per
+ * frame q[frames][4] / t[frames][3], intrinsics cam[n_seq][9]; seq_start / seq_len give each sequence's frame range.
+ * Sample b = (sample_seq[b], sample_start[b]) is the reference's (seq_i, start_3d) pair; window frame k reads source
+ * frame clamp(start_3d - pad - causal_shift + k, 0, len - 1) (np.pad 'edge', generators.py:92-100).
+ *   out2    [batch][chunk_length + 2 pad][joints][2]  project_to_2d(world_to_camera(X, q, t), cam)   (camera.py:28-67)
+ *   target3 [batch][chunk_length][joints][3] or NULL  camera-space joints of the chunk frames, root-relative if asked
+ *                                                     (run.py:72-74)
+ *   cam3x4  [batch][window][3][4] or NULL             K @ [R | -R c] per window frame (generators.py:113-125) */
+typedef struct vp3d_window_args {
+  const float* x_world; const float* q; const float* t; const float* cam;
+  const long long* seq_start; const long long* seq_len;
+  const int* sample_seq; const long long* sample_start;
+  int batch, joints, chunk_length, pad, causal_shift, root_relative, linear;
+  float* out2; float* target3; float* cam3x4;
+} vp3d_window_args;
+int vp3d_project_windows(const vp3d_window_args* args, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * K6  losses on joint grids pred/target[n_joints][3] fp32 (contiguous). Replaces common/loss.py:11-27,70-80.
  * `workspace` must hold vp3d_loss_workspace_bytes() bytes. `out` / `grad_out` are single device floats.
