@@ -369,6 +369,48 @@ def bench_train(args, rank, world, dev, steps, warm):
     barrier()
     ms_e2e = e2.elapsed_time(e3)
 
+    # ---- device-resident feeder: 64 world-space sequences x 4096 frames stay in HBM; a step uploads 16 KB of
+    # (sequence, frame) indices, one kernel gathers + pads + projects the 1024 windows, then the same graph runs
+    from vp3d_b200.feeder import DeviceWindowFeeder
+    g = torch.Generator().manual_seed(77 + rank)
+    n_seq, seq_len = 64, 4096
+    seqs_w = (torch.randn(n_seq, seq_len, 17, 3, generator=g) * 0.3 + torch.tensor([0.0, 0.0, 4.0]))
+    seqs_q = torch.tensor([1.0, 0, 0, 0]) + torch.randn(n_seq, seq_len, 4, generator=g) * 0.05
+    seqs_q = seqs_q / seqs_q.norm(dim=-1, keepdim=True)
+    seqs_t = torch.randn(n_seq, seq_len, 3, generator=g) * 0.1
+    feeder = DeviceWindowFeeder(list(seqs_w), list(seqs_q), list(seqs_t), torch.tensor(H36M_CAM0).repeat(n_seq, 1),
+                                batch_size=batch, pad=RF // 2, endless=True, device=dev)
+    batches = feeder.next_epoch()
+
+    def step_feeder():
+        _, b3d, b2d = next(batches)
+        if graphed_2d is not None:
+            loss = graphed_2d((b2d,), b3d)
+        else:
+            opt.zero_grad(set_to_none=True)
+            loss = mpjpe(model(b2d), b3d)
+            loss.backward()
+            opt.step()
+            loss = loss.detach()
+        loss_host.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_host)
+
+    graphed_2d = None
+    if use_graph:
+        _, b3d0, b2d0 = next(batches)
+        graphed_2d = GraphedTrainStep(model, opt, mpjpe, (b2d0,), b3d0)
+    for _ in range(3):
+        step_feeder()
+    barrier()
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e4.record()
+    for _ in range(steps):
+        step_feeder()
+    e5.record()
+    barrier()
+    ms_feed = e4.elapsed_time(e5)
+
     if world > 1:
         tt = torch.tensor([ms, ms_e2e, gemm_ms, proj_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -393,6 +435,11 @@ def bench_train(args, rank, world, dev, steps, warm):
                    'launch': 'one CUDA graph per step (vp3d_b200.graphs.GraphedTrainStep)' if use_graph else 'eager'},
         'e2e': {'value': total / (ms_e2e * 1e-3), 'unit': 'samples/s', 'ms_per_step': ms_e2e / steps,
                 'h2d_bytes_per_step': sum(v.numel() * 4 for v in (Wh, qh, th, camh)), 'd2h_bytes_per_step': 4},
+        'e2e_device_feeder': {'value': batch * world * steps / (ms_feed * 1e-3), 'unit': 'samples/s',
+                              'ms_per_step': ms_feed / steps, 'h2d_bytes_per_step': batch * 16, 'd2h_bytes_per_step': 4,
+                              'note': 'vp3d_b200.feeder.DeviceWindowFeeder: sequences resident in HBM, windows gathered, '
+                                      'edge-padded and projected by one kernel per step (replaces ChunkedGenerator, '
+                                      'generators.py:102-132), loss read back every step'},
         'gpu_launches': n_launch * steps,
         'loss_first_last': [float(first_loss), float(last_loss)],
         'roofline': {'bound': 'tensor', 'kernel': 'conv_gemm_kernel + wgrad_gemm_kernel (%d launches per step)' % n_gemm,

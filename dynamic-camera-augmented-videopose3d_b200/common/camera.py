@@ -89,8 +89,7 @@ def project_to_2d(X, camera_params):
     """
     _check_projection_args(X, camera_params)
     per_cam = max(X.numel() // 3 // max(X.shape[0], 1), 1)
-    _, out = ops.project_points(X, cam=camera_params, pts_per_cam=per_cam, mode=native.PT_PROJECT, want2=True)
-    return out.to(X.dtype)
+    return ops.project_2d(X, camera_params, per_cam, linear=False).to(X.dtype)   # differentiable wrt X
 
 
 def project_to_2d_linear(X, camera_params):
@@ -103,9 +102,7 @@ def project_to_2d_linear(X, camera_params):
     """
     _check_projection_args(X, camera_params)
     per_cam = max(X.numel() // 3 // max(X.shape[0], 1), 1)
-    _, out = ops.project_points(X, cam=camera_params, pts_per_cam=per_cam,
-                                mode=native.PT_PROJECT | native.PT_LINEAR, want2=True)
-    return out.to(X.dtype)
+    return ops.project_2d(X, camera_params, per_cam, linear=True).to(X.dtype)    # differentiable wrt X
 
 
 def world_to_image(X, R, t, camera_params, linear=False, return_camera_space=True):

@@ -10,6 +10,8 @@ namespace vp3d {
 cudaError_t launch_project_points(const float* X, float* out3, float* out2, long long n_pts, const float* q,
                                   const float* t, const float* cam, long long pts_per_q, long long pts_per_cam,
                                   int mode, int sm_count, cudaStream_t stream);
+cudaError_t launch_project_bwd(const float* X, const float* cam, const float* g, long long n_pts, long long pts_per_cam,
+                               int linear, float* gx, int sm_count, cudaStream_t stream);
 cudaError_t launch_project_windows(const float* x, const float* q, const float* t, const float* cam,
                                    const long long* seq_start, const long long* seq_len, const int* sample_seq,
                                    const long long* sample_start, int batch, int joints, int chunk, int pad, int shift,
@@ -21,6 +23,12 @@ cudaError_t launch_mpjpe_fwd(const float* pred, const float* tgt, long long n_jo
 cudaError_t launch_mpjpe_bwd(const float* pred, const float* tgt, const float* grad_out, long long n_joints,
                              const float* w, long long T, long long J, long long s_n, long long s_t, long long s_j,
                              float* grad_pred, int sm_count, cudaStream_t stream);
+cudaError_t launch_mpjpe_nd_fwd(const float* pred, const float* tgt, long long n_pts, int D, const float* w, long long T,
+                                long long J, long long s_n, long long s_t, long long s_j, double* partial, float* out,
+                                int sm_count, cudaStream_t stream);
+cudaError_t launch_mpjpe_nd_bwd(const float* pred, const float* tgt, const float* grad_out, long long n_pts, int D,
+                                const float* w, long long T, long long J, long long s_n, long long s_t, long long s_j,
+                                float* grad_pred, int sm_count, cudaStream_t stream);
 cudaError_t launch_n_mpjpe_fwd(const float* pred, const float* tgt, long long n_poses, int J, double* partial,
                                float* out, int sm_count, cudaStream_t stream);
 cudaError_t launch_pack_rows(int dtype, const float* src, void* dst, long long rows, int c, int c_pad, int sm_count,
@@ -326,6 +334,19 @@ int vp3d_project_points(const float* x, float* out3, float* out2, long long n_pt
   return VP3D_OK;
 }
 
+int vp3d_project_bwd(const float* x, const float* cam, const float* grad_out2, long long n_pts, long long pts_per_cam,
+                     int linear, float* grad_x, void* stream) {
+  if (n_pts < 0) return fail(VP3D_ERR_INVALID, "n_pts < 0");
+  if (n_pts == 0) return VP3D_OK;
+  if (!x || !cam || !grad_out2 || !grad_x || pts_per_cam <= 0) return fail(VP3D_ERR_INVALID, "project_bwd args");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_project_bwd(x, cam, grad_out2, n_pts, pts_per_cam, linear, grad_x, dev->sm_count,
+                                           static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "project_bwd launch");
+  return VP3D_OK;
+}
+
 int vp3d_project_windows(const vp3d_window_args* a, void* stream) {
   if (a == nullptr) return fail(VP3D_ERR_INVALID, "args is NULL");
   if (!a->x_world || !a->q || !a->t || !a->cam || !a->seq_start || !a->seq_len || !a->sample_seq || !a->sample_start ||
@@ -373,6 +394,34 @@ int vp3d_mpjpe_bwd(const float* pred, const float* target, const float* grad_out
   cudaError_t e = vp3d::launch_mpjpe_bwd(pred, target, grad_out, n_joints, w, T, J, w_stride_n, w_stride_t, w_stride_j,
                                          grad_pred, dev->sm_count, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "mpjpe_bwd launch");
+  return VP3D_OK;
+}
+
+int vp3d_mpjpe_nd_fwd(const float* pred, const float* target, long long n_points, int dim, const float* w, long long T,
+                      long long J, long long w_stride_n, long long w_stride_t, long long w_stride_j, void* workspace,
+                      float* out, void* stream) {
+  if (!pred || !target || !workspace || !out || n_points <= 0 || dim <= 0) return fail(VP3D_ERR_INVALID, "mpjpe_nd_fwd args");
+  if (w != nullptr && (T <= 0 || J <= 0 || n_points % (T * J) != 0)) return fail(VP3D_ERR_INVALID, "mpjpe_nd_fwd weight grid");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_mpjpe_nd_fwd(pred, target, n_points, dim, w, T, J, w_stride_n, w_stride_t, w_stride_j,
+                                            static_cast<double*>(workspace), out, dev->sm_count,
+                                            static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "mpjpe_nd_fwd launch");
+  return VP3D_OK;
+}
+
+int vp3d_mpjpe_nd_bwd(const float* pred, const float* target, const float* grad_out, long long n_points, int dim,
+                      const float* w, long long T, long long J, long long w_stride_n, long long w_stride_t,
+                      long long w_stride_j, float* grad_pred, void* stream) {
+  if (!pred || !target || !grad_out || !grad_pred || n_points <= 0 || dim <= 0)
+    return fail(VP3D_ERR_INVALID, "mpjpe_nd_bwd args");
+  if (w != nullptr && (T <= 0 || J <= 0 || n_points % (T * J) != 0)) return fail(VP3D_ERR_INVALID, "mpjpe_nd_bwd weight grid");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_mpjpe_nd_bwd(pred, target, grad_out, n_points, dim, w, T, J, w_stride_n, w_stride_t,
+                                            w_stride_j, grad_pred, dev->sm_count, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "mpjpe_nd_bwd launch");
   return VP3D_OK;
 }
 

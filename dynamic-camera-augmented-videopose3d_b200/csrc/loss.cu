@@ -155,6 +155,42 @@ n_mpjpe_partial_kernel(const float* __restrict__ pred, const float* __restrict__
   if (threadIdx.x == 0) partial[blockIdx.x] = s;
 }
 
+// Generic point dimension D (the reference's mpjpe is a norm over the last axis whatever its length, loss.py:17 --
+// upstream uses it on 2-D reprojections): one thread per point, D strided reads.
+__global__ void __launch_bounds__(kLossThreads)
+mpjpe_nd_partial_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, long long n_pts, int D,
+                        WeightView wv, double* __restrict__ partial) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += stride) {
+    float s = 0.f;
+    for (int d = 0; d < D; ++d) {
+      const float v = pred[i * D + d] - tgt[i * D + d];
+      s += v * v;
+    }
+    acc += (double)(weight_at(wv, i) * sqrtf(s));
+  }
+  const double r = block_sum(acc);
+  if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+
+__global__ void __launch_bounds__(kLossThreads)
+mpjpe_nd_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, const float* __restrict__ grad_out,
+                    float inv_count, long long n_pts, int D, WeightView wv, float* __restrict__ grad_pred) {
+  const float g0 = __ldg(grad_out) * inv_count;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += stride) {
+    float s = 0.f;
+    for (int d = 0; d < D; ++d) {
+      const float v = pred[i * D + d] - tgt[i * D + d];
+      s += v * v;
+    }
+    const float nrm = sqrtf(s);
+    const float k = nrm > 0.f ? g0 * weight_at(wv, i) / nrm : 0.f;
+    for (int d = 0; d < D; ++d) grad_pred[i * D + d] = (pred[i * D + d] - tgt[i * D + d]) * k;
+  }
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int loss_grid(long long n_joints, int sm_count) {
@@ -185,6 +221,27 @@ cudaError_t launch_mpjpe_bwd(const float* pred, const float* tgt, const float* g
   const int vec_ok = aligned16(pred) && aligned16(tgt) && aligned16(grad_pred);
   mpjpe_bwd_kernel<<<grid, kLossThreads, 0, stream>>>(pred, tgt, grad_out, 1.f / (float)n_joints, n_joints, wv, vec_ok,
                                                       grad_pred);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mpjpe_nd_fwd(const float* pred, const float* tgt, long long n_pts, int D, const float* w, long long T,
+                                long long J, long long s_n, long long s_t, long long s_j, double* partial, float* out,
+                                int sm_count, cudaStream_t stream) {
+  WeightView wv{w, T > 0 ? T : 1, J > 0 ? J : 1, s_n, s_t, s_j};
+  const int grid = loss_grid(n_pts * 4, sm_count);
+  mpjpe_nd_partial_kernel<<<grid, kLossThreads, 0, stream>>>(pred, tgt, n_pts, D, wv, partial);
+  mean_finish_kernel<<<1, kLossThreads, 0, stream>>>(partial, grid, n_pts > 0 ? 1.0 / (double)n_pts : 0.0, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mpjpe_nd_bwd(const float* pred, const float* tgt, const float* grad_out, long long n_pts, int D,
+                                const float* w, long long T, long long J, long long s_n, long long s_t, long long s_j,
+                                float* grad_pred, int sm_count, cudaStream_t stream) {
+  if (n_pts <= 0) return cudaSuccess;
+  WeightView wv{w, T > 0 ? T : 1, J > 0 ? J : 1, s_n, s_t, s_j};
+  mpjpe_nd_bwd_kernel<<<loss_grid(n_pts * 4, sm_count), kLossThreads, 0, stream>>>(pred, tgt, grad_out,
+                                                                                   1.f / (float)n_pts, n_pts, D, wv,
+                                                                                   grad_pred);
   return cudaGetLastError();
 }
 

@@ -375,6 +375,46 @@ cudaError_t launch_project_windows(const float* x, const float* q, const float* 
   return cudaGetLastError();
 }
 
+// Backward of project_to_2d / project_to_2d_linear wrt the camera-space points (the reference's docstring calls the
+// projection "differentiable", camera.py:39-40; autograd derives exactly this):  gx = d sum(g * proj(X)) / dX.
+__global__ void __launch_bounds__(256)
+project_bwd_kernel(const float* __restrict__ X, const float* __restrict__ cam, const float* __restrict__ g,
+                   long long n_pts, long long pts_per_cam, int linear, float* __restrict__ gx) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += stride) {
+    const float* c = cam + 9 * (i / pts_per_cam);
+    const float x = X[3 * i], y = X[3 * i + 1], z = X[3 * i + 2];
+    const float rx = x / z, ry = y / z;
+    const float xx = clamp_unit(rx), yy = clamp_unit(ry);
+    const float a = __ldg(c) * g[2 * i], b = __ldg(c + 1) * g[2 * i + 1];
+    float gxx = a, gyy = b;
+    if (!linear) {
+      const float k1 = __ldg(c + 4), k2 = __ldg(c + 5), k3 = __ldg(c + 6), p1 = __ldg(c + 7), p2 = __ldg(c + 8);
+      const float r2 = xx * xx + yy * yy;
+      const float s = 1.f + r2 * (k1 + r2 * (k2 + r2 * k3)) + p1 * xx + p2 * yy;
+      const float gs = a * xx + b * yy;
+      const float gr2 = a * p1 + b * p2 + gs * (k1 + r2 * (2.f * k2 + 3.f * k3 * r2));
+      gxx = a * s + gs * p1 + gr2 * 2.f * xx;
+      gyy = b * s + gs * p2 + gr2 * 2.f * yy;
+    }
+    if (!(rx >= -1.f && rx <= 1.f)) gxx = 0.f;   // torch.clamp backward: pass inside [-1, 1], bounds included
+    if (!(ry >= -1.f && ry <= 1.f)) gyy = 0.f;
+    const float iz = 1.f / z;
+    gx[3 * i] = gxx * iz;
+    gx[3 * i + 1] = gyy * iz;
+    gx[3 * i + 2] = -(gxx * x + gyy * y) * iz * iz;
+  }
+}
+
+cudaError_t launch_project_bwd(const float* X, const float* cam, const float* g, long long n_pts, long long pts_per_cam,
+                               int linear, float* gx, int sm_count, cudaStream_t stream) {
+  long long blocks = (n_pts + 255) / 256;
+  if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
+  if (blocks < 1) blocks = 1;
+  project_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(X, cam, g, n_pts, pts_per_cam > 0 ? pts_per_cam : 1, linear, gx);
+  return cudaGetLastError();
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 cudaError_t launch_project_points(const float* X, float* out3, float* out2, long long n_pts, const float* q,

@@ -54,6 +54,37 @@ def project_points(x, q=None, t=None, cam=None, pts_per_q=1, pts_per_cam=1, mode
     return out3, out2
 
 
+class _ProjectFn(torch.autograd.Function):
+    """project_to_2d / project_to_2d_linear with the gradient wrt the camera-space points (vp3d_project_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, cam, per_cam, linear):
+        x, cam = f32c(x), f32c(cam)
+        mode = native.PT_PROJECT | (native.PT_LINEAR if linear else 0)
+        _, out = project_points(x.detach(), cam=cam.detach(), pts_per_cam=per_cam, mode=mode, want2=True)
+        ctx.save_for_backward(x, cam)
+        ctx.meta = (per_cam, linear)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, cam = ctx.saved_tensors
+        per_cam, linear = ctx.meta
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None
+        g = f32c(g)
+        gx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            check(lib().vp3d_project_bwd(_ptr(x), _ptr(cam), _ptr(g), x.numel() // 3, int(per_cam), 1 if linear else 0,
+                                         _ptr(gx), _stream()), 'project_bwd')
+        return gx, None, None, None
+
+
+def project_2d(x, cam, per_cam, linear=False):
+    require_cuda(x, cam)
+    return _ProjectFn.apply(x, cam, per_cam, linear)
+
+
 # ------------------------------------------------------------------------------------------------ K6 losses
 _ws_cache = {}
 
@@ -83,9 +114,9 @@ class _MpjpeFn(torch.autograd.Function):
     def forward(ctx, pred, tgt, w):
         require_cuda(pred, tgt, w)
         assert pred.shape == tgt.shape  # loss.py:16
-        assert pred.shape[-1] == 3, 'joint coordinates must be 3-D'
+        D = int(pred.shape[-1])           # norm over the last axis, whatever its length (loss.py:17)
         p, g = f32c(pred), f32c(tgt)
-        n_joints = p.numel() // 3
+        n_joints = p.numel() // D
         if w is not None:
             assert w.shape[0] == pred.shape[0]  # loss.py:26
             wt, T, J, sn, st, sj = _weight_view(w, tuple(pred.shape[:-1]))
@@ -93,34 +124,37 @@ class _MpjpeFn(torch.autograd.Function):
             wt, T, J, sn, st, sj = None, 1, 1, 0, 0, 0
         out = torch.empty((), dtype=torch.float32, device=p.device)
         with torch.cuda.device(p.device):
-            check(lib().vp3d_mpjpe_fwd(_ptr(p), _ptr(g), n_joints, _ptr(wt), T, J, sn, st, sj,
-                                       _ptr(_loss_workspace(p.device)), _ptr(out), _stream()), 'mpjpe_fwd')
+            if D == 3:
+                check(lib().vp3d_mpjpe_fwd(_ptr(p), _ptr(g), n_joints, _ptr(wt), T, J, sn, st, sj,
+                                           _ptr(_loss_workspace(p.device)), _ptr(out), _stream()), 'mpjpe_fwd')
+            else:
+                check(lib().vp3d_mpjpe_nd_fwd(_ptr(p), _ptr(g), n_joints, D, _ptr(wt), T, J, sn, st, sj,
+                                              _ptr(_loss_workspace(p.device)), _ptr(out), _stream()), 'mpjpe_nd_fwd')
         ctx.save_for_backward(p, g, wt if wt is not None else torch.empty(0, device=p.device))
-        ctx.meta = (n_joints, wt is not None, T, J, sn, st, sj, pred.shape, pred.dtype)
+        ctx.meta = (n_joints, wt is not None, T, J, sn, st, sj, pred.shape, pred.dtype, D)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         p, g, wt = ctx.saved_tensors
-        n_joints, has_w, T, J, sn, st, sj, shape, dtype = ctx.meta
-        grad_pred = None
-        if ctx.needs_input_grad[0]:
+        n_joints, has_w, T, J, sn, st, sj, shape, dtype, D = ctx.meta
+
+        def grad_wrt_pred():
             go = f32c(grad_out).reshape(1)
-            grad_pred = torch.empty_like(p)
+            gp = torch.empty_like(p)
             with torch.cuda.device(p.device):
-                check(lib().vp3d_mpjpe_bwd(_ptr(p), _ptr(g), _ptr(go), n_joints, _ptr(wt) if has_w else None, T, J,
-                                           sn, st, sj, _ptr(grad_pred), _stream()), 'mpjpe_bwd')
-            grad_pred = grad_pred.reshape(shape).to(dtype)
+                if D == 3:
+                    check(lib().vp3d_mpjpe_bwd(_ptr(p), _ptr(g), _ptr(go), n_joints, _ptr(wt) if has_w else None, T, J,
+                                               sn, st, sj, _ptr(gp), _stream()), 'mpjpe_bwd')
+                else:
+                    check(lib().vp3d_mpjpe_nd_bwd(_ptr(p), _ptr(g), _ptr(go), n_joints, D, _ptr(wt) if has_w else None,
+                                                  T, J, sn, st, sj, _ptr(gp), _stream()), 'mpjpe_nd_bwd')
+            return gp.reshape(shape).to(dtype)
+
+        grad_pred = grad_wrt_pred() if ctx.needs_input_grad[0] else None
         grad_tgt = None
         if ctx.needs_input_grad[1]:
-            grad_tgt = -grad_pred if grad_pred is not None else None
-            if grad_tgt is None:
-                go = f32c(grad_out).reshape(1)
-                gp = torch.empty_like(p)
-                with torch.cuda.device(p.device):
-                    check(lib().vp3d_mpjpe_bwd(_ptr(p), _ptr(g), _ptr(go), n_joints, _ptr(wt) if has_w else None, T,
-                                               J, sn, st, sj, _ptr(gp), _stream()), 'mpjpe_bwd')
-                grad_tgt = (-gp).reshape(shape).to(dtype)
+            grad_tgt = -(grad_pred if grad_pred is not None else grad_wrt_pred())
         return grad_pred, grad_tgt, None
 
 

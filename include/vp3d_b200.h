@@ -135,6 +135,12 @@ enum {
 int vp3d_project_points(const float* x, float* out3, float* out2, long long n_pts, const float* q, const float* t,
                         const float* cam, long long pts_per_q, long long pts_per_cam, int mode, void* stream);
 
+/* Backward of VP3D_PT_PROJECT (| VP3D_PT_LINEAR) wrt the camera-space points: grad_x[n_pts][3] = d sum(grad_out2 *
+ * project_to_2d(x, cam)) / dx -- what autograd derives for camera.py:54-67 / :85-90 (torch.clamp passes the gradient
+ * inside [-1, 1], bounds included). */
+int vp3d_project_bwd(const float* x, const float* cam, const float* grad_out2, long long n_pts, long long pts_per_cam,
+                     int linear, float* grad_x, void* stream);
+
 /* Window feeder: the batch assembly of common/generators.py:102-132 fused with the dynamic-camera
  * projection. All sequences are resident on the device, concatenated: x_world[frames][joints][3], one camera pose per
  * frame q[frames][4] / t[frames][3], intrinsics cam[n_seq][9]; seq_start / seq_len give each sequence's frame range.
@@ -166,6 +172,14 @@ int vp3d_mpjpe_fwd(const float* pred, const float* target, long long n_joints, c
 int vp3d_mpjpe_bwd(const float* pred, const float* target, const float* grad_out, long long n_joints, const float* w,
                    long long T, long long J, long long w_stride_n, long long w_stride_t, long long w_stride_j,
                    float* grad_pred, void* stream);
+/* The same two for points of any dimension `dim` (pred/target[n_points][dim]): loss.py:17 takes the norm over the last
+ * axis whatever its length (2-D reprojection errors). dim == 3 callers should use the vectorised pair above. */
+int vp3d_mpjpe_nd_fwd(const float* pred, const float* target, long long n_points, int dim, const float* w, long long T,
+                      long long J, long long w_stride_n, long long w_stride_t, long long w_stride_j, void* workspace,
+                      float* out, void* stream);
+int vp3d_mpjpe_nd_bwd(const float* pred, const float* target, const float* grad_out, long long n_points, int dim,
+                      const float* w, long long T, long long J, long long w_stride_n, long long w_stride_t,
+                      long long w_stride_j, float* grad_pred, void* stream);
 int vp3d_n_mpjpe_fwd(const float* pred, const float* target, long long n_poses, int J, void* workspace, float* out,
                      void* stream);
 

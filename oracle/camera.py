@@ -115,3 +115,30 @@ def quat_to_matrix(q):
     return np.stack((np.stack((1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)), -1),
                      np.stack((2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)), -1),
                      np.stack((2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)), -1)), -2)
+
+
+def project_to_2d_grad(X, camera_params, grad_out, linear=False):
+    """d sum(grad_out * project_to_2d(X)) / dX in closed form -- what torch autograd derives for camera.py:54-67
+    (:85-90 when linear). torch.clamp passes the gradient where -1 <= ratio <= 1 (bounds included)."""
+    cp = camera_params
+    while cp.ndim < X.ndim:
+        cp = cp[:, None]
+    fx, fy = cp[..., 0], cp[..., 1]
+    k1, k2, k3, p1, p2 = (cp[..., i] for i in range(4, 9))
+    x, y, z = X[..., 0], X[..., 1], X[..., 2]
+    with np.errstate(divide='ignore', invalid='ignore'):
+        rx, ry = x / z, y / z
+    xx, yy = np.clip(rx, -1, 1), np.clip(ry, -1, 1)
+    a, b = fx * grad_out[..., 0], fy * grad_out[..., 1]
+    if linear:
+        gxx, gyy = a, b
+    else:
+        r2 = xx * xx + yy * yy
+        s = 1 + k1 * r2 + k2 * r2 ** 2 + k3 * r2 ** 3 + p1 * xx + p2 * yy
+        gs = a * xx + b * yy
+        gr2 = a * p1 + b * p2 + gs * (k1 + 2 * k2 * r2 + 3 * k3 * r2 ** 2)
+        gxx = a * s + gs * p1 + gr2 * 2 * xx
+        gyy = b * s + gs * p2 + gr2 * 2 * yy
+    gxx = np.where((rx >= -1) & (rx <= 1), gxx, 0)
+    gyy = np.where((ry >= -1) & (ry <= 1), gyy, 0)
+    return np.stack([gxx / z, gyy / z, -(gxx * x + gyy * y) / (z * z)], axis=-1).astype(X.dtype)

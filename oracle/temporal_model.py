@@ -182,21 +182,13 @@ def _ste_round(v, dtype):
     return v + (v.to(dtype).to(torch.float32) - v).detach()
 
 
-def train_step_grads_lowp(sd, x, target, filter_widths, causal=False, strided=True, dtype=torch.float16, masks=None):
-    """train_step_grads with the *forward* rounding points of the CUDA training path emulated on the CPU: GEMM
-    operands (input, weights) and every stored matrix (raw convolution output z, activation a) rounded to `dtype`,
-    batch statistics taken from the unrounded fp32 accumulators, fp32 everywhere else. Gradients of a ReLU network
-    are discontinuous in the activations -- a pre-activation that rounding moves across zero flips a mask bit -- so
-    the fp32 oracle is only a loose bound for low-precision gradients. Even this emulation differs from the GPU in
-    fp32 summation order, which moves a few stored values by one 16-bit ulp and flips a few more bits; `masks` (one
-    bool tensor (N, C, T') per BatchNorm layer, in forward order, taken from the GPU's own saved pre-activations) pins
-    the ReLU pattern so that the comparison isolates the backward arithmetic. Used by tests/ only."""
-    from . import loss as oloss
+def forward_lowp_train(sd, x, filter_widths, causal=False, strided=True, dtype=torch.float16, masks=None):
+    """Train-mode forward with the rounding points of the CUDA training path emulated on the CPU (see
+    train_step_grads_lowp). Returns (prediction with grad_fn, dict of leaf parameters)."""
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
               if v.dtype.is_floating_point and 'running_' not in k}
     plan = make_plan(filter_widths, causal, False, strided)
     rnd = lambda v: _ste_round(v, dtype)
-
     mask_iter = iter(masks) if masks is not None else None
 
     def bn_act(z, prefix, res=None):
@@ -224,7 +216,20 @@ def train_step_grads_lowp(sd, x, target, filter_widths, causal=False, strided=Tr
                    res=res)
     h = F.conv1d(h, rnd(params['shrink.weight']), params['shrink.bias'])
     j_out = sd['shrink.weight'].shape[0] // 3
-    pred = h.permute(0, 2, 1).reshape(n, -1, j_out, 3)
+    return h.permute(0, 2, 1).reshape(n, -1, j_out, 3), params
+
+
+def train_step_grads_lowp(sd, x, target, filter_widths, causal=False, strided=True, dtype=torch.float16, masks=None):
+    """train_step_grads with the *forward* rounding points of the CUDA training path emulated on the CPU: GEMM
+    operands (input, weights) and every stored matrix (raw convolution output z, activation a) rounded to `dtype`,
+    batch statistics taken from the unrounded fp32 accumulators, fp32 everywhere else. Gradients of a ReLU network
+    are discontinuous in the activations -- a pre-activation that rounding moves across zero flips a mask bit -- so
+    the fp32 oracle is only a loose bound for low-precision gradients. Even this emulation differs from the GPU in
+    fp32 summation order, which moves a few stored values by one 16-bit ulp and flips a few more bits; `masks` (one
+    bool tensor (N, C, T') per BatchNorm layer, in forward order, taken from the GPU's own saved pre-activations) pins
+    the ReLU pattern so that the comparison isolates the backward arithmetic. Used by tests/ only."""
+    from . import loss as oloss
+    pred, params = forward_lowp_train(sd, x, filter_widths, causal, strided, dtype, masks)
     loss = oloss.mpjpe(pred, target)
     loss.backward()
     grads = {k: v.grad.detach() for k, v in params.items()}

@@ -147,6 +147,27 @@ def camera_cases():
     np.savez_compressed(os.path.join(HERE, 'camera.npz'), **out)
 
 
+def camera_grad_cases():
+    """Autograd of the reference's project_to_2d / project_to_2d_linear (camera.py:37-90) wrt the camera-space points:
+    d sum(W * proj(X)) / dX, incl. saturated (clamped) ratios and negative depth."""
+    import torch
+    rng = np.random.default_rng(4321)
+    h36m = np.array([2.2900989, 2.2875624, 0.025083065, 0.028902981, -0.20709892, 0.24777518, -0.0030751503,
+                     -0.00097569887, -0.0014244716], dtype=np.float32)
+    cams = np.stack([h36m, h36m * np.float32(0.9), h36m * np.float32(1.1)])
+    X = (rng.standard_normal((3, 20, 17, 3)) * 0.7 + np.array([0.0, 0.0, 3.0])).astype(np.float32)
+    X[0, 0, 0] = [5.0, -7.0, 1.0]       # both ratios saturate: gradient 0
+    X[0, 0, 1] = [0.3, 0.2, -2.0]       # negative depth
+    X[0, 0, 2] = [2.5, 0.1, 2.0]        # x saturates, y does not
+    W = rng.standard_normal((3, 20, 17, 2)).astype(np.float32)
+    out = {'X': X, 'cams': cams, 'W': W}
+    for name, fn in (('grad', rcam.project_to_2d), ('grad_linear', rcam.project_to_2d_linear)):
+        xt = torch.from_numpy(X).clone().requires_grad_(True)
+        (fn(xt, torch.from_numpy(cams)) * torch.from_numpy(W)).sum().backward()
+        out[name] = xt.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, 'camera_grad.npz'), **out)
+
+
 def loss_cases():
     g = torch.Generator().manual_seed(77)
     out = {}
@@ -182,6 +203,7 @@ if __name__ == '__main__':
     seeded_large('temporal_243f_1024_causal.npz', [3, 3, 3, 3, 3], 247, seed=9, causal=True)
     seeded_large('temporal_243f_j31.npz', [3, 3, 3, 3, 3], 245, seed=10, j_in=31, j_out=31)
     camera_cases()
+    camera_grad_cases()
     loss_cases()
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):

@@ -111,3 +111,39 @@ def test_mpjpe_large_and_ragged_sizes_against_oracle():
         ref = oloss.mpjpe(pred.double(), tgt.double()).item()
         got = closs.mpjpe(pred.cuda(), tgt.cuda()).item()
         assert abs(got - ref) < 1e-6 * max(1.0, abs(ref)), shape
+
+
+def test_projection_backward_against_reference_autograd():
+    """project_to_2d / project_to_2d_linear are differentiable wrt the camera-space points (camera.py:39-40); gradient
+    against autograd of the reference itself (golden) and the oracle's closed form."""
+    from oracle import camera as ocam
+    z = load_golden('camera_grad.npz')
+    cams = torch.from_numpy(z['cams']).cuda()
+    W = torch.from_numpy(z['W']).cuda()
+    for key, fn, lin in (('grad', cam.project_to_2d, False), ('grad_linear', cam.project_to_2d_linear, True)):
+        X = torch.from_numpy(z['X']).cuda().requires_grad_(True)
+        (fn(X, cams) * W).sum().backward()
+        np.testing.assert_allclose(X.grad.cpu().numpy(), z[key], atol=PROJ_TOL)
+        np.testing.assert_allclose(X.grad.cpu().numpy(), ocam.project_to_2d_grad(z['X'], z['cams'], z['W'], linear=lin),
+                                   atol=PROJ_TOL)
+
+
+def test_mpjpe_on_2d_points_value_and_gradient():
+    """loss.py:17 norms the last axis whatever its length; upstream applies mpjpe to 2-D reprojections."""
+    g = torch.Generator().manual_seed(2)
+    pred = torch.randn(7, 3, 17, 2, generator=g)
+    tgt = torch.randn(7, 3, 17, 2, generator=g)
+    w = torch.rand(7, 1, 1, generator=g)
+    for weights in (None, w):
+        pc = pred.clone().requires_grad_(True)
+        pg = pred.cuda().requires_grad_(True)
+        if weights is None:
+            ref = torch.mean(torch.norm(pc - tgt, dim=3))
+            got = closs.mpjpe(pg, tgt.cuda())
+        else:
+            ref = torch.mean(weights * torch.norm(pc - tgt, dim=3))
+            got = closs.weighted_mpjpe(pg, tgt.cuda(), weights.cuda())
+        ref.backward()
+        got.backward()
+        assert abs(got.item() - ref.item()) < 1e-6
+        np.testing.assert_allclose(pg.grad.cpu().numpy(), pc.grad.numpy(), atol=1e-8, rtol=1e-5)

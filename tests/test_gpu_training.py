@@ -341,3 +341,63 @@ def test_train_step_with_dropout_runs_and_learns():
     with torch.no_grad():
         y = m(x)
     assert torch.isfinite(y).all()
+
+
+def test_j31_pose_and_trajectory_heads_with_reprojection_loss():
+    """BASELINE configs[4] primitives: 31-joint skeleton (62 input channels, 93 / 3 output channels), a pose model and a
+    trajectory model (num_joints_out = 1) trained jointly with mpjpe + weighted_mpjpe + a reprojection term through the
+    differentiable project_to_2d -- the loss composition of upstream VideoPose3D's semi-supervised step, whose
+    primitives (loss.py:21,70, camera.py:37) are all that remain in this fork. Gradients against the CPU emulation."""
+    from common.camera import project_to_2d
+    from common.loss import weighted_mpjpe
+    from oracle import camera as ocam
+    from oracle import loss as oloss
+    fw, J = [3, 3, 3], 31
+    sd_p = otm.init_state(J, 2, J, fw, channels=1024, seed=31)
+    sd_t = otm.init_state(J, 2, 1, fw, channels=1024, seed=32)
+    g = torch.Generator().manual_seed(33)
+    n = 48
+    x = torch.rand(n, 27, J, 2, generator=g) * 2 - 1
+    tgt = torch.randn(n, 1, J, 3, generator=g) * 0.3
+    tgt[:, :, 0] = 0
+    traj = torch.randn(n, 1, 1, 3, generator=g) * 0.2 + torch.tensor([0.0, 0.0, 4.0])
+    cam_p = torch.tensor([2.29, 2.2876, 0.0251, 0.0289, -0.2071, 0.2478, -0.0031, -0.00098, -0.0014]).repeat(n, 1)
+    x2d_center = x[:, 13:14]
+    mp = _build(TemporalModelOptimized1f, sd_p, fw, 1024, 'fp16', j=J)
+    mt = TemporalModelOptimized1f(J, 2, 1, fw, dropout=0.0, channels=1024)
+    mt.load_state_dict(sd_t)
+    mt = mt.cuda().train()
+    mt.operand_dtype = 'fp16'
+    xc, tc, trc, camc = x.cuda(), tgt.cuda(), traj.cuda(), cam_p.cuda()
+    pose = mp(xc)
+    masks_p = _gpu_masks(n, 1024)
+    tr = mt(xc)
+    masks_t = _gpu_masks(n, 1024)
+    w = 1 / trc[:, :, :, 2]
+    # reprojection of (pose + trajectory) placed ~6 m in front of the camera: at random init both heads output O(1)
+    # values, and a depth near zero would make the 1/z^2 gradient chaotic
+    depth = torch.tensor([0.0, 0.0, 6.0])
+    loss = mpjpe(pose, tc) + weighted_mpjpe(tr, trc, w) + \
+        mpjpe(project_to_2d(pose + tr + depth.cuda(), camc), x2d_center.cuda())
+    loss.backward()
+    assert pose.shape == (n, 1, J, 3) and tr.shape == (n, 1, 1, 3)
+
+    # CPU emulation of the same composite loss (masks pinned), torch autograd over the oracle's functional model
+    def proj_t(X, cp):
+        cp = cp.view(n, 1, 1, 9)
+        XX = torch.clamp(X[..., :2] / X[..., 2:], min=-1, max=1)
+        r2 = (XX ** 2).sum(-1, keepdim=True)
+        radial = 1 + (cp[..., 4:7] * torch.cat((r2, r2 ** 2, r2 ** 3), -1)).sum(-1, keepdim=True)
+        tan = (cp[..., 7:] * XX).sum(-1, keepdim=True)
+        return cp[..., :2] * (XX * (radial + tan) + cp[..., 7:] * r2) + cp[..., 2:4]
+
+    pose_e, params_p = otm.forward_lowp_train(sd_p, x, fw, strided=True, masks=masks_p)
+    tr_e, params_t = otm.forward_lowp_train(sd_t, x, fw, strided=True, masks=masks_t)
+    w_e = 1 / traj[:, :, :, 2]
+    loss_e = oloss.mpjpe(pose_e, tgt) + oloss.weighted_mpjpe(tr_e, traj, w_e) + \
+        oloss.mpjpe(proj_t(pose_e + tr_e + depth, cam_p), x2d_center)
+    loss_e.backward()
+    assert abs(loss.item() - loss_e.item()) < 2e-3 * abs(loss_e.item())
+    for model, params in ((mp, params_p), (mt, params_t)):
+        errs = {k: rel_err(p.grad, params[k].grad) for k, p in model.named_parameters()}
+        assert max(errs.values()) < GRAD_TOL_EMU['fp16'] * 2, errs

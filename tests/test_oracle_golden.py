@@ -124,3 +124,14 @@ def test_loss_oracle():
     P, T = z['pred'].reshape(-1, J, 3), z['tgt'].reshape(-1, J, 3)
     np.testing.assert_allclose(oloss.p_mpjpe(P.copy(), T.copy()), float(z['p_mpjpe']), rtol=1e-6)
     np.testing.assert_allclose(oloss.mean_velocity_error(P[:, 0], T[:, 0]), float(z['mve']), rtol=1e-6)
+
+
+def test_projection_gradient_oracle():
+    """Closed-form d project_to_2d / dX (oracle) against autograd of the reference (tests/golden/camera_grad.npz)."""
+    from oracle import camera as ocam
+    z = load_golden('camera_grad.npz')
+    for key, lin in (('grad', False), ('grad_linear', True)):
+        g = ocam.project_to_2d_grad(z['X'], z['cams'], z['W'], linear=lin)
+        np.testing.assert_allclose(g, z[key], atol=2e-6)
+    assert (z['grad'][0, 0, 0] == 0).all()                      # both ratios clamped
+    assert z['grad'][0, 0, 2, 0] == 0 and z['grad'][0, 0, 2, 1] != 0
