@@ -269,7 +269,11 @@ def bench_train(args, rank, world, dev, steps, warm):
     model = model.to(dev).train()
     model.operand_dtype = args.dtype if args.dtype != 'tf32' else 'fp16'
     use_graph = not args.no_graph      # N > 1: the NCCL all-reduces are captured in the graph as well
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, amsgrad=True, capturable=use_graph)       # run.py:662
+    if args.optimizer == 'fused':
+        from vp3d_b200.optim import FusedAdam                                # Adam(amsgrad) + operand re-pack, one pass
+        opt = FusedAdam(model.parameters(), lr=1e-3, amsgrad=True)
+    else:
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, amsgrad=True, capturable=use_graph)   # run.py:662
     sync = None
     if world > 1:
         ddp.broadcast_parameters(model)
@@ -428,6 +432,7 @@ def bench_train(args, rank, world, dev, steps, warm):
         'config': {'workload': 'TemporalModelOptimized1f 3,3,3,3,3 training step, batch %d per GPU, dropout 0.25, '
                                'per-frame camera projection (H36M cam-0 distortion) -> fwd -> mpjpe -> bwd -> Adam '
                                'amsgrad (BASELINE configs[2])' % batch,
+                   'optimizer': args.optimizer,
                    'grad_exchange': 'none (1 GPU)' if world == 1 else 'NCCL all-reduce (avg) of fp32 gradients, large '
                                     'tensors overlapped with backward, %d collectives, %.1f MB per step'
                                     % (coll_per_step[0], coll_per_step[1] / 1e6),
@@ -503,6 +508,8 @@ def main():
     ap.add_argument('--mode', default='all', choices=['all', 'infer', 'train'],
                     help='all: inference headline + train object; train: training headline only')
     ap.add_argument('--batch', type=int, default=TRAIN_BATCH, help='training samples per GPU per step')
+    ap.add_argument('--optimizer', default='fused', choices=['fused', 'torch'],
+                    help='training: vp3d_b200.optim.FusedAdam (default) or stock torch.optim.Adam')
     ap.add_argument('--no-graph', action='store_true', help='training: launch kernels eagerly instead of one CUDA graph')
     args = ap.parse_args()
 

@@ -641,4 +641,30 @@ int vp3d_grad_pack_rows(int dtype, const float* src, void* dst, long long rows, 
   return VP3D_OK;
 }
 
+int vp3d_adam_step(const vp3d_adam_args* a, void* stream) {
+  if (a == nullptr) return fail(VP3D_ERR_INVALID, "args is NULL");
+  if (!a->p || !a->g || !a->m || !a->v || !a->step || a->n <= 0 || a->n % 4 != 0)
+    return fail(VP3D_ERR_INVALID, "adam_step: null pointer or n not a positive multiple of 4");
+  if ((reinterpret_cast<uintptr_t>(a->p) | reinterpret_cast<uintptr_t>(a->g) | reinterpret_cast<uintptr_t>(a->m) |
+       reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->vmax)) & 15)
+    return fail(VP3D_ERR_INVALID, "adam_step: tensors must be 16-byte aligned");
+  if (a->packed != nullptr) {
+    if (a->dtype != VP3D_F16 && a->dtype != VP3D_BF16) return fail(VP3D_ERR_INVALID, "adam_step: packed dtype");
+    if (a->c_in <= 0 || a->taps <= 0 || a->k_pad < a->c_in || a->n % ((long long)a->c_in * a->taps) != 0)
+      return fail(VP3D_ERR_INVALID, "adam_step: weight geometry");
+  }
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  vp3d::AdamParams q;
+  q.p = a->p; q.g = a->g; q.m = a->m; q.v = a->v; q.vmax = a->vmax;
+  q.n = a->n;
+  q.lr = a->lr; q.beta1 = a->beta1; q.beta2 = a->beta2; q.eps = a->eps; q.weight_decay = a->weight_decay;
+  q.step = a->step; q.lr_dev = a->lr_dev;
+  q.maximize = a->maximize;
+  q.packed = a->packed; q.c_in = a->c_in; q.taps = a->taps; q.k_pad = a->k_pad;
+  cudaError_t e = vp3d::launch_adam_pack(a->dtype, q, dev->sm_count, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "adam_step launch");
+  return VP3D_OK;
+}
+
 }  // extern "C"

@@ -77,6 +77,17 @@ struct DropoutParams {
   const unsigned long long* step_counter;
 };
 cudaError_t launch_counter_add(unsigned long long* counter, unsigned long long inc, cudaStream_t stream);
+struct AdamParams {
+  float* p; const float* g; float* m; float* v; float* vmax;
+  long long n;
+  float lr, beta1, beta2, eps, weight_decay;
+  const float* step;    // device: step count of THIS update (already incremented)
+  const float* lr_dev;  // optional device learning rate (overrides lr)
+  int maximize;
+  void* packed;         // optional 16-bit K-major operand [c_out_pad][taps][k_pad]
+  int c_in, taps, k_pad;
+};
+cudaError_t launch_adam_pack(int dtype, const AdamParams& a, int sm_count, cudaStream_t stream);
 cudaError_t launch_bn_finalize(const double* sum, const double* sqsum, long long count, const float* gamma,
                                const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                                long long* nbt, float* scale, float* shift, float* mean, float* invstd, int c, int c_pad,

@@ -476,6 +476,79 @@ grad_pack_rows_kernel(const float* __restrict__ src, void* __restrict__ dst, lon
   }
 }
 
+// ---------------------------------------------------------------------------------------------- fused Adam + re-pack
+// optim.Adam(amsgrad=True) (run.py:662,487) on one convolution weight, fused with the re-pack of the
+// updated weight into the K-major 16-bit operand the next forward reads. One pass: p, g, m, v, vmax in (20 B), p, m, v,
+// vmax out (16 B) + 2 B packed per parameter, instead of torch's multi-tensor Adam pass followed by a pack kernel that
+// reads p again. Arithmetic follows torch.optim.adam (capturable / fused form):
+//   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  vmax = max(vmax, v)
+//   p -= lr / (1 - b1^t) * m / (sqrt(vmax) / sqrt(1 - b2^t) + eps)
+template <int DT>
+__global__ void __launch_bounds__(256)
+adam_pack_kernel(AdamParams a) {
+  const float t = *a.step;
+  const float lr = a.lr_dev != nullptr ? *a.lr_dev : a.lr;
+  const float bc1 = 1.f - powf(a.beta1, t);
+  const float bc2_sqrt = sqrtf(1.f - powf(a.beta2, t));
+  const float step_size = lr / bc1;
+  const int row_len = a.c_in * a.taps;           // elements per output channel in the nn.Conv1d layout
+  const long long n4 = a.n >> 2;                 // float4 groups (n is a multiple of 4 for every conv weight here)
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
+    float4 p4 = reinterpret_cast<float4*>(a.p)[q];
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.g) + q);
+    float4 m4 = reinterpret_cast<float4*>(a.m)[q];
+    float4 v4 = reinterpret_cast<float4*>(a.v)[q];
+    float4 x4 = a.vmax != nullptr ? reinterpret_cast<float4*>(a.vmax)[q] : make_float4(0, 0, 0, 0);
+    float pp[4] = {p4.x, p4.y, p4.z, p4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w},
+          vv[4] = {v4.x, v4.y, v4.z, v4.w}, xx[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float g = a.maximize ? -gg[e] : gg[e];
+      if (a.weight_decay != 0.f) g = fmaf(a.weight_decay, pp[e], g);
+      mm[e] = fmaf(a.beta1, mm[e], (1.f - a.beta1) * g);      // lerp form of exp_avg.lerp_(grad, 1 - beta1)
+      vv[e] = fmaf(a.beta2, vv[e], (1.f - a.beta2) * g * g);
+      float denom_v = vv[e];
+      if (a.vmax != nullptr) {
+        xx[e] = fmaxf(xx[e], vv[e]);
+        denom_v = xx[e];
+      }
+      const float denom = sqrtf(denom_v) / bc2_sqrt + a.eps;
+      pp[e] -= step_size * (mm[e] / denom);
+    }
+    reinterpret_cast<float4*>(a.p)[q] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    reinterpret_cast<float4*>(a.m)[q] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    reinterpret_cast<float4*>(a.v)[q] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    if (a.vmax != nullptr) reinterpret_cast<float4*>(a.vmax)[q] = make_float4(xx[0], xx[1], xx[2], xx[3]);
+    if (a.packed != nullptr) {
+      // element i = (co, ci, tap) of the (c_out, c_in, taps) weight -> packed[co][tap * k_pad + ci]
+      const long long i0 = 4 * q;
+      int co = (int)(i0 / row_len);
+      int rem = (int)(i0 - (long long)co * row_len);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int ci = rem / a.taps, tap = rem - ci * a.taps;
+        const long long d = ((long long)co * a.taps + tap) * a.k_pad + ci;
+        if (DT == VP3D_F16) static_cast<__half*>(a.packed)[d] = __float2half_rn(pp[e]);
+        else static_cast<__nv_bfloat16*>(a.packed)[d] = __float2bfloat16_rn(pp[e]);
+        if (++rem == row_len) {
+          rem = 0;
+          ++co;
+        }
+      }
+    }
+  }
+}
+
+cudaError_t launch_adam_pack(int dtype, const AdamParams& a, int sm_count, cudaStream_t stream) {
+  long long blocks = ((a.n >> 2) + 255) / 256;
+  if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
+  if (blocks < 1) blocks = 1;
+  if (dtype == VP3D_BF16) adam_pack_kernel<VP3D_BF16><<<(int)blocks, 256, 0, stream>>>(a);
+  else adam_pack_kernel<VP3D_F16><<<(int)blocks, 256, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
 __global__ void counter_add_kernel(unsigned long long* counter, unsigned long long inc) { *counter += inc; }
 cudaError_t launch_counter_add(unsigned long long* counter, unsigned long long inc, cudaStream_t stream) {
   counter_add_kernel<<<1, 1, 0, stream>>>(counter, inc);

@@ -57,6 +57,16 @@ class WindowArgs(C.Structure):
                 ('out2', C.c_void_p), ('target3', C.c_void_p), ('cam3x4', C.c_void_p)]
 
 
+class AdamArgs(C.Structure):
+    """struct vp3d_adam_args (include/vp3d_b200.h)"""
+    _fields_ = [('p', C.c_void_p), ('g', C.c_void_p), ('m', C.c_void_p), ('v', C.c_void_p), ('vmax', C.c_void_p),
+                ('n', C.c_longlong),
+                ('lr', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float),
+                ('weight_decay', C.c_float),
+                ('step', C.c_void_p), ('lr_dev', C.c_void_p), ('maximize', C.c_int),
+                ('packed', C.c_void_p), ('dtype', C.c_int), ('c_in', C.c_int), ('taps', C.c_int), ('k_pad', C.c_int)]
+
+
 class Dropout(C.Structure):
     """struct vp3d_dropout (include/vp3d_b200.h)"""
     _fields_ = [('p', C.c_float), ('seed', C.c_ulonglong), ('stream', C.c_ulonglong), ('step_counter', C.c_void_p)]
@@ -97,6 +107,7 @@ _SIGNATURES = {
                                                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     'vp3d_bn_act_bwd_apply': (C.c_int, [C.c_int] + [C.c_void_p] * 6 + [C.c_longlong, C.c_longlong, C.c_int, C.c_int,
                                                                       C.POINTER(Dropout)] + [C.c_void_p] * 7),
+    'vp3d_adam_step': (C.c_int, [C.POINTER(AdamArgs), C.c_void_p]),
     'vp3d_counter_add': (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_void_p]),
     'vp3d_grad_scale': (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     'vp3d_grad_pack_rows': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p,

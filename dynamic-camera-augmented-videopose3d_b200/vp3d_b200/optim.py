@@ -1,0 +1,86 @@
+"""Fused Adam(amsgrad) + operand re-pack.
+
+The reference trains with `optim.Adam(model.parameters(), lr, amsgrad=True)` (run.py:662) and, on this path, every
+optimiser step is followed by a re-pack of the fp32 convolution weights into the 16-bit K-major operands of the next
+forward. FusedAdam is a drop-in subclass of torch.optim.Adam -- same constructor, same per-parameter state
+(`step`, `exp_avg`, `exp_avg_sq`, `max_exp_avg_sq`), so `state_dict()` / `load_state_dict()` and run.py's checkpoints
+(run.py:436-445,559-569) are interchangeable with the stock optimiser -- whose `step()` sends the large convolution
+weights (99.9 % of the bytes) through vp3d_adam_step: one pass that updates p, m, v, vmax AND writes the packed operand
+the training forward has registered for that weight. Small tensors (BatchNorm affine, shrink layer) go through torch's
+own multi-tensor implementation. State steps live on the device (capturable), so the whole step can sit in a CUDA graph.
+"""
+import ctypes as C
+
+import torch
+from torch.optim import adam as _adam
+
+from . import native, ops
+
+
+class FusedAdam(torch.optim.Adam):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, *, maximize=False,
+                 min_numel=1 << 20):
+        super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad,
+                         maximize=maximize, capturable=True)
+        self.min_numel = min_numel
+
+    def _is_big(self, p, g):
+        return (p.is_cuda and p.dtype == torch.float32 and p.dim() == 3 and p.numel() >= self.min_numel and
+                p.numel() % 4 == 0 and p.is_contiguous() and g.dtype == torch.float32 and g.is_contiguous() and
+                not g.is_sparse)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            params, grads, exp_avgs, exp_avg_sqs, max_sqs, steps = [], [], [], [], [], []
+            has_complex = self._init_group(group, params, grads, exp_avgs, exp_avg_sqs, max_sqs, steps)
+            beta1, beta2 = group['betas']
+            big = [i for i, (p, g) in enumerate(zip(params, grads)) if self._is_big(p, g)]
+            big_set = set(big)
+            small = [i for i in range(len(params)) if i not in big_set]
+            pick = lambda lst, idx: [lst[i] for i in idx] if lst else []
+            if small:
+                _adam.adam(pick(params, small), pick(grads, small), pick(exp_avgs, small), pick(exp_avg_sqs, small),
+                           pick(max_sqs, small), pick(steps, small), amsgrad=group['amsgrad'], has_complex=has_complex,
+                           beta1=beta1, beta2=beta2, lr=group['lr'], weight_decay=group['weight_decay'], eps=group['eps'],
+                           maximize=group['maximize'], foreach=group['foreach'], capturable=True,
+                           differentiable=False, fused=group['fused'],
+                           decoupled_weight_decay=group.get('decoupled_weight_decay', False))
+            if not big:
+                continue
+            torch._foreach_add_(pick(steps, big), 1)
+            lr = group['lr']
+            lr_dev = lr.data_ptr() if isinstance(lr, torch.Tensor) and lr.is_cuda else None
+            for i in big:
+                p, g = params[i], grads[i]
+                a = native.AdamArgs()
+                a.p, a.g, a.m, a.v = p.data_ptr(), g.data_ptr(), exp_avgs[i].data_ptr(), exp_avg_sqs[i].data_ptr()
+                a.vmax = max_sqs[i].data_ptr() if group['amsgrad'] else None
+                a.n = p.numel()
+                a.lr = float(lr) if lr_dev is None else 0.0
+                a.beta1, a.beta2, a.eps, a.weight_decay = float(beta1), float(beta2), float(group['eps']), float(
+                    group['weight_decay'])
+                a.step, a.lr_dev, a.maximize = steps[i].data_ptr(), lr_dev, int(bool(group['maximize']))
+                reg = p.__dict__.get('_vp3d_packed')
+                entry = None
+                if reg:
+                    # the training forward registered the operand(s) it packs from this weight: refresh the first in the
+                    # same pass, drop the others (they will be re-packed on demand)
+                    key = next(iter(reg))
+                    entry = reg[key]
+                    for k in list(reg):
+                        if k != key:
+                            del reg[k]
+                    dt, _rows_pad, k_pad = key
+                    a.packed, a.dtype = entry[0].data_ptr(), dt
+                    a.c_in, a.taps, a.k_pad = p.shape[1], p.shape[2], k_pad
+                with torch.cuda.device(p.device):
+                    native.check(native.lib().vp3d_adam_step(C.byref(a), ops._stream()), 'adam_step')
+                torch.autograd.graph.increment_version(p)     # p changed behind autograd's back
+                if entry is not None:
+                    entry[1] = p._version
+        return loss

@@ -32,8 +32,20 @@ class _Layer:
                  'shift', 'mean', 'invstd', 'drop', 'res_of', 'res_mul', 'res_off', 'res_t', 'w_fwd', 'count')
 
 
-def _conv_w(dt, conv, rows_pad, k_pad, transpose=0):
-    return ops.pack_conv_weight(dt, conv.weight, rows_pad, k_pad, transpose=transpose)
+def _conv_w(dt, conv, rows_pad, k_pad):
+    """Forward-packed operand [rows_pad][taps * k_pad] of a convolution weight. The buffer is registered on the
+    parameter (`_vp3d_packed`, keyed by operand type and padding, stamped with the parameter version): a weight that
+    has not changed is not packed again, and vp3d_b200.optim.FusedAdam refreshes the registered buffer inside its
+    update kernel, so with that optimiser the pack kernel disappears from the training step."""
+    w = conv.weight
+    reg = w.__dict__.setdefault('_vp3d_packed', {})
+    key = (dt, rows_pad, k_pad)
+    entry = reg.get(key)
+    if entry is not None and entry[1] == w._version and entry[0].device == w.device:
+        return entry[0]
+    packed = ops.pack_conv_weight(dt, w, rows_pad, k_pad)
+    reg[key] = [packed, w._version]
+    return packed
 
 
 def _step_counter(model, dev):

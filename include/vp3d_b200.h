@@ -274,6 +274,22 @@ int vp3d_grad_scale(const float* dy, long long n, float* gscale_buf, void* strea
 int vp3d_grad_pack_rows(int dtype, const float* src, void* dst, long long rows, int c, int c_pad,
                         const float* gscale_buf, float* col_sum, void* stream);
 
+/* Fused optimiser step for one convolution weight: torch.optim.Adam(amsgrad) as run.py:662 uses it, in
+ * the arithmetic of torch's capturable implementation, plus the re-pack of the updated fp32 weight (c_out, c_in, taps)
+ * into the 16-bit K-major operand packed[c_out_pad][taps][k_pad] the next forward reads (padding entries are left
+ * untouched: the caller zero-fills the buffer once). `step` is a device float holding the number of THIS update (>= 1),
+ * `lr_dev` an optional device learning rate -- both so that a captured CUDA graph needs no re-capture when they change.
+ * n must be a multiple of 4; vmax == NULL disables amsgrad; packed == NULL skips the re-pack. */
+typedef struct vp3d_adam_args {
+  float* p; const float* g; float* m; float* v; float* vmax;
+  long long n;
+  float lr, beta1, beta2, eps, weight_decay;
+  const float* step; const float* lr_dev;
+  int maximize;
+  void* packed; int dtype, c_in, taps, k_pad;
+} vp3d_adam_args;
+int vp3d_adam_step(const vp3d_adam_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

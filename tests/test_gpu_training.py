@@ -401,3 +401,45 @@ def test_j31_pose_and_trajectory_heads_with_reprojection_loss():
     for model, params in ((mp, params_p), (mt, params_t)):
         errs = {k: rel_err(p.grad, params[k].grad) for k, p in model.named_parameters()}
         assert max(errs.values()) < GRAD_TOL_EMU['fp16'] * 2, errs
+
+
+def test_fused_adam_matches_torch_adam_and_refreshes_packed_operands():
+    """vp3d_b200.optim.FusedAdam against torch.optim.Adam(amsgrad=True) as run.py:662 builds it: same
+    parameters after several steps, interchangeable state_dict, and the packed 16-bit operand registered by the
+    training forward equals a fresh pack of the updated weight (so the pack kernel can be skipped)."""
+    from vp3d_b200.optim import FusedAdam
+    fw = [3, 3, 3]
+    sd = otm.init_state(17, 2, 17, fw, channels=1024, seed=41)
+    g = torch.Generator().manual_seed(42)
+    x = (torch.rand(96, 27, 17, 2, generator=g) * 2 - 1).cuda()
+    tgt = (torch.randn(96, 1, 17, 3, generator=g) * 0.3).cuda()
+    ma = _build(TemporalModelOptimized1f, sd, fw, 1024, 'fp16')
+    mb = _build(TemporalModelOptimized1f, sd, fw, 1024, 'fp16')
+    oa = torch.optim.Adam(ma.parameters(), lr=1e-3, amsgrad=True)
+    ob = FusedAdam(mb.parameters(), lr=1e-3, amsgrad=True)
+    for step in range(4):
+        for m, o in ((ma, oa), (mb, ob)):
+            o.zero_grad()
+            mpjpe(m(x), tgt).backward()
+        # identical gradients in, so that only the optimiser arithmetic is compared
+        for pa, pb in zip(ma.parameters(), mb.parameters()):
+            pb.grad.copy_(pa.grad)
+        oa.step()
+        ob.step()
+        for (k, pa), pb in zip(ma.named_parameters(), mb.parameters()):
+            assert (pa - pb).abs().max().item() < 2e-6, (step, k)
+    w = mb.layers_conv[0].weight
+    reg = w.__dict__['_vp3d_packed']
+    (key, (packed, version)), = reg.items()
+    assert version == w._version
+    fresh = ops.pack_conv_weight(key[0], w, key[1], key[2])
+    assert torch.equal(packed, fresh)
+    # state dicts are interchangeable with the stock optimiser
+    oc = torch.optim.Adam(mb.parameters(), lr=1e-3, amsgrad=True)
+    oc.load_state_dict(ob.state_dict())
+    sa, sc = oa.state_dict()['state'], oc.state_dict()['state']
+    assert sa.keys() == sc.keys()
+    for idx in sa:
+        assert float(sa[idx]['step']) == float(sc[idx]['step']) == 4
+        assert (sa[idx]['exp_avg'] - sc[idx]['exp_avg']).abs().max().item() < 1e-6
+        assert (sa[idx]['max_exp_avg_sq'] - sc[idx]['max_exp_avg_sq']).abs().max().item() < 1e-9
