@@ -643,8 +643,9 @@ int vp3d_grad_pack_rows(int dtype, const float* src, void* dst, long long rows, 
 
 int vp3d_adam_step(const vp3d_adam_args* a, void* stream) {
   if (a == nullptr) return fail(VP3D_ERR_INVALID, "args is NULL");
-  if (!a->p || !a->g || !a->m || !a->v || !a->step || a->n <= 0 || a->n % 4 != 0)
-    return fail(VP3D_ERR_INVALID, "adam_step: null pointer or n not a positive multiple of 4");
+  if (!a->p || !a->g || !a->m || !a->v || !a->step || a->n <= 0)
+    return fail(VP3D_ERR_INVALID, "adam_step: null pointer or empty tensor");
+  if (a->packed != nullptr && a->n % 4 != 0) return fail(VP3D_ERR_INVALID, "adam_step: packed weights need n % 4 == 0");
   if ((reinterpret_cast<uintptr_t>(a->p) | reinterpret_cast<uintptr_t>(a->g) | reinterpret_cast<uintptr_t>(a->m) |
        reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->vmax)) & 15)
     return fail(VP3D_ERR_INVALID, "adam_step: tensors must be 16-byte aligned");

@@ -30,13 +30,11 @@ __device__ __forceinline__ void store_elem<VP3D_TF32>(void* dst, long long i, fl
 template <int DT>
 __global__ void __launch_bounds__(256)
 pack_rows_kernel(const float* __restrict__ src, void* __restrict__ dst, long long rows, int c, int c_pad) {
-  const long long total = rows * c_pad;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const long long r = i / c_pad;
-    const int k = (int)(i - r * c_pad);
-    store_elem<DT>(dst, i, k < c ? __ldg(src + r * c + k) : 0.f);
-  }
+  // blockDim.x = c_pad threads across a row (coalesced in src and dst), blockDim.y rows per block, grid-stride over rows
+  const int k = threadIdx.x;
+  for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < rows; r += (long long)gridDim.x * blockDim.y)
+    for (int kk = k; kk < c_pad; kk += blockDim.x)
+      store_elem<DT>(dst, r * c_pad + kk, kk < c ? __ldg(src + r * c + kk) : 0.f);
 }
 
 // dst[n][tap][ci] = w[n][ci][tap]                  (transpose == 0; rows = output channels, K = tap*c_in_pad + ci)
@@ -114,10 +112,15 @@ static int ew_grid(long long total, int sm_count) {
 
 cudaError_t launch_pack_rows(int dtype, const float* src, void* dst, long long rows, int c, int c_pad, int sm_count,
                              cudaStream_t stream) {
-  const int grid = ew_grid(rows * c_pad, sm_count);
-  if (dtype == VP3D_F16) pack_rows_kernel<VP3D_F16><<<grid, 256, 0, stream>>>(src, dst, rows, c, c_pad);
-  else if (dtype == VP3D_BF16) pack_rows_kernel<VP3D_BF16><<<grid, 256, 0, stream>>>(src, dst, rows, c, c_pad);
-  else if (dtype == VP3D_TF32) pack_rows_kernel<VP3D_TF32><<<grid, 256, 0, stream>>>(src, dst, rows, c, c_pad);
+  const int bx = c_pad >= 256 ? 256 : ((c_pad + 31) / 32) * 32;
+  const dim3 block(bx, 256 / bx > 0 ? 256 / bx : 1);
+  long long gx = (rows + block.y - 1) / block.y;
+  if (gx > (long long)sm_count * 16) gx = (long long)sm_count * 16;
+  if (gx < 1) gx = 1;
+  const int grid = (int)gx;
+  if (dtype == VP3D_F16) pack_rows_kernel<VP3D_F16><<<grid, block, 0, stream>>>(src, dst, rows, c, c_pad);
+  else if (dtype == VP3D_BF16) pack_rows_kernel<VP3D_BF16><<<grid, block, 0, stream>>>(src, dst, rows, c, c_pad);
+  else if (dtype == VP3D_TF32) pack_rows_kernel<VP3D_TF32><<<grid, block, 0, stream>>>(src, dst, rows, c, c_pad);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }

@@ -483,6 +483,20 @@ grad_pack_rows_kernel(const float* __restrict__ src, void* __restrict__ dst, lon
 // reads p again. Arithmetic follows torch.optim.adam (capturable / fused form):
 //   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  vmax = max(vmax, v)
 //   p -= lr / (1 - b1^t) * m / (sqrt(vmax) / sqrt(1 - b2^t) + eps)
+__device__ __forceinline__ void adam_update(const AdamParams& a, float step_size, float bc2_sqrt, float& p, float g,
+                                            float& m, float& v, float& x) {
+  if (a.maximize) g = -g;
+  if (a.weight_decay != 0.f) g = fmaf(a.weight_decay, p, g);
+  m = fmaf(a.beta1, m, (1.f - a.beta1) * g);      // lerp form of exp_avg.lerp_(grad, 1 - beta1)
+  v = fmaf(a.beta2, v, (1.f - a.beta2) * g * g);
+  float denom_v = v;
+  if (a.vmax != nullptr) {
+    x = fmaxf(x, v);
+    denom_v = x;
+  }
+  p -= step_size * (m / (sqrtf(denom_v) / bc2_sqrt + a.eps));
+}
+
 template <int DT>
 __global__ void __launch_bounds__(256)
 adam_pack_kernel(AdamParams a) {
@@ -503,19 +517,7 @@ adam_pack_kernel(AdamParams a) {
     float pp[4] = {p4.x, p4.y, p4.z, p4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w},
           vv[4] = {v4.x, v4.y, v4.z, v4.w}, xx[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float g = a.maximize ? -gg[e] : gg[e];
-      if (a.weight_decay != 0.f) g = fmaf(a.weight_decay, pp[e], g);
-      mm[e] = fmaf(a.beta1, mm[e], (1.f - a.beta1) * g);      // lerp form of exp_avg.lerp_(grad, 1 - beta1)
-      vv[e] = fmaf(a.beta2, vv[e], (1.f - a.beta2) * g * g);
-      float denom_v = vv[e];
-      if (a.vmax != nullptr) {
-        xx[e] = fmaxf(xx[e], vv[e]);
-        denom_v = xx[e];
-      }
-      const float denom = sqrtf(denom_v) / bc2_sqrt + a.eps;
-      pp[e] -= step_size * (mm[e] / denom);
-    }
+    for (int e = 0; e < 4; ++e) adam_update(a, step_size, bc2_sqrt, pp[e], gg[e], mm[e], vv[e], xx[e]);
     reinterpret_cast<float4*>(a.p)[q] = make_float4(pp[0], pp[1], pp[2], pp[3]);
     reinterpret_cast<float4*>(a.m)[q] = make_float4(mm[0], mm[1], mm[2], mm[3]);
     reinterpret_cast<float4*>(a.v)[q] = make_float4(vv[0], vv[1], vv[2], vv[3]);
@@ -538,10 +540,19 @@ adam_pack_kernel(AdamParams a) {
       }
     }
   }
+  // scalar tail (small tensors whose length is not a multiple of 4; they carry no packed operand)
+  for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+    float pv = a.p[i], mv = a.m[i], vv1 = a.v[i], xv = a.vmax != nullptr ? a.vmax[i] : 0.f;
+    adam_update(a, step_size, bc2_sqrt, pv, a.g[i], mv, vv1, xv);
+    a.p[i] = pv;
+    a.m[i] = mv;
+    a.v[i] = vv1;
+    if (a.vmax != nullptr) a.vmax[i] = xv;
+  }
 }
 
 cudaError_t launch_adam_pack(int dtype, const AdamParams& a, int sm_count, cudaStream_t stream) {
-  long long blocks = ((a.n >> 2) + 255) / 256;
+  long long blocks = ((a.n + 3) / 4 + 255) / 256;
   if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
   if (blocks < 1) blocks = 1;
   if (dtype == VP3D_BF16) adam_pack_kernel<VP3D_BF16><<<(int)blocks, 256, 0, stream>>>(a);

@@ -4,10 +4,10 @@ The reference trains with `optim.Adam(model.parameters(), lr, amsgrad=True)` (ru
 optimiser step is followed by a re-pack of the fp32 convolution weights into the 16-bit K-major operands of the next
 forward. FusedAdam is a drop-in subclass of torch.optim.Adam -- same constructor, same per-parameter state
 (`step`, `exp_avg`, `exp_avg_sq`, `max_exp_avg_sq`), so `state_dict()` / `load_state_dict()` and run.py's checkpoints
-(run.py:436-445,559-569) are interchangeable with the stock optimiser -- whose `step()` sends the large convolution
-weights (99.9 % of the bytes) through vp3d_adam_step: one pass that updates p, m, v, vmax AND writes the packed operand
-the training forward has registered for that weight. Small tensors (BatchNorm affine, shrink layer) go through torch's
-own multi-tensor implementation. State steps live on the device (capturable), so the whole step can sit in a CUDA graph.
+(run.py:436-445,559-569) are interchangeable with the stock optimiser -- whose `step()` sends every fp32 CUDA parameter
+through vp3d_adam_step: one pass that updates p, m, v, vmax AND, for a convolution weight, writes the packed operand the
+training forward has registered for it. Anything else (non-contiguous, other dtypes) falls through to torch's own
+implementation. State steps live on the device (capturable), so the whole step can sit in a CUDA graph.
 """
 import ctypes as C
 
@@ -19,15 +19,17 @@ from . import native, ops
 
 class FusedAdam(torch.optim.Adam):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, *, maximize=False,
-                 min_numel=1 << 20):
+                 min_numel=1):
         super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=amsgrad,
                          maximize=maximize, capturable=True)
         self.min_numel = min_numel
 
     def _is_big(self, p, g):
-        return (p.is_cuda and p.dtype == torch.float32 and p.dim() == 3 and p.numel() >= self.min_numel and
-                p.numel() % 4 == 0 and p.is_contiguous() and g.dtype == torch.float32 and g.is_contiguous() and
-                not g.is_sparse)
+        """Tensors the native kernel updates: every contiguous fp32 CUDA parameter (the name is historical -- torch's
+        capturable multi-tensor path costs ~0.3 ms per step on the 27 small BatchNorm / bias tensors alone)."""
+        return (p.is_cuda and p.dtype == torch.float32 and p.numel() >= self.min_numel and p.is_contiguous() and
+                g.dtype == torch.float32 and g.is_contiguous() and not g.is_sparse and p.data_ptr() % 16 == 0 and
+                g.data_ptr() % 16 == 0)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -67,7 +69,7 @@ class FusedAdam(torch.optim.Adam):
                 a.step, a.lr_dev, a.maximize = steps[i].data_ptr(), lr_dev, int(bool(group['maximize']))
                 reg = p.__dict__.get('_vp3d_packed')
                 entry = None
-                if reg:
+                if reg and p.dim() == 3 and p.numel() % 4 == 0:
                     # the training forward registered the operand(s) it packs from this weight: refresh the first in the
                     # same pass, drop the others (they will be re-packed on demand)
                     key = next(iter(reg))

@@ -175,8 +175,8 @@ def _data_grad(dt, L, dz, n, c_pad, fan_in=None, fan_rows=0, fan_off=0, fan_mul=
     cin_pad = L.c_in_pad
     g_in = torch.empty((n, L.t_in, cin_pad), dtype=dz.dtype, device=dz.device)
     block_n = 256 if cin_pad % 256 == 0 else 64
-    if block_n == 256 and ((n * L.t_out + 127) // 128) * (taps * cin_pad // 256) < 148:
-        block_n = 64    # few tiles: narrower column tiles keep all SMs busy
+    if block_n == 256 and ((n * L.t_out + 127) // 128) * (taps * cin_pad // 256) * 4 <= 148:
+        block_n = 64    # few tiles: narrower column tiles keep all SMs busy (while they still fit in one wave)
     if s > 1 or taps == 1:
         if s > 1 and L.t_in != taps * L.t_out:
             raise RuntimeError('vp3d_b200: training a strided (1f) block needs t_in == %d * t_out (got %d -> %d)'

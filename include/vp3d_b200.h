@@ -279,7 +279,7 @@ int vp3d_grad_pack_rows(int dtype, const float* src, void* dst, long long rows, 
  * into the 16-bit K-major operand packed[c_out_pad][taps][k_pad] the next forward reads (padding entries are left
  * untouched: the caller zero-fills the buffer once). `step` is a device float holding the number of THIS update (>= 1),
  * `lr_dev` an optional device learning rate -- both so that a captured CUDA graph needs no re-capture when they change.
- * n must be a multiple of 4; vmax == NULL disables amsgrad; packed == NULL skips the re-pack. */
+ * Works on any fp32 tensor (BatchNorm affine, biases) with packed == NULL; vmax == NULL disables amsgrad. */
 typedef struct vp3d_adam_args {
   float* p; const float* g; float* m; float* v; float* vmax;
   long long n;
