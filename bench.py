@@ -352,10 +352,14 @@ def bench_train(args, rank, world, dev, steps, warm):
              'vp3d_wgrad_finish', 'vp3d_grad_scale', 'vp3d_grad_pack_rows')
     inst = min(steps, 10)
     coll0 = (sync.collectives, sync.bytes_reduced) if sync is not None else (0, 0)
+    from vp3d_b200 import training as _training
+    _overlap = _training.overlap_wgrad
+    _training.overlap_wgrad = False                   # one stream: a launch's events then bracket only that kernel
     with LaunchTimer(lib, gemm + bn + other) as lt:   # per-kernel-family timing needs the eager path
         for _ in range(inst):
             step(Wd, qd, td, camd)
         torch.cuda.synchronize()
+    _training.overlap_wgrad = _overlap
     coll_per_step = ((sync.collectives - coll0[0]) // inst, (sync.bytes_reduced - coll0[1]) / inst) if sync else (0, 0)
     gemm_ms, bn_ms, proj_ms = lt.ms(*gemm) / inst, lt.ms(*bn) / inst, lt.ms('vp3d_project_points') / inst
     conv_ms, wgrad_ms = lt.ms('vp3d_conv_block_fwd') / inst, lt.ms('vp3d_wgrad') / inst

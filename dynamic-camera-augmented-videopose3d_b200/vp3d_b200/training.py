@@ -22,6 +22,8 @@ STATS_IN_EPILOGUE_MIN_K = 2048
 grad_ready_hook = None   # set by vp3d_b200.ddp: called as hook(parameter, gradient) as soon as a gradient is issued
 grad_finish_hook = None  # ... and once at the end of the backward (waits for the outstanding all-reduces)
 sync_bn_group = None     # process group over which train-mode BatchNorm statistics are summed (None: per replica)
+overlap_wgrad = True     # weight-gradient GEMMs on a second stream, concurrent with the HBM-bound BN backward passes
+_side_streams = {}
 debug_keep_saved = False  # tests: keep the last forward's saved per-layer tensors in `debug_last_saved`
 debug_last_saved = None
 
@@ -151,17 +153,21 @@ def _views(L, n, c_pad):
     return ((n, L.t_out, c_pad, L.t_out * c_pad), (L.t_in, L.c_in_pad, L.c_in_pad, L.t_in * L.c_in_pad), d, 0)
 
 
-def _weight_grad(dt, L, dz, n, c_pad, gscale):
+def _weight_grad(dt, L, dz, n, c_pad, gscale, keep=None):
     dzv, av, row_step, col_step = _views(L, n, c_pad)
     c_out = L.conv.out_channels
     if L.stride > 1 and L.taps * L.c_in_pad <= 256:
         # narrow strided layer (expand: 3 x 64 input columns): all taps are adjacent columns of the reshaped view, so
         # they form ONE 256-wide tile (columns past taps * c_in_pad are zero-filled by TMA) and dz is read once
         packed = torch.zeros((1, c_pad, 256), dtype=torch.float32, device=dz.device)
+        if keep is not None:
+            keep.append(packed)
         ops.wgrad(dt, dz, dzv, L.a_in, av, c_pad, 256, 1, packed, block_n=256)
         return ops.wgrad_finish(packed, c_out, L.c_in, L.taps, c_pad, 256, gscale, tap_stride=L.c_in_pad, row_stride=256)
     block_n = 256 if L.c_in_pad % 256 == 0 else 64
     packed = torch.zeros((L.taps, c_pad, L.c_in_pad), dtype=torch.float32, device=dz.device)
+    if keep is not None:
+        keep.append(packed)
     ops.wgrad(dt, dz, dzv, L.a_in, av, c_pad, L.c_in_pad, L.taps, packed, b_tap_row_step=row_step,
               b_tap_col_step=col_step, block_n=block_n)
     return ops.wgrad_finish(packed, c_out, L.c_in, L.taps, c_pad, L.c_in_pad, gscale)
@@ -218,11 +224,35 @@ class _StackTrainFn(torch.autograd.Function):
         model, dt, layers, n, c_pad = ctx.model, ctx.dt, ctx.layers, ctx.n, ctx.c_pad
         hook = grad_ready_hook
         grads = {}
+        # The weight gradient of layer L (tensor-core bound) depends only on dz_L and the saved input; the critical path
+        # continues with dgrad_L -> BN/ReLU backward of layer L-1 (HBM bound). Issuing the wgrad GEMMs (+ their layout
+        # pass, + the gradient all-reduce hook) on a second stream lets the two kinds of work share the SMs: the wgrad
+        # kernel leaves enough registers for one BN-backward block per SM. Every tensor the side stream touches is kept
+        # alive in `keep` until the streams have joined (no reliance on record_stream, so the step stays capturable).
+        main = torch.cuda.current_stream(dy.device)
+        side = None
+        if overlap_wgrad:
+            key = (dy.device.index, main.cuda_stream)
+            side = _side_streams.get(key)
+            if side is None:
+                side = _side_streams[key] = torch.cuda.Stream(dy.device)
+        keep = []
 
         def done(param, g):
             grads[id(param)] = g
             if hook is not None:
                 hook(param, g)
+
+        def on_side(fn, *tensors):
+            """Runs fn() on the side stream after everything issued so far on the main stream."""
+            if side is None:
+                return fn()
+            keep.extend(tensors)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                return fn()
 
         # ---- shrink layer: y = a_last W^T + b
         n_out = model.shrink.out_channels
@@ -231,10 +261,15 @@ class _StackTrainFn(torch.autograd.Function):
         dzs, dbias = ops.grad_pack_rows(dt, dy2, SHRINK_PAD, gscale, want_col_sum=True)
         done(model.shrink.bias, dbias)
         rows = n * ctx.t_last
-        packed = torch.zeros((1, SHRINK_PAD, c_pad), dtype=torch.float32, device=dy.device)
-        ops.wgrad(dt, dzs, (1, rows, SHRINK_PAD, rows * SHRINK_PAD), ctx.a_last, (rows, c_pad, c_pad, rows * c_pad),
-                  SHRINK_PAD, c_pad, 1, packed)
-        done(model.shrink.weight, ops.wgrad_finish(packed, n_out, model.shrink.in_channels, 1, SHRINK_PAD, c_pad, gscale))
+
+        def shrink_wgrad():
+            packed = torch.zeros((1, SHRINK_PAD, c_pad), dtype=torch.float32, device=dy.device)
+            ops.wgrad(dt, dzs, (1, rows, SHRINK_PAD, rows * SHRINK_PAD), ctx.a_last, (rows, c_pad, c_pad, rows * c_pad),
+                      SHRINK_PAD, c_pad, 1, packed)
+            keep.append(packed)
+            done(model.shrink.weight,
+                 ops.wgrad_finish(packed, n_out, model.shrink.in_channels, 1, SHRINK_PAD, c_pad, gscale))
+        on_side(shrink_wgrad, dzs, gscale)
         g = torch.empty((n, ctx.t_last, c_pad), dtype=dzs.dtype, device=dy.device)
         k_shrink = ctx.w_shrink.shape[0]      # forward-packed [n_out_pad][c_pad], read as W^T
         ops.conv_block(dt, dzs, (1, rows, SHRINK_PAD, SHRINK_PAD, rows * SHRINK_PAD), ctx.w_shrink, 1, 0, k_shrink, rows,
@@ -248,7 +283,7 @@ class _StackTrainFn(torch.autograd.Function):
                                                L.drop, gscale, count=L.count, group=sync_bn_group)
             done(L.bn.weight, dgamma)
             done(L.bn.bias, dbeta)
-            done(L.conv.weight, _weight_grad(dt, L, dz, n, c_pad, gscale))
+            on_side(lambda L=L, dz=dz: done(L.conv.weight, _weight_grad(dt, L, dz, n, c_pad, gscale, keep)), dz)
             if idx == 0:
                 break  # no gradient wrt the 2-D keypoints (the reference never asks for one, run.py:458-485)
             if L.res_of is not None:
@@ -259,8 +294,11 @@ class _StackTrainFn(torch.autograd.Function):
             else:
                 g_block, fan_rows, fan_off, fan_mul = fan
                 g = _data_grad(dt, L, dz, n, c_pad, fan_in=g_block, fan_rows=fan_rows, fan_off=fan_off, fan_mul=fan_mul)
+        if side is not None:
+            main.wait_stream(side)
         if grad_finish_hook is not None:
             grad_finish_hook()
+        keep.clear()
         out = [grads.get(id(p)) for p in ctx.params]
         ctx.layers = ctx.a_last = None
         return (None, None, None) + tuple(out)
