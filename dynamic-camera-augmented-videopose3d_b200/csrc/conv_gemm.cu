@@ -23,6 +23,10 @@ namespace vp3d {
 
 constexpr int kBlockM = 128;
 constexpr int kTileKBytes = 128;  // one swizzle span of K per stage row
+#ifndef VP3D_K1_STAGES
+#define VP3D_K1_STAGES 4
+#endif
+constexpr int kOutBufs = 2;                         // TMA-store staging buffers per epilogue warp (ring)
 constexpr int kEpiWarps = 8;                        // two per TMEM lane quadrant, each takes half of the columns
 constexpr int kNumThreads = 64 + 32 * kEpiWarps;    // + TMA producer warp + MMA issuer warp
 
@@ -31,14 +35,19 @@ struct GemmCfg {
   static constexpr int kABytes = kBlockM * kTileKBytes;
   static constexpr int kBBytes = BN * kTileKBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : 8;
+  static constexpr int kStages = (BN == 256) ? VP3D_K1_STAGES : 2 * VP3D_K1_STAGES;
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int kOutStageBytes = kEpiWarps * 32 * 64;  // per epilogue warp: 32 rows x 64 B staging for a TMA store
+  // TMA-store staging: per epilogue warp a ring of kOutBufs buffers of 32 rows x 64 B. The second half of the region
+  // doubles as the train-mode statistics accumulators (per warp: BN/2 columns x {sum, sum of squares} fp32 = 8 KB for
+  // BN = 256): launches that reduce statistics in the epilogue are the long-K, MMA-bound ones, where one staging buffer
+  // per warp is enough.
+  static constexpr int kOutBufBytes = kEpiWarps * 32 * 64;
+  static constexpr int kOutStageBytes = kOutBufs * kOutBufBytes;
   static constexpr int kBarBytes = 256;
-  static constexpr int kStatBytes = 4 * BN * 2 * 4;  // per epilogue warp: BN x {sum, sum of squares} fp32
+  static constexpr int kStatBytes = 4 * BN * 2 * 4;
+  static_assert(kStatBytes <= kOutBufBytes, "statistics accumulators alias the second staging buffer");
   static constexpr int kAffineBytes = 2 * BN * 4;    // scale / shift of the CTA's current column tile
-  static constexpr int kSmemBytes =
-      kStages * kStageBytes + kOutStageBytes + kBarBytes + kStatBytes + kAffineBytes + 1024;  // +1024: alignment slack
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutStageBytes + kBarBytes + kAffineBytes;
 };
 
 template <int DT>
@@ -119,8 +128,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int kMmasPerStage = 4;                           // 32 bytes of K per tcgen05.mma
   constexpr uint32_t kIdesc = make_instr_desc(ET::kFormat, kBlockM, BN) | (BMN ? (1u << 16) : 0u);
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // SWIZZLE_128B tiles need 1024-byte alignment; the kernel has no static shared memory, so the dynamic window starts at
+  // the CTA's (1024-aligned) shared base -- checked below instead of paying 1 KB of slack
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("vp3d: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   uint8_t* out_stage = smem + Cfg::kStages * Cfg::kStageBytes;  // 1024-aligned: stages are multiples of 1 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + Cfg::kOutStageBytes);
   uint64_t* full_bar = bars;
@@ -128,8 +142,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  float* stat_smem = reinterpret_cast<float*>(out_stage + Cfg::kOutStageBytes + Cfg::kBarBytes);
-  float* affine_smem = stat_smem + Cfg::kStatBytes / 4;  // [0, BN) scale, [BN, 2 BN) shift
+  float* stat_smem = reinterpret_cast<float*>(out_stage + Cfg::kOutBufBytes);  // aliases staging buffer 1 (see GemmCfg)
+  float* affine_smem = reinterpret_cast<float*>(out_stage + Cfg::kOutStageBytes + Cfg::kBarBytes);  // scale | shift
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -240,6 +254,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int epi = warp - 2;
     const int half = epi >> 2;
     const int row = quad * 32 + lane;
+    unsigned out_buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     // per-warp fp32 statistics accumulators in shared memory, flushed (double atomics) when the CTA moves to another
@@ -406,8 +421,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // memory in the SWIZZLE_64B layout (conflict-free 16-byte stores) and leave as ONE coalesced TMA store;
           // TMA clips rows past the end of the sequence, so no row mask is needed here
           constexpr int D16 = (DT == VP3D_TF32) ? VP3D_F16 : DT;
-          uint8_t* my_stage = out_stage + epi * (32 * 64);
-          if (lane == 0) tma_store_wait_read<0>();  // the previous store of this warp has drained the buffer
+          // ring of 2 staging buffers (1 when the second one holds the statistics accumulators)
+          const unsigned b = p.stat_sum != nullptr ? 0u : (out_buf++ & 1u);
+          uint8_t* my_stage = out_stage + b * Cfg::kOutBufBytes + epi * (32 * 64);
+          if (lane == 0) {  // the store that last used this buffer has drained it
+            if (p.stat_sum != nullptr) tma_store_wait_read<0>();
+            else tma_store_wait_read<1>();
+          }
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
