@@ -21,6 +21,17 @@ import torch
 from . import native, ops
 
 
+def build_pairs(lengths, chunk_length):
+    """(seq_idx, start_frame, end_frame) lineage tuples, exactly as generators.py:39-45 builds them."""
+    pairs = []
+    for i, n in enumerate(lengths):
+        n_chunks = (n + chunk_length - 1) // chunk_length
+        offset = (n_chunks * chunk_length - n) // 2
+        bounds = np.arange(n_chunks + 1) * chunk_length - offset
+        pairs += zip(np.repeat(i, len(bounds) - 1), bounds[:-1], bounds[1:])
+    return pairs
+
+
 class DeviceWindowFeeder:
     def __init__(self, world_3d, quats, trans, intrinsics, batch_size, chunk_length=1, pad=0, causal_shift=0,
                  shuffle=True, random_seed=1234, root_relative=True, linear=False, want_cameras=False, device='cuda',
@@ -41,14 +52,7 @@ class DeviceWindowFeeder:
         starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
         self.seq_start = torch.from_numpy(starts).to(dev)
         self.seq_len = torch.tensor(lens, dtype=torch.int64, device=dev)
-        # lineage info, as generators.py:39-45
-        pairs = []
-        for i, n in enumerate(lens):
-            n_chunks = (n + chunk_length - 1) // chunk_length
-            offset = (n_chunks * chunk_length - n) // 2
-            bounds = np.arange(n_chunks + 1) * chunk_length - offset
-            pairs += zip(np.repeat(i, len(bounds) - 1), bounds[:-1], bounds[1:])
-        self.pairs = pairs
+        self.pairs = pairs = build_pairs(lens, chunk_length)
         self.batch_size, self.chunk_length, self.pad, self.causal_shift = batch_size, chunk_length, pad, causal_shift
         self.num_batches = (len(pairs) + batch_size - 1) // batch_size
         self.random = np.random.RandomState(random_seed)

@@ -168,6 +168,37 @@ def camera_grad_cases():
     np.savez_compressed(os.path.join(HERE, 'camera_grad.npz'), **out)
 
 
+def generator_cases():
+    """Epoch order and window placement of the reference's ChunkedGenerator (generators.py:11-137) on a small synthetic
+    set: the (seq, start_3d, end_3d) chunks of the first batches of two epochs, and one assembled 2-D batch row."""
+    from common.generators import ChunkedGenerator
+    rng = np.random.default_rng(99)
+    lens = [37, 64, 21, 50]
+    p3 = [rng.standard_normal((n, 17, 3)).astype(np.float32) for n in lens]
+    p2 = [rng.standard_normal((n, 17, 2)).astype(np.float32) for n in lens]
+    cams = [{'extrinsics': rng.standard_normal((n, 3, 4)).astype(np.float32),
+             'intrinsics': {'focal_length': (1.5, 1.5), 'center': (0.0, 0.0)}} for n in lens]
+    out = {'lens': np.array(lens)}
+    for chunk, pad, shift, tag in ((1, 13, 0, 'a'), (3, 4, 4, 'b')):
+        gen = ChunkedGenerator(16, cams, p3, p2, chunk, pad=pad, causal_shift=shift, shuffle=True, random_seed=1234)
+        out['pairs_' + tag] = np.array([[int(a), int(b), int(c)] for a, b, c in gen.pairs])
+        order = []
+        rows = []
+        for epoch in range(2):
+            st = np.random.RandomState(1234) if False else None
+            start_idx, pairs = gen.next_pairs()
+            order.append(np.array(pairs[:48]).astype(np.int64))
+            for _cam, b3, b2 in gen.next_epoch():
+                rows.append(np.array(b2[:4]).astype(np.float32))
+                break
+        out['order_' + tag] = np.stack(order)
+        out['batch2d_' + tag] = np.stack(rows)
+        out['params_' + tag] = np.array([chunk, pad, shift])
+    for i, a in enumerate(p2):
+        out['p2_%d' % i] = a
+    np.savez_compressed(os.path.join(HERE, 'generator.npz'), **out)
+
+
 def loss_cases():
     g = torch.Generator().manual_seed(77)
     out = {}
@@ -204,6 +235,7 @@ if __name__ == '__main__':
     seeded_large('temporal_243f_j31.npz', [3, 3, 3, 3, 3], 245, seed=10, j_in=31, j_out=31)
     camera_cases()
     camera_grad_cases()
+    generator_cases()
     loss_cases()
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
