@@ -34,7 +34,8 @@ cudaError_t launch_n_mpjpe_fwd(const float* pred, const float* tgt, long long n_
 cudaError_t launch_pack_rows(int dtype, const float* src, void* dst, long long rows, int c, int c_pad, int sm_count,
                              cudaStream_t stream);
 cudaError_t launch_pack_weight(int dtype, const float* w, void* dst, int c_out, int c_in, int taps, int rows_pad,
-                               int k_pad_per_tap, int transpose, int sm_count, cudaStream_t stream);
+                               int k_pad_per_tap, int transpose, int sm_count, cudaStream_t stream,
+                               const float* row_scale = nullptr);
 cudaError_t launch_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                            float* scale, float* shift, int c, int c_pad, cudaStream_t stream);
 }  // namespace vp3d
@@ -177,7 +178,6 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
   if ((a->a_row_stride * eb) % 16 != 0 || (a->a_seq_stride * eb) % 16 != 0)
     return fail(VP3D_ERR_INVALID, "activation strides must be multiples of 16 bytes");
   if (a->scale != nullptr && a->shift == nullptr) return fail(VP3D_ERR_INVALID, "scale without shift");
-  if (a->scale == nullptr && a->shift != nullptr) return fail(VP3D_ERR_INVALID, "shift without scale");
   if ((a->stat_sum == nullptr) != (a->stat_sqsum == nullptr)) return fail(VP3D_ERR_INVALID, "stat_sum / stat_sqsum");
   if (a->dtype == VP3D_TF32 && !a->out_f32) return fail(VP3D_ERR_INVALID, "TF32 activations are fp32: set out_f32");
   if (!a->out_f32 && ((a->out_row_stride * 2) % 16 != 0 || (a->out_seq_stride * 2) % 16 != 0))
@@ -293,6 +293,20 @@ int vp3d_pack_conv_weight(int dtype, const float* w, void* dst, int c_out, int c
   cudaError_t e = vp3d::launch_pack_weight(dtype, w, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap, transpose,
                                            dev->sm_count, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "pack_weight launch");
+  return VP3D_OK;
+}
+
+int vp3d_pack_conv_weight_scaled(int dtype, const float* w, const float* row_scale, void* dst, int c_out, int c_in,
+                                 int taps, int rows_pad, int k_pad_per_tap, void* stream) {
+  if (w == nullptr || dst == nullptr || row_scale == nullptr || c_out <= 0 || c_in <= 0 || taps <= 0)
+    return fail(VP3D_ERR_INVALID, "pack_conv_weight_scaled args");
+  if (rows_pad < c_out || k_pad_per_tap < c_in) return fail(VP3D_ERR_INVALID, "pack_conv_weight_scaled padding");
+  if ((long long)rows_pad * k_pad_per_tap >= (1LL << 31)) return fail(VP3D_ERR_INVALID, "pack_conv_weight_scaled: too large");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_pack_weight(dtype, w, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap, 0, dev->sm_count,
+                                           static_cast<cudaStream_t>(stream), row_scale);
+  if (e != cudaSuccess) return cuda_fail(e, "pack_weight (scaled) launch");
   return VP3D_OK;
 }
 

@@ -279,14 +279,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         stat_flush();
         stat_n0 = tc.n0;
       }
-      if (p.scale != nullptr && tc.n0 != affine_n0) {
+      if (p.shift != nullptr && tc.n0 != affine_n0) {
         // per-channel scale / shift of this column tile -> shared memory (once per launch when the grid is a multiple
         // of n_tiles). Named barrier 1 over the epilogue threads on both sides: nobody still reads the old tile's
         // values, everybody sees the new ones.
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
         const int e = threadIdx.x - 64;
         for (int j = e; j < BN; j += 32 * kEpiWarps) {
-          affine_smem[j] = __ldg(p.scale + tc.n0 * BN + j);
+          if (p.scale != nullptr) affine_smem[j] = __ldg(p.scale + tc.n0 * BN + j);
           affine_smem[BN + j] = __ldg(p.shift + tc.n0 * BN + j);
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
@@ -315,6 +315,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       };
       uint4 rcur[4], rnext[4];
+      if (res_any) {
+        // the whole residual span of this thread's row (kChunks x 64 B) goes to L2 now; the register prefetch below is
+        // only one chunk deep, which covers an L2 hit but not a DRAM miss
+        const char* rp = reinterpret_cast<const char*>(static_cast<const uint16_t*>(p.res) + res_off + tc.n0 * BN +
+                                                       half * kChunks * 32);
+#pragma unroll
+        for (int k = 0; k < kChunks * 64; k += 128)
+          if (res_in_window(half * kChunks + k / 64)) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + k));
+      }
       res_load(half * kChunks, rcur);
 
       mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -366,6 +375,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             f[4 * j + 1] = fmaf(f[4 * j + 1], sc.y, sh.y);
             f[4 * j + 2] = fmaf(f[4 * j + 2], sc.z, sh.z);
             f[4 * j + 3] = fmaf(f[4 * j + 3], sc.w, sh.w);
+          }
+        } else if (p.shift != nullptr) {
+          // shift only: the per-channel scale was folded into the packed weight rows (eval-mode BatchNorm, bias)
+          const float4* sh4 = reinterpret_cast<const float4*>(affine_smem + BN + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 sh = sh4[j];
+            f[4 * j + 0] += sh.x;
+            f[4 * j + 1] += sh.y;
+            f[4 * j + 2] += sh.z;
+            f[4 * j + 3] += sh.w;
           }
         }
         if (p.relu) {

@@ -89,16 +89,18 @@ bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, 
 // contiguous span) and writes one element into each tap's K block (contiguous across the warp)
 template <int DT>
 __global__ void __launch_bounds__(256)
-pack_weight_fwd_kernel(const float* __restrict__ w, void* __restrict__ dst, int c_out, int c_in, int taps, int rows_pad,
-                       int k_pad_per_tap) {
+pack_weight_fwd_kernel(const float* __restrict__ w, const float* __restrict__ row_scale, void* __restrict__ dst,
+                       int c_out, int c_in, int taps, int rows_pad, int k_pad_per_tap) {
   const int total = rows_pad * k_pad_per_tap;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int n = i / k_pad_per_tap;
     const int ci = i - n * k_pad_per_tap;
     const bool ok = n < c_out && ci < c_in;
+    const float sc = (ok && row_scale != nullptr) ? __ldg(row_scale + n) : 1.f;
     const float* src = w + ((long long)n * c_in + ci) * taps;
     const long long d0 = (long long)n * taps * k_pad_per_tap + ci;
-    for (int tap = 0; tap < taps; ++tap) store_elem<DT>(dst, d0 + (long long)tap * k_pad_per_tap, ok ? __ldg(src + tap) : 0.f);
+    for (int tap = 0; tap < taps; ++tap)
+      store_elem<DT>(dst, d0 + (long long)tap * k_pad_per_tap, ok ? __ldg(src + tap) * sc : 0.f);
   }
 }
 
@@ -126,16 +128,17 @@ cudaError_t launch_pack_rows(int dtype, const float* src, void* dst, long long r
 }
 
 cudaError_t launch_pack_weight(int dtype, const float* w, void* dst, int c_out, int c_in, int taps, int rows_pad,
-                               int k_pad_per_tap, int transpose, int sm_count, cudaStream_t stream) {
+                               int k_pad_per_tap, int transpose, int sm_count, cudaStream_t stream,
+                               const float* row_scale) {
   const long long k_total = transpose == 1 ? k_pad_per_tap : (long long)taps * k_pad_per_tap;
   if (transpose == 0 && (long long)rows_pad * k_pad_per_tap < (1LL << 31)) {
     const int g = ew_grid((long long)rows_pad * k_pad_per_tap, sm_count);
     if (dtype == VP3D_F16)
-      pack_weight_fwd_kernel<VP3D_F16><<<g, 256, 0, stream>>>(w, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap);
+      pack_weight_fwd_kernel<VP3D_F16><<<g, 256, 0, stream>>>(w, row_scale, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap);
     else if (dtype == VP3D_BF16)
-      pack_weight_fwd_kernel<VP3D_BF16><<<g, 256, 0, stream>>>(w, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap);
+      pack_weight_fwd_kernel<VP3D_BF16><<<g, 256, 0, stream>>>(w, row_scale, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap);
     else if (dtype == VP3D_TF32)
-      pack_weight_fwd_kernel<VP3D_TF32><<<g, 256, 0, stream>>>(w, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap);
+      pack_weight_fwd_kernel<VP3D_TF32><<<g, 256, 0, stream>>>(w, row_scale, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap);
     else
       return cudaErrorInvalidValue;
     return cudaGetLastError();

@@ -200,6 +200,17 @@ def pack_conv_weight(dt, w, rows_pad, k_pad_per_tap, transpose=0):
     return dst
 
 
+def pack_conv_weight_scaled(dt, w, row_scale, rows_pad, k_pad_per_tap):
+    """Forward operand with every output-channel row multiplied by row_scale[n] (folded BatchNorm scale)."""
+    w = f32c(w.detach())
+    c_out, c_in, taps = w.shape
+    dst = torch.empty((rows_pad, taps * k_pad_per_tap), dtype=torch_dtype(dt), device=w.device)
+    with torch.cuda.device(w.device):
+        check(lib().vp3d_pack_conv_weight_scaled(dt, _ptr(w), _ptr(f32c(row_scale)), _ptr(dst), c_out, c_in, taps,
+                                                 rows_pad, k_pad_per_tap, _stream()), 'pack_conv_weight_scaled')
+    return dst
+
+
 def bn_fold(bn, c_pad):
     """nn.BatchNorm1d container (eval statistics) -> (scale, shift) fp32 [c_pad]."""
     c = bn.num_features

@@ -78,7 +78,8 @@ typedef struct vp3d_conv_args {
   long long n_valid;
   int out_round_tf32;      /* fp32 output rounded (nearest) to TF32 so a following TF32 layer reads exact operands */
 
-  const float* scale;      /* [n_pad] or NULL */
+  const float* scale;      /* [n_pad] or NULL (NULL with shift given: epilogue(x) = relu?(x + shift[n]) -- the scale is
+                              folded into the packed weight rows, see vp3d_pack_conv_weight_scaled) */
   const float* shift;      /* [n_pad]; required when scale is given */
   int relu;
   const void* res;         /* residual source, element type = dtype (fp32 for TF32), or NULL */
@@ -107,6 +108,11 @@ int vp3d_pack_rows(int dtype, const float* src, void* dst, long long rows, int c
  *                 (data-gradient operand of a dilated convolution, taps walked with a negative row step) */
 int vp3d_pack_conv_weight(int dtype, const float* w, void* dst, int c_out, int c_in, int taps, int rows_pad,
                           int k_pad_per_tap, int transpose, void* stream);
+
+/* transpose == 0 packing with every output-channel row multiplied by row_scale[n] before rounding to the operand type:
+ * eval-mode BatchNorm's gamma / sqrt(var + eps) folded into the weights, so the GEMM epilogue only adds the shift. */
+int vp3d_pack_conv_weight_scaled(int dtype, const float* w, const float* row_scale, void* dst, int c_out, int c_in,
+                                 int taps, int rows_pad, int k_pad_per_tap, void* stream);
 
 /* Eval-mode nn.BatchNorm1d (TemporalModel.py:32,117,119) -> scale = gamma / sqrt(var + eps), shift = beta - mean *
  * scale; entries [c, c_pad) are zeroed. */
