@@ -188,6 +188,8 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
       return fail(VP3D_ERR_INVALID, "residual must be 16-byte aligned with 16-byte strides");
   }
   if (a->out_f32 && (a->n_valid <= 0 || a->n_valid > a->n_pad)) return fail(VP3D_ERR_INVALID, "bad n_valid");
+  if (a->dyn_offsets != nullptr && (a->out_f32 || a->a_seqs != 1 || a->out_rows_total < a->rows_out))
+    return fail(VP3D_ERR_INVALID, "dyn_offsets: 16-bit output, one flat sequence and out_rows_total >= rows_out required");
   if (a->res_cols < 0 || a->res_col_off < 0 || a->res_cols % 32 != 0 || a->res_col_off % 32 != 0 ||
       a->res_col_off + a->res_cols > a->n_pad)
     return fail(VP3D_ERR_INVALID, "residual column window must be 32-aligned and inside n_pad");
@@ -219,9 +221,10 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
   memset(&tmC, 0, sizeof(tmC));
   if (!a->out_f32) {
     // output view [n_pad columns][rows_out][sequences]; one store = 32 columns x 32 rows (one epilogue warp, 64 B rows)
-    cuuint64_t dims[3] = {(cuuint64_t)a->n_pad, (cuuint64_t)a->rows_out, (cuuint64_t)a->a_seqs};
+    const long long out_rows = a->dyn_offsets != nullptr ? a->out_rows_total : a->rows_out;
+    cuuint64_t dims[3] = {(cuuint64_t)a->n_pad, (cuuint64_t)out_rows, (cuuint64_t)a->a_seqs};
     cuuint64_t strides[2] = {(cuuint64_t)(a->out_row_stride * 2), (cuuint64_t)(a->out_seq_stride * 2)};
-    if (a->a_seqs == 1) strides[1] = (cuuint64_t)(a->rows_out * a->out_row_stride * 2);
+    if (a->a_seqs == 1) strides[1] = (cuuint64_t)(out_rows * a->out_row_stride * 2);
     cuuint32_t box[3] = {32, 32, 1};
     if (int rc = encode_map(&tmC, a->dtype, 3, a->out, dims, strides, box, "output", CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
   }
@@ -237,6 +240,7 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
   p.tap_row_step = a->tap_row_step;
   p.a_row_off = (int)a->a_row_off;
   p.b_tap_col_step = (int)a->w_tap_col_step;
+  p.dyn = a->dyn_offsets;
   p.scale = a->scale;
   p.shift = a->shift;
   p.relu = a->relu;
@@ -652,6 +656,32 @@ int vp3d_grad_pack_rows(int dtype, const float* src, void* dst, long long rows, 
   cudaError_t e = vp3d::launch_grad_pack_rows(dtype, src, dst, rows, c, c_pad, gscale_buf, col_sum, dev->sm_count,
                                               static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "grad_pack_rows launch");
+  return VP3D_OK;
+}
+
+int vp3d_stream_advance(long long* step, int n_rings, const int* ring_len, const int* ring_dil, const int* ring_taps,
+                        int rows_per_slot, int* table, int n_launch, const int* launch_desc, int* launch_table,
+                        void* stream) {
+  if (!step || !ring_len || !ring_dil || !ring_taps || !table || n_rings <= 0 || n_rings > 64 || rows_per_slot <= 0)
+    return fail(VP3D_ERR_INVALID, "stream_advance args");
+  if (n_launch < 0 || n_launch > 64 || (n_launch > 0 && (!launch_desc || !launch_table)))
+    return fail(VP3D_ERR_INVALID, "stream_advance launch table");
+  cudaError_t e = vp3d::launch_stream_advance(step, n_rings, ring_len, ring_dil, ring_taps, rows_per_slot, table,
+                                              n_launch, launch_desc, launch_table,
+                                              static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "stream_advance launch");
+  return VP3D_OK;
+}
+
+int vp3d_ring_write(int dtype, const float* src, void* ring, const int* table_entry, long long rows, int c, int c_pad,
+                    void* stream) {
+  if (dtype != VP3D_F16 && dtype != VP3D_BF16) return fail(VP3D_ERR_INVALID, "ring_write: dtype must be F16 or BF16");
+  if (!src || !ring || !table_entry || rows <= 0 || c <= 0 || c_pad < c) return fail(VP3D_ERR_INVALID, "ring_write args");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_ring_write(dtype, src, ring, table_entry, rows, c, c_pad, dev->sm_count,
+                                          static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "ring_write launch");
   return VP3D_OK;
 }
 

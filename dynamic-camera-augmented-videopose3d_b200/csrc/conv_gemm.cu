@@ -178,6 +178,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const int a_row_off = p.dyn != nullptr ? p.dyn[0] : p.a_row_off;  // streaming: ring position read on the device
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(tile, p);
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -187,7 +188,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           tma_load_3d(sa, &tmA, &full_bar[stage], kc * kElemsPerKBlock,
-                      tc.t0 + p.a_row_off + tap * p.tap_row_step, tc.seq);
+                      tc.t0 + a_row_off + tap * p.tap_row_step, tc.seq);
           if (BMN) {
             // rows kc*64.. of the [c_out][taps * c_in] weights, columns of this tap's N tile, 64 at a time
 #pragma unroll
@@ -273,6 +274,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     };
     if (p.stat_sum != nullptr) stat_flush();
     int affine_n0 = -1;
+    // streaming (CausalStream under a CUDA graph): residual row, output row and mirror output row come from a device
+    // table that a small kernel advances once per frame, so the captured launch never changes
+    const int res_row_off_dyn = p.dyn != nullptr ? p.dyn[1] : p.res_row_off;
+    const int out_row_off = p.dyn != nullptr ? p.dyn[2] : 0;
+    const int out_row_off2 = p.dyn != nullptr ? p.dyn[3] : -1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(tile, p);
       if (p.stat_sum != nullptr && tc.n0 != stat_n0) {
@@ -295,7 +301,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int t = tc.t0 + row;
       const bool row_ok = t < p.rows_out;
       const long long out_off = (long long)tc.seq * p.out_seq_stride + (long long)t * p.out_row_stride;
-      const long long res_row = (long long)t * p.res_row_mul + p.res_row_off;
+      const long long res_row = (long long)t * p.res_row_mul + res_row_off_dyn;
       const bool res_row_ok = p.res_rows <= 0 || (res_row >= 0 && res_row < p.res_rows);
       const long long res_off =
           (long long)tc.seq * p.res_seq_stride + res_row * p.res_row_stride - p.res_col_off;
@@ -460,7 +466,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&tmC, my_stage, tc.n0 * BN + c * 32, tc.t0 + quad * 32, tc.seq);
+            tma_store_3d(&tmC, my_stage, tc.n0 * BN + c * 32, tc.t0 + quad * 32 + out_row_off, tc.seq);
+            if (out_row_off2 >= 0)   // mirror slot of a streaming ring
+              tma_store_3d(&tmC, my_stage, tc.n0 * BN + c * 32, tc.t0 + quad * 32 + out_row_off2, tc.seq);
             tma_store_commit();
           }
         }

@@ -104,6 +104,68 @@ pack_weight_fwd_kernel(const float* __restrict__ w, const float* __restrict__ ro
   }
 }
 
+// Streaming ring bookkeeping (vp3d_b200/streaming.py): see vp3d_stream_advance in include/vp3d_b200.h.
+__global__ void stream_advance_kernel(long long* step, int n_rings, const int* ring_len, const int* ring_dil,
+                                      const int* ring_taps, int rows_per_slot, int* table, int n_launch,
+                                      const int* launch_desc, int* launch_table) {
+  __shared__ int ring[64][4];
+  const long long t = *step;          // frame index of the step being issued
+  const int i = threadIdx.x;
+  if (i < n_rings) {
+    const int L = ring_len[i];
+    const int q = (int)(t % L) + L;   // upper copy of the current slot: taps q - k*d never wrap
+    ring[i][0] = (q - (ring_taps[i] - 1) * ring_dil[i]) * rows_per_slot;
+    ring[i][1] = q * rows_per_slot;
+    ring[i][2] = q * rows_per_slot;
+    ring[i][3] = (q - L) * rows_per_slot;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) table[4 * i + k] = ring[i][k];
+  }
+  __syncthreads();
+  if (i < n_launch) {
+    // launch i reads ring launch_desc[3i] as its A operand, ring [3i+1] as residual, writes ring [3i+2] (-1: none)
+    const int ra = launch_desc[3 * i], rr = launch_desc[3 * i + 1], ro = launch_desc[3 * i + 2];
+    launch_table[4 * i + 0] = ra >= 0 ? ring[ra][0] : 0;
+    launch_table[4 * i + 1] = rr >= 0 ? ring[rr][1] : 0;
+    launch_table[4 * i + 2] = ro >= 0 ? ring[ro][2] : 0;
+    launch_table[4 * i + 3] = ro >= 0 ? ring[ro][3] : -1;
+  }
+  if (i == 0) *step = t + 1;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256)
+ring_write_kernel(const float* __restrict__ src, void* __restrict__ ring, const int* __restrict__ entry, long long rows,
+                  int c, int c_pad) {
+  const long long r_hi = entry[2], r_lo = entry[3];
+  const long long total = rows * c_pad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / c_pad;
+    const int k = (int)(i - r * c_pad);
+    const float v = k < c ? __ldg(src + r * c + k) : 0.f;
+    store_elem<DT>(ring, (r_hi + r) * c_pad + k, v);
+    store_elem<DT>(ring, (r_lo + r) * c_pad + k, v);
+  }
+}
+
+cudaError_t launch_stream_advance(long long* step, int n_rings, const int* ring_len, const int* ring_dil,
+                                  const int* ring_taps, int rows_per_slot, int* table, int n_launch,
+                                  const int* launch_desc, int* launch_table, cudaStream_t stream) {
+  stream_advance_kernel<<<1, 64, 0, stream>>>(step, n_rings, ring_len, ring_dil, ring_taps, rows_per_slot, table,
+                                              n_launch, launch_desc, launch_table);
+  return cudaGetLastError();
+}
+
+static int ew_grid(long long total, int sm_count);
+cudaError_t launch_ring_write(int dtype, const float* src, void* ring, const int* table, long long rows, int c, int c_pad,
+                              int sm_count, cudaStream_t stream) {
+  const int grid = ew_grid(rows * c_pad, sm_count);
+  if (dtype == VP3D_F16) ring_write_kernel<VP3D_F16><<<grid, 256, 0, stream>>>(src, ring, table, rows, c, c_pad);
+  else if (dtype == VP3D_BF16) ring_write_kernel<VP3D_BF16><<<grid, 256, 0, stream>>>(src, ring, table, rows, c, c_pad);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
 static int ew_grid(long long total, int sm_count) {
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)sm_count * 8;

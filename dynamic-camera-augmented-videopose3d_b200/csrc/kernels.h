@@ -20,6 +20,7 @@ struct ConvGemmParams {
   int tap_row_step;     // input-row distance between consecutive taps (dilation)
   int a_row_off;        // input row of tap 0 for output row 0 (may be negative: TMA zero-fills)
   int b_tap_col_step;   // MN-major weights only: weight columns per tap (c_in_pad of the forward layer)
+  const int* dyn;       // optional device int[4] {a_row_off, res_row_off, out_row_off, out_row_off2 | -1} (streaming)
 
   const float* scale;   // per output channel, nullptr = identity
   const float* shift;
@@ -88,6 +89,11 @@ struct AdamParams {
   int c_in, taps, k_pad;
 };
 cudaError_t launch_adam_pack(int dtype, const AdamParams& a, int sm_count, cudaStream_t stream);
+cudaError_t launch_stream_advance(long long* step, int n_rings, const int* ring_len, const int* ring_dil,
+                                  const int* ring_taps, int rows_per_slot, int* table, int n_launch,
+                                  const int* launch_desc, int* launch_table, cudaStream_t stream);
+cudaError_t launch_ring_write(int dtype, const float* src, void* ring, const int* table, long long rows, int c, int c_pad,
+                              int sm_count, cudaStream_t stream);
 cudaError_t launch_bn_finalize(const double* sum, const double* sqsum, long long count, const float* gamma,
                                const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                                long long* nbt, float* scale, float* shift, float* mean, float* invstd, int c, int c_pad,

@@ -30,6 +30,7 @@ class ConvArgs(C.Structure):
         ('res', C.c_void_p), ('res_row_stride', C.c_longlong), ('res_seq_stride', C.c_longlong),
         ('res_row_mul', C.c_int), ('res_row_off', C.c_int),
         ('res_rows', C.c_longlong), ('res_col_off', C.c_longlong), ('res_cols', C.c_longlong),
+        ('dyn_offsets', C.c_void_p), ('out_rows_total', C.c_longlong),
         ('stat_sum', C.c_void_p), ('stat_sqsum', C.c_void_p),
     ]
 
@@ -109,6 +110,10 @@ _SIGNATURES = {
                                                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     'vp3d_bn_act_bwd_apply': (C.c_int, [C.c_int] + [C.c_void_p] * 6 + [C.c_longlong, C.c_longlong, C.c_int, C.c_int,
                                                                       C.POINTER(Dropout)] + [C.c_void_p] * 7),
+    'vp3d_stream_advance': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                      C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'vp3d_ring_write': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int,
+                                  C.c_void_p]),
     'vp3d_adam_step': (C.c_int, [C.POINTER(AdamArgs), C.c_void_p]),
     'vp3d_counter_add': (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_void_p]),
     'vp3d_grad_scale': (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),

@@ -227,7 +227,7 @@ def bn_fold(bn, c_pad):
 def conv_block(dt, a, a_view, w, taps, tap_row_step, k_per_tap, rows_out, out, out_view, block_n=256, a_row_off=0,
                scale=None, shift=None, relu=False, res=None, res_view=None, out_f32=False, n_valid=None,
                stat_sum=None, stat_sqsum=None, out_round_tf32=False, res_rows=0, res_col_off=0, res_cols=0,
-               w_mn_major=None):
+               w_mn_major=None, dyn_offsets=None, out_rows_total=0):
     """One vp3d_conv_block_fwd launch.
     a_view   = (seqs, rows, kdim, row_stride, seq_stride)    out_view = (row_stride, seq_stride)
     res_view = (row_stride, seq_stride, row_mul, row_off)"""
@@ -257,6 +257,8 @@ def conv_block(dt, a, a_view, w, taps, tap_row_step, k_per_tap, rows_out, out, o
         args.res = res.data_ptr()
         args.res_row_stride, args.res_seq_stride, args.res_row_mul, args.res_row_off = res_view
         args.res_rows, args.res_col_off, args.res_cols = res_rows, res_col_off, res_cols
+    if dyn_offsets is not None:       # device int[4] (a view into the streaming offsets table)
+        args.dyn_offsets, args.out_rows_total = dyn_offsets.data_ptr(), out_rows_total
     args.stat_sum = None if stat_sum is None else stat_sum.data_ptr()
     args.stat_sqsum = None if stat_sqsum is None else stat_sqsum.data_ptr()
     with torch.cuda.device(a.device):

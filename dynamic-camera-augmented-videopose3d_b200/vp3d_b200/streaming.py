@@ -5,15 +5,21 @@ The reference has no streaming mode; it re-runs the fully-convolutional model ov
 at t, t-d and t-2d (d = 1, 3, 9, 27, 81), so each layer keeps a ring of its last 2d+1 input frames and one step is ten
 M = S GEMMs (34.7 GFLOP for S = 1024) instead of a 243-frame window per output.
 
-Ring layout: ring[i] is [2*L_i slots][S streams][C] in the operand type with L_i = 2*d_i + 1; frame t lives in slot
-(t mod L_i) AND in slot (t mod L_i) + L_i. With the mirror, the three taps of a step are always the arithmetic row
-progression q-2d, q-d, q of one flat [slot*S + stream] view (q = (t mod L) + L), which is exactly what one
-vp3d_conv_block_fwd launch with taps = 3, tap_row_step = d*S consumes -- no wrap-around case, no gather kernel.
-The mirror copy is a device-to-device memcpy of S*C elements per layer per step.
+Ring layout: ring[i] is [2*L_i slots][S_pad rows][C] in the operand type with L_i = 2*d_i + 1 and S_pad = S rounded up
+to the 128-row GEMM tile; frame t lives in slot (t mod L_i) AND in slot (t mod L_i) + L_i. With the mirror, the three
+taps of a step are always the arithmetic row progression q-2d, q-d, q of one flat [slot*S_pad + stream] view
+(q = (t mod L) + L), which is exactly what one vp3d_conv_block_fwd launch with taps = 3, tap_row_step = d*S_pad
+consumes -- no wrap-around case, no gather kernel; the producing GEMM stores every output box twice (slot and mirror).
+
+The ring positions live on the DEVICE: vp3d_stream_advance ticks a frame counter and rewrites a small offsets table
+that the GEMM launches read (vp3d_conv_args.dyn_offsets), so the ~15 launches of a step never change and are captured
+once as a CUDA graph; a frame then costs one graph launch instead of ~20 Python-issued launches.
 
 Per-frame camera: `step_world()` takes world-space joints plus this frame's camera (quaternion, translation, intrinsics
 with distortion) per stream and projects on the device (vp3d_project_points) before the stack.
 """
+import ctypes as C
+
 import torch
 
 from . import native, ops
@@ -21,96 +27,127 @@ from .temporal import N_TILE, packed_for, resolve_dtype
 
 
 class CausalStream:
-    def __init__(self, model, n_streams, dtype=None):
+    def __init__(self, model, n_streams, dtype=None, use_graph=True):
         assert not model._strided, 'streaming uses the dilated TemporalModel (weights are interchangeable with the 1f model)'
         assert all(s > 0 for s in model.causal_shift[1:]) or len(model.filter_widths) == 1, \
             'streaming needs TemporalModel(causal=True)'
         assert not model.training, 'streaming runs the eval-mode (folded BatchNorm) path'
         self.model = model
         self.S = int(n_streams)
+        self.S_pad = (self.S + 127) // 128 * 128
         self.dt = resolve_dtype(dtype or getattr(model, 'operand_dtype', None))
         if self.dt == native.TF32:
             raise RuntimeError('vp3d_b200 streaming runs fp16 / bf16 operands')
-        self.pk = packed_for(model, self.dt)
-        self.dev = model.expand_conv.weight.device
+        self.pk = pk = packed_for(model, self.dt)
+        self.dev = dev = model.expand_conv.weight.device
         fw = model.filter_widths
-        self.taps = [fw[0]] + [model.layers_conv[2 * i].kernel_size[0] for i in range(len(fw) - 1)]
-        self.dil = [1] + [model.layers_conv[2 * i].dilation[0] for i in range(len(fw) - 1)]
+        nb = len(fw) - 1
+        self.taps = [fw[0]] + [model.layers_conv[2 * i].kernel_size[0] for i in range(nb)]
+        self.dil = [1] + [model.layers_conv[2 * i].dilation[0] for i in range(nb)]
+        self.L = [(self.taps[i] - 1) * self.dil[i] + 1 for i in range(nb + 1)]
         td = ops.torch_dtype(self.dt)
-        widths = [self.pk.c_in_pad] + [self.pk.c_pad] * (len(fw) - 1)
+        widths = [pk.c_in_pad] + [pk.c_pad] * nb
         # ring i holds the INPUT of convolution i (i = 0: packed 2-D keypoints; i >= 1: output of the previous block)
-        self.L = [(self.taps[i] - 1) * self.dil[i] + 1 for i in range(len(fw))]
-        self.rings = [torch.zeros((2 * self.L[i], self.S, widths[i]), dtype=td, device=self.dev) for i in range(len(fw))]
-        self.t = 0
+        self.rings = [torch.zeros((2 * self.L[i], self.S_pad, widths[i]), dtype=td, device=dev) for i in range(nb + 1)]
+        i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=dev)
+        self.ring_len, self.ring_dil, self.ring_taps = i32(self.L), i32(self.dil), i32(self.taps)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.table = torch.zeros((nb + 1, 4), dtype=torch.int32, device=dev)
+        # GEMM launches of one step: (A ring, residual ring, output ring); -1 = a plain buffer
+        desc = [(0, -1, 1 if nb else -1)]
+        for i in range(1, nb + 1):
+            desc += [(i, -1, -1), (-1, i, i + 1 if i < nb else -1)]
+        self.launch_desc = i32(desc)
+        self.launch_table = torch.zeros((len(desc), 4), dtype=torch.int32, device=dev)
+        C_ = pk.c_pad
+        self.x_in = torch.zeros((self.S, pk.c_in), dtype=torch.float32, device=dev)
+        self.y1 = torch.empty((self.S_pad, C_), dtype=td, device=dev)
+        self.h_last = torch.empty((self.S_pad, C_), dtype=td, device=dev)
+        self.y = torch.empty((self.S, pk.n_out), dtype=torch.float32, device=dev)
         # small M: 64-wide column tiles give 4x more CTAs than the 256-wide tile of the batch path
-        self.block_n = 64 if (self.S + 127) // 128 * (self.pk.c_pad // N_TILE) < 148 else N_TILE
+        self.block_n = 64 if (self.S_pad // 128) * (C_ // N_TILE) * 4 <= 148 else N_TILE
+        self.use_graph = use_graph
+        self.graph = None
+        self._warm = 0
 
     def reset(self):
         for r in self.rings:
             r.zero_()
-        self.t = 0
-
+        self.step_dev.zero_()
+        
     def prime(self, x0):
         """Left edge padding of the reference's generator (generators.py:193-195 replicates the first frame over the
         receptive field): feed frame 0 RF-1 times so that the first real step sees that history."""
         for _ in range(self.model.receptive_field() - 1):
             self.step(x0)
 
-    def _slot(self, i):
-        return self.t % self.L[i] + self.L[i]
+    # ------------------------------------------------------------------------------------------------------------
+    def _issue(self):
+        """All launches of one frame, reading self.x_in and writing self.y. Nothing here depends on the frame index on
+        the host: ring positions come from the device table."""
+        pk, S, Sp, dt, dev = self.pk, self.S, self.S_pad, self.dt, self.dev
+        lib = native.lib()
+        nb = len(self.model.filter_widths) - 1
+        C_ = pk.c_pad
+        with torch.cuda.device(dev):
+            native.check(lib.vp3d_stream_advance(self.step_dev.data_ptr(), nb + 1, self.ring_len.data_ptr(),
+                                                 self.ring_dil.data_ptr(), self.ring_taps.data_ptr(), Sp,
+                                                 self.table.data_ptr(), self.launch_table.shape[0],
+                                                 self.launch_desc.data_ptr(), self.launch_table.data_ptr(),
+                                                 ops._stream()), 'stream_advance')
+            native.check(lib.vp3d_ring_write(dt, self.x_in.data_ptr(), self.rings[0].data_ptr(),
+                                             self.table[0].data_ptr(), S, pk.c_in, pk.c_in_pad, ops._stream()),
+                         'ring_write')
+        launch = 0
 
-    def _conv(self, i, w, scale, shift, out, out_rows_view, k_pad, res=None, res_row=0):
-        S, d, taps = self.S, self.dil[i], self.taps[i]
-        ring = self.rings[i]
-        q = self._slot(i)
-        rows = ring.shape[0] * S
-        kw = {}
-        if res is not None:
-            kw = dict(res=res, res_view=(res.shape[-1], 0, 1, res_row))
-        ops.conv_block(self.dt, ring, (1, rows, k_pad, k_pad, rows * k_pad), w, taps, d * S, k_pad, S, out, out_rows_view,
-                       block_n=self.block_n, a_row_off=(q - (taps - 1) * d) * S, scale=scale, shift=shift, relu=True, **kw)
+        def gemm(a, a_rows, k_pad, w, taps, dil, shift, out, out_rows_total, res=None, relu=True):
+            nonlocal launch
+            kw = {}
+            if res is not None:
+                kw = dict(res=res, res_view=(C_, 0, 1, 0))
+            ops.conv_block(dt, a, (1, a_rows, k_pad, k_pad, a_rows * k_pad), w, taps, dil * Sp, k_pad, S, out,
+                           (C_, out_rows_total * C_), block_n=self.block_n, scale=None, shift=shift, relu=relu,
+                           dyn_offsets=self.launch_table[launch], out_rows_total=out_rows_total, **kw)
+            launch += 1
+
+        ring_rows = lambda i: self.rings[i].shape[0] * Sp
+        out0 = self.rings[1] if nb else self.h_last
+        gemm(self.rings[0], ring_rows(0), pk.c_in_pad, pk.w_expand, self.taps[0], self.dil[0], pk.bn_expand[1], out0,
+             ring_rows(1) if nb else Sp)
+        for i in range(1, nb + 1):
+            gemm(self.rings[i], ring_rows(i), C_, pk.w_layers[2 * (i - 1)], self.taps[i], self.dil[i],
+                 pk.bn_layers[2 * (i - 1)][1], self.y1, Sp)
+            last = i == nb
+            out = self.h_last if last else self.rings[i + 1]
+            gemm(self.y1, Sp, C_, pk.w_layers[2 * (i - 1) + 1], 1, 0, pk.bn_layers[2 * (i - 1) + 1][1], out,
+                 Sp if last else ring_rows(i + 1), res=self.rings[i])
+        ops.conv_block(dt, self.h_last, (1, Sp, C_, C_, Sp * C_), pk.w_shrink, 1, 0, C_, S, self.y,
+                       (pk.n_out, S * pk.n_out), block_n=64, scale=None, shift=pk.shrink_shift, relu=False, out_f32=True,
+                       n_valid=pk.n_out)
 
     def step(self, x_t):
-        """x_t: (S, J, F) fp32 CUDA, the frame every stream has just received -> (S, J_out, 3) fp32."""
+        """x_t: (S, J, F) fp32 CUDA, the frame every stream has just received -> (S, J_out, 3) fp32 (a fresh tensor)."""
         ops.require_cuda(x_t)
-        m, pk, S, dt = self.model, self.pk, self.S, self.dt
-        assert x_t.shape[0] == S and x_t.shape[1] * x_t.shape[2] == pk.c_in
-        nb = len(m.filter_widths) - 1
-        # frame t of the input ring (+ mirror)
-        q0 = self._slot(0)
-        xin = ops.pack_rows(dt, x_t.reshape(S, pk.c_in), pk.c_in_pad)
-        self.rings[0][q0].copy_(xin)
-        self.rings[0][q0 - self.L[0]].copy_(xin)
-        td = ops.torch_dtype(dt)
-        C = pk.c_pad
-        h_last = None
-        for i in range(nb + 1):
-            last = i == nb
-            # destination of this stage's output: slot of the next ring, or a plain buffer after the last block
-            if not last:
-                qn = self._slot(i + 1)
-                dst = self.rings[i + 1][qn]
-            else:
-                dst = torch.empty((S, C), dtype=td, device=self.dev)
-            if i == 0:
-                self._conv(0, pk.w_expand, pk.bn_expand[0], pk.bn_expand[1], dst, (C, S * C), pk.c_in_pad)
-            else:
-                y1 = torch.empty((S, C), dtype=td, device=self.dev)
-                bn3, bn1 = pk.bn_layers[2 * (i - 1)], pk.bn_layers[2 * (i - 1) + 1]
-                self._conv(i, pk.w_layers[2 * (i - 1)], bn3[0], bn3[1], y1, (C, S * C), C)
-                # 1x1 convolution + residual = this block's input at frame t (the causal slice keeps the newest frame)
-                qi = self._slot(i)
-                ops.conv_block(dt, y1, (1, S, C, C, S * C), pk.w_layers[2 * (i - 1) + 1], 1, 0, C, S, dst, (C, S * C),
-                               block_n=self.block_n, scale=bn1[0], shift=bn1[1], relu=True, res=self.rings[i],
-                               res_view=(C, 0, 1, qi * S))
-            if not last:
-                self.rings[i + 1][qn - self.L[i + 1]].copy_(dst)
-            h_last = dst
-        y = torch.empty((S, pk.n_out), dtype=torch.float32, device=self.dev)
-        ops.conv_block(dt, h_last, (1, S, C, C, S * C), pk.w_shrink, 1, 0, C, S, y, (pk.n_out, S * pk.n_out), block_n=64,
-                       scale=pk.shrink_scale, shift=pk.shrink_shift, relu=False, out_f32=True, n_valid=pk.n_out)
-        self.t += 1
-        return y.view(S, m.num_joints_out, 3)
+        m, pk, S = self.model, self.pk, self.S
+        assert x_t.shape[0] == S and x_t.numel() == S * pk.c_in
+        self.x_in.copy_(x_t.reshape(S, pk.c_in))
+        if not self.use_graph:
+            self._issue()
+        elif self.graph is None:
+            self._issue()                       # first frames run eagerly (lazy initialisations, attribute setup) ...
+            self._warm += 1
+            if self._warm >= 2:                 # ... then the step is captured once
+                torch.cuda.synchronize(self.dev)
+                g = torch.cuda.CUDAGraph()
+                step_before = self.step_dev.clone()
+                with torch.cuda.graph(g):
+                    self._issue()
+                # capture does not execute: restore nothing, but make sure the counter was not advanced by the capture
+                assert torch.equal(step_before, self.step_dev)
+                self.graph = g
+        else:
+            self.graph.replay()
+        return self.y.view(S, m.num_joints_out, 3).clone()
 
     def step_world(self, X_world, q, t, camera_params):
         """X_world (S, J, 3) world-space joints of this frame, q (S, 4) / t (S, 3) this frame's camera pose per stream,

@@ -91,6 +91,13 @@ typedef struct vp3d_conv_args {
   long long res_col_off;   /* the residual is added to output columns [res_col_off, res_col_off + res_cols) only, */
   long long res_cols;      /* reading residual column (col - res_col_off); res_cols == 0: every column, offset 0  */
 
+  const int* dyn_offsets;  /* optional DEVICE int[4] {a_row_off, res_row_off, out_row_off, out_row_off2 or -1}: when given,
+                              the first two replace the fields above, out rows are shifted by out_row_off and every
+                              16-bit output box is stored a second time at out_row_off2 (mirror slot). `out_rows_total`
+                              must then give the number of rows of the whole output matrix (stores are clipped to it,
+                              not to rows_out). Lets a captured CUDA graph walk ring buffers (vp3d_stream_advance). */
+  long long out_rows_total;
+
   double* stat_sum;        /* optional [n_pad] accumulators (+=) of the raw output and its square over valid rows */
   double* stat_sqsum;      /* (train-mode BatchNorm statistics, fp32 per CTA, double across CTAs) */
 } vp3d_conv_args;
@@ -279,6 +286,21 @@ int vp3d_grad_scale(const float* dy, long long n, float* gscale_buf, void* strea
  * unscaled: the bias gradient of the shrink layer, TemporalModel.py:33), col_sum may be NULL. */
 int vp3d_grad_pack_rows(int dtype, const float* src, void* dst, long long rows, int c, int c_pad,
                         const float* gscale_buf, float* col_sum, void* stream);
+
+/* Streaming ring bookkeeping on the device (causal inference, BASELINE configs[3]). Ring i holds the last L_i = (taps_i -
+ * 1) * dil_i + 1 input frames of convolution i twice: frame t lives in slots t mod L_i and t mod L_i + L_i, each slot
+ * `rows_per_slot` rows. vp3d_stream_advance increments *step and writes, for every ring, table[i] = {a_row_off of tap 0
+ * for this frame, row of the current frame (residual / write position, upper copy), the same row again as out_row_off,
+ * row of the mirror copy}, all in rows. A GEMM launch usually reads one ring and writes another, so the same kernel
+ * also composes launch_table[l] = {table[a_ring][0], table[res_ring][1], table[out_ring][2], table[out_ring][3]} from
+ * launch_desc[l] = {a_ring, res_ring, out_ring} (-1 = none -> 0, 0, 0, -1): the int[4] blocks that
+ * vp3d_conv_args.dyn_offsets points at.
+ * vp3d_ring_write casts the new fp32 input rows [rows][c] into both copies of ring 0's current slot. */
+int vp3d_stream_advance(long long* step, int n_rings, const int* ring_len, const int* ring_dil, const int* ring_taps,
+                        int rows_per_slot, int* table, int n_launch, const int* launch_desc, int* launch_table,
+                        void* stream);
+int vp3d_ring_write(int dtype, const float* src, void* ring, const int* table_entry, long long rows, int c, int c_pad,
+                    void* stream);
 
 /* Fused optimiser step for one convolution weight: torch.optim.Adam(amsgrad) as run.py:662 uses it, in
  * the arithmetic of torch's capturable implementation, plus the re-pack of the updated fp32 weight (c_out, c_in, taps)
