@@ -24,3 +24,20 @@ with open(out, 'w', newline='') as f:
     for r in data:
         w.writerow([r[c][:90] for c in cols])
 print(open(out).read())
+
+# optional third argument: JSON file to merge "<key>": average DRAM bytes per launch over the kernels matching a regex
+if len(sys.argv) >= 6:
+    import json, os, re
+    out_json, key, pattern = sys.argv[3], sys.argv[4], sys.argv[5]
+    ki, ri, wi = H.index('Kernel Name'), H.index('dram__bytes_read.sum'), H.index('dram__bytes_write.sum')
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    tot, n = 0.0, 0
+    for r in data:
+        if re.search(pattern, r[ki]):
+            tot += float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]]
+            n += 1
+    d = json.load(open(out_json)) if os.path.exists(out_json) else {}
+    d[key] = tot / max(n, 1)
+    d[key + '__launches'] = n
+    json.dump(d, open(out_json, 'w'), indent=1)
+    print(key, d[key], 'bytes per launch over', n, 'launches')
