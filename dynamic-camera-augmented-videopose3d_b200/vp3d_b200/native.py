@@ -7,7 +7,7 @@ import os
 import threading
 
 _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG_DIR, 'lib', 'libvp3d_b200.so')
+LIB_PATH = os.environ.get('VP3D_LIB_PATH') or os.path.join(_PKG_DIR, 'lib', 'libvp3d_b200.so')   # override: A/B builds
 
 F16, BF16, TF32 = 0, 1, 2
 DTYPE_NAMES = {'fp16': F16, 'float16': F16, 'half': F16, 'bf16': BF16, 'bfloat16': BF16, 'tf32': TF32}
