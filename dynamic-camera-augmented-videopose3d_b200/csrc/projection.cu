@@ -201,7 +201,40 @@ __device__ __forceinline__ float2 project_regs(const float3 X, const float (&cam
   return o;
 }
 
-template <typename IndexT>
+// ---- contracted-arithmetic variants (mode bit VP3D_PT_FAST): the same formulas written for the compiler to fuse into
+// FMAs, one reciprocal for both ratios. Results differ from the un-contracted path in the last bits (<= 1e-6 relative,
+// inside the 1e-5 budget of BASELINE.json); special values behave the same (x/0 -> +-inf -> clamp, 0/0 -> NaN). The
+// un-contracted path executes 158 instructions per point and is issue bound at 58 % of HBM peak (ncu: 67 % issue
+// active, 30 % DRAM); this one is what the fused world_to_image / feeder / streaming entry points use by default.
+__device__ __forceinline__ float3 qrot_fast(const Quat q, const float3 v) {
+  const float ux = q.y * v.z - q.z * v.y, uy = q.z * v.x - q.x * v.z, uz = q.x * v.y - q.y * v.x;
+  const float wx = q.y * uz - q.z * uy, wy = q.z * ux - q.x * uz, wz = q.x * uy - q.y * ux;
+  return make_float3(fmaf(2.f, fmaf(q.w, ux, wx), v.x), fmaf(2.f, fmaf(q.w, uy, wy), v.y),
+                     fmaf(2.f, fmaf(q.w, uz, wz), v.z));
+}
+__device__ __forceinline__ float3 transform_fast(const PointOps& o, const CamRegs& r, float3 X) {
+  if (o.mode & 7) {
+    if (o.mode & 1) {
+      X = qrot_fast(r.q, make_float3(X.x - r.t.x, X.y - r.t.y, X.z - r.t.z));
+    } else if (o.mode & 2) {
+      X = qrot_fast(r.q, X);
+      X = make_float3(X.x + r.t.x, X.y + r.t.y, X.z + r.t.z);
+    } else {
+      X = qrot_fast(r.q, X);
+    }
+  }
+  return X;
+}
+__device__ __forceinline__ float2 project_fast(const float3 X, const float (&cam)[9], int linear) {
+  const float iz = 1.f / X.z;   // IEEE reciprocal (no -use_fast_math): 0 -> inf, so x * iz keeps the reference's edge cases
+  const float xx = clamp_unit(X.x * iz), yy = clamp_unit(X.y * iz);
+  if (linear) return make_float2(fmaf(cam[0], xx, cam[2]), fmaf(cam[1], yy, cam[3]));
+  const float r2 = fmaf(xx, xx, yy * yy);
+  const float s = 1.f + r2 * fmaf(r2, fmaf(r2, cam[6], cam[5]), cam[4]) + fmaf(cam[7], xx, cam[8] * yy);
+  return make_float2(fmaf(cam[0], fmaf(xx, s, cam[7] * r2), cam[2]), fmaf(cam[1], fmaf(yy, s, cam[8] * r2), cam[3]));
+}
+
+template <typename IndexT, bool FAST>
 __global__ void __launch_bounds__(256, 4)
 project_points_kernel(const float* __restrict__ X, float* __restrict__ out3, float* __restrict__ out2, long long n_pts,
                       PointOps o, int vec_ok) {
@@ -219,8 +252,8 @@ project_points_kernel(const float* __restrict__ X, float* __restrict__ out3, flo
     if (has_proj) load_intrinsics(o, (long long)cc.idx, r);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      P[i] = transform_regs(o, r, P[i]);
-      if (has_proj) Q[i] = project_regs(P[i], r.cam, o.mode & 32);
+      P[i] = FAST ? transform_fast(o, r, P[i]) : transform_regs(o, r, P[i]);
+      if (has_proj) Q[i] = FAST ? project_fast(P[i], r.cam, o.mode & 32) : project_regs(P[i], r.cam, o.mode & 32);
       if (i < 3) {
         if (has_pose && qc.next()) load_pose(o, (long long)qc.idx, r);
         if (has_proj && cc.next()) load_intrinsics(o, (long long)cc.idx, r);
@@ -241,14 +274,25 @@ project_points_kernel(const float* __restrict__ X, float* __restrict__ out3, flo
   // scalar tail (and the whole range when the buffers are not 16-byte aligned)
   for (long long idx = 4 * n_quads + (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n_pts; idx += stride) {
     float3 P = {X[3 * idx], X[3 * idx + 1], X[3 * idx + 2]};
-    P = transform_point(o, idx, P);
+    float2 Q = make_float2(0.f, 0.f);
+    if (FAST) {   // same arithmetic as the vector path, so both agree bit for bit
+      CamRegs r;
+      if (has_pose) load_pose(o, idx / o.pts_per_q, r);
+      P = transform_fast(o, r, P);
+      if (out2 != nullptr) {
+        load_intrinsics(o, idx / o.pts_per_cam, r);
+        Q = project_fast(P, r.cam, o.mode & 32);
+      }
+    } else {
+      P = transform_point(o, idx, P);
+      if (out2 != nullptr) Q = project_dev(P, o.cam + 9 * (idx / o.pts_per_cam), o.mode & 32);
+    }
     if (out3 != nullptr) {
       out3[3 * idx] = P.x;
       out3[3 * idx + 1] = P.y;
       out3[3 * idx + 2] = P.z;
     }
     if (out2 != nullptr) {
-      const float2 Q = project_dev(P, o.cam + 9 * (idx / o.pts_per_cam), o.mode & 32);
       out2[2 * idx] = Q.x;
       out2[2 * idx + 1] = Q.y;
     }
@@ -428,10 +472,13 @@ cudaError_t launch_project_points(const float* X, float* out3, float* out2, long
   const long long cap = (long long)sm_count * 8;  // 8 resident CTAs of 256 threads per SM, grid-stride beyond
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  if (n_pts < (1LL << 31))
-    project_points_kernel<unsigned int><<<(unsigned)blocks, 256, 0, stream>>>(X, out3, out2, n_pts, o, vec_ok);
-  else
-    project_points_kernel<long long><<<(unsigned)blocks, 256, 0, stream>>>(X, out3, out2, n_pts, o, vec_ok);
+  const bool fast = (mode & 64) != 0;   // VP3D_PT_FAST
+  if (n_pts < (1LL << 31)) {
+    if (fast) project_points_kernel<unsigned int, true><<<(unsigned)blocks, 256, 0, stream>>>(X, out3, out2, n_pts, o, vec_ok);
+    else project_points_kernel<unsigned int, false><<<(unsigned)blocks, 256, 0, stream>>>(X, out3, out2, n_pts, o, vec_ok);
+  } else {
+    project_points_kernel<long long, false><<<(unsigned)blocks, 256, 0, stream>>>(X, out3, out2, n_pts, o, vec_ok);
+  }
   return cudaGetLastError();
 }
 

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get('VP3D_LIB_PATH') or os.path.join(_PKG_DIR, 'lib', 'lib
 F16, BF16, TF32 = 0, 1, 2
 DTYPE_NAMES = {'fp16': F16, 'float16': F16, 'half': F16, 'bf16': BF16, 'bfloat16': BF16, 'tf32': TF32}
 
-PT_WORLD_TO_CAMERA, PT_CAMERA_TO_WORLD, PT_ROTATE, PT_CONJ, PT_PROJECT, PT_LINEAR = 1, 2, 4, 8, 16, 32
+PT_WORLD_TO_CAMERA, PT_CAMERA_TO_WORLD, PT_ROTATE, PT_CONJ, PT_PROJECT, PT_LINEAR, PT_FAST = 1, 2, 4, 8, 16, 32, 64
 
 
 class ConvArgs(C.Structure):

@@ -153,6 +153,6 @@ class CausalStream:
         """X_world (S, J, 3) world-space joints of this frame, q (S, 4) / t (S, 3) this frame's camera pose per stream,
         camera_params (S, 9) intrinsics incl. distortion -> (S, J_out, 3). world -> camera -> image on the device."""
         J = X_world.shape[1]
-        mode = native.PT_WORLD_TO_CAMERA | native.PT_PROJECT
+        mode = native.PT_WORLD_TO_CAMERA | native.PT_PROJECT | native.PT_FAST
         _, x2d = ops.project_points(X_world, q=q, t=t, cam=camera_params, pts_per_q=J, pts_per_cam=J, mode=mode, want2=True)
         return self.step(x2d)

@@ -143,7 +143,10 @@ enum {
   VP3D_PT_ROTATE = 4,
   VP3D_PT_CONJ = 8,
   VP3D_PT_PROJECT = 16,
-  VP3D_PT_LINEAR = 32
+  VP3D_PT_LINEAR = 32,
+  VP3D_PT_FAST = 64   /* contracted (FMA) arithmetic and one reciprocal per point instead of the reference's operation
+                         by operation evaluation: <= 1e-6 relative difference, ~2x fewer instructions (the default of
+                         the fused world_to_image / streaming paths; the drop-in functions stay un-contracted) */
 };
 int vp3d_project_points(const float* x, float* out3, float* out2, long long n_pts, const float* q, const float* t,
                         const float* cam, long long pts_per_q, long long pts_per_cam, int mode, void* stream);

@@ -52,7 +52,8 @@ def test_projection_against_golden_including_edge_cases():
 
 
 @pytest.mark.parametrize('per_frame_intrinsics', [False, True])
-def test_fused_dynamic_camera_projection(per_frame_intrinsics):
+@pytest.mark.parametrize('exact', [True, False])
+def test_fused_dynamic_camera_projection(per_frame_intrinsics, exact):
     rng = np.random.default_rng(4)
     S, T, J = 5, 243, 17
     X = (rng.standard_normal((S, T, J, 3)) * 0.4 + np.array([0, 0, 4.0])).astype(np.float32)
@@ -72,12 +73,14 @@ def test_fused_dynamic_camera_projection(per_frame_intrinsics):
         p_ref = ocam.project_to_2d(Xc_ref, cams.reshape(S * T, 9)).reshape(S, T, J, 2)
     else:
         p_ref = ocam.project_to_2d(Xc_ref.reshape(S, T, J, 3), cams)
-    x3, x2 = cam.world_to_image(*(torch.from_numpy(v).cuda() for v in (X, q, t, cams)))
+    # exact: operation by operation like the reference; default: fused multiply-adds (VP3D_PT_FAST), same 1e-5 budget
+    x3, x2 = cam.world_to_image(*(torch.from_numpy(v).cuda() for v in (X, q, t, cams)), exact=exact)
     np.testing.assert_allclose(x3.cpu().numpy().reshape(S * T, J, 3), Xc_ref, atol=PROJ_TOL)
     np.testing.assert_allclose(x2.cpu().numpy(), p_ref, atol=PROJ_TOL)
     # odd point counts / unaligned views take the scalar path and must agree bit for bit
     x3b, x2b = cam.world_to_image(*(torch.from_numpy(v).cuda() for v in (X[:, :3, :], q[:, :3], t[:, :3],
-                                                                          cams[:, :3] if per_frame_intrinsics else cams)))
+                                                                          cams[:, :3] if per_frame_intrinsics else cams)),
+                                  exact=exact)
     assert torch.equal(x2b, x2[:, :3]) and torch.equal(x3b, x3[:, :3])
 
 
