@@ -31,6 +31,8 @@ cudaError_t launch_mpjpe_nd_bwd(const float* pred, const float* tgt, const float
                                 float* grad_pred, int sm_count, cudaStream_t stream);
 cudaError_t launch_n_mpjpe_fwd(const float* pred, const float* tgt, long long n_poses, int J, double* partial,
                                float* out, int sm_count, cudaStream_t stream);
+cudaError_t launch_n_mpjpe_bwd(const float* pred, const float* tgt, const float* grad_out, long long n_poses, int J,
+                               float* grad_pred, int sm_count, cudaStream_t stream);
 cudaError_t launch_pack_rows(int dtype, const float* src, void* dst, long long rows, int c, int c_pad, int sm_count,
                              cudaStream_t stream);
 cudaError_t launch_pack_weight(int dtype, const float* w, void* dst, int c_out, int c_in, int taps, int rows_pad,
@@ -451,6 +453,17 @@ int vp3d_n_mpjpe_fwd(const float* pred, const float* target, long long n_poses, 
   cudaError_t e = vp3d::launch_n_mpjpe_fwd(pred, target, n_poses, J, static_cast<double*>(workspace), out, dev->sm_count,
                                            static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "n_mpjpe_fwd launch");
+  return VP3D_OK;
+}
+
+int vp3d_n_mpjpe_bwd(const float* pred, const float* target, const float* grad_out, long long n_poses, int J,
+                     float* grad_pred, void* stream) {
+  if (!pred || !target || !grad_out || !grad_pred || n_poses <= 0 || J <= 0) return fail(VP3D_ERR_INVALID, "n_mpjpe_bwd args");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_n_mpjpe_bwd(pred, target, grad_out, n_poses, J, grad_pred, dev->sm_count,
+                                           static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "n_mpjpe_bwd launch");
   return VP3D_OK;
 }
 

@@ -191,6 +191,54 @@ mpjpe_nd_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tg
   }
 }
 
+// Backward of n_mpjpe wrt the prediction (autograd of loss.py:77-80): with A = mean_j |P_j|^2, B = mean_j <T_j, P_j>,
+// s = B / A, e_j = s P_j - T_j, u_j = e_j / |e_j| and w = sum_j <u_j, P_j>:
+//   dL/dP_k = g / count * ( s u_k + w (T_k - 2 s P_k) / (J A) )
+// One warp per (n, t) pose, lanes stride over the joints.
+__global__ void __launch_bounds__(kLossThreads)
+n_mpjpe_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, const float* __restrict__ grad_out,
+                   float inv_count, long long n_poses, int J, float* __restrict__ grad_pred) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const float g0 = __ldg(grad_out) * inv_count;
+  for (long long pose = warp_global; pose < n_poses; pose += n_warps) {
+    const float* p = pred + pose * J * 3;
+    const float* t = tgt + pose * J * 3;
+    float* o = grad_pred + pose * J * 3;
+    float pp = 0.f, tp = 0.f;
+    for (int j = lane; j < J; j += 32) {
+      pp += p[3 * j] * p[3 * j] + p[3 * j + 1] * p[3 * j + 1] + p[3 * j + 2] * p[3 * j + 2];
+      tp += t[3 * j] * p[3 * j] + t[3 * j + 1] * p[3 * j + 1] + t[3 * j + 2] * p[3 * j + 2];
+    }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) {
+      pp += __shfl_xor_sync(0xffffffffu, pp, k);
+      tp += __shfl_xor_sync(0xffffffffu, tp, k);
+    }
+    const float A = pp / (float)J;
+    const float s = (tp / (float)J) / A;
+    float w = 0.f;
+    for (int j = lane; j < J; j += 32) {
+      const float ex = s * p[3 * j] - t[3 * j], ey = s * p[3 * j + 1] - t[3 * j + 1], ez = s * p[3 * j + 2] - t[3 * j + 2];
+      const float nrm = sqrtf(ex * ex + ey * ey + ez * ez);
+      if (nrm > 0.f) w += (ex * p[3 * j] + ey * p[3 * j + 1] + ez * p[3 * j + 2]) / nrm;
+    }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) w += __shfl_xor_sync(0xffffffffu, w, k);
+    const float c = w / ((float)J * A);
+    for (int j = lane; j < J; j += 32) {
+      const float px = p[3 * j], py = p[3 * j + 1], pz = p[3 * j + 2];
+      const float ex = s * px - t[3 * j], ey = s * py - t[3 * j + 1], ez = s * pz - t[3 * j + 2];
+      const float nrm = sqrtf(ex * ex + ey * ey + ez * ez);
+      const float inv = nrm > 0.f ? s / nrm : 0.f;
+      o[3 * j] = g0 * (ex * inv + c * (t[3 * j] - 2.f * s * px));
+      o[3 * j + 1] = g0 * (ey * inv + c * (t[3 * j + 1] - 2.f * s * py));
+      o[3 * j + 2] = g0 * (ez * inv + c * (t[3 * j + 2] - 2.f * s * pz));
+    }
+  }
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int loss_grid(long long n_joints, int sm_count) {
@@ -254,6 +302,18 @@ cudaError_t launch_n_mpjpe_fwd(const float* pred, const float* tgt, long long n_
   n_mpjpe_partial_kernel<<<(int)blocks, kLossThreads, 0, stream>>>(pred, tgt, n_poses, J, partial);
   const double cnt = (double)n_poses * (double)J;
   mean_finish_kernel<<<1, kLossThreads, 0, stream>>>(partial, (int)blocks, cnt > 0 ? 1.0 / cnt : 0.0, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_n_mpjpe_bwd(const float* pred, const float* tgt, const float* grad_out, long long n_poses, int J,
+                               float* grad_pred, int sm_count, cudaStream_t stream) {
+  long long blocks = (n_poses * 32 + kLossThreads - 1) / kLossThreads;
+  const long long cap = (long long)sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  const double cnt = (double)n_poses * (double)J;
+  n_mpjpe_bwd_kernel<<<(int)blocks, kLossThreads, 0, stream>>>(pred, tgt, grad_out, (float)(1.0 / cnt), n_poses, J,
+                                                               grad_pred);
   return cudaGetLastError();
 }
 

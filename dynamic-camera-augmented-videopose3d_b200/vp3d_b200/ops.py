@@ -162,18 +162,38 @@ def mpjpe(pred, tgt, w=None):
     return _MpjpeFn.apply(pred, tgt, w)
 
 
+class _NMpjpeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, tgt):
+        p, g = f32c(pred), f32c(tgt)
+        J = p.shape[2]
+        n_poses = p.shape[0] * p.shape[1]
+        out = torch.empty((), dtype=torch.float32, device=p.device)
+        with torch.cuda.device(p.device):
+            check(lib().vp3d_n_mpjpe_fwd(_ptr(p), _ptr(g), n_poses, J, _ptr(_loss_workspace(p.device)), _ptr(out),
+                                         _stream()), 'n_mpjpe_fwd')
+        ctx.save_for_backward(p, g)
+        ctx.meta = (n_poses, J, pred.shape, pred.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        p, g = ctx.saved_tensors
+        n_poses, J, shape, dtype = ctx.meta
+        if ctx.needs_input_grad[1]:
+            raise RuntimeError('vp3d_b200 n_mpjpe: gradient wrt the target is not implemented')
+        gp = torch.empty_like(p)
+        with torch.cuda.device(p.device):
+            check(lib().vp3d_n_mpjpe_bwd(_ptr(p), _ptr(g), _ptr(f32c(grad_out).reshape(1)), n_poses, J, _ptr(gp),
+                                         _stream()), 'n_mpjpe_bwd')
+        return gp.reshape(shape).to(dtype), None
+
+
 def n_mpjpe(pred, tgt):
     require_cuda(pred, tgt)
     assert pred.shape == tgt.shape  # loss.py:75
     assert pred.dim() == 4 and pred.shape[-1] == 3, 'n_mpjpe expects (N, T, J, 3) (loss.py:77 reduces dims 3 and 2)'
-    p, g = f32c(pred), f32c(tgt)
-    J = p.shape[2]
-    n_poses = p.shape[0] * p.shape[1]
-    out = torch.empty((), dtype=torch.float32, device=p.device)
-    with torch.cuda.device(p.device):
-        check(lib().vp3d_n_mpjpe_fwd(_ptr(p), _ptr(g), n_poses, J, _ptr(_loss_workspace(p.device)), _ptr(out),
-                                     _stream()), 'n_mpjpe_fwd')
-    return out
+    return _NMpjpeFn.apply(pred, tgt)
 
 
 # ------------------------------------------------------------------------------------------------ K1 plumbing

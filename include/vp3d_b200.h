@@ -198,6 +198,9 @@ int vp3d_mpjpe_nd_bwd(const float* pred, const float* target, const float* grad_
                       long long w_stride_j, float* grad_pred, void* stream);
 int vp3d_n_mpjpe_fwd(const float* pred, const float* target, long long n_poses, int J, void* workspace, float* out,
                      void* stream);
+/* grad_pred = grad_out * d n_mpjpe / d pred (the scale factor is differentiated too, as autograd does for loss.py:77-80). */
+int vp3d_n_mpjpe_bwd(const float* pred, const float* target, const float* grad_out, long long n_poses, int J,
+                     float* grad_pred, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Training path (TemporalModel.py:126-138 / :188-198 in train() mode and their autograd backward, run.py:473-485).

@@ -182,12 +182,12 @@ def _ste_round(v, dtype):
     return v + (v.to(dtype).to(torch.float32) - v).detach()
 
 
-def forward_lowp_train(sd, x, filter_widths, causal=False, strided=True, dtype=torch.float16, masks=None):
+def forward_lowp_train(sd, x, filter_widths, causal=False, strided=True, dtype=torch.float16, masks=None, dense=False):
     """Train-mode forward with the rounding points of the CUDA training path emulated on the CPU (see
     train_step_grads_lowp). Returns (prediction with grad_fn, dict of leaf parameters)."""
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
               if v.dtype.is_floating_point and 'running_' not in k}
-    plan = make_plan(filter_widths, causal, False, strided)
+    plan = make_plan(filter_widths, causal, dense, strided)
     rnd = lambda v: _ste_round(v, dtype)
     mask_iter = iter(masks) if masks is not None else None
 

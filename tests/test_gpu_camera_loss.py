@@ -150,3 +150,18 @@ def test_mpjpe_on_2d_points_value_and_gradient():
         got.backward()
         assert abs(got.item() - ref.item()) < 1e-6
         np.testing.assert_allclose(pg.grad.cpu().numpy(), pc.grad.numpy(), atol=1e-8, rtol=1e-5)
+
+
+def test_n_mpjpe_gradient_matches_autograd_of_the_reference_formula():
+    """n_mpjpe differentiates through its own scale factor (loss.py:77-80)."""
+    g = torch.Generator().manual_seed(6)
+    for J in (17, 31, 40):
+        pred = torch.randn(5, 4, J, 3, generator=g)
+        tgt = pred * 0.7 + torch.randn(5, 4, J, 3, generator=g) * 0.2
+        pc = pred.clone().requires_grad_(True)
+        oloss.n_mpjpe(pc, tgt).backward()
+        pg = pred.cuda().requires_grad_(True)
+        val = closs.n_mpjpe(pg, tgt.cuda())
+        val.backward()
+        assert abs(val.item() - oloss.n_mpjpe(pred, tgt).item()) < 1e-6
+        np.testing.assert_allclose(pg.grad.cpu().numpy(), pc.grad.numpy(), atol=2e-8, rtol=2e-4)

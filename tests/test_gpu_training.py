@@ -443,3 +443,37 @@ def test_fused_adam_matches_torch_adam_and_refreshes_packed_operands():
         assert float(sa[idx]['step']) == float(sc[idx]['step']) == 4
         assert (sa[idx]['exp_avg'] - sc[idx]['exp_avg']).abs().max().item() < 1e-6
         assert (sa[idx]['max_exp_avg_sq'] - sc[idx]['max_exp_avg_sq']).abs().max().item() < 1e-9
+
+
+@pytest.mark.parametrize('kw', [dict(causal=True), dict(dense=True)])
+def test_dilated_variants_train_step_against_emulation(kw):
+    """Causal and dense (ablation) TemporalModel in train mode: the residual slice moves (pad + shift) and the dense
+    layers have 7 / 19 taps; gradients against the mask-pinned CPU emulation."""
+    fw = [3, 3, 3]
+    sd = otm.init_state(17, 2, 17, fw, channels=256, dense=kw.get('dense', False), seed=51)
+    g = torch.Generator().manual_seed(52)
+    x = torch.rand(12, 27 + 9, 17, 2, generator=g) * 2 - 1
+    tgt = torch.randn(12, 10, 17, 3, generator=g) * 0.3
+    m = _build(TemporalModel, sd, fw, 256, 'fp16', **kw)
+    pred = m(x.cuda())
+    mpjpe(pred, tgt.cuda()).backward()
+    masks = _gpu_masks(12, 256)
+    if kw.get('dense'):
+        loss_o, pred_o, grads_o, _ = None, None, None, None
+        # the emulation helper builds dilated plans; dense layers are plain multi-tap convolutions of the same stack
+        pe, params = otm.forward_lowp_train(sd, x, fw, strided=False, masks=masks, dense=True)
+    else:
+        pe, params = otm.forward_lowp_train(sd, x, fw, causal=True, strided=False, masks=masks)
+    from oracle import loss as oloss
+    oloss.mpjpe(pe, tgt).backward()
+    assert rel_err(pred.detach(), pe.detach()) < 1.5e-3
+    errs = {k: rel_err(p.grad, params[k].grad) for k, p in m.named_parameters()}
+    assert max(errs.values()) < GRAD_TOL_EMU['fp16'] * 2, errs
+
+
+def test_batchnorm_needs_more_than_one_value_per_channel():
+    """torch raises ValueError('Expected more than 1 value per channel when training'); the 1f model's last block sees
+    one row per sample, so batch size 1 must fail loudly here too."""
+    m = TemporalModelOptimized1f(17, 2, 17, [3, 3, 3], dropout=0.0, channels=64).cuda().train()
+    with pytest.raises(AssertionError, match='more than 1 value per channel'):
+        m(torch.rand(1, 27, 17, 2).cuda())
