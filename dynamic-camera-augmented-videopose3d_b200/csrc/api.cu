@@ -181,6 +181,7 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
     return fail(VP3D_ERR_INVALID, "activation strides must be multiples of 16 bytes");
   if (a->scale != nullptr && a->shift == nullptr) return fail(VP3D_ERR_INVALID, "scale without shift");
   if ((a->stat_sum == nullptr) != (a->stat_sqsum == nullptr)) return fail(VP3D_ERR_INVALID, "stat_sum / stat_sqsum");
+  if (a->stat_sum != nullptr && a->out_f32) return fail(VP3D_ERR_INVALID, "statistics need a 16-bit output (they are taken from the stored values)");
   if (a->dtype == VP3D_TF32 && !a->out_f32) return fail(VP3D_ERR_INVALID, "TF32 activations are fp32: set out_f32");
   if (!a->out_f32 && ((a->out_row_stride * 2) % 16 != 0 || (a->out_seq_stride * 2) % 16 != 0))
     return fail(VP3D_ERR_INVALID, "16-bit output strides must be multiples of 16 bytes");

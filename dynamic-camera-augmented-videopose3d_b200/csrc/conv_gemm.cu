@@ -37,15 +37,10 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? VP3D_K1_STAGES : 2 * VP3D_K1_STAGES;
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-  // TMA-store staging: per epilogue warp a ring of kOutBufs buffers of 32 rows x 64 B. The second half of the region
-  // doubles as the train-mode statistics accumulators (per warp: BN/2 columns x {sum, sum of squares} fp32 = 8 KB for
-  // BN = 256): launches that reduce statistics in the epilogue are the long-K, MMA-bound ones, where one staging buffer
-  // per warp is enough.
+  // TMA-store staging: per epilogue warp a ring of kOutBufs buffers of 32 rows x 64 B
   static constexpr int kOutBufBytes = kEpiWarps * 32 * 64;
   static constexpr int kOutStageBytes = kOutBufs * kOutBufBytes;
   static constexpr int kBarBytes = 256;
-  static constexpr int kStatBytes = 4 * BN * 2 * 4;
-  static_assert(kStatBytes <= kOutBufBytes, "statistics accumulators alias the second staging buffer");
   static constexpr int kAffineBytes = 2 * BN * 4;    // scale / shift of the CTA's current column tile
   static constexpr int kSmemBytes = kStages * kStageBytes + kOutStageBytes + kBarBytes + kAffineBytes;
 };
@@ -142,7 +137,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  float* stat_smem = reinterpret_cast<float*>(out_stage + Cfg::kOutBufBytes);  // aliases staging buffer 1 (see GemmCfg)
   float* affine_smem = reinterpret_cast<float*>(out_stage + Cfg::kOutStageBytes + Cfg::kBarBytes);  // scale | shift
 
   const int warp = threadIdx.x >> 5;
@@ -258,21 +252,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     unsigned out_buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    // per-warp fp32 statistics accumulators in shared memory, flushed (double atomics) when the CTA moves to another
-    // column tile -- with gridDim.x a multiple of n_tiles a CTA keeps one column tile for the whole launch
-    float* stat_warp = stat_smem + epi * (BN / 2) * 2;   // this warp's BN/2 columns x {sum, sum of squares}
+    // Train-mode BatchNorm statistics: lane l owns column (chunk * 32 + l) of this warp's column half and keeps its
+    // fp32 sum / sum of squares in registers across all tiles of the launch; flushed with double atomics when the CTA
+    // moves to another column tile (with gridDim.x a multiple of n_tiles: once, at the end)
+    float st_s[4] = {0.f, 0.f, 0.f, 0.f}, st_q[4] = {0.f, 0.f, 0.f, 0.f};
+    static_assert(kChunks <= 4, "statistics accumulators");
     int stat_n0 = -1;
     auto stat_flush = [&]() {
       if (stat_n0 >= 0) {
-        for (int j = lane; j < BN / 2; j += 32) {
-          atomicAdd(p.stat_sum + stat_n0 * BN + half * (BN / 2) + j, (double)stat_warp[2 * j]);
-          atomicAdd(p.stat_sqsum + stat_n0 * BN + half * (BN / 2) + j, (double)stat_warp[2 * j + 1]);
+#pragma unroll
+        for (int ci = 0; ci < kChunks; ++ci) {
+          const int col = stat_n0 * BN + (half * kChunks + ci) * 32 + lane;
+          atomicAdd(p.stat_sum + col, (double)st_s[ci]);
+          atomicAdd(p.stat_sqsum + col, (double)st_q[ci]);
+          st_s[ci] = st_q[ci] = 0.f;
         }
       }
-      for (int j = lane; j < BN; j += 32) stat_warp[j] = 0.f;
-      __syncwarp();
     };
-    if (p.stat_sum != nullptr) stat_flush();
     int affine_n0 = -1;
     // streaming (CausalStream under a CUDA graph): residual row, output row and mirror output row come from a device
     // table that a small kernel advances once per frame, so the captured launch never changes
@@ -346,30 +342,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
 
-        if (p.stat_sum != nullptr) {
-          // Train-mode BatchNorm statistics of the raw convolution output. Thread = row, so a per-channel sum over
-          // the warp's 32 rows is a transposing butterfly: after the 5 exchange steps lane j holds column j.
-          float s[32], q[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            s[j] = row_ok ? f[j] : 0.f;
-            q[j] = s[j] * s[j];
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const bool up = (lane & o) != 0;
-#pragma unroll
-            for (int i = 0; i < o; ++i) {
-              const float ks = up ? s[i + o] : s[i], ss = up ? s[i] : s[i + o];
-              const float kq = up ? q[i + o] : q[i], sq = up ? q[i] : q[i + o];
-              s[i] = ks + __shfl_xor_sync(0xffffffffu, ss, o);
-              q[i] = kq + __shfl_xor_sync(0xffffffffu, sq, o);
-            }
-          }
-          float* acc_s = stat_warp + ((c - half * kChunks) * 32 + lane) * 2;  // owned by this lane: no smem atomics
-          acc_s[0] += s[0];
-          acc_s[1] += q[0];
-        }
         if (p.scale != nullptr) {
           const float4* sc4 = reinterpret_cast<const float4*>(affine_smem + c * 32);
           const float4* sh4 = reinterpret_cast<const float4*>(affine_smem + BN + c * 32);
@@ -447,13 +419,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // memory in the SWIZZLE_64B layout (conflict-free 16-byte stores) and leave as ONE coalesced TMA store;
           // TMA clips rows past the end of the sequence, so no row mask is needed here
           constexpr int D16 = (DT == VP3D_TF32) ? VP3D_F16 : DT;
-          // ring of 2 staging buffers (1 when the second one holds the statistics accumulators)
-          const unsigned b = p.stat_sum != nullptr ? 0u : (out_buf++ & 1u);
+          const unsigned b = out_buf++ & 1u;   // ring of 2 staging buffers
           uint8_t* my_stage = out_stage + b * Cfg::kOutBufBytes + epi * (32 * 64);
-          if (lane == 0) {  // the store that last used this buffer has drained it
-            if (p.stat_sum != nullptr) tma_store_wait_read<0>();
-            else tma_store_wait_read<1>();
-          }
+          if (lane == 0) tma_store_wait_read<1>();  // the store that last used this buffer has drained it
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -465,6 +433,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           fence_proxy_async_smem();
           __syncwarp();
+          if (p.stat_sum != nullptr) {
+            // Per-channel sum / sum of squares of the values as stored (16-bit): the tile is in shared memory now,
+            // so lane l walks column l down the warp's rows -- 32 lanes read one 64-byte row per step, conflict free.
+            // (The first version reduced the fp32 accumulators with a 62-shuffle transposing butterfly per chunk.)
+            int valid = p.rows_out - (tc.t0 + quad * 32);
+            valid = valid < 0 ? 0 : (valid > 32 ? 32 : valid);
+            float cs = 0.f, cq = 0.f;
+            const uint32_t col_off = (lane & 7) * 2, col_chunk = lane >> 3;
+#pragma unroll 8
+            for (int r = 0; r < valid; ++r) {
+              const uint16_t h = *reinterpret_cast<const uint16_t*>(my_stage + r * 64 + ((col_chunk ^ ((r >> 1) & 3)) << 4) +
+                                                                    col_off);
+              const float v = (D16 == VP3D_F16) ? __half2float(__ushort_as_half(h)) : __uint_as_float((uint32_t)h << 16);
+              cs += v;
+              cq = fmaf(v, v, cq);
+            }
+            const int ci = c - half * kChunks;
+#pragma unroll
+            for (int k = 0; k < kChunks; ++k)
+              if (k == ci) {
+                st_s[k] += cs;
+                st_q[k] += cq;
+              }
+          }
           if (lane == 0) {
             tma_store_3d(&tmC, my_stage, tc.n0 * BN + c * 32, tc.t0 + quad * 32 + out_row_off, tc.seq);
             if (out_row_off2 >= 0)   // mirror slot of a streaming ring
@@ -480,10 +472,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-    if (p.stat_sum != nullptr) {
-      __syncwarp();
-      stat_flush();
-    }
+    if (p.stat_sum != nullptr) stat_flush();
     if (lane == 0) tma_store_wait_all<0>();  // every output tile of this warp has reached global memory
   }
 

@@ -18,7 +18,6 @@ from . import native, ops
 from .temporal import K_ALIGN, N_TILE, LayerPlan, _round_up, _run_layer, resolve_dtype
 
 SHRINK_PAD = 128      # shrink-layer output channels are padded to one 128-row MMA tile for its weight gradient
-STATS_IN_EPILOGUE_MIN_K = 2048
 grad_ready_hook = None   # set by vp3d_b200.ddp: called as hook(parameter, gradient) as soon as a gradient is issued
 grad_finish_hook = None  # ... and once at the end of the backward (waits for the outstanding all-reduces)
 sync_bn_group = None     # process group over which train-mode BatchNorm statistics are summed (None: per replica)
@@ -87,12 +86,9 @@ def _forward_stack(model, x, dt):
         w = _conv_w(dt, conv, c_pad, cin_pad)
         L.w_fwd = w   # [c_out_pad][taps * c_in_pad]; the data-gradient GEMM reads it again as W^T (MN-major operand)
         stats = torch.zeros((2, c_pad), dtype=torch.float64, device=dev)
-        # per-channel sum / sum of squares: in the GEMM epilogue when the contraction is long enough to hide it
-        # (3-tap 1024-channel layers), otherwise one extra read of the stored matrix (mostly L2 hits)
-        fused_stats = plan.taps * cin_pad >= STATS_IN_EPILOGUE_MIN_K
-        z, t_out = _run_layer(dt, a_in, n, t, cin_pad, w, plan, None, None, False, stats=stats if fused_stats else None)
-        if not fused_stats:
-            ops.col_stats(dt, z, stats)
+        # per-channel sum / sum of squares of the stored z come out of the GEMM epilogue (the staged output tile is read
+        # back column-wise from shared memory); vp3d_col_stats remains as a stand-alone entry point
+        z, t_out = _run_layer(dt, a_in, n, t, cin_pad, w, plan, None, None, False, stats=stats)
         L.z, L.t_out = z, t_out
         count = n * t_out
         if sync_bn_group is not None:

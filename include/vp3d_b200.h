@@ -98,8 +98,8 @@ typedef struct vp3d_conv_args {
                               not to rows_out). Lets a captured CUDA graph walk ring buffers (vp3d_stream_advance). */
   long long out_rows_total;
 
-  double* stat_sum;        /* optional [n_pad] accumulators (+=) of the raw output and its square over valid rows */
-  double* stat_sqsum;      /* (train-mode BatchNorm statistics, fp32 per CTA, double across CTAs) */
+  double* stat_sum;        /* optional [n_pad] accumulators (+=) of the output AS STORED (16-bit) and its square over the */
+  double* stat_sqsum;      /* valid rows: train-mode BatchNorm statistics; fp32 per CTA, double across CTAs */
 } vp3d_conv_args;
 
 int vp3d_conv_block_fwd(const vp3d_conv_args* args, void* stream);
