@@ -502,7 +502,9 @@ int vp3d_wgrad(const vp3d_wgrad_args* a, void* stream) {
   }
   vp3d::WgradParams p;
   memset(&p, 0, sizeof(p));
-  p.co_tiles = (int)(a->co_pad / 128);
+  // wide layers: 256 x 256 tiles (fewer bytes per flop, deeper latency cover); narrow ones keep 128-row tiles
+  const int block_m = (a->block_n == 256 && a->co_pad % 256 == 0 && a->dz_seqs * ((a->dz_rows + 63) / 64) >= 32) ? 256 : 128;
+  p.co_tiles = (int)(a->co_pad / block_m);
   p.ci_tiles = (int)(a->ci_pad / a->block_n);
   p.num_tiles = a->taps * p.co_tiles * p.ci_tiles;
   p.seqs = (int)a->dz_seqs;
@@ -533,7 +535,8 @@ int vp3d_wgrad(const vp3d_wgrad_args* a, void* stream) {
   p.out_row_stride = a->ci_pad;
   const long long items = (long long)p.num_tiles * p.num_slices;
   const int grid = (int)(items < dev->sm_count ? items : dev->sm_count);
-  cudaError_t e = vp3d::launch_wgrad(a->dtype, a->block_n, tmA, tmB, p, grid, static_cast<cudaStream_t>(stream));
+  cudaError_t e = vp3d::launch_wgrad(a->dtype, a->block_n, block_m, tmA, tmB, p, grid,
+                                     static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "wgrad launch");
   return VP3D_OK;
 }

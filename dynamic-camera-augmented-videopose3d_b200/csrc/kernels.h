@@ -53,7 +53,7 @@ cudaError_t launch_conv_gemm(int dtype, int block_n, int w_mn_major, const CUten
 // Launch parameters of wgrad_gemm_kernel (see wgrad.cu).
 struct WgradParams {
   int num_tiles;        // taps * co_tiles * ci_tiles
-  int co_tiles;         // co_pad / 128
+  int co_tiles;         // co_pad / BLOCK_M (128 or 256)
   int ci_tiles;         // ci_pad / BLOCK_N
   int seqs;
   int kb_per_seq;       // ceil(rows per sequence / 64)
@@ -65,8 +65,8 @@ struct WgradParams {
   long long out_tap_stride;
   long long out_row_stride;
 };
-cudaError_t launch_wgrad(int dtype, int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const WgradParams& p,
-                         int grid, cudaStream_t stream);
+cudaError_t launch_wgrad(int dtype, int block_n, int block_m, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                         const WgradParams& p, int grid, cudaStream_t stream);
 cudaError_t launch_wgrad_finish(const float* packed, float* dw, int c_out, int c_in, int taps, long long tap_stride,
                                 long long row_stride, const float* gscale_buf, int sm_count, cudaStream_t stream);
 

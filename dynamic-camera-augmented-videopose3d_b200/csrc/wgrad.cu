@@ -25,17 +25,23 @@
 
 namespace vp3d {
 
-constexpr int kWgBlockM = 128;    // output channels per tile
 constexpr int kWgRows = 64;       // frames (reduction depth) per pipeline stage
 constexpr int kWgThreads = 192;
 
-template <int BN>
+// BM = output channels per tile. BM = 256 (two 128-row MMAs sharing the B tile, all 512 TMEM columns as ONE accumulator
+// set) is the wide-layer configuration: both operands of a weight gradient stream from L2 / HBM with no reuse inside a
+// CTA, so the mainloop is latency bound by bytes per flop and bytes in flight -- a 256 x 256 tile moves 64 KB per 1024
+// MMA cycles (128 x 256: 48 KB per 512) and its three stages cover 3072 MMA cycles of latency instead of 2048. The
+// price, no accumulator double buffering, is small here: a CTA runs one or two long items per launch.
+template <int BN, int BM>
 struct WgradCfg {
-  static constexpr int kABytes = kWgBlockM * kWgRows * 2;  // 16 KB: 2 boxes of [64 frames][64 channels]
+  static constexpr int kABytes = BM * kWgRows * 2;         // BM / 64 boxes of [64 frames][64 channels]
   static constexpr int kBBytes = BN * kWgRows * 2;         // BN / 64 boxes
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : 8;
-  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int kStages = (BM == 256) ? 3 : ((BN == 256) ? 4 : 8);
+  static constexpr int kAccBufs = (BM == 256) ? 1 : 2;
+  static constexpr int kAccCols = (BM / 128) * BN;         // TMEM columns of one accumulator set
+  static constexpr int kTmemCols = (kAccBufs * kAccCols < 32) ? 32 : kAccBufs * kAccCols;
   static constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
 };
 
@@ -62,18 +68,19 @@ __device__ __forceinline__ void decode_tile(int tile, const WgradParams& p, int&
   const int rest = tile / p.ci_tiles;
   const int co_t = rest % p.co_tiles;
   tap = rest / p.co_tiles;
-  co0 = co_t * kWgBlockM;
+  co0 = co_t;   // tile index; the kernel multiplies by its BM
   ci0 = ci_t;
 }
 
-template <int DT, int BN>
+template <int DT, int BN, int BM>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const WgradParams p) {
-  using Cfg = WgradCfg<BN>;
+  using Cfg = WgradCfg<BN, BM>;
+  constexpr int kMH = BM / 128;   // 128-row MMAs per tile
   constexpr uint32_t kFormat = (DT == VP3D_BF16) ? 1u : 0u;
   // instruction descriptor: fp32 accumulate, A and B both MN-major (bits 15, 16)
-  constexpr uint32_t kIdesc = make_instr_desc(kFormat, kWgBlockM, BN) | (1u << 15) | (1u << 16);
+  constexpr uint32_t kIdesc = make_instr_desc(kFormat, 128, BN) | (1u << 15) | (1u << 16);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -132,8 +139,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
 #pragma unroll
-          for (int g = 0; g < kWgBlockM / 64; ++g)
-            tma_load_3d(sa + g * (kWgRows * 128), &tmA, &full_bar[stage], co0 + g * 64, r0, seq);
+          for (int g = 0; g < BM / 64; ++g)
+            tma_load_3d(sa + g * (kWgRows * 128), &tmA, &full_bar[stage], co0 * BM + g * 64, r0, seq);
           uint8_t* sb = sa + Cfg::kABytes;
           const int b_col = ci_t * BN + tap * p.b_tap_col_step;
           const int b_row = r0 + p.b_row_off + tap * p.b_tap_row_step;
@@ -161,18 +168,22 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const long long kb_hi = kb_all * (sl + 1) / p.num_slices;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
         for (long long kb = kb_lo; kb < kb_hi; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint64_t adesc = make_mnmajor_sw128_desc(sa, kWgRows * 128);
           const uint64_t bdesc = make_mnmajor_sw128_desc(sa + Cfg::kABytes, kWgRows * 128);
 #pragma unroll
-          for (int k = 0; k < kWgRows / 16; ++k) {
-            // 16 frames of reduction per MMA = two 8-frame groups = 2048 bytes further into every box
-            umma_f16_ss(d_tmem, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), kIdesc,
-                        !(kb == kb_lo && k == 0));
+          for (int h = 0; h < kMH; ++h) {
+            // output channels [128 h, 128 h + 128): two 64-channel boxes further into the A part of the stage
+            const uint64_t adesc = make_mnmajor_sw128_desc(sa + h * 2 * (kWgRows * 128), kWgRows * 128);
+#pragma unroll
+            for (int k = 0; k < kWgRows / 16; ++k) {
+              // 16 frames of reduction per MMA = two 8-frame groups = 2048 bytes further into every box
+              umma_f16_ss(d_tmem + h * BN, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), kIdesc,
+                          !(kb == kb_lo && k == 0));
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) {
@@ -181,8 +192,12 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         umma_commit(&tmem_full_bar[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (Cfg::kAccBufs == 2) {
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        } else {
+          acc_phase ^= 1;
+        }
       }
     }
     __syncwarp();
@@ -197,24 +212,32 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int tile = item - sl * p.num_tiles;
       int tap, co0, ci_t;
       decode_tile(tile, p, tap, co0, ci_t);
-      float* out_row = p.out + (long long)tap * p.out_tap_stride + (long long)(co0 + row) * p.out_row_stride +
-                       (long long)ci_t * BN;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + acc * BN + c * 32 + (static_cast<uint32_t>(quad * 32) << 16), v);
-        tmem_wait_ld();
+      for (int h = 0; h < kMH; ++h) {
+        float* out_row = p.out + (long long)tap * p.out_tap_stride +
+                         (long long)(co0 * BM + h * 128 + row) * p.out_row_stride + (long long)ci_t * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + acc * Cfg::kAccCols + h * BN + c * 32 + (static_cast<uint32_t>(quad * 32) << 16),
+                             v);
+          tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          red_add_v4(out_row + c * 32 + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                     __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          for (int j = 0; j < 8; ++j)
+            red_add_v4(out_row + c * 32 + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
       }
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (Cfg::kAccBufs == 2) {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      } else {
+        acc_phase ^= 1;
+      }
     }
   }
 
@@ -226,29 +249,32 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-template <int DT, int BN>
+template <int DT, int BN, int BM>
 static cudaError_t launch_wg(const CUtensorMap& tmA, const CUtensorMap& tmB, const WgradParams& p, int grid,
                              cudaStream_t stream) {
-  using Cfg = WgradCfg<BN>;
+  using Cfg = WgradCfg<BN, BM>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel<DT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel<DT, BN, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  wgrad_gemm_kernel<DT, BN><<<grid, kWgThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  wgrad_gemm_kernel<DT, BN, BM><<<grid, kWgThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
   return cudaGetLastError();
 }
 
-cudaError_t launch_wgrad(int dtype, int block_n, const CUtensorMap& tmA, const CUtensorMap& tmB, const WgradParams& p,
-                         int grid, cudaStream_t stream) {
-  if (block_n == 256) {
-    if (dtype == VP3D_F16) return launch_wg<VP3D_F16, 256>(tmA, tmB, p, grid, stream);
-    if (dtype == VP3D_BF16) return launch_wg<VP3D_BF16, 256>(tmA, tmB, p, grid, stream);
+cudaError_t launch_wgrad(int dtype, int block_n, int block_m, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                         const WgradParams& p, int grid, cudaStream_t stream) {
+  if (block_n == 256 && block_m == 256) {
+    if (dtype == VP3D_F16) return launch_wg<VP3D_F16, 256, 256>(tmA, tmB, p, grid, stream);
+    if (dtype == VP3D_BF16) return launch_wg<VP3D_BF16, 256, 256>(tmA, tmB, p, grid, stream);
+  } else if (block_n == 256) {
+    if (dtype == VP3D_F16) return launch_wg<VP3D_F16, 256, 128>(tmA, tmB, p, grid, stream);
+    if (dtype == VP3D_BF16) return launch_wg<VP3D_BF16, 256, 128>(tmA, tmB, p, grid, stream);
   } else if (block_n == 64) {
-    if (dtype == VP3D_F16) return launch_wg<VP3D_F16, 64>(tmA, tmB, p, grid, stream);
-    if (dtype == VP3D_BF16) return launch_wg<VP3D_BF16, 64>(tmA, tmB, p, grid, stream);
+    if (dtype == VP3D_F16) return launch_wg<VP3D_F16, 64, 128>(tmA, tmB, p, grid, stream);
+    if (dtype == VP3D_BF16) return launch_wg<VP3D_BF16, 64, 128>(tmA, tmB, p, grid, stream);
   }
   return cudaErrorInvalidValue;
 }
