@@ -60,9 +60,6 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-struct WgUnit {
-  int tap, co0, ci0, seq, r0;
-};
 __device__ __forceinline__ void decode_tile(int tile, const WgradParams& p, int& tap, int& co0, int& ci0) {
   const int ci_t = tile % p.ci_tiles;
   const int rest = tile / p.ci_tiles;

@@ -18,7 +18,6 @@ once as a CUDA graph; a frame then costs one graph launch instead of ~20 Python-
 Per-frame camera: `step_world()` takes world-space joints plus this frame's camera (quaternion, translation, intrinsics
 with distortion) per stream and projects on the device (vp3d_project_points) before the stack.
 """
-import ctypes as C
 
 import torch
 
