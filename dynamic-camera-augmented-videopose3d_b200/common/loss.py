@@ -1,8 +1,9 @@
 """Drop-in for the reference's common/loss.py.
 
-mpjpe / weighted_mpjpe / n_mpjpe run as fused sm_100a reductions (K6) on CUDA tensors and are differentiable where
-the training loop needs it (mpjpe, weighted_mpjpe: run.py:480-485). p_mpjpe and mean_velocity_error are evaluation
-metrics that the reference computes in NumPy on the host (run.py:749-756); they keep NumPy semantics here.
+mpjpe / weighted_mpjpe / n_mpjpe run as fused sm_100a reductions (K6) on CUDA tensors and are differentiable
+(run.py:480-485). p_mpjpe and mean_velocity_error are evaluation metrics that the reference computes in NumPy on the
+host (run.py:749-756): NumPy arrays keep exactly those semantics here, CUDA tensors are reduced on the device
+(vp3d_p_mpjpe_fwd: per-pose 3x3 SVD Procrustes; vp3d_velocity_error) and come back as 0-dim tensors.
 """
 import numpy as np
 import torch
@@ -34,6 +35,8 @@ def p_mpjpe(predicted, target):
     often referred to as "Protocol #2" in many papers.
     """
     assert predicted.shape == target.shape
+    if isinstance(predicted, torch.Tensor):
+        return ops.p_mpjpe(predicted, target)       # CUDA tensors stay on the device (vp3d_p_mpjpe_fwd)
 
     # centre both point sets and bring them to unit Frobenius norm
     tgt_mean = target.mean(axis=1, keepdims=True)
@@ -74,5 +77,7 @@ def mean_velocity_error(predicted, target):
     Mean per-joint velocity error (i.e. mean Euclidean distance of the 1st derivative)
     """
     assert predicted.shape == target.shape
+    if isinstance(predicted, torch.Tensor):
+        return ops.mean_velocity_error(predicted, target)   # CUDA tensors stay on the device (vp3d_velocity_error)
     dv = np.diff(predicted, axis=0) - np.diff(target, axis=0)
     return np.mean(np.linalg.norm(dv, axis=len(target.shape) - 1))

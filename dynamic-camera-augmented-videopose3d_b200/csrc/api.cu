@@ -31,6 +31,10 @@ cudaError_t launch_mpjpe_nd_bwd(const float* pred, const float* tgt, const float
                                 float* grad_pred, int sm_count, cudaStream_t stream);
 cudaError_t launch_n_mpjpe_fwd(const float* pred, const float* tgt, long long n_poses, int J, double* partial,
                                float* out, int sm_count, cudaStream_t stream);
+cudaError_t launch_p_mpjpe_fwd(const float* pred, const float* tgt, long long n_poses, int J, double* partial, float* out,
+                               int sm_count, cudaStream_t stream);
+cudaError_t launch_velocity_error(const float* pred, const float* tgt, long long T, long long inner, int D,
+                                  double* partial, float* out, int sm_count, cudaStream_t stream);
 cudaError_t launch_n_mpjpe_bwd(const float* pred, const float* tgt, const float* grad_out, long long n_poses, int J,
                                float* grad_pred, int sm_count, cudaStream_t stream);
 cudaError_t launch_pack_rows(int dtype, const float* src, void* dst, long long rows, int c, int c_pad, int sm_count,
@@ -454,6 +458,29 @@ int vp3d_n_mpjpe_fwd(const float* pred, const float* target, long long n_poses, 
   cudaError_t e = vp3d::launch_n_mpjpe_fwd(pred, target, n_poses, J, static_cast<double*>(workspace), out, dev->sm_count,
                                            static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "n_mpjpe_fwd launch");
+  return VP3D_OK;
+}
+
+int vp3d_p_mpjpe_fwd(const float* pred, const float* target, long long n_poses, int J, void* workspace, float* out,
+                     void* stream) {
+  if (!pred || !target || !workspace || !out || n_poses <= 0 || J <= 0) return fail(VP3D_ERR_INVALID, "p_mpjpe_fwd args");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_p_mpjpe_fwd(pred, target, n_poses, J, static_cast<double*>(workspace), out, dev->sm_count,
+                                           static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "p_mpjpe_fwd launch");
+  return VP3D_OK;
+}
+
+int vp3d_velocity_error(const float* pred, const float* target, long long T, long long inner, int dim, void* workspace,
+                        float* out, void* stream) {
+  if (!pred || !target || !workspace || !out || T < 2 || inner <= 0 || dim <= 0)
+    return fail(VP3D_ERR_INVALID, "velocity_error args (needs at least two frames)");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_velocity_error(pred, target, T, inner, dim, static_cast<double*>(workspace), out,
+                                              dev->sm_count, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "velocity_error launch");
   return VP3D_OK;
 }
 

@@ -239,6 +239,159 @@ n_mpjpe_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tgt
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Evaluation metrics on the device: p_mpjpe (loss.py:29-68, Procrustes-aligned MPJPE) and
+// mean_velocity_error (loss.py:82-91). The reference computes both in NumPy on the host after a D2H copy per sequence
+// (run.py:749-756). One thread per pose: centroids, norms, the 3x3 cross-covariance H = X0^T Y0, its SVD (cyclic Jacobi
+// on H^T H in double, U recovered as H v / s), the reflection fix on the last singular vector, then the aligned error.
+__device__ void jacobi_eig3(double A[3][3], double V[3][3], double w[3]) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) V[i][j] = i == j ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+    if (off < 1e-30) break;
+    for (int pq = 0; pq < 3; ++pq) {
+      const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+      if (fabs(A[p][q]) < 1e-300) continue;
+      const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+      const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+      const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+      for (int k = 0; k < 3; ++k) {   // A <- A J
+        const double akp = A[k][p], akq = A[k][q];
+        A[k][p] = c * akp - sn * akq;
+        A[k][q] = sn * akp + c * akq;
+      }
+      for (int k = 0; k < 3; ++k) {   // A <- J^T A
+        const double apk = A[p][k], aqk = A[q][k];
+        A[p][k] = c * apk - sn * aqk;
+        A[q][k] = sn * apk + c * aqk;
+      }
+      for (int k = 0; k < 3; ++k) {
+        const double vkp = V[k][p], vkq = V[k][q];
+        V[k][p] = c * vkp - sn * vkq;
+        V[k][q] = sn * vkp + c * vkq;
+      }
+    }
+  }
+  for (int i = 0; i < 3; ++i) w[i] = A[i][i];
+}
+
+__global__ void __launch_bounds__(kLossThreads)
+p_mpjpe_partial_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, long long n_poses, int J,
+                       double* __restrict__ partial) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  double acc = 0.0;
+  for (long long pose = (long long)blockIdx.x * blockDim.x + threadIdx.x; pose < n_poses; pose += stride) {
+    const float* Y = pred + pose * J * 3;   // "Y" = predicted, "X" = target, as in the reference
+    const float* X = tgt + pose * J * 3;
+    double muX[3] = {0, 0, 0}, muY[3] = {0, 0, 0};
+    for (int j = 0; j < J; ++j)
+      for (int d = 0; d < 3; ++d) {
+        muX[d] += X[3 * j + d];
+        muY[d] += Y[3 * j + d];
+      }
+    for (int d = 0; d < 3; ++d) {
+      muX[d] /= J;
+      muY[d] /= J;
+    }
+    double nX = 0, nY = 0, H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int j = 0; j < J; ++j) {
+      double x[3], y[3];
+      for (int d = 0; d < 3; ++d) {
+        x[d] = X[3 * j + d] - muX[d];
+        y[d] = Y[3 * j + d] - muY[d];
+        nX += x[d] * x[d];
+        nY += y[d] * y[d];
+      }
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) H[a][b] += x[a] * y[b];
+    }
+    nX = sqrt(nX);
+    nY = sqrt(nY);
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) H[a][b] /= nX * nY;   // H of the normalised point sets
+    // SVD H = U diag(s) V^T
+    double A[3][3], V[3][3], w[3];
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) A[a][b] = H[0][a] * H[0][b] + H[1][a] * H[1][b] + H[2][a] * H[2][b];
+    jacobi_eig3(A, V, w);
+    int ord[3] = {0, 1, 2};   // descending singular values
+    for (int i = 0; i < 2; ++i)
+      for (int k = i + 1; k < 3; ++k)
+        if (w[ord[k]] > w[ord[i]]) {
+          const int tmp = ord[i];
+          ord[i] = ord[k];
+          ord[k] = tmp;
+        }
+    double sv[3], Vs[3][3], U[3][3];
+    for (int i = 0; i < 3; ++i) {
+      sv[i] = sqrt(w[ord[i]] > 0 ? w[ord[i]] : 0.0);
+      for (int k = 0; k < 3; ++k) Vs[k][i] = V[k][ord[i]];
+    }
+    for (int i = 0; i < 3; ++i) {
+      double u[3];
+      for (int a = 0; a < 3; ++a) u[a] = H[a][0] * Vs[0][i] + H[a][1] * Vs[1][i] + H[a][2] * Vs[2][i];
+      const double n = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+      if (i < 2 || n > 1e-12 * (sv[0] + 1e-300)) {
+        for (int a = 0; a < 3; ++a) U[a][i] = n > 0 ? u[a] / n : (a == i ? 1.0 : 0.0);
+      } else {   // rank-deficient H: complete the basis (the sign is settled by the reflection fix below)
+        U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
+        U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
+        U[2][2] = U[0][0] * U[1][1] - U[1][0] * U[0][1];
+      }
+    }
+    // R = V U^T, reflections removed by flipping the last singular vector / value
+    double R[3][3];
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) R[a][b] = Vs[a][0] * U[b][0] + Vs[a][1] * U[b][1] + Vs[a][2] * U[b][2];
+    const double det = R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) - R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) +
+                       R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
+    if (det < 0) {
+      for (int a = 0; a < 3; ++a) Vs[a][2] = -Vs[a][2];
+      sv[2] = -sv[2];
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) R[a][b] = Vs[a][0] * U[b][0] + Vs[a][1] * U[b][1] + Vs[a][2] * U[b][2];
+    }
+    const double scale = (sv[0] + sv[1] + sv[2]) * nX / nY;
+    double tvec[3];
+    for (int b = 0; b < 3; ++b)
+      tvec[b] = muX[b] - scale * (muY[0] * R[0][b] + muY[1] * R[1][b] + muY[2] * R[2][b]);
+    double e = 0.0;
+    for (int j = 0; j < J; ++j) {
+      double d2 = 0.0;
+      for (int b = 0; b < 3; ++b) {
+        const double al = scale * (Y[3 * j] * R[0][b] + Y[3 * j + 1] * R[1][b] + Y[3 * j + 2] * R[2][b]) + tvec[b];
+        const double df = al - X[3 * j + b];
+        d2 += df * df;
+      }
+      e += sqrt(d2);
+    }
+    acc += e;
+  }
+  const double r = block_sum(acc);
+  if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+
+// mean over (t, point) of | (p[t+1] - p[t]) - (g[t+1] - g[t]) |_2 for arrays [T][inner points][D]
+__global__ void __launch_bounds__(kLossThreads)
+velocity_partial_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, long long T, long long inner, int D,
+                        double* __restrict__ partial) {
+  const long long n = (T - 1) * inner;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long a = i * D, b = (i + inner) * D;
+    float s = 0.f;
+    for (int d = 0; d < D; ++d) {
+      const float v = (pred[b + d] - pred[a + d]) - (tgt[b + d] - tgt[a + d]);
+      s += v * v;
+    }
+    acc += (double)sqrtf(s);
+  }
+  const double r = block_sum(acc);
+  if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int loss_grid(long long n_joints, int sm_count) {
@@ -302,6 +455,26 @@ cudaError_t launch_n_mpjpe_fwd(const float* pred, const float* tgt, long long n_
   n_mpjpe_partial_kernel<<<(int)blocks, kLossThreads, 0, stream>>>(pred, tgt, n_poses, J, partial);
   const double cnt = (double)n_poses * (double)J;
   mean_finish_kernel<<<1, kLossThreads, 0, stream>>>(partial, (int)blocks, cnt > 0 ? 1.0 / cnt : 0.0, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_p_mpjpe_fwd(const float* pred, const float* tgt, long long n_poses, int J, double* partial, float* out,
+                               int sm_count, cudaStream_t stream) {
+  long long blocks = (n_poses + kLossThreads - 1) / kLossThreads;
+  const long long cap = (long long)sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  p_mpjpe_partial_kernel<<<(int)blocks, kLossThreads, 0, stream>>>(pred, tgt, n_poses, J, partial);
+  mean_finish_kernel<<<1, kLossThreads, 0, stream>>>(partial, (int)blocks, 1.0 / ((double)n_poses * J), out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_velocity_error(const float* pred, const float* tgt, long long T, long long inner, int D,
+                                  double* partial, float* out, int sm_count, cudaStream_t stream) {
+  const long long n = (T - 1) * inner;
+  const int grid = loss_grid(n * 4, sm_count);
+  velocity_partial_kernel<<<grid, kLossThreads, 0, stream>>>(pred, tgt, T, inner, D, partial);
+  mean_finish_kernel<<<1, kLossThreads, 0, stream>>>(partial, grid, n > 0 ? 1.0 / (double)n : 0.0, out);
   return cudaGetLastError();
 }
 

@@ -99,6 +99,9 @@ _SIGNATURES = {
     'vp3d_mpjpe_nd_bwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p] +
                           [C.c_longlong] * 5 + [C.c_void_p, C.c_void_p]),
     'vp3d_n_mpjpe_fwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'vp3d_p_mpjpe_fwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'vp3d_velocity_error': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]),
     'vp3d_n_mpjpe_bwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     'vp3d_wgrad': (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
     'vp3d_wgrad_finish': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 3 + [C.c_longlong] * 2 + [C.c_void_p, C.c_void_p]),

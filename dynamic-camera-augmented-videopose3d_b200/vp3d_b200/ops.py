@@ -196,6 +196,34 @@ def n_mpjpe(pred, tgt):
     return _NMpjpeFn.apply(pred, tgt)
 
 
+def p_mpjpe(pred, tgt):
+    """(n_poses, J, 3) CUDA tensors -> 0-dim tensor: Procrustes-aligned MPJPE (loss.py:29-68) without leaving the device."""
+    require_cuda(pred, tgt)
+    assert pred.shape == tgt.shape
+    assert pred.dim() == 3 and pred.shape[-1] == 3, 'p_mpjpe expects (n_poses, J, 3) (loss.py:36 averages over axis 1)'
+    p, g = f32c(pred.detach()), f32c(tgt.detach())
+    out = torch.empty((), dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        check(lib().vp3d_p_mpjpe_fwd(_ptr(p), _ptr(g), p.shape[0], p.shape[1], _ptr(_loss_workspace(p.device)),
+                                     _ptr(out), _stream()), 'p_mpjpe_fwd')
+    return out
+
+
+def mean_velocity_error(pred, tgt):
+    """(T, ..., D) CUDA tensors -> 0-dim tensor (loss.py:82-91: first differences along axis 0)."""
+    require_cuda(pred, tgt)
+    assert pred.shape == tgt.shape
+    assert pred.dim() >= 2 and pred.shape[0] >= 2
+    p, g = f32c(pred.detach()), f32c(tgt.detach())
+    T, D = p.shape[0], p.shape[-1]
+    inner = p.numel() // (T * D)
+    out = torch.empty((), dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        check(lib().vp3d_velocity_error(_ptr(p), _ptr(g), T, inner, D, _ptr(_loss_workspace(p.device)), _ptr(out),
+                                        _stream()), 'velocity_error')
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ K1 plumbing
 def pack_rows(dt, src, c_pad):
     """fp32 (rows, c) -> operand type (rows, c_pad) zero padded."""

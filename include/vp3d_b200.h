@@ -198,6 +198,15 @@ int vp3d_mpjpe_nd_bwd(const float* pred, const float* target, const float* grad_
                       long long w_stride_j, float* grad_pred, void* stream);
 int vp3d_n_mpjpe_fwd(const float* pred, const float* target, long long n_poses, int J, void* workspace, float* out,
                      void* stream);
+/* Evaluation metrics on the device (the reference computes them in NumPy after a D2H copy, run.py:749-756):
+ *   vp3d_p_mpjpe_fwd       loss.py:29-68   MPJPE after the optimal similarity transform per pose (3x3 SVD Procrustes with
+ *                                          the reflection fix), poses pred/target[n_poses][J][3]
+ *   vp3d_velocity_error    loss.py:82-91   mean | diff_t(pred) - diff_t(target) |_2 over arrays [T][inner][dim]
+ * `workspace` as for vp3d_mpjpe_fwd; `out` one device float. */
+int vp3d_p_mpjpe_fwd(const float* pred, const float* target, long long n_poses, int J, void* workspace, float* out,
+                     void* stream);
+int vp3d_velocity_error(const float* pred, const float* target, long long T, long long inner, int dim, void* workspace,
+                        float* out, void* stream);
 /* grad_pred = grad_out * d n_mpjpe / d pred (the scale factor is differentiated too, as autograd does for loss.py:77-80). */
 int vp3d_n_mpjpe_bwd(const float* pred, const float* target, const float* grad_out, long long n_poses, int J,
                      float* grad_pred, void* stream);

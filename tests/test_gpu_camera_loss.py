@@ -165,3 +165,30 @@ def test_n_mpjpe_gradient_matches_autograd_of_the_reference_formula():
         val.backward()
         assert abs(val.item() - oloss.n_mpjpe(pred, tgt).item()) < 1e-6
         np.testing.assert_allclose(pg.grad.cpu().numpy(), pc.grad.numpy(), atol=2e-8, rtol=2e-4)
+
+
+def test_gpu_eval_metrics_match_the_numpy_reference_semantics():
+    """p_mpjpe (Procrustes, 3x3 SVD per pose) and mean_velocity_error on the device against the oracle's NumPy
+    restatement and the reference's golden values."""
+    z = load_golden('loss.npz')
+    pred, tgt = z['pred'], z['tgt']                      # (6, 5, 17, 3)
+    p2, t2 = pred.reshape(-1, 17, 3), tgt.reshape(-1, 17, 3)
+    got = closs.p_mpjpe(torch.from_numpy(p2).cuda(), torch.from_numpy(t2).cuda()).item()
+    assert abs(got - float(z['p_mpjpe'])) < 2e-6 * max(1.0, abs(float(z['p_mpjpe'])))
+    pv, tv = pred[0], tgt[0]                             # (5, 17, 3): frames along axis 0
+    got_v = closs.mean_velocity_error(torch.from_numpy(pv).cuda(), torch.from_numpy(tv).cuda()).item()
+    assert abs(got_v - oloss.mean_velocity_error(pv, tv)) < 1e-6
+    rng = np.random.default_rng(3)
+    for J in (17, 31):
+        t = rng.standard_normal((300, J, 3)).astype(np.float32)
+        # similarity-transformed + noisy copies, incl. a mirrored pose (reflection branch) and a planar pose (rank 2)
+        ang = rng.standard_normal((300, 3))
+        p = (t * 1.3 + 0.05 * rng.standard_normal(t.shape)).astype(np.float32)
+        p[0, :, 0] *= -1
+        p[1, :, 2] = 0
+        t[1, :, 2] = 0
+        want = oloss.p_mpjpe(p.copy(), t.copy())
+        got = closs.p_mpjpe(torch.from_numpy(p).cuda(), torch.from_numpy(t).cuda()).item()
+        assert abs(got - want) < 5e-6 * max(1.0, want), (J, got, want)
+    # NumPy inputs keep the reference's host semantics
+    assert abs(closs.p_mpjpe(p2.copy(), t2.copy()) - float(z['p_mpjpe'])) < 1e-6
