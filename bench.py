@@ -488,12 +488,12 @@ def bench_train(args, rank, world, dev, steps, warm):
                      'algorithmic_flop_per_sample': TRAIN_FLOP_PER_SAMPLE,
                      'gemm_ms_per_step': gemm_ms, 'conv_fwd_dgrad_ms': conv_ms, 'wgrad_ms': wgrad_ms,
                      'bn_act_ms_per_step': bn_ms, 'kernel_share_of_step': gemm_ms / (ms / steps)},
-        'projection_roofline': {'bound': 'hbm', 'kernel': 'project_points_kernel', 'achieved': proj_gbs,
+        'projection_roofline': {'bound': 'hbm', 'kernel': 'project_frames_kernel (bulk-copy staged tiles of whole frames)', 'achieved': proj_gbs,
                                 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': proj_gbs / peaks['hbm_gbs'],
                                 'ms_per_launch': proj_ms, 'algorithmic_bytes_per_frame': PROJ_BYTES_PER_FRAME,
                                 'frames_per_launch': batch * RF,
                                 'how': '40 launches over 4 rotating input sets (> L2) replayed from a CUDA graph, CUDA events',
-                                'traffic': load_traffic().get('project_points_kernel')},
+                                'traffic': load_traffic().get('project_frames_kernel')},
         'mpjpe_ms_per_step': mpjpe_ms,
     }
 

@@ -15,7 +15,10 @@
 // Access pattern: each thread owns 4 consecutive points = three aligned float4 loads (48 B) and writes two float4
 // of 2-D output; the per-frame camera record (quaternion 4 + translation 3 + intrinsics 9 floats) is read through the
 // read-only path and is shared by the J joints of a frame. A scalar path covers tails and unaligned views.
+#include <cstdlib>
+
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace vp3d {
 
@@ -459,12 +462,252 @@ cudaError_t launch_project_bwd(const float* X, const float* cam, const float* g,
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Dynamic-camera fast path: world -> camera -> image plane with ONE camera pose per frame (the per-frame form of
+// camera.py:28-30 + camera.py:37-67), VP3D_PT_FAST arithmetic.
+//
+// project_points_kernel above is instruction bound (a quad of points per thread: record cursors, a quaternion rotation
+// per point, an IEEE division, 3 strided 16-byte loads). This kernel spends its instructions differently:
+//   * persistent CTAs walk tiles of F whole frames; a tile's joints, quaternions and translations are three contiguous
+//     byte ranges, fetched by three bulk async copies (cp.async.bulk, the untiled TMA path) into a ring of STAGES
+//     shared-memory buffers signalled on mbarriers -- no load instructions, no address arithmetic, and
+//     (STAGES - 1) tiles per CTA in flight whatever the occupancy;
+//   * per frame (not per point) one thread turns the conjugate quaternion into the 3x3 matrix of the same linear map
+//     (I + 2w[q]x + 2[q]x^2, identical to qrot for any q, unit or not) and another fetches the frame's intrinsics;
+//     both land in a 96-byte shared-memory record;
+//   * per point: 3 conflict-free LDS (stride 3 words), the record as 6 broadcast LDS.128, 3 subtractions + 9 FMAs,
+//     one MUFU reciprocal (<= 1 ulp), NaN-propagating min/max for torch.clamp, the distortion polynomial in Horner
+//     form, one coalesced 8-byte store. ~50 instructions instead of ~90.
+// Differences from the un-contracted path stay <= 1e-6 absolute on normalised image coordinates (tests: 1e-5 budget).
+struct FrameParams {
+  const float* x;      // [frames][J][3]
+  const float* q;      // [frames][4]
+  const float* t;      // [frames][3]
+  const float* cam;    // [frames / frames_per_cam][9]
+  float* out3;         // optional camera-space points
+  float* out2;         // image-plane points
+  unsigned n_frames, joints, frames_per_cam, tile_frames, joint_magic;
+  int linear;
+};
+
+constexpr int kFrameThreads = 256;
+constexpr int kFrameMaxTile = 128;       // frames per tile (<= kFrameThreads / 2: one record thread + one intrinsics thread)
+constexpr int kFrameMaxPoints = 2304;    // points per tile (27 KB of joints per stage)
+
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // one MUFU; the non-ftz form adds a 6-instruction range fix-up
+  return y;
+}
+// torch.clamp(x, -1, 1): NaN stays NaN
+__device__ __forceinline__ float clamp_unit_nan(float x) {
+  float y;
+  asm("max.NaN.f32 %0, %1, 0fBF800000;\n\tmin.NaN.f32 %0, %0, 0f3F800000;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int STAGES, bool HAS3>
+__global__ void __launch_bounds__(kFrameThreads, 3)
+project_frames_kernel(const FrameParams p) {
+  extern __shared__ __align__(128) unsigned char frame_smem[];
+  const unsigned F = p.tile_frames, J = p.joints;
+  const unsigned x_bytes = F * J * 12, q_bytes = F * 16, t_bytes = F * 12;   // all multiples of 16 (F % 4 == 0)
+  const unsigned stage_bytes = x_bytes + q_bytes + t_bytes;
+  float4* rec = reinterpret_cast<float4*>(frame_smem + STAGES * stage_bytes);   // [F][6]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rec + 6 * F);
+  const unsigned tid = threadIdx.x;
+  const unsigned n_tiles = (p.n_frames + F - 1) / F;
+
+  auto issue = [&](unsigned tile, unsigned s) {   // one thread; `tile` is a full tile
+    unsigned char* dst = frame_smem + s * stage_bytes;
+    const size_t f0 = (size_t)tile * F;
+    mbar_expect_tx(&bars[s], stage_bytes);
+    bulk_load_1d(dst, p.x + f0 * J * 3, x_bytes, &bars[s]);
+    bulk_load_1d(dst + x_bytes, p.q + f0 * 4, q_bytes, &bars[s]);
+    bulk_load_1d(dst + x_bytes + q_bytes, p.t + f0 * 3, t_bytes, &bars[s]);
+  };
+  auto is_full = [&](unsigned tile) { return (size_t)(tile + 1) * F <= p.n_frames; };
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+    fence_barrier_init();
+    for (unsigned s = 0; s < STAGES; ++s) {
+      const unsigned tile = blockIdx.x + s * gridDim.x;
+      if (tile < n_tiles && is_full(tile)) issue(tile, s);
+    }
+  }
+  __syncthreads();
+
+  unsigned it = 0;
+  for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const unsigned s = it % STAGES, parity = (it / STAGES) & 1;
+    const unsigned f0 = tile * F;
+    const unsigned nf = min(F, p.n_frames - f0);
+    const unsigned npts = nf * J;
+    const float* sx = reinterpret_cast<const float*>(frame_smem + s * stage_bytes);
+    const float4* sq = reinterpret_cast<const float4*>(frame_smem + s * stage_bytes + x_bytes);
+    const float* st = reinterpret_cast<const float*>(frame_smem + s * stage_bytes + x_bytes + q_bytes);
+
+    // intrinsics of this tile's frames: independent of the tile data, so requested before waiting for it
+    float c[9];
+    const bool cam_thread = tid >= kFrameMaxTile && tid - kFrameMaxTile < nf;
+    if (cam_thread) {
+      const float* cp = p.cam + 9 * (size_t)((f0 + tid - kFrameMaxTile) / p.frames_per_cam);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) c[k] = __ldg(cp + k);
+    }
+
+    if (nf == F) {
+      mbar_wait(&bars[s], parity);
+    } else {   // ragged last tile (sizes not multiples of 16 bytes): ordinary loads; its stage is idle by construction
+      float* wx = const_cast<float*>(sx);
+      float* wq = reinterpret_cast<float*>(const_cast<float4*>(sq));
+      float* wt = const_cast<float*>(st);
+      for (unsigned i = tid; i < npts * 3; i += kFrameThreads) wx[i] = __ldg(p.x + (size_t)f0 * J * 3 + i);
+      for (unsigned i = tid; i < nf * 4; i += kFrameThreads) wq[i] = __ldg(p.q + (size_t)f0 * 4 + i);
+      for (unsigned i = tid; i < nf * 3; i += kFrameThreads) wt[i] = __ldg(p.t + (size_t)f0 * 3 + i);
+      __syncthreads();
+    }
+
+    if (tid < nf) {   // rows of the matrix of v -> qrot(conj(q), v), each with its translation component
+      const float4 qq = sq[tid];
+      const float w = qq.x, x = -qq.y, y = -qq.z, z = -qq.w;
+      const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, xz = x * z, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
+      rec[6 * tid + 0] = make_float4(fmaf(-2.f, yy + zz, 1.f), 2.f * (xy - wz), 2.f * (xz + wy), st[3 * tid + 0]);
+      rec[6 * tid + 1] = make_float4(2.f * (xy + wz), fmaf(-2.f, xx + zz, 1.f), 2.f * (yz - wx), st[3 * tid + 1]);
+      rec[6 * tid + 2] = make_float4(2.f * (xz - wy), 2.f * (yz + wx), fmaf(-2.f, xx + yy, 1.f), st[3 * tid + 2]);
+    } else if (cam_thread) {
+      const unsigned lf = tid - kFrameMaxTile;
+      rec[6 * lf + 3] = make_float4(c[0], c[1], c[2], c[3]);
+      rec[6 * lf + 4] = make_float4(c[4], c[5], c[6], c[7]);
+      rec[6 * lf + 5] = make_float4(c[8], 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+
+    float2* o2 = reinterpret_cast<float2*>(p.out2) + (size_t)f0 * J;
+    float* o3 = HAS3 ? p.out3 + (size_t)f0 * J * 3 : nullptr;
+#pragma unroll 2
+    for (unsigned i = tid; i < npts; i += kFrameThreads) {
+      const unsigned f = __umulhi(i, p.joint_magic);   // i / J, exact for i * J < 2^32 (J >= 2)
+      const float4 r0 = rec[6 * f + 0], r1 = rec[6 * f + 1], r2 = rec[6 * f + 2];
+      const float dx = sx[3 * i] - r0.w, dy = sx[3 * i + 1] - r1.w, dz = sx[3 * i + 2] - r2.w;
+      const float X = fmaf(r0.z, dz, fmaf(r0.y, dy, r0.x * dx));
+      const float Y = fmaf(r1.z, dz, fmaf(r1.y, dy, r1.x * dx));
+      const float Z = fmaf(r2.z, dz, fmaf(r2.y, dy, r2.x * dx));
+      if (HAS3) {
+        o3[3 * i] = X;
+        o3[3 * i + 1] = Y;
+        o3[3 * i + 2] = Z;
+      }
+      {
+        const float4 c0 = rec[6 * f + 3];
+        const float iz = rcp_approx(Z);   // 0 -> inf: x * inf -> +-inf -> clamp, 0 * inf -> NaN, like x / 0 and 0 / 0
+        const float u = clamp_unit_nan(X * iz), v = clamp_unit_nan(Y * iz);
+        float2 o;
+        if (p.linear) {
+          o = make_float2(fmaf(c0.x, u, c0.z), fmaf(c0.y, v, c0.w));
+        } else {
+          const float4 c1 = rec[6 * f + 4];
+          const float p2 = rec[6 * f + 5].x;
+          const float r2s = fmaf(u, u, v * v);
+          const float sden = 1.f + r2s * fmaf(r2s, fmaf(r2s, c1.z, c1.y), c1.x) + fmaf(c1.w, u, p2 * v);
+          o = make_float2(fmaf(c0.x, fmaf(u, sden, c1.w * r2s), c0.z), fmaf(c0.y, fmaf(v, sden, p2 * r2s), c0.w));
+        }
+        o2[i] = o;
+      }
+    }
+    __syncthreads();   // the stage and the records are free again
+
+    if (tid == 0) {
+      const unsigned next = tile + STAGES * gridDim.x;
+      if (next < n_tiles && is_full(next)) issue(next, s);
+    }
+  }
+}
+
+// Tuning knobs for A/B runs: VP3D_PROJ_TUNE="stages,max_points_per_tile,ctas_per_sm"; "0" disables the frame kernel
+// (everything takes project_points_kernel). Measured on B200 (tools/proj_probe.py, fraction of the 6565 GB/s copy peak at
+// 1024 / 4096 windows of 243 x 17 joints): 3,2304,2 -> 0.59 / 0.77; 2,2304,3 -> 0.73 / 0.85; 2,1536,4 -> 0.73 / 0.86
+// (default); 3,1152,4 -> 0.70 / 0.85: resident threads matter more than bytes in flight (the kernel still issues ~50
+// instructions per point), so two stages and four 256-thread CTAs per SM (64 registers) win.
+struct FrameTune {
+  int stages = 2, max_points = 1536, ctas = 4;
+  FrameTune() {
+    if (const char* e = std::getenv("VP3D_PROJ_TUNE")) {
+      int a = 0, b = 0, c = 0;
+      const int n = std::sscanf(e, "%d,%d,%d", &a, &b, &c);
+      if (n >= 1) stages = a;
+      if (n >= 2 && b > 0) max_points = b;
+      if (n >= 3 && c > 0) ctas = c;
+    }
+  }
+};
+
+static inline bool aligned16(const void* p);
+
+// Returns cudaErrorNotSupported when the call does not fit the frame kernel (the caller then uses the generic one).
+static cudaError_t try_launch_project_frames(const float* X, float* out3, float* out2, long long n_pts, const float* q,
+                                             const float* t, const float* cam, long long pts_per_q,
+                                             long long pts_per_cam, int mode, int sm_count, cudaStream_t stream) {
+  static const FrameTune tune;
+  const int want = VP3D_PT_WORLD_TO_CAMERA | VP3D_PT_PROJECT | VP3D_PT_FAST;
+  if (tune.stages < 2 || tune.stages > 3) return cudaErrorNotSupported;
+  if ((mode & ~VP3D_PT_LINEAR) != want || out2 == nullptr) return cudaErrorNotSupported;
+  const long long J = pts_per_q;
+  if (J < 2 || J > tune.max_points / 4 || n_pts % J != 0 || pts_per_cam % J != 0) return cudaErrorNotSupported;
+  const long long n_frames = n_pts / J;
+  if (n_frames >= (1LL << 31) / 2 || n_pts >= (1LL << 40)) return cudaErrorNotSupported;
+  if (!aligned16(X) || !aligned16(q) || !aligned16(t) || (reinterpret_cast<uintptr_t>(out2) & 7) ||
+      (reinterpret_cast<uintptr_t>(out3) & 3))
+    return cudaErrorNotSupported;
+  // tile size: whole frames, a multiple of 4 (16-byte granularity of the bulk copies), chosen so that the tile count
+  // fills the last wave of the persistent grid
+  long long fmax = tune.max_points / J;
+  if (fmax > kFrameMaxTile) fmax = kFrameMaxTile;
+  fmax &= ~3LL;
+  const long long grid_cap = (long long)sm_count * tune.ctas;
+  if (fmax < 4) return cudaErrorNotSupported;
+  long long F = fmax, best = -1;
+  for (long long f = fmax; f >= 4 && f >= fmax / 2; f -= 4) {   // frames the busiest CTA walks, + 4 per tile of overhead
+    const long long tiles = (n_frames + f - 1) / f;
+    const long long cost = ((tiles + grid_cap - 1) / grid_cap) * (f + 4);
+    if (best < 0 || cost < best) best = cost, F = f;
+  }
+  const long long n_tiles = (n_frames + F - 1) / F;
+  const unsigned grid = (unsigned)(n_tiles < grid_cap ? n_tiles : grid_cap);
+  FrameParams p{X, q, t, cam, out3, out2, (unsigned)n_frames, (unsigned)J, (unsigned)(pts_per_cam / J), (unsigned)F,
+                (unsigned)(((1ULL << 32) + J - 1) / J), (mode & VP3D_PT_LINEAR) ? 1 : 0};
+  const size_t smem = (size_t)tune.stages * (F * J * 12 + F * 28) + F * 96 + 8 * tune.stages;
+  if (smem > 200 * 1024) return cudaErrorNotSupported;
+  static const cudaError_t configured = [] {   // opt in to > 48 KB of dynamic shared memory, once per process
+    cudaError_t e = cudaSuccess;
+    for (auto kernel : {project_frames_kernel<2, true>, project_frames_kernel<3, true>, project_frames_kernel<2, false>,
+                        project_frames_kernel<3, false>}) {
+      const cudaError_t r = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (r != cudaSuccess) e = r;
+    }
+    return e;
+  }();
+  if (configured != cudaSuccess) return configured;
+  auto launch = [&](auto kernel) {
+    kernel<<<grid, kFrameThreads, smem, stream>>>(p);
+    return cudaGetLastError();
+  };
+  if (out3 != nullptr) return tune.stages == 2 ? launch(project_frames_kernel<2, true>) : launch(project_frames_kernel<3, true>);
+  return tune.stages == 2 ? launch(project_frames_kernel<2, false>) : launch(project_frames_kernel<3, false>);
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 cudaError_t launch_project_points(const float* X, float* out3, float* out2, long long n_pts, const float* q,
                                   const float* t, const float* cam, long long pts_per_q, long long pts_per_cam,
                                   int mode, int sm_count, cudaStream_t stream) {
   if (n_pts <= 0) return cudaSuccess;
+  {
+    const cudaError_t e = try_launch_project_frames(X, out3, out2, n_pts, q, t, cam, pts_per_q, pts_per_cam, mode,
+                                                    sm_count, stream);
+    if (e != cudaErrorNotSupported) return e;
+  }
   PointOps o{q, t, cam, pts_per_q > 0 ? pts_per_q : 1, pts_per_cam > 0 ? pts_per_cam : 1, mode};
   const int vec_ok = aligned16(X) && (out3 == nullptr || aligned16(out3)) && (out2 == nullptr || aligned16(out2));
   const long long work = vec_ok ? ((n_pts + 3) >> 2) : n_pts;

@@ -93,6 +93,15 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
       : "memory");
 }
 
+// Untiled bulk copy (global -> shared) of a contiguous byte range: both addresses 16-byte aligned, size a multiple of
+// 16 bytes; completion is signalled on the mbarrier like the tiled form.
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gmem_src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // TMA tiled store (shared -> global, bulk async-group completion). Rows / columns of the box that fall outside the
 // tensor are not written, so ragged tile tails need no masks.
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* smem_src, int32_t c0, int32_t c1,
