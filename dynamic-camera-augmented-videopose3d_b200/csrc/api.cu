@@ -625,10 +625,41 @@ int vp3d_bn_act_fwd(int dtype, const void* z, const float* scale, const float* s
     return fail(VP3D_ERR_INVALID, "bn_act_fwd: residual rows out of range");
   DeviceInfo* dev = nullptr;
   if (int rc = device_info(&dev)) return rc;
+  vp3d::BnFinalizeParams fin;
+  memset(&fin, 0, sizeof(fin));
   cudaError_t e = vp3d::launch_bn_act_fwd(dtype, z, scale, shift, res, seqs, rows_per_seq, res_seq_rows, res_row_mul,
-                                          res_row_off, c_pad, drop_of(drop), a, dev->sm_count,
+                                          res_row_off, c_pad, drop_of(drop), a, fin, dev->sm_count,
                                           static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "bn_act_fwd launch");
+  return VP3D_OK;
+}
+
+int vp3d_bn_finalize_act_fwd(int dtype, const void* z, const double* stat_sum, const double* stat_sqsum, long long count,
+                             const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                             float* running_var, long long* num_batches_tracked, float* scale, float* shift, float* mean,
+                             float* invstd, int c, const void* res, long long seqs, long long rows_per_seq,
+                             long long res_seq_rows, int res_row_mul, int res_row_off, int c_pad,
+                             const vp3d_dropout* drop, void* a, void* stream) {
+  if (int rc = check_ew(dtype, c_pad, "bn_finalize_act_fwd")) return rc;
+  if (!z || !a || seqs <= 0 || rows_per_seq <= 0) return fail(VP3D_ERR_INVALID, "bn_finalize_act_fwd args");
+  if (!stat_sum || !stat_sqsum || !gamma || !beta || !scale || !shift || !mean || !invstd || count <= 0 || c <= 0 ||
+      c > c_pad || (running_mean == nullptr) != (running_var == nullptr))
+    return fail(VP3D_ERR_INVALID, "bn_finalize_act_fwd: statistics arguments");
+  if (count <= 1)
+    return fail(VP3D_ERR_INVALID, "Expected more than 1 value per channel when training (got %lld)", count);
+  if (drop && (drop->p < 0.f || drop->p >= 1.f)) return fail(VP3D_ERR_INVALID, "dropout p must be in [0, 1)");
+  if (res != nullptr &&
+      (res_row_off < 0 || (rows_per_seq - 1) * (long long)res_row_mul + res_row_off >= res_seq_rows))
+    return fail(VP3D_ERR_INVALID, "bn_finalize_act_fwd: residual rows out of range");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  const double n = (double)count;
+  vp3d::BnFinalizeParams fin{stat_sum, stat_sqsum, 1.0 / n, (float)(n / (n - 1.0)), gamma, beta, eps, momentum,
+                             running_mean, running_var, num_batches_tracked, scale, shift, mean, invstd, c};
+  cudaError_t e = vp3d::launch_bn_act_fwd(dtype, z, nullptr, nullptr, res, seqs, rows_per_seq, res_seq_rows, res_row_mul,
+                                          res_row_off, c_pad, drop_of(drop), a, fin, dev->sm_count,
+                                          static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "bn_finalize_act_fwd launch");
   return VP3D_OK;
 }
 
@@ -729,8 +760,7 @@ int vp3d_ring_write(int dtype, const float* src, void* ring, const int* table_en
   return VP3D_OK;
 }
 
-int vp3d_adam_step(const vp3d_adam_args* a, void* stream) {
-  if (a == nullptr) return fail(VP3D_ERR_INVALID, "args is NULL");
+static int check_adam_args(const vp3d_adam_args* a) {
   if (!a->p || !a->g || !a->m || !a->v || !a->step || a->n <= 0)
     return fail(VP3D_ERR_INVALID, "adam_step: null pointer or empty tensor");
   if (a->packed != nullptr && a->n % 4 != 0) return fail(VP3D_ERR_INVALID, "adam_step: packed weights need n % 4 == 0");
@@ -742,6 +772,12 @@ int vp3d_adam_step(const vp3d_adam_args* a, void* stream) {
     if (a->c_in <= 0 || a->taps <= 0 || a->k_pad < a->c_in || a->n % ((long long)a->c_in * a->taps) != 0)
       return fail(VP3D_ERR_INVALID, "adam_step: weight geometry");
   }
+  return VP3D_OK;
+}
+
+int vp3d_adam_step(const vp3d_adam_args* a, void* stream) {
+  if (a == nullptr) return fail(VP3D_ERR_INVALID, "args is NULL");
+  if (int rc = check_adam_args(a)) return rc;
   DeviceInfo* dev = nullptr;
   if (int rc = device_info(&dev)) return rc;
   vp3d::AdamParams q;
@@ -753,6 +789,57 @@ int vp3d_adam_step(const vp3d_adam_args* a, void* stream) {
   q.packed = a->packed; q.c_in = a->c_in; q.taps = a->taps; q.k_pad = a->k_pad;
   cudaError_t e = vp3d::launch_adam_pack(a->dtype, q, dev->sm_count, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "adam_step launch");
+  return VP3D_OK;
+}
+
+int vp3d_adam_step_multi(const vp3d_adam_args* args, int count, void* stream) {
+  if (count < 0 || (count > 0 && args == nullptr)) return fail(VP3D_ERR_INVALID, "adam_step_multi: bad arguments");
+  if (count == 0) return VP3D_OK;
+  const vp3d_adam_args& h = args[0];
+  int dtype = -1;
+  for (int i = 0; i < count; ++i) {
+    const vp3d_adam_args& a = args[i];
+    if (int rc = check_adam_args(&a)) return rc;
+    if (a.lr != h.lr || a.beta1 != h.beta1 || a.beta2 != h.beta2 || a.eps != h.eps || a.weight_decay != h.weight_decay ||
+        a.lr_dev != h.lr_dev || a.maximize != h.maximize || (a.vmax == nullptr) != (h.vmax == nullptr))
+      return fail(VP3D_ERR_INVALID, "adam_step_multi: tensors of one call share their hyper-parameters");
+    if (a.packed != nullptr) {
+      if (dtype >= 0 && a.dtype != dtype) return fail(VP3D_ERR_INVALID, "adam_step_multi: one packed dtype per call");
+      dtype = a.dtype;
+    }
+  }
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  const long long budget = (long long)dev->sm_count * 8;   // blocks of 256 threads in flight, dealt by tensor size
+  for (int first = 0; first < count; first += vp3d::kAdamMaxTensors) {
+    const int n_t = count - first < vp3d::kAdamMaxTensors ? count - first : vp3d::kAdamMaxTensors;
+    long long total = 0;
+    for (int i = 0; i < n_t; ++i) total += args[first + i].n;
+    vp3d::AdamMultiParams mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.count = n_t;
+    mp.lr = h.lr; mp.beta1 = h.beta1; mp.beta2 = h.beta2; mp.eps = h.eps; mp.weight_decay = h.weight_decay;
+    mp.lr_dev = h.lr_dev;
+    mp.maximize = h.maximize;
+    int blocks = 0;
+    for (int i = 0; i < n_t; ++i) {
+      const vp3d_adam_args& a = args[first + i];
+      vp3d::AdamTensor& T = mp.t[i];
+      T.p = a.p; T.g = a.g; T.m = a.m; T.v = a.v; T.vmax = a.vmax;
+      T.n = a.n;
+      T.step = a.step;
+      T.packed = a.packed; T.c_in = a.c_in; T.taps = a.taps; T.k_pad = a.k_pad;
+      const long long need = ((a.n + 3) / 4 + 255) / 256;                 // blocks that give every thread one float4
+      long long share = (budget * a.n + total - 1) / total;               // proportional share of the grid
+      if (share > need) share = need;
+      if (share < 1) share = 1;
+      mp.block_start[i] = blocks;
+      blocks += (int)share;
+    }
+    mp.block_start[n_t] = blocks;
+    cudaError_t e = vp3d::launch_adam_multi(dtype >= 0 ? dtype : VP3D_F16, mp, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "adam_step_multi launch");
+  }
   return VP3D_OK;
 }
 

@@ -89,6 +89,26 @@ struct AdamParams {
   int c_in, taps, k_pad;
 };
 cudaError_t launch_adam_pack(int dtype, const AdamParams& a, int sm_count, cudaStream_t stream);
+// Several tensors in ONE launch (the 30 parameter tensors of a model: 10 convolution weights with their packed
+// operands, 18 BatchNorm affine vectors, the shrink bias): consecutive block ranges are dealt to the tensors in proportion
+// to their size. The hyper-parameters are shared, `step` / `packed` geometry are per tensor.
+constexpr int kAdamMaxTensors = 32;
+struct AdamTensor {
+  float* p; const float* g; float* m; float* v; float* vmax;
+  long long n;
+  const float* step;
+  void* packed;
+  int c_in, taps, k_pad, reserved;
+};
+struct AdamMultiParams {
+  AdamTensor t[kAdamMaxTensors];
+  int block_start[kAdamMaxTensors + 1];   // tensor i owns blocks [block_start[i], block_start[i + 1])
+  int count;
+  float lr, beta1, beta2, eps, weight_decay;
+  const float* lr_dev;
+  int maximize;
+};
+cudaError_t launch_adam_multi(int dtype, const AdamMultiParams& a, cudaStream_t stream);
 cudaError_t launch_stream_advance(long long* step, int n_rings, const int* ring_len, const int* ring_dil,
                                   const int* ring_taps, int rows_per_slot, int* table, int n_launch,
                                   const int* launch_desc, int* launch_table, cudaStream_t stream);
@@ -98,10 +118,21 @@ cudaError_t launch_bn_finalize(const double* sum, const double* sqsum, long long
                                const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                                long long* nbt, float* scale, float* shift, float* mean, float* invstd, int c, int c_pad,
                                cudaStream_t stream);
+// bn_finalize folded into bn_act_fwd: sum == nullptr -> the kernel reads ready-made scale / shift instead
+struct BnFinalizeParams {
+  const double* sum; const double* sqsum;
+  double inv_n;          // 1 / rows the sums were taken over
+  float unbias;          // n / (n - 1): running_var takes the unbiased variance
+  const float* gamma; const float* beta;
+  float eps, momentum;
+  float* running_mean; float* running_var; long long* nbt;
+  float* scale_out; float* shift_out; float* mean_out; float* invstd_out;
+  int c;
+};
 cudaError_t launch_bn_act_fwd(int dtype, const void* z, const float* scale, const float* shift, const void* res,
                               long long seqs, long long rows_per_seq, long long res_seq_rows, int res_row_mul,
-                              int res_row_off, int c_pad, const DropoutParams& dp, void* a, int sm_count,
-                              cudaStream_t stream);
+                              int res_row_off, int c_pad, const DropoutParams& dp, void* a,
+                              const BnFinalizeParams& fin, int sm_count, cudaStream_t stream);
 cudaError_t launch_col_stats(int dtype, const void* z, long long rows, int c_pad, double* sum, double* sqsum,
                              int sm_count, cudaStream_t stream);
 cudaError_t launch_bn_act_bwd_reduce(int dtype, const void* g, const void* z, const float* scale, const float* shift,

@@ -99,8 +99,27 @@ __device__ __forceinline__ void drop_mult8(const DropCtx& d, uint32_t w0, uint32
 }
 
 // ---------------------------------------------------------------------------------------------- bn_finalize
+// Batch statistics of one channel from its double-precision sums. Shared by bn_finalize_kernel and the fused
+// bn_act_fwd_kernel so that both give the same bits. Only the cancellation-prone part (E[z^2] - E[z]^2) is done in
+// double precision -- three operations; a double division / square root per channel in EVERY thread of the fused apply
+// pass cost 55 us per training step on B200's thin FP64 pipe -- and invstd is an IEEE fp32 1 / sqrt(var + eps), the
+// precision F.batch_norm itself normalises with.
+struct BnChannel {
+  float mean, invstd, var;
+};
+__device__ __forceinline__ BnChannel bn_channel_stats(double sum, double sqsum, double inv_n, float eps) {
+  const double m = sum * inv_n;
+  double var = fma(sqsum, inv_n, -m * m);   // biased, as F.batch_norm normalises with
+  if (var < 0.0) var = 0.0;
+  BnChannel r;
+  r.mean = (float)m;
+  r.var = (float)var;
+  r.invstd = 1.f / sqrtf(r.var + eps);
+  return r;
+}
+
 __global__ void __launch_bounds__(256)
-bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sqsum, long long count,
+bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sqsum, double inv_n, float unbias,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
                    float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ nbt,
                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
@@ -115,20 +134,15 @@ bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sq
     invstd_out[i] = 0.f;
     return;
   }
-  const double n = (double)count;
-  const double m = sum[i] / n;
-  double var = sqsum[i] / n - m * m;  // biased, as F.batch_norm normalises with
-  if (var < 0.0) var = 0.0;
-  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
-  const float sc = gamma[i] * invstd;
+  const BnChannel ch = bn_channel_stats(sum[i], sqsum[i], inv_n, eps);
+  const float sc = gamma[i] * ch.invstd;
   scale[i] = sc;
-  shift[i] = beta[i] - (float)m * sc;
-  mean_out[i] = (float)m;
-  invstd_out[i] = invstd;
+  shift[i] = beta[i] - ch.mean * sc;
+  mean_out[i] = ch.mean;
+  invstd_out[i] = ch.invstd;
   if (running_mean != nullptr) {
-    const double unbiased = count > 1 ? var * n / (n - 1.0) : var;
-    running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * (float)m;
-    running_var[i] = (1.f - momentum) * running_var[i] + momentum * (float)unbiased;
+    running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * ch.mean;
+    running_var[i] = (1.f - momentum) * running_var[i] + momentum * (ch.var * unbias);   // unbiased: n / (n - 1)
   }
 }
 
@@ -166,17 +180,48 @@ struct RowWalkT {
 };
 using RowWalk = RowWalkT<kEwLanes>;
 
+// bn_finalize folded into the apply pass (fin.sum != nullptr): every thread derives the scale / shift of its 8 channels
+// from the batch sums itself (16 doubles, the arithmetic of bn_finalize_kernel to the bit), and the threads of the first
+// row block additionally publish scale / shift / mean / invstd for the backward and update the running statistics --
+// one launch (and one dependent-launch gap) less per layer.
 template <int DT>
 __global__ void __launch_bounds__(kEwGroups * kEwLanes, 3)
 bn_act_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                   const uint4* __restrict__ res, long long rows, long long rows_per_seq, long long res_seq_rows,
-                  int res_row_mul, int res_row_off, int groups, DropoutParams dp, uint4* __restrict__ a) {
+                  int res_row_mul, int res_row_off, int groups, DropoutParams dp, uint4* __restrict__ a,
+                  const BnFinalizeParams fin) {
   const RowWalk w;
   if (w.grp >= groups) return;
   const DropCtx drop = make_drop(dp);
   float sc[8], sh[8];
-  load8(scale, w.grp, sc);
-  load8(shift, w.grp, sh);
+  if (fin.sum != nullptr) {
+    const bool publish = blockIdx.x == 0 && w.lane == 0;
+    if (publish && w.grp == 0 && fin.nbt != nullptr) *fin.nbt += 1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = w.grp * 8 + k;
+      BnChannel ch{0.f, 0.f, 0.f};
+      sc[k] = sh[k] = 0.f;
+      if (i < fin.c) {
+        ch = bn_channel_stats(fin.sum[i], fin.sqsum[i], fin.inv_n, fin.eps);
+        sc[k] = fin.gamma[i] * ch.invstd;
+        sh[k] = fin.beta[i] - ch.mean * sc[k];
+        if (publish && fin.running_mean != nullptr) {
+          fin.running_mean[i] = (1.f - fin.momentum) * fin.running_mean[i] + fin.momentum * ch.mean;
+          fin.running_var[i] = (1.f - fin.momentum) * fin.running_var[i] + fin.momentum * (ch.var * fin.unbias);
+        }
+      }
+      if (publish) {
+        fin.scale_out[i] = sc[k];
+        fin.shift_out[i] = sh[k];
+        fin.mean_out[i] = ch.mean;
+        fin.invstd_out[i] = ch.invstd;
+      }
+    }
+  } else {
+    load8(scale, w.grp, sc);
+    load8(shift, w.grp, sh);
+  }
   const long long iters = (rows + (long long)gridDim.x * kRowsPerIter - 1) / ((long long)gridDim.x * kRowsPerIter);
   for (long long it = 0; it < iters; ++it) {
     uint4 zv[2 * kPairUnroll], rv[2 * kPairUnroll];
@@ -498,8 +543,7 @@ __device__ __forceinline__ void adam_update(const AdamParams& a, float step_size
 }
 
 template <int DT>
-__global__ void __launch_bounds__(256)
-adam_pack_kernel(AdamParams a) {
+__device__ __forceinline__ void adam_pack_body(const AdamParams& a, const long long first, const long long stride) {
   const float t = *a.step;
   const float lr = a.lr_dev != nullptr ? *a.lr_dev : a.lr;
   const float bc1 = 1.f - powf(a.beta1, t);
@@ -507,8 +551,7 @@ adam_pack_kernel(AdamParams a) {
   const float step_size = lr / bc1;
   const int row_len = a.c_in * a.taps;           // elements per output channel in the nn.Conv1d layout
   const long long n4 = a.n >> 2;                 // float4 groups (n is a multiple of 4 for every conv weight here)
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
+  for (long long q = first; q < n4; q += stride) {
     float4 p4 = reinterpret_cast<float4*>(a.p)[q];
     const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.g) + q);
     float4 m4 = reinterpret_cast<float4*>(a.m)[q];
@@ -541,7 +584,7 @@ adam_pack_kernel(AdamParams a) {
     }
   }
   // scalar tail (small tensors whose length is not a multiple of 4; they carry no packed operand)
-  for (long long i = 4 * n4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+  for (long long i = 4 * n4 + first; i < a.n; i += stride) {
     float pv = a.p[i], mv = a.m[i], vv1 = a.v[i], xv = a.vmax != nullptr ? a.vmax[i] : 0.f;
     adam_update(a, step_size, bc2_sqrt, pv, a.g[i], mv, vv1, xv);
     a.p[i] = pv;
@@ -549,6 +592,37 @@ adam_pack_kernel(AdamParams a) {
     a.v[i] = vv1;
     if (a.vmax != nullptr) a.vmax[i] = xv;
   }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256)
+adam_pack_kernel(AdamParams a) {
+  adam_pack_body<DT>(a, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(const __grid_constant__ AdamMultiParams mp) {
+  int i = 0;
+  while (i + 1 < mp.count && (int)blockIdx.x >= mp.block_start[i + 1]) ++i;   // <= 32 entries, uniform per block
+  const AdamTensor& T = mp.t[i];
+  AdamParams a;
+  a.p = T.p; a.g = T.g; a.m = T.m; a.v = T.v; a.vmax = T.vmax;
+  a.n = T.n;
+  a.lr = mp.lr; a.beta1 = mp.beta1; a.beta2 = mp.beta2; a.eps = mp.eps; a.weight_decay = mp.weight_decay;
+  a.step = T.step; a.lr_dev = mp.lr_dev;
+  a.maximize = mp.maximize;
+  a.packed = T.packed; a.c_in = T.c_in; a.taps = T.taps; a.k_pad = T.k_pad;
+  const int b0 = mp.block_start[i], nb = mp.block_start[i + 1] - b0;
+  adam_pack_body<DT>(a, (long long)(blockIdx.x - b0) * blockDim.x + threadIdx.x, (long long)nb * blockDim.x);
+}
+
+cudaError_t launch_adam_multi(int dtype, const AdamMultiParams& a, cudaStream_t stream) {
+  const int blocks = a.block_start[a.count];
+  if (blocks <= 0) return cudaSuccess;
+  if (dtype == VP3D_BF16) adam_multi_kernel<VP3D_BF16><<<blocks, 256, 0, stream>>>(a);
+  else adam_multi_kernel<VP3D_F16><<<blocks, 256, 0, stream>>>(a);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_adam_pack(int dtype, const AdamParams& a, int sm_count, cudaStream_t stream) {
@@ -591,7 +665,9 @@ cudaError_t launch_bn_finalize(const double* sum, const double* sqsum, long long
                                const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                                long long* nbt, float* scale, float* shift, float* mean, float* invstd, int c, int c_pad,
                                cudaStream_t stream) {
-  bn_finalize_kernel<<<(c_pad + 255) / 256, 256, 0, stream>>>(sum, sqsum, count, gamma, beta, eps, momentum,
+  const double n = (double)count;
+  bn_finalize_kernel<<<(c_pad + 255) / 256, 256, 0, stream>>>(sum, sqsum, 1.0 / n,
+                                                              count > 1 ? (float)(n / (n - 1.0)) : 1.f, gamma, beta, eps, momentum,
                                                               running_mean, running_var, nbt, scale, shift, mean,
                                                               invstd, c, c_pad);
   return cudaGetLastError();
@@ -605,14 +681,14 @@ cudaError_t launch_bn_finalize(const double* sum, const double* sqsum, long long
 
 cudaError_t launch_bn_act_fwd(int dtype, const void* z, const float* scale, const float* shift, const void* res,
                               long long seqs, long long rows_per_seq, long long res_seq_rows, int res_row_mul,
-                              int res_row_off, int c_pad, const DropoutParams& dp, void* a, int sm_count,
-                              cudaStream_t stream) {
+                              int res_row_off, int c_pad, const DropoutParams& dp, void* a,
+                              const BnFinalizeParams& fin, int sm_count, cudaStream_t stream) {
   const long long rows = seqs * rows_per_seq;
   const int groups = c_pad / 8;
   const dim3 grid = row_walk_grid(rows, groups, sm_count, 8);
   const int block = kEwGroups * kEwLanes;
   VP3D_DISPATCH_16(bn_act_fwd_kernel, static_cast<const uint4*>(z), scale, shift, static_cast<const uint4*>(res), rows,
-                   rows_per_seq, res_seq_rows, res_row_mul, res_row_off, groups, dp, static_cast<uint4*>(a))
+                   rows_per_seq, res_seq_rows, res_row_mul, res_row_off, groups, dp, static_cast<uint4*>(a), fin)
 }
 
 cudaError_t launch_col_stats(int dtype, const void* z, long long rows, int c_pad, double* sum, double* sqsum,

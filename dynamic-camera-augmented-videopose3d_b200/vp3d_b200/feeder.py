@@ -125,3 +125,41 @@ class DeviceWindowFeeder:
                 self.state = None
             else:
                 enabled = False
+
+
+class DeviceSequenceFeeder(DeviceWindowFeeder):
+    """UnchunkedGenerator (common/generators.py:140-205) on the device: one whole sequence per iteration (batch 1), the
+    2-D input edge-padded by (pad + causal_shift, pad - causal_shift) frames (:193-195) -- here the padded frames are
+    *projected* edge frames, which is the same thing because padding repeats the edge frame's joints and camera --, the
+    camera-space (root-relative) 3-D target of the un-padded frames, optionally the padded K @ [R|t] matrices (:184-198)
+    and the sequence's camera-motion statistics passed through (`seq_info`, :200-205).
+
+    The sequences stay resident in HBM; an iteration is one launch of vp3d_project_windows with chunk = sequence length,
+    so the evaluation loop of run.py:697-705 has no host-side padding, no float64 staging and no H2D copy per sequence."""
+
+    def __init__(self, world_3d, quats, trans, intrinsics, pad=0, causal_shift=0, root_relative=True, linear=False,
+                 want_cameras=False, seq_info=None, device='cuda'):
+        super().__init__(world_3d, quats, trans, intrinsics, batch_size=1, chunk_length=1, pad=pad,
+                         causal_shift=causal_shift, shuffle=False, root_relative=root_relative, linear=linear,
+                         want_cameras=want_cameras, device=device)
+        self.lengths = [int(x.shape[0]) for x in world_3d]
+        self.seq_info = seq_info if seq_info is not None else [{} for _ in self.lengths]
+        assert len(self.seq_info) == len(self.lengths)
+        self.seq_length = 1 + 2 * pad     # attribute of the reference class (:170)
+
+    def num_frames(self):
+        return sum(self.lengths)
+
+    def sequence(self, i):
+        """(batch_cam or None, batch_3d (1, T, J, 3), batch_2d (1, T + 2 pad, J, 2)) of sequence i."""
+        n = self.lengths[i]
+        self.chunk_length, self.window = n, n + 2 * self.pad
+        try:
+            return self.assemble(np.array([[i, 0, n]], dtype=np.int64))
+        finally:
+            self.chunk_length, self.window = 1, 1 + 2 * self.pad
+
+    def next_epoch(self):
+        for i in range(len(self.lengths)):
+            cams, b3d, b2d = self.sequence(i)
+            yield cams, b3d, b2d, self.seq_info[i]

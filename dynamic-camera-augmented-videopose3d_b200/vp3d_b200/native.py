@@ -109,6 +109,9 @@ _SIGNATURES = {
                          [C.c_void_p] * 7 + [C.c_int, C.c_int, C.c_void_p]),
     'vp3d_bn_act_fwd': (C.c_int, [C.c_int] + [C.c_void_p] * 4 + [C.c_longlong] * 3 + [C.c_int] * 3 +
                         [C.POINTER(Dropout), C.c_void_p, C.c_void_p]),
+    'vp3d_bn_finalize_act_fwd': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
+                                           C.c_float, C.c_float] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p] +
+                                 [C.c_longlong] * 3 + [C.c_int] * 3 + [C.POINTER(Dropout), C.c_void_p, C.c_void_p]),
     'vp3d_col_stats': (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     'vp3d_bn_act_bwd_reduce': (C.c_int, [C.c_int] + [C.c_void_p] * 6 + [C.c_longlong, C.c_int, C.POINTER(Dropout),
                                                                        C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -119,6 +122,7 @@ _SIGNATURES = {
     'vp3d_ring_write': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int,
                                   C.c_void_p]),
     'vp3d_adam_step': (C.c_int, [C.POINTER(AdamArgs), C.c_void_p]),
+    'vp3d_adam_step_multi': (C.c_int, [C.POINTER(AdamArgs), C.c_int, C.c_void_p]),
     'vp3d_counter_add': (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_void_p]),
     'vp3d_grad_scale': (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     'vp3d_grad_pack_rows': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p,

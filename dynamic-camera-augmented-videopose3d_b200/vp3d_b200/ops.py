@@ -394,13 +394,34 @@ def bn_act_fwd(dt, z, scale, shift, seqs, rows_per_seq, drop, res=None, res_seq_
     return a
 
 
-def bn_act_bwd(dt, g, z, scale, shift, mean, invstd, rows, c, drop, gscale_buf, count=None, group=None):
+def bn_finalize_act_fwd(dt, z, stat, count, bn, seqs, rows_per_seq, drop, res=None, res_seq_rows=0, res_row_mul=1,
+                        res_row_off=0, update_running=True):
+    """bn_finalize + bn_act_fwd in one launch -> (a, scale, shift, mean, invstd); same results as the two calls."""
+    c_pad = z.shape[-1]
+    c = bn.num_features
+    dev = z.device
+    out = torch.empty((4, c_pad), dtype=torch.float32, device=dev)
+    a = torch.empty_like(z)
+    track = update_running and bn.track_running_stats and bn.running_mean is not None
+    momentum = 0.0 if bn.momentum is None else float(bn.momentum)
+    with torch.cuda.device(dev):
+        check(lib().vp3d_bn_finalize_act_fwd(
+            dt, _ptr(z), _ptr(stat[0]), _ptr(stat[1]), int(count), _ptr(f32c(bn.weight.detach())),
+            _ptr(f32c(bn.bias.detach())), float(bn.eps), momentum, _ptr(bn.running_mean) if track else None,
+            _ptr(bn.running_var) if track else None, _ptr(bn.num_batches_tracked) if track else None,
+            _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), c, _ptr(res), seqs, rows_per_seq, res_seq_rows,
+            res_row_mul, res_row_off, c_pad, C.byref(drop), _ptr(a), _stream()), 'bn_finalize_act_fwd')
+    return a, out[0], out[1], out[2], out[3]
+
+
+def bn_act_bwd(dt, g, z, scale, shift, mean, invstd, rows, c, drop, gscale_buf, count=None, group=None, sums=None):
     """-> (dz operand-typed [rows][c_pad], d_gamma [c], d_beta [c]). `count` (>= rows) is the number of rows the
     batch statistics were taken over; with `group` the per-channel sums are all-reduced first (SyncBN: the parameter
     gradients that come out are then already summed over the group)."""
     c_pad = z.shape[-1]
     dev = z.device
-    sums = torch.zeros((2, c_pad), dtype=torch.float64, device=dev)
+    if sums is None:     # [2][c_pad] doubles, zero on entry (callers with many layers pass slices of one arena)
+        sums = torch.zeros((2, c_pad), dtype=torch.float64, device=dev)
     dz = torch.empty_like(z)
     dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):

@@ -5,11 +5,12 @@ optimiser step is followed by a re-pack of the fp32 convolution weights into the
 forward. FusedAdam is a drop-in subclass of torch.optim.Adam -- same constructor, same per-parameter state
 (`step`, `exp_avg`, `exp_avg_sq`, `max_exp_avg_sq`), so `state_dict()` / `load_state_dict()` and run.py's checkpoints
 (run.py:436-445,559-569) are interchangeable with the stock optimiser -- whose `step()` sends every fp32 CUDA parameter
-through vp3d_adam_step: one pass that updates p, m, v, vmax AND, for a convolution weight, writes the packed operand the
+through vp3d_adam_step_multi (all tensors of a parameter group in ONE launch): one pass that updates p, m, v, vmax AND, for a convolution weight, writes the packed operand the
 training forward has registered for it. Anything else (non-contiguous, other dtypes) falls through to torch's own
 implementation. State steps live on the device (capturable), so the whole step can sit in a CUDA graph.
 """
 import ctypes as C
+import os
 
 import torch
 from torch.optim import adam as _adam
@@ -57,9 +58,11 @@ class FusedAdam(torch.optim.Adam):
             torch._foreach_add_(pick(steps, big), 1)
             lr = group['lr']
             lr_dev = lr.data_ptr() if isinstance(lr, torch.Tensor) and lr.is_cuda else None
-            for i in big:
+            args = (native.AdamArgs * len(big))()
+            entries = []
+            for slot, i in enumerate(big):
                 p, g = params[i], grads[i]
-                a = native.AdamArgs()
+                a = args[slot]
                 a.p, a.g, a.m, a.v = p.data_ptr(), g.data_ptr(), exp_avgs[i].data_ptr(), exp_avg_sqs[i].data_ptr()
                 a.vmax = max_sqs[i].data_ptr() if group['amsgrad'] else None
                 a.n = p.numel()
@@ -80,9 +83,20 @@ class FusedAdam(torch.optim.Adam):
                     dt, _rows_pad, k_pad = key
                     a.packed, a.dtype = entry[0].data_ptr(), dt
                     a.c_in, a.taps, a.k_pad = p.shape[1], p.shape[2], k_pad
-                with torch.cuda.device(p.device):
-                    native.check(native.lib().vp3d_adam_step(C.byref(a), ops._stream()), 'adam_step')
+                entries.append(entry)
+            # ONE launch for all tensors of the group (on one device, one packed dtype); otherwise tensor by tensor
+            devices = {params[i].device for i in big}
+            dtypes = {args[k].dtype for k in range(len(big)) if args[k].packed}
+            if len(devices) == 1 and len(dtypes) <= 1 and os.environ.get('VP3D_ADAM_MULTI', '1') != '0':
+                with torch.cuda.device(params[big[0]].device):
+                    native.check(native.lib().vp3d_adam_step_multi(args, len(big), ops._stream()), 'adam_step_multi')
+            else:
+                for slot, i in enumerate(big):
+                    with torch.cuda.device(params[i].device):
+                        native.check(native.lib().vp3d_adam_step(C.byref(args[slot]), ops._stream()), 'adam_step')
+            for slot, i in enumerate(big):
+                p = params[i]
                 torch.autograd.graph.increment_version(p)     # p changed behind autograd's back
-                if entry is not None:
-                    entry[1] = p._version
+                if entries[slot] is not None:
+                    entries[slot][1] = p._version
         return loss

@@ -5,6 +5,7 @@ Every FLOP runs in libvp3d_b200.so:
   forward   conv GEMM (raw output z + per-channel sum / sum of squares in the epilogue)  vp3d_conv_block_fwd
             batch statistics -> scale/shift, running statistics                          vp3d_bn_finalize
             a = dropout(relu(z * scale + shift)) [+ residual rows]                       vp3d_bn_act_fwd
+            (both in one launch: vp3d_bn_finalize_act_fwd, optional)
   backward  dz = BN/ReLU/dropout backward of the incoming gradient (two passes)           vp3d_bn_act_bwd_*
             dW = dz^T a_in (stream-K tcgen05 GEMM, MN-major operands)                    vp3d_wgrad (+ _finish)
             g_in = dz W (same kernel as the forward, transposed weights, residual fan-in) vp3d_conv_block_fwd
@@ -12,6 +13,8 @@ PyTorch only allocates the buffers and records the graph edge. Gradients travel 
 by a power-of-two scale chosen on the device from max|dL/dy| (no host synchronisation); parameter gradients come out
 as unscaled fp32 in the nn.Conv1d / nn.BatchNorm1d layouts, so torch.optim and load/state_dict work unchanged.
 """
+import os
+
 import torch
 
 from . import native, ops
@@ -21,6 +24,11 @@ SHRINK_PAD = 128      # shrink-layer output channels are padded to one 128-row M
 grad_ready_hook = None   # set by vp3d_b200.ddp: called as hook(parameter, gradient) as soon as a gradient is issued
 grad_finish_hook = None  # ... and once at the end of the backward (waits for the outstanding all-reduces)
 sync_bn_group = None     # process group over which train-mode BatchNorm statistics are summed (None: per replica)
+# vp3d_bn_finalize_act_fwd (statistics -> scale/shift inside the apply pass, one launch less per layer) is available but
+# off: same-box A/B at batch 1024 gave 2.01-2.03 ms per step with it against 1.97 without -- every block of the apply pass
+# then starts with dependent loads of the double-precision sums before its first row, which costs more than the 5 us
+# finalize launch it saves. VP3D_FUSE_BN=1 switches it on.
+fuse_bn_finalize = os.environ.get('VP3D_FUSE_BN', '0') == '1'
 overlap_wgrad = True     # weight-gradient GEMMs on a second stream, concurrent with the HBM-bound BN backward passes
 _side_streams = {}
 debug_keep_saved = False  # tests: keep the last forward's saved per-layer tensors in `debug_last_saved`
@@ -77,6 +85,8 @@ def _forward_stack(model, x, dt):
     ops.counter_add(counter, 1)
     step = counter.clone()   # this call's own copy: its backward sees the same value even if another forward runs first
     layers = []
+    # BatchNorm statistics of all layers in one zero-filled arena (one fill launch per forward instead of one per layer)
+    stats_all = torch.zeros((2 * len(fw) - 1, 2, c_pad), dtype=torch.float64, device=dev)
 
     def conv_bn_act(idx, conv, bn, a_in, t, cin, cin_pad, plan, res=None, res_t=0, res_mul=1, res_off=0):
         L = _Layer()
@@ -85,7 +95,7 @@ def _forward_stack(model, x, dt):
         L.c_in, L.c_in_pad, L.t_in, L.a_in = cin, cin_pad, t, a_in
         w = _conv_w(dt, conv, c_pad, cin_pad)
         L.w_fwd = w   # [c_out_pad][taps * c_in_pad]; the data-gradient GEMM reads it again as W^T (MN-major operand)
-        stats = torch.zeros((2, c_pad), dtype=torch.float64, device=dev)
+        stats = stats_all[idx]
         # per-channel sum / sum of squares of the stored z come out of the GEMM epilogue (the staged output tile is read
         # back column-wise from shared memory); vp3d_col_stats remains as a stand-alone entry point
         z, t_out = _run_layer(dt, a_in, n, t, cin_pad, w, plan, None, None, False, stats=stats)
@@ -96,11 +106,16 @@ def _forward_stack(model, x, dt):
             dist.all_reduce(stats, group=sync_bn_group)
             count *= dist.get_world_size(sync_bn_group)
         L.count = count
-        L.scale, L.shift, L.mean, L.invstd = ops.bn_finalize(stats, count, bn, c_pad)
         L.drop = _dropout_for(model, idx, step)
         L.res_of, L.res_t, L.res_mul, L.res_off = res, res_t, res_mul, res_off
-        a = ops.bn_act_fwd(dt, z, L.scale, L.shift, n, t_out, L.drop, res=res, res_seq_rows=res_t,
-                           res_row_mul=res_mul, res_row_off=res_off)
+        if fuse_bn_finalize:
+            a, L.scale, L.shift, L.mean, L.invstd = ops.bn_finalize_act_fwd(
+                dt, z, stats, count, bn, n, t_out, L.drop, res=res, res_seq_rows=res_t, res_row_mul=res_mul,
+                res_row_off=res_off)
+        else:
+            L.scale, L.shift, L.mean, L.invstd = ops.bn_finalize(stats, count, bn, c_pad)
+            a = ops.bn_act_fwd(dt, z, L.scale, L.shift, n, t_out, L.drop, res=res, res_seq_rows=res_t,
+                               res_row_mul=res_mul, res_row_off=res_off)
         layers.append(L)
         return a, t_out
 
@@ -272,11 +287,12 @@ class _StackTrainFn(torch.autograd.Function):
                        g, (c_pad, rows * c_pad), w_mn_major=(c_pad, 0))
 
         # ---- blocks and the expand layer, last to first. `g` is the gradient wrt the current layer's output.
+        sums_all = torch.zeros((len(layers), 2, c_pad), dtype=torch.float64, device=dy.device)   # one fill per backward
         for idx in range(len(layers) - 1, -1, -1):
             L = layers[idx]
             rows = n * L.t_out
             dz, dgamma, dbeta = ops.bn_act_bwd(dt, g, L.z, L.scale, L.shift, L.mean, L.invstd, rows, L.bn.num_features,
-                                               L.drop, gscale, count=L.count, group=sync_bn_group)
+                                               L.drop, gscale, count=L.count, group=sync_bn_group, sums=sums_all[idx])
             done(L.bn.weight, dgamma)
             done(L.bn.bias, dbeta)
             on_side(lambda L=L, dz=dz: done(L.conv.weight, _weight_grad(dt, L, dz, n, c_pad, gscale, keep)), dz)

@@ -279,6 +279,16 @@ int vp3d_counter_add(unsigned long long* counter, unsigned long long inc, void* 
 int vp3d_bn_act_fwd(int dtype, const void* z, const float* scale, const float* shift, const void* res,
                     long long seqs, long long rows_per_seq, long long res_seq_rows, int res_row_mul, int res_row_off,
                     int c_pad, const vp3d_dropout* drop, void* a, void* stream);
+/* vp3d_bn_finalize and vp3d_bn_act_fwd in one launch (the training forward of every layer when the statistics need no
+ * all-reduce in between): every thread derives scale / shift of its channels from the sums; scale / shift / mean /
+ * invstd (fp32 [c_pad]) are written for the backward, running statistics and num_batches_tracked updated as by
+ * vp3d_bn_finalize. Results are bit-identical to the two-call sequence. */
+int vp3d_bn_finalize_act_fwd(int dtype, const void* z, const double* stat_sum, const double* stat_sqsum, long long count,
+                             const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                             float* running_var, long long* num_batches_tracked, float* scale, float* shift, float* mean,
+                             float* invstd, int c, const void* res, long long seqs, long long rows_per_seq,
+                             long long res_seq_rows, int res_row_mul, int res_row_off, int c_pad,
+                             const vp3d_dropout* drop, void* a, void* stream);
 
 /* Backward of the same chain, phase 1: with dy = g * dropout-mask / (1 - p) * [z * scale + shift > 0] and
  * xhat = (z - mean) * invstd, accumulate sum_dy[c] += sum_rows dy, sum_dy_xhat[c] += sum_rows dy * xhat (double). */
@@ -332,6 +342,11 @@ typedef struct vp3d_adam_args {
   void* packed; int dtype, c_in, taps, k_pad;
 } vp3d_adam_args;
 int vp3d_adam_step(const vp3d_adam_args* args, void* stream);
+/* The same update for `count` tensors in one launch (the 30 parameter tensors of a TemporalModel: one kernel instead of
+ * 30 back-to-back ones, whose launch gaps cost more than their work for the BatchNorm vectors). All entries must share
+ * lr / betas / eps / weight_decay / lr_dev / maximize / amsgrad and, where given, the packed dtype; `step` stays per
+ * tensor (torch keeps one step counter per parameter, run.py:436-445 restores them from checkpoints). */
+int vp3d_adam_step_multi(const vp3d_adam_args* args, int count, void* stream);
 
 #ifdef __cplusplus
 }

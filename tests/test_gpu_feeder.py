@@ -86,3 +86,43 @@ def test_feeder_drives_a_training_step():
             opt.step()
             losses.append(loss.item())
     assert np.isfinite(losses).all() and losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize('pad,shift', [(13, 0), (13, 13), (121, 0)])
+def test_sequence_feeder_matches_unchunked_generator_semantics(pad, shift):
+    """UnchunkedGenerator.next_epoch (generators.py:178-205): whole sequences, np.pad(..., 'edge') by
+    (pad + shift, pad - shift); fed to the eval-mode model the output has one pose per un-padded frame."""
+    from vp3d_b200.feeder import DeviceSequenceFeeder
+    X, Q, T, cam = _data(n_seq=3, seed=5)
+    info = [{'cam_velocity': float(i)} for i in range(3)]
+    fd = DeviceSequenceFeeder(X, Q, T, cam, pad=pad, causal_shift=shift, want_cameras=True, seq_info=info)
+    assert fd.num_frames() == sum(x.shape[0] for x in X)
+    n = 0
+    for s, (cams, b3d, b2d, meta) in enumerate(fd.next_epoch()):
+        L = X[s].shape[0]
+        assert b2d.shape == (1, L + 2 * pad, 17, 2) and b3d.shape == (1, L, 17, 3) and cams.shape == (1, L + 2 * pad, 3, 4)
+        assert meta is info[s]
+        xc = ocam.world_to_camera(X[s], Q[s], T[s])
+        p2 = ocam.project_to_2d(xc[None], cam[s:s + 1])[0]
+        want2 = np.pad(p2, ((pad + shift, pad - shift), (0, 0), (0, 0)), 'edge')
+        np.testing.assert_allclose(b2d[0].cpu().numpy(), want2, atol=1e-5)
+        np.testing.assert_allclose(b3d[0].cpu().numpy(), xc - xc[:, :1], atol=2e-6)
+        c = cams[0].cpu().numpy()
+        np.testing.assert_array_equal(c[:pad + shift + 1], np.broadcast_to(c[pad + shift], (pad + shift + 1, 3, 4)))
+        n += 1
+    assert n == 3
+
+
+def test_sequence_feeder_drives_evaluation():
+    from common.loss import mpjpe
+    from common.models.TemporalModel import TemporalModel
+    from vp3d_b200.feeder import DeviceSequenceFeeder
+    X, Q, T, cam = _data(n_seq=2, seed=7)
+    torch.manual_seed(0)
+    m = TemporalModel(17, 2, 17, [3, 3, 3], channels=1024).cuda().eval()
+    fd = DeviceSequenceFeeder(X, Q, T, cam, pad=(m.receptive_field() - 1) // 2)
+    with torch.no_grad():
+        for _, b3d, b2d, _ in fd.next_epoch():
+            pred = m(b2d)
+            assert pred.shape == b3d.shape        # run.py:711-734: one pose per frame of the sequence
+            assert np.isfinite(mpjpe(pred, b3d).item())

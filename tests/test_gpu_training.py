@@ -477,3 +477,72 @@ def test_batchnorm_needs_more_than_one_value_per_channel():
     m = TemporalModelOptimized1f(17, 2, 17, [3, 3, 3], dropout=0.0, channels=64).cuda().train()
     with pytest.raises(AssertionError, match='more than 1 value per channel'):
         m(torch.rand(1, 27, 17, 2).cuda())
+
+
+@pytest.mark.parametrize('with_res', [False, True])
+def test_bn_finalize_act_fwd_is_bit_identical_to_the_two_call_sequence(with_res):
+    """vp3d_bn_finalize_act_fwd (statistics -> scale / shift inside the apply pass) against vp3d_bn_finalize followed by
+    vp3d_bn_act_fwd: same activations, saved vectors and running statistics to the bit, dropout on."""
+    torch.manual_seed(7)
+    seqs, rows_per_seq, c, c_pad = 6, 37, 200, 256     # ragged channel count: [c, c_pad) must come out as zeros
+    rows = seqs * rows_per_seq
+    z = torch.zeros(rows, c_pad, device='cuda')
+    z[:, :c] = torch.randn(rows, c, device='cuda') * 1.5 + 0.3
+    z = z.half()
+    res = torch.randn(seqs, 3 * rows_per_seq + 1, c_pad, device='cuda').half() if with_res else None
+    kw = dict(res=res, res_seq_rows=3 * rows_per_seq + 1, res_row_mul=3, res_row_off=1) if with_res else {}
+    drop = ops.make_dropout(0.25, 1234, 3)
+    outs = []
+    for fused in (False, True):
+        bn = torch.nn.BatchNorm1d(c, momentum=0.1).cuda()
+        with torch.no_grad():
+            bn.weight.copy_(torch.linspace(0.5, 1.5, c))
+            bn.bias.copy_(torch.linspace(-0.2, 0.2, c))
+            bn.running_mean.copy_(torch.linspace(-1, 1, c))
+            bn.running_var.copy_(torch.linspace(0.5, 2, c))
+        stat = torch.zeros(2, c_pad, dtype=torch.float64, device='cuda')
+        ops.col_stats(native.F16, z, stat)
+        if fused:
+            a, sc, sh, mean, invstd = ops.bn_finalize_act_fwd(native.F16, z, stat, rows, bn, seqs, rows_per_seq, drop, **kw)
+        else:
+            sc, sh, mean, invstd = ops.bn_finalize(stat, rows, bn, c_pad)
+            a = ops.bn_act_fwd(native.F16, z, sc, sh, seqs, rows_per_seq, drop, **kw)
+        outs.append((a, sc, sh, mean, invstd, bn.running_mean.clone(), bn.running_var.clone(),
+                     bn.num_batches_tracked.clone()))
+    for u, v in zip(*outs):
+        assert torch.equal(u, v)
+    assert int(outs[1][-1]) == 1
+    # and against torch's own batch norm (fp32 of the stored 16-bit z)
+    want_mean = z[:, :c].float().mean(0)
+    np.testing.assert_allclose(outs[1][3][:c].cpu().numpy(), want_mean.cpu().numpy(), atol=1e-5)
+
+
+def test_adam_step_multi_matches_per_tensor_calls():
+    """One vp3d_adam_step_multi launch over tensors of very different sizes (odd lengths included) == one
+    vp3d_adam_step per tensor, bit for bit."""
+    import ctypes as C
+    torch.manual_seed(3)
+    sizes = [1024 * 1024 * 3, 1024, 1024, 51, 7, 34 * 1024 * 3, 1]
+    def make():
+        g = torch.Generator(device='cuda').manual_seed(11)
+        return [[torch.randn(n, device='cuda', generator=g) * s for s in (1.0, 0.1, 0.05, 0.01, 0.01)] for n in sizes]
+    sets = [make(), make()]
+    steps = [torch.full((), 3.0, device='cuda') for _ in sizes]
+    for which, tensors in enumerate(sets):
+        args = (native.AdamArgs * len(sizes))()
+        for i, (p, g, m, v, x) in enumerate(tensors):
+            v.abs_(), x.abs_()
+            a = args[i]
+            a.p, a.g, a.m, a.v, a.vmax = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), x.data_ptr()
+            a.n, a.lr, a.beta1, a.beta2, a.eps, a.weight_decay = p.numel(), 1e-3, 0.9, 0.999, 1e-8, 0.0
+            a.step, a.lr_dev, a.maximize, a.packed = steps[i].data_ptr(), None, 0, None
+        if which == 0:
+            for i in range(len(sizes)):
+                native.check(native.lib().vp3d_adam_step(C.byref(args[i]), ops._stream()), 'adam_step')
+        else:
+            native.check(native.lib().vp3d_adam_step_multi(args, len(sizes), ops._stream()), 'adam_step_multi')
+    torch.cuda.synchronize()
+    for ta, tb in zip(*sets):
+        for u, v in zip(ta, tb):
+            assert torch.equal(u, v)
+    assert not torch.equal(sets[0][0][0], make()[0][0])      # the update did change the parameters
