@@ -31,6 +31,7 @@ sync_bn_group = None     # process group over which train-mode BatchNorm statist
 fuse_bn_finalize = os.environ.get('VP3D_FUSE_BN', '0') == '1'
 overlap_wgrad = True     # weight-gradient GEMMs on a second stream, concurrent with the HBM-bound BN backward passes
 _side_streams = {}
+_ones = {}               # constant unit scale vectors of the shrink layer, per (device, padded width)
 debug_keep_saved = False  # tests: keep the last forward's saved per-layer tensors in `debug_last_saved`
 debug_last_saved = None
 
@@ -140,9 +141,10 @@ def _forward_stack(model, x, dt):
     n_out = model.shrink.out_channels
     n_out_pad = _round_up(n_out, 64)
     w_shrink = _conv_w(dt, model.shrink, n_out_pad, c_pad)
-    bias = torch.zeros(n_out_pad, dtype=torch.float32, device=dev)
-    bias[:n_out] = model.shrink.bias.detach().float()
-    ones = torch.ones(n_out_pad, dtype=torch.float32, device=dev)
+    bias = torch.nn.functional.pad(model.shrink.bias.detach().float(), (0, n_out_pad - n_out))   # one launch
+    ones = _ones.get((dev, n_out_pad))
+    if ones is None:
+        ones = _ones[(dev, n_out_pad)] = torch.ones(n_out_pad, dtype=torch.float32, device=dev)
     y, t = _run_layer(dt, h, n, t, c_pad, w_shrink, LayerPlan(1), ones, bias, False, out_f32=True, n_valid=n_out,
                       block_n=64)
     return y, layers, h, t, c_pad, w_shrink
