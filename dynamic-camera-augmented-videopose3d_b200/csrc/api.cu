@@ -1,5 +1,6 @@
 // C-ABI layer: argument validation, TMA tensor-map encoding, kernel launches. No torch types, no allocation.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -274,6 +275,24 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
   int grid = (int)(total_tiles < dev->sm_count ? total_tiles : dev->sm_count);
   // a grid that is a multiple of n_tiles keeps every CTA on one column tile (weights and BN statistics stay put)
   if (grid > p.n_tiles && grid % p.n_tiles != 0) grid -= grid % p.n_tiles;
+  // CTA-pair kernel (cta_group::2) for the layers it covers. VP3D_K1_2CTA: "0" keeps everything on the single-CTA
+  // kernel, "force" uses pairs whenever supported (tests on small shapes), default: launches of at least two waves.
+  static const int use_pairs = [] {
+    const char* e = std::getenv("VP3D_K1_2CTA");
+    if (e == nullptr) return 1;
+    return std::strcmp(e, "force") == 0 ? 2 : (std::strcmp(e, "0") == 0 ? 0 : 1);
+  }();
+  if (use_pairs && vp3d::conv_gemm_pair_supported(a->dtype, a->block_n, a->w_mn_major, p) &&
+      (use_pairs == 2 || total_tiles >= 2LL * dev->sm_count)) {
+    CUtensorMap tmBh;
+    cuuint64_t dims[2] = {(cuuint64_t)a->k_total, (cuuint64_t)a->n_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)(a->k_total * eb)};
+    cuuint32_t box[2] = {(cuuint32_t)kblk, (cuuint32_t)(a->block_n / 2)};
+    if (int rc = encode_map(&tmBh, a->dtype, 2, a->w, dims, strides, box, "weights (half tile)")) return rc;
+    cudaError_t e2 = vp3d::launch_conv_gemm_pair(a->dtype, tmA, tmBh, tmC, p, dev->sm_count, static_cast<cudaStream_t>(stream));
+    if (e2 != cudaSuccess) return cuda_fail(e2, "conv_gemm_pair launch");
+    return VP3D_OK;
+  }
   cudaError_t e = vp3d::launch_conv_gemm(a->dtype, a->block_n, a->w_mn_major, tmA, tmB, tmC, p, grid, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "conv_gemm launch");
   return VP3D_OK;

@@ -1,0 +1,379 @@
+// K1 on CTA pairs (cta_group::2): the eval-mode temporal-convolution block -- nn.Conv1d + folded BatchNorm + ReLU +
+// residual slice-add (common/models/TemporalModel.py:126-138) -- as ONE tcgen05.mma of M = 256 per K step over two CTAs
+// of a 2-cluster.
+//
+// Same math, layouts and epilogue as conv_gemm.cu; what changes is who stages what. A pair owns two adjacent 128-row
+// tiles of one 256-wide column tile. Each CTA loads its own A tile (16 KB per stage) and HALF of the shared weight tile
+// (128 of the 256 output channels, 16 KB), so a stage is 32 KB per SM instead of 48 KB: a third less L2 -> SM traffic
+// and shared-memory fill per FLOP, and 5 stages where the single-CTA kernel has 4. Completion of all four loads of a
+// stage is collected on the LEADER's full barrier (TMA .cta_group::2 may signal the peer's mbarrier); the leader's MMA
+// thread issues tcgen05.mma.cta_group::2 and releases the stage / publishes the accumulators in both CTAs with multicast
+// commits; both CTAs run the usual 8-warp epilogue on their own 128 TMEM lanes, and the follower's epilogue warps
+// arrive remotely on the leader's accumulator-empty barrier.
+//
+// Scope: 16-bit operands, K-major weights, 16-bit output through TMA stores, at most 1024 output channels when a
+// scale / shift is applied (the whole per-channel table sits in shared memory because a pair changes column tile from
+// tile to tile). Everything else (training statistics, fp32 output, streaming offsets, MN-major weights) stays on
+// conv_gemm_kernel.
+#include "ptx.cuh"
+#include "kernels.h"
+
+namespace vp3d {
+namespace {
+
+constexpr int kBM = 128;                  // rows per CTA (256 per pair)
+constexpr int kBN = 256;                  // output channels per pair tile
+constexpr int kKBytes = 128;              // one swizzle span of K per stage row
+constexpr int kStages = 5;
+constexpr int kEpi = 8;                   // epilogue warps, two per TMEM lane quadrant
+constexpr int kThreads = 64 + 32 * kEpi;
+constexpr int kABytes = kBM * kKBytes;            // 16 KB
+constexpr int kBHalfBytes = (kBN / 2) * kKBytes;  // 16 KB: this CTA's half of the weight tile
+constexpr int kStageBytes = kABytes + kBHalfBytes;
+constexpr int kOutBufBytes = kEpi * 32 * 64;      // one 32 x 32 staging tile (64 B rows) per epilogue warp
+constexpr int kOutStageBytes = 2 * kOutBufBytes;  // ring of two
+constexpr int kBarBytes = 512;
+constexpr int kAffineCols = 1024;
+constexpr int kAffineBytes = 2 * kAffineCols * 4;
+constexpr int kSmemBytes = kStages * kStageBytes + kOutStageBytes + kBarBytes + kAffineBytes;
+constexpr int kTmemCols = 2 * kBN;                // two accumulator buffers
+
+template <int DT>
+struct Fmt;
+template <>
+struct Fmt<VP3D_F16> {
+  static constexpr uint32_t kFormat = 0;
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ float2 unpack(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
+};
+template <>
+struct Fmt<VP3D_BF16> {
+  static constexpr uint32_t kFormat = 1;
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ float2 unpack(uint32_t u) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  }
+};
+
+struct PairTile {
+  int seq, t0, n0;
+};
+// pair tile `pt` (column tile fastest, so that the four column tiles of a row pair run at the same time and share A
+// through L2) -> this CTA's 128-row tile
+__device__ __forceinline__ PairTile decode_pair(int pt, const ConvGemmParams& p, int pairs_per_seq, int rank) {
+  PairTile c;
+  c.n0 = pt % p.n_tiles;
+  const int mp = pt / p.n_tiles;
+  c.seq = mp / pairs_per_seq;
+  c.t0 = ((mp - c.seq * pairs_per_seq) * 2 + rank) * kBM;
+  return c;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmC, const ConvGemmParams p) {
+  using F = Fmt<DT>;
+  constexpr int kElemsPerKBlock = kKBytes / 2;
+  constexpr uint32_t kIdesc = make_instr_desc(F::kFormat, 2 * kBM, kBN);
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("vp3d: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+  uint8_t* out_stage = smem + kStages * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + kOutStageBytes);
+  uint64_t* full_bar = bars;                       // used in the leader only: bytes of BOTH CTAs' loads
+  uint64_t* empty_bar = bars + kStages;            // per CTA, released by multicast commits
+  uint64_t* tmem_full_bar = bars + 2 * kStages;    // per CTA, multicast commit
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // leader only: epilogue warps of both CTAs arrive
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* affine_smem = reinterpret_cast<float*>(out_stage + kOutStageBytes + kBarBytes);   // scale[1024] | shift[1024]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int pairs_per_seq = (p.m_tiles_per_seq + 1) / 2;
+  const int total_pairs = p.a_seqs * pairs_per_seq * p.n_tiles;
+  const int first_pair = (int)cluster_id_x();
+  const int pair_step = (int)cluster_count_x();
+  const int num_kb = p.taps * p.kblocks_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 2 * kEpi);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_base_slot, kTmemCols);
+    tmem_relinquish_2cta();
+  }
+  if (p.shift != nullptr) {
+    const int n_cols = p.n_tiles * kBN;
+    for (int j = threadIdx.x; j < n_cols; j += kThreads) {
+      affine_smem[j] = p.scale != nullptr ? __ldg(p.scale + j) : 1.f;
+      affine_smem[kAffineCols + j] = __ldg(p.shift + j);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's barriers are initialised before anything here can signal them
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = first_pair; pt < total_pairs; pt += pair_step) {
+        const PairTile tc = decode_pair(pt, p, pairs_per_seq, rank);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / p.kblocks_per_tap;
+          const int kc = kb - tap * p.kblocks_per_tap;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);
+          const uint32_t full_leader = map_to_cta(smem_u32(&full_bar[stage]), 0);
+          uint8_t* sa = smem + stage * kStageBytes;
+          tma_load_3d_2cta(sa, &tmA, full_leader, kc * kElemsPerKBlock, tc.t0 + p.a_row_off + tap * p.tap_row_step,
+                           tc.seq);
+          tma_load_2d_2cta(sa + kABytes, &tmB, full_leader, kb * kElemsPerKBlock, tc.n0 * kBN + rank * (kBN / 2));
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int pt = first_pair; pt < total_pairs; pt += pair_step) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kBN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint64_t adesc = make_kmajor_sw128_desc(sa);
+          const uint64_t bdesc = make_kmajor_sw128_desc(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0);
+          umma_commit_2cta(&empty_bar[stage], 3);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2cta(&tmem_full_bar[acc], 3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
+    constexpr int kChunks = kBN / 64;   // 32-column chunks per epilogue warp
+    const int quad = warp & 3;
+    const int epi = warp - 2;
+    const int half = epi >> 2;
+    const int row = quad * 32 + lane;
+    unsigned out_buf = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t empty_leader0 = map_to_cta(smem_u32(&tmem_empty_bar[0]), 0);
+    const uint32_t empty_leader1 = map_to_cta(smem_u32(&tmem_empty_bar[1]), 0);
+    for (int pt = first_pair; pt < total_pairs; pt += pair_step) {
+      const PairTile tc = decode_pair(pt, p, pairs_per_seq, rank);
+      const int t = tc.t0 + row;
+      const bool row_ok = t < p.rows_out;
+      const long long res_row = (long long)t * p.res_row_mul + p.res_row_off;
+      const bool res_row_ok = p.res_rows <= 0 || (res_row >= 0 && res_row < p.res_rows);
+      const long long res_off = (long long)tc.seq * p.res_seq_stride + res_row * p.res_row_stride - p.res_col_off;
+      const bool res_any = p.res != nullptr && row_ok && res_row_ok;
+      auto res_in_window = [&](int c) {
+        const int col0 = tc.n0 * kBN + c * 32;
+        return p.res_cols <= 0 || (col0 >= p.res_col_off && col0 < p.res_col_off + p.res_cols);
+      };
+      auto res_load = [&](int c, uint4 (&r)[4]) {
+        if (res_any && res_in_window(c)) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.res) + res_off +
+                                                           tc.n0 * kBN + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) r[j] = __ldg(r4 + j);
+        }
+      };
+      uint4 rcur[4], rnext[4];
+      if (res_any) {
+        const char* rp = reinterpret_cast<const char*>(static_cast<const uint16_t*>(p.res) + res_off + tc.n0 * kBN +
+                                                       half * kChunks * 32);
+#pragma unroll
+        for (int k = 0; k < kChunks * 64; k += 128)
+          if (res_in_window(half * kChunks + k / 64)) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + k));
+      }
+      res_load(half * kChunks, rcur);
+
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+
+#pragma unroll 1
+      for (int c = half * kChunks; c < (half + 1) * kChunks; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + acc * kBN + c * 32 + (static_cast<uint32_t>(quad * 32) << 16), v);
+        if (c + 1 < (half + 1) * kChunks) res_load(c + 1, rnext);
+        tmem_wait_ld();
+        const int col0 = tc.n0 * kBN + c * 32;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.scale != nullptr) {
+          const float4* sc4 = reinterpret_cast<const float4*>(affine_smem + col0);
+          const float4* sh4 = reinterpret_cast<const float4*>(affine_smem + kAffineCols + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 sc = sc4[j];
+            const float4 sh = sh4[j];
+            f[4 * j + 0] = fmaf(f[4 * j + 0], sc.x, sh.x);
+            f[4 * j + 1] = fmaf(f[4 * j + 1], sc.y, sh.y);
+            f[4 * j + 2] = fmaf(f[4 * j + 2], sc.z, sh.z);
+            f[4 * j + 3] = fmaf(f[4 * j + 3], sc.w, sh.w);
+          }
+        } else if (p.shift != nullptr) {
+          const float4* sh4 = reinterpret_cast<const float4*>(affine_smem + kAffineCols + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 sh = sh4[j];
+            f[4 * j + 0] += sh.x;
+            f[4 * j + 1] += sh.y;
+            f[4 * j + 2] += sh.z;
+            f[4 * j + 3] += sh.w;
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (res_any && res_in_window(c)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 r = rcur[j];
+            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 x = F::unpack(rr[e]);
+              f[8 * j + 2 * e + 0] += x.x;
+              f[8 * j + 2 * e + 1] += x.y;
+            }
+          }
+        }
+        // staged SWIZZLE_64B tile -> one TMA store per warp per 32 columns (rows past the sequence end are clipped)
+        const unsigned b = out_buf++ & 1u;
+        uint8_t* my_stage = out_stage + b * kOutBufBytes + epi * (32 * 64);
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          st_shared_v4(my_stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), F::pack(f[8 * j + 0], f[8 * j + 1]),
+                       F::pack(f[8 * j + 2], f[8 * j + 3]), F::pack(f[8 * j + 4], f[8 * j + 5]),
+                       F::pack(f[8 * j + 6], f[8 * j + 7]));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmC, my_stage, col0, tc.t0 + quad * 32, tc.seq);
+          tma_store_commit();
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+      }
+      // this warp has read its share of the accumulator buffer: one arrival per warp on the LEADER's barrier
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        else mbar_arrive_cluster(acc ? empty_leader1 : empty_leader0);
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  // nobody leaves (or frees tensor memory) while the peer may still read this CTA's shared memory or signal its barriers
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_2cta(tmem_base, kTmemCols);
+  }
+}
+
+template <int DT>
+cudaError_t launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvGemmParams& p,
+                        int clusters, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_pair_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<DT>, tmA, tmB, tmC, p);
+}
+
+}  // namespace
+
+bool conv_gemm_pair_supported(int dtype, int block_n, int w_mn_major, const ConvGemmParams& p) {
+  if (dtype != VP3D_F16 && dtype != VP3D_BF16) return false;
+  if (block_n != kBN || w_mn_major || p.out_f32 || p.stat_sum != nullptr || p.dyn != nullptr) return false;
+  if (p.shift != nullptr && p.n_tiles * kBN > kAffineCols) return false;
+  return true;
+}
+
+// tmB must be encoded with a box of 128 output channels (half a column tile) x 64 elements of K
+cudaError_t launch_conv_gemm_pair(int dtype, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                                  const ConvGemmParams& p, int sm_count, cudaStream_t stream) {
+  const int pairs_per_seq = (p.m_tiles_per_seq + 1) / 2;
+  const long long total_pairs = (long long)p.a_seqs * pairs_per_seq * p.n_tiles;
+  int clusters = sm_count / 2;
+  if (total_pairs < clusters) clusters = (int)total_pairs;
+  if (clusters < 1) return cudaSuccess;
+  if (dtype == VP3D_BF16) return launch_pair<VP3D_BF16>(tmA, tmB, tmC, p, clusters, stream);
+  return launch_pair<VP3D_F16>(tmA, tmB, tmC, p, clusters, stream);
+}
+
+}  // namespace vp3d
