@@ -284,12 +284,15 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
   }();
   if (use_pairs && vp3d::conv_gemm_pair_supported(a->dtype, a->block_n, a->w_mn_major, p) &&
       (use_pairs == 2 || total_tiles >= 2LL * dev->sm_count)) {
-    CUtensorMap tmBh;
-    cuuint64_t dims[2] = {(cuuint64_t)a->k_total, (cuuint64_t)a->n_pad};
-    cuuint64_t strides[1] = {(cuuint64_t)(a->k_total * eb)};
-    cuuint32_t box[2] = {(cuuint32_t)kblk, (cuuint32_t)(a->block_n / 2)};
-    if (int rc = encode_map(&tmBh, a->dtype, 2, a->w, dims, strides, box, "weights (half tile)")) return rc;
-    cudaError_t e2 = vp3d::launch_conv_gemm_pair(a->dtype, tmA, tmBh, tmC, p, dev->sm_count, static_cast<cudaStream_t>(stream));
+    CUtensorMap tmBh = tmB;    // MN-major: the same [64 k-rows][64 columns] boxes, two per CTA
+    if (!a->w_mn_major) {
+      cuuint64_t dims[2] = {(cuuint64_t)a->k_total, (cuuint64_t)a->n_pad};
+      cuuint64_t strides[1] = {(cuuint64_t)(a->k_total * eb)};
+      cuuint32_t box[2] = {(cuuint32_t)kblk, (cuuint32_t)(a->block_n / 2)};
+      if (int rc = encode_map(&tmBh, a->dtype, 2, a->w, dims, strides, box, "weights (half tile)")) return rc;
+    }
+    cudaError_t e2 = vp3d::launch_conv_gemm_pair(a->dtype, a->w_mn_major, tmA, tmBh, tmC, p, dev->sm_count,
+                                                 static_cast<cudaStream_t>(stream));
     if (e2 != cudaSuccess) return cuda_fail(e2, "conv_gemm_pair launch");
     return VP3D_OK;
   }

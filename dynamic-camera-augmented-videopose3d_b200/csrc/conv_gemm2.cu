@@ -11,10 +11,10 @@
 // commits; both CTAs run the usual 8-warp epilogue on their own 128 TMEM lanes, and the follower's epilogue warps
 // arrive remotely on the leader's accumulator-empty barrier.
 //
-// Scope: 16-bit operands, K-major weights, 16-bit output through TMA stores, at most 1024 output channels when a
-// scale / shift is applied (the whole per-channel table sits in shared memory because a pair changes column tile from
-// tile to tile). Everything else (training statistics, fp32 output, streaming offsets, MN-major weights) stays on
-// conv_gemm_kernel.
+// Scope: 16-bit operands (K-major weights: forward; MN-major: data gradient), 16-bit output through TMA stores, train-
+// mode statistics, at most 1024 output channels when a scale / shift is applied (the whole per-channel table sits in
+// shared memory because a pair changes column tile from tile to tile). fp32 output (shrink layer), streaming offsets
+// and TF32 stay on conv_gemm_kernel, as do launches of less than two waves.
 #include "ptx.cuh"
 #include "kernels.h"
 
@@ -75,13 +75,25 @@ __device__ __forceinline__ PairTile decode_pair(int pt, const ConvGemmParams& p,
   return c;
 }
 
-template <int DT>
+// MN-major SWIZZLE_128B weight operand (the forward-packed weights read as W^T by the data-gradient GEMM): 64-column
+// groups `lbo` bytes apart, 8-row groups 1024 B apart (see conv_gemm.cu)
+__device__ __forceinline__ uint64_t mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+template <int DT, bool BMN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmC, const ConvGemmParams p) {
   using F = Fmt<DT>;
   constexpr int kElemsPerKBlock = kKBytes / 2;
-  constexpr uint32_t kIdesc = make_instr_desc(F::kFormat, 2 * kBM, kBN);
+  constexpr uint32_t kIdesc = make_instr_desc(F::kFormat, 2 * kBM, kBN) | (BMN ? (1u << 16) : 0u);
 
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) {
@@ -153,7 +165,15 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           uint8_t* sa = smem + stage * kStageBytes;
           tma_load_3d_2cta(sa, &tmA, full_leader, kc * kElemsPerKBlock, tc.t0 + p.a_row_off + tap * p.tap_row_step,
                            tc.seq);
-          tma_load_2d_2cta(sa + kABytes, &tmB, full_leader, kb * kElemsPerKBlock, tc.n0 * kBN + rank * (kBN / 2));
+          if (BMN) {
+            // k-rows kc*64.. of the [c_out][taps * c_in] weights, this CTA's 128 columns of the tap's column tile
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+              tma_load_2d_2cta(sa + kABytes + g * 8192, &tmB, full_leader,
+                               tap * p.b_tap_col_step + tc.n0 * kBN + rank * (kBN / 2) + g * 64, kc * kElemsPerKBlock);
+          } else {
+            tma_load_2d_2cta(sa + kABytes, &tmB, full_leader, kb * kElemsPerKBlock, tc.n0 * kBN + rank * (kBN / 2));
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -178,9 +198,11 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
           const uint64_t adesc = make_kmajor_sw128_desc(sa);
-          const uint64_t bdesc = make_kmajor_sw128_desc(sa + kABytes);
+          const uint64_t bdesc = BMN ? mnmajor_sw128_desc(sa + kABytes, 8192) : make_kmajor_sw128_desc(sa + kABytes);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k)   // 32 bytes of K: +2 in the address field (K-major), 16 k-rows = 2048 B (MN-major)
+            umma_f16_ss_2cta(d_tmem, adesc + 2 * k, bdesc + (BMN ? (uint64_t)(128 * k) : (uint64_t)(2 * k)), kIdesc,
+                             (kb | k) != 0);
           umma_commit_2cta(&empty_bar[stage], 3);
           if (++stage == kStages) {
             stage = 0;
@@ -203,10 +225,29 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     unsigned out_buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    // train-mode BatchNorm statistics of the stored values, as in conv_gemm.cu: lane l owns column chunk * 32 + l of
+    // this warp's column half, accumulated in registers and flushed when the CTA changes column tile
+    float st_s[4] = {0.f, 0.f, 0.f, 0.f}, st_q[4] = {0.f, 0.f, 0.f, 0.f};
+    int stat_n0 = -1;
+    auto stat_flush = [&]() {
+      if (stat_n0 >= 0) {
+#pragma unroll
+        for (int ci = 0; ci < kChunks; ++ci) {
+          const int col = stat_n0 * kBN + (half * kChunks + ci) * 32 + lane;
+          atomicAdd(p.stat_sum + col, (double)st_s[ci]);
+          atomicAdd(p.stat_sqsum + col, (double)st_q[ci]);
+          st_s[ci] = st_q[ci] = 0.f;
+        }
+      }
+    };
     const uint32_t empty_leader0 = map_to_cta(smem_u32(&tmem_empty_bar[0]), 0);
     const uint32_t empty_leader1 = map_to_cta(smem_u32(&tmem_empty_bar[1]), 0);
     for (int pt = first_pair; pt < total_pairs; pt += pair_step) {
       const PairTile tc = decode_pair(pt, p, pairs_per_seq, rank);
+      if (p.stat_sum != nullptr && tc.n0 != stat_n0) {
+        stat_flush();
+        stat_n0 = tc.n0;
+      }
       const int t = tc.t0 + row;
       const bool row_ok = t < p.rows_out;
       const long long res_row = (long long)t * p.res_row_mul + p.res_row_off;
@@ -301,6 +342,27 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
         fence_proxy_async_smem();
         __syncwarp();
+        if (p.stat_sum != nullptr) {
+          int valid = p.rows_out - (tc.t0 + quad * 32);
+          valid = valid < 0 ? 0 : (valid > 32 ? 32 : valid);
+          float cs = 0.f, cq = 0.f;
+          const uint32_t col_off = (lane & 7) * 2, col_chunk = lane >> 3;
+#pragma unroll 8
+          for (int r = 0; r < valid; ++r) {
+            const uint16_t h = *reinterpret_cast<const uint16_t*>(my_stage + r * 64 + ((col_chunk ^ ((r >> 1) & 3)) << 4) +
+                                                                  col_off);
+            const float x = (DT == VP3D_F16) ? __half2float(__ushort_as_half(h)) : __uint_as_float((uint32_t)h << 16);
+            cs += x;
+            cq = fmaf(x, x, cq);
+          }
+          const int ci = c - half * kChunks;
+#pragma unroll
+          for (int k = 0; k < kChunks; ++k)
+            if (k == ci) {
+              st_s[k] += cs;
+              st_q[k] += cq;
+            }
+        }
         if (lane == 0) {
           tma_store_3d(&tmC, my_stage, col0, tc.t0 + quad * 32, tc.seq);
           tma_store_commit();
@@ -318,6 +380,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (p.stat_sum != nullptr) stat_flush();
     if (lane == 0) tma_store_wait_all<0>();
   }
 
@@ -331,12 +394,12 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
 }
 
-template <int DT>
+template <int DT, bool BMN>
 cudaError_t launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvGemmParams& p,
                         int clusters, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_pair_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_pair_kernel<DT, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -352,28 +415,37 @@ cudaError_t launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<DT>, tmA, tmB, tmC, p);
+  return cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<DT, BMN>, tmA, tmB, tmC, p);
 }
 
 }  // namespace
 
 bool conv_gemm_pair_supported(int dtype, int block_n, int w_mn_major, const ConvGemmParams& p) {
   if (dtype != VP3D_F16 && dtype != VP3D_BF16) return false;
-  if (block_n != kBN || w_mn_major || p.out_f32 || p.stat_sum != nullptr || p.dyn != nullptr) return false;
+  if (block_n != kBN || p.out_f32 || p.dyn != nullptr) return false;
+  (void)w_mn_major;
   if (p.shift != nullptr && p.n_tiles * kBN > kAffineCols) return false;
   return true;
 }
 
-// tmB must be encoded with a box of 128 output channels (half a column tile) x 64 elements of K
-cudaError_t launch_conv_gemm_pair(int dtype, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
-                                  const ConvGemmParams& p, int sm_count, cudaStream_t stream) {
+// K-major weights: tmB must be encoded with a box of 128 output channels (half a column tile) x 64 elements of K;
+// MN-major weights: the [64 k-rows][64 columns] map of the single-CTA kernel
+cudaError_t launch_conv_gemm_pair(int dtype, int w_mn_major, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                                  const CUtensorMap& tmC, const ConvGemmParams& p, int sm_count, cudaStream_t stream) {
   const int pairs_per_seq = (p.m_tiles_per_seq + 1) / 2;
   const long long total_pairs = (long long)p.a_seqs * pairs_per_seq * p.n_tiles;
   int clusters = sm_count / 2;
   if (total_pairs < clusters) clusters = (int)total_pairs;
   if (clusters < 1) return cudaSuccess;
-  if (dtype == VP3D_BF16) return launch_pair<VP3D_BF16>(tmA, tmB, tmC, p, clusters, stream);
-  return launch_pair<VP3D_F16>(tmA, tmB, tmC, p, clusters, stream);
+  // statistics: a cluster count that is a multiple of the column-tile count keeps every CTA on one column tile, so its
+  // per-channel sums stay in registers for the whole launch and are flushed once
+  if (p.stat_sum != nullptr && clusters > p.n_tiles) clusters -= clusters % p.n_tiles;
+  if (w_mn_major) {
+    if (dtype == VP3D_BF16) return launch_pair<VP3D_BF16, true>(tmA, tmB, tmC, p, clusters, stream);
+    return launch_pair<VP3D_F16, true>(tmA, tmB, tmC, p, clusters, stream);
+  }
+  if (dtype == VP3D_BF16) return launch_pair<VP3D_BF16, false>(tmA, tmB, tmC, p, clusters, stream);
+  return launch_pair<VP3D_F16, false>(tmA, tmB, tmC, p, clusters, stream);
 }
 
 }  // namespace vp3d

@@ -53,8 +53,8 @@ cudaError_t launch_conv_gemm(int dtype, int block_n, int w_mn_major, const CUten
 // CTA-pair variant (conv_gemm2.cu): tcgen05.mma.cta_group::2, each CTA stages its A tile and half of the weight tile.
 // `tmB_half` is the weight map with a box of 128 output channels x 64 elements of K.
 bool conv_gemm_pair_supported(int dtype, int block_n, int w_mn_major, const ConvGemmParams& p);
-cudaError_t launch_conv_gemm_pair(int dtype, const CUtensorMap& tmA, const CUtensorMap& tmB_half, const CUtensorMap& tmC,
-                                  const ConvGemmParams& p, int sm_count, cudaStream_t stream);
+cudaError_t launch_conv_gemm_pair(int dtype, int w_mn_major, const CUtensorMap& tmA, const CUtensorMap& tmB_half,
+                                  const CUtensorMap& tmC, const ConvGemmParams& p, int sm_count, cudaStream_t stream);
 
 // Launch parameters of wgrad_gemm_kernel (see wgrad.cu).
 struct WgradParams {
