@@ -31,7 +31,11 @@ constexpr int kABytes = kBM * kKBytes;            // 16 KB
 constexpr int kBHalfBytes = (kBN / 2) * kKBytes;  // 16 KB: this CTA's half of the weight tile
 constexpr int kStageBytes = kABytes + kBHalfBytes;
 constexpr int kOutBufBytes = kEpi * 32 * 64;      // one 32 x 32 staging tile (64 B rows) per epilogue warp
-constexpr int kOutStageBytes = 2 * kOutBufBytes;  // ring of two
+#ifndef VP3D_PAIR_OUTBUFS
+#define VP3D_PAIR_OUTBUFS 2
+#endif
+constexpr int kOutBufs = VP3D_PAIR_OUTBUFS;       // ring of TMA-store staging buffers per epilogue warp
+constexpr int kOutStageBytes = kOutBufs * kOutBufBytes;
 constexpr int kBarBytes = 512;
 constexpr int kAffineCols = 1024;
 constexpr int kAffineBytes = 2 * kAffineCols * 4;
@@ -266,7 +270,9 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           for (int j = 0; j < 4; ++j) r[j] = __ldg(r4 + j);
         }
       };
-      uint4 rcur[4], rnext[4];
+      // residual rows travel through registers two 32-column chunks ahead of their use (ncu: with one chunk of lead
+      // the first use of a residual register was the top stall of the kernel, 10 % of all warp samples)
+      uint4 rcur[4], rnext[4], rnext2[4];
       if (res_any) {
         const char* rp = reinterpret_cast<const char*>(static_cast<const uint16_t*>(p.res) + res_off + tc.n0 * kBN +
                                                        half * kChunks * 32);
@@ -275,6 +281,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           if (res_in_window(half * kChunks + k / 64)) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + k));
       }
       res_load(half * kChunks, rcur);
+      res_load(half * kChunks + 1, rnext);
 
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
@@ -283,7 +290,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       for (int c = half * kChunks; c < (half + 1) * kChunks; ++c) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + acc * kBN + c * 32 + (static_cast<uint32_t>(quad * 32) << 16), v);
-        if (c + 1 < (half + 1) * kChunks) res_load(c + 1, rnext);
+        if (c + 2 < (half + 1) * kChunks) res_load(c + 2, rnext2);
         tmem_wait_ld();
         const int col0 = tc.n0 * kBN + c * 32;
         float f[32];
@@ -330,9 +337,10 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           }
         }
         // staged SWIZZLE_64B tile -> one TMA store per warp per 32 columns (rows past the sequence end are clipped)
-        const unsigned b = out_buf++ & 1u;
+        const unsigned b = out_buf;
+        out_buf = out_buf + 1 == kOutBufs ? 0 : out_buf + 1;
         uint8_t* my_stage = out_stage + b * kOutBufBytes + epi * (32 * 64);
-        if (lane == 0) tma_store_wait_read<1>();
+        if (lane == 0) tma_store_wait_read<kOutBufs - 1>();   // the store that last used this buffer has drained it
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -368,7 +376,10 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           tma_store_commit();
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+        for (int j = 0; j < 4; ++j) {
+          rcur[j] = rnext[j];
+          rnext[j] = rnext2[j];
+        }
       }
       // this warp has read its share of the accumulator buffer: one arrival per warp on the LEADER's barrier
       tcgen05_fence_before();

@@ -220,8 +220,11 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
   return r;
 }
+// Default semantics (.release at CTA scope), as CUTLASS' ClusterBarrier::arrive(cta_id) does: what the remote waiter
+// needs ordered here is TMEM traffic, which tcgen05.fence::before_thread_sync covers. (.release.cluster compiles to
+// MEMBAR.ALL.GPU + ERRBAR and cost 9 % of the pair kernel's warp samples.)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
