@@ -7,7 +7,7 @@ One "step" = one eval forward of TemporalModel(17, 2, 17, [3,3,3,3,3], channels=
 sequences of 4096+242 frames (262,144 output frames) per GPU. Prints ONE JSON line (rank 0):
   value      frames/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e        same metric through the public module API with HOST (pinned) inputs and outputs inside the timed region
-  roofline   tensor-core roofline of the dominant kernel (conv_gemm_kernel), measured live with CUDA events
+  roofline   tensor-core roofline of the dominant kernel (conv_gemm_pair_kernel / conv_gemm_kernel), measured live with CUDA events
   cpu_baseline  the CPU oracle (a torch-CPU port of the reference stack) timed on this box's host cores
 With --impl reference the CPU port itself is the thing measured (the reference is Python and cannot travel to the GPU
 box; oracle/ is its restatement, pinned to the reference by tests/golden).
@@ -480,7 +480,7 @@ def bench_train(args, rank, world, dev, steps, warm):
                                       'generators.py:102-132), loss read back every step'},
         'gpu_launches': n_launch * steps,
         'loss_first_last': [float(first_loss), float(last_loss)],
-        'roofline': {'bound': 'tensor', 'kernel': 'conv_gemm_kernel + wgrad_gemm_kernel (%d launches per step)' % n_gemm,
+        'roofline': {'bound': 'tensor', 'kernel': 'conv_gemm_pair_kernel / conv_gemm_kernel + wgrad_gemm_kernel (%d launches per step)' % n_gemm,
                      'achieved': achieved, 'peak': peaks['sustained'], 'unit': 'TFLOP/s',
                      'frac': achieved / peaks['sustained'], 'peak_source': peaks['source'] + ', sustained dense bf16',
                      'traffic': load_traffic().get('train_gemm_avg_bytes_per_launch'),
@@ -698,7 +698,7 @@ def main():
         peak = peaks['sustained']
         if args.dtype == 'tf32':
             peak = peak / 2
-        roofline = {'bound': 'tensor', 'kernel': 'conv_gemm_kernel (tcgen05 implicit GEMM)', 'achieved': achieved,
+        roofline = {'bound': 'tensor', 'kernel': 'conv_gemm_pair_kernel (tcgen05 cta_group::2 implicit GEMM; expand tail / shrink on conv_gemm_kernel)', 'achieved': achieved,
                     'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
                     'frac_of_burst_peak': achieved / (peaks['burst'] / (2 if args.dtype == 'tf32' else 1)),
                     'peak_source': peaks['source'] + ', sustained dense bf16 (x0.5 for tf32)',
