@@ -64,9 +64,16 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 // Immutable per-device facts, resolved once (no other global state).
 struct DeviceInfo {
-  int sm_count = 0, cc_major = 0, cc_minor = 0;
+  int sm_count = 0, sm_real = 0, cc_major = 0, cc_minor = 0;
   bool ok = false;
 };
+// Upper bound on the SMs the persistent kernels size their grids for (0: all). Data-parallel training sets it a few
+// SMs below the device's count so that NCCL's all-reduce CTAs find free SMs next to a running GEMM instead of queueing
+// behind it (or, worse, a statically scheduled persistent GEMM queueing behind them).
+int g_sm_limit = [] {
+  const char* e = std::getenv("VP3D_SM_LIMIT");
+  return e != nullptr ? std::atoi(e) : 0;
+}();
 constexpr int kMaxDevices = 64;
 DeviceInfo g_dev[kMaxDevices];
 std::mutex g_dev_mu;
@@ -79,12 +86,13 @@ int device_info(DeviceInfo** out) {
   std::lock_guard<std::mutex> lock(g_dev_mu);
   DeviceInfo& d = g_dev[dev];
   if (!d.ok) {
-    if ((e = cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess ||
+    if ((e = cudaDeviceGetAttribute(&d.sm_real, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess ||
         (e = cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev)) != cudaSuccess ||
         (e = cudaDeviceGetAttribute(&d.cc_minor, cudaDevAttrComputeCapabilityMinor, dev)) != cudaSuccess)
       return cuda_fail(e, "cudaDeviceGetAttribute");
     d.ok = true;
   }
+  d.sm_count = (g_sm_limit > 0 && g_sm_limit < d.sm_real) ? g_sm_limit : d.sm_real;
   if (d.cc_major != 10)
     return fail(VP3D_ERR_UNSUPPORTED, "vp3d_b200 kernels are built for sm_100a only; device is sm_%d%d", d.cc_major,
                 d.cc_minor);
@@ -156,6 +164,12 @@ int vp3d_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   if (cc_major) *cc_major = maj;
   if (cc_minor) *cc_minor = min;
   if (maj != 10) return fail(VP3D_ERR_UNSUPPORTED, "device is sm_%d%d, need sm_100", maj, min);
+  return VP3D_OK;
+}
+
+int vp3d_set_sm_limit(int sms) {
+  std::lock_guard<std::mutex> lock(g_dev_mu);
+  g_sm_limit = sms > 0 ? sms : 0;
   return VP3D_OK;
 }
 

@@ -80,9 +80,16 @@ class GradSync:
 _active = None
 
 
-def enable_grad_sync(group=None):
-    """Install gradient averaging for every vp3d_b200 training backward of this process. Returns the GradSync."""
+def enable_grad_sync(group=None, reserve_sms=0):
+    """Install gradient averaging for every vp3d_b200 training backward of this process. Returns the GradSync.
+    `reserve_sms` > 0 sizes the persistent GEMM grids for that many SMs fewer than the device has, so that NCCL's
+    all-reduce CTAs (cap them with NCCL_MAX_CTAS <= reserve_sms before the process group is created) run beside the
+    backward GEMMs instead of taking turns with them."""
     global _active
+    if reserve_sms > 0 and torch.cuda.is_available():
+        from . import native
+        sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+        native.check(native.lib().vp3d_set_sm_limit(int(sms - reserve_sms)), 'set_sm_limit')
     _active = GradSync(group)
     training.grad_ready_hook = _active
     training.grad_finish_hook = _active.finish
@@ -92,6 +99,9 @@ def enable_grad_sync(group=None):
 def disable_grad_sync():
     global _active
     _active = None
+    if torch.cuda.is_available():
+        from . import native
+        native.check(native.lib().vp3d_set_sm_limit(0), 'set_sm_limit')
     training.grad_ready_hook = None
     training.grad_finish_hook = None
 

@@ -32,6 +32,10 @@ int vp3d_version(void);
 const char* vp3d_last_error(void);
 /* SM count and compute capability of the current device; VP3D_ERR_UNSUPPORTED unless cc == 10.x. */
 int vp3d_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Grid-size bound for the persistent kernels: they size their grids for at most `sms` SMs (<= 0: all of them; the
+ * environment variable VP3D_SM_LIMIT sets the initial value). Used by data-parallel training to leave a few SMs to
+ * NCCL's all-reduce kernels (vp3d_b200.ddp.enable_grad_sync(reserve_sms=...)); no reference counterpart. */
+int vp3d_set_sm_limit(int sms);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * K1  temporal convolution block: Conv1d (+ folded BatchNorm1d + ReLU + residual slice-add) as one implicit GEMM.
