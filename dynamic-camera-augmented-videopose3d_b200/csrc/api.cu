@@ -70,6 +70,13 @@ struct DeviceInfo {
 // Upper bound on the SMs the persistent kernels size their grids for (0: all). Data-parallel training sets it a few
 // SMs below the device's count so that NCCL's all-reduce CTAs find free SMs next to a running GEMM instead of queueing
 // behind it (or, worse, a statically scheduled persistent GEMM queueing behind them).
+// K1 on CTA pairs: 0 = never, 1 = launches of at least two waves of tiles (default), 2 = whenever the launch is
+// supported (tests on small shapes). Initial value from VP3D_K1_2CTA ("0" / "force").
+int g_pair_mode = [] {
+  const char* e = std::getenv("VP3D_K1_2CTA");
+  if (e == nullptr) return 1;
+  return std::strcmp(e, "force") == 0 ? 2 : (std::strcmp(e, "0") == 0 ? 0 : 1);
+}();
 int g_sm_limit = [] {
   const char* e = std::getenv("VP3D_SM_LIMIT");
   return e != nullptr ? std::atoi(e) : 0;
@@ -164,6 +171,12 @@ int vp3d_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   if (cc_major) *cc_major = maj;
   if (cc_minor) *cc_minor = min;
   if (maj != 10) return fail(VP3D_ERR_UNSUPPORTED, "device is sm_%d%d, need sm_100", maj, min);
+  return VP3D_OK;
+}
+
+int vp3d_set_pair_mode(int mode) {
+  if (mode < 0 || mode > 2) return fail(VP3D_ERR_INVALID, "pair mode must be 0 (off), 1 (auto) or 2 (whenever supported)");
+  g_pair_mode = mode;
   return VP3D_OK;
 }
 
@@ -289,13 +302,8 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
   int grid = (int)(total_tiles < dev->sm_count ? total_tiles : dev->sm_count);
   // a grid that is a multiple of n_tiles keeps every CTA on one column tile (weights and BN statistics stay put)
   if (grid > p.n_tiles && grid % p.n_tiles != 0) grid -= grid % p.n_tiles;
-  // CTA-pair kernel (cta_group::2) for the layers it covers. VP3D_K1_2CTA: "0" keeps everything on the single-CTA
-  // kernel, "force" uses pairs whenever supported (tests on small shapes), default: launches of at least two waves.
-  static const int use_pairs = [] {
-    const char* e = std::getenv("VP3D_K1_2CTA");
-    if (e == nullptr) return 1;
-    return std::strcmp(e, "force") == 0 ? 2 : (std::strcmp(e, "0") == 0 ? 0 : 1);
-  }();
+  // CTA-pair kernel (cta_group::2) for the layers it covers (g_pair_mode: vp3d_set_pair_mode / VP3D_K1_2CTA)
+  const int use_pairs = g_pair_mode;
   if (use_pairs && vp3d::conv_gemm_pair_supported(a->dtype, a->block_n, a->w_mn_major, p) &&
       (use_pairs == 2 || total_tiles >= 2LL * dev->sm_count)) {
     CUtensorMap tmBh = tmB;    // MN-major: the same [64 k-rows][64 columns] boxes, two per CTA

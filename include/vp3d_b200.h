@@ -36,6 +36,10 @@ int vp3d_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * environment variable VP3D_SM_LIMIT sets the initial value). Used by data-parallel training to leave a few SMs to
  * NCCL's all-reduce kernels (vp3d_b200.ddp.enable_grad_sync(reserve_sms=...)); no reference counterpart. */
 int vp3d_set_sm_limit(int sms);
+/* Which K1 kernel vp3d_conv_block_fwd launches: 0 = always the single-CTA kernel, 1 = the CTA-pair kernel
+ * (tcgen05.mma.cta_group::2) for supported launches of at least two waves of tiles (default), 2 = for every supported
+ * launch. Initial value from the environment variable VP3D_K1_2CTA ("0", "force"). */
+int vp3d_set_pair_mode(int mode);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * K1  temporal convolution block: Conv1d (+ folded BatchNorm1d + ReLU + residual slice-add) as one implicit GEMM.

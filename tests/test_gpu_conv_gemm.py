@@ -127,3 +127,68 @@ def test_argument_errors_are_reported_not_crashed():
         ops.conv_block(native.F16, a, (1, 128, 64, 64, 128 * 64), w, 1, 0, 48, 128, out, (256, 128 * 256))  # bad K
     with pytest.raises(AssertionError):
         ops.conv_block(native.F16, a, (1, 128, 64, 64, 128 * 64), w, 1, 0, 64, 128, out, (256, 128 * 256), block_n=96)
+
+
+@pytest.fixture
+def pair_mode():
+    """Selects the K1 kernel explicitly (vp3d_set_pair_mode) and restores the default afterwards."""
+    def set_mode(mode):
+        native.check(native.lib().vp3d_set_pair_mode(mode), 'set_pair_mode')
+    yield set_mode
+    set_mode(1)
+
+
+@pytest.mark.parametrize('dtype', ['fp16', 'bf16'])
+@pytest.mark.parametrize('seqs,rows,c,n,taps,step', [
+    (1, 128, 64, 256, 1, 0),        # one pair tile whose second CTA has no valid row at all
+    (1, 300, 256, 256, 1, 0),       # odd number of row tiles: the last pair's partner tile is out of range
+    (3, 200, 128, 512, 3, 5),       # dilated 3-tap, per-sequence pairs, 2 column tiles
+    (2, 700, 1024, 1024, 3, 81),    # the block-4 geometry of the 243-frame model (4 column tiles, affine table)
+    (1, 1500, 128, 1024, 1, 0),     # more pair tiles than clusters: several tiles per pair, column tile changes
+])
+def test_pair_kernel_matches_fp64_and_single_cta_kernel(pair_mode, dtype, seqs, rows, c, n, taps, step):
+    """conv_gemm_pair_kernel (tcgen05.mma.cta_group::2) forced on small shapes: against the fp64 contraction and,
+    bit for bit, against the single-CTA kernel (same MMA shapes per row, same epilogue arithmetic)."""
+    dt = DT[dtype]
+    td = ops.torch_dtype(dt)
+    g = torch.Generator(device='cpu').manual_seed(seqs * 1000 + rows + 7)
+    a = (torch.randn(seqs, rows, c, generator=g) * 0.5).to(td).cuda()
+    w = (torch.randn(n, taps * c, generator=g) / (taps * c) ** 0.5).to(td).cuda()
+    rows_out = rows - step * (taps - 1)
+    scale = (torch.rand(n, generator=g) + 0.5).cuda()
+    shift = (torch.randn(n, generator=g) * 0.1).cuda()
+    res = (torch.randn(seqs, rows + 2, n, generator=g) * 0.5).to(td).cuda()
+    outs = []
+    for mode in (0, 2):
+        pair_mode(mode)
+        out = torch.full((seqs, rows_out, n), float('nan'), dtype=td, device='cuda')
+        ops.conv_block(dt, a, (seqs, rows, c, c, rows * c), w, taps, step, c, rows_out, out, (n, rows_out * n),
+                       scale=scale, shift=shift, relu=True, res=res, res_view=(n, (rows + 2) * n, 1, 2))
+        torch.cuda.synchronize()
+        outs.append(out)
+    ref = _ref_conv(a.float(), w.float(), taps, step, rows_out)
+    ref = torch.relu(ref * scale.double().cpu() + shift.double().cpu()) + res.double().cpu()[:, 2:2 + rows_out]
+    got = outs[1].double().cpu()
+    assert torch.isfinite(got).all(), 'pair kernel left unwritten / non-finite outputs'
+    assert (got - ref).abs().max().item() < TOL[dtype]
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_sm_limit_changes_the_grid_not_the_result(pair_mode):
+    """vp3d_set_sm_limit (SMs left to NCCL under data-parallel training) only re-sizes the persistent grids."""
+    g = torch.Generator(device='cpu').manual_seed(77)
+    rows, c, n = 5000, 256, 512
+    a = (torch.randn(1, rows, c, generator=g) * 0.5).half().cuda()
+    w = (torch.randn(n, c, generator=g) / c ** 0.5).half().cuda()
+    outs = []
+    try:
+        for limit, mode in ((0, 1), (100, 1), (37, 2)):
+            native.check(native.lib().vp3d_set_sm_limit(limit), 'set_sm_limit')
+            pair_mode(mode)
+            out = torch.empty((1, rows, n), dtype=torch.float16, device='cuda')
+            ops.conv_block(native.F16, a, (1, rows, c, c, rows * c), w, 1, 0, c, rows, out, (n, rows * n), relu=True)
+            torch.cuda.synchronize()
+            outs.append(out)
+    finally:
+        native.check(native.lib().vp3d_set_sm_limit(0), 'set_sm_limit')
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
