@@ -197,7 +197,7 @@ def run_reference_arm(args, rank, world):
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 class LaunchTimer:
@@ -532,7 +532,23 @@ def bench_stream(args, rank, world, dev):
     return out
 
 
+_json_out = None
+
+
+def emit(obj):
+    """The ONE JSON line of the contract, on the process's real stdout."""
+    out = _json_out if _json_out is not None else sys.stdout
+    out.write(json.dumps(obj) + '\n')
+    out.flush()
+
+
 def main():
+    # stdout carries exactly one JSON line: everything else that writes to file descriptor 1 (NCCL's version banner at
+    # NCCL_DEBUG=WARN / VERSION, library chatter) is sent to stderr
+    global _json_out
+    sys.stdout.flush()
+    _json_out = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=50)
@@ -566,9 +582,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        # stdout carries ONE JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
-        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
 
     warm = max(args.warmup, 3)
@@ -581,7 +594,7 @@ def main():
         if rank == 0:
             tr.update({'n_gpus': world, 'steps': steps, 'warmup': warm, 'higher_is_better': True, 'vs_baseline': None,
                        'data': 'synthetic', 'clocks': sampler.stop()})
-            print(json.dumps(tr))
+            emit(tr)
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
@@ -739,7 +752,7 @@ def main():
                 train['cpu_baseline'] = {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
                                          'sample': sample}
             line['train'] = train
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
