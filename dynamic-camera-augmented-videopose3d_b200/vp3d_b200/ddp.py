@@ -17,7 +17,11 @@ import torch.distributed as dist
 
 from . import training
 
-LARGE_BYTES = 1 << 20
+import os
+
+# gradients of at least this many bytes are all-reduced on their own as soon as they exist; smaller ones share one flat
+# bucket at the end of the backward (VP3D_DDP_LARGE_BYTES overrides, e.g. a huge value = one exchange after the backward)
+LARGE_BYTES = int(os.environ.get('VP3D_DDP_LARGE_BYTES', 1 << 20))
 
 
 def shard_range(n_items, rank, world):

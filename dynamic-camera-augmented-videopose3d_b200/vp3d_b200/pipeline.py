@@ -5,6 +5,7 @@ The reference moves every batch with a blocking .cuda() and reads results back w
 
 * infer_host(): a batch of sequences held in pinned host memory is cut into chunks of sequences; chunk i+1 is uploaded
   and chunk i-1 is downloaded while chunk i runs through the model (three streams, event-ordered, two buffers each).
+* HostInferPipeline: the same across batches -- nothing drains between two batches of a serving loop.
 * HostPrefetcher: double-buffered upload of training batches -- the next batch travels while the current step runs.
 """
 import torch
@@ -57,6 +58,72 @@ def infer_host(model, x_host, y_host=None, chunk_seqs=8):
     down.synchronize()
     main.synchronize()
     return y_host
+
+
+class HostInferPipeline:
+    """infer_host without the drain at the end of every batch: streams, device staging buffers and the chunk counter
+    persist between calls, so the first upload of batch i+1 and the last download of batch i overlap with compute of
+    the neighbouring batch. `submit(x_host, y_host)` enqueues one batch and returns a CUDA event that fires when its
+    last result byte is in `y_host` (pinned); `infer()` = submit + wait. Successive calls must pass distinct `y_host`
+    buffers for as long as an earlier result is still being read."""
+
+    def __init__(self, model, chunk_seqs=8):
+        assert not model.training, 'HostInferPipeline runs the eval-mode (folded BatchNorm) path'
+        self.model = model
+        self.dev = next(model.parameters()).device
+        self.chunk_seqs = chunk_seqs
+        self.up, self.down = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+        self.xbuf = None
+        self.x_free = [torch.cuda.Event() for _ in range(2)]
+        self.x_ready = [torch.cuda.Event() for _ in range(2)]
+        self.n_chunks = 0        # chunks issued so far, over all batches (buffer = chunk number % 2)
+
+    def submit(self, x_host, y_host):
+        model, dev, cs = self.model, self.dev, self.chunk_seqs
+        n = x_host.shape[0]
+        main = torch.cuda.current_stream(dev)
+        if self.xbuf is None or tuple(self.xbuf[0].shape[1:]) != tuple(x_host.shape[1:]):
+            torch.cuda.synchronize(dev)
+            self.xbuf = [torch.empty((cs,) + tuple(x_host.shape[1:]), dtype=torch.float32, device=dev) for _ in range(2)]
+            self.n_chunks = 0
+        chunks = [(lo, min(lo + cs, n)) for lo in range(0, n, cs)]
+
+        def upload(k, lo, hi):
+            b = k % 2
+            with torch.cuda.stream(self.up):
+                if k >= 2:
+                    self.up.wait_event(self.x_free[b])
+                self.xbuf[b][:hi - lo].copy_(x_host[lo:hi], non_blocking=True)
+                self.x_ready[b].record(self.up)
+
+        k0 = self.n_chunks
+        upload(k0, *chunks[0])
+        with torch.no_grad():
+            for i, (lo, hi) in enumerate(chunks):
+                k = k0 + i
+                b = k % 2
+                if i + 1 < len(chunks):
+                    upload(k + 1, *chunks[i + 1])
+                main.wait_event(self.x_ready[b])
+                y = model(self.xbuf[b][:hi - lo])
+                self.x_free[b].record(main)
+                done = torch.cuda.Event()
+                done.record(main)
+                with torch.cuda.stream(self.down):
+                    self.down.wait_event(done)
+                    y_host[lo:hi].copy_(y, non_blocking=True)
+                y.record_stream(self.down)
+        self.n_chunks = k0 + len(chunks)
+        landed = torch.cuda.Event()
+        landed.record(self.down)
+        return landed
+
+    def infer(self, x_host, y_host=None):
+        if y_host is None:
+            t_out = x_host.shape[1] - (self.model.receptive_field() - 1)
+            y_host = torch.empty((x_host.shape[0], t_out, self.model.num_joints_out, 3), dtype=torch.float32).pin_memory()
+        self.submit(x_host, y_host).synchronize()
+        return y_host
 
 
 class HostPrefetcher:

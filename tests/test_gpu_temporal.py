@@ -207,3 +207,27 @@ def test_streaming_with_per_frame_camera():
         outs = [st.step_world(Xd[:, t].contiguous(), qd[:, t].contiguous(), td[:, t].contiguous(), camd).cpu()
                 for t in range(T)]
     assert rel_err(torch.stack(outs, dim=1), full) < 5e-4
+
+
+def test_host_pipelines_return_what_the_model_returns():
+    """pipeline.infer_host and pipeline.HostInferPipeline (pinned host buffers in and out, upload / compute / download
+    overlapped, the latter also across batches) against the plain module call, bit for bit."""
+    from vp3d_b200 import pipeline
+    fw = [3, 3, 3]
+    sd = otm.init_state(17, 2, 17, fw, channels=256, seed=71)
+    m = TemporalModel(17, 2, 17, fw, channels=256)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(72)
+    batches = [(torch.rand(11, 200, 17, 2, generator=g) * 2 - 1).pin_memory() for _ in range(3)]
+    with torch.no_grad():
+        want = [m(x.cuda()).cpu() for x in batches]
+    got = pipeline.infer_host(m, batches[0], chunk_seqs=4)
+    assert torch.equal(got, want[0])
+    pipe = pipeline.HostInferPipeline(m, chunk_seqs=4)     # 11 sequences -> chunks of 4, 4, 3; three batches in flight
+    outs = [torch.empty(11, 200 - 26, 17, 3).pin_memory() for _ in batches]
+    events = [pipe.submit(x, y) for x, y in zip(batches, outs)]
+    for ev, y, w in zip(events, outs, want):
+        ev.synchronize()
+        assert torch.equal(y, w)
+    assert torch.equal(pipe.infer(batches[1]), want[1])
