@@ -296,7 +296,36 @@ def bench_train(args, rank, world, dev, steps, warm):
         Xc = world_to_camera(Wd[:, mid:mid + 1].contiguous(), qd[:, mid:mid + 1].contiguous(),
                              td[:, mid:mid + 1].contiguous())
         tgt = (Xc - Xc[:, :, :1]).contiguous()
-    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+    class LossReader:
+        """Reads every step's loss back to the host (run.py:481 `.item()`) one step late: the copy of step i's loss is
+        enqueued behind step i, and the host waits for it only after it has enqueued step i + 1 -- so the GPU never
+        idles while the host blocks, and every step's loss is still read inside the timed region (`drain`)."""
+
+        def __init__(self):
+            self.bufs = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+            self.evs = [torch.cuda.Event() for _ in range(2)]
+            self.i = 0
+            self.last = None
+
+        def push(self, loss):
+            k = self.i % 2
+            self.bufs[k].copy_(loss, non_blocking=True)
+            self.evs[k].record()
+            if self.i > 0:
+                self.evs[1 - k].synchronize()
+                self.last = float(self.bufs[1 - k])
+            self.i += 1
+            return self.last
+
+        def drain(self):
+            if self.i > 0:
+                k = (self.i - 1) % 2
+                self.evs[k].synchronize()
+                self.last = float(self.bufs[k])
+            self.i = 0
+            return self.last
+
+    reader = LossReader()
 
     def step(W, q, t, cam):
         _, x2d = world_to_image(W, q, t, cam, return_camera_space=False)
@@ -326,14 +355,13 @@ def bench_train(args, rank, world, dev, steps, warm):
 
     def step_e2e():
         # this step's batch was uploaded (pinned host -> device, side stream) while the previous step computed; the
-        # next one starts travelling now. Every step still moves its own 57.8 MB and reads its loss back.
+        # next one starts travelling now. Every step still moves its own 57.8 MB and reads its loss back (the host waits
+        # for step i's loss after it has enqueued step i + 1).
         b, bufs = pre.get()
         pre.put((Wh, qh, th, camh))
         loss = graphed(bufs) if graphed is not None else step(*bufs)
         pre.release(b)
-        loss_host.copy_(loss, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(loss_host)
+        return reader.push(loss)
 
     def barrier():
         torch.cuda.synchronize()
@@ -378,11 +406,13 @@ def bench_train(args, rank, world, dev, steps, warm):
 
     for _ in range(2):
         step_e2e()
+    reader.drain()
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for _ in range(steps):
         step_e2e()
+    reader.drain()        # the last step's loss is on the host before the region ends
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
@@ -410,9 +440,7 @@ def bench_train(args, rank, world, dev, steps, warm):
             loss.backward()
             opt.step()
             loss = loss.detach()
-        loss_host.copy_(loss, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(loss_host)
+        return reader.push(loss)
 
     graphed_2d = None
     if use_graph:
@@ -420,11 +448,13 @@ def bench_train(args, rank, world, dev, steps, warm):
         graphed_2d = GraphedTrainStep(model, opt, mpjpe, (b2d0,), b3d0)
     for _ in range(3):
         step_feeder()
+    reader.drain()
     barrier()
     e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e4.record()
     for _ in range(steps):
         step_feeder()
+    reader.drain()
     e5.record()
     barrier()
     ms_feed = e4.elapsed_time(e5)
@@ -477,7 +507,7 @@ def bench_train(args, rank, world, dev, steps, warm):
                               'ms_per_step': ms_feed / steps, 'h2d_bytes_per_step': batch * 16, 'd2h_bytes_per_step': 4,
                               'note': 'vp3d_b200.feeder.DeviceWindowFeeder: sequences resident in HBM, windows gathered, '
                                       'edge-padded and projected by one kernel per step (replaces ChunkedGenerator, '
-                                      'generators.py:102-132), loss read back every step'},
+                                      'generators.py:102-132), loss read back every step (one step late)'},
         'gpu_launches': n_launch * steps,
         'loss_first_last': [float(first_loss), float(last_loss)],
         'roofline': {'bound': 'tensor', 'kernel': 'conv_gemm_pair_kernel / conv_gemm_kernel + wgrad_gemm_kernel (%d launches per step)' % n_gemm,
