@@ -1,6 +1,6 @@
-// K1 on CTA pairs (cta_group::2): the eval-mode temporal-convolution block -- nn.Conv1d + folded BatchNorm + ReLU +
-// residual slice-add (common/models/TemporalModel.py:126-138) -- as ONE tcgen05.mma of M = 256 per K step over two CTAs
-// of a 2-cluster.
+// K1 on CTA pairs (cta_group::2): the temporal-convolution block -- nn.Conv1d + folded BatchNorm + ReLU + residual
+// slice-add (common/models/TemporalModel.py:126-138,188-198), the raw train-mode output with BatchNorm statistics, and
+// the data gradient of autograd's conv backward -- as ONE tcgen05.mma of M = 256 per K step over two CTAs of a 2-cluster.
 //
 // Same math, layouts and epilogue as conv_gemm.cu; what changes is who stages what. A pair owns two adjacent 128-row
 // tiles of one 256-wide column tile. Each CTA loads its own A tile (16 KB per stage) and HALF of the shared weight tile
@@ -431,10 +431,10 @@ cudaError_t launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
 
 }  // namespace
 
-bool conv_gemm_pair_supported(int dtype, int block_n, int w_mn_major, const ConvGemmParams& p) {
+bool conv_gemm_pair_supported(int dtype, int block_n, int /*w_mn_major: both weight layouts are covered*/,
+                              const ConvGemmParams& p) {
   if (dtype != VP3D_F16 && dtype != VP3D_BF16) return false;
   if (block_n != kBN || p.out_f32 || p.dyn != nullptr) return false;
-  (void)w_mn_major;
   if (p.shift != nullptr && p.n_tiles * kBN > kAffineCols) return false;
   return true;
 }
