@@ -192,3 +192,60 @@ def test_gpu_eval_metrics_match_the_numpy_reference_semantics():
         assert abs(got - want) < 5e-6 * max(1.0, want), (J, got, want)
     # NumPy inputs keep the reference's host semantics
     assert abs(closs.p_mpjpe(p2.copy(), t2.copy()) - float(z['p_mpjpe'])) < 1e-6
+
+
+@pytest.mark.parametrize('S,T,J,linear,per_frame', [
+    (1, 1, 2, False, False),      # one frame, smallest joint count the frame kernel takes
+    (2, 3, 5, True, False),       # fewer frames than one 4-frame tile: ragged tile only
+    (3, 50, 31, False, True),     # CMU-sized skeleton, intrinsics per frame
+    (1, 9, 300, False, False),    # very wide frames: tiles of 4 frames
+    (4, 243, 17, False, False),   # several full tiles per CTA + a ragged last tile
+    (2, 17, 1, False, False),     # J = 1 is left to the generic kernel
+])
+def test_frame_kernel_edge_shapes_against_the_exact_path(S, T, J, linear, per_frame):
+    """project_frames_kernel (bulk-copy staged tiles, VP3D_PT_FAST arithmetic) against the un-contracted generic kernel
+    (exact=True, itself pinned to the reference's golden values) on ragged / tiny / wide shapes."""
+    rng = np.random.default_rng(S * 1000 + T * 10 + J)
+    X = (rng.standard_normal((S, T, J, 3)) * 0.4 + np.array([0, 0, 4.0])).astype(np.float32)
+    q = rng.standard_normal((S, T, 4)).astype(np.float32) * 0.05 + np.array([1, 0, 0, 0], dtype=np.float32)
+    q = (q / np.linalg.norm(q, axis=-1, keepdims=True)).astype(np.float32)
+    t = (rng.standard_normal((S, T, 3)) * 0.2).astype(np.float32)
+    base = np.array([2.2900989, 2.2875624, 0.025083065, 0.028902981, -0.20709892, 0.24777518, -0.0030751503,
+                     -0.00097569887, -0.0014244716], dtype=np.float32)
+    cams = (base * (1 + 0.01 * rng.standard_normal((S, T, 1) if per_frame else (S, 1)))).astype(np.float32)
+    args = [torch.from_numpy(v).cuda() for v in (X, q, t, cams)]
+    c3, p2 = cam.world_to_image(*args, linear=linear)
+    c3e, p2e = cam.world_to_image(*args, linear=linear, exact=True)
+    np.testing.assert_allclose(c3.cpu().numpy(), c3e.cpu().numpy(), atol=PROJ_TOL)
+    np.testing.assert_allclose(p2.cpu().numpy(), p2e.cpu().numpy(), atol=PROJ_TOL)
+    _, p2_only = cam.world_to_image(*args, linear=linear, return_camera_space=False)
+    assert torch.equal(p2_only, p2)
+
+
+def test_frame_kernel_special_values_follow_the_reference():
+    """camera.py:59 clamps x/z to [-1, 1]: z = 0 saturates (x != 0) or gives NaN (0/0), z < 0 flips the sign; the frame
+    kernel's reciprocal-multiply must land on the same values as the exact path (project_to_2d semantics)."""
+    J = 8
+    X = np.zeros((1, 4, J, 3), np.float32)
+    X[..., 2] = 4.0
+    X[0, 0, 0] = [1.0, -2.0, 0.0]        # x/0 -> +inf -> 1, y/0 -> -inf -> -1
+    X[0, 0, 1] = [0.0, 0.0, 0.0]         # 0/0 -> NaN
+    X[0, 1, 2] = [3.0, 1.0, -2.0]        # behind the camera: ratios change sign, x saturates at -1
+    X[0, 2, 3] = [np.inf, 1.0, 2.0]      # inf / z -> inf -> 1
+    X[0, 3, 4] = [np.nan, 1.0, 2.0]      # NaN propagates through the clamp
+    q = np.tile(np.array([1, 0, 0, 0], np.float32), (1, 4, 1))      # identity pose: camera space == world space
+    t = np.zeros((1, 4, 3), np.float32)
+    cams = np.array([[2.29, 2.2876, 0.0251, 0.0289, -0.2071, 0.2478, -0.0031, -0.00098, -0.0014]], np.float32)
+    args = [torch.from_numpy(v).cuda() for v in (X, q, t, cams)]
+    _, p2 = cam.world_to_image(*args)
+    _, p2e = cam.world_to_image(*args, exact=True)
+    # the reference composition: qrot by the (identity) quaternion spreads an inf / NaN coordinate to the whole point
+    # (0 * inf inside the cross products, quaternion.py:21-24), exactly as the rotation-matrix form of the frame kernel
+    with np.errstate(invalid='ignore', divide='ignore'):
+        xc = ocam.world_to_camera(X.reshape(4, J, 3), q.reshape(4, 4), t.reshape(4, 3))
+        want = ocam.project_to_2d(xc.reshape(1, 4 * J, 3), cams).reshape(1, 4, J, 2)
+    got, gote = p2.cpu().numpy(), p2e.cpu().numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(np.isnan(gote), np.isnan(want))
+    ok = ~np.isnan(want)
+    np.testing.assert_allclose(got[ok], want[ok], atol=PROJ_TOL)
+    np.testing.assert_allclose(gote[ok], want[ok], atol=PROJ_TOL)
