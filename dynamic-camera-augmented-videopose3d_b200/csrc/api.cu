@@ -315,8 +315,13 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
     }
     cudaError_t e2 = vp3d::launch_conv_gemm_pair(a->dtype, a->w_mn_major, tmA, tmBh, tmC, p, dev->sm_count,
                                                  static_cast<cudaStream_t>(stream));
-    if (e2 != cudaSuccess) return cuda_fail(e2, "conv_gemm_pair launch");
-    return VP3D_OK;
+    if (e2 == cudaSuccess) return VP3D_OK;
+    // a cluster launch can be refused where the plain one is not (MPS / partitioned devices): not an error of the call --
+    // the single-CTA kernel below covers every case, and the pair kernel is left alone for the rest of the process
+    (void)cudaGetLastError();
+    g_pair_mode = 0;
+    fprintf(stderr, "vp3d_b200: CTA-pair launch refused (%s); using the single-CTA kernel from now on\n",
+            cudaGetErrorString(e2));
   }
   cudaError_t e = vp3d::launch_conv_gemm(a->dtype, a->block_n, a->w_mn_major, tmA, tmB, tmC, p, grid, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "conv_gemm launch");
