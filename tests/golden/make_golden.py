@@ -199,6 +199,53 @@ def generator_cases():
     np.savez_compressed(os.path.join(HERE, 'generator.npz'), **out)
 
 
+def unchunked_generator_cases():
+    """The reference's UnchunkedGenerator (generators.py:140-205) on synthetic dynamic-camera sequences: per sequence
+    the 2-D input it yields (edge-padded by (pad + causal_shift, pad - causal_shift)), the padded K @ [R|t] matrices and
+    the 3-D target, where the generator's inputs are themselves made with the reference's own camera functions from
+    world-space joints + one quaternion / translation per frame (qinverse, qrot, project_to_2d; run.py:72-74 for the
+    root-relative target). This is the end-to-end expectation for vp3d_b200.feeder.DeviceSequenceFeeder."""
+    from common.generators import UnchunkedGenerator
+    rng = np.random.default_rng(123)
+    lens = [45, 70, 33]
+    J = 17
+    intr = np.array([1.5625, 1.5625, 0.0, 0.0, 0, 0, 0, 0, 0], np.float32)      # CMUMocapDataset.py:53-69, normalised
+    out = {'lens': np.array(lens), 'intrinsics': intr}
+    cams, p3, p2 = [], [], []
+    for i, n in enumerate(lens):
+        X = (np.cumsum(rng.normal(0, 0.02, (n, J, 3)), axis=0) + np.array([0, 0, 4.0])).astype(np.float32)
+        q = np.array([1, 0, 0, 0], np.float32) + np.cumsum(rng.normal(0, 0.004, (n, 4)), axis=0).astype(np.float32)
+        q = (q / np.linalg.norm(q, axis=-1, keepdims=True)).astype(np.float32)
+        t = np.cumsum(rng.normal(0, 0.01, (n, 3)), axis=0).astype(np.float32)
+        qt, tt = torch.from_numpy(q), torch.from_numpy(t)
+        qi = r_qinverse(qt)                                                        # (n, 4)
+        xc = r_qrot(qi[:, None, :].expand(n, J, 4).contiguous(), torch.from_numpy(X) - tt[:, None, :])
+        x2 = rcam.project_to_2d(xc, torch.from_numpy(intr)[None].expand(n, 9).contiguous())
+        # extrinsics [R | -R c] of the same pose: columns of R = qrot(qinverse(q), e_k)
+        eye = torch.eye(3)
+        R = torch.stack([r_qrot(qi, eye[k].expand(n, 3).contiguous()) for k in range(3)], dim=-1)      # (n, 3, 3)
+        tc = r_qrot(qi, -tt)
+        E = torch.cat([R, tc[:, :, None]], dim=-1).numpy().astype(np.float32)
+        cams.append({'extrinsics': E, 'intrinsics': {'focal_length': (float(intr[0]), float(intr[1])),
+                                                     'center': (float(intr[2]), float(intr[3]))},
+                     'cam_velocity': rng.normal(0, 1, 3), 'cam_acceleration': rng.normal(0, 1, 3),
+                     'cam_angular_velocity': rng.normal(0, 1, 3), 'cam_angular_acceleration': rng.normal(0, 1, 3)})
+        xcn = xc.numpy()
+        p3.append((xcn - xcn[:, :1]).astype(np.float32))                           # run.py:72-74
+        p2.append(x2.numpy().astype(np.float32))
+        out['world_%d' % i], out['q_%d' % i], out['t_%d' % i] = X, q, t
+    for pad, shift, tag in ((13, 0, 'a'), (13, 13, 'b')):
+        gen = UnchunkedGenerator(cams, p3, p2, pad=pad, causal_shift=shift)
+        assert gen.num_frames() == sum(lens)
+        for i, (bc, b3, b2, info) in enumerate(gen.next_epoch()):
+            out['cam_%s_%d' % (tag, i)] = bc.astype(np.float32)
+            out['b3d_%s_%d' % (tag, i)] = b3.astype(np.float32)
+            out['b2d_%s_%d' % (tag, i)] = b2.astype(np.float32)
+            assert info['cam_velocity'] is cams[i]['cam_velocity']
+        out['params_' + tag] = np.array([pad, shift])
+    np.savez_compressed(os.path.join(HERE, 'generator_unchunked.npz'), **out)
+
+
 def loss_cases():
     g = torch.Generator().manual_seed(77)
     out = {}
@@ -236,6 +283,7 @@ if __name__ == '__main__':
     camera_cases()
     camera_grad_cases()
     generator_cases()
+    unchunked_generator_cases()
     loss_cases()
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):

@@ -126,3 +126,22 @@ def test_sequence_feeder_drives_evaluation():
             pred = m(b2d)
             assert pred.shape == b3d.shape        # run.py:711-734: one pose per frame of the sequence
             assert np.isfinite(mpjpe(pred, b3d).item())
+
+
+@pytest.mark.parametrize('tag', ['a', 'b'])
+def test_sequence_feeder_against_the_reference_unchunked_generator(tag):
+    """DeviceSequenceFeeder against what the reference's own UnchunkedGenerator yields for the same sequences
+    (tests/golden/generator_unchunked.npz, made by importing common/generators.py and the reference camera functions):
+    padded 2-D input, root-relative 3-D target, padded K @ [R|t] matrices."""
+    from conftest import load_golden
+    from vp3d_b200.feeder import DeviceSequenceFeeder
+    z = load_golden('generator_unchunked.npz')
+    n = len(z['lens'])
+    pad, shift = [int(v) for v in z['params_' + tag]]
+    X, Q, T = [z['world_%d' % i] for i in range(n)], [z['q_%d' % i] for i in range(n)], [z['t_%d' % i] for i in range(n)]
+    cam = np.tile(z['intrinsics'], (n, 1))
+    fd = DeviceSequenceFeeder(X, Q, T, cam, pad=pad, causal_shift=shift, want_cameras=True)
+    for i, (cams, b3d, b2d, _info) in enumerate(fd.next_epoch()):
+        np.testing.assert_allclose(b2d.cpu().numpy(), z['b2d_%s_%d' % (tag, i)], atol=1e-5)
+        np.testing.assert_allclose(b3d.cpu().numpy(), z['b3d_%s_%d' % (tag, i)], atol=2e-6)
+        np.testing.assert_allclose(cams.cpu().numpy(), z['cam_%s_%d' % (tag, i)], atol=1e-5)

@@ -135,3 +135,22 @@ def test_projection_gradient_oracle():
         np.testing.assert_allclose(g, z[key], atol=2e-6)
     assert (z['grad'][0, 0, 0] == 0).all()                      # both ratios clamped
     assert z['grad'][0, 0, 2, 0] == 0 and z['grad'][0, 0, 2, 1] != 0
+
+
+def test_unchunked_generator_composition_against_reference_generator():
+    """The host restatement the GPU sequence-feeder tests use -- np.pad(..., 'edge') of the oracle's per-frame
+    world_to_camera / project_to_2d, K @ [R | -R c] -- against the batches the reference's own UnchunkedGenerator yields
+    (tests/golden/generator_unchunked.npz, generators.py:178-205)."""
+    from oracle import camera as ocam
+    z = load_golden('generator_unchunked.npz')
+    intr = z['intrinsics']
+    for tag in ('a', 'b'):
+        pad, shift = [int(v) for v in z['params_' + tag]]
+        for i in range(len(z['lens'])):
+            X, q, t = z['world_%d' % i], z['q_%d' % i], z['t_%d' % i]
+            xc = ocam.world_to_camera(X, q, t)
+            p2 = ocam.project_to_2d(xc[None], intr[None])[0]
+            want2 = np.pad(p2, ((pad + shift, pad - shift), (0, 0), (0, 0)), 'edge')
+            np.testing.assert_allclose(want2[None], z['b2d_%s_%d' % (tag, i)], atol=2e-6)
+            np.testing.assert_allclose((xc - xc[:, :1])[None], z['b3d_%s_%d' % (tag, i)], atol=2e-6)
+            assert z['cam_%s_%d' % (tag, i)].shape == (1, X.shape[0] + 2 * pad, 3, 4)
