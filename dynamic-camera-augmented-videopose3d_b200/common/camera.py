@@ -35,7 +35,15 @@ def _rigid(X, R, t, mode):
     assert X.shape[-1] == 3
     assert R.shape[-1] == 4 and t.shape[-1] == 3
     n_pts = X.numel() // 3
+    if R.dim() == 1 and t.dim() > 1:
+        # static orientation, one translation per frame: the reference computes X - t by broadcasting, so t is
+        # (..., 1, 3) there; give every frame its own copy of R and take the per-frame path
+        tt = t.squeeze(-2) if (t.dim() == X.dim() and t.shape[-2] == 1) else t
+        assert tuple(tt.shape[:-1]) == tuple(X.shape[:-2]), \
+            'a per-frame translation needs one row per frame of X (shape X.shape[:-2] + (3,) or (..., 1, 3))'
+        R, t = R.expand(tuple(X.shape[:-2]) + (4,)).contiguous(), tt.contiguous()
     if R.dim() == 1:
+        assert t.dim() == 1, 'a static camera is one quaternion (4,) and one translation (3,)'
         pts_per_q = max(n_pts, 1)
     else:
         assert tuple(R.shape[:-1]) == tuple(X.shape[:-2]) and tuple(t.shape[:-1]) == tuple(X.shape[:-2]), \

@@ -66,6 +66,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 struct DeviceInfo {
   int sm_count = 0, sm_real = 0, cc_major = 0, cc_minor = 0;
   bool ok = false;
+  bool pair_refused = false;   // THIS device refused a cluster launch once (MPS / partitioned GPU): single-CTA kernel from then on
 };
 // Upper bound on the SMs the persistent kernels size their grids for (0: all). Data-parallel training sets it a few
 // SMs below the device's count so that NCCL's all-reduce CTAs find free SMs next to a running GEMM instead of queueing
@@ -303,7 +304,7 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
   // a grid that is a multiple of n_tiles keeps every CTA on one column tile (weights and BN statistics stay put)
   if (grid > p.n_tiles && grid % p.n_tiles != 0) grid -= grid % p.n_tiles;
   // CTA-pair kernel (cta_group::2) for the layers it covers (g_pair_mode: vp3d_set_pair_mode / VP3D_K1_2CTA)
-  const int use_pairs = g_pair_mode;
+  const int use_pairs = dev->pair_refused ? 0 : g_pair_mode;
   if (use_pairs && vp3d::conv_gemm_pair_supported(a->dtype, a->block_n, a->w_mn_major, p) &&
       (use_pairs == 2 || total_tiles >= 2LL * dev->sm_count)) {
     CUtensorMap tmBh = tmB;    // MN-major: the same [64 k-rows][64 columns] boxes, two per CTA
@@ -317,10 +318,11 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
                                                  static_cast<cudaStream_t>(stream));
     if (e2 == cudaSuccess) return VP3D_OK;
     // a cluster launch can be refused where the plain one is not (MPS / partitioned devices): not an error of the call --
-    // the single-CTA kernel below covers every case, and the pair kernel is left alone for the rest of the process
+    // the single-CTA kernel below covers every case. The refusal is remembered for THIS device only; other devices of
+    // the process and the global mode (vp3d_set_pair_mode) are left alone.
     (void)cudaGetLastError();
-    g_pair_mode = 0;
-    fprintf(stderr, "vp3d_b200: CTA-pair launch refused (%s); using the single-CTA kernel from now on\n",
+    dev->pair_refused = true;
+    fprintf(stderr, "vp3d_b200: CTA-pair launch refused on this device (%s); it uses the single-CTA kernel from now on\n",
             cudaGetErrorString(e2));
   }
   cudaError_t e = vp3d::launch_conv_gemm(a->dtype, a->block_n, a->w_mn_major, tmA, tmB, tmC, p, grid, static_cast<cudaStream_t>(stream));

@@ -488,13 +488,10 @@ template <int DT, int BN, bool BMN>
 static cudaError_t launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                               const ConvGemmParams& p, int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;  // per-process; idempotent, so a benign race at worst repeats the call
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<DT, BN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};   // one bit per device ordinal
+  if (cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(conv_gemm_kernel<DT, BN, BMN>), Cfg::kSmemBytes,
+                                        attr_done))
+    return e;
   conv_gemm_kernel<DT, BN, BMN><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
   return cudaGetLastError();
 }

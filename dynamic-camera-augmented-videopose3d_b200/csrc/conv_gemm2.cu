@@ -408,12 +408,9 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 template <int DT, bool BMN>
 cudaError_t launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvGemmParams& p,
                         int clusters, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_pair_kernel<DT, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};   // one bit per device ordinal
+  if (cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(conv_gemm_pair_kernel<DT, BMN>), kSmemBytes, attr_done))
+    return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * clusters);
   cfg.blockDim = dim3(kThreads);

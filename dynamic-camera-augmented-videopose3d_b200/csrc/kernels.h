@@ -1,6 +1,7 @@
 // Internal declarations shared by the kernel translation units and the C-ABI layer (api.cu).
 #pragma once
 
+#include <atomic>
 #include <cstdint>
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -8,6 +9,19 @@
 #include "../../include/vp3d_b200.h"
 
 namespace vp3d {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE property of a kernel: `done` (one per kernel
+// instantiation) holds one bit per device ordinal, so a process that drives several GPUs raises the limit on each of them.
+inline cudaError_t set_max_smem_once(const void* func, int bytes, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+  return e;
+}
 
 // Launch parameters of conv_gemm_kernel (see conv_gemm.cu). All strides are in elements of the named buffer.
 struct ConvGemmParams {

@@ -118,31 +118,39 @@ __device__ __forceinline__ BnChannel bn_channel_stats(double sum, double sqsum, 
   return r;
 }
 
-__global__ void __launch_bounds__(256)
+// One block walks all channels (c_pad <= a few thousand): the step counter is read by every thread BEFORE thread 0 ticks
+// it, which the cumulative-average mode (momentum < 0: nn.BatchNorm1d(momentum=None), factor 1 / num_batches_tracked
+// after the tick) needs and a multi-block grid could not order.
+__global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sqsum, double inv_n, float unbias,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
                    float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ nbt,
                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                    float* __restrict__ invstd_out, int c, int c_pad) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0 && nbt != nullptr) *nbt += 1;
-  if (i >= c_pad) return;
-  if (i >= c) {
-    scale[i] = 0.f;
-    shift[i] = 0.f;
-    mean_out[i] = 0.f;
-    invstd_out[i] = 0.f;
-    return;
+  if (momentum < 0.f) {
+    const long long seen = nbt != nullptr ? *nbt : 0;
+    momentum = 1.f / (float)(seen + 1);
+    __syncthreads();
   }
-  const BnChannel ch = bn_channel_stats(sum[i], sqsum[i], inv_n, eps);
-  const float sc = gamma[i] * ch.invstd;
-  scale[i] = sc;
-  shift[i] = beta[i] - ch.mean * sc;
-  mean_out[i] = ch.mean;
-  invstd_out[i] = ch.invstd;
-  if (running_mean != nullptr) {
-    running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * ch.mean;
-    running_var[i] = (1.f - momentum) * running_var[i] + momentum * (ch.var * unbias);   // unbiased: n / (n - 1)
+  if (threadIdx.x == 0 && nbt != nullptr) *nbt += 1;
+  for (int i = threadIdx.x; i < c_pad; i += blockDim.x) {
+    if (i >= c) {
+      scale[i] = 0.f;
+      shift[i] = 0.f;
+      mean_out[i] = 0.f;
+      invstd_out[i] = 0.f;
+      continue;
+    }
+    const BnChannel ch = bn_channel_stats(sum[i], sqsum[i], inv_n, eps);
+    const float sc = gamma[i] * ch.invstd;
+    scale[i] = sc;
+    shift[i] = beta[i] - ch.mean * sc;
+    mean_out[i] = ch.mean;
+    invstd_out[i] = ch.invstd;
+    if (running_mean != nullptr) {
+      running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * ch.mean;
+      running_var[i] = (1.f - momentum) * running_var[i] + momentum * (ch.var * unbias);   // unbiased: n / (n - 1)
+    }
   }
 }
 
@@ -666,7 +674,7 @@ cudaError_t launch_bn_finalize(const double* sum, const double* sqsum, long long
                                long long* nbt, float* scale, float* shift, float* mean, float* invstd, int c, int c_pad,
                                cudaStream_t stream) {
   const double n = (double)count;
-  bn_finalize_kernel<<<(c_pad + 255) / 256, 256, 0, stream>>>(sum, sqsum, 1.0 / n,
+  bn_finalize_kernel<<<1, c_pad >= 1024 ? 1024 : ((c_pad + 31) / 32) * 32, 0, stream>>>(sum, sqsum, 1.0 / n,
                                                               count > 1 ? (float)(n / (n - 1.0)) : 1.f, gamma, beta, eps, momentum,
                                                               running_mean, running_var, nbt, scale, shift, mean,
                                                               invstd, c, c_pad);

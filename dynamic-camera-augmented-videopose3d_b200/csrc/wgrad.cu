@@ -250,13 +250,10 @@ template <int DT, int BN, int BM>
 static cudaError_t launch_wg(const CUtensorMap& tmA, const CUtensorMap& tmB, const WgradParams& p, int grid,
                              cudaStream_t stream) {
   using Cfg = WgradCfg<BN, BM>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel<DT, BN, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};   // one bit per device ordinal
+  if (cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(wgrad_gemm_kernel<DT, BN, BM>), Cfg::kSmemBytes,
+                                        attr_done))
+    return e;
   wgrad_gemm_kernel<DT, BN, BM><<<grid, kWgThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
   return cudaGetLastError();
 }

@@ -22,14 +22,15 @@ from . import native, ops
 
 
 def build_pairs(lengths, chunk_length):
-    """(seq_idx, start_frame, end_frame) lineage tuples, exactly as generators.py:39-45 builds them."""
-    pairs = []
-    for i, n in enumerate(lengths):
-        n_chunks = (n + chunk_length - 1) // chunk_length
-        offset = (n_chunks * chunk_length - n) // 2
-        bounds = np.arange(n_chunks + 1) * chunk_length - offset
-        pairs += zip(np.repeat(i, len(bounds) - 1), bounds[:-1], bounds[1:])
-    return pairs
+    """(n_chunks, 3) int64 table of (sequence, first frame, one-past-last frame). A sequence of n frames is cut into
+    ceil(n / chunk_length) chunks centred on it (the cut overhangs both ends by half of the excess), which is the
+    lineage rule of generators.py:39-45; the table is what RandomState.permutation shuffles row-wise each epoch."""
+    tables = []
+    for seq, n in enumerate(lengths):
+        k = -(-int(n) // chunk_length)
+        first = np.arange(k, dtype=np.int64) * chunk_length - (k * chunk_length - int(n)) // 2
+        tables.append(np.stack([np.full(k, seq, dtype=np.int64), first, first + chunk_length], axis=1))
+    return np.concatenate(tables) if tables else np.zeros((0, 3), dtype=np.int64)
 
 
 class DeviceWindowFeeder:
@@ -56,13 +57,15 @@ class DeviceWindowFeeder:
         self.batch_size, self.chunk_length, self.pad, self.causal_shift = batch_size, chunk_length, pad, causal_shift
         self.num_batches = (len(pairs) + batch_size - 1) // batch_size
         self.random = np.random.RandomState(random_seed)
-        self.shuffle, self.endless, self.state = shuffle, endless, None
+        self.shuffle, self.endless = shuffle, endless
+        self._resume = None      # (next batch, this epoch's order) of an interrupted endless epoch
         self.root_relative, self.linear, self.want_cameras = root_relative, linear, want_cameras
         self.dev = dev
         self.window = chunk_length + 2 * pad
         # pinned staging for the per-batch index upload (two buffers: the copy of batch i+1 may overlap batch i)
         self._idx_host = [torch.empty((batch_size, 2), dtype=torch.int64).pin_memory() for _ in range(2)]
         self._idx_dev = [torch.empty((batch_size, 2), dtype=torch.int64, device=dev) for _ in range(2)]
+        self._idx_copied = [None, None]   # event recorded behind the H2D copy that last read each pinned buffer
         self._flip = 0
 
     # -- generator protocol of the reference ------------------------------------------------------------------
@@ -75,11 +78,14 @@ class DeviceWindowFeeder:
     def set_random_state(self, random):
         self.random = random
 
-    def next_pairs(self):
-        if self.state is None:
-            pairs = self.random.permutation(self.pairs) if self.shuffle else np.asarray(self.pairs)
-            return 0, pairs
-        return self.state
+    def epoch_order(self):
+        """(first batch, chunk table in this epoch's order): a fresh draw from the RandomState (generators.py:85), or
+        the remainder of an endless epoch that was interrupted (checkpoint / resume, run.py:436-445)."""
+        if self._resume is not None:
+            return self._resume
+        return 0, (self.random.permutation(self.pairs) if self.shuffle else self.pairs)
+
+    next_pairs = epoch_order     # the reference generator's name for it
 
     def assemble(self, chunks):
         """chunks: (n, 3) int array of (seq_i, start_3d, end_3d) -> (cams or None, batch_3d, batch_2d) on the device."""
@@ -88,10 +94,14 @@ class DeviceWindowFeeder:
         b = self._flip
         self._flip ^= 1
         host = self._idx_host[b]
-        host[:n, 0] = torch.from_numpy(chunks[:, 0].astype(np.int64))
-        host[:n, 1] = torch.from_numpy(chunks[:, 1].astype(np.int64))
+        if self._idx_copied[b] is not None:
+            # a host that runs batches ahead of the GPU must not overwrite indices a pending copy still has to read
+            self._idx_copied[b].synchronize()
+        host[:n] = torch.from_numpy(np.ascontiguousarray(chunks[:, :2], dtype=np.int64))
         idx = self._idx_dev[b]
         idx[:n].copy_(host[:n], non_blocking=True)
+        ev = self._idx_copied[b] = self._idx_copied[b] or torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
         seq32 = idx[:n, 0].to(torch.int32).contiguous()
         start = idx[:n, 1].contiguous()
         J = self.joints
@@ -113,18 +123,16 @@ class DeviceWindowFeeder:
     def next_epoch(self):
         """Yields (batch_cam, batch_3d, batch_2d) like ChunkedGenerator.next_epoch (generators.py:102-132), as fp32 CUDA
         tensors (batch_cam is None unless want_cameras)."""
-        enabled = True
-        while enabled:
-            start_idx, pairs = self.next_pairs()
-            for b_i in range(start_idx, self.num_batches):
-                chunks = pairs[b_i * self.batch_size:(b_i + 1) * self.batch_size]
+        bs = self.batch_size
+        while True:
+            first, order = self.epoch_order()
+            for b in range(first, self.num_batches):
                 if self.endless:
-                    self.state = (b_i + 1, pairs)
-                yield self.assemble(chunks)
-            if self.endless:
-                self.state = None
-            else:
-                enabled = False
+                    self._resume = (b + 1, order)
+                yield self.assemble(order[b * bs:(b + 1) * bs])
+            self._resume = None
+            if not self.endless:
+                return
 
 
 class DeviceSequenceFeeder(DeviceWindowFeeder):

@@ -171,3 +171,20 @@ def device_info():
     sm, maj, mnr = C.c_int(), C.c_int(), C.c_int()
     check(lib().vp3d_device_info(C.byref(sm), C.byref(maj), C.byref(mnr)), 'device_info')
     return sm.value, maj.value, mnr.value
+
+
+_sm_counts = {}
+
+
+def sm_count(device=None):
+    """SMs of `device` (a torch device / index; default: the current CUDA device), asked from the library once per
+    device. Host-side tile heuristics size against this, never against a literal."""
+    import torch
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    n = _sm_counts.get(idx)
+    if n is None:
+        with torch.cuda.device(idx):
+            n = _sm_counts[idx] = device_info()[0]
+    return n

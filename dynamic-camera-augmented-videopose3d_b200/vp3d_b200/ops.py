@@ -367,6 +367,20 @@ def col_stats(dt, z, stats):
     return stats
 
 
+def _bn_momentum(bn):
+    """nn.BatchNorm1d.momentum for the kernels: None (cumulative moving average, factor 1 / num_batches_tracked) is
+    passed as a negative value and resolved on the device from the counter."""
+    return -1.0 if bn.momentum is None else float(bn.momentum)
+
+
+def _bump_running_stats(bn):
+    """The kernels write running_mean / running_var / num_batches_tracked through raw pointers; tell autograd's version
+    counters, which key the folded eval-mode cache (temporal.packed_for)."""
+    for b in (bn.running_mean, bn.running_var, bn.num_batches_tracked):
+        if b is not None:
+            torch.autograd.graph.increment_version(b)
+
+
 def bn_finalize(stat, count, bn, c_pad, update_running=True):
     """stat: double [2][c_pad] (sum, sum of squares) -> (scale, shift, mean, invstd) fp32 [c_pad]; updates the
     nn.BatchNorm1d container's running statistics in place like F.batch_norm(training=True)."""
@@ -374,14 +388,15 @@ def bn_finalize(stat, count, bn, c_pad, update_running=True):
     dev = stat.device
     out = torch.empty((4, c_pad), dtype=torch.float32, device=dev)
     track = update_running and bn.track_running_stats and bn.running_mean is not None
-    momentum = 0.0 if bn.momentum is None else float(bn.momentum)
     with torch.cuda.device(dev):
         check(lib().vp3d_bn_finalize(_ptr(stat[0]), _ptr(stat[1]), int(count), _ptr(f32c(bn.weight.detach())),
-                                     _ptr(f32c(bn.bias.detach())), float(bn.eps), momentum,
+                                     _ptr(f32c(bn.bias.detach())), float(bn.eps), _bn_momentum(bn),
                                      _ptr(bn.running_mean) if track else None, _ptr(bn.running_var) if track else None,
                                      _ptr(bn.num_batches_tracked) if track else None,
                                      _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), c, c_pad, _stream()),
               'bn_finalize')
+    if track:
+        _bump_running_stats(bn)
     return out[0], out[1], out[2], out[3]
 
 
@@ -403,7 +418,10 @@ def bn_finalize_act_fwd(dt, z, stat, count, bn, seqs, rows_per_seq, drop, res=No
     out = torch.empty((4, c_pad), dtype=torch.float32, device=dev)
     a = torch.empty_like(z)
     track = update_running and bn.track_running_stats and bn.running_mean is not None
-    momentum = 0.0 if bn.momentum is None else float(bn.momentum)
+    if bn.momentum is None:
+        raise RuntimeError('vp3d_b200: bn_finalize_act_fwd needs a numeric BatchNorm momentum (momentum=None, the '
+                           'cumulative average, is served by bn_finalize + bn_act_fwd)')
+    momentum = float(bn.momentum)
     with torch.cuda.device(dev):
         check(lib().vp3d_bn_finalize_act_fwd(
             dt, _ptr(z), _ptr(stat[0]), _ptr(stat[1]), int(count), _ptr(f32c(bn.weight.detach())),
@@ -411,6 +429,8 @@ def bn_finalize_act_fwd(dt, z, stat, count, bn, seqs, rows_per_seq, drop, res=No
             _ptr(bn.running_var) if track else None, _ptr(bn.num_batches_tracked) if track else None,
             _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), c, _ptr(res), seqs, rows_per_seq, res_seq_rows,
             res_row_mul, res_row_off, c_pad, C.byref(drop), _ptr(a), _stream()), 'bn_finalize_act_fwd')
+    if track:
+        _bump_running_stats(bn)
     return a, out[0], out[1], out[2], out[3]
 
 

@@ -64,12 +64,24 @@ class CausalStream:
         self.h_last = torch.empty((self.S_pad, C_), dtype=td, device=dev)
         self.y = torch.empty((self.S, pk.n_out), dtype=torch.float32, device=dev)
         # small M: 64-wide column tiles give 4x more CTAs than the 256-wide tile of the batch path
-        self.block_n = 64 if (self.S_pad // 128) * (C_ // N_TILE) * 4 <= 148 else N_TILE
+        self.block_n = 64 if (self.S_pad // 128) * (C_ // N_TILE) * 4 <= native.sm_count(dev) else N_TILE
         self.use_graph = use_graph
         self.graph = None
         self._warm = 0
 
+    def refresh_weights(self):
+        """Re-resolves the packed eval operands (folded BatchNorm) from the module's CURRENT parameters and buffers. The
+        pack is looked up once per stream object because checking ~60 tensor versions would cost a fifth of a 0.13 ms
+        frame; call this (or reset()) after load_state_dict / further training of the module. A captured graph that
+        baked the old operands' addresses is dropped and re-captured."""
+        pk = packed_for(self.model, self.dt)
+        if pk is not self.pk:
+            self.pk = pk
+            self.graph = None
+            self._warm = 0
+
     def reset(self):
+        self.refresh_weights()
         for r in self.rings:
             r.zero_()
         self.step_dev.zero_()

@@ -120,7 +120,7 @@ def _run_layer(dt, x, n, t_in, c_in_pad, w, plan, scale, shift, relu, res=None, 
         # few output tiles (the 1f model's last blocks: 3 or 1 frames per sample): 64-wide column tiles give 4x more
         # CTAs than SMs would otherwise be left idle by 128 x 256 tiles
         tiles = a_view[0] * ((rows_out + 127) // 128) * (n_pad // N_TILE)
-        if tiles * 4 <= 148:          # the narrow tiles still fit in one wave
+        if tiles * 4 <= native.sm_count(x.device):          # the narrow tiles still fit in one wave
             block_n = N_TILE_NARROW
     ops.conv_block(dt, x, a_view, w, g_taps, g_step, k_per_tap, rows_out, y, out_view, block_n=block_n,
                    scale=scale, shift=shift, relu=relu, res=res, res_view=res_view, out_f32=out_f32, n_valid=cols,

@@ -109,7 +109,7 @@ def _forward_stack(model, x, dt):
         L.count = count
         L.drop = _dropout_for(model, idx, step)
         L.res_of, L.res_t, L.res_mul, L.res_off = res, res_t, res_mul, res_off
-        if fuse_bn_finalize:
+        if fuse_bn_finalize and bn.momentum is not None:
             a, L.scale, L.shift, L.mean, L.invstd = ops.bn_finalize_act_fwd(
                 dt, z, stats, count, bn, n, t_out, L.drop, res=res, res_seq_rows=res_t, res_row_mul=res_mul,
                 res_row_off=res_off)
@@ -194,7 +194,7 @@ def _data_grad(dt, L, dz, n, c_pad, fan_in=None, fan_rows=0, fan_off=0, fan_mul=
     cin_pad = L.c_in_pad
     g_in = torch.empty((n, L.t_in, cin_pad), dtype=dz.dtype, device=dz.device)
     block_n = 256 if cin_pad % 256 == 0 else 64
-    if block_n == 256 and ((n * L.t_out + 127) // 128) * (taps * cin_pad // 256) * 4 <= 148:
+    if block_n == 256 and ((n * L.t_out + 127) // 128) * (taps * cin_pad // 256) * 4 <= native.sm_count(dz.device):
         block_n = 64    # few tiles: narrower column tiles keep all SMs busy (while they still fit in one wave)
     if s > 1 or taps == 1:
         if s > 1 and L.t_in != taps * L.t_out:
@@ -230,11 +230,24 @@ class _StackTrainFn(torch.autograd.Function):
         ctx.model, ctx.dt, ctx.layers, ctx.a_last, ctx.t_last, ctx.c_pad = model, dt, layers, a_last, t_last, c_pad
         ctx.n = x.shape[0]
         ctx.params = params
+        # The backward reads the packed weight operands again (data gradient). They are plain buffers that
+        # FusedAdam.step() rewrites in place, outside autograd's version tracking, so the parameter versions of this
+        # forward are stamped here and checked in the backward.
+        ctx.weight_versions = [(L.conv.weight, L.conv.weight._version) for L in layers]
+        ctx.weight_versions.append((model.shrink.weight, model.shrink.weight._version))
         return y
 
     @staticmethod
     def backward(ctx, dy):
         model, dt, layers, n, c_pad = ctx.model, ctx.dt, ctx.layers, ctx.n, ctx.c_pad
+        if layers is None:
+            raise RuntimeError('vp3d_b200: the saved activations of this forward were released by its first backward '
+                               '(a second backward / retain_graph=True is not supported on the fused training path)')
+        for w, version in ctx.weight_versions:
+            if w._version != version:
+                raise RuntimeError('vp3d_b200: a convolution weight was modified (optimizer.step()?) between the forward '
+                                   'and its backward; the data gradient would be taken with the NEW weights. Run '
+                                   'backward() before step(), as run.py:485-487 does.')
         hook = grad_ready_hook
         grads = {}
         # The weight gradient of layer L (tensor-core bound) depends only on dz_L and the saved input; the critical path
@@ -333,6 +346,10 @@ def forward_train(model, x):
     if dt == native.TF32:
         raise RuntimeError('vp3d_b200: the training path runs fp16 or bf16 operands (fp32 accumulation); '
                            'set model.operand_dtype / VP3D_DTYPE to fp16 or bf16')
+    if x.requires_grad and torch.is_grad_enabled():
+        raise RuntimeError('vp3d_b200: the training path does not produce a gradient wrt the 2-D input keypoints (the '
+                           'reference never asks for one, run.py:458-485); detach() the input or keep the module that '
+                           'produces it out of the autograd graph')
     x = ops.f32c(x)
     if not torch.is_grad_enabled():
         with torch.no_grad():
