@@ -130,7 +130,7 @@ def oracle_state():
     return otm.init_state(17, 2, 17, FW, channels=1024, seed=1234)
 
 
-def cpu_port_frames_per_s(seqs=4, out_frames=4096, repeats=3):
+def cpu_port_frames_per_s(seqs=4, out_frames=4096, repeats=5):
     """The CPU oracle (torch-CPU port of the reference eval forward) on all host threads; bounded sample."""
     from oracle import temporal_model as otm
     cores = os.cpu_count() or 1
@@ -170,7 +170,14 @@ def cpu_port_train_samples_per_s(batch=32, repeats=2):
         batch, repeats, torch.__version__)
 
 
+REF_SAMPLE = (4, 4096)     # sequences x output frames of one CPU step: the sample cpu_baseline times as well
+
+
 def run_reference_arm(args, rank, world):
+    """--impl reference: the CPU port of the reference (oracle/temporal_model.py; the reference is a Python tree that
+    cannot travel to the GPU box) on all host threads. A step = one eval forward over REF_SAMPLE (the same bounded
+    sample `cpu_baseline` uses); every step is timed on its own and `value` is taken from the MEDIAN step so that one
+    noisy step on a shared host does not move the number (ms_per_step_mean is printed beside it)."""
     if rank != 0:
         return
     steps, warm = max(args.steps, 1), max(args.warmup, 0)
@@ -178,23 +185,29 @@ def run_reference_arm(args, rank, world):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = oracle_state()
-    seqs, out_frames = 1, 2048
+    seqs, out_frames = REF_SAMPLE
     x = make_inputs(0, seqs, out_frames + RF - 1)
+    times = []
     with torch.no_grad():
         for _ in range(warm):
             otm.forward(sd, x, FW)
-        t0 = time.perf_counter()
         for _ in range(steps):
+            t0 = time.perf_counter()
             otm.forward(sd, x, FW)
-        dt = time.perf_counter() - t0
-    value = steps * seqs * out_frames / dt
-    sample = '%d seq x %d output frames per step (bounded sample of the 64 x 4096 workload)' % (seqs, out_frames)
+            times.append(time.perf_counter() - t0)
+    med = sorted(times)[len(times) // 2]
+    value = seqs * out_frames / med
+    sample = '%d seq x %d output frames per step (bounded sample of the 64 x 4096 workload), median of %d steps, ' \
+             '%d torch threads' % (seqs, out_frames, steps, torch.get_num_threads())
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps,
-            'warmup': warm, 'ms_per_step': dt / steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'warmup': warm, 'ms_per_step': med * 1e3, 'ms_per_step_mean': sum(times) / len(times) * 1e3,
+            'ms_per_step_min_max': [min(times) * 1e3, max(times) * 1e3],
+            'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': 'TemporalModel 3,3,3,3,3 (243f) eval, J=17, 1024 ch; CPU port of the reference '
                                    '(oracle/temporal_model.py, torch CPU conv1d/batch_norm), ' + sample},
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'threads': torch.get_num_threads(),
+                             'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     emit(line)

@@ -39,7 +39,7 @@ cudaError_t launch_velocity_error(const float* pred, const float* tgt, long long
 cudaError_t launch_n_mpjpe_bwd(const float* pred, const float* tgt, const float* grad_out, long long n_poses, int J,
                                float* grad_pred, int sm_count, cudaStream_t stream);
 cudaError_t launch_pack_rows(int dtype, const float* src, void* dst, long long rows, int c, int c_pad, int sm_count,
-                             cudaStream_t stream);
+                             cudaStream_t stream, int ones_col = -1);
 cudaError_t launch_pack_weight(int dtype, const float* w, void* dst, int c_out, int c_in, int taps, int rows_pad,
                                int k_pad_per_tap, int transpose, int sm_count, cudaStream_t stream,
                                const float* row_scale = nullptr);
@@ -123,6 +123,15 @@ EncodeTiledFn get_encode() {
       g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   });
   return g_encode;
+}
+
+vp3d::DropoutParams drop_of(const vp3d_dropout* d) {
+  vp3d::DropoutParams dp;
+  dp.p = d ? d->p : 0.f;
+  dp.seed = d ? d->seed : 0ull;
+  dp.stream = d ? d->stream : 0ull;
+  dp.step_counter = d ? d->step_counter : nullptr;
+  return dp;
 }
 
 int elem_bytes(int dtype) { return dtype == VP3D_TF32 ? 4 : 2; }
@@ -229,6 +238,15 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
   if (a->res_cols < 0 || a->res_col_off < 0 || a->res_cols % 32 != 0 || a->res_col_off % 32 != 0 ||
       a->res_col_off + a->res_cols > a->n_pad)
     return fail(VP3D_ERR_INVALID, "residual column window must be 32-aligned and inside n_pad");
+  const bool want_drop = a->drop != nullptr && a->drop->p > 0.f;
+  const bool want_epi = want_drop || a->side_mode != 0;
+  if (want_drop && a->drop->p >= 1.f) return fail(VP3D_ERR_INVALID, "dropout p must be in [0, 1)");
+  if (a->side_mode < 0 || a->side_mode > 2) return fail(VP3D_ERR_INVALID, "side_mode must be 0, 1 or 2");
+  if (a->side_mode != 0) {
+    if (a->side == nullptr || (reinterpret_cast<uintptr_t>(a->side) & 15) || (a->side_row_stride * 2) % 16 != 0 ||
+        (a->side_seq_stride * 2) % 16 != 0 || a->side_rows <= 0)
+      return fail(VP3D_ERR_INVALID, "side input must be 16-byte aligned with 16-byte strides and side_rows > 0");
+  }
 
   DeviceInfo* dev = nullptr;
   if (int rc = device_info(&dev)) return rc;
@@ -265,6 +283,17 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
     if (int rc = encode_map(&tmC, a->dtype, 3, a->out, dims, strides, box, "output", CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
   }
 
+  // epilogue side input: the view [n_pad columns][side_rows][sequences] read in the output's 32 x 32 boxes
+  CUtensorMap tmS;
+  memset(&tmS, 0, sizeof(tmS));
+  if (a->side_mode != 0) {
+    cuuint64_t dims[3] = {(cuuint64_t)a->n_pad, (cuuint64_t)a->side_rows, (cuuint64_t)a->a_seqs};
+    cuuint64_t strides[2] = {(cuuint64_t)(a->side_row_stride * 2), (cuuint64_t)(a->side_seq_stride * 2)};
+    if (a->a_seqs == 1) strides[1] = (cuuint64_t)(a->side_rows * a->side_row_stride * 2);
+    cuuint32_t box[3] = {32, 32, 1};
+    if (int rc = encode_map(&tmS, a->dtype, 3, a->side, dims, strides, box, "side input", CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+  }
+
   vp3d::ConvGemmParams p;
   memset(&p, 0, sizeof(p));
   p.a_seqs = (int)a->a_seqs;
@@ -297,6 +326,10 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
   p.out_round_tf32 = a->out_round_tf32;
   p.stat_sum = a->stat_sum;
   p.stat_sqsum = a->stat_sqsum;
+  if (want_drop) p.drop = drop_of(a->drop);
+  p.side_mode = a->side_mode;
+  p.side_row_off = a->side_row_off;
+  p.side_scale = a->side_scale;
 
   const long long total_tiles = (long long)p.a_seqs * p.m_tiles_per_seq * p.n_tiles;
   if (total_tiles > 0x7fffffffLL) return fail(VP3D_ERR_INVALID, "too many tiles");
@@ -304,9 +337,13 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
   // a grid that is a multiple of n_tiles keeps every CTA on one column tile (weights and BN statistics stay put)
   if (grid > p.n_tiles && grid % p.n_tiles != 0) grid -= grid % p.n_tiles;
   // CTA-pair kernel (cta_group::2) for the layers it covers (g_pair_mode: vp3d_set_pair_mode / VP3D_K1_2CTA)
-  const int use_pairs = dev->pair_refused ? 0 : g_pair_mode;
-  if (use_pairs && vp3d::conv_gemm_pair_supported(a->dtype, a->block_n, a->w_mn_major, p) &&
-      (use_pairs == 2 || total_tiles >= 2LL * dev->sm_count)) {
+  // (fused dropout / side input exist in the pair kernel only: such a launch takes it whatever the mode and tile count)
+  const int use_pairs = dev->pair_refused ? 0 : (want_epi ? 2 : g_pair_mode);
+  const bool pair_ok = vp3d::conv_gemm_pair_supported(a->dtype, a->block_n, a->w_mn_major, p);
+  if (want_epi && !(use_pairs && pair_ok))
+    return fail(VP3D_ERR_UNSUPPORTED, "fused dropout / side input need the CTA-pair kernel (16-bit operands and output, "
+                "block_n 256, no dyn_offsets, cluster launches available on this device)");
+  if (use_pairs && pair_ok && (use_pairs == 2 || total_tiles >= 2LL * dev->sm_count)) {
     CUtensorMap tmBh = tmB;    // MN-major: the same [64 k-rows][64 columns] boxes, two per CTA
     if (!a->w_mn_major) {
       cuuint64_t dims[2] = {(cuuint64_t)a->k_total, (cuuint64_t)a->n_pad};
@@ -314,9 +351,10 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
       cuuint32_t box[2] = {(cuuint32_t)kblk, (cuuint32_t)(a->block_n / 2)};
       if (int rc = encode_map(&tmBh, a->dtype, 2, a->w, dims, strides, box, "weights (half tile)")) return rc;
     }
-    cudaError_t e2 = vp3d::launch_conv_gemm_pair(a->dtype, a->w_mn_major, tmA, tmBh, tmC, p, dev->sm_count,
+    cudaError_t e2 = vp3d::launch_conv_gemm_pair(a->dtype, a->w_mn_major, tmA, tmBh, tmC, tmS, p, dev->sm_count,
                                                  static_cast<cudaStream_t>(stream));
     if (e2 == cudaSuccess) return VP3D_OK;
+    if (want_epi) return cuda_fail(e2, "conv_gemm_pair launch (fused epilogue)");
     // a cluster launch can be refused where the plain one is not (MPS / partitioned devices): not an error of the call --
     // the single-CTA kernel below covers every case. The refusal is remembered for THIS device only; other devices of
     // the process and the global mode (vp3d_set_pair_mode) are left alone.
@@ -337,6 +375,55 @@ int vp3d_pack_rows(int dtype, const float* src, void* dst, long long rows, int c
   if (int rc = device_info(&dev)) return rc;
   cudaError_t e = vp3d::launch_pack_rows(dtype, src, dst, rows, c, c_pad, dev->sm_count, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "pack_rows launch");
+  return VP3D_OK;
+}
+
+int vp3d_pack_rows_ones(int dtype, const float* src, void* dst, long long rows, int c, int c_pad, int ones_col,
+                        void* stream) {
+  if (src == nullptr || dst == nullptr || rows < 0 || c <= 0 || c_pad < c) return fail(VP3D_ERR_INVALID, "pack_rows_ones args");
+  if (dtype != VP3D_F16 && dtype != VP3D_BF16) return fail(VP3D_ERR_INVALID, "pack_rows_ones: dtype must be F16 or BF16");
+  if (ones_col < c || ones_col >= c_pad) return fail(VP3D_ERR_INVALID, "pack_rows_ones: ones_col must be a padding column");
+  if (c_pad % 8 != 0 || (reinterpret_cast<uintptr_t>(dst) & 15)) return fail(VP3D_ERR_INVALID, "pack_rows_ones: c_pad % 8, 16-byte dst");
+  if (rows == 0) return VP3D_OK;
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_pack_rows(dtype, src, dst, rows, c, c_pad, dev->sm_count, static_cast<cudaStream_t>(stream),
+                                         ones_col);
+  if (e != cudaSuccess) return cuda_fail(e, "pack_rows_ones launch");
+  return VP3D_OK;
+}
+
+int vp3d_expand_bn_stats(int dtype, const float* gram, const void* w, int k_total, int ones_col, const float* gamma,
+                         const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                         long long* num_batches_tracked, float* scale, float* shift, float* mean, float* invstd,
+                         float* wg, int c, int c_pad, void* stream) {
+  if (dtype != VP3D_F16 && dtype != VP3D_BF16) return fail(VP3D_ERR_INVALID, "expand_bn_stats: dtype must be F16 or BF16");
+  if (!gram || !w || !gamma || !beta || !scale || !shift || !mean || !invstd || !wg)
+    return fail(VP3D_ERR_INVALID, "expand_bn_stats: null pointer");
+  if (k_total <= 0 || k_total > 256 || ones_col < 0 || ones_col >= k_total || c <= 0 || c_pad < c || c_pad % 8 != 0)
+    return fail(VP3D_ERR_INVALID, "expand_bn_stats: need 0 < k_total <= 256, ones_col < k_total, c <= c_pad, c_pad % 8 == 0");
+  if ((running_mean == nullptr) != (running_var == nullptr)) return fail(VP3D_ERR_INVALID, "expand_bn_stats running stats");
+  cudaError_t e = vp3d::launch_expand_bn_stats(dtype, gram, w, k_total, ones_col, gamma, beta, eps, momentum, running_mean,
+                                               running_var, num_batches_tracked, scale, shift, mean, invstd, wg, c, c_pad,
+                                               static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "expand_bn_stats launch");
+  return VP3D_OK;
+}
+
+int vp3d_expand_bwd_finish(int dtype, const float* p_packed, const float* wg, const float* gram, const void* w, int k_total,
+                           int ones_col, const float* scale, const float* mean, const float* invstd,
+                           const float* gscale_buf, int c, int c_pad, int c_in, int c_in_pad, int taps, float* dw,
+                           float* d_gamma, float* d_beta, void* stream) {
+  if (dtype != VP3D_F16 && dtype != VP3D_BF16) return fail(VP3D_ERR_INVALID, "expand_bwd_finish: dtype must be F16 or BF16");
+  if (!p_packed || !wg || !gram || !w || !scale || !mean || !invstd || !dw || !d_gamma || !d_beta)
+    return fail(VP3D_ERR_INVALID, "expand_bwd_finish: null pointer");
+  if (k_total <= 0 || k_total > 256 || ones_col < 0 || ones_col >= k_total || c <= 0 || c_pad < c || c_pad % 8 != 0 ||
+      c_in <= 0 || c_in > c_in_pad || taps <= 0 || taps * c_in_pad != k_total)
+    return fail(VP3D_ERR_INVALID, "expand_bwd_finish: inconsistent sizes");
+  cudaError_t e = vp3d::launch_expand_bwd_finish(dtype, p_packed, wg, gram, w, k_total, ones_col, scale, mean, invstd,
+                                                 gscale_buf, c, c_pad, c_in, c_in_pad, taps, dw, d_gamma, d_beta,
+                                                 static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "expand_bwd_finish launch");
   return VP3D_OK;
 }
 
@@ -565,7 +652,10 @@ int vp3d_wgrad(const vp3d_wgrad_args* a, void* stream) {
 
   CUtensorMap tmA, tmB;
   {
-    cuuint64_t dims[3] = {(cuuint64_t)a->co_pad, (cuuint64_t)a->dz_rows, (cuuint64_t)a->dz_seqs};
+    /* dz_cols < co_pad: the missing output-channel columns read as zero (TMA), like a_cols on the other operand */
+    const long long dz_cols = a->dz_cols > 0 ? a->dz_cols : a->co_pad;
+    if (dz_cols > a->co_pad) return fail(VP3D_ERR_INVALID, "wgrad: dz_cols > co_pad");
+    cuuint64_t dims[3] = {(cuuint64_t)dz_cols, (cuuint64_t)a->dz_rows, (cuuint64_t)a->dz_seqs};
     cuuint64_t strides[2] = {(cuuint64_t)(a->dz_row_stride * 2), (cuuint64_t)(a->dz_seq_stride * 2)};
     if (a->dz_seqs == 1) strides[1] = (cuuint64_t)(a->dz_rows * a->dz_row_stride * 2);
     cuuint32_t box[3] = {64, 64, 1};
@@ -654,14 +744,6 @@ int check_ew(int dtype, int c_pad, const char* what) {
   if (dtype != VP3D_F16 && dtype != VP3D_BF16) return fail(VP3D_ERR_INVALID, "%s: dtype must be F16 or BF16", what);
   if (c_pad <= 0 || c_pad % 8 != 0) return fail(VP3D_ERR_INVALID, "%s: c_pad must be a positive multiple of 8", what);
   return VP3D_OK;
-}
-vp3d::DropoutParams drop_of(const vp3d_dropout* d) {
-  vp3d::DropoutParams dp;
-  dp.p = d ? d->p : 0.f;
-  dp.seed = d ? d->seed : 0ull;
-  dp.stream = d ? d->stream : 0ull;
-  dp.step_counter = d ? d->step_counter : nullptr;
-  return dp;
 }
 }  // namespace
 

@@ -17,6 +17,7 @@
 // and TF32 stay on conv_gemm_kernel, as do launches of less than two waves.
 #include "ptx.cuh"
 #include "kernels.h"
+#include "dropout.cuh"
 
 namespace vp3d {
 namespace {
@@ -34,12 +35,18 @@ constexpr int kOutBufBytes = kEpi * 32 * 64;      // one 32 x 32 staging tile (6
 #ifndef VP3D_PAIR_OUTBUFS
 #define VP3D_PAIR_OUTBUFS 2
 #endif
-constexpr int kOutBufs = VP3D_PAIR_OUTBUFS;       // ring of TMA-store staging buffers per epilogue warp
-constexpr int kOutStageBytes = kOutBufs * kOutBufBytes;
+// ring of TMA-store staging buffers per epilogue warp. EPI = 1 (side input / fused dropout) uses three: a side tile is
+// fetched INTO the staging buffer its result is later written over, two chunks ahead of its use.
+template <int EPI>
+struct EpiCfg {
+  static constexpr int kOutBufs = EPI ? 3 : VP3D_PAIR_OUTBUFS;
+  static constexpr int kOutStageBytes = kOutBufs * kOutBufBytes;
+};
 constexpr int kBarBytes = 512;
 constexpr int kAffineCols = 1024;
 constexpr int kAffineBytes = 2 * kAffineCols * 4;
-constexpr int kSmemBytes = kStages * kStageBytes + kOutStageBytes + kBarBytes + kAffineBytes;
+template <int EPI>
+constexpr int smem_bytes() { return kStages * kStageBytes + EpiCfg<EPI>::kOutStageBytes + kBarBytes + kAffineBytes; }
 constexpr int kTmemCols = 2 * kBN;                // two accumulator buffers
 
 template <int DT>
@@ -91,11 +98,19 @@ __device__ __forceinline__ uint64_t mnmajor_sw128_desc(uint32_t smem_addr, uint3
   return d;
 }
 
-template <int DT, bool BMN>
+// EPI = 1 adds to the epilogue (train-mode fusions and the TMA residual path):
+//   * dropout after the ReLU (p.drop), same counter-based mask as train.cu's bn_act_fwd pass;
+//   * a side input with the geometry of the output (tmS), fetched by TMA into the staging tile two chunks ahead:
+//     side_mode 1 adds it (residual rows without a register round trip), side_mode 2 gates the result by side > 0
+//     (the ReLU / dropout mask of a layer recovered from its stored activation: dropped and clipped elements are 0).
+template <int DT, bool BMN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const __grid_constant__ CUtensorMap tmC, const ConvGemmParams p) {
+                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmS,
+                      const ConvGemmParams p) {
   using F = Fmt<DT>;
+  constexpr int kOutBufs = EpiCfg<EPI>::kOutBufs;
+  constexpr int kOutStageBytes = EpiCfg<EPI>::kOutStageBytes;
   constexpr int kElemsPerKBlock = kKBytes / 2;
   constexpr uint32_t kIdesc = make_instr_desc(F::kFormat, 2 * kBM, kBN) | (BMN ? (1u << 16) : 0u);
 
@@ -111,6 +126,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint64_t* tmem_full_bar = bars + 2 * kStages;    // per CTA, multicast commit
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // leader only: epilogue warps of both CTAs arrive
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* side_bar = tmem_empty_bar + 4;         // EPI: [epilogue warp][staging buffer], this CTA's own TMA loads
   float* affine_smem = reinterpret_cast<float*>(out_stage + kOutStageBytes + kBarBytes);   // scale[1024] | shift[1024]
 
   const int warp = threadIdx.x >> 5;
@@ -133,6 +149,10 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], 2 * kEpi);
+    }
+    if (EPI) {
+      tma_prefetch_desc(&tmS);
+      for (int s = 0; s < kEpi * kOutBufs; ++s) mbar_init(&side_bar[s], 1);
     }
     fence_barrier_init();
   }
@@ -229,6 +249,29 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     unsigned out_buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    // EPI: this warp's chunks form one stream gc = tile iteration * kChunks + chunk; chunk gc is staged in buffer
+    // gc % kOutBufs, whose side tile was requested while chunk gc - 2 was being finished
+    const bool side_on = EPI && p.side_mode != 0;
+    int gc = 0;
+    auto side_issue = [&](int g) {   // lane 0: request the side tile of chunk g (no-op past the last tile)
+      const int it = g / kChunks;
+      const int pt = first_pair + it * pair_step;
+      if (pt >= total_pairs) return;
+      const PairTile tcs = decode_pair(pt, p, pairs_per_seq, rank);
+      const int bb = g % kOutBufs;
+      uint64_t* bar = &side_bar[epi * kOutBufs + bb];
+      mbar_expect_tx(bar, 32 * 64);
+      tma_load_3d(out_stage + bb * kOutBufBytes + epi * (32 * 64), &tmS, bar,
+                  tcs.n0 * kBN + (half * kChunks + (g - it * kChunks)) * 32, tcs.t0 + quad * 32 + p.side_row_off,
+                  tcs.seq);
+    };
+    if (side_on && lane == 0) {
+      side_issue(0);
+      side_issue(1);
+    }
+    DropCtx drop;
+    drop.on = false;
+    if (EPI && p.drop.p > 0.f) drop = make_drop(p.drop);
     // train-mode BatchNorm statistics of the stored values, as in conv_gemm.cu: lane l owns column chunk * 32 + l of
     // this warp's column half, accumulated in registers and flushed when the CTA changes column tile
     float st_s[4] = {0.f, 0.f, 0.f, 0.f}, st_q[4] = {0.f, 0.f, 0.f, 0.f};
@@ -323,6 +366,18 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
+        if (EPI && drop.on) {
+          // the mask of train.cu's passes: one Philox block per (row pair, 8-channel group), this row's half of it
+          const long long grow = (long long)tc.seq * p.rows_out + t;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 bits = drop_bits(drop, grow >> 1, (col0 >> 3) + j);
+            float m[8];
+            drop_mult8(drop, (grow & 1) ? bits.z : bits.x, (grow & 1) ? bits.w : bits.y, m);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[8 * j + k] *= m[k];
+          }
+        }
         if (res_any && res_in_window(c)) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -340,8 +395,29 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const unsigned b = out_buf;
         out_buf = out_buf + 1 == kOutBufs ? 0 : out_buf + 1;
         uint8_t* my_stage = out_stage + b * kOutBufBytes + epi * (32 * 64);
-        if (lane == 0) tma_store_wait_read<kOutBufs - 1>();   // the store that last used this buffer has drained it
-        __syncwarp();
+        if (side_on) {
+          // the side tile of this chunk sits in the staging buffer (same SWIZZLE_64B box as the store): thread = row
+          mbar_wait(&side_bar[epi * kOutBufs + b], (uint32_t)(gc / kOutBufs) & 1u);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 r = *reinterpret_cast<const uint4*>(my_stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
+            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 x = F::unpack(rr[e]);
+              if (p.side_mode == 1) {
+                f[8 * j + 2 * e + 0] += x.x;
+                f[8 * j + 2 * e + 1] += x.y;
+              } else {
+                f[8 * j + 2 * e + 0] = x.x > 0.f ? f[8 * j + 2 * e + 0] * p.side_scale : 0.f;
+                f[8 * j + 2 * e + 1] = x.y > 0.f ? f[8 * j + 2 * e + 1] * p.side_scale : 0.f;
+              }
+            }
+          }
+        } else {
+          if (lane == 0) tma_store_wait_read<kOutBufs - 1>();   // the store that last used this buffer has drained it
+          __syncwarp();
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           st_shared_v4(my_stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), F::pack(f[8 * j + 0], f[8 * j + 1]),
@@ -374,7 +450,13 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (lane == 0) {
           tma_store_3d(&tmC, my_stage, col0, tc.t0 + quad * 32, tc.seq);
           tma_store_commit();
+          if (side_on) {
+            // chunk gc + 2 reuses the buffer of chunk gc - 1: its store (all but the newest one) has drained it
+            tma_store_wait_read<1>();
+            side_issue(gc + kOutBufs - 1);
+          }
         }
+        ++gc;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           rcur[j] = rnext[j];
@@ -405,16 +487,17 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
 }
 
-template <int DT, bool BMN>
-cudaError_t launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvGemmParams& p,
-                        int clusters, cudaStream_t stream) {
+template <int DT, bool BMN, int EPI>
+cudaError_t launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmS,
+                        const ConvGemmParams& p, int clusters, cudaStream_t stream) {
   static std::atomic<unsigned long long> attr_done{0};   // one bit per device ordinal
-  if (cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(conv_gemm_pair_kernel<DT, BMN>), kSmemBytes, attr_done))
+  if (cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(conv_gemm_pair_kernel<DT, BMN, EPI>),
+                                        smem_bytes<EPI>(), attr_done))
     return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * clusters);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.dynamicSmemBytes = smem_bytes<EPI>();
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -423,7 +506,14 @@ cudaError_t launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<DT, BMN>, tmA, tmB, tmC, p);
+  return cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<DT, BMN, EPI>, tmA, tmB, tmC, tmS, p);
+}
+
+template <int DT, bool BMN>
+cudaError_t launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmS,
+                            const ConvGemmParams& p, int clusters, cudaStream_t stream) {
+  if (p.side_mode != 0 || p.drop.p > 0.f) return launch_pair<DT, BMN, 1>(tmA, tmB, tmC, tmS, p, clusters, stream);
+  return launch_pair<DT, BMN, 0>(tmA, tmB, tmC, tmS, p, clusters, stream);
 }
 
 }  // namespace
@@ -439,7 +529,8 @@ bool conv_gemm_pair_supported(int dtype, int block_n, int /*w_mn_major: both wei
 // K-major weights: tmB must be encoded with a box of 128 output channels (half a column tile) x 64 elements of K;
 // MN-major weights: the [64 k-rows][64 columns] map of the single-CTA kernel
 cudaError_t launch_conv_gemm_pair(int dtype, int w_mn_major, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                                  const CUtensorMap& tmC, const ConvGemmParams& p, int sm_count, cudaStream_t stream) {
+                                  const CUtensorMap& tmC, const CUtensorMap& tmS, const ConvGemmParams& p, int sm_count,
+                                  cudaStream_t stream) {
   const int pairs_per_seq = (p.m_tiles_per_seq + 1) / 2;
   const long long total_pairs = (long long)p.a_seqs * pairs_per_seq * p.n_tiles;
   int clusters = sm_count / 2;
@@ -449,11 +540,11 @@ cudaError_t launch_conv_gemm_pair(int dtype, int w_mn_major, const CUtensorMap& 
   // per-channel sums stay in registers for the whole launch and are flushed once
   if (p.stat_sum != nullptr && clusters > p.n_tiles) clusters -= clusters % p.n_tiles;
   if (w_mn_major) {
-    if (dtype == VP3D_BF16) return launch_pair<VP3D_BF16, true>(tmA, tmB, tmC, p, clusters, stream);
-    return launch_pair<VP3D_F16, true>(tmA, tmB, tmC, p, clusters, stream);
+    if (dtype == VP3D_BF16) return launch_pair_epi<VP3D_BF16, true>(tmA, tmB, tmC, tmS, p, clusters, stream);
+    return launch_pair_epi<VP3D_F16, true>(tmA, tmB, tmC, tmS, p, clusters, stream);
   }
-  if (dtype == VP3D_BF16) return launch_pair<VP3D_BF16, false>(tmA, tmB, tmC, p, clusters, stream);
-  return launch_pair<VP3D_F16, false>(tmA, tmB, tmC, p, clusters, stream);
+  if (dtype == VP3D_BF16) return launch_pair_epi<VP3D_BF16, false>(tmA, tmB, tmC, tmS, p, clusters, stream);
+  return launch_pair_epi<VP3D_F16, false>(tmA, tmB, tmC, tmS, p, clusters, stream);
 }
 
 }  // namespace vp3d

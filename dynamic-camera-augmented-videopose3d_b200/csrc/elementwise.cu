@@ -42,7 +42,8 @@ pack_rows_kernel(const float* __restrict__ src, void* __restrict__ dst, long lon
 // bytes moved would take 10 us)
 template <int DT>
 __global__ void __launch_bounds__(256)
-pack_rows_vec8_kernel(const float* __restrict__ src, uint4* __restrict__ dst, long long rows, int c, int groups) {
+pack_rows_vec8_kernel(const float* __restrict__ src, uint4* __restrict__ dst, long long rows, int c, int groups,
+                      int ones_col) {
   const long long total = rows * groups;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -51,7 +52,7 @@ pack_rows_vec8_kernel(const float* __restrict__ src, uint4* __restrict__ dst, lo
     const float* s = src + r * c + k0;
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = k0 + j < c ? __ldg(s + j) : 0.f;
+    for (int j = 0; j < 8; ++j) v[j] = k0 + j < c ? __ldg(s + j) : (k0 + j == ones_col ? 1.f : 0.f);
     uint4 o;
     if (DT == VP3D_F16) {
       __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
@@ -205,17 +206,20 @@ static int ew_grid(long long total, int sm_count) {
   return (int)blocks;
 }
 
+// ones_col >= 0 (16-bit, c_pad % 8 == 0 only): that padding column holds 1.0 -- the Gram matrix of the packed rows then
+// carries the column sums and the row count (expand.cu)
 cudaError_t launch_pack_rows(int dtype, const float* src, void* dst, long long rows, int c, int c_pad, int sm_count,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, int ones_col) {
   if ((dtype == VP3D_F16 || dtype == VP3D_BF16) && c_pad % 8 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
     const int groups = c_pad / 8;
     const int g = ew_grid(rows * groups, sm_count);
     if (dtype == VP3D_F16)
-      pack_rows_vec8_kernel<VP3D_F16><<<g, 256, 0, stream>>>(src, static_cast<uint4*>(dst), rows, c, groups);
+      pack_rows_vec8_kernel<VP3D_F16><<<g, 256, 0, stream>>>(src, static_cast<uint4*>(dst), rows, c, groups, ones_col);
     else
-      pack_rows_vec8_kernel<VP3D_BF16><<<g, 256, 0, stream>>>(src, static_cast<uint4*>(dst), rows, c, groups);
+      pack_rows_vec8_kernel<VP3D_BF16><<<g, 256, 0, stream>>>(src, static_cast<uint4*>(dst), rows, c, groups, ones_col);
     return cudaGetLastError();
   }
+  if (ones_col >= 0) return cudaErrorInvalidValue;
   const int bx = c_pad >= 256 ? 256 : ((c_pad + 31) / 32) * 32;
   const dim3 block(bx, 256 / bx > 0 ? 256 / bx : 1);
   long long gx = (rows + block.y - 1) / block.y;

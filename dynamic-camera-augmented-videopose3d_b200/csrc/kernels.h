@@ -23,6 +23,14 @@ inline cudaError_t set_max_smem_once(const void* func, int bytes, std::atomic<un
   return e;
 }
 
+// Counter-based dropout description (dropout.cuh).
+struct DropoutParams {
+  float p;
+  unsigned long long seed;
+  unsigned long long stream;
+  const unsigned long long* step_counter;
+};
+
 // Launch parameters of conv_gemm_kernel (see conv_gemm.cu). All strides are in elements of the named buffer.
 struct ConvGemmParams {
   int a_seqs;           // sequences (outermost TMA coordinate of the activation view)
@@ -59,6 +67,13 @@ struct ConvGemmParams {
 
   double* stat_sum;     // optional per-channel sum / sum-of-squares of the raw accumulator (train-mode BN)
   double* stat_sqsum;
+
+  // CTA-pair kernel only (conv_gemm2.cu, EPI = 1):
+  DropoutParams drop;   // drop.p > 0: dropout after the ReLU, keyed by (flat output row seq * rows_out + t, 8-channel group)
+  int side_mode;        // epilogue side input fetched by TMA (tmS, geometry of the output): 0 none,
+                        // 1: out += side[seq][t + side_row_off][n]   2: out = side[seq][t][n] > 0 ? out * side_scale : 0
+  int side_row_off;
+  float side_scale;
 };
 
 cudaError_t launch_conv_gemm(int dtype, int block_n, int w_mn_major, const CUtensorMap& tmA, const CUtensorMap& tmB,
@@ -68,7 +83,8 @@ cudaError_t launch_conv_gemm(int dtype, int block_n, int w_mn_major, const CUten
 // `tmB_half` is the weight map with a box of 128 output channels x 64 elements of K.
 bool conv_gemm_pair_supported(int dtype, int block_n, int w_mn_major, const ConvGemmParams& p);
 cudaError_t launch_conv_gemm_pair(int dtype, int w_mn_major, const CUtensorMap& tmA, const CUtensorMap& tmB_half,
-                                  const CUtensorMap& tmC, const ConvGemmParams& p, int sm_count, cudaStream_t stream);
+                                  const CUtensorMap& tmC, const CUtensorMap& tmS, const ConvGemmParams& p, int sm_count,
+                                  cudaStream_t stream);
 
 // Launch parameters of wgrad_gemm_kernel (see wgrad.cu).
 struct WgradParams {
@@ -90,13 +106,6 @@ cudaError_t launch_wgrad(int dtype, int block_n, int block_m, const CUtensorMap&
 cudaError_t launch_wgrad_finish(const float* packed, float* dw, int c_out, int c_in, int taps, long long tap_stride,
                                 long long row_stride, const float* gscale_buf, int sm_count, cudaStream_t stream);
 
-// Counter-based dropout description (train.cu).
-struct DropoutParams {
-  float p;
-  unsigned long long seed;
-  unsigned long long stream;
-  const unsigned long long* step_counter;
-};
 cudaError_t launch_counter_add(unsigned long long* counter, unsigned long long inc, cudaStream_t stream);
 struct AdamParams {
   float* p; const float* g; float* m; float* v; float* vmax;
@@ -164,6 +173,14 @@ cudaError_t launch_bn_act_bwd_apply(int dtype, const void* g, const void* z, con
                                     int c_pad, const DropoutParams& dp, const double* sum_dy, const double* sum_dy_xhat,
                                     const float* gscale_buf, void* dz, float* d_gamma, float* d_beta, int sm_count,
                                     cudaStream_t stream);
+cudaError_t launch_expand_bn_stats(int dtype, const float* G, const void* w, int k_total, int ones_col,
+                                   const float* gamma, const float* beta, float eps, float momentum,
+                                   float* running_mean, float* running_var, long long* nbt, float* scale, float* shift,
+                                   float* mean, float* invstd, float* wg, int c, int c_pad, cudaStream_t stream);
+cudaError_t launch_expand_bwd_finish(int dtype, const float* P, const float* wg, const float* G, const void* w, int k_total,
+                                     int ones_col, const float* scale, const float* mean, const float* invstd,
+                                     const float* gscale_buf, int c, int c_pad, int c_in, int c_in_pad, int taps, float* dw,
+                                     float* d_gamma, float* d_beta, cudaStream_t stream);
 cudaError_t launch_grad_scale(const float* dy, long long n, float* gscale_buf, int sm_count, cudaStream_t stream);
 cudaError_t launch_grad_pack_rows(int dtype, const float* src, void* dst, long long rows, int c, int c_pad,
                                   const float* gscale_buf, float* col_sum, int sm_count, cudaStream_t stream);

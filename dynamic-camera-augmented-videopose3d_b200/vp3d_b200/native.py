@@ -32,6 +32,9 @@ class ConvArgs(C.Structure):
         ('res_rows', C.c_longlong), ('res_col_off', C.c_longlong), ('res_cols', C.c_longlong),
         ('dyn_offsets', C.c_void_p), ('out_rows_total', C.c_longlong),
         ('stat_sum', C.c_void_p), ('stat_sqsum', C.c_void_p),
+        ('drop', C.c_void_p), ('side', C.c_void_p), ('side_mode', C.c_int), ('side_row_off', C.c_int),
+        ('side_row_stride', C.c_longlong), ('side_seq_stride', C.c_longlong), ('side_rows', C.c_longlong),
+        ('side_scale', C.c_float),
     ]
 
 
@@ -44,7 +47,7 @@ class WgradArgs(C.Structure):
         ('a', C.c_void_p), ('a_rows', C.c_longlong), ('a_cols', C.c_longlong), ('a_row_stride', C.c_longlong),
         ('a_seq_stride', C.c_longlong), ('ci_pad', C.c_longlong),
         ('taps', C.c_int), ('b_row_off', C.c_longlong), ('b_tap_row_step', C.c_int), ('b_tap_col_step', C.c_longlong),
-        ('dw_packed', C.c_void_p),
+        ('dw_packed', C.c_void_p), ('dz_cols', C.c_longlong),
     ]
 
 
@@ -81,6 +84,12 @@ _SIGNATURES = {
     'vp3d_set_pair_mode': (C.c_int, [C.c_int]),
     'vp3d_conv_block_fwd': (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     'vp3d_pack_rows': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
+    'vp3d_pack_rows_ones': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p]),
+    'vp3d_expand_bn_stats': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_float, C.c_float] + [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_void_p]),
+    'vp3d_expand_bwd_finish': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int] +
+                               [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_void_p] * 4),
     'vp3d_pack_conv_weight': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_void_p]),
     'vp3d_pack_conv_weight_scaled': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,

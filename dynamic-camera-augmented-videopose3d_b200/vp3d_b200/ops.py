@@ -225,13 +225,18 @@ def mean_velocity_error(pred, tgt):
 
 
 # ------------------------------------------------------------------------------------------------ K1 plumbing
-def pack_rows(dt, src, c_pad):
-    """fp32 (rows, c) -> operand type (rows, c_pad) zero padded."""
+def pack_rows(dt, src, c_pad, ones_col=None):
+    """fp32 (rows, c) -> operand type (rows, c_pad) zero padded; `ones_col`: that padding column holds 1.0 instead
+    (vp3d_pack_rows_ones: the Gram matrix of the rows then carries their column sums and count)."""
     src = f32c(src)
     rows, c = src.shape
     dst = torch.empty((rows, c_pad), dtype=torch_dtype(dt), device=src.device)
     with torch.cuda.device(src.device):
-        check(lib().vp3d_pack_rows(dt, _ptr(src), _ptr(dst), rows, c, c_pad, _stream()), 'pack_rows')
+        if ones_col is None:
+            check(lib().vp3d_pack_rows(dt, _ptr(src), _ptr(dst), rows, c, c_pad, _stream()), 'pack_rows')
+        else:
+            check(lib().vp3d_pack_rows_ones(dt, _ptr(src), _ptr(dst), rows, c, c_pad, int(ones_col), _stream()),
+                  'pack_rows_ones')
     return dst
 
 
@@ -275,10 +280,12 @@ def bn_fold(bn, c_pad):
 def conv_block(dt, a, a_view, w, taps, tap_row_step, k_per_tap, rows_out, out, out_view, block_n=256, a_row_off=0,
                scale=None, shift=None, relu=False, res=None, res_view=None, out_f32=False, n_valid=None,
                stat_sum=None, stat_sqsum=None, out_round_tf32=False, res_rows=0, res_col_off=0, res_cols=0,
-               w_mn_major=None, dyn_offsets=None, out_rows_total=0):
+               w_mn_major=None, dyn_offsets=None, out_rows_total=0, drop=None, side=None, side_view=None, side_mode=0,
+               side_scale=1.0):
     """One vp3d_conv_block_fwd launch.
     a_view   = (seqs, rows, kdim, row_stride, seq_stride)    out_view = (row_stride, seq_stride)
-    res_view = (row_stride, seq_stride, row_mul, row_off)"""
+    res_view = (row_stride, seq_stride, row_mul, row_off)    side_view = (row_stride, seq_stride, rows, row_off)
+    drop (a native.Dropout) / side: the fused epilogue of the CTA-pair kernel (see vp3d_conv_args)."""
     args = ConvArgs()
     args.dtype, args.block_n = dt, block_n
     args.a = a.data_ptr()
@@ -309,6 +316,11 @@ def conv_block(dt, a, a_view, w, taps, tap_row_step, k_per_tap, rows_out, out, o
         args.dyn_offsets, args.out_rows_total = dyn_offsets.data_ptr(), out_rows_total
     args.stat_sum = None if stat_sum is None else stat_sum.data_ptr()
     args.stat_sqsum = None if stat_sqsum is None else stat_sqsum.data_ptr()
+    if drop is not None and drop.p > 0:
+        args.drop = C.addressof(drop)
+    if side is not None:
+        args.side, args.side_mode, args.side_scale = side.data_ptr(), int(side_mode), float(side_scale)
+        args.side_row_stride, args.side_seq_stride, args.side_rows, args.side_row_off = side_view
     with torch.cuda.device(a.device):
         check(lib().vp3d_conv_block_fwd(C.byref(args), _stream()), 'conv_block_fwd')
     return out
@@ -329,7 +341,7 @@ def counter_add(counter, inc=1):
 
 
 def wgrad(dt, dz, dz_view, a, a_view, co_pad, ci_pad, taps, dw_packed, b_row_off=0, b_tap_row_step=0,
-          b_tap_col_step=0, block_n=256):
+          b_tap_col_step=0, block_n=256, dz_cols=0):
     """One vp3d_wgrad launch. dz_view = (seqs, rows, row_stride, seq_stride); a_view = (rows, cols, row_stride,
     seq_stride). dw_packed: zero-filled fp32 [taps][co_pad][ci_pad]."""
     args = WgradArgs()
@@ -342,6 +354,7 @@ def wgrad(dt, dz, dz_view, a, a_view, co_pad, ci_pad, taps, dw_packed, b_row_off
     args.ci_pad = ci_pad
     args.taps, args.b_row_off, args.b_tap_row_step, args.b_tap_col_step = taps, b_row_off, b_tap_row_step, b_tap_col_step
     args.dw_packed = dw_packed.data_ptr()
+    args.dz_cols = dz_cols
     with torch.cuda.device(dz.device):
         check(lib().vp3d_wgrad(C.byref(args), _stream()), 'wgrad')
     return dw_packed
@@ -398,6 +411,46 @@ def bn_finalize(stat, count, bn, c_pad, update_running=True):
     if track:
         _bump_running_stats(bn)
     return out[0], out[1], out[2], out[3]
+
+
+def keep_scale(p):
+    """Multiplier of kept elements: the kernels quantise the drop probability to 1/256 (see dropout.cuh)."""
+    thresh = int(float(p) * 256.0 + 0.5)
+    return 256.0 / (256.0 - thresh) if thresh > 0 else 1.0
+
+
+def expand_bn_stats(dt, gram, w, k_total, ones_col, bn, c_pad, update_running=True):
+    """Train-mode BatchNorm of the expand layer from the Gram matrix of its input (vp3d_expand_bn_stats)
+    -> (scale, shift, mean, invstd [c_pad], wg [c_pad][256])."""
+    dev = gram.device
+    out = torch.empty((4, c_pad), dtype=torch.float32, device=dev)
+    wg = torch.empty((c_pad, 256), dtype=torch.float32, device=dev)
+    track = update_running and bn.track_running_stats and bn.running_mean is not None
+    with torch.cuda.device(dev):
+        check(lib().vp3d_expand_bn_stats(dt, _ptr(gram), _ptr(w), int(k_total), int(ones_col),
+                                         _ptr(f32c(bn.weight.detach())), _ptr(f32c(bn.bias.detach())), float(bn.eps),
+                                         _bn_momentum(bn), _ptr(bn.running_mean) if track else None,
+                                         _ptr(bn.running_var) if track else None,
+                                         _ptr(bn.num_batches_tracked) if track else None, _ptr(out[0]), _ptr(out[1]),
+                                         _ptr(out[2]), _ptr(out[3]), _ptr(wg), bn.num_features, c_pad, _stream()),
+              'expand_bn_stats')
+    if track:
+        _bump_running_stats(bn)
+    return out[0], out[1], out[2], out[3], wg
+
+
+def expand_bwd_finish(dt, p_packed, wg, gram, w, k_total, ones_col, scale, mean, invstd, gscale_buf, c, c_pad, c_in,
+                      c_in_pad, taps):
+    """-> (dW (c, c_in, taps), d_gamma [c], d_beta [c]) of the expand layer (vp3d_expand_bwd_finish)."""
+    dev = p_packed.device
+    dw = torch.empty((c, c_in, taps), dtype=torch.float32, device=dev)
+    dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().vp3d_expand_bwd_finish(dt, _ptr(p_packed), _ptr(wg), _ptr(gram), _ptr(w), int(k_total), int(ones_col),
+                                           _ptr(scale), _ptr(mean), _ptr(invstd), _ptr(gscale_buf), c, c_pad, c_in,
+                                           c_in_pad, taps, _ptr(dw), _ptr(dgb[0]), _ptr(dgb[1]), _stream()),
+              'expand_bwd_finish')
+    return dw, dgb[0], dgb[1]
 
 
 def bn_act_fwd(dt, z, scale, shift, seqs, rows_per_seq, drop, res=None, res_seq_rows=0, res_row_mul=1, res_row_off=0):

@@ -79,7 +79,7 @@ def packed_for(model, dt):
 
 
 def _run_layer(dt, x, n, t_in, c_in_pad, w, plan, scale, shift, relu, res=None, res_t=0, out_f32=False, n_valid=None,
-               block_n=N_TILE, stats=None):
+               block_n=N_TILE, stats=None, drop=None):
     """x: [n][t_in][c_in_pad] operand-typed, contiguous. Returns (y [n][t_out][cols], t_out).
 
     View selection. A stride==width convolution reads `taps` consecutive frames per output frame, i.e. it is a plain
@@ -116,7 +116,7 @@ def _run_layer(dt, x, n, t_in, c_in_pad, w, plan, scale, shift, relu, res=None, 
         rows_out = t_out
         out_view = (cols, t_out * cols)
         res_view = None if res is None else (res_c, res_t * res_c, plan.res_mul, plan.res_off)
-    if block_n == N_TILE and dt != native.TF32:
+    if block_n == N_TILE and dt != native.TF32 and drop is None:   # (fused dropout lives in the 256-wide pair kernel)
         # few output tiles (the 1f model's last blocks: 3 or 1 frames per sample): 64-wide column tiles give 4x more
         # CTAs than SMs would otherwise be left idle by 128 x 256 tiles
         tiles = a_view[0] * ((rows_out + 127) // 128) * (n_pad // N_TILE)
@@ -125,7 +125,8 @@ def _run_layer(dt, x, n, t_in, c_in_pad, w, plan, scale, shift, relu, res=None, 
     ops.conv_block(dt, x, a_view, w, g_taps, g_step, k_per_tap, rows_out, y, out_view, block_n=block_n,
                    scale=scale, shift=shift, relu=relu, res=res, res_view=res_view, out_f32=out_f32, n_valid=cols,
                    out_round_tf32=(dt == native.TF32 and not final),
-                   stat_sum=None if stats is None else stats[0], stat_sqsum=None if stats is None else stats[1])
+                   stat_sum=None if stats is None else stats[0], stat_sqsum=None if stats is None else stats[1],
+                   drop=drop)
     return y, t_out
 
 

@@ -32,6 +32,11 @@ fuse_bn_finalize = os.environ.get('VP3D_FUSE_BN', '0') == '1'
 overlap_wgrad = True     # weight-gradient GEMMs on a second stream, concurrent with the HBM-bound BN backward passes
 _side_streams = {}
 _ones = {}               # constant unit scale vectors of the shrink layer, per (device, padded width)
+# Expand layer without its HBM-bound passes (csrc/expand.cu): BatchNorm statistics from the Gram matrix of the layer
+# input, BatchNorm + ReLU + dropout applied by the GEMM epilogue, and a backward that needs neither the raw output nor a
+# reduction / apply pass. VP3D_FUSED_EXPAND=0 restores bn_finalize + bn_act_fwd / bn_act_bwd for that layer (the path
+# every other layer takes; also used under SyncBN, where the statistics must be exchanged between the two steps).
+fused_expand = os.environ.get('VP3D_FUSED_EXPAND', '1') != '0'
 debug_keep_saved = False  # tests: keep the last forward's saved per-layer tensors in `debug_last_saved`
 debug_last_saved = None
 
@@ -39,7 +44,7 @@ debug_last_saved = None
 class _Layer:
     """Everything the backward needs about one convolution + BatchNorm + activation of the stack."""
     __slots__ = ('conv', 'bn', 'taps', 'dilation', 'stride', 't_in', 't_out', 'c_in', 'c_in_pad', 'a_in', 'z', 'scale',
-                 'shift', 'mean', 'invstd', 'drop', 'res_of', 'res_mul', 'res_off', 'res_t', 'w_fwd', 'count')
+                 'shift', 'mean', 'invstd', 'drop', 'res_of', 'res_mul', 'res_off', 'res_t', 'w_fwd', 'count', 'fused')
 
 
 def _conv_w(dt, conv, rows_pad, k_pad):
@@ -91,6 +96,7 @@ def _forward_stack(model, x, dt):
 
     def conv_bn_act(idx, conv, bn, a_in, t, cin, cin_pad, plan, res=None, res_t=0, res_mul=1, res_off=0):
         L = _Layer()
+        L.fused = None
         L.conv, L.bn = conv, bn
         L.taps, L.dilation, L.stride = plan.taps, plan.dilation, plan.stride
         L.c_in, L.c_in_pad, L.t_in, L.a_in = cin, cin_pad, t, a_in
@@ -120,9 +126,14 @@ def _forward_stack(model, x, dt):
         layers.append(L)
         return a, t_out
 
-    h = ops.pack_rows(dt, x.reshape(n * t_in, c_in), c_in_pad).view(n, t_in, c_in_pad)
     plan = LayerPlan(fw[0], 1, fw[0] if strided else 1)
-    h, t = conv_bn_act(0, model.expand_conv, model.expand_bn, h, t_in, c_in, c_in_pad, plan)
+    k0 = fw[0] * c_in_pad
+    if (fused_expand and sync_bn_group is None and len(fw) > 1 and c_in < c_in_pad and k0 <= 256 and
+            model.expand_conv.dilation[0] == 1):
+        h, t = _expand_fused(model, dt, x, n, t_in, c_in, c_in_pad, c_pad, plan, _dropout_for(model, 0, step), layers)
+    else:
+        h = ops.pack_rows(dt, x.reshape(n * t_in, c_in), c_in_pad).view(n, t_in, c_in_pad)
+        h, t = conv_bn_act(0, model.expand_conv, model.expand_bn, h, t_in, c_in, c_in_pad, plan)
     for i in range(len(fw) - 1):
         conv3, conv1 = model.layers_conv[2 * i], model.layers_conv[2 * i + 1]
         taps = conv3.kernel_size[0]
@@ -148,6 +159,43 @@ def _forward_stack(model, x, dt):
     y, t = _run_layer(dt, h, n, t, c_pad, w_shrink, LayerPlan(1), ones, bias, False, out_f32=True, n_valid=n_out,
                       block_n=64)
     return y, layers, h, t, c_pad, w_shrink
+
+
+def _expand_fused(model, dt, x, n, t_in, c_in, c_in_pad, c_pad, plan, drop, layers):
+    """expand_conv -> expand_bn -> relu -> drop (TemporalModel.py:127 / :189) as Gram GEMM + statistics kernel + ONE
+    convolution GEMM whose epilogue applies BatchNorm, ReLU and dropout (csrc/expand.cu). Appends the saved layer."""
+    conv, bn = model.expand_conv, model.expand_bn
+    taps, s = plan.taps, plan.stride
+    k_total = taps * c_in_pad
+    ones_col = c_in                                      # first padding column of tap 0
+    h = ops.pack_rows(dt, x.reshape(n * t_in, c_in), c_in_pad, ones_col=ones_col).view(n, t_in, c_in_pad)
+    t_out = (t_in - taps) // s + 1
+    # X = the [rows][k_total] view of the packed input the convolution contracts over: consecutive frames of a strided
+    # (stride == width) layer, overlapping windows of a stride-1 layer (row stride = one frame)
+    row_stride = k_total if s > 1 else c_in_pad
+    if s > 1 and t_in == taps * t_out:
+        xv, av = (1, n * t_out, row_stride, n * t_in * c_in_pad), (n * t_out, k_total, row_stride, n * t_in * c_in_pad)
+    else:
+        xv, av = (n, t_out, row_stride, t_in * c_in_pad), (t_out, k_total, row_stride, t_in * c_in_pad)
+    # 128 x 64 tiles: 8 tiles x ~18 row slices fill the SMs once; ONE 256 x 256 tile split 64 ways spent 40 us of its
+    # 48 us in 64-way red.add contention on the same 256 KB
+    gram = torch.zeros((1, 256, 256), dtype=torch.float32, device=x.device)
+    ops.wgrad(dt, h, xv, h, av, 256, 256, 1, gram, block_n=64, dz_cols=k_total)
+    w = _conv_w(dt, conv, c_pad, c_in_pad)
+    L = _Layer()
+    L.conv, L.bn, L.w_fwd = conv, bn, w
+    L.taps, L.dilation, L.stride = plan.taps, plan.dilation, plan.stride
+    L.c_in, L.c_in_pad, L.t_in, L.a_in = c_in, c_in_pad, t_in, h
+    L.scale, L.shift, L.mean, L.invstd, wg = ops.expand_bn_stats(dt, gram, w, k_total, ones_col, bn, c_pad)
+    L.drop = drop
+    a, t_out2 = _run_layer(dt, h, n, t_in, c_in_pad, w, plan, L.scale, L.shift, True, drop=drop)
+    assert t_out2 == t_out
+    L.z, L.t_out, L.count = None, t_out, n * t_out
+    L.res_of, L.res_t, L.res_mul, L.res_off = None, 0, 1, 0
+    L.fused = dict(gram=gram, wg=wg, xv=xv, av=av, k_total=k_total, ones_col=ones_col, a=a,
+                   keep_scale=ops.keep_scale(drop.p))
+    layers.append(L)
+    return a, t_out
 
 
 def _views(L, n, c_pad):
@@ -186,15 +234,19 @@ def _weight_grad(dt, L, dz, n, c_pad, gscale, keep=None):
     return ops.wgrad_finish(packed, c_out, L.c_in, L.taps, c_pad, L.c_in_pad, gscale)
 
 
-def _data_grad(dt, L, dz, n, c_pad, fan_in=None, fan_rows=0, fan_off=0, fan_mul=1):
+def _data_grad(dt, L, dz, n, c_pad, fan_in=None, fan_rows=0, fan_off=0, fan_mul=1, gate=None):
     """Gradient wrt the layer input: g_in[s][t'][ci] = sum_{tap, co} dz[s][t' - tap * d][co] * W[co][tap][ci]. The
     forward-packed weights [co][tap * c_in_pad + ci] are the W^T operand as they are (MN-major), no transposed copy.
-    `fan_in` is the block-output gradient that also reaches this input through the residual slice."""
+    `fan_in` is the block-output gradient that also reaches this input through the residual slice.
+    `gate` = (a, keep_scale): the input of this layer is the activation `a` of a layer whose backward works on the
+    GATED gradient (the fused expand layer): the epilogue multiplies by keep_scale where a > 0 and zeroes the rest."""
     taps, d, s = L.taps, L.dilation, L.stride
     cin_pad = L.c_in_pad
     g_in = torch.empty((n, L.t_in, cin_pad), dtype=dz.dtype, device=dz.device)
     block_n = 256 if cin_pad % 256 == 0 else 64
-    if block_n == 256 and ((n * L.t_out + 127) // 128) * (taps * cin_pad // 256) * 4 <= native.sm_count(dz.device):
+    if gate is not None:
+        assert block_n == 256
+    elif block_n == 256 and ((n * L.t_out + 127) // 128) * (taps * cin_pad // 256) * 4 <= native.sm_count(dz.device):
         block_n = 64    # few tiles: narrower column tiles keep all SMs busy (while they still fit in one wave)
     if s > 1 or taps == 1:
         if s > 1 and L.t_in != taps * L.t_out:
@@ -206,6 +258,8 @@ def _data_grad(dt, L, dz, n, c_pad, fan_in=None, fan_rows=0, fan_off=0, fan_mul=
         if fan_in is not None:
             # residual x[:, :, off::taps]: in that view it is the column block [off*C, (off+1)*C)
             kw = dict(res=fan_in, res_view=(c_pad, rows * c_pad, 1, 0), res_col_off=fan_off * cin_pad, res_cols=cin_pad)
+        if gate is not None:
+            kw.update(side=gate[0], side_view=(n_cols, rows * n_cols, rows, 0), side_mode=2, side_scale=gate[1])
         ops.conv_block(dt, dz, (1, rows, c_pad, c_pad, rows * c_pad), L.w_fwd, 1, 0, c_pad, rows, g_in,
                        (n_cols, rows * n_cols), block_n=block_n, w_mn_major=(n_cols, 0), **kw)
         return g_in
@@ -214,6 +268,8 @@ def _data_grad(dt, L, dz, n, c_pad, fan_in=None, fan_rows=0, fan_off=0, fan_mul=
     if fan_in is not None:
         # residual x[:, :, off : off + fan_rows]: input row t' receives block-output row t' - off
         kw = dict(res=fan_in, res_view=(c_pad, fan_rows * c_pad, 1, -fan_off), res_rows=fan_rows)
+    if gate is not None:
+        kw.update(side=gate[0], side_view=(cin_pad, L.t_in * cin_pad, L.t_in, 0), side_mode=2, side_scale=gate[1])
     ops.conv_block(dt, dz, (n, L.t_out, c_pad, c_pad, L.t_out * c_pad), L.w_fwd, taps, -d, c_pad, L.t_in, g_in,
                    (cin_pad, L.t_in * cin_pad), block_n=block_n, w_mn_major=(cin_pad, cin_pad), **kw)
     return g_in
@@ -306,6 +362,24 @@ class _StackTrainFn(torch.autograd.Function):
         for idx in range(len(layers) - 1, -1, -1):
             L = layers[idx]
             rows = n * L.t_out
+            if L.fused is not None:
+                # fused expand layer: `g` arrived gated by its ReLU / dropout mask (gm); everything else is P = gm^T X
+                F = L.fused
+
+                def expand_grads(L=L, F=F, gm=g):
+                    p_packed = torch.zeros((1, c_pad, 256), dtype=torch.float32, device=gm.device)
+                    keep.append(p_packed)
+                    seqs, rws = F['xv'][0], F['xv'][1]
+                    ops.wgrad(dt, gm, (seqs, rws, c_pad, rws * c_pad), L.a_in, F['av'], c_pad, 256, 1, p_packed,
+                              block_n=256)
+                    dw, dgamma, dbeta = ops.expand_bwd_finish(dt, p_packed, F['wg'], F['gram'], L.w_fwd, F['k_total'],
+                                                              F['ones_col'], L.scale, L.mean, L.invstd, gscale,
+                                                              L.bn.num_features, c_pad, L.c_in, L.c_in_pad, L.taps)
+                    done(L.bn.weight, dgamma)
+                    done(L.bn.bias, dbeta)
+                    done(L.conv.weight, dw)
+                on_side(expand_grads, g)
+                break
             dz, dgamma, dbeta = ops.bn_act_bwd(dt, g, L.z, L.scale, L.shift, L.mean, L.invstd, rows, L.bn.num_features,
                                                L.drop, gscale, count=L.count, group=sync_bn_group, sums=sums_all[idx])
             done(L.bn.weight, dgamma)
@@ -320,7 +394,10 @@ class _StackTrainFn(torch.autograd.Function):
                 g = _data_grad(dt, L, dz, n, c_pad)
             else:
                 g_block, fan_rows, fan_off, fan_mul = fan
-                g = _data_grad(dt, L, dz, n, c_pad, fan_in=g_block, fan_rows=fan_rows, fan_off=fan_off, fan_mul=fan_mul)
+                below = layers[idx - 1].fused
+                gate = (below['a'], below['keep_scale']) if below is not None else None
+                g = _data_grad(dt, L, dz, n, c_pad, fan_in=g_block, fan_rows=fan_rows, fan_off=fan_off, fan_mul=fan_mul,
+                               gate=gate)
         if side is not None:
             main.wait_stream(side)
         if grad_finish_hook is not None:

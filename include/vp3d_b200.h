@@ -41,6 +41,16 @@ int vp3d_set_sm_limit(int sms);
  * launch. Initial value from the environment variable VP3D_K1_2CTA ("0", "force"). */
 int vp3d_set_pair_mode(int mode);
 
+/* Dropout description shared by forward and backward: keep-mask = Philox4x32-10(seed, stream, row, channel group)
+ * >= p; kept values are multiplied by 1 / (1 - p) (nn.Dropout, TemporalModel.py:28,127,134-135). p == 0: off. */
+typedef struct vp3d_dropout {
+  float p;
+  unsigned long long seed;
+  unsigned long long stream;              /* distinguishes layers */
+  const unsigned long long* step_counter; /* optional device counter read by the kernel and mixed into the Philox
+                                             counter: a captured CUDA graph draws a fresh mask on every replay */
+} vp3d_dropout;
+
 /* ---------------------------------------------------------------------------------------------------------------
  * K1  temporal convolution block: Conv1d (+ folded BatchNorm1d + ReLU + residual slice-add) as one implicit GEMM.
  * Replaces nn.Conv1d / nn.BatchNorm1d(eval) / nn.ReLU / `res + x` of common/models/TemporalModel.py:126-138
@@ -108,12 +118,35 @@ typedef struct vp3d_conv_args {
 
   double* stat_sum;        /* optional [n_pad] accumulators (+=) of the output AS STORED (16-bit) and its square over the */
   double* stat_sqsum;      /* valid rows: train-mode BatchNorm statistics; fp32 per CTA, double across CTAs */
+
+  /* Fused train-mode epilogue (CTA-pair kernel: 16-bit operands and output, block_n 256, no dyn_offsets; the launch
+   * takes that kernel whatever vp3d_set_pair_mode says and fails with VP3D_ERR_UNSUPPORTED where it cannot run). */
+  const vp3d_dropout* drop;/* optional: nn.Dropout after the ReLU (TemporalModel.py:127 / :189), the same counter-based mask as
+                              vp3d_bn_act_fwd draws for (flat output row s * rows_out + t, channel) */
+  const void* side;        /* optional side input [s][side_rows][n_pad] in the operand type, fetched by TMA in the output's
+                              tiles (column n of output row t reads side row t + side_row_off; rows outside read 0) */
+  int side_mode;           /* 0: none. 1: out += side (a residual whose rows map 1:1; the generic `res` also covers strided
+                              rows and column windows). 2: out = side > 0 ? out * side_scale : 0 -- the ReLU + dropout mask
+                              of a layer recovered from its stored activation (clipped and dropped elements are 0),
+                              applied to the gradient that reaches that activation (data-gradient GEMM of the next
+                              layer); with stat_sum the column sums of the gated gradient come out of the same pass */
+  int side_row_off;
+  long long side_row_stride;
+  long long side_seq_stride;
+  long long side_rows;
+  float side_scale;
 } vp3d_conv_args;
 
 int vp3d_conv_block_fwd(const vp3d_conv_args* args, void* stream);
 
 /* fp32 [rows][c] -> dtype [rows][c_pad], zero padded (the (N,T,J*F) model input, TemporalModel.py:67-68). */
 int vp3d_pack_rows(int dtype, const float* src, void* dst, long long rows, int c, int c_pad, void* stream);
+
+/* The same with 1.0 in padding column `ones_col` (c <= ones_col < c_pad; F16 / BF16, c_pad % 8 == 0): the Gram matrix
+ * of the packed rows then carries their column sums and the row count (vp3d_expand_bn_stats). The convolution weights
+ * of a padding column are zero, so the layer output does not change. */
+int vp3d_pack_rows_ones(int dtype, const float* src, void* dst, long long rows, int c, int c_pad, int ones_col,
+                        void* stream);
 
 /* nn.Conv1d weight (c_out, c_in, taps) fp32 (TemporalModel.py:33,102,113-118) -> packed GEMM operand.
  * transpose == 0: dst[rows_pad][taps * k_pad_per_tap], dst[n][tap * k_pad_per_tap + ci] = w[n][ci][tap]
@@ -246,6 +279,7 @@ typedef struct vp3d_wgrad_args {
   int b_tap_row_step;      /* dilated convolution: tap k reads input row r + k * dilation */
   long long b_tap_col_step;/* stride == width convolution on the reshaped view: tap k reads columns k * c_in_pad + ci */
   float* dw_packed;        /* [taps][co_pad][ci_pad] fp32, accumulated with red.add */
+  long long dz_cols;       /* 0: co_pad. Otherwise the real column count of `dz` (<= co_pad); the rest reads as zero */
 } vp3d_wgrad_args;
 int vp3d_wgrad(const vp3d_wgrad_args* args, void* stream);
 
@@ -255,6 +289,29 @@ int vp3d_wgrad(const vp3d_wgrad_args* args, void* stream);
  * (taps = 1, b_tap_col_step = 0 on the [rows][taps * c_in_pad] view) has tap_stride = c_in_pad, row_stride = 256. */
 int vp3d_wgrad_finish(const float* dw_packed, float* dw, int c_out, int c_in, int taps, long long tap_stride,
                       long long row_stride, const float* gscale_buf, void* stream);
+
+/* Train-mode BatchNorm of the EXPAND layer (TemporalModel.py:127 / :189: expand_bn(expand_conv(x))) from the Gram matrix
+ * of the layer input instead of a pass over the layer output: the convolution is linear with a contraction of only
+ * k_total = taps * c_in_pad <= 256 columns, so with X the [rows][k_total] view of the packed input (one padding column
+ * `ones_col` holding 1.0), gram = X^T X (fp32 [256][256], e.g. vp3d_wgrad with both operands = X) and w the packed
+ * weights [c_pad][k_total]:  mean_c = w_c . s / n,  var_c = w_c^T (G / n - s s^T / n^2) w_c  (s = gram[ones_col][:],
+ * n = gram[ones_col][ones_col]). Writes scale / shift / mean / invstd like vp3d_bn_finalize (running statistics and
+ * num_batches_tracked updated the same way; momentum < 0 = cumulative average) and wg[c_pad][256] = W * gram, which
+ * vp3d_expand_bwd_finish reads again. */
+int vp3d_expand_bn_stats(int dtype, const float* gram, const void* w, int k_total, int ones_col, const float* gamma,
+                         const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                         long long* num_batches_tracked, float* scale, float* shift, float* mean, float* invstd,
+                         float* wg, int c, int c_pad, void* stream);
+/* Backward of the same layer from p_packed[c_pad][256] = gm^T X (vp3d_wgrad), gm = the gradient wrt the layer's
+ * activation gated by its ReLU / dropout mask and scaled by gscale_buf[0] (vp3d_conv_block_fwd side_mode 2):
+ *   Sg = p[c][ones_col],  Sgz = sum_k w[c][k] p[c][k],  d_beta = Sg,  d_gamma = invstd (Sgz - mean Sg),
+ *   dw[c][ci][tap] = scale_c ( p[c][k] - Sg s_k / n - d_gamma invstd (wg[c][k] - mean s_k) / n ),  k = tap * c_in_pad + ci
+ * (all multiplied by gscale_buf[1]) -- the sum over rows of dz x_k with dz the BatchNorm backward, without materialising
+ * dz and without a reduction pass over the activation gradient. */
+int vp3d_expand_bwd_finish(int dtype, const float* p_packed, const float* wg, const float* gram, const void* w, int k_total,
+                           int ones_col, const float* scale, const float* mean, const float* invstd,
+                           const float* gscale_buf, int c, int c_pad, int c_in, int c_in_pad, int taps, float* dw,
+                           float* d_gamma, float* d_beta, void* stream);
 
 /* Train-mode nn.BatchNorm1d statistics (TemporalModel.py:32,117,119 in train()): from the per-channel sum / sum of
  * squares over `count` rows (accumulated by vp3d_conv_block_fwd) produce the forward affine scale = gamma * invstd,
@@ -269,15 +326,6 @@ int vp3d_bn_finalize(const double* stat_sum, const double* stat_sqsum, long long
  * as the GEMM epilogue's stat_sum / stat_sqsum, for layers whose contraction is too short to hide that reduction. */
 int vp3d_col_stats(int dtype, const void* z, long long rows, int c_pad, double* sum, double* sqsum, void* stream);
 
-/* Dropout description shared by forward and backward: keep-mask = Philox4x32-10(seed, stream, row, channel group)
- * >= p; kept values are multiplied by 1 / (1 - p) (nn.Dropout, TemporalModel.py:28,127,134-135). p == 0: off. */
-typedef struct vp3d_dropout {
-  float p;
-  unsigned long long seed;
-  unsigned long long stream;              /* distinguishes layers */
-  const unsigned long long* step_counter; /* optional device counter read by the kernel and mixed into the Philox
-                                             counter: a captured CUDA graph draws a fresh mask on every replay */
-} vp3d_dropout;
 /* *counter += inc on the stream (one thread): the per-step tick of step_counter, capturable in a CUDA graph. */
 int vp3d_counter_add(unsigned long long* counter, unsigned long long inc, void* stream);
 

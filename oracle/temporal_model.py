@@ -182,7 +182,8 @@ def _ste_round(v, dtype):
     return v + (v.to(dtype).to(torch.float32) - v).detach()
 
 
-def forward_lowp_train(sd, x, filter_widths, causal=False, strided=True, dtype=torch.float16, masks=None, dense=False):
+def forward_lowp_train(sd, x, filter_widths, causal=False, strided=True, dtype=torch.float16, masks=None, dense=False,
+                       expand_unrounded=True):
     """Train-mode forward with the rounding points of the CUDA training path emulated on the CPU (see
     train_step_grads_lowp). Returns (prediction with grad_fn, dict of leaf parameters)."""
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
@@ -191,18 +192,21 @@ def forward_lowp_train(sd, x, filter_widths, causal=False, strided=True, dtype=t
     rnd = lambda v: _ste_round(v, dtype)
     mask_iter = iter(masks) if masks is not None else None
 
-    def bn_act(z, prefix, res=None):
+    def bn_act(z, prefix, res=None, round_z=True):
         mean = z.mean(dim=(0, 2), keepdim=True)
         var = z.var(dim=(0, 2), unbiased=False, keepdim=True)
         scale = params[prefix + '.weight'].view(1, -1, 1) / torch.sqrt(var + BN_EPS)
         shift = params[prefix + '.bias'].view(1, -1, 1) - mean * scale
-        pre = rnd(z) * scale + shift
+        pre = (rnd(z) if round_z else z) * scale + shift
         y = F.relu(pre) if mask_iter is None else pre * next(mask_iter).to(pre.dtype)
         return rnd(y if res is None else y + res)
 
     n, t = x.shape[0], x.shape[1]
     h = rnd(x.reshape(n, t, -1).permute(0, 2, 1))
-    h = bn_act(F.conv1d(h, rnd(params['expand_conv.weight']), None, stride=plan['expand_stride']), 'expand_bn')
+    # the expand layer's GEMM epilogue applies BatchNorm to the fp32 accumulator (its raw output is never stored), every
+    # other layer stores the raw output in the operand type first
+    h = bn_act(F.conv1d(h, rnd(params['expand_conv.weight']), None, stride=plan['expand_stride']), 'expand_bn',
+               round_z=not expand_unrounded)
     for i, blk in enumerate(plan['blocks']):
         pad, shift = plan['pad'][i + 1], plan['causal_shift'][i + 1]
         if strided:
