@@ -173,6 +173,67 @@ def cpu_port_train_samples_per_s(batch=32, repeats=2):
 REF_SAMPLE = (4, 4096)     # sequences x output frames of one CPU step: the sample cpu_baseline times as well
 
 
+def rel_fro(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def infer_parity(model, x_host, x_dev, picks):
+    """Parity of the MEASURED forward at the MEASURED size: sequences `picks` of one more forward over the timed batch
+    (same launches: CTA-pair kernel, full 4338-frame length) against the CPU oracle on the same inputs."""
+    from oracle import loss as oloss
+    from oracle import temporal_model as otm
+    from vp3d_b200 import native
+    with torch.no_grad():
+        y = model(x_dev)[picks].float().cpu()
+        ref = otm.forward(oracle_state(), x_host[picks], FW)
+    g = torch.Generator().manual_seed(5)
+    tgt = ref + 0.05 * torch.randn(ref.shape, generator=g)
+    d_mm = abs(float(oloss.mpjpe(y, tgt)) - float(oloss.mpjpe(ref, tgt))) * 1e3
+    sm = native.sm_count()
+    tiles = x_dev.shape[0] * ((x_dev.shape[1] - 8 + 127) // 128) * 4      # block-1 launch: rows / 128 x 1024 / 256
+    return {'rel_fro': rel_fro(y, ref), 'mpjpe_delta_mm': d_mm, 'max_abs': float((y - ref).abs().max()),
+            'n_frames': int(y.shape[0] * y.shape[1]), 'sequences': list(picks), 'frames_per_sequence': int(x_dev.shape[1]),
+            'kernel': 'conv_gemm_pair_kernel (cta_group::2)' if tiles >= 2 * sm and os.environ.get('VP3D_K1_2CTA') != '0'
+                      else 'conv_gemm_kernel',
+            'oracle': 'oracle/temporal_model.py forward (fp32 torch CPU), pinned to the reference by tests/golden',
+            'tolerance': {'rel_fro': 1e-3, 'mpjpe_delta_mm': 1e-2}}
+
+
+def train_parity(state, x2d, tgt, dtype):
+    """One dropout-0 training step (forward, mpjpe, backward) at the BENCHMARK batch on the GPU path against the fp32
+    CPU oracle on the same batch and weights: loss, prediction, gradients. (BatchNorm couples the samples of a batch,
+    so the oracle has to see the whole batch, not a slice.)"""
+    from common.loss import mpjpe
+    from common.models.TemporalModel import TemporalModelOptimized1f
+    from oracle import loss as oloss
+    from oracle import temporal_model as otm
+    sd = {k: v.detach().float().cpu() if v.dtype.is_floating_point else v.detach().cpu() for k, v in state.items()}
+    m = TemporalModelOptimized1f(17, 2, 17, FW, dropout=0.0, channels=1024)
+    m.load_state_dict(sd)
+    m = m.to(x2d.device).train()
+    m.operand_dtype = dtype
+    pred = m(x2d)
+    loss = mpjpe(pred, tgt)
+    loss.backward()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    torch.set_num_threads(os.cpu_count() or 1)
+    loss_o, pred_o, grads_o, _ = otm.train_step_grads(sd, x2d.cpu(), tgt.cpu(), FW, strided=True)
+    cpu_s = time.perf_counter() - t0
+    gerr = {k: rel_fro(p.grad, grads_o[k]) for k, p in m.named_parameters()}
+    worst = max(gerr, key=gerr.get)
+    d_mm = abs(float(oloss.mpjpe(pred.detach().cpu(), tgt.cpu())) - float(loss_o)) * 1e3
+    return {'batch': int(x2d.shape[0]), 'dropout': 0.0, 'loss_gpu': float(loss), 'loss_oracle': float(loss_o),
+            'loss_rel': abs(float(loss) - float(loss_o)) / abs(float(loss_o)), 'pred_rel_fro': rel_fro(pred.detach(), pred_o),
+            'mpjpe_delta_mm': d_mm, 'grad_rel_fro': {'expand_conv.weight': gerr['expand_conv.weight'],
+                                                    'layers_conv.0.weight': gerr['layers_conv.0.weight'],
+                                                    'shrink.weight': gerr['shrink.weight'], 'worst': [worst, gerr[worst]]},
+            'oracle': 'oracle/temporal_model.py train_step_grads (fp32 torch CPU autograd), %.1f s' % cpu_s,
+            'tolerance': {'pred_rel_fro': 2e-3, 'loss_rel': 1e-3, 'grad_rel_fro': '1.2e-1 (16-bit operands flip ReLU '
+                          'decisions; DESIGN.md section 1)'}}
+
+
 def run_reference_arm(args, rank, world):
     """--impl reference: the CPU port of the reference (oracle/temporal_model.py; the reference is a Python tree that
     cannot travel to the GPU box) on all host threads. A step = one eval forward over REF_SAMPLE (the same bounded
@@ -474,14 +535,18 @@ def bench_train(args, rank, world, dev, steps, warm):
 
     # ---- projection kernel alone: 4 rotating input sets (400 MB > L2), 40 launches captured in one CUDA graph so that the
     # events bracket kernel time only (a 30 us kernel issued from Python is launch-bound)
+    # Every launch of the replay also gets its OWN output buffer (they are kept alive during the capture, 40 x 34 MB):
+    # when the outputs were freed and re-allocated inside the capture every launch re-wrote one L2-resident buffer and
+    # a third of the "bytes" never reached HBM (4.7 MB of DRAM writes for 33.8 MB of output).
     psets = [tuple(v.clone() for v in (Wd, qd, td, camd)) for _ in range(4)]
     for ps in psets:
         world_to_image(*ps, return_camera_space=False)
     torch.cuda.synchronize()
     pg = torch.cuda.CUDAGraph()
+    keep_out = []
     with torch.cuda.graph(pg):
         for k in range(40):
-            world_to_image(*psets[k % 4], return_camera_space=False)
+            keep_out.append(world_to_image(*psets[k % 4], return_camera_space=False)[1])
     pg.replay()
     torch.cuda.synchronize()
     e6, e7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -490,7 +555,7 @@ def bench_train(args, rank, world, dev, steps, warm):
     e7.record()
     torch.cuda.synchronize()
     proj_ms = e6.elapsed_time(e7) / 40
-    del pg
+    del pg, keep_out
 
     # the same kernel on a 4x larger launch (4096 windows): a 21 us launch spends ~5 us in launch gap, pipeline fill and
     # tail, so the fraction at the training-batch size understates what the kernel sustains
@@ -501,9 +566,10 @@ def bench_train(args, rank, world, dev, steps, warm):
         world_to_image(*bs, return_camera_space=False)
     torch.cuda.synchronize()
     pg2 = torch.cuda.CUDAGraph()
+    keep_out = []
     with torch.cuda.graph(pg2):
         for k in range(10):
-            world_to_image(*bsets[k % 2], return_camera_space=False)
+            keep_out.append(world_to_image(*bsets[k % 2], return_camera_space=False)[1])
     pg2.replay()
     torch.cuda.synchronize()
     e8, e9 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -512,15 +578,22 @@ def bench_train(args, rank, world, dev, steps, warm):
     e9.record()
     torch.cuda.synchronize()
     proj_big_ms = e8.elapsed_time(e9) / 10
-    del pg2, bsets
+    del pg2, bsets, keep_out
 
+    multi = None
     if world > 1:
+        multi = bench_train_multi(args, rank, world, dev, model, opt, mpjpe, steps, world_to_image, graphed is not None)
         tt = torch.tensor([ms, ms_e2e, gemm_ms, proj_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, ms_e2e, gemm_ms, proj_ms = [float(v) for v in tt.tolist()]
         ddp.disable_grad_sync()
     if rank != 0:
         return None
+    parity = None
+    if not args.no_parity:
+        with torch.no_grad():
+            x2d_p = world_to_image(Wd, qd, td, camd, return_camera_space=False)[1]
+        parity = train_parity(model.state_dict(), x2d_p, tgt, model.operand_dtype)
     peaks = load_peaks()
     total = batch * world * steps
     achieved = TRAIN_FLOP_PER_SAMPLE * batch / (gemm_ms * 1e-3) / 1e12
@@ -539,7 +612,10 @@ def bench_train(args, rank, world, dev, steps, warm):
                    'bn': 'per-replica batch statistics',
                    'launch': 'one CUDA graph per step (vp3d_b200.graphs.GraphedTrainStep)' if use_graph else 'eager'},
         'e2e': {'value': total / (ms_e2e * 1e-3), 'unit': 'samples/s', 'ms_per_step': ms_e2e / steps,
-                'h2d_bytes_per_step': sum(v.numel() * 4 for v in (Wh, qh, th, camh)), 'd2h_bytes_per_step': 4},
+                'h2d_bytes_per_step': sum(v.numel() * 4 for v in (Wh, qh, th, camh)), 'd2h_bytes_per_step': 4,
+                'note': 'throughput, pipelined across steps: the batch of step i+1 is uploaded (pinned host -> device, '
+                        'side stream) while step i computes; the host reads the loss of step i after it has enqueued '
+                        'step i+1; every step moves its own batch and its loss inside the timed region'},
         'e2e_device_feeder': {'value': batch * world * steps / (ms_feed * 1e-3), 'unit': 'samples/s',
                               'ms_per_step': ms_feed / steps, 'h2d_bytes_per_step': batch * 16, 'd2h_bytes_per_step': 4,
                               'note': 'vp3d_b200.feeder.DeviceWindowFeeder: sequences resident in HBM, windows gathered, '
@@ -553,18 +629,119 @@ def bench_train(args, rank, world, dev, steps, warm):
                      'traffic': load_traffic().get('train_gemm_avg_bytes_per_launch'),
                      'algorithmic_flop_per_sample': TRAIN_FLOP_PER_SAMPLE,
                      'gemm_ms_per_step': gemm_ms, 'conv_fwd_dgrad_ms': conv_ms, 'wgrad_ms': wgrad_ms,
-                     'bn_act_ms_per_step': bn_ms, 'kernel_share_of_step': gemm_ms / (ms / steps)},
+                     'bn_act_ms_per_step': bn_ms, 'kernel_share_of_step': gemm_ms / (ms / steps),
+                     # the whole step (every launch, Adam and projection included) against the same peak
+                     'achieved_whole_step': TRAIN_FLOP_PER_SAMPLE * batch / (ms / steps * 1e-3) / 1e12,
+                     'frac_whole_step': TRAIN_FLOP_PER_SAMPLE * batch / (ms / steps * 1e-3) / 1e12 / peaks['sustained']},
+        'parity': parity,
         'projection_roofline': {'bound': 'hbm', 'kernel': 'project_frames_kernel (bulk-copy staged tiles of whole frames)', 'achieved': proj_gbs,
                                 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': proj_gbs / peaks['hbm_gbs'],
                                 'ms_per_launch': proj_ms, 'algorithmic_bytes_per_frame': PROJ_BYTES_PER_FRAME,
                                 'frames_per_launch': batch * RF,
-                                'how': '40 launches over 4 rotating input sets (> L2) as one CUDA graph replay, CUDA events',
+                                'how': '40 launches over 4 rotating input sets (> L2), each launch writing its own output buffer, as one CUDA graph replay, CUDA events',
                                 'traffic': load_traffic().get('project_frames_kernel'),
                                 'large_launch': {'frames_per_launch': batch * big * RF, 'ms_per_launch': proj_big_ms,
                                                  'achieved': proj_big_gbs, 'frac': proj_big_gbs / peaks['hbm_gbs'],
                                                  'how': '10 launches over 2 rotating input sets as one CUDA graph replay'}},
         'mpjpe_ms_per_step': mpjpe_ms,
+        'multi_gpu': multi,
     }
+
+
+def bench_train_multi(args, rank, world, dev, model, opt, loss_fn, steps, world_to_image, use_graph):
+    """N > 1 only, after the weak-scaling loop: (1) every rank must hold identical parameters after the timed steps;
+    (2) STRONG scaling -- the same step at global batch = args.batch (args.batch / N per GPU); (3) SyncBN -- one
+    dropout-0 forward + backward of a global batch sharded over the ranks with synchronised BatchNorm statistics must
+    give the loss ONE GPU computes on the whole batch (the reference's semantics are single-GPU batch statistics,
+    TemporalModel.py:32,117,119)."""
+    import torch.distributed as dist
+    from common.camera import world_to_camera
+    from common.models.TemporalModel import TemporalModelOptimized1f
+    from vp3d_b200 import ddp
+    out = {}
+    # (1) parameter checksum: MIN == MAX over ranks
+    chk = torch.stack([p.detach().double().sum() for p in model.parameters()]).sum().reshape(1)
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    out['params_in_sync'] = bool(lo.item() == hi.item())
+    out['param_checksum_min_max'] = [float(lo), float(hi)]
+
+    def batch_of(seed, n):
+        W, q, t, cam = [v.to(dev) for v in synthetic_training_batch(seed, n)]
+        mid = RF // 2
+        with torch.no_grad():
+            Xc = world_to_camera(W[:, mid:mid + 1].contiguous(), q[:, mid:mid + 1].contiguous(),
+                                 t[:, mid:mid + 1].contiguous())
+        return (W, q, t, cam), (Xc - Xc[:, :, :1]).contiguous()
+
+    pre = lambda W_, q_, t_, c_: world_to_image(W_, q_, t_, c_, return_camera_space=False)[1]
+    # (2) strong scaling: global batch fixed at args.batch
+    per = max(args.batch // world, 1)
+    inputs, tg = batch_of(1000 + rank, per)
+    if use_graph:
+        from vp3d_b200.graphs import GraphedTrainStep
+        gs = GraphedTrainStep(model, opt, loss_fn, inputs, tg, preprocess=pre)
+
+        def run():
+            return gs(gs.static_inputs)
+    else:
+        def run():
+            opt.zero_grad(set_to_none=True)
+            loss = loss_fn(model(pre(*inputs)), tg)
+            loss.backward()
+            opt.step()
+            return loss.detach()
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    tt = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    out['strong'] = {'global_batch': per * world, 'per_gpu_batch': per, 'ms_per_step': float(tt) / steps,
+                     'value': per * world * steps / (float(tt) * 1e-3), 'unit': 'samples/s',
+                     'bn': 'per-replica batch statistics'}
+    chk = torch.stack([p.detach().double().sum() for p in model.parameters()]).sum().reshape(1)
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    out['strong']['params_in_sync'] = bool(lo.item() == hi.item())
+
+    # (3) SyncBN: every rank builds the SAME global batch (seed without the rank) and takes its slice
+    g_inputs, g_tgt = batch_of(555, per * world)
+    ref_model = TemporalModelOptimized1f(17, 2, 17, FW, dropout=0.0, channels=1024)
+    ref_model.load_state_dict(oracle_state())
+    ref_model = ref_model.to(dev).train()
+    ref_model.operand_dtype = model.operand_dtype
+    ddp.disable_grad_sync()
+    x_all = pre(*g_inputs)
+    single = loss_fn(ref_model(x_all), g_tgt)                     # one GPU, whole batch: the reference's semantics
+    single.backward()
+    g_single = ref_model.expand_bn.weight.grad.detach().clone()
+    ref_model.zero_grad(set_to_none=True)
+    ref_model.load_state_dict(oracle_state())                       # running statistics back to the start
+    ddp.enable_sync_bn()
+    sync = ddp.enable_grad_sync()
+    sl = slice(rank * per, (rank + 1) * per)
+    local = loss_fn(ref_model(x_all[sl].contiguous()), g_tgt[sl].contiguous())
+    local.backward()
+    g_sync = ref_model.expand_bn.weight.grad.detach().clone()       # averaged over ranks by the hook
+    ddp.enable_sync_bn(on=False)
+    glob = local.detach().clone()
+    dist.all_reduce(glob, op=dist.ReduceOp.AVG)
+    out['syncbn'] = {'global_batch': per * world, 'loss_one_gpu': float(single), 'loss_syncbn': float(glob),
+                     'loss_rel_delta': abs(float(glob) - float(single)) / abs(float(single)),
+                     'expand_bn_weight_grad_rel': rel_fro(g_sync, g_single),
+                     'collectives_per_step': sync.collectives, 'tolerance': {'loss_rel_delta': 1e-3}}
+    return out
 
 
 def bench_stream(args, rank, world, dev):
@@ -634,6 +811,7 @@ def main():
     ap.add_argument('--optimizer', default='fused', choices=['fused', 'torch'],
                     help='training: vp3d_b200.optim.FusedAdam (default) or stock torch.optim.Adam')
     ap.add_argument('--no-graph', action='store_true', help='training: launch kernels eagerly instead of one CUDA graph')
+    ap.add_argument('--no-parity', action='store_true', help='skip the oracle comparison of the measured sizes (outside the timed regions)')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
@@ -810,6 +988,7 @@ def main():
                     'launches_per_step': conv_launches_per_step, 'avg_launch_ms': conv_ms_per_step / conv_launches_per_step,
                     'algorithmic_flop_per_frame': FLOP_PER_FRAME,
                     'kernel_share_of_step': conv_ms_per_step / (ms / steps)}
+        parity = None if args.no_parity else infer_parity(model, x_host, x_dev, [0, seqs - 1] if seqs > 1 else [0])
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': warm,
                 'ms_per_step': ms / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': args.dtype, 'data': 'synthetic',
@@ -819,7 +998,12 @@ def main():
                            'exceed the 126 MB L2, no flush needed' % (seqs * t_in * 1024 * 2 / 1e6),
                            'weights': 'random init (seed 1234), BN statistics randomised'},
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': x_host.numel() * 4,
-                        'd2h_bytes_per_step': y_host.numel() * 4, 'ms_per_step': ms_e2e / steps},
+                        'd2h_bytes_per_step': y_host.numel() * 4, 'ms_per_step': ms_e2e / steps,
+                        'note': 'throughput, pipelined across steps (vp3d_b200.pipeline.HostInferPipeline): a step '
+                                'submits its pinned host batch and waits until the PREVIOUS step\'s result is in host '
+                                'memory; upload, compute and download of neighbouring steps overlap on three streams; '
+                                'the region ends when the last result byte has landed'},
+                'parity': parity,
                 'gpu_launches': launches_per_step * steps,
                 'roofline': roofline, 'clocks': clocks}
         if not args.no_cpu_baseline:

@@ -326,6 +326,20 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
   p.out_round_tf32 = a->out_round_tf32;
   p.stat_sum = a->stat_sum;
   p.stat_sqsum = a->stat_sqsum;
+  if (a->fin != nullptr) {
+    const vp3d_bn_fin* f = a->fin;
+    if (a->stat_sum == nullptr) return fail(VP3D_ERR_INVALID, "fin needs stat_sum / stat_sqsum");
+    if (!f->gamma || !f->beta || !f->scale || !f->shift || !f->mean || !f->invstd || !f->done_counter || f->c <= 0 ||
+        f->c > a->n_pad || (f->running_mean == nullptr) != (f->running_var == nullptr))
+      return fail(VP3D_ERR_INVALID, "fin: null pointer or bad channel count");
+    if (f->count <= 1)
+      return fail(VP3D_ERR_INVALID, "Expected more than 1 value per channel when training (got %lld)", f->count);
+    const double n = (double)f->count;
+    p.fin = vp3d::BnFinalizeParams{a->stat_sum, a->stat_sqsum, 1.0 / n, (float)(n / (n - 1.0)), f->gamma, f->beta, f->eps,
+                                   f->momentum, f->running_mean, f->running_var, f->num_batches_tracked, f->scale,
+                                   f->shift, f->mean, f->invstd, f->c};
+    p.fin_counter = f->done_counter;
+  }
   if (want_drop) p.drop = drop_of(a->drop);
   p.side_mode = a->side_mode;
   p.side_row_off = a->side_row_off;
@@ -684,7 +698,8 @@ int vp3d_wgrad(const vp3d_wgrad_args* a, void* stream) {
     const long long flush = 8;
     long long best = -1;
     int best_s = 1;
-    for (int s_try = 1; s_try <= 64 && s_try <= kb_all; ++s_try) {
+    const int s_max = a->max_slices > 0 ? a->max_slices : 64;
+    for (int s_try = 1; s_try <= s_max && s_try <= kb_all; ++s_try) {
       const long long items = (long long)p.num_tiles * s_try;
       const long long waves = (items + dev->sm_count - 1) / dev->sm_count;
       const long long cost = waves * ((kb_all + s_try - 1) / s_try + flush);

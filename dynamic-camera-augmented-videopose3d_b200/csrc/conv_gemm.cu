@@ -18,6 +18,7 @@
 //                                convert, 16-byte stores; overlaps the next tile's MMAs through the 2nd TMEM buffer
 #include "ptx.cuh"
 #include "kernels.h"
+#include "bn_tail.cuh"
 
 namespace vp3d {
 
@@ -482,6 +483,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+  if (p.fin.sum != nullptr)
+    bn_finalize_tail(p.fin, p.fin_counter, p.n_tiles * BN, reinterpret_cast<volatile int*>(reinterpret_cast<uint8_t*>(bars) + Cfg::kBarBytes - 4));
 }
 
 template <int DT, int BN, bool BMN>

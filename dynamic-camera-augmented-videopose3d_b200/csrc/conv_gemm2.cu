@@ -18,6 +18,7 @@
 #include "ptx.cuh"
 #include "kernels.h"
 #include "dropout.cuh"
+#include "bn_tail.cuh"
 
 namespace vp3d {
 namespace {
@@ -367,13 +368,38 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
         if (EPI && drop.on) {
-          // the mask of train.cu's passes: one Philox block per (row pair, 8-channel group), this row's half of it
+          // the mask of train.cu's passes: one Philox block per (row pair, 8-channel group) holds the bits of both rows
+          // of the pair. Adjacent lanes own the two rows of a pair whenever the warp's first row is even: each of them
+          // then draws TWO of the chunk's four blocks and hands the partner its half (4 shuffles instead of 2 blocks).
           const long long grow = (long long)tc.seq * p.rows_out + t;
+          const bool h = (grow & 1) != 0;
+          uint32_t lo[4], hi[4];
+          if (((grow - lane) & 1) == 0) {
+            const int jg = (lane & 1) * 2;
+            const uint4 b0 = drop_bits(drop, grow >> 1, (col0 >> 3) + jg);
+            const uint4 b1 = drop_bits(drop, grow >> 1, (col0 >> 3) + jg + 1);
+            const uint32_t m0 = h ? b0.z : b0.x, m1 = h ? b0.w : b0.y, m2 = h ? b1.z : b1.x, m3 = h ? b1.w : b1.y;
+            const uint32_t r0 = __shfl_xor_sync(0xffffffffu, h ? b0.x : b0.z, 1);
+            const uint32_t r1 = __shfl_xor_sync(0xffffffffu, h ? b0.y : b0.w, 1);
+            const uint32_t r2 = __shfl_xor_sync(0xffffffffu, h ? b1.x : b1.z, 1);
+            const uint32_t r3 = __shfl_xor_sync(0xffffffffu, h ? b1.y : b1.w, 1);
+            const bool even = jg == 0;   // even lane drew groups 0, 1 and received 2, 3; odd lane the other way round
+            lo[0] = even ? m0 : r0; hi[0] = even ? m1 : r1;
+            lo[1] = even ? m2 : r2; hi[1] = even ? m3 : r3;
+            lo[2] = even ? r0 : m0; hi[2] = even ? r1 : m1;
+            lo[3] = even ? r2 : m2; hi[3] = even ? r3 : m3;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 bits = drop_bits(drop, grow >> 1, (col0 >> 3) + j);
+              lo[j] = h ? bits.z : bits.x;
+              hi[j] = h ? bits.w : bits.y;
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint4 bits = drop_bits(drop, grow >> 1, (col0 >> 3) + j);
             float m[8];
-            drop_mult8(drop, (grow & 1) ? bits.z : bits.x, (grow & 1) ? bits.w : bits.y, m);
+            drop_mult8(drop, lo[j], hi[j], m);
 #pragma unroll
             for (int k = 0; k < 8; ++k) f[8 * j + k] *= m[k];
           }
@@ -485,6 +511,9 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tcgen05_fence_after();
     tmem_dealloc_2cta(tmem_base, kTmemCols);
   }
+  if (p.fin.sum != nullptr)
+    bn_finalize_tail(p.fin, p.fin_counter, p.n_tiles * kBN,
+                     reinterpret_cast<volatile int*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes - 4));
 }
 
 template <int DT, bool BMN, int EPI>

@@ -23,6 +23,18 @@ inline cudaError_t set_max_smem_once(const void* func, int bytes, std::atomic<un
   return e;
 }
 
+// bn_finalize folded into bn_act_fwd: sum == nullptr -> the kernel reads ready-made scale / shift instead
+struct BnFinalizeParams {
+  const double* sum; const double* sqsum;
+  double inv_n;          // 1 / rows the sums were taken over
+  float unbias;          // n / (n - 1): running_var takes the unbiased variance
+  const float* gamma; const float* beta;
+  float eps, momentum;
+  float* running_mean; float* running_var; long long* nbt;
+  float* scale_out; float* shift_out; float* mean_out; float* invstd_out;
+  int c;
+};
+
 // Counter-based dropout description (dropout.cuh).
 struct DropoutParams {
   float p;
@@ -67,6 +79,11 @@ struct ConvGemmParams {
 
   double* stat_sum;     // optional per-channel sum / sum-of-squares of the raw accumulator (train-mode BN)
   double* stat_sqsum;
+
+  // train-mode BatchNorm finalize in the tail of the GEMM (with stat_sum): the last CTA to finish turns the sums into
+  // scale / shift / mean / invstd and updates the running statistics (bn_tail.cuh). fin.sum == nullptr: off.
+  BnFinalizeParams fin;
+  unsigned int* fin_counter;   // zero on entry; counts finished CTAs
 
   // CTA-pair kernel only (conv_gemm2.cu, EPI = 1):
   DropoutParams drop;   // drop.p > 0: dropout after the ReLU, keyed by (flat output row seq * rows_out + t, 8-channel group)
@@ -147,17 +164,6 @@ cudaError_t launch_bn_finalize(const double* sum, const double* sqsum, long long
                                const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                                long long* nbt, float* scale, float* shift, float* mean, float* invstd, int c, int c_pad,
                                cudaStream_t stream);
-// bn_finalize folded into bn_act_fwd: sum == nullptr -> the kernel reads ready-made scale / shift instead
-struct BnFinalizeParams {
-  const double* sum; const double* sqsum;
-  double inv_n;          // 1 / rows the sums were taken over
-  float unbias;          // n / (n - 1): running_var takes the unbiased variance
-  const float* gamma; const float* beta;
-  float eps, momentum;
-  float* running_mean; float* running_var; long long* nbt;
-  float* scale_out; float* shift_out; float* mean_out; float* invstd_out;
-  int c;
-};
 cudaError_t launch_bn_act_fwd(int dtype, const void* z, const float* scale, const float* shift, const void* res,
                               long long seqs, long long rows_per_seq, long long res_seq_rows, int res_row_mul,
                               int res_row_off, int c_pad, const DropoutParams& dp, void* a,

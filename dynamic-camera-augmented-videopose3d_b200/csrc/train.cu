@@ -16,6 +16,7 @@
 
 #include "kernels.h"
 #include "dropout.cuh"
+#include "bn_tail.cuh"
 
 namespace vp3d {
 
@@ -51,25 +52,6 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // ---------------------------------------------------------------------------------------------- bn_finalize
-// Batch statistics of one channel from its double-precision sums. Shared by bn_finalize_kernel and the fused
-// bn_act_fwd_kernel so that both give the same bits. Only the cancellation-prone part (E[z^2] - E[z]^2) is done in
-// double precision -- three operations; a double division / square root per channel in EVERY thread of the fused apply
-// pass cost 55 us per training step on B200's thin FP64 pipe -- and invstd is an IEEE fp32 1 / sqrt(var + eps), the
-// precision F.batch_norm itself normalises with.
-struct BnChannel {
-  float mean, invstd, var;
-};
-__device__ __forceinline__ BnChannel bn_channel_stats(double sum, double sqsum, double inv_n, float eps) {
-  const double m = sum * inv_n;
-  double var = fma(sqsum, inv_n, -m * m);   // biased, as F.batch_norm normalises with
-  if (var < 0.0) var = 0.0;
-  BnChannel r;
-  r.mean = (float)m;
-  r.var = (float)var;
-  r.invstd = 1.f / sqrtf(r.var + eps);
-  return r;
-}
-
 // One block walks all channels (c_pad <= a few thousand): the step counter is read by every thread BEFORE thread 0 ticks
 // it, which the cumulative-average mode (momentum < 0: nn.BatchNorm1d(momentum=None), factor 1 / num_batches_tracked
 // after the tick) needs and a multi-block grid could not order.
@@ -79,31 +61,11 @@ bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sq
                    float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ nbt,
                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                    float* __restrict__ invstd_out, int c, int c_pad) {
-  if (momentum < 0.f) {
-    const long long seen = nbt != nullptr ? *nbt : 0;
-    momentum = 1.f / (float)(seen + 1);
-    __syncthreads();
-  }
-  if (threadIdx.x == 0 && nbt != nullptr) *nbt += 1;
-  for (int i = threadIdx.x; i < c_pad; i += blockDim.x) {
-    if (i >= c) {
-      scale[i] = 0.f;
-      shift[i] = 0.f;
-      mean_out[i] = 0.f;
-      invstd_out[i] = 0.f;
-      continue;
-    }
-    const BnChannel ch = bn_channel_stats(sum[i], sqsum[i], inv_n, eps);
-    const float sc = gamma[i] * ch.invstd;
-    scale[i] = sc;
-    shift[i] = beta[i] - ch.mean * sc;
-    mean_out[i] = ch.mean;
-    invstd_out[i] = ch.invstd;
-    if (running_mean != nullptr) {
-      running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * ch.mean;
-      running_var[i] = (1.f - momentum) * running_var[i] + momentum * (ch.var * unbias);   // unbiased: n / (n - 1)
-    }
-  }
+  BnFinalizeParams f;
+  f.sum = sum; f.sqsum = sqsum; f.inv_n = inv_n; f.unbias = unbias; f.gamma = gamma; f.beta = beta; f.eps = eps;
+  f.momentum = momentum; f.running_mean = running_mean; f.running_var = running_var; f.nbt = nbt;
+  f.scale_out = scale; f.shift_out = shift; f.mean_out = mean_out; f.invstd_out = invstd_out; f.c = c;
+  bn_finalize_block(f, c_pad, false);
 }
 
 // ---------------------------------------------------------------------------------------------- row-walking kernels
@@ -164,11 +126,13 @@ bn_act_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, 
       sc[k] = sh[k] = 0.f;
       if (i < fin.c) {
         ch = bn_channel_stats(fin.sum[i], fin.sqsum[i], fin.inv_n, fin.eps);
-        sc[k] = fin.gamma[i] * ch.invstd;
-        sh[k] = fin.beta[i] - ch.mean * sc[k];
+        sc[k] = __fmul_rn(fin.gamma[i], ch.invstd);
+        sh[k] = __fsub_rn(fin.beta[i], __fmul_rn(ch.mean, sc[k]));
         if (publish && fin.running_mean != nullptr) {
-          fin.running_mean[i] = (1.f - fin.momentum) * fin.running_mean[i] + fin.momentum * ch.mean;
-          fin.running_var[i] = (1.f - fin.momentum) * fin.running_var[i] + fin.momentum * (ch.var * fin.unbias);
+          fin.running_mean[i] = __fadd_rn(__fmul_rn(1.f - fin.momentum, fin.running_mean[i]),
+                                          __fmul_rn(fin.momentum, ch.mean));
+          fin.running_var[i] = __fadd_rn(__fmul_rn(1.f - fin.momentum, fin.running_var[i]),
+                                         __fmul_rn(fin.momentum, __fmul_rn(ch.var, fin.unbias)));
         }
       }
       if (publish) {

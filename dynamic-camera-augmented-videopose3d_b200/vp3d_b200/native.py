@@ -32,10 +32,19 @@ class ConvArgs(C.Structure):
         ('res_rows', C.c_longlong), ('res_col_off', C.c_longlong), ('res_cols', C.c_longlong),
         ('dyn_offsets', C.c_void_p), ('out_rows_total', C.c_longlong),
         ('stat_sum', C.c_void_p), ('stat_sqsum', C.c_void_p),
+        ('fin', C.c_void_p),
         ('drop', C.c_void_p), ('side', C.c_void_p), ('side_mode', C.c_int), ('side_row_off', C.c_int),
         ('side_row_stride', C.c_longlong), ('side_seq_stride', C.c_longlong), ('side_rows', C.c_longlong),
         ('side_scale', C.c_float),
     ]
+
+
+class BnFin(C.Structure):
+    """struct vp3d_bn_fin (include/vp3d_b200.h)"""
+    _fields_ = [('count', C.c_longlong), ('gamma', C.c_void_p), ('beta', C.c_void_p), ('eps', C.c_float),
+                ('momentum', C.c_float), ('running_mean', C.c_void_p), ('running_var', C.c_void_p),
+                ('num_batches_tracked', C.c_void_p), ('scale', C.c_void_p), ('shift', C.c_void_p), ('mean', C.c_void_p),
+                ('invstd', C.c_void_p), ('c', C.c_int), ('done_counter', C.c_void_p)]
 
 
 class WgradArgs(C.Structure):
@@ -47,7 +56,7 @@ class WgradArgs(C.Structure):
         ('a', C.c_void_p), ('a_rows', C.c_longlong), ('a_cols', C.c_longlong), ('a_row_stride', C.c_longlong),
         ('a_seq_stride', C.c_longlong), ('ci_pad', C.c_longlong),
         ('taps', C.c_int), ('b_row_off', C.c_longlong), ('b_tap_row_step', C.c_int), ('b_tap_col_step', C.c_longlong),
-        ('dw_packed', C.c_void_p), ('dz_cols', C.c_longlong),
+        ('dw_packed', C.c_void_p), ('dz_cols', C.c_longlong), ('max_slices', C.c_int),
     ]
 
 

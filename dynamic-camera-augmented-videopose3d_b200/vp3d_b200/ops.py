@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import native
-from .native import ConvArgs, Dropout, WgradArgs, check, lib
+from .native import BnFin, ConvArgs, Dropout, WgradArgs, check, lib
 
 
 def _stream():
@@ -281,7 +281,7 @@ def conv_block(dt, a, a_view, w, taps, tap_row_step, k_per_tap, rows_out, out, o
                scale=None, shift=None, relu=False, res=None, res_view=None, out_f32=False, n_valid=None,
                stat_sum=None, stat_sqsum=None, out_round_tf32=False, res_rows=0, res_col_off=0, res_cols=0,
                w_mn_major=None, dyn_offsets=None, out_rows_total=0, drop=None, side=None, side_view=None, side_mode=0,
-               side_scale=1.0):
+               side_scale=1.0, fin=None):
     """One vp3d_conv_block_fwd launch.
     a_view   = (seqs, rows, kdim, row_stride, seq_stride)    out_view = (row_stride, seq_stride)
     res_view = (row_stride, seq_stride, row_mul, row_off)    side_view = (row_stride, seq_stride, rows, row_off)
@@ -316,6 +316,8 @@ def conv_block(dt, a, a_view, w, taps, tap_row_step, k_per_tap, rows_out, out, o
         args.dyn_offsets, args.out_rows_total = dyn_offsets.data_ptr(), out_rows_total
     args.stat_sum = None if stat_sum is None else stat_sum.data_ptr()
     args.stat_sqsum = None if stat_sqsum is None else stat_sqsum.data_ptr()
+    if fin is not None:           # a native.BnFin (make_bn_fin): vp3d_bn_finalize in the tail of this launch
+        args.fin = C.addressof(fin)
     if drop is not None and drop.p > 0:
         args.drop = C.addressof(drop)
     if side is not None:
@@ -332,6 +334,9 @@ def make_dropout(p, seed, stream, step_counter=None):
     d = Dropout()
     d.p, d.seed, d.stream = float(p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream) & 0xFFFFFFFFFFFFFFFF
     d.step_counter = None if step_counter is None else step_counter.data_ptr()
+    # the struct carries a raw device pointer; the backward recomputes the forward's masks from it long after the caller's
+    # local tensor has gone out of scope, so the tensor lives as long as the description does
+    d._keepalive = step_counter
     return d
 
 
@@ -341,7 +346,7 @@ def counter_add(counter, inc=1):
 
 
 def wgrad(dt, dz, dz_view, a, a_view, co_pad, ci_pad, taps, dw_packed, b_row_off=0, b_tap_row_step=0,
-          b_tap_col_step=0, block_n=256, dz_cols=0):
+          b_tap_col_step=0, block_n=256, dz_cols=0, max_slices=0):
     """One vp3d_wgrad launch. dz_view = (seqs, rows, row_stride, seq_stride); a_view = (rows, cols, row_stride,
     seq_stride). dw_packed: zero-filled fp32 [taps][co_pad][ci_pad]."""
     args = WgradArgs()
@@ -355,6 +360,7 @@ def wgrad(dt, dz, dz_view, a, a_view, co_pad, ci_pad, taps, dw_packed, b_row_off
     args.taps, args.b_row_off, args.b_tap_row_step, args.b_tap_col_step = taps, b_row_off, b_tap_row_step, b_tap_col_step
     args.dw_packed = dw_packed.data_ptr()
     args.dz_cols = dz_cols
+    args.max_slices = max_slices
     with torch.cuda.device(dz.device):
         check(lib().vp3d_wgrad(C.byref(args), _stream()), 'wgrad')
     return dw_packed
@@ -392,6 +398,27 @@ def _bump_running_stats(bn):
     for b in (bn.running_mean, bn.running_var, bn.num_batches_tracked):
         if b is not None:
             torch.autograd.graph.increment_version(b)
+
+
+def make_bn_fin(bn, count, c_pad, done_counter, update_running=True):
+    """-> (native.BnFin for vp3d_conv_args.fin, (scale, shift, mean, invstd) fp32 [c_pad] it will fill).
+    `done_counter`: a zeroed 4-byte device word (a view into the caller's zero-filled arena)."""
+    dev = bn.weight.device
+    out = torch.empty((4, c_pad), dtype=torch.float32, device=dev)
+    track = update_running and bn.track_running_stats and bn.running_mean is not None
+    f = BnFin()
+    f.count = int(count)
+    gamma, beta = f32c(bn.weight.detach()), f32c(bn.bias.detach())
+    f.gamma, f.beta, f.eps, f.momentum = gamma.data_ptr(), beta.data_ptr(), float(bn.eps), _bn_momentum(bn)
+    if track:
+        f.running_mean, f.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+        f.num_batches_tracked = bn.num_batches_tracked.data_ptr()
+    f.scale, f.shift, f.mean, f.invstd = (out[i].data_ptr() for i in range(4))
+    f.c, f.done_counter = bn.num_features, done_counter.data_ptr()
+    f._keepalive = (gamma, beta, out, done_counter)
+    if track:
+        _bump_running_stats(bn)
+    return f, (out[0], out[1], out[2], out[3])
 
 
 def bn_finalize(stat, count, bn, c_pad, update_running=True):
@@ -489,8 +516,10 @@ def bn_finalize_act_fwd(dt, z, stat, count, bn, seqs, rows_per_seq, drop, res=No
 
 def bn_act_bwd(dt, g, z, scale, shift, mean, invstd, rows, c, drop, gscale_buf, count=None, group=None, sums=None):
     """-> (dz operand-typed [rows][c_pad], d_gamma [c], d_beta [c]). `count` (>= rows) is the number of rows the
-    batch statistics were taken over; with `group` the per-channel sums are all-reduced first (SyncBN: the parameter
-    gradients that come out are then already summed over the group)."""
+    batch statistics were taken over; with `group` the per-channel sums are all-reduced first (SyncBN). The kernel
+    then writes the GLOBAL sums as d_gamma / d_beta; they are divided by the group size here so that the gradient
+    AVERAGE a data-parallel hook takes afterwards (ddp.GradSync, like torch DDP) leaves the gradient of the global mean
+    loss -- the same convention as every other parameter, whose per-rank gradients are local sums."""
     c_pad = z.shape[-1]
     dev = z.device
     if sums is None:     # [2][c_pad] doubles, zero on entry (callers with many layers pass slices of one arena)
@@ -508,6 +537,9 @@ def bn_act_bwd(dt, g, z, scale, shift, mean, invstd, rows, c, drop, gscale_buf, 
                                           rows, int(count or rows), c, c_pad, C.byref(drop), _ptr(sums[0]), _ptr(sums[1]),
                                           _ptr(gscale_buf), _ptr(dz), _ptr(dgb[0]), _ptr(dgb[1]), _stream()),
               'bn_act_bwd_apply')
+        if group is not None:
+            import torch.distributed as dist
+            dgb.mul_(1.0 / dist.get_world_size(group))
     return dz, dgb[0], dgb[1]
 
 

@@ -15,6 +15,9 @@ from . import native, ops
 K_ALIGN = 64     # input channels are padded to one 128-byte K block of 16-bit elements (two blocks of tf32)
 N_TILE = 256     # output-channel tile of the wide layers
 N_TILE_NARROW = 64
+# eval-mode residual of the dilated model through the TMA side input of the pair kernel (A/B switch; measured in
+# profiles/README.md)
+RES_VIA_TMA = os.environ.get('VP3D_RES_TMA', '0') == '1'
 
 
 def _round_up(v, m):
@@ -79,7 +82,7 @@ def packed_for(model, dt):
 
 
 def _run_layer(dt, x, n, t_in, c_in_pad, w, plan, scale, shift, relu, res=None, res_t=0, out_f32=False, n_valid=None,
-               block_n=N_TILE, stats=None, drop=None):
+               block_n=N_TILE, stats=None, drop=None, fin=None):
     """x: [n][t_in][c_in_pad] operand-typed, contiguous. Returns (y [n][t_out][cols], t_out).
 
     View selection. A stride==width convolution reads `taps` consecutive frames per output frame, i.e. it is a plain
@@ -122,11 +125,20 @@ def _run_layer(dt, x, n, t_in, c_in_pad, w, plan, scale, shift, relu, res=None, 
         tiles = a_view[0] * ((rows_out + 127) // 128) * (n_pad // N_TILE)
         if tiles * 4 <= native.sm_count(x.device):          # the narrow tiles still fit in one wave
             block_n = N_TILE_NARROW
+    side_kw = {}
+    if (RES_VIA_TMA and res is not None and plan.res_mul == 1 and block_n == N_TILE and not out_f32 and
+            dt != native.TF32 and stats is None):
+        # residual rows that map 1:1 onto output rows (dilated model): fetched by TMA into the epilogue's staging tile
+        # (vp3d_conv_args.side_mode 1) instead of through registers
+        side_kw = dict(side=res, side_view=(res_view[0], res_view[1], n * res_t if flat else res_t, plan.res_off),
+                       side_mode=1)
+        res, res_view = None, None
     ops.conv_block(dt, x, a_view, w, g_taps, g_step, k_per_tap, rows_out, y, out_view, block_n=block_n,
                    scale=scale, shift=shift, relu=relu, res=res, res_view=res_view, out_f32=out_f32, n_valid=cols,
+                   **side_kw,
                    out_round_tf32=(dt == native.TF32 and not final),
                    stat_sum=None if stats is None else stats[0], stat_sqsum=None if stats is None else stats[1],
-                   drop=drop)
+                   drop=drop, fin=fin)
     return y, t_out
 
 

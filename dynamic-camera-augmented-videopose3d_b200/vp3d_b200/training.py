@@ -37,6 +37,9 @@ _ones = {}               # constant unit scale vectors of the shrink layer, per 
 # reduction / apply pass. VP3D_FUSED_EXPAND=0 restores bn_finalize + bn_act_fwd / bn_act_bwd for that layer (the path
 # every other layer takes; also used under SyncBN, where the statistics must be exchanged between the two steps).
 fused_expand = os.environ.get('VP3D_FUSED_EXPAND', '1') != '0'
+# vp3d_bn_finalize in the tail of the producing GEMM (last CTA done; vp3d_conv_args.fin): 8 launches and their dependent-
+# launch gaps less per training forward. VP3D_FIN_IN_GEMM=0 restores the stand-alone finalize launch.
+finalize_in_gemm = os.environ.get('VP3D_FIN_IN_GEMM', '1') != '0'
 debug_keep_saved = False  # tests: keep the last forward's saved per-layer tensors in `debug_last_saved`
 debug_last_saved = None
 
@@ -91,8 +94,9 @@ def _forward_stack(model, x, dt):
     ops.counter_add(counter, 1)
     step = counter.clone()   # this call's own copy: its backward sees the same value even if another forward runs first
     layers = []
-    # BatchNorm statistics of all layers in one zero-filled arena (one fill launch per forward instead of one per layer)
-    stats_all = torch.zeros((2 * len(fw) - 1, 2, c_pad), dtype=torch.float64, device=dev)
+    # BatchNorm statistics of all layers in one zero-filled arena (one fill launch per forward instead of one per layer);
+    # each layer's row ends with the word in which its GEMM counts finished CTAs (in-GEMM finalize)
+    stats_all = torch.zeros((2 * len(fw) - 1, 2 * c_pad + 2), dtype=torch.float64, device=dev)
 
     def conv_bn_act(idx, conv, bn, a_in, t, cin, cin_pad, plan, res=None, res_t=0, res_mul=1, res_off=0):
         L = _Layer()
@@ -102,10 +106,16 @@ def _forward_stack(model, x, dt):
         L.c_in, L.c_in_pad, L.t_in, L.a_in = cin, cin_pad, t, a_in
         w = _conv_w(dt, conv, c_pad, cin_pad)
         L.w_fwd = w   # [c_out_pad][taps * c_in_pad]; the data-gradient GEMM reads it again as W^T (MN-major operand)
-        stats = stats_all[idx]
+        stats = stats_all[idx, :2 * c_pad].view(2, c_pad)
         # per-channel sum / sum of squares of the stored z come out of the GEMM epilogue (the staged output tile is read
         # back column-wise from shared memory); vp3d_col_stats remains as a stand-alone entry point
-        z, t_out = _run_layer(dt, a_in, n, t, cin_pad, w, plan, None, None, False, stats=stats)
+        taps_, d_, s_ = plan.taps, plan.dilation, plan.stride
+        t_out_pre = (t - d_ * (taps_ - 1) - 1) // s_ + 1
+        fin = fin_out = None
+        if finalize_in_gemm and sync_bn_group is None and not fuse_bn_finalize:
+            # the last CTA of the GEMM finalizes the statistics (no vp3d_bn_finalize launch)
+            fin, fin_out = ops.make_bn_fin(bn, n * t_out_pre, c_pad, stats_all[idx, 2 * c_pad:].view(torch.int32))
+        z, t_out = _run_layer(dt, a_in, n, t, cin_pad, w, plan, None, None, False, stats=stats, fin=fin)
         L.z, L.t_out = z, t_out
         count = n * t_out
         if sync_bn_group is not None:
@@ -115,7 +125,11 @@ def _forward_stack(model, x, dt):
         L.count = count
         L.drop = _dropout_for(model, idx, step)
         L.res_of, L.res_t, L.res_mul, L.res_off = res, res_t, res_mul, res_off
-        if fuse_bn_finalize and bn.momentum is not None:
+        if fin is not None:
+            L.scale, L.shift, L.mean, L.invstd = fin_out
+            a = ops.bn_act_fwd(dt, z, L.scale, L.shift, n, t_out, L.drop, res=res, res_seq_rows=res_t,
+                               res_row_mul=res_mul, res_row_off=res_off)
+        elif fuse_bn_finalize and bn.momentum is not None:
             a, L.scale, L.shift, L.mean, L.invstd = ops.bn_finalize_act_fwd(
                 dt, z, stats, count, bn, n, t_out, L.drop, res=res, res_seq_rows=res_t, res_row_mul=res_mul,
                 res_row_off=res_off)
@@ -177,10 +191,10 @@ def _expand_fused(model, dt, x, n, t_in, c_in, c_in_pad, c_pad, plan, drop, laye
         xv, av = (1, n * t_out, row_stride, n * t_in * c_in_pad), (n * t_out, k_total, row_stride, n * t_in * c_in_pad)
     else:
         xv, av = (n, t_out, row_stride, t_in * c_in_pad), (t_out, k_total, row_stride, t_in * c_in_pad)
-    # 128 x 64 tiles: 8 tiles x ~18 row slices fill the SMs once; ONE 256 x 256 tile split 64 ways spent 40 us of its
-    # 48 us in 64-way red.add contention on the same 256 KB
+    # one 256 x 256 tile, 64 row slices: 27 us at batch 1024 (tools/gram_probe.py: 128 x 64 tiles 32 us, 148 slices 33 us,
+    # 16 slices 58 us)
     gram = torch.zeros((1, 256, 256), dtype=torch.float32, device=x.device)
-    ops.wgrad(dt, h, xv, h, av, 256, 256, 1, gram, block_n=64, dz_cols=k_total)
+    ops.wgrad(dt, h, xv, h, av, 256, 256, 1, gram, block_n=256, dz_cols=k_total)
     w = _conv_w(dt, conv, c_pad, c_in_pad)
     L = _Layer()
     L.conv, L.bn, L.w_fwd = conv, bn, w

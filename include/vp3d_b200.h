@@ -63,6 +63,24 @@ typedef struct vp3d_dropout {
  * Activations are channels-last. Rows of `a` outside [0, a_rows) read as zero. A strided convolution whose stride
  * equals its width is expressed as taps = 1 on the reshaped view [s][t_out][taps * c].
  */
+/* Arguments of vp3d_bn_finalize for the in-GEMM finalize (vp3d_conv_args.fin): same meaning, plus a counter. */
+typedef struct vp3d_bn_fin {
+  long long count;          /* rows the statistics are taken over (> 1) */
+  const float* gamma;
+  const float* beta;
+  float eps;
+  float momentum;           /* < 0: cumulative moving average (nn.BatchNorm1d(momentum=None)) */
+  float* running_mean;      /* may be NULL (together with running_var) */
+  float* running_var;
+  long long* num_batches_tracked;   /* may be NULL */
+  float* scale;             /* outputs, fp32 [n_pad] */
+  float* shift;
+  float* mean;
+  float* invstd;
+  int c;                    /* real channels (<= n_pad) */
+  unsigned int* done_counter;   /* device word, ZERO on entry; the launch counts its finished CTAs in it */
+} vp3d_bn_fin;
+
 typedef struct vp3d_conv_args {
   int dtype;               /* vp3d_dtype */
   int block_n;             /* output-channel tile: 256, or 64 for narrow layers; n_pad must be a multiple */
@@ -118,6 +136,10 @@ typedef struct vp3d_conv_args {
 
   double* stat_sum;        /* optional [n_pad] accumulators (+=) of the output AS STORED (16-bit) and its square over the */
   double* stat_sqsum;      /* valid rows: train-mode BatchNorm statistics; fp32 per CTA, double across CTAs */
+
+  const struct vp3d_bn_fin* fin; /* optional (with stat_sum): vp3d_bn_finalize in the tail of this launch -- the last CTA to
+                              finish turns the sums into scale / shift / mean / invstd and updates the running
+                              statistics, so the stand-alone finalize launch (and its launch gap) disappears */
 
   /* Fused train-mode epilogue (CTA-pair kernel: 16-bit operands and output, block_n 256, no dyn_offsets; the launch
    * takes that kernel whatever vp3d_set_pair_mode says and fails with VP3D_ERR_UNSUPPORTED where it cannot run). */
@@ -280,6 +302,7 @@ typedef struct vp3d_wgrad_args {
   long long b_tap_col_step;/* stride == width convolution on the reshaped view: tap k reads columns k * c_in_pad + ci */
   float* dw_packed;        /* [taps][co_pad][ci_pad] fp32, accumulated with red.add */
   long long dz_cols;       /* 0: co_pad. Otherwise the real column count of `dz` (<= co_pad); the rest reads as zero */
+  int max_slices;          /* 0: 64. Upper bound on the row slices (split-K depth) the launch may choose */
 } vp3d_wgrad_args;
 int vp3d_wgrad(const vp3d_wgrad_args* args, void* stream);
 

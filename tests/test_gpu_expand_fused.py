@@ -231,3 +231,47 @@ def test_fused_expand_against_fp32_oracle_243():
     assert max(worst.values()) < 1.2e-1, worst
     for k in ('expand_bn.running_mean', 'expand_bn.running_var'):
         assert (bufs[k].cpu() - stats_o[k]).abs().max().item() < 1e-4, k     # analytic statistics: fp32-accurate
+
+
+@pytest.mark.parametrize('pair', [False, True])
+@pytest.mark.parametrize('momentum', [0.1, None])
+def test_finalize_in_the_gemm_tail_is_bit_identical_to_the_stand_alone_launch(pair, momentum):
+    """vp3d_conv_args.fin (the last CTA of the GEMM finalizes the BatchNorm statistics) against the GEMM followed by
+    vp3d_bn_finalize: same sums, same arithmetic -> the same bits, running statistics and counter included; also
+    nn.BatchNorm1d(momentum=None) (cumulative average) over two calls."""
+    dt, td = native.F16, torch.float16
+    g = torch.Generator().manual_seed(17)
+    seqs, rows, c, n = (3, 700, 256, 1024) if pair else (1, 300, 128, 512)
+    a = (torch.randn(seqs, rows, c, generator=g) * 0.5).to(td).cuda()
+    w = (torch.randn(n, c, generator=g) / c ** 0.5).to(td).cuda()
+    bns = [_bn(n - 3, 18) for _ in range(2)]
+    for bn in bns:
+        bn.momentum = momentum
+    res = []
+    native.check(native.lib().vp3d_set_pair_mode(2 if pair else 0), 'pair')
+    try:
+        for use_fin, bn in zip((False, True), bns):
+            outs = []
+            for _ in range(2):
+                arena = torch.zeros(2 * n + 2, dtype=torch.float64, device='cuda')
+                stats = arena[:2 * n].view(2, n)
+                z = torch.empty((seqs, rows, n), dtype=td, device='cuda')
+                fin, fin_out = (ops.make_bn_fin(bn, seqs * rows, n, arena[2 * n:].view(torch.int32)) if use_fin
+                                else (None, None))
+                ops.conv_block(dt, a, (seqs, rows, c, c, rows * c), w, 1, 0, c, rows, z, (n, rows * n),
+                               stat_sum=stats[0], stat_sqsum=stats[1], fin=fin)
+                if not use_fin:
+                    fin_out = ops.bn_finalize(stats, seqs * rows, bn, n)
+                torch.cuda.synchronize()
+                outs.append([t.clone() for t in fin_out])
+            res.append((outs, bn))
+    finally:
+        native.check(native.lib().vp3d_set_pair_mode(1), 'pair')
+    (o0, bn0), (o1, bn1) = res
+    for step in range(2):
+        for t0, t1 in zip(o0[step], o1[step]):
+            assert torch.equal(t0, t1)
+    assert torch.equal(bn0.running_mean, bn1.running_mean) and torch.equal(bn0.running_var, bn1.running_var)
+    assert int(bn0.num_batches_tracked) == int(bn1.num_batches_tracked) == 2
+    if momentum is None:     # cumulative average of two identical batches = the batch statistics themselves
+        assert (bn1.running_mean[:n - 3] - o1[1][2][:n - 3]).abs().max().item() < 1e-6
