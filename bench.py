@@ -311,12 +311,12 @@ class LaunchTimer:
         return sum(len(self.events[n]) for n in (names or self.names))
 
 
-def synthetic_training_batch(rank, batch):
+def synthetic_training_batch(rank, batch, J=17):
     """World-space joints of `batch` 243-frame windows with one camera pose per frame: root =
     smooth random walk 2-6 m in front of the camera, joints = root + low-pass N(0, 0.25 m) offsets; camera = unit
     quaternion near identity with smooth drift, smooth translation; H36M camera-0 intrinsics with distortion."""
     g = torch.Generator().manual_seed(4321 + rank)
-    T, J = RF, 17
+    T = RF
 
     def smooth(shape, scale, k=31):
         v = torch.randn(shape, generator=g) * scale
@@ -359,9 +359,11 @@ def bench_train(args, rank, world, dev, steps, warm):
     else:
         opt = torch.optim.Adam(model.parameters(), lr=1e-3, amsgrad=True, capturable=use_graph)   # run.py:662
     sync = None
+    sync_compress = None
     if world > 1:
         ddp.broadcast_parameters(model)
         sync = ddp.enable_grad_sync()
+        sync_compress = sync.compress
 
     Wh, qh, th, camh = [v.pin_memory() for v in synthetic_training_batch(rank, batch)]
     Wd, qd, td, camd = [v.to(dev) for v in (Wh, qh, th, camh)]
@@ -606,9 +608,10 @@ def bench_train(args, rank, world, dev, steps, warm):
                                'per-frame camera projection (H36M cam-0 distortion) -> fwd -> mpjpe -> bwd -> Adam '
                                'amsgrad (BASELINE configs[2])' % batch,
                    'optimizer': args.optimizer,
-                   'grad_exchange': 'none (1 GPU)' if world == 1 else 'NCCL all-reduce (avg) of fp32 gradients, large '
-                                    'tensors overlapped with backward, %d collectives, %.1f MB per step'
-                                    % (coll_per_step[0], coll_per_step[1] / 1e6),
+                   'grad_exchange': 'none (1 GPU)' if world == 1 else 'NCCL all-reduce (avg) of %s gradients, large '
+                                    'tensors overlapped with backward, %d collectives, %.1f MB on the wire per step'
+                                    % ('fp32 (sent as bf16, written back as fp32)' if sync_compress else 'fp32',
+                                       coll_per_step[0], coll_per_step[1] / 1e6),
                    'bn': 'per-replica batch statistics',
                    'launch': 'one CUDA graph per step (vp3d_b200.graphs.GraphedTrainStep)' if use_graph else 'eager'},
         'e2e': {'value': total / (ms_e2e * 1e-3), 'unit': 'samples/s', 'ms_per_step': ms_e2e / steps,
@@ -744,6 +747,143 @@ def bench_train_multi(args, rank, world, dev, model, opt, loss_fn, steps, world_
     return out
 
 
+def c4_flop_per_sample(J):
+    """Useful MAC x 2 of one training step of the 243-frame 1f pose model (3 J outputs) + trajectory model (3 outputs) on
+    a J-joint skeleton: forward + data gradient (none for the expand layer) + weight gradient, as SURVEY 8d counts them."""
+    blocks = sum(t * (3 * 1024 + 1024) * 1024 for t in (27, 9, 3, 1))
+    total = 0
+    for n_out in (3 * J, 3):
+        expand, shrink = 81 * (3 * 2 * J) * 1024, 1024 * n_out
+        fwd = expand + blocks + shrink
+        total += 2 * (fwd + (blocks + shrink) + fwd)
+    return total
+
+
+def bench_c4(args, rank, world, dev, steps, warm):
+    """BASELINE configs[4]: CMU-mocap-shaped 31-joint skeleton, pose model (93 outputs) + trajectory model
+    (num_joints_out = 1) trained jointly. The fork removed the semi-supervised loop from run.py and kept only its
+    primitives (loss.py:21-27,70-80, camera.py:37-67), so the step composition is defined HERE: per-frame dynamic-camera
+    projection of the world-space batch -> both 1f models -> mpjpe(pose) + weighted_mpjpe(trajectory, w = 1 / depth) +
+    reprojection loss mpjpe(project_to_2d(pose + trajectory), 2-D keypoints of the centre frame) (fused kernel) ->
+    backward through both -> one Adam(amsgrad) step over both parameter sets; gradients averaged over ranks (N > 1)."""
+    import torch.distributed as dist
+    from common.camera import world_to_camera, world_to_image
+    from common.loss import mpjpe, reprojection_mpjpe, weighted_mpjpe
+    from common.models.TemporalModel import TemporalModelOptimized1f
+    from oracle import temporal_model as otm
+    from vp3d_b200 import ddp
+    from vp3d_b200.graphs import GraphedTrainStep
+    from vp3d_b200.optim import FusedAdam
+    J, batch = 31, args.c4_batch
+    torch.manual_seed(4321)
+    pose_m = TemporalModelOptimized1f(J, 2, J, FW, dropout=0.25, channels=1024)
+    traj_m = TemporalModelOptimized1f(J, 2, 1, FW, dropout=0.25, channels=1024)
+    pose_m.load_state_dict(otm.init_state(J, 2, J, FW, channels=1024, seed=41))
+    traj_m.load_state_dict(otm.init_state(J, 2, 1, FW, channels=1024, seed=42))
+
+    class Both(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.pose, self.traj = pose_m, traj_m
+
+        def forward(self, x):
+            return self.pose(x), self.traj(x)
+
+    model = Both().to(dev).train()
+    for m in (model.pose, model.traj):
+        m.operand_dtype = args.dtype if args.dtype != 'tf32' else 'fp16'
+    opt = FusedAdam(model.parameters(), lr=1e-3, amsgrad=True)
+    sync = None
+    if world > 1:
+        ddp.broadcast_parameters(model)
+        sync = ddp.enable_grad_sync()
+    W, q, t, cam = [v.to(dev) for v in synthetic_training_batch(100 + rank, batch, J=J)]
+    mid = RF // 2
+    with torch.no_grad():
+        Xc = world_to_camera(W[:, mid:mid + 1].contiguous(), q[:, mid:mid + 1].contiguous(), t[:, mid:mid + 1].contiguous())
+        tgt_traj = Xc[:, :, :1].contiguous()
+        tgt_pose = (Xc - tgt_traj).contiguous()
+        x2d_mid = world_to_image(W[:, mid:mid + 1].contiguous(), q[:, mid:mid + 1].contiguous(),
+                                 t[:, mid:mid + 1].contiguous(), cam, return_camera_space=False)[1].contiguous()
+        w_traj = (1.0 / tgt_traj[:, :, :, 2]).contiguous()
+
+    def loss_fn(pred, target):
+        pose, traj = pred
+        t_pose, t_traj, t_2d, w = target
+        return mpjpe(pose, t_pose) + weighted_mpjpe(traj, t_traj, w) + \
+            reprojection_mpjpe(pose, cam_static[0], t_2d, trajectory=traj)
+
+    cam_static = [cam]
+    pre = lambda W_, q_, t_, c_: world_to_image(W_, q_, t_, c_, return_camera_space=False)[1]
+    use_graph = not args.no_graph
+    torch.cuda.reset_peak_memory_stats(dev)
+    if use_graph:
+        gs = GraphedTrainStep(model, opt, loss_fn, (W, q, t, cam), (tgt_pose, tgt_traj, x2d_mid, w_traj), preprocess=pre)
+        cam_static[0] = gs.static_inputs[3]
+
+        def run():
+            return gs(gs.static_inputs)
+    else:
+        def run():
+            opt.zero_grad(set_to_none=True)
+            loss = loss_fn(model(pre(W, q, t, cam)), (tgt_pose, tgt_traj, x2d_mid, w_traj))
+            loss.backward()
+            opt.step()
+            return loss.detach()
+    first = None
+    for i in range(max(warm, 3)):
+        loss = run()
+        if i == 0:
+            first = float(loss)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        last = run()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    in_sync = None
+    if world > 1:
+        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt)
+        chk = torch.stack([p.detach().double().sum() for p in model.parameters()]).sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        in_sync = bool(lo.item() == hi.item())
+        ddp.disable_grad_sync()
+    peak_mem = torch.cuda.max_memory_allocated(dev)
+    if rank != 0:
+        return None
+    peaks = load_peaks()
+    flop = c4_flop_per_sample(J)
+    tfs = flop * batch / (ms / steps * 1e-3) / 1e12
+    return {'metric': 'J=31 pose + trajectory 1f training throughput', 'value': batch * world * steps / (ms * 1e-3),
+            'unit': 'samples/s', 'ms_per_step': ms / steps, 'per_gpu_batch': batch, 'n_gpus': world, 'scaling': 'weak',
+            'dtype': model.pose.operand_dtype,
+            'config': {'workload': 'BASELINE configs[4]: 31-joint skeleton, TemporalModelOptimized1f 3,3,3,3,3 pose model '
+                                   '(93 outputs) + trajectory model (3 outputs), dropout 0.25, per-frame camera projection -> '
+                                   'both forwards -> mpjpe + weighted_mpjpe(1/depth) + fused reprojection loss -> backward '
+                                   '-> Adam amsgrad over both models; step composition defined by this benchmark (the fork '
+                                   'removed the semi-supervised loop, only its primitives remain)',
+                       'batch_choice': '%d samples per GPU: %.1f GB peak allocated of 180 GB; the step time is linear in the '
+                                       'batch beyond ~2k samples, so a larger batch buys no throughput'
+                                       % (batch, peak_mem / 1e9),
+                       'launch': 'one CUDA graph per step' if use_graph else 'eager'},
+            'peak_memory_bytes': int(peak_mem), 'loss_first_last': [first, float(last)],
+            'params_in_sync': in_sync,
+            'roofline': {'bound': 'tensor', 'achieved_whole_step': tfs, 'peak': peaks['sustained'], 'unit': 'TFLOP/s',
+                         'frac_whole_step': tfs / peaks['sustained'], 'algorithmic_flop_per_sample': flop,
+                         'peak_source': peaks['source'] + ', sustained dense bf16'}}
+
+
 def bench_stream(args, rank, world, dev):
     """BASELINE configs[3]: causal 243-frame model, S concurrent streams advancing one frame per step with this
     frame's camera (quaternion, translation, distortion intrinsics) per stream; plus single-stream latency."""
@@ -805,12 +945,13 @@ def main():
     ap.add_argument('--seqs', type=int, default=SEQS_PER_GPU)
     ap.add_argument('--frames', type=int, default=OUT_FRAMES)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--mode', default='all', choices=['all', 'infer', 'train'],
+    ap.add_argument('--mode', default='all', choices=['all', 'infer', 'train', 'c4'],
                     help='all: inference headline + train object; train: training headline only')
     ap.add_argument('--batch', type=int, default=TRAIN_BATCH, help='training samples per GPU per step')
     ap.add_argument('--optimizer', default='fused', choices=['fused', 'torch'],
                     help='training: vp3d_b200.optim.FusedAdam (default) or stock torch.optim.Adam')
     ap.add_argument('--no-graph', action='store_true', help='training: launch kernels eagerly instead of one CUDA graph')
+    ap.add_argument('--c4-batch', type=int, default=8192, help='configs[4] (J=31 pose + trajectory) samples per GPU per step')
     ap.add_argument('--no-parity', action='store_true', help='skip the oracle comparison of the measured sizes (outside the timed regions)')
     args = ap.parse_args()
 
@@ -834,6 +975,16 @@ def main():
 
     warm = max(args.warmup, 3)
     steps = max(args.steps, 1)
+    if args.mode == 'c4':
+        c4 = bench_c4(args, rank, world, dev, min(steps, 10), warm)
+        if rank == 0:
+            c4.update({'steps': min(steps, 10), 'warmup': warm, 'higher_is_better': True, 'vs_baseline': None,
+                       'data': 'synthetic'})
+            emit(c4)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     if args.mode == 'train':
         sampler = ClockSampler(local_rank)
         if rank == 0:
@@ -1015,9 +1166,15 @@ def main():
         torch.cuda.empty_cache()
         train = bench_train(args, rank, world, dev, max(steps, 10), warm)
     stream = bench_stream(args, rank, world, dev) if args.mode == 'all' and rank == 0 else None
+    c4 = None
+    if args.mode == 'all':
+        torch.cuda.empty_cache()
+        c4 = bench_c4(args, rank, world, dev, 5, 3)
     if rank == 0:
         if stream is not None:
             line['stream'] = stream
+        if c4 is not None:
+            line['c4'] = c4
         if train is not None:
             if not args.no_cpu_baseline:
                 v, cores, sample = cpu_port_train_samples_per_s()

@@ -81,3 +81,12 @@ def mean_velocity_error(predicted, target):
         return ops.mean_velocity_error(predicted, target)   # CUDA tensors stay on the device (vp3d_velocity_error)
     dv = np.diff(predicted, axis=0) - np.diff(target, axis=0)
     return np.mean(np.linalg.norm(dv, axis=len(target.shape) - 1))
+
+
+def reprojection_mpjpe(predicted_3d, camera_params, target_2d, trajectory=None, linear=False):
+    """Addition beyond the reference API: mpjpe(project_to_2d(predicted_3d + trajectory, camera_params), target_2d)
+    -- the reprojection term of upstream VideoPose3D's semi-supervised step, built from this fork's camera.py:37-67 and
+    loss.py:11-17 -- as ONE fused kernel per direction (vp3d_reproj_mpjpe_fwd / _bwd): the 2-D projection never reaches
+    memory. predicted_3d (N, ..., J, 3) CUDA, trajectory (N, ..., 1, 3) or None, camera_params (N, 9),
+    target_2d (N, ..., J, 2). Differentiable wrt predicted_3d and trajectory."""
+    return ops.reproj_mpjpe(predicted_3d, camera_params, target_2d, traj=trajectory, linear=linear)

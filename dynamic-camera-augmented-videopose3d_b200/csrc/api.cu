@@ -38,6 +38,13 @@ cudaError_t launch_velocity_error(const float* pred, const float* tgt, long long
                                   double* partial, float* out, int sm_count, cudaStream_t stream);
 cudaError_t launch_n_mpjpe_bwd(const float* pred, const float* tgt, const float* grad_out, long long n_poses, int J,
                                float* grad_pred, int sm_count, cudaStream_t stream);
+cudaError_t launch_reproj_fwd(const float* pose, const float* traj, long long n_pts, long long pts_per_traj,
+                              const float* cam, long long pts_per_cam, int linear, const float* tgt, double* partial,
+                              float* out, int sm_count, cudaStream_t stream);
+cudaError_t launch_reproj_bwd(const float* pose, const float* traj, long long n_pts, long long pts_per_traj,
+                              const float* cam, long long pts_per_cam, int linear, const float* tgt,
+                              const float* grad_out, float* grad_pose, float* grad_traj, int sm_count,
+                              cudaStream_t stream);
 cudaError_t launch_pack_rows(int dtype, const float* src, void* dst, long long rows, int c, int c_pad, int sm_count,
                              cudaStream_t stream, int ones_col = -1);
 cudaError_t launch_pack_weight(int dtype, const float* w, void* dst, int c_out, int c_in, int taps, int rows_pad,
@@ -77,6 +84,13 @@ int g_pair_mode = [] {
   const char* e = std::getenv("VP3D_K1_2CTA");
   if (e == nullptr) return 1;
   return std::strcmp(e, "force") == 0 ? 2 : (std::strcmp(e, "0") == 0 ? 0 : 1);
+}();
+// Tile schedule of the CTA-pair kernel for launches without statistics of at least two waves: 0 = static persistent
+// (default), 1 = dynamic (cluster launch control, conv_gemm2.cu). Initial value from VP3D_SCHED ("dynamic").
+int g_sched_mode = [] {
+  const char* e = std::getenv("VP3D_SCHED");
+  if (e == nullptr) return 0;
+  return std::strcmp(e, "dynamic") == 0 ? 1 : (std::strcmp(e, "dynamic-all") == 0 ? 2 : 0);
 }();
 int g_sm_limit = [] {
   const char* e = std::getenv("VP3D_SM_LIMIT");
@@ -187,6 +201,13 @@ int vp3d_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 int vp3d_set_pair_mode(int mode) {
   if (mode < 0 || mode > 2) return fail(VP3D_ERR_INVALID, "pair mode must be 0 (off), 1 (auto) or 2 (whenever supported)");
   g_pair_mode = mode;
+  return VP3D_OK;
+}
+
+int vp3d_set_sched_mode(int mode) {
+  if (mode < 0 || mode > 2)
+    return fail(VP3D_ERR_INVALID, "sched mode must be 0 (static), 1 (dynamic) or 2 (dynamic for every pair launch)");
+  g_sched_mode = mode;
   return VP3D_OK;
 }
 
@@ -358,6 +379,8 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
     return fail(VP3D_ERR_UNSUPPORTED, "fused dropout / side input need the CTA-pair kernel (16-bit operands and output, "
                 "block_n 256, no dyn_offsets, cluster launches available on this device)");
   if (use_pairs && pair_ok && (use_pairs == 2 || total_tiles >= 2LL * dev->sm_count)) {
+    p.dyn_sched = (a->stat_sum == nullptr &&
+                   (g_sched_mode == 2 || (g_sched_mode == 1 && total_tiles >= 2LL * dev->sm_count))) ? 1 : 0;
     CUtensorMap tmBh = tmB;    // MN-major: the same [64 k-rows][64 columns] boxes, two per CTA
     if (!a->w_mn_major) {
       cuuint64_t dims[2] = {(cuuint64_t)a->k_total, (cuuint64_t)a->n_pad};
@@ -647,6 +670,40 @@ int vp3d_n_mpjpe_bwd(const float* pred, const float* target, const float* grad_o
   return VP3D_OK;
 }
 
+int vp3d_reproj_mpjpe_fwd(const float* pose, const float* traj, long long n_points, long long pts_per_traj,
+                          const float* cam, long long pts_per_cam, int linear, const float* target2, void* workspace,
+                          float* out, void* stream) {
+  if (!pose || !cam || !target2 || !workspace || !out || n_points <= 0 || pts_per_cam <= 0)
+    return fail(VP3D_ERR_INVALID, "reproj_mpjpe_fwd args");
+  if (traj != nullptr && (pts_per_traj <= 0 || n_points % pts_per_traj != 0))
+    return fail(VP3D_ERR_INVALID, "reproj_mpjpe_fwd: n_points must be a multiple of pts_per_traj");
+  if (reinterpret_cast<uintptr_t>(target2) & 7) return fail(VP3D_ERR_INVALID, "reproj_mpjpe_fwd: target2 must be 8-byte aligned");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_reproj_fwd(pose, traj, n_points, pts_per_traj, cam, pts_per_cam, linear, target2,
+                                          static_cast<double*>(workspace), out, dev->sm_count,
+                                          static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "reproj_mpjpe_fwd launch");
+  return VP3D_OK;
+}
+
+int vp3d_reproj_mpjpe_bwd(const float* pose, const float* traj, long long n_points, long long pts_per_traj,
+                          const float* cam, long long pts_per_cam, int linear, const float* target2,
+                          const float* grad_out, float* grad_pose, float* grad_traj, void* stream) {
+  if (!pose || !cam || !target2 || !grad_out || n_points <= 0 || pts_per_cam <= 0 || (!grad_pose && !grad_traj))
+    return fail(VP3D_ERR_INVALID, "reproj_mpjpe_bwd args");
+  if (traj != nullptr && (pts_per_traj <= 0 || n_points % pts_per_traj != 0))
+    return fail(VP3D_ERR_INVALID, "reproj_mpjpe_bwd: n_points must be a multiple of pts_per_traj");
+  if (grad_traj != nullptr && traj == nullptr) return fail(VP3D_ERR_INVALID, "reproj_mpjpe_bwd: grad_traj without traj");
+  if (reinterpret_cast<uintptr_t>(target2) & 7) return fail(VP3D_ERR_INVALID, "reproj_mpjpe_bwd: target2 must be 8-byte aligned");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_reproj_bwd(pose, traj, n_points, pts_per_traj, cam, pts_per_cam, linear, target2, grad_out,
+                                          grad_pose, grad_traj, dev->sm_count, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "reproj_mpjpe_bwd launch");
+  return VP3D_OK;
+}
+
 int vp3d_wgrad(const vp3d_wgrad_args* a, void* stream) {
   if (a == nullptr) return fail(VP3D_ERR_INVALID, "args is NULL");
   if (a->dtype != VP3D_F16 && a->dtype != VP3D_BF16) return fail(VP3D_ERR_INVALID, "wgrad: dtype must be F16 or BF16");
@@ -699,7 +756,21 @@ int vp3d_wgrad(const vp3d_wgrad_args* a, void* stream) {
     long long best = -1;
     int best_s = 1;
     const int s_max = a->max_slices > 0 ? a->max_slices : 64;
-    for (int s_try = 1; s_try <= s_max && s_try <= kb_all; ++s_try) {
+    // dynamic schedule (vp3d_set_sched_mode, data-parallel training): items are handed out one by one to whichever CTA
+    // is free, so a launch degrades gracefully when some SMs are busy with something else -- provided there are a few
+    // items per worker. Every extra slice costs a flush of the tile (not overlapped with the MMAs for the 256-row tile;
+    // measured ~40 row blocks' worth), so: the SMALLEST slice count that gives two items per SM, never slices shallower
+    // than 32 row blocks, the cap when neither can be met.
+    p.dyn_sched = g_sched_mode != 0 ? 1 : 0;
+    if (p.dyn_sched) {
+      best_s = 1;
+      for (int s_try = 1; s_try <= s_max && s_try <= kb_all; ++s_try) {
+        best_s = s_try;
+        const long long depth = (kb_all + s_try - 1) / s_try;
+        if ((long long)p.num_tiles * s_try >= 2LL * dev->sm_count || depth <= 32) break;
+      }
+    }
+    for (int s_try = 1; !p.dyn_sched && s_try <= s_max && s_try <= kb_all; ++s_try) {
       const long long items = (long long)p.num_tiles * s_try;
       const long long waves = (items + dev->sm_count - 1) / dev->sm_count;
       const long long cost = waves * ((kb_all + s_try - 1) / s_try + flush);
@@ -717,7 +788,7 @@ int vp3d_wgrad(const vp3d_wgrad_args* a, void* stream) {
   p.out_tap_stride = a->co_pad * a->ci_pad;
   p.out_row_stride = a->ci_pad;
   const long long items = (long long)p.num_tiles * p.num_slices;
-  const int grid = (int)(items < dev->sm_count ? items : dev->sm_count);
+  const int grid = (int)((items < dev->sm_count || p.dyn_sched) ? items : dev->sm_count);
   cudaError_t e = vp3d::launch_wgrad(a->dtype, a->block_n, block_m, tmA, tmB, p, grid,
                                      static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return cuda_fail(e, "wgrad launch");

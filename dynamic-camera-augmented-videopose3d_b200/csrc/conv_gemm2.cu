@@ -28,7 +28,10 @@ constexpr int kBN = 256;                  // output channels per pair tile
 constexpr int kKBytes = 128;              // one swizzle span of K per stage row
 constexpr int kStages = 5;
 constexpr int kEpi = 8;                   // epilogue warps, two per TMEM lane quadrant
-constexpr int kThreads = 64 + 32 * kEpi;
+constexpr int kSchedWarp = 2 + kEpi;      // last warp: tile scheduler (cluster launch control), leader CTA only
+constexpr int kThreads = 64 + 32 * kEpi + 32;
+constexpr int kClcSlots = 3;              // responses in flight: the producer may be 3 tiles ahead of the slowest epilogue warp
+constexpr int kClcConsumers = 2 + 1 + 2 * kEpi;   // both producers, the MMA thread, the epilogue warps of both CTAs
 constexpr int kABytes = kBM * kKBytes;            // 16 KB
 constexpr int kBHalfBytes = (kBN / 2) * kKBytes;  // 16 KB: this CTA's half of the weight tile
 constexpr int kStageBytes = kABytes + kBHalfBytes;
@@ -128,6 +131,11 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // leader only: epilogue warps of both CTAs arrive
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   uint64_t* side_bar = tmem_empty_bar + 4;         // EPI: [epilogue warp][staging buffer], this CTA's own TMA loads
+  uint64_t* clc_full = bars + 40;                  // dynamic schedule: response landed (per CTA, multicast complete_tx)
+  uint64_t* clc_empty = bars + 40 + kClcSlots;     // leader only: every consumer of both CTAs has read the response
+  uint8_t* clc_resp = reinterpret_cast<uint8_t*>(bars) + 384;   // kClcSlots x 16 bytes
+  static_assert(2 * kStages + 4 + 2 + kEpi * 3 <= 40 && (40 + 2 * kClcSlots) * 8 <= 384 && 384 + 16 * kClcSlots <= kBarBytes - 4,
+                "barrier area layout");
   float* affine_smem = reinterpret_cast<float*>(out_stage + kOutStageBytes + kBarBytes);   // scale[1024] | shift[1024]
 
   const int warp = threadIdx.x >> 5;
@@ -138,6 +146,31 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const int first_pair = (int)cluster_id_x();
   const int pair_step = (int)cluster_count_x();
   const int num_kb = p.taps * p.kblocks_per_tap;
+  const bool dyn = p.dyn_sched != 0;
+
+  // Tile sequence of this cluster. Static: first_pair, first_pair + pair_step, ... Dynamic: the cluster's own index, then
+  // whatever the scheduler warp steals (see there); every consumer role walks the response ring on its own.
+  struct TileFeed {
+    int slot = 0;
+    uint32_t phase = 0;
+  };
+  auto next_tile = [&](TileFeed& tf, int pt, bool elected, bool whole_warp) -> int {
+    if (!dyn) {
+      pt += pair_step;
+      return pt < total_pairs ? pt : -1;
+    }
+    mbar_wait(&clc_full[tf.slot], tf.phase);
+    int x;
+    const bool ok = clc_query(clc_resp + 16 * tf.slot, x);
+    fence_proxy_async_smem();     // this generic read is ordered before the next (async-proxy) response into the slot
+    if (whole_warp) __syncwarp();   // (every lane of an epilogue warp has read the slot before lane 0 releases it)
+    if (elected) mbar_arrive_cluster(map_to_cta(smem_u32(&clc_empty[tf.slot]), 0));
+    if (++tf.slot == kClcSlots) {
+      tf.slot = 0;
+      tf.phase ^= 1;
+    }
+    return ok ? (x >> 1) : -1;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -154,6 +187,10 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (EPI) {
       tma_prefetch_desc(&tmS);
       for (int s = 0; s < kEpi * kOutBufs; ++s) mbar_init(&side_bar[s], 1);
+    }
+    for (int s = 0; s < kClcSlots; ++s) {
+      mbar_init(&clc_full[s], 1);
+      mbar_init(&clc_empty[s], kClcConsumers);
     }
     fence_barrier_init();
   }
@@ -179,7 +216,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int pt = first_pair; pt < total_pairs; pt += pair_step) {
+      TileFeed tf;
+      for (int pt = first_pair; pt >= 0; pt = next_tile(tf, pt, true, false)) {
         const PairTile tc = decode_pair(pt, p, pairs_per_seq, rank);
         for (int kb = 0; kb < num_kb; ++kb) {
           const int tap = kb / p.kblocks_per_tap;
@@ -214,7 +252,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int pt = first_pair; pt < total_pairs; pt += pair_step) {
+      TileFeed tf;
+      for (int pt = first_pair; pt >= 0; pt = next_tile(tf, pt, true, false)) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kBN;
@@ -240,6 +279,31 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
     __syncwarp();
+  } else if (warp == kSchedWarp) {
+    // ------------------------------------------------------------------ tile scheduler (leader CTA, dynamic mode)
+    // One outstanding steal per free response slot: arm the slot's barrier in both CTAs, ask the hardware to cancel the
+    // next cluster of this grid that has not started, and look at the answer only to learn when to stop (the first
+    // refusal ends the sequence for every consumer as well).
+    if (dyn && rank == 0 && lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      while (true) {
+        mbar_wait(&clc_empty[slot], phase ^ 1);
+        mbar_expect_tx(&clc_full[slot], 16);
+        mbar_expect_tx_cluster(map_to_cta(smem_u32(&clc_full[slot]), 1), 16);
+        clc_try_cancel_multicast(clc_resp + 16 * slot, &clc_full[slot]);
+        mbar_wait(&clc_full[slot], phase);
+        int x;
+        const bool ok = clc_query(clc_resp + 16 * slot, x);
+        fence_proxy_async_smem();
+        if (!ok) break;
+        if (++slot == kClcSlots) {
+          slot = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
     constexpr int kChunks = kBN / 64;   // 32-column chunks per epilogue warp
@@ -250,26 +314,18 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     unsigned out_buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    // EPI: this warp's chunks form one stream gc = tile iteration * kChunks + chunk; chunk gc is staged in buffer
-    // gc % kOutBufs, whose side tile was requested while chunk gc - 2 was being finished
+    // EPI: this warp's chunks form one stream gc = tiles done * kChunks + chunk; chunk gc is staged in buffer
+    // gc % kOutBufs. A side tile is requested two chunks ahead of its use within a tile, the first two of a tile at the
+    // top of the tile (before the wait for its accumulator, which hides their latency).
     const bool side_on = EPI && p.side_mode != 0;
     int gc = 0;
-    auto side_issue = [&](int g) {   // lane 0: request the side tile of chunk g (no-op past the last tile)
-      const int it = g / kChunks;
-      const int pt = first_pair + it * pair_step;
-      if (pt >= total_pairs) return;
-      const PairTile tcs = decode_pair(pt, p, pairs_per_seq, rank);
+    auto side_issue = [&](const PairTile& tcs, int ci, int g) {   // lane 0: side tile of chunk ci of tile tcs, stream index g
       const int bb = g % kOutBufs;
       uint64_t* bar = &side_bar[epi * kOutBufs + bb];
       mbar_expect_tx(bar, 32 * 64);
-      tma_load_3d(out_stage + bb * kOutBufBytes + epi * (32 * 64), &tmS, bar,
-                  tcs.n0 * kBN + (half * kChunks + (g - it * kChunks)) * 32, tcs.t0 + quad * 32 + p.side_row_off,
-                  tcs.seq);
+      tma_load_3d(out_stage + bb * kOutBufBytes + epi * (32 * 64), &tmS, bar, tcs.n0 * kBN + (half * kChunks + ci) * 32,
+                  tcs.t0 + quad * 32 + p.side_row_off, tcs.seq);
     };
-    if (side_on && lane == 0) {
-      side_issue(0);
-      side_issue(1);
-    }
     DropCtx drop;
     drop.on = false;
     if (EPI && p.drop.p > 0.f) drop = make_drop(p.drop);
@@ -290,8 +346,14 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     };
     const uint32_t empty_leader0 = map_to_cta(smem_u32(&tmem_empty_bar[0]), 0);
     const uint32_t empty_leader1 = map_to_cta(smem_u32(&tmem_empty_bar[1]), 0);
-    for (int pt = first_pair; pt < total_pairs; pt += pair_step) {
+    TileFeed tf;
+    for (int pt = first_pair; pt >= 0; pt = next_tile(tf, pt, lane == 0, true)) {
       const PairTile tc = decode_pair(pt, p, pairs_per_seq, rank);
+      if (side_on && lane == 0) {
+        tma_store_wait_read<0>();     // the staging buffers of the previous tile's last chunks have been drained
+        side_issue(tc, 0, gc);
+        side_issue(tc, 1, gc + 1);
+      }
       if (p.stat_sum != nullptr && tc.n0 != stat_n0) {
         stat_flush();
         stat_n0 = tc.n0;
@@ -476,10 +538,10 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (lane == 0) {
           tma_store_3d(&tmC, my_stage, col0, tc.t0 + quad * 32, tc.seq);
           tma_store_commit();
-          if (side_on) {
+          if (side_on && c + 2 < (half + 1) * kChunks) {
             // chunk gc + 2 reuses the buffer of chunk gc - 1: its store (all but the newest one) has drained it
             tma_store_wait_read<1>();
-            side_issue(gc + kOutBufs - 1);
+            side_issue(tc, c + 2 - half * kChunks, gc + 2);
           }
         }
         ++gc;
@@ -563,7 +625,7 @@ cudaError_t launch_conv_gemm_pair(int dtype, int w_mn_major, const CUtensorMap& 
   const int pairs_per_seq = (p.m_tiles_per_seq + 1) / 2;
   const long long total_pairs = (long long)p.a_seqs * pairs_per_seq * p.n_tiles;
   int clusters = sm_count / 2;
-  if (total_pairs < clusters) clusters = (int)total_pairs;
+  if (total_pairs < clusters || p.dyn_sched) clusters = (int)total_pairs;   // dynamic: one cluster per tile, most get stolen
   if (clusters < 1) return cudaSuccess;
   // statistics: a cluster count that is a multiple of the column-tile count keeps every CTA on one column tile, so its
   // per-channel sums stay in registers for the whole launch and are flushed once

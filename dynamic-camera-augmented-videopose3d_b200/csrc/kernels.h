@@ -85,6 +85,11 @@ struct ConvGemmParams {
   BnFinalizeParams fin;
   unsigned int* fin_counter;   // zero on entry; counts finished CTAs
 
+  // CTA-pair kernel: 1 = the grid has one cluster per tile and running clusters steal the tiles of clusters that were not
+  // launched yet (cluster launch control) instead of walking a static persistent schedule -- a launch then adapts to
+  // SMs that are busy with something else (NCCL's all-reduce CTAs during a data-parallel backward)
+  int dyn_sched;
+
   // CTA-pair kernel only (conv_gemm2.cu, EPI = 1):
   DropoutParams drop;   // drop.p > 0: dropout after the ReLU, keyed by (flat output row seq * rows_out + t, 8-channel group)
   int side_mode;        // epilogue side input fetched by TMA (tmS, geometry of the output): 0 none,
@@ -114,6 +119,7 @@ struct WgradParams {
   int b_row_off;        // input row read against gradient row 0 by tap 0
   int b_tap_row_step;   // extra input rows per tap (dilation)
   int b_tap_col_step;   // extra input columns per tap (stride == width layers on the reshaped view)
+  int dyn_sched;        // 1: grid = one CTA per item, running CTAs steal the items of CTAs not yet launched (wgrad.cu)
   float* out;           // packed fp32 [taps][co_pad][ci_pad]
   long long out_tap_stride;
   long long out_row_stride;

@@ -490,4 +490,139 @@ cudaError_t launch_n_mpjpe_bwd(const float* pred, const float* tgt, const float*
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused reprojection loss: mpjpe(project_to_2d(pose + trajectory, camera_params), target_2d) in ONE pass over the points
+// (common/camera.py:37-67 + common/loss.py:11-17; the reprojection term of upstream VideoPose3D's semi-supervised
+// step, whose primitives are all this fork keeps). Unfused it is an add, the projection kernel, the 2-D error
+// reduction and -- backwards -- the error gradient, the projection backward and the broadcast-sum of the trajectory
+// gradient: 20 B / point written and read again between the kernels. Here the forward reads 12 B (pose) + 8 B (target)
+// per point, the backward the same and writes 12 B.
+struct ReprojArgs {
+  const float* pose;     // [n_pts][3] camera-space points
+  const float* traj;     // optional [n_pts / pts_per_traj][3], added to every point of its group
+  const float* cam;      // [n_pts / pts_per_cam][9]
+  const float* tgt;      // [n_pts][2]
+  long long n_pts, pts_per_traj, pts_per_cam;
+  int linear;
+};
+
+struct Reproj {
+  float u, v;              // projected point
+  float rx, ry, xx, yy;    // unclamped and clamped normalised coordinates
+  float x, y, z;
+};
+__device__ __forceinline__ float clamp_unit_keep_nan(float x) {
+  if (x != x) return x;
+  return fminf(fmaxf(x, -1.f), 1.f);
+}
+__device__ __forceinline__ Reproj reproject(const ReprojArgs& a, long long i, const float*& c) {
+  Reproj r;
+  r.x = a.pose[3 * i];
+  r.y = a.pose[3 * i + 1];
+  r.z = a.pose[3 * i + 2];
+  if (a.traj != nullptr) {
+    const float* t = a.traj + 3 * (i / a.pts_per_traj);
+    r.x += __ldg(t);
+    r.y += __ldg(t + 1);
+    r.z += __ldg(t + 2);
+  }
+  c = a.cam + 9 * (i / a.pts_per_cam);
+  r.rx = r.x / r.z;
+  r.ry = r.y / r.z;
+  r.xx = clamp_unit_keep_nan(r.rx);
+  r.yy = clamp_unit_keep_nan(r.ry);
+  const float fx = __ldg(c), fy = __ldg(c + 1), cx = __ldg(c + 2), cy = __ldg(c + 3);
+  if (a.linear) {
+    r.u = fx * r.xx + cx;
+    r.v = fy * r.yy + cy;
+  } else {
+    const float k1 = __ldg(c + 4), k2 = __ldg(c + 5), k3 = __ldg(c + 6), p1 = __ldg(c + 7), p2 = __ldg(c + 8);
+    const float r2 = r.xx * r.xx + r.yy * r.yy;
+    const float s = 1.f + r2 * (k1 + r2 * (k2 + r2 * k3)) + p1 * r.xx + p2 * r.yy;
+    r.u = fx * (r.xx * s + p1 * r2) + cx;
+    r.v = fy * (r.yy * s + p2 * r2) + cy;
+  }
+  return r;
+}
+
+__global__ void __launch_bounds__(kLossThreads)
+reproj_partial_kernel(const ReprojArgs a, double* __restrict__ partial) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_pts; i += stride) {
+    const float* c;
+    const Reproj r = reproject(a, i, c);
+    const float2 t = __ldg(reinterpret_cast<const float2*>(a.tgt) + i);
+    const float du = r.u - t.x, dv = r.v - t.y;
+    acc += (double)sqrtf(du * du + dv * dv);
+  }
+  const double s = block_sum(acc);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// grad_pose[i] = d loss / d pose[i]; grad_traj (zero on entry) += the same summed over the points of its group
+__global__ void __launch_bounds__(kLossThreads)
+reproj_bwd_kernel(const ReprojArgs a, const float* __restrict__ grad_out, float inv_count, float* __restrict__ grad_pose,
+                  float* __restrict__ grad_traj) {
+  const float g0 = __ldg(grad_out) * inv_count;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_pts; i += stride) {
+    const float* c;
+    const Reproj r = reproject(a, i, c);
+    const float2 t = __ldg(reinterpret_cast<const float2*>(a.tgt) + i);
+    const float du = r.u - t.x, dv = r.v - t.y;
+    const float nrm = sqrtf(du * du + dv * dv);
+    const float k = nrm > 0.f ? g0 / nrm : 0.f;
+    // chain of project_bwd_kernel (projection.cu) with g = (du, dv) * k
+    const float ga = __ldg(c) * du * k, gb = __ldg(c + 1) * dv * k;
+    float gxx = ga, gyy = gb;
+    if (!a.linear) {
+      const float k1 = __ldg(c + 4), k2 = __ldg(c + 5), k3 = __ldg(c + 6), p1 = __ldg(c + 7), p2 = __ldg(c + 8);
+      const float r2 = r.xx * r.xx + r.yy * r.yy;
+      const float s = 1.f + r2 * (k1 + r2 * (k2 + r2 * k3)) + p1 * r.xx + p2 * r.yy;
+      const float gs = ga * r.xx + gb * r.yy;
+      const float gr2 = ga * p1 + gb * p2 + gs * (k1 + r2 * (2.f * k2 + 3.f * k3 * r2));
+      gxx = ga * s + gs * p1 + gr2 * 2.f * r.xx;
+      gyy = gb * s + gs * p2 + gr2 * 2.f * r.yy;
+    }
+    if (!(r.rx >= -1.f && r.rx <= 1.f)) gxx = 0.f;   // torch.clamp backward
+    if (!(r.ry >= -1.f && r.ry <= 1.f)) gyy = 0.f;
+    const float iz = 1.f / r.z;
+    const float gx = gxx * iz, gy = gyy * iz, gz = -(gxx * r.x + gyy * r.y) * iz * iz;
+    if (grad_pose != nullptr) {
+      grad_pose[3 * i] = gx;
+      grad_pose[3 * i + 1] = gy;
+      grad_pose[3 * i + 2] = gz;
+    }
+    if (grad_traj != nullptr) {
+      float* gt = grad_traj + 3 * (i / a.pts_per_traj);
+      atomicAdd(gt, gx);
+      atomicAdd(gt + 1, gy);
+      atomicAdd(gt + 2, gz);
+    }
+  }
+}
+
+cudaError_t launch_reproj_fwd(const float* pose, const float* traj, long long n_pts, long long pts_per_traj,
+                              const float* cam, long long pts_per_cam, int linear, const float* tgt, double* partial,
+                              float* out, int sm_count, cudaStream_t stream) {
+  const ReprojArgs a{pose, traj, cam, tgt, n_pts, pts_per_traj > 0 ? pts_per_traj : 1, pts_per_cam > 0 ? pts_per_cam : 1,
+                     linear};
+  const int grid = loss_grid(n_pts * 4, sm_count);
+  reproj_partial_kernel<<<grid, kLossThreads, 0, stream>>>(a, partial);
+  mean_finish_kernel<<<1, kLossThreads, 0, stream>>>(partial, grid, n_pts > 0 ? 1.0 / (double)n_pts : 0.0, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reproj_bwd(const float* pose, const float* traj, long long n_pts, long long pts_per_traj,
+                              const float* cam, long long pts_per_cam, int linear, const float* tgt,
+                              const float* grad_out, float* grad_pose, float* grad_traj, int sm_count,
+                              cudaStream_t stream) {
+  const ReprojArgs a{pose, traj, cam, tgt, n_pts, pts_per_traj > 0 ? pts_per_traj : 1, pts_per_cam > 0 ? pts_per_cam : 1,
+                     linear};
+  const int grid = loss_grid(n_pts * 4, sm_count);
+  reproj_bwd_kernel<<<grid, kLossThreads, 0, stream>>>(a, grad_out, 1.f / (float)n_pts, grad_pose, grad_traj);
+  return cudaGetLastError();
+}
+
 }  // namespace vp3d

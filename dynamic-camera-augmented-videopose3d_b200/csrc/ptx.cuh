@@ -278,6 +278,49 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t cta_mas
 }
 
 // ----------------------------------------------------------------------------------------------
+// Cluster launch control (sm_100): a running cluster cancels a cluster of the same grid that has not been launched yet
+// and takes over its tile -- hardware work stealing for a grid of one cluster per tile. The 16-byte response is written
+// (async proxy) to the same shared-memory offset in EVERY CTA of the cluster and completes 16 bytes on the mbarrier at
+// the same offset in every CTA.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar_cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster_addr), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void clc_try_cancel_multicast(void* response16, uint64_t* bar) {
+  asm volatile(
+      "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 "
+      "[%0], [%1];" ::"r"(smem_u32(response16)),
+      "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void clc_try_cancel(void* response16, uint64_t* bar) {
+  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];" ::"r"(
+                   smem_u32(response16)),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+// -> true and ctaid.x of the first CTA of the cancelled cluster, or false (nothing left to cancel: stop asking)
+__device__ __forceinline__ bool clc_query(const void* response16, int& first_ctaid_x) {
+  uint32_t ok, x;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p1;\n\t"
+      ".reg .b128 r;\n\t"
+      "ld.shared.b128 r, [%2];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+      "selp.u32 %1, 1, 0, p1;\n\t"
+      "mov.u32 %0, 0;\n\t"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, _, _, _}, r;\n\t"
+      "}\n"
+      : "=r"(x), "=r"(ok)
+      : "r"(smem_u32(response16))
+      : "memory");
+  first_ctaid_x = (int)x;
+  return ok != 0;
+}
+
+// ----------------------------------------------------------------------------------------------
 // Descriptors
 // ----------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor for a K-major tile whose rows are exactly one 128-byte swizzle span

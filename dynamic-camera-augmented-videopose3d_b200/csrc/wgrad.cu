@@ -26,7 +26,10 @@
 namespace vp3d {
 
 constexpr int kWgRows = 64;       // frames (reduction depth) per pipeline stage
-constexpr int kWgThreads = 192;
+constexpr int kWgThreads = 224;   // TMA producer, MMA issuer, 4 epilogue warps, tile scheduler
+constexpr int kWgSchedWarp = 6;
+constexpr int kWgClcSlots = 2;
+constexpr int kWgClcConsumers = 1 + 1 + 4;   // producer, MMA thread, epilogue warps
 
 // BM = output channels per tile. BM = 256 (two 128-row MMAs sharing the B tile, all 512 TMEM columns as ONE accumulator
 // set) is the wide-layer configuration: both operands of a weight gradient stream from L2 / HBM with no reuse inside a
@@ -42,7 +45,7 @@ struct WgradCfg {
   static constexpr int kAccBufs = (BM == 256) ? 1 : 2;
   static constexpr int kAccCols = (BM / 128) * BN;         // TMEM columns of one accumulator set
   static constexpr int kTmemCols = (kAccBufs * kAccCols < 32) ? 32 : kAccBufs * kAccCols;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 256 + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 512 + 1024;
 };
 
 // MN-major SWIZZLE_128B operand: 64-element (128-byte) channel groups `lbo` bytes apart, 8-frame groups 1024 B apart.
@@ -87,9 +90,38 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tmem_full_bar = bars + 2 * Cfg::kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* clc_full = bars + 2 * Cfg::kStages + 6;          // dynamic schedule (p.dyn_sched): response landed
+  uint64_t* clc_empty = clc_full + kWgClcSlots;              // every consumer has read the response
+  uint8_t* clc_resp = reinterpret_cast<uint8_t*>(bars) + 256;   // kWgClcSlots x 16 bytes
+  static_assert((2 * Cfg::kStages + 6 + 2 * kWgClcSlots) * 8 <= 256, "barrier area layout");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool dyn = p.dyn_sched != 0;
+  // Work items of this CTA. Static: blockIdx.x, + gridDim.x, ... Dynamic: the grid has one CTA per item; a running CTA
+  // takes its own item, then the items of CTAs that have not been launched yet (cluster launch control) -- CTAs that
+  // cannot be placed because something else (NCCL) holds their SM just never get work.
+  struct ItemFeed {
+    int slot = 0;
+    uint32_t phase = 0;
+  };
+  auto next_item = [&](ItemFeed& f, int item, bool elected, bool whole_warp, int num_items_) -> int {
+    if (!dyn) {
+      item += gridDim.x;
+      return item < num_items_ ? item : -1;
+    }
+    mbar_wait(&clc_full[f.slot], f.phase);
+    int x;
+    const bool ok = clc_query(clc_resp + 16 * f.slot, x);
+    fence_proxy_async_smem();
+    if (whole_warp) __syncwarp();
+    if (elected) mbar_arrive(&clc_empty[f.slot]);
+    if (++f.slot == kWgClcSlots) {
+      f.slot = 0;
+      f.phase ^= 1;
+    }
+    return ok ? x : -1;
+  };
 
   // row blocks kb = seq * kb_per_seq + block-in-sequence; slice s owns kb in [s * kb_all / S, (s + 1) * kb_all / S)
   const long long kb_all = (long long)p.seqs * p.kb_per_seq;
@@ -105,6 +137,10 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], 128);
+    }
+    for (int s = 0; s < kWgClcSlots; ++s) {
+      mbar_init(&clc_full[s], 1);
+      mbar_init(&clc_empty[s], kWgClcConsumers);
     }
     fence_barrier_init();
   }
@@ -122,7 +158,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      ItemFeed feed;
+      for (int item = blockIdx.x; item >= 0; item = next_item(feed, item, true, false, num_items)) {
         const int sl = item / p.num_tiles;
         const int tile = item - sl * p.num_tiles;
         const long long kb_lo = kb_all * sl / p.num_slices;
@@ -159,7 +196,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      ItemFeed feed;
+      for (int item = blockIdx.x; item >= 0; item = next_item(feed, item, true, false, num_items)) {
         const int sl = item / p.num_tiles;
         const long long kb_lo = kb_all * sl / p.num_slices;
         const long long kb_hi = kb_all * (sl + 1) / p.num_slices;
@@ -198,13 +236,35 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
     __syncwarp();
+  } else if (warp == kWgSchedWarp) {
+    // ------------------------------------------------------------------ tile scheduler (dynamic mode)
+    if (dyn && lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      while (true) {
+        mbar_wait(&clc_empty[slot], phase ^ 1);
+        mbar_expect_tx(&clc_full[slot], 16);
+        clc_try_cancel(clc_resp + 16 * slot, &clc_full[slot]);
+        mbar_wait(&clc_full[slot], phase);
+        int x;
+        const bool ok = clc_query(clc_resp + 16 * slot, x);
+        fence_proxy_async_smem();
+        if (!ok) break;
+        if (++slot == kWgClcSlots) {
+          slot = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5): TMEM -> red.add
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    ItemFeed feed;
+    for (int item = blockIdx.x; item >= 0; item = next_item(feed, item, lane == 0, true, num_items)) {
       const int sl = item / p.num_tiles;
       const int tile = item - sl * p.num_tiles;
       int tap, co0, ci_t;

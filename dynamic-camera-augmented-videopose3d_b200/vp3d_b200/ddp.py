@@ -32,9 +32,14 @@ def shard_range(n_items, rank, world):
 
 
 class GradSync:
-    """Averages parameter gradients over the ranks of `group`, overlapped with the backward pass."""
+    """Averages parameter gradients over the ranks of `group`, overlapped with the backward pass.
+    `compress='bf16'`: gradients travel as bfloat16 (half the bytes on the wire; the sum over ranks is taken in bf16, a
+    relative error of ~2^-9 per gradient element -- far below the ~5e-2 that 16-bit GEMM operands already put on these
+    gradients) and are written back into the fp32 gradient tensors the optimiser reads."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, compress=None):
+        assert compress in (None, 'bf16')
+        self.compress = compress
         self.group = group
         self.world = dist.get_world_size(group)
         backend = dist.get_backend(group)
@@ -55,9 +60,10 @@ class GradSync:
 
     def _launch(self, t):
         op = self._avg if self._avg is not None else dist.ReduceOp.SUM
-        work = dist.all_reduce(t, op=op, group=self.group, async_op=True)
-        self._pending.append((work, t))
-        self.bytes_reduced += t.numel() * t.element_size()
+        wire = t.to(torch.bfloat16) if (self.compress == 'bf16' and t.dtype == torch.float32) else t
+        work = dist.all_reduce(wire, op=op, group=self.group, async_op=True)
+        self._pending.append((work, t, wire))
+        self.bytes_reduced += wire.numel() * wire.element_size()
         self.collectives += 1
 
     def finish(self):
@@ -68,8 +74,10 @@ class GradSync:
         if self._small:
             flat = torch.cat([g.reshape(-1) for g in self._small])
             self._launch(flat)
-        for work, t in self._pending:
+        for work, t, wire in self._pending:
             work.wait()
+            if wire is not t:
+                t.copy_(wire)
             if self._avg is None:
                 t.div_(self.world)
         if flat is not None:
@@ -84,8 +92,14 @@ class GradSync:
 _active = None
 
 
-def enable_grad_sync(group=None, reserve_sms=0):
+def enable_grad_sync(group=None, reserve_sms=0, dynamic_schedule=None, compress=None):
     """Install gradient averaging for every vp3d_b200 training backward of this process. Returns the GradSync.
+    `dynamic_schedule` (default off; env VP3D_DDP_SCHED=dynamic turns it on): the big GEMMs of the backward take their
+    tiles dynamically (cluster launch control, vp3d_set_sched_mode) instead of walking a static persistent schedule, so
+    SMs that NCCL's all-reduce CTAs occupy only shrink the pool of workers instead of leaving a fixed share of the tiles
+    waiting behind them. Measured at 2 GPUs (profiles/README.md): within the box-to-box noise of the static schedule
+    (1.96-2.01 vs 1.96-1.99 ms per step), so it is an option, not the default.
+    `compress='bf16'` (env VP3D_DDP_COMPRESS=bf16): see GradSync.
     `reserve_sms` > 0 sizes the persistent GEMM grids for that many SMs fewer than the device has, so that NCCL's
     all-reduce CTAs (cap them with NCCL_MAX_CTAS <= reserve_sms before the process group is created) run beside the
     backward GEMMs instead of taking turns with them."""
@@ -94,7 +108,14 @@ def enable_grad_sync(group=None, reserve_sms=0):
         from . import native
         sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
         native.check(native.lib().vp3d_set_sm_limit(int(sms - reserve_sms)), 'set_sm_limit')
-    _active = GradSync(group)
+    if compress is None:
+        compress = os.environ.get('VP3D_DDP_COMPRESS') or None
+    _active = GradSync(group, compress=compress)
+    if dynamic_schedule is None:
+        dynamic_schedule = _active.world > 1 and os.environ.get('VP3D_DDP_SCHED', 'static') == 'dynamic'
+    if torch.cuda.is_available():
+        from . import native
+        native.check(native.lib().vp3d_set_sched_mode(1 if dynamic_schedule else 0), 'set_sched_mode')
     training.grad_ready_hook = _active
     training.grad_finish_hook = _active.finish
     return _active
@@ -106,6 +127,7 @@ def disable_grad_sync():
     if torch.cuda.is_available():
         from . import native
         native.check(native.lib().vp3d_set_sm_limit(0), 'set_sm_limit')
+        native.check(native.lib().vp3d_set_sched_mode(0), 'set_sched_mode')
     training.grad_ready_hook = None
     training.grad_finish_hook = None
 

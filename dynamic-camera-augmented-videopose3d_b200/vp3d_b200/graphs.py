@@ -21,7 +21,9 @@ class GraphedTrainStep:
         self.model, self.optimizer, self.loss_fn = model, optimizer, loss_fn
         self.preprocess = preprocess if preprocess is not None else (lambda *a: a[0])
         self.static_inputs = [t.clone() for t in example_inputs]
-        self.static_target = example_target.clone()
+        # (a tuple of tensors is passed to loss_fn as a tuple: composite losses with several targets)
+        self.static_target = (tuple(t.clone() for t in example_target) if isinstance(example_target, (tuple, list))
+                              else example_target.clone())
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -46,7 +48,11 @@ class GraphedTrainStep:
         for dst, src in zip(self.static_inputs, inputs):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
-        if target is not None and target.data_ptr() != self.static_target.data_ptr():
-            self.static_target.copy_(target, non_blocking=True)
+        if target is not None:
+            pairs = (zip(self.static_target, target) if isinstance(self.static_target, tuple)
+                     else [(self.static_target, target)])
+            for dst, src in pairs:
+                if dst.data_ptr() != src.data_ptr():
+                    dst.copy_(src, non_blocking=True)
         self.graph.replay()
         return self.static_loss

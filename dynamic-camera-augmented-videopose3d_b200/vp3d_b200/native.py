@@ -91,6 +91,7 @@ _SIGNATURES = {
     'vp3d_device_info': (C.c_int, [C.POINTER(C.c_int)] * 3),
     'vp3d_set_sm_limit': (C.c_int, [C.c_int]),
     'vp3d_set_pair_mode': (C.c_int, [C.c_int]),
+    'vp3d_set_sched_mode': (C.c_int, [C.c_int]),
     'vp3d_conv_block_fwd': (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     'vp3d_pack_rows': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
     'vp3d_pack_rows_ones': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int,
@@ -123,6 +124,10 @@ _SIGNATURES = {
     'vp3d_velocity_error': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p,
                                       C.c_void_p]),
     'vp3d_n_mpjpe_bwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
+    'vp3d_reproj_mpjpe_fwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_longlong,
+                                        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'vp3d_reproj_mpjpe_bwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_longlong,
+                                        C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'vp3d_wgrad': (C.c_int, [C.POINTER(WgradArgs), C.c_void_p]),
     'vp3d_wgrad_finish': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 3 + [C.c_longlong] * 2 + [C.c_void_p, C.c_void_p]),
     'vp3d_bn_finalize': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_float, C.c_float] +

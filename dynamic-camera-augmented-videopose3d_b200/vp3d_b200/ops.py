@@ -162,6 +162,55 @@ def mpjpe(pred, tgt, w=None):
     return _MpjpeFn.apply(pred, tgt, w)
 
 
+class _ReprojFn(torch.autograd.Function):
+    """mpjpe(project_to_2d(pose + traj, cam), target_2d) in one kernel each way (vp3d_reproj_mpjpe_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, pose, traj, cam, tgt2, linear):
+        p, c, t2 = f32c(pose), f32c(cam), f32c(tgt2)
+        tr = None if traj is None else f32c(traj)
+        n_pts = p.numel() // 3
+        per_cam = max(n_pts // max(c.shape[0], 1), 1)
+        per_traj = 0 if tr is None else n_pts // (tr.numel() // 3)
+        out = torch.empty((), dtype=torch.float32, device=p.device)
+        with torch.cuda.device(p.device):
+            check(lib().vp3d_reproj_mpjpe_fwd(_ptr(p), _ptr(tr), n_pts, per_traj, _ptr(c), per_cam, 1 if linear else 0,
+                                              _ptr(t2), _ptr(_loss_workspace(p.device)), _ptr(out), _stream()),
+                  'reproj_mpjpe_fwd')
+        ctx.save_for_backward(p, tr if tr is not None else torch.empty(0, device=p.device), c, t2)
+        ctx.meta = (n_pts, per_traj, per_cam, linear, tr is not None, pose.shape, None if traj is None else traj.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        p, tr, c, t2 = ctx.saved_tensors
+        n_pts, per_traj, per_cam, linear, has_traj, pshape, tshape = ctx.meta
+        want_p = ctx.needs_input_grad[0]
+        want_t = has_traj and ctx.needs_input_grad[1]
+        if not (want_p or want_t):
+            return None, None, None, None, None
+        gp = torch.empty_like(p) if want_p else None
+        gt = torch.zeros_like(tr) if want_t else None
+        with torch.cuda.device(p.device):
+            check(lib().vp3d_reproj_mpjpe_bwd(_ptr(p), _ptr(tr) if has_traj else None, n_pts, per_traj, _ptr(c), per_cam,
+                                              1 if linear else 0, _ptr(t2), _ptr(f32c(grad_out).reshape(1)), _ptr(gp),
+                                              _ptr(gt), _stream()), 'reproj_mpjpe_bwd')
+        return (gp.reshape(pshape) if want_p else None, gt.reshape(tshape) if want_t else None, None, None, None)
+
+
+def reproj_mpjpe(pose, camera_params, target_2d, traj=None, linear=False):
+    """Reprojection loss mpjpe(project_to_2d(pose + traj, camera_params), target_2d) (camera.py:37-67 + loss.py:11-17)
+    fused into one kernel per direction. pose (N, ..., J, 3) camera-space points, traj (N, ..., 1, 3) or None (added to
+    every joint of its pose), camera_params (N, 9), target_2d (N, ..., J, 2). Differentiable wrt pose and traj."""
+    require_cuda(pose, camera_params, target_2d, traj)
+    assert pose.shape[-1] == 3 and target_2d.shape[-1] == 2 and tuple(pose.shape[:-1]) == tuple(target_2d.shape[:-1])
+    assert camera_params.dim() == 2 and camera_params.shape[-1] == 9 and camera_params.shape[0] == pose.shape[0]
+    if traj is not None:
+        assert traj.shape[-1] == 3 and traj.shape[-2] == 1 and tuple(traj.shape[:-2]) == tuple(pose.shape[:-2]), \
+            'traj must be (..., 1, 3) with the leading dimensions of pose'
+    return _ReprojFn.apply(pose, traj, camera_params, target_2d, linear)
+
+
 class _NMpjpeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, tgt):

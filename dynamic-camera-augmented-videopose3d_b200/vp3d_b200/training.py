@@ -228,19 +228,48 @@ def _views(L, n, c_pad):
     return ((n, L.t_out, c_pad, L.t_out * c_pad), (L.t_in, L.c_in_pad, L.c_in_pad, L.t_in * L.c_in_pad), d, 0)
 
 
-def _weight_grad(dt, L, dz, n, c_pad, gscale, keep=None):
+def _packed_floats(L, c_pad):
+    """fp32 elements of the zero-filled split-K accumulator of one layer's weight gradient."""
+    if L.fused is not None or (L.stride > 1 and L.taps * L.c_in_pad <= 256):
+        return c_pad * 256
+    return L.taps * c_pad * L.c_in_pad
+
+
+class _ZeroArena:
+    """ONE zero-filled buffer per backward for every split-K accumulator and the BatchNorm-backward sums (one fill
+    launch instead of one per layer: ~20 launches of 2-4 us each at batch 1024)."""
+
+    def __init__(self, n_floats, device):
+        self.buf = torch.zeros(n_floats, dtype=torch.float32, device=device)
+        self.used = 0
+
+    def take(self, shape, dtype=torch.float32):
+        n = 1
+        for d in shape:
+            n *= d
+        words = n * (2 if dtype == torch.float64 else 1)
+        self.used = (self.used + 3) // 4 * 4                    # 16-byte aligned views
+        out = self.buf[self.used:self.used + words]
+        assert out.numel() == words, 'zero arena exhausted'
+        self.used += words
+        return out.view(dtype).view(shape)
+
+
+def _weight_grad(dt, L, dz, n, c_pad, gscale, keep=None, arena=None):
     dzv, av, row_step, col_step = _views(L, n, c_pad)
     c_out = L.conv.out_channels
+    zeros = (lambda shape: arena.take(shape)) if arena is not None else (
+        lambda shape: torch.zeros(shape, dtype=torch.float32, device=dz.device))
     if L.stride > 1 and L.taps * L.c_in_pad <= 256:
         # narrow strided layer (expand: 3 x 64 input columns): all taps are adjacent columns of the reshaped view, so
         # they form ONE 256-wide tile (columns past taps * c_in_pad are zero-filled by TMA) and dz is read once
-        packed = torch.zeros((1, c_pad, 256), dtype=torch.float32, device=dz.device)
+        packed = zeros((1, c_pad, 256))
         if keep is not None:
             keep.append(packed)
         ops.wgrad(dt, dz, dzv, L.a_in, av, c_pad, 256, 1, packed, block_n=256)
         return ops.wgrad_finish(packed, c_out, L.c_in, L.taps, c_pad, 256, gscale, tap_stride=L.c_in_pad, row_stride=256)
     block_n = 256 if L.c_in_pad % 256 == 0 else 64
-    packed = torch.zeros((L.taps, c_pad, L.c_in_pad), dtype=torch.float32, device=dz.device)
+    packed = zeros((L.taps, c_pad, L.c_in_pad))
     if keep is not None:
         keep.append(packed)
     ops.wgrad(dt, dz, dzv, L.a_in, av, c_pad, L.c_in_pad, L.taps, packed, b_tap_row_step=row_step,
@@ -350,6 +379,11 @@ class _StackTrainFn(torch.autograd.Function):
                 side.wait_event(ev)
                 return fn()
 
+        # every zero-initialised accumulator of this backward in one fill
+        arena = _ZeroArena(4 * len(layers) * c_pad + SHRINK_PAD * c_pad + sum(_packed_floats(L, c_pad) for L in layers) +
+                           8 * (len(layers) + 2), dy.device)
+        sums_all = arena.take((len(layers), 2, c_pad), torch.float64)
+
         # ---- shrink layer: y = a_last W^T + b
         n_out = model.shrink.out_channels
         dy2 = ops.f32c(dy).reshape(n * ctx.t_last, n_out)
@@ -359,7 +393,7 @@ class _StackTrainFn(torch.autograd.Function):
         rows = n * ctx.t_last
 
         def shrink_wgrad():
-            packed = torch.zeros((1, SHRINK_PAD, c_pad), dtype=torch.float32, device=dy.device)
+            packed = arena.take((1, SHRINK_PAD, c_pad))
             ops.wgrad(dt, dzs, (1, rows, SHRINK_PAD, rows * SHRINK_PAD), ctx.a_last, (rows, c_pad, c_pad, rows * c_pad),
                       SHRINK_PAD, c_pad, 1, packed)
             keep.append(packed)
@@ -372,7 +406,6 @@ class _StackTrainFn(torch.autograd.Function):
                        g, (c_pad, rows * c_pad), w_mn_major=(c_pad, 0))
 
         # ---- blocks and the expand layer, last to first. `g` is the gradient wrt the current layer's output.
-        sums_all = torch.zeros((len(layers), 2, c_pad), dtype=torch.float64, device=dy.device)   # one fill per backward
         for idx in range(len(layers) - 1, -1, -1):
             L = layers[idx]
             rows = n * L.t_out
@@ -381,7 +414,7 @@ class _StackTrainFn(torch.autograd.Function):
                 F = L.fused
 
                 def expand_grads(L=L, F=F, gm=g):
-                    p_packed = torch.zeros((1, c_pad, 256), dtype=torch.float32, device=gm.device)
+                    p_packed = arena.take((1, c_pad, 256))
                     keep.append(p_packed)
                     seqs, rws = F['xv'][0], F['xv'][1]
                     ops.wgrad(dt, gm, (seqs, rws, c_pad, rws * c_pad), L.a_in, F['av'], c_pad, 256, 1, p_packed,
@@ -398,7 +431,7 @@ class _StackTrainFn(torch.autograd.Function):
                                                L.drop, gscale, count=L.count, group=sync_bn_group, sums=sums_all[idx])
             done(L.bn.weight, dgamma)
             done(L.bn.bias, dbeta)
-            on_side(lambda L=L, dz=dz: done(L.conv.weight, _weight_grad(dt, L, dz, n, c_pad, gscale, keep)), dz)
+            on_side(lambda L=L, dz=dz: done(L.conv.weight, _weight_grad(dt, L, dz, n, c_pad, gscale, keep, arena)), dz)
             if idx == 0:
                 break  # no gradient wrt the 2-D keypoints (the reference never asks for one, run.py:458-485)
             if L.res_of is not None:

@@ -36,6 +36,14 @@ int vp3d_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * environment variable VP3D_SM_LIMIT sets the initial value). Used by data-parallel training to leave a few SMs to
  * NCCL's all-reduce kernels (vp3d_b200.ddp.enable_grad_sync(reserve_sms=...)); no reference counterpart. */
 int vp3d_set_sm_limit(int sms);
+/* Tile schedule of the CTA-pair kernel (launches without statistics of at least two waves of tiles): 0 = static
+ * persistent schedule, one cluster per SM pair walking tiles i, i + n, ... (default); 1 = dynamic: the grid has one
+ * cluster per tile and running clusters steal the tiles of clusters that have not been launched yet (cluster launch
+ * control, clusterlaunchcontrol.try_cancel). The dynamic schedule adapts to SMs that are busy with another kernel --
+ * NCCL's all-reduce CTAs during a data-parallel backward (vp3d_b200.ddp switches it on). Initial value from the
+ * environment variable VP3D_SCHED ("dynamic"). Mode 2 ("dynamic-all") applies it to every pair-kernel launch without
+ * statistics whatever its size (tests). Results are identical in all modes. */
+int vp3d_set_sched_mode(int mode);
 /* Which K1 kernel vp3d_conv_block_fwd launches: 0 = always the single-CTA kernel, 1 = the CTA-pair kernel
  * (tcgen05.mma.cta_group::2) for supported launches of at least two waves of tiles (default), 2 = for every supported
  * launch. Initial value from the environment variable VP3D_K1_2CTA ("0", "force"). */
@@ -273,6 +281,19 @@ int vp3d_velocity_error(const float* pred, const float* target, long long T, lon
 /* grad_pred = grad_out * d n_mpjpe / d pred (the scale factor is differentiated too, as autograd does for loss.py:77-80). */
 int vp3d_n_mpjpe_bwd(const float* pred, const float* target, const float* grad_out, long long n_poses, int J,
                      float* grad_pred, void* stream);
+
+/* Fused reprojection loss (north-star item 3, "projection kernel with fused MPJPE"):
+ *   out = mean_i || project_to_2d(pose[i] + traj[i / pts_per_traj], cam[i / pts_per_cam]) - target2[i] ||_2
+ * i.e. common/loss.py:11-17 applied to common/camera.py:37-67 (linear != 0: :69-90) in one pass over the points, without
+ * the 2-D projection ever reaching memory. `traj` may be NULL. The backward writes d out / d pose (grad_pose, may be
+ * NULL) and accumulates d out / d traj into grad_traj (ZERO on entry, may be NULL) with the clamp / z -> 0 conventions
+ * of vp3d_project_bwd. workspace: vp3d_loss_workspace_bytes(). */
+int vp3d_reproj_mpjpe_fwd(const float* pose, const float* traj, long long n_points, long long pts_per_traj,
+                          const float* cam, long long pts_per_cam, int linear, const float* target2, void* workspace,
+                          float* out, void* stream);
+int vp3d_reproj_mpjpe_bwd(const float* pose, const float* traj, long long n_points, long long pts_per_traj,
+                          const float* cam, long long pts_per_cam, int linear, const float* target2,
+                          const float* grad_out, float* grad_pose, float* grad_traj, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Training path (TemporalModel.py:126-138 / :188-198 in train() mode and their autograd backward, run.py:473-485).

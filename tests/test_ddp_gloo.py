@@ -68,6 +68,17 @@ def _worker(rank, world, port, out):
         assert torch.all(m.running_mean == 1.0)
         ddp.disable_grad_sync()
         assert training.grad_ready_hook is None
+        # bf16 on the wire: same protocol, half the bytes, fp32 gradients written back
+        sync16 = ddp.enable_grad_sync(compress='bf16')
+        g2 = [torch.randn(s, generator=torch.Generator().manual_seed(100 + rank)) for s in shapes[:2]]
+        for p_, g_ in zip(params[:2], g2):
+            training.grad_ready_hook(p_, g_)
+        training.grad_finish_hook()
+        want2 = sum(torch.randn(shapes[0], generator=torch.Generator().manual_seed(100 + r)) for r in range(world)) / world
+        rel = ((g2[0] - want2).norm() / want2.norm()).item()
+        assert g2[0].dtype == torch.float32 and rel < 1e-2, rel
+        assert sync16.bytes_reduced == 2 * sum(g.numel() for g in g2)
+        ddp.disable_grad_sync()
     finally:
         dist.destroy_process_group()
 

@@ -249,3 +249,43 @@ def test_frame_kernel_special_values_follow_the_reference():
     ok = ~np.isnan(want)
     np.testing.assert_allclose(got[ok], want[ok], atol=PROJ_TOL)
     np.testing.assert_allclose(gote[ok], want[ok], atol=PROJ_TOL)
+
+
+@pytest.mark.parametrize('with_traj', [False, True])
+@pytest.mark.parametrize('linear', [False, True])
+def test_fused_reprojection_loss_matches_the_composition(with_traj, linear):
+    """vp3d_reproj_mpjpe_fwd / _bwd (projection with the loss fused in, north-star item 3) against
+    mpjpe(project_to_2d(pose + traj, cam), target) composed from the drop-in functions -- value and both gradients --
+    and against the CPU oracle; includes points whose x / z saturates the clamp (zero gradient through it)."""
+    from common.camera import project_to_2d, project_to_2d_linear
+    from common.loss import mpjpe, reprojection_mpjpe
+    from oracle import camera as ocam
+    from oracle import loss as oloss
+    g = torch.Generator().manual_seed(91)
+    N, T, J = 37, 3, 31
+    pose = (torch.randn(N, T, J, 3, generator=g) * 0.4)
+    traj = torch.randn(N, T, 1, 3, generator=g) * 0.2 + torch.tensor([0.0, 0.0, 3.0])
+    if not with_traj:
+        pose = pose + torch.tensor([0.0, 0.0, 3.0])
+    pose[0, 0, :4, 0] = 9.0                      # |x / z| > 1: clamped, no gradient through x
+    cam = torch.tensor([2.29, 2.2876, 0.0251, 0.0289, -0.2071, 0.2478, -0.0031, -0.00098, -0.0014]).repeat(N, 1)
+    cam[:, 0] += torch.randn(N, generator=g) * 0.05
+    tgt = torch.randn(N, T, J, 2, generator=g) * 0.3
+    pc, tc = pose.cuda().requires_grad_(True), traj.cuda().requires_grad_(True)
+    fused = reprojection_mpjpe(pc, cam.cuda(), tgt.cuda(), trajectory=tc if with_traj else None, linear=linear)
+    fused.backward()
+    gp_f, gt_f = pc.grad.clone(), (tc.grad.clone() if with_traj else None)
+    pc2, tc2 = pose.cuda().requires_grad_(True), traj.cuda().requires_grad_(True)
+    X = pc2 + tc2 if with_traj else pc2
+    proj = (project_to_2d_linear if linear else project_to_2d)(X, cam.cuda())
+    ref = mpjpe(proj, tgt.cuda())
+    ref.backward()
+    assert abs(fused.item() - ref.item()) < 1e-6 * max(1.0, abs(ref.item()))
+    assert (gp_f - pc2.grad).abs().max().item() < 1e-7 + 1e-4 * pc2.grad.abs().max().item()
+    if with_traj:
+        assert (gt_f - tc2.grad).abs().max().item() < 1e-7 + 1e-4 * tc2.grad.abs().max().item()
+    assert gp_f[0, 0, :4, 0].abs().max().item() == 0
+    Xn = (pose + traj).numpy() if with_traj else pose.numpy()
+    p_ref = (ocam.project_to_2d_linear if linear else ocam.project_to_2d)(Xn, cam.numpy())
+    want = oloss.mpjpe(torch.from_numpy(p_ref), tgt).item()
+    assert abs(fused.item() - want) < 1e-5

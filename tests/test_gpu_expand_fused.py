@@ -275,3 +275,74 @@ def test_finalize_in_the_gemm_tail_is_bit_identical_to_the_stand_alone_launch(pa
     assert int(bn0.num_batches_tracked) == int(bn1.num_batches_tracked) == 2
     if momentum is None:     # cumulative average of two identical batches = the batch statistics themselves
         assert (bn1.running_mean[:n - 3] - o1[1][2][:n - 3]).abs().max().item() < 1e-6
+
+
+def test_dynamic_tile_schedule_gives_the_same_bits():
+    """Cluster launch control (one cluster per tile, running clusters steal the tiles of clusters not yet launched)
+    against the static persistent schedule: forward with residual, data gradient with MN-major weights + fan-in, and
+    both side-input modes -- identical outputs; sizes from one tile to many waves per cluster."""
+    dt, td = native.F16, torch.float16
+    g = torch.Generator().manual_seed(23)
+    lib = native.lib()
+
+    def run(sched, seqs, rows, c, n, kind):
+        a = (torch.randn(seqs, rows, c, generator=torch.Generator().manual_seed(seqs * rows + c)) * 0.5).to(td).cuda()
+        gen = torch.Generator().manual_seed(n + c)
+        out = torch.full((seqs, rows, n), float('nan'), dtype=td, device='cuda')
+        kw = {}
+        if kind == 'dgrad':
+            w = (torch.randn(c, n, generator=gen) / c ** 0.5).to(td).cuda()
+            kw['w_mn_major'] = (n, 0)
+        else:
+            w = (torch.randn(n, c, generator=gen) / c ** 0.5).to(td).cuda()
+            kw['shift'] = (torch.randn(n, generator=gen) * 0.2).cuda()
+            kw['relu'] = True
+        extra = (torch.randn(seqs, rows, n, generator=gen)).to(td).cuda()
+        if kind == 'res':
+            kw.update(res=extra, res_view=(n, rows * n, 1, 0))
+        elif kind == 'side_add':
+            kw.update(side=extra, side_view=(n, rows * n, rows, 0), side_mode=1)
+        elif kind == 'dgrad':
+            kw.update(side=torch.relu(extra), side_view=(n, rows * n, rows, 0), side_mode=2, side_scale=4.0 / 3.0)
+        native.check(lib.vp3d_set_pair_mode(2), 'pair')
+        native.check(lib.vp3d_set_sched_mode(sched), 'sched')
+        try:
+            ops.conv_block(dt, a, (seqs, rows, c, c, rows * c), w, 1, 0, c, rows, out, (n, rows * n), **kw)
+            torch.cuda.synchronize()
+        finally:
+            native.check(lib.vp3d_set_pair_mode(1), 'pair')
+            native.check(lib.vp3d_set_sched_mode(0), 'sched')
+        return out
+
+    for seqs, rows, c, n in [(1, 100, 64, 256), (3, 700, 256, 1024), (1, 40000, 128, 1024), (7, 1111, 192, 512)]:
+        for kind in ('res', 'side_add', 'dgrad'):
+            ref = run(0, seqs, rows, c, n, kind)
+            dyn = run(2, seqs, rows, c, n, kind)
+            assert torch.isfinite(dyn.float()).all(), (seqs, rows, c, n, kind)
+            assert torch.equal(ref, dyn), (seqs, rows, c, n, kind)
+
+
+def test_weight_gradient_with_dynamic_items_matches_static():
+    """vp3d_wgrad with the dynamic item schedule (one CTA per item, stolen through cluster launch control, finer row
+    slices) against the static persistent schedule: the same sum in a different fp32 order."""
+    dt, td = native.F16, torch.float16
+    g = torch.Generator().manual_seed(29)
+    lib = native.lib()
+    for seqs, rows, co, ci, taps, step in [(1, 5000, 1024, 1024, 1, 0), (6, 700, 1024, 1024, 3, 9), (1, 300, 128, 1024, 1, 0)]:
+        dz = (torch.randn(seqs, rows, co, generator=g) * 0.5).to(td).cuda()
+        a = (torch.randn(seqs, rows + step * (taps - 1), ci, generator=g) * 0.5).to(td).cuda()
+        outs = []
+        for mode in (0, 2):
+            native.check(lib.vp3d_set_sched_mode(mode), 'sched')
+            try:
+                packed = torch.zeros(taps, co, ci, device='cuda')
+                ops.wgrad(dt, dz, (seqs, rows, co, rows * co), a, (a.shape[1], ci, ci, a.shape[1] * ci), co, ci, taps,
+                          packed, b_tap_row_step=step, block_n=256)
+                torch.cuda.synchronize()
+            finally:
+                native.check(lib.vp3d_set_sched_mode(0), 'sched')
+            outs.append(packed)
+        ref = torch.stack([torch.einsum('srk,src->kc', dz.double(), a[:, t * step:t * step + rows].double())
+                           for t in range(taps)])
+        assert rel_err(outs[0], ref) < 2e-6 and rel_err(outs[1], ref) < 2e-6
+        assert rel_err(outs[1], outs[0]) < 2e-6
