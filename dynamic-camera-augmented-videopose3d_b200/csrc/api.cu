@@ -781,6 +781,8 @@ int vp3d_wgrad(const vp3d_wgrad_args* a, void* stream) {
     }
     p.num_slices = best_s;
   }
+  p.valid_co = (int)(a->dz_cols > 0 ? a->dz_cols : a->co_pad);
+  p.valid_ci = (int)(a->a_cols < a->ci_pad && a->b_tap_col_step == 0 ? a->a_cols : a->ci_pad);
   p.b_row_off = (int)a->b_row_off;
   p.b_tap_row_step = a->b_tap_row_step;
   p.b_tap_col_step = (int)a->b_tap_col_step;

@@ -392,8 +392,9 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
 
-#pragma unroll 1
-      for (int c = half * kChunks; c < (half + 1) * kChunks; ++c) {
+#pragma unroll
+      for (int cq = 0; cq < kChunks; ++cq) {
+        const int c = half * kChunks + cq;
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + acc * kBN + c * 32 + (static_cast<uint32_t>(quad * 32) << 16), v);
         if (c + 2 < (half + 1) * kChunks) res_load(c + 2, rnext2);

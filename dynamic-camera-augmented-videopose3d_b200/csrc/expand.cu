@@ -67,14 +67,22 @@ expand_bn_stats_kernel(const float* __restrict__ G, const void* __restrict__ w, 
                        float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ nbt,
                        float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                        float* __restrict__ invstd_out, float* __restrict__ wg, int c, int tick_inline) {
-  __shared__ float ws[kExCh][256];
+  // weights of the block's 8 channels, [column][channel]: the inner loop below reads one column's 8 weights as two
+  // broadcast LDS.128 (a [channel][column] layout needs 8 scalar LDS per column, and the kernel was bound by the LSU's
+  // instruction rate: 30 us)
+  __shared__ __align__(16) float ws[256][kExCh];
   __shared__ float red[kExCh][8];
+  static_assert(kExCh == 8, "two float4 per column");
   const int k = threadIdx.x;
   const int c0 = blockIdx.x * kExCh;
   if (momentum < 0.f) momentum = 1.f / (float)((nbt != nullptr ? *nbt : 0) + 1);   // cumulative average (momentum=None)
   if (tick_inline && blockIdx.x == 0 && k == 0 && nbt != nullptr) *nbt += 1;       // nobody reads the count in this mode
+  float wk[kExCh];                                  // this thread's column of the 8 weight rows
 #pragma unroll
-  for (int cc = 0; cc < kExCh; ++cc) ws[cc][k] = (k < k_total && c0 + cc < c) ? load_w<DT>(w, (long long)(c0 + cc) * k_total + k) : 0.f;
+  for (int cc = 0; cc < kExCh; ++cc) {
+    wk[cc] = (k < k_total && c0 + cc < c) ? load_w<DT>(w, (long long)(c0 + cc) * k_total + k) : 0.f;
+    ws[k][cc] = wk[cc];
+  }
   __syncthreads();
   const float n = G[ones_col * 256 + ones_col];
   const float inv_n = 1.f / n;
@@ -88,20 +96,28 @@ expand_bn_stats_kernel(const float* __restrict__ G, const void* __restrict__ w, 
 #pragma unroll 16
   for (int j = 0; j < k_total; ++j) {
     const float g = __ldg(G + j * 256 + k);
-#pragma unroll
-    for (int cc = 0; cc < kExCh; ++cc) t[cc] = fmaf(g, ws[cc][j], t[cc]);
+    const float4 w0 = *reinterpret_cast<const float4*>(&ws[j][0]);
+    const float4 w1 = *reinterpret_cast<const float4*>(&ws[j][4]);
+    t[0] = fmaf(g, w0.x, t[0]);
+    t[1] = fmaf(g, w0.y, t[1]);
+    t[2] = fmaf(g, w0.z, t[2]);
+    t[3] = fmaf(g, w0.w, t[3]);
+    t[4] = fmaf(g, w1.x, t[4]);
+    t[5] = fmaf(g, w1.y, t[5]);
+    t[6] = fmaf(g, w1.z, t[6]);
+    t[7] = fmaf(g, w1.w, t[7]);
   }
 #pragma unroll
   for (int cc = 0; cc < kExCh; ++cc) {
     wg[(long long)(c0 + cc) * 256 + k] = t[cc];
-    dot_s[cc] = ws[cc][k] * s_k;                    // -> w . s
+    dot_s[cc] = wk[cc] * s_k;                       // -> w . s
   }
   block_sum(dot_s, red);
   // centred quadratic form: var = (1/n) sum_k w_k (t_k - s_k (w . s) / n)  -- the subtraction happens per column, before
   // the sum, so the cancellation of E[z^2] - E[z]^2 is spread over K small terms
   float q[kExCh];
 #pragma unroll
-  for (int cc = 0; cc < kExCh; ++cc) q[cc] = ws[cc][k] * (t[cc] - s_k * dot_s[cc] * inv_n);
+  for (int cc = 0; cc < kExCh; ++cc) q[cc] = wk[cc] * (t[cc] - s_k * dot_s[cc] * inv_n);
   block_sum(q, red);
   if (k < kExCh) {
     const int ch = c0 + k;

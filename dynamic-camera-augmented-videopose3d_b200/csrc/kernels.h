@@ -119,6 +119,7 @@ struct WgradParams {
   int b_row_off;        // input row read against gradient row 0 by tap 0
   int b_tap_row_step;   // extra input rows per tap (dilation)
   int b_tap_col_step;   // extra input columns per tap (stride == width layers on the reshaped view)
+  int valid_co, valid_ci;   // real output rows / columns of a tile grid that was padded to the tile size
   int dyn_sched;        // 1: grid = one CTA per item, running CTAs steal the items of CTAs not yet launched (wgrad.cu)
   float* out;           // packed fp32 [taps][co_pad][ci_pad]
   long long out_tap_stride;

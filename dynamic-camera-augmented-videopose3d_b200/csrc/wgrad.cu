@@ -275,8 +275,12 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int h = 0; h < kMH; ++h) {
         float* out_row = p.out + (long long)tap * p.out_tap_stride +
                          (long long)(co0 * BM + h * 128 + row) * p.out_row_stride + (long long)ci_t * BN;
+        // rows / 32-column chunks that lie entirely in the padding of a narrow operand (valid_co / valid_ci) hold exact
+        // zeros: their reductions are skipped (the Gram GEMM of the expand layer: 192 of 256 in both directions)
+        if (co0 * BM + h * 128 + (row & ~31) >= p.valid_co) continue;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
+          if (ci_t * BN + c * 32 >= p.valid_ci) break;
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_base + acc * Cfg::kAccCols + h * BN + c * 32 + (static_cast<uint32_t>(quad * 32) << 16),
                              v);

@@ -135,6 +135,9 @@ def test_train_eval_checkpoint_resume_like_run_py(tmp_path):
         assert abs(resumed_evals[e] - full_evals[e]) < 5e-3 * full_evals[e]
     for (k, a), (_, b) in zip(m_full.state_dict().items(), m_res.state_dict().items()):
         if a.dtype.is_floating_point:
-            assert (a - b).abs().max().item() <= 2e-2 * max(a.abs().max().item(), 1e-3), k
+            # in norm, not element by element: where a gradient is ~0 Adam's update is +-lr whatever its size, so the
+            # order of the fp32 atomics moves single weights by a few lr (1e-3) between two runs
+            assert (a - b).norm().item() <= 2e-2 * max(a.norm().item(), 1e-3), k
+            assert (a - b).abs().max().item() <= 8 * LR + 2e-2 * a.abs().max().item(), k
         else:
             assert int(a) == int(b), k
