@@ -364,7 +364,8 @@ def bench_train(args, rank, world, dev, steps, warm):
     sync_compress = None
     if world > 1:
         ddp.broadcast_parameters(model)
-        sync = ddp.enable_grad_sync()
+        sync = ddp.enable_grad_sync(exchange=None if args.exchange == 'auto' else args.exchange,
+                                    params=list(model.parameters()))
         sync_compress = sync.compress
 
     Wh, qh, th, camh = [v.pin_memory() for v in synthetic_training_batch(rank, batch)]
@@ -610,9 +611,10 @@ def bench_train(args, rank, world, dev, steps, warm):
                                'per-frame camera projection (H36M cam-0 distortion) -> fwd -> mpjpe -> bwd -> Adam '
                                'amsgrad (BASELINE configs[2])' % batch,
                    'optimizer': args.optimizer,
-                   'grad_exchange': 'none (1 GPU)' if world == 1 else 'NCCL all-reduce (avg) of %s gradients, large '
-                                    'tensors overlapped with backward, %d collectives, %.1f MB on the wire per step'
-                                    % ('fp32 (sent as bf16, written back as fp32)' if sync_compress else 'fp32',
+                   'grad_exchange': 'none (1 GPU)' if world == 1 else '%s (avg) of %s gradients, large '
+                                    'tensors overlapped with backward, %d collectives, %.1f MB reduced per step'
+                                    % (exchange_name(sync),
+                                       'fp32 (sent as bf16, written back as fp32)' if sync_compress else 'fp32',
                                        coll_per_step[0], coll_per_step[1] / 1e6),
                    'bn': 'per-replica batch statistics',
                    'launch': 'one CUDA graph per step (vp3d_b200.graphs.GraphedTrainStep)' if use_graph else 'eager'},
@@ -651,6 +653,15 @@ def bench_train(args, rank, world, dev, steps, warm):
         'mpjpe_ms_per_step': mpjpe_ms,
         'multi_gpu': multi,
     }
+
+
+def exchange_name(sync):
+    from vp3d_b200 import ddp
+    if isinstance(sync, ddp.PeerGradSync):
+        return ('vp3d_peer_allreduce_f32 (own kernel, %d CTAs beside GEMM grids %d SMs smaller; %s)'
+                % (sync.ctas, sync.reserve, 'NVSwitch multicast: multimem.ld_reduce / multimem.st' if sync.multicast
+                   else 'peer loads / stores over NVLink'))
+    return 'NCCL all-reduce'
 
 
 def bench_train_multi(args, rank, world, dev, model, opt, loss_fn, steps, world_to_image, use_graph):
@@ -798,7 +809,8 @@ def bench_c4(args, rank, world, dev, steps, warm):
     sync = None
     if world > 1:
         ddp.broadcast_parameters(model)
-        sync = ddp.enable_grad_sync()
+        sync = ddp.enable_grad_sync(exchange=None if args.exchange == 'auto' else args.exchange,
+                                    params=list(model.parameters()))
     W, q, t, cam = [v.to(dev) for v in synthetic_training_batch(100 + rank, batch, J=J)]
     mid = RF // 2
     with torch.no_grad():
@@ -952,6 +964,8 @@ def main():
     ap.add_argument('--batch', type=int, default=TRAIN_BATCH, help='training samples per GPU per step')
     ap.add_argument('--optimizer', default='fused', choices=['fused', 'torch'],
                     help='training: vp3d_b200.optim.FusedAdam (default) or stock torch.optim.Adam')
+    ap.add_argument('--exchange', default='auto', choices=['auto', 'nccl', 'peer'],
+                    help='N > 1 training: gradient exchange (auto: own peer-memory kernel when symmetric memory is available)')
     ap.add_argument('--no-graph', action='store_true', help='training: launch kernels eagerly instead of one CUDA graph')
     ap.add_argument('--c4-batch', type=int, default=8192, help='configs[4] (J=31 pose + trajectory) samples per GPU per step')
     ap.add_argument('--no-parity', action='store_true', help='skip the oracle comparison of the measured sizes (outside the timed regions)')

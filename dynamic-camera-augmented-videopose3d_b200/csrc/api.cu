@@ -1064,4 +1064,38 @@ int vp3d_adam_step_multi(const vp3d_adam_args* args, int count, void* stream) {
   return VP3D_OK;
 }
 
+int vp3d_peer_allreduce_f32(const vp3d_allreduce_args* a, void* stream) {
+  if (a == nullptr || a->peers == nullptr || a->flags == nullptr) return fail(VP3D_ERR_INVALID, "peer_allreduce: null arguments");
+  if (a->world < 1 || a->world > vp3d::kArMaxRanks || a->rank < 0 || a->rank >= a->world)
+    return fail(VP3D_ERR_INVALID, "peer_allreduce: rank %d of %d (at most %d ranks)", a->rank, a->world, vp3d::kArMaxRanks);
+  if (a->ctas < 2 || a->ctas > vp3d::kArMaxCtas || a->ctas % 2 != 0)
+    return fail(VP3D_ERR_INVALID, "peer_allreduce: ctas must be even, 2..%d", vp3d::kArMaxCtas);
+  if (a->offset < 0 || a->count < 0 || a->offset % 4 != 0 || a->count % 4 != 0)
+    return fail(VP3D_ERR_INVALID, "peer_allreduce: offset / count must be non-negative multiples of 4 floats");
+  if (a->count == 0) return VP3D_OK;
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  vp3d::AllReduceParams p;
+  memset(&p, 0, sizeof(p));
+  p.mc = static_cast<float*>(a->multicast);
+  for (int k = 0; k < a->world; ++k) {
+    if (a->peers[k] == nullptr || a->flags[k] == nullptr) return fail(VP3D_ERR_INVALID, "peer_allreduce: null mapping of rank %d", k);
+    if ((reinterpret_cast<uintptr_t>(a->peers[k]) & 15) != 0) return fail(VP3D_ERR_INVALID, "peer_allreduce: buffers must be 16-byte aligned");
+    p.peers[k] = static_cast<float*>(a->peers[k]);
+    p.flags[k] = static_cast<uint32_t*>(a->flags[k]);
+  }
+  if ((reinterpret_cast<uintptr_t>(a->multicast) & 15) != 0) return fail(VP3D_ERR_INVALID, "peer_allreduce: multicast address must be 16-byte aligned");
+  p.rank = a->rank;
+  p.world = a->world;
+  p.off = a->offset;
+  p.n = a->count;
+  p.scale = a->scale;
+  const double t = a->timeout_s > 0 ? a->timeout_s : 10.0;
+  p.timeout_ns = static_cast<unsigned long long>(t * 1e9);
+  cudaError_t e = vp3d::launch_peer_allreduce(p, a->ctas, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "peer_allreduce launch");
+  return VP3D_OK;
+}
+
+
 }  // extern "C"

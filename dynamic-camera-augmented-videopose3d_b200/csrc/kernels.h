@@ -198,4 +198,18 @@ cudaError_t launch_grad_scale(const float* dy, long long n, float* gscale_buf, i
 cudaError_t launch_grad_pack_rows(int dtype, const float* src, void* dst, long long rows, int c, int c_pad,
                                   const float* gscale_buf, float* col_sum, int sm_count, cudaStream_t stream);
 
+// Peer-memory gradient exchange (allreduce.cu). Pointer tables by value: at most kArMaxRanks ranks of one NVLink domain.
+constexpr int kArMaxRanks = 16;
+constexpr int kArMaxCtas = 64;
+struct AllReduceParams {
+  float* mc;                      // multicast mapping of the exchange buffer, or nullptr (plain peer loads / stores)
+  float* peers[kArMaxRanks];      // this process's mapping of every rank's exchange buffer
+  uint32_t* flags[kArMaxRanks];   // ... of every rank's flag words [ctas][world]
+  int rank, world;
+  long long off, n;               // fp32 elements, multiples of 4
+  float scale;
+  unsigned long long timeout_ns;
+};
+cudaError_t launch_peer_allreduce(const AllReduceParams& p, int ctas, cudaStream_t stream);
+
 }  // namespace vp3d

@@ -89,11 +89,137 @@ class GradSync:
         self._pending, self._small = [], []
 
 
+class PeerGradSync:
+    """Gradient averaging through NVLink / NVSwitch peer memory with the library's own kernel
+    (vp3d_peer_allreduce_f32, csrc/allreduce.cu) instead of NCCL.
+
+    All parameter gradients of a replica live in ONE symmetric fp32 buffer (torch.distributed._symmetric_memory: CUDA
+    VMM allocations every rank of the node maps, plus the NVSwitch multicast address when the fabric has one). The
+    backward writes each gradient straight into its slot (training.grad_alloc); the moment a large gradient has been
+    issued its slot is all-reduced in place on a communication stream by a kernel of `ctas` CTAs with no shared memory
+    -- two-shot over multimem.ld_reduce / multimem.st, or plain peer loads / stores without multicast -- while the
+    persistent GEMMs of the earlier layers run on grids sized `ctas` SMs smaller (vp3d_set_sm_limit for the duration of
+    the backward). The small tensors (BatchNorm affine, shrink layer) are adjacent in the buffer and travel as one
+    slice at the end. Everything is a kernel launch on a stream: the step stays capturable as one CUDA graph.
+    One rank computes each element and all ranks receive the same bits, so replicas stay bit-identical."""
+
+    FLAG_FLOATS = 64 * 16          # kArMaxCtas x kArMaxRanks flag words at the start of every rank's buffer
+    ALIGN = 32                     # slots start on 128-byte boundaries
+
+    def __init__(self, params, group=None, ctas=None, reserve_sms=None, use_multicast=None, timeout_s=20.0):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from . import native
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.compress = None
+        params = [p for p in params if p.requires_grad]
+        assert params and all(p.is_cuda and p.dtype == torch.float32 for p in params), 'fp32 CUDA parameters'
+        dev = params[0].device
+        self.ctas = int(ctas if ctas is not None else os.environ.get('VP3D_DDP_CTAS', 8))
+        assert 2 <= self.ctas <= 64 and self.ctas % 2 == 0
+        self.reserve = int(reserve_sms if reserve_sms is not None else os.environ.get('VP3D_DDP_RESERVE', self.ctas))
+        up = lambda n: (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.slots = {}
+        off = self.FLAG_FLOATS
+        large = [p for p in params if p.numel() * 4 >= LARGE_BYTES]
+        small = [p for p in params if p.numel() * 4 < LARGE_BYTES]
+        for p in large:
+            self.slots[id(p)] = (off, p.numel())
+            off += up(p.numel())
+        self.small_range = (off, 0)
+        for p in small:
+            self.slots[id(p)] = (off, p.numel())
+            off += up(p.numel())
+        self.small_range = (self.small_range[0], off - self.small_range[0])
+        self.large_ids = {id(p) for p in large}
+        self.total = off
+        with torch.cuda.device(dev):
+            self.buf = symm.empty(self.total, dtype=torch.float32, device=dev)
+            self.handle = symm.rendezvous(self.buf, self.group.group_name)
+            self.buf.zero_()
+            torch.cuda.synchronize()
+        dist.barrier(self.group)
+        base_off = int(getattr(self.handle, 'offset', 0) or 0)
+        ptrs = [int(a) + base_off for a in self.handle.buffer_ptrs]
+        assert ptrs[self.rank] == self.buf.data_ptr(), 'symmetric buffer of this rank is not the tensor rendezvous()ed'
+        self._peers = (C.c_void_p * self.world)(*ptrs)
+        mc = int(getattr(self.handle, 'multicast_ptr', 0) or 0)
+        if use_multicast is None:
+            use_multicast = os.environ.get('VP3D_DDP_MULTICAST', '1') != '0'
+        self.multicast = (mc + base_off) if (mc and use_multicast) else None
+        self.timeout_s = float(timeout_s)
+        self.comm = torch.cuda.Stream(dev)
+        self._native = native
+        self._dev = dev
+        self.bytes_reduced = 0
+        self.collectives = 0
+
+    # -- training hooks ------------------------------------------------------------------------------------------
+    def alloc(self, param):
+        s = self.slots.get(id(param))
+        if s is None:
+            return None
+        slot = self.buf[s[0]:s[0] + s[1]]
+        if param.grad is not None and param.grad.data_ptr() == slot.data_ptr():
+            # the previous step's gradient is still attached and lives in this slot (zero_grad(set_to_none=False),
+            # gradient accumulation): move it out, autograd is going to add this step's gradient to it
+            param.grad = param.grad.clone()
+        return slot
+
+    def begin(self):
+        if self.reserve > 0:
+            sms = torch.cuda.get_device_properties(self._dev).multi_processor_count
+            self._native.check(self._native.lib().vp3d_set_sm_limit(int(sms - self.reserve)), 'set_sm_limit')
+
+    def _exchange(self, off, n):
+        """All-reduce of buf[off : off + n) on the communication stream, after everything issued so far on the current one."""
+        cur = torch.cuda.current_stream(self._dev)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        n4 = (n + 3) // 4 * 4
+        a = self._native.AllReduceArgs()
+        a.multicast = self.multicast
+        a.peers = self._peers
+        a.flags = self._peers                 # the flag words are the head of every buffer
+        a.rank, a.world, a.offset, a.count = self.rank, self.world, off, n4
+        a.scale, a.ctas, a.timeout_s = 1.0 / self.world, self.ctas, self.timeout_s
+        import ctypes as C
+        with torch.cuda.device(self._dev):
+            self.comm.wait_event(ev)
+            self._native.check(self._native.lib().vp3d_peer_allreduce_f32(C.byref(a), self.comm.cuda_stream),
+                               'peer_allreduce')
+        self.bytes_reduced += n4 * 4
+        self.collectives += 1
+
+    def __call__(self, param, grad):
+        s = self.slots.get(id(param))
+        if s is None:
+            raise RuntimeError('vp3d_b200.ddp: gradient of a parameter that was not registered with PeerGradSync')
+        off, n = s
+        slot = self.buf[off:off + n]
+        if grad.data_ptr() != slot.data_ptr():
+            slot.copy_(grad.reshape(-1))       # a producer that did not take the slot (generic path): one copy
+        if id(param) in self.large_ids:
+            self._exchange(off, n)
+
+    def finish(self):
+        self._exchange(*self.small_range)
+        torch.cuda.current_stream(self._dev).wait_stream(self.comm)
+        if self.reserve > 0:
+            self._native.check(self._native.lib().vp3d_set_sm_limit(0), 'set_sm_limit')
+        return None
+
+
 _active = None
 
 
-def enable_grad_sync(group=None, reserve_sms=0, dynamic_schedule=None, compress=None):
+def enable_grad_sync(group=None, reserve_sms=0, dynamic_schedule=None, compress=None, exchange=None, params=None):
     """Install gradient averaging for every vp3d_b200 training backward of this process. Returns the GradSync.
+    `exchange`: 'nccl' = dist.all_reduce per gradient (GradSync); 'peer' = the library's own all-reduce kernel over
+    NVLink peer memory (PeerGradSync; needs `params`, CUDA, one node); default: env VP3D_DDP_EXCHANGE, else 'peer' when
+    `params` are given and symmetric memory can be set up, else 'nccl'.
     `dynamic_schedule` (default off; env VP3D_DDP_SCHED=dynamic turns it on): the big GEMMs of the backward take their
     tiles dynamically (cluster launch control, vp3d_set_sched_mode) instead of walking a static persistent schedule, so
     SMs that NCCL's all-reduce CTAs occupy only shrink the pool of workers instead of leaving a fixed share of the tiles
@@ -104,6 +230,29 @@ def enable_grad_sync(group=None, reserve_sms=0, dynamic_schedule=None, compress=
     all-reduce CTAs (cap them with NCCL_MAX_CTAS <= reserve_sms before the process group is created) run beside the
     backward GEMMs instead of taking turns with them."""
     global _active
+    if exchange is None:
+        exchange = 'nccl' if params is None else (os.environ.get('VP3D_DDP_EXCHANGE') or 'peer')
+    assert exchange in ('nccl', 'peer')
+    world = dist.get_world_size(group)
+    if exchange == 'peer' and world > 1 and torch.cuda.is_available() and dist.get_backend(group) == 'nccl':
+        if params is None:
+            raise ValueError("enable_grad_sync(exchange='peer') needs params=model.parameters()")
+        try:
+            _active = PeerGradSync(list(params), group, reserve_sms=reserve_sms or None)
+        except Exception as e:          # no symmetric memory on this system (no P2P / fabric): NCCL carries the exchange
+            if os.environ.get('VP3D_DDP_EXCHANGE') == 'peer':
+                raise
+            import warnings
+            warnings.warn('vp3d_b200.ddp: peer-memory gradient exchange unavailable (%s); using NCCL' % (e,))
+            _active = None
+        if _active is not None:
+            from . import native
+            native.check(native.lib().vp3d_set_sched_mode(0), 'set_sched_mode')
+            training.grad_ready_hook = _active
+            training.grad_finish_hook = _active.finish
+            training.grad_begin_hook = _active.begin
+            training.grad_alloc = _active.alloc
+            return _active
     if reserve_sms > 0 and torch.cuda.is_available():
         from . import native
         sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
@@ -118,6 +267,8 @@ def enable_grad_sync(group=None, reserve_sms=0, dynamic_schedule=None, compress=
         native.check(native.lib().vp3d_set_sched_mode(1 if dynamic_schedule else 0), 'set_sched_mode')
     training.grad_ready_hook = _active
     training.grad_finish_hook = _active.finish
+    training.grad_begin_hook = None
+    training.grad_alloc = None
     return _active
 
 
@@ -130,6 +281,8 @@ def disable_grad_sync():
         native.check(native.lib().vp3d_set_sched_mode(0), 'set_sched_mode')
     training.grad_ready_hook = None
     training.grad_finish_hook = None
+    training.grad_begin_hook = None
+    training.grad_alloc = None
 
 
 def enable_sync_bn(group=None, on=True):

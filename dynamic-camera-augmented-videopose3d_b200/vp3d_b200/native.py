@@ -80,6 +80,13 @@ class AdamArgs(C.Structure):
                 ('packed', C.c_void_p), ('dtype', C.c_int), ('c_in', C.c_int), ('taps', C.c_int), ('k_pad', C.c_int)]
 
 
+class AllReduceArgs(C.Structure):
+    """struct vp3d_allreduce_args (include/vp3d_b200.h)"""
+    _fields_ = [('multicast', C.c_void_p), ('peers', C.POINTER(C.c_void_p)), ('flags', C.POINTER(C.c_void_p)),
+                ('rank', C.c_int), ('world', C.c_int), ('offset', C.c_longlong), ('count', C.c_longlong),
+                ('scale', C.c_float), ('ctas', C.c_int), ('timeout_s', C.c_double)]
+
+
 class Dropout(C.Structure):
     """struct vp3d_dropout (include/vp3d_b200.h)"""
     _fields_ = [('p', C.c_float), ('seed', C.c_ulonglong), ('stream', C.c_ulonglong), ('step_counter', C.c_void_p)]
@@ -148,6 +155,7 @@ _SIGNATURES = {
                                   C.c_void_p]),
     'vp3d_adam_step': (C.c_int, [C.POINTER(AdamArgs), C.c_void_p]),
     'vp3d_adam_step_multi': (C.c_int, [C.POINTER(AdamArgs), C.c_int, C.c_void_p]),
+    'vp3d_peer_allreduce_f32': (C.c_int, [C.POINTER(AllReduceArgs), C.c_void_p]),
     'vp3d_counter_add': (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_void_p]),
     'vp3d_grad_scale': (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     'vp3d_grad_pack_rows': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p,

@@ -4,6 +4,7 @@ PyTorch is plumbing here (device memory from the caching allocator, the current 
 bookkeeping); every arithmetic operation on the hot path runs in libvp3d_b200.so.
 """
 import ctypes as C
+import math
 
 import torch
 
@@ -415,9 +416,18 @@ def wgrad(dt, dz, dz_view, a, a_view, co_pad, ci_pad, taps, dw_packed, b_row_off
     return dw_packed
 
 
-def wgrad_finish(dw_packed, c_out, c_in, taps, co_pad, ci_pad, gscale_buf, tap_stride=None, row_stride=None):
+def _grad_out(out, shape, device):
+    """`out` (a caller-owned fp32 buffer of that many elements, e.g. a slot of the data-parallel exchange buffer) viewed
+    as `shape`, or a fresh tensor."""
+    if out is None:
+        return torch.empty(shape, dtype=torch.float32, device=device)
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == math.prod(shape), (out.shape, shape)
+    return out.view(shape)
+
+
+def wgrad_finish(dw_packed, c_out, c_in, taps, co_pad, ci_pad, gscale_buf, tap_stride=None, row_stride=None, out=None):
     """packed [taps][co_pad][ci_pad] (or the strides given) -> nn.Conv1d layout (c_out, c_in, taps), un-scaled."""
-    dw = torch.empty((c_out, c_in, taps), dtype=torch.float32, device=dw_packed.device)
+    dw = _grad_out(out, (c_out, c_in, taps), dw_packed.device)
     tap_stride = co_pad * ci_pad if tap_stride is None else tap_stride
     row_stride = ci_pad if row_stride is None else row_stride
     with torch.cuda.device(dw.device):
@@ -516,11 +526,11 @@ def expand_bn_stats(dt, gram, w, k_total, ones_col, bn, c_pad, update_running=Tr
 
 
 def expand_bwd_finish(dt, p_packed, wg, gram, w, k_total, ones_col, scale, mean, invstd, gscale_buf, c, c_pad, c_in,
-                      c_in_pad, taps):
+                      c_in_pad, taps, out=(None, None, None)):
     """-> (dW (c, c_in, taps), d_gamma [c], d_beta [c]) of the expand layer (vp3d_expand_bwd_finish)."""
     dev = p_packed.device
-    dw = torch.empty((c, c_in, taps), dtype=torch.float32, device=dev)
-    dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
+    dw = _grad_out(out[0], (c, c_in, taps), dev)
+    dgb = (_grad_out(out[1], (c,), dev), _grad_out(out[2], (c,), dev))
     with torch.cuda.device(dev):
         check(lib().vp3d_expand_bwd_finish(dt, _ptr(p_packed), _ptr(wg), _ptr(gram), _ptr(w), int(k_total), int(ones_col),
                                            _ptr(scale), _ptr(mean), _ptr(invstd), _ptr(gscale_buf), c, c_pad, c_in,
@@ -563,7 +573,8 @@ def bn_finalize_act_fwd(dt, z, stat, count, bn, seqs, rows_per_seq, drop, res=No
     return a, out[0], out[1], out[2], out[3]
 
 
-def bn_act_bwd(dt, g, z, scale, shift, mean, invstd, rows, c, drop, gscale_buf, count=None, group=None, sums=None):
+def bn_act_bwd(dt, g, z, scale, shift, mean, invstd, rows, c, drop, gscale_buf, count=None, group=None, sums=None,
+               out=(None, None)):
     """-> (dz operand-typed [rows][c_pad], d_gamma [c], d_beta [c]). `count` (>= rows) is the number of rows the
     batch statistics were taken over; with `group` the per-channel sums are all-reduced first (SyncBN). The kernel
     then writes the GLOBAL sums as d_gamma / d_beta; they are divided by the group size here so that the gradient
@@ -574,7 +585,7 @@ def bn_act_bwd(dt, g, z, scale, shift, mean, invstd, rows, c, drop, gscale_buf, 
     if sums is None:     # [2][c_pad] doubles, zero on entry (callers with many layers pass slices of one arena)
         sums = torch.zeros((2, c_pad), dtype=torch.float64, device=dev)
     dz = torch.empty_like(z)
-    dgb = torch.empty((2, c), dtype=torch.float32, device=dev)
+    dgb = (_grad_out(out[0], (c,), dev), _grad_out(out[1], (c,), dev))
     with torch.cuda.device(dev):
         check(lib().vp3d_bn_act_bwd_reduce(dt, _ptr(g), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd),
                                            rows, c_pad, C.byref(drop), _ptr(sums[0]), _ptr(sums[1]), _stream()),
@@ -588,7 +599,7 @@ def bn_act_bwd(dt, g, z, scale, shift, mean, invstd, rows, c, drop, gscale_buf, 
               'bn_act_bwd_apply')
         if group is not None:
             import torch.distributed as dist
-            dgb.mul_(1.0 / dist.get_world_size(group))
+            torch._foreach_mul_(list(dgb), 1.0 / dist.get_world_size(group))
     return dz, dgb[0], dgb[1]
 
 
@@ -600,10 +611,13 @@ def grad_scale(dy):
     return buf
 
 
-def grad_pack_rows(dt, src, c_pad, gscale_buf, want_col_sum=False):
+def grad_pack_rows(dt, src, c_pad, gscale_buf, want_col_sum=False, col_sum_out=None):
     rows, c = src.shape
     dst = torch.empty((rows, c_pad), dtype=torch_dtype(dt), device=src.device)
-    col_sum = torch.zeros(c, dtype=torch.float32, device=src.device) if want_col_sum else None
+    col_sum = None
+    if want_col_sum:
+        col_sum = (torch.zeros(c, dtype=torch.float32, device=src.device) if col_sum_out is None
+                   else _grad_out(col_sum_out, (c,), src.device).zero_())
     with torch.cuda.device(src.device):
         check(lib().vp3d_grad_pack_rows(dt, _ptr(src), _ptr(dst), rows, c, c_pad, _ptr(gscale_buf), _ptr(col_sum),
                                         _stream()), 'grad_pack_rows')

@@ -22,7 +22,11 @@ from .temporal import K_ALIGN, N_TILE, LayerPlan, _round_up, _run_layer, resolve
 
 SHRINK_PAD = 128      # shrink-layer output channels are padded to one 128-row MMA tile for its weight gradient
 grad_ready_hook = None   # set by vp3d_b200.ddp: called as hook(parameter, gradient) as soon as a gradient is issued
-grad_finish_hook = None  # ... and once at the end of the backward (waits for the outstanding all-reduces)
+grad_finish_hook = None  # ... and once at the end of the backward (waits for the outstanding all-reduces); may return
+                         # {id(parameter): gradient} replacements for the tensors the backward hands to autograd
+grad_begin_hook = None   # ... and once at its start
+grad_alloc = None        # set by vp3d_b200.ddp (peer exchange): grad_alloc(parameter) -> flat fp32 buffer the gradient of
+                         # that parameter is to be written into (a slot of the exchange buffer), or None
 sync_bn_group = None     # process group over which train-mode BatchNorm statistics are summed (None: per replica)
 # vp3d_bn_finalize_act_fwd (statistics -> scale/shift inside the apply pass, one launch less per layer) is available but
 # off: same-box A/B at batch 1024 gave 2.01-2.03 ms per step with it against 1.97 without -- every block of the apply pass
@@ -255,9 +259,14 @@ class _ZeroArena:
         return out.view(dtype).view(shape)
 
 
+def _slot(param):
+    return grad_alloc(param) if grad_alloc is not None else None
+
+
 def _weight_grad(dt, L, dz, n, c_pad, gscale, keep=None, arena=None):
     dzv, av, row_step, col_step = _views(L, n, c_pad)
     c_out = L.conv.out_channels
+    out = _slot(L.conv.weight)
     zeros = (lambda shape: arena.take(shape)) if arena is not None else (
         lambda shape: torch.zeros(shape, dtype=torch.float32, device=dz.device))
     if L.stride > 1 and L.taps * L.c_in_pad <= 256:
@@ -267,14 +276,15 @@ def _weight_grad(dt, L, dz, n, c_pad, gscale, keep=None, arena=None):
         if keep is not None:
             keep.append(packed)
         ops.wgrad(dt, dz, dzv, L.a_in, av, c_pad, 256, 1, packed, block_n=256)
-        return ops.wgrad_finish(packed, c_out, L.c_in, L.taps, c_pad, 256, gscale, tap_stride=L.c_in_pad, row_stride=256)
+        return ops.wgrad_finish(packed, c_out, L.c_in, L.taps, c_pad, 256, gscale, tap_stride=L.c_in_pad, row_stride=256,
+                                out=out)
     block_n = 256 if L.c_in_pad % 256 == 0 else 64
     packed = zeros((L.taps, c_pad, L.c_in_pad))
     if keep is not None:
         keep.append(packed)
     ops.wgrad(dt, dz, dzv, L.a_in, av, c_pad, L.c_in_pad, L.taps, packed, b_tap_row_step=row_step,
               b_tap_col_step=col_step, block_n=block_n)
-    return ops.wgrad_finish(packed, c_out, L.c_in, L.taps, c_pad, L.c_in_pad, gscale)
+    return ops.wgrad_finish(packed, c_out, L.c_in, L.taps, c_pad, L.c_in_pad, gscale, out=out)
 
 
 def _data_grad(dt, L, dz, n, c_pad, fan_in=None, fan_rows=0, fan_off=0, fan_mul=1, gate=None):
@@ -349,6 +359,8 @@ class _StackTrainFn(torch.autograd.Function):
                                    'backward() before step(), as run.py:485-487 does.')
         hook = grad_ready_hook
         grads = {}
+        if grad_begin_hook is not None:
+            grad_begin_hook()
         # The weight gradient of layer L (tensor-core bound) depends only on dz_L and the saved input; the critical path
         # continues with dgrad_L -> BN/ReLU backward of layer L-1 (HBM bound). Issuing the wgrad GEMMs (+ their layout
         # pass, + the gradient all-reduce hook) on a second stream lets the two kinds of work share the SMs: the wgrad
@@ -388,7 +400,8 @@ class _StackTrainFn(torch.autograd.Function):
         n_out = model.shrink.out_channels
         dy2 = ops.f32c(dy).reshape(n * ctx.t_last, n_out)
         gscale = ops.grad_scale(dy2)
-        dzs, dbias = ops.grad_pack_rows(dt, dy2, SHRINK_PAD, gscale, want_col_sum=True)
+        dzs, dbias = ops.grad_pack_rows(dt, dy2, SHRINK_PAD, gscale, want_col_sum=True,
+                                        col_sum_out=_slot(model.shrink.bias))
         done(model.shrink.bias, dbias)
         rows = n * ctx.t_last
 
@@ -398,7 +411,8 @@ class _StackTrainFn(torch.autograd.Function):
                       SHRINK_PAD, c_pad, 1, packed)
             keep.append(packed)
             done(model.shrink.weight,
-                 ops.wgrad_finish(packed, n_out, model.shrink.in_channels, 1, SHRINK_PAD, c_pad, gscale))
+                 ops.wgrad_finish(packed, n_out, model.shrink.in_channels, 1, SHRINK_PAD, c_pad, gscale,
+                                  out=_slot(model.shrink.weight)))
         on_side(shrink_wgrad, dzs, gscale)
         g = torch.empty((n, ctx.t_last, c_pad), dtype=dzs.dtype, device=dy.device)
         k_shrink = ctx.w_shrink.shape[0]      # forward-packed [n_out_pad][c_pad], read as W^T
@@ -421,14 +435,17 @@ class _StackTrainFn(torch.autograd.Function):
                               block_n=256)
                     dw, dgamma, dbeta = ops.expand_bwd_finish(dt, p_packed, F['wg'], F['gram'], L.w_fwd, F['k_total'],
                                                               F['ones_col'], L.scale, L.mean, L.invstd, gscale,
-                                                              L.bn.num_features, c_pad, L.c_in, L.c_in_pad, L.taps)
+                                                              L.bn.num_features, c_pad, L.c_in, L.c_in_pad, L.taps,
+                                                              out=(_slot(L.conv.weight), _slot(L.bn.weight),
+                                                                   _slot(L.bn.bias)))
                     done(L.bn.weight, dgamma)
                     done(L.bn.bias, dbeta)
                     done(L.conv.weight, dw)
                 on_side(expand_grads, g)
                 break
             dz, dgamma, dbeta = ops.bn_act_bwd(dt, g, L.z, L.scale, L.shift, L.mean, L.invstd, rows, L.bn.num_features,
-                                               L.drop, gscale, count=L.count, group=sync_bn_group, sums=sums_all[idx])
+                                               L.drop, gscale, count=L.count, group=sync_bn_group, sums=sums_all[idx],
+                                               out=(_slot(L.bn.weight), _slot(L.bn.bias)))
             done(L.bn.weight, dgamma)
             done(L.bn.bias, dbeta)
             on_side(lambda L=L, dz=dz: done(L.conv.weight, _weight_grad(dt, L, dz, n, c_pad, gscale, keep, arena)), dz)
@@ -448,7 +465,7 @@ class _StackTrainFn(torch.autograd.Function):
         if side is not None:
             main.wait_stream(side)
         if grad_finish_hook is not None:
-            grad_finish_hook()
+            grads.update(grad_finish_hook() or {})
         keep.clear()
         out = [grads.get(id(p)) for p in ctx.params]
         ctx.layers = ctx.a_last = None

@@ -448,6 +448,29 @@ int vp3d_adam_step(const vp3d_adam_args* args, void* stream);
  * tensor (torch keeps one step counter per parameter, run.py:436-445 restores them from checkpoints). */
 int vp3d_adam_step_multi(const vp3d_adam_args* args, int count, void* stream);
 
+/* Gradient exchange of data-parallel training through NVLink / NVSwitch peer memory (no reference counterpart: the
+ * reference trains in one process, run.py:473-487). In-place sum x scale of the fp32 slice
+ * [offset, offset + count) of an exchange buffer that every rank of the NVLink domain has mapped: a two-shot all-reduce
+ * in ONE kernel of `ctas` CTAs (rank barrier -> every rank reduces its 1 / world share and writes it to all replicas ->
+ * rank barrier). `multicast` != NULL: the share is reduced by the switch (multimem.ld_reduce) and broadcast by it
+ * (multimem.st); NULL: plain peer loads / stores through `peers`. One rank computes each element, every rank receives
+ * the same bits. Every rank must issue the same sequence of calls (offset, count, ctas); calls on one stream are ordered.
+ *   peers[k] / flags[k]  THIS process's mapping of rank k's exchange buffer / flag words (HOST arrays of `world` device
+ *                        pointers, read during the call). Flag words: uint32 [ctas][world] per rank, zero before the
+ *                        first call, touched by nothing else; consecutive calls and graph replays reuse them.
+ *   timeout_s            a rank that does not arrive within this time traps the kernel (<= 0: 10 s). */
+typedef struct vp3d_allreduce_args {
+  void* multicast;
+  void* const* peers;
+  void* const* flags;
+  int rank, world;
+  long long offset, count;   /* fp32 elements, multiples of 4; the buffers 16-byte aligned */
+  float scale;               /* 1 / world for the gradient average */
+  int ctas;                  /* even (clusters of two CTAs), 2..64 */
+  double timeout_s;
+} vp3d_allreduce_args;
+int vp3d_peer_allreduce_f32(const vp3d_allreduce_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
