@@ -358,6 +358,8 @@ def bench_train(args, rank, world, dev, steps, warm):
     if args.optimizer == 'fused':
         from vp3d_b200.optim import FusedAdam                                # Adam(amsgrad) + operand re-pack, one pass
         opt = FusedAdam(model.parameters(), lr=1e-3, amsgrad=True)
+        if not args.no_update_in_backward:
+            opt.update_in_backward()      # Adam of a layer beside the weight-gradient GEMMs of the layers below it
     else:
         opt = torch.optim.Adam(model.parameters(), lr=1e-3, amsgrad=True, capturable=use_graph)   # run.py:662
     sync = None
@@ -592,6 +594,9 @@ def bench_train(args, rank, world, dev, steps, warm):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, ms_e2e, gemm_ms, proj_ms = [float(v) for v in tt.tolist()]
         ddp.disable_grad_sync()
+    early_update = args.optimizer == 'fused' and not args.no_update_in_backward
+    if early_update:
+        opt.update_in_backward(False)
     if rank != 0:
         return None
     parity = None
@@ -610,7 +615,8 @@ def bench_train(args, rank, world, dev, steps, warm):
         'config': {'workload': 'TemporalModelOptimized1f 3,3,3,3,3 training step, batch %d per GPU, dropout 0.25, '
                                'per-frame camera projection (H36M cam-0 distortion) -> fwd -> mpjpe -> bwd -> Adam '
                                'amsgrad (BASELINE configs[2])' % batch,
-                   'optimizer': args.optimizer,
+                   'optimizer': args.optimizer + (' (FusedAdam.update_in_backward: each layer updated inside the backward, '
+                                                  'beside the weight-gradient GEMMs of the layers below)' if early_update else ''),
                    'grad_exchange': 'none (1 GPU)' if world == 1 else '%s (avg) of %s gradients, large '
                                     'tensors overlapped with backward, %d collectives, %.1f MB reduced per step'
                                     % (exchange_name(sync),
@@ -806,6 +812,8 @@ def bench_c4(args, rank, world, dev, steps, warm):
     for m in (model.pose, model.traj):
         m.operand_dtype = args.dtype if args.dtype != 'tf32' else 'fp16'
     opt = FusedAdam(model.parameters(), lr=1e-3, amsgrad=True)
+    if not args.no_update_in_backward:
+        opt.update_in_backward()
     sync = None
     if world > 1:
         ddp.broadcast_parameters(model)
@@ -873,6 +881,7 @@ def bench_c4(args, rank, world, dev, steps, warm):
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         in_sync = bool(lo.item() == hi.item())
         ddp.disable_grad_sync()
+    opt.update_in_backward(False)
     peak_mem = torch.cuda.max_memory_allocated(dev)
     if rank != 0:
         return None
@@ -966,6 +975,8 @@ def main():
                     help='training: vp3d_b200.optim.FusedAdam (default) or stock torch.optim.Adam')
     ap.add_argument('--exchange', default='auto', choices=['auto', 'nccl', 'peer'],
                     help='N > 1 training: gradient exchange (auto: own peer-memory kernel when symmetric memory is available)')
+    ap.add_argument('--no-update-in-backward', action='store_true',
+                    help='training: FusedAdam.step() does the whole update after the backward (default: per layer inside it)')
     ap.add_argument('--no-graph', action='store_true', help='training: launch kernels eagerly instead of one CUDA graph')
     ap.add_argument('--c4-batch', type=int, default=8192, help='configs[4] (J=31 pose + trajectory) samples per GPU per step')
     ap.add_argument('--no-parity', action='store_true', help='skip the oracle comparison of the measured sizes (outside the timed regions)')

@@ -18,6 +18,7 @@
 // (DESIGN.md section 5). One rank computes each element and every rank receives the same bits, so replicas stay
 // bit-identical.
 #include "kernels.h"
+#include "pdl.cuh"
 #include "ptx.cuh"
 
 namespace vp3d {
@@ -97,6 +98,7 @@ __device__ __forceinline__ void peer_st(float* ptr, float4 v) {
 template <bool MC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kArThreads, 1)
 peer_allreduce_kernel(const AllReduceParams p) {
+  pdl_enter();
   rank_barrier(p);
   const long long vecs = p.n >> 2;
   const long long lo = vecs * p.rank / p.world, hi = vecs * (p.rank + 1) / p.world;
@@ -144,9 +146,9 @@ peer_allreduce_kernel(const AllReduceParams p) {
 
 cudaError_t launch_peer_allreduce(const AllReduceParams& p, int ctas, cudaStream_t stream) {
   if (p.mc != nullptr)
-    peer_allreduce_kernel<true><<<ctas, kArThreads, 0, stream>>>(p);
+    launch_k(peer_allreduce_kernel<true>, dim3(ctas), dim3(kArThreads), 0, stream, p);
   else
-    peer_allreduce_kernel<false><<<ctas, kArThreads, 0, stream>>>(p);
+    launch_k(peer_allreduce_kernel<false>, dim3(ctas), dim3(kArThreads), 0, stream, p);
   return cudaGetLastError();
 }
 

@@ -54,6 +54,14 @@ cudaError_t launch_bn_fold(const float* gamma, const float* beta, const float* m
                            float* scale, float* shift, int c, int c_pad, cudaStream_t stream);
 }  // namespace vp3d
 
+namespace vp3d {
+// Programmatic dependent launch for every kernel of the library (pdl.cuh). Initial value from VP3D_PDL ("0": off).
+int g_pdl = [] {
+  const char* e = std::getenv("VP3D_PDL");
+  return (e != nullptr && std::strcmp(e, "0") == 0) ? 0 : 1;
+}();
+}  // namespace vp3d
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -208,6 +216,11 @@ int vp3d_set_sched_mode(int mode) {
   if (mode < 0 || mode > 2)
     return fail(VP3D_ERR_INVALID, "sched mode must be 0 (static), 1 (dynamic) or 2 (dynamic for every pair launch)");
   g_sched_mode = mode;
+  return VP3D_OK;
+}
+
+int vp3d_set_pdl(int on) {
+  vp3d::g_pdl = on ? 1 : 0;
   return VP3D_OK;
 }
 

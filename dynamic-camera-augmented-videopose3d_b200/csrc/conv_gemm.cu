@@ -18,6 +18,7 @@
 //                                convert, 16-byte stores; overlaps the next tile's MMAs through the 2nd TMEM buffer
 #include "ptx.cuh"
 #include "kernels.h"
+#include "pdl.cuh"
 #include "bn_tail.cuh"
 
 namespace vp3d {
@@ -167,6 +168,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  // everything above touched only this CTA's shared / tensor memory: it overlaps the tail of the previous kernel (pdl.cuh)
+  pdl_enter();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -496,7 +499,7 @@ static cudaError_t launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, co
   if (cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(conv_gemm_kernel<DT, BN, BMN>), Cfg::kSmemBytes,
                                         attr_done))
     return e;
-  conv_gemm_kernel<DT, BN, BMN><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, p);
+  launch_k(conv_gemm_kernel<DT, BN, BMN>, dim3(grid), dim3(kNumThreads), Cfg::kSmemBytes, stream, tmA, tmB, tmC, p);
   return cudaGetLastError();
 }
 

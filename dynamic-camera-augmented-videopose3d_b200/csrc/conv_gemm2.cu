@@ -17,6 +17,7 @@
 // and TF32 stay on conv_gemm_kernel, as do launches of less than two waves.
 #include "ptx.cuh"
 #include "kernels.h"
+#include "pdl.cuh"
 #include "dropout.cuh"
 #include "bn_tail.cuh"
 
@@ -198,6 +199,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tmem_alloc_2cta(tmem_base_slot, kTmemCols);
     tmem_relinquish_2cta();
   }
+  // everything above touched only this CTA's shared / tensor memory: it overlaps the tail of the previous kernel (pdl.cuh)
+  pdl_enter();
   if (p.shift != nullptr) {
     const int n_cols = p.n_tiles * kBN;
     for (int j = threadIdx.x; j < n_cols; j += kThreads) {
@@ -591,13 +594,15 @@ cudaError_t launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem_bytes<EPI>();
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // pdl.cuh
+  attr[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   return cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<DT, BMN, EPI>, tmA, tmB, tmC, tmS, p);
 }
 

@@ -7,6 +7,7 @@
 #include <cuda_fp16.h>
 
 #include "kernels.h"
+#include "pdl.cuh"
 
 namespace vp3d {
 
@@ -30,6 +31,7 @@ __device__ __forceinline__ void store_elem<VP3D_TF32>(void* dst, long long i, fl
 template <int DT>
 __global__ void __launch_bounds__(256)
 pack_rows_kernel(const float* __restrict__ src, void* __restrict__ dst, long long rows, int c, int c_pad) {
+  pdl_enter();
   // blockDim.x = c_pad threads across a row (coalesced in src and dst), blockDim.y rows per block, grid-stride over rows
   const int k = threadIdx.x;
   for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < rows; r += (long long)gridDim.x * blockDim.y)
@@ -44,6 +46,7 @@ template <int DT>
 __global__ void __launch_bounds__(256)
 pack_rows_vec8_kernel(const float* __restrict__ src, uint4* __restrict__ dst, long long rows, int c, int groups,
                       int ones_col) {
+  pdl_enter();
   const long long total = rows * groups;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -76,6 +79,7 @@ template <int DT>
 __global__ void __launch_bounds__(256)
 pack_weight_kernel(const float* __restrict__ w, void* __restrict__ dst, int c_out, int c_in, int taps, int rows_pad,
                    int k_pad_per_tap, int transpose) {
+  pdl_enter();
   const long long k_total = transpose == 1 ? k_pad_per_tap : (long long)taps * k_pad_per_tap;
   const long long total = (long long)rows_pad * k_total;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -105,6 +109,7 @@ __global__ void __launch_bounds__(256)
 bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
                const float* __restrict__ var, float eps, float* __restrict__ scale, float* __restrict__ shift, int c,
                int c_pad) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c_pad) return;
   if (i < c) {
@@ -123,6 +128,7 @@ template <int DT>
 __global__ void __launch_bounds__(256)
 pack_weight_fwd_kernel(const float* __restrict__ w, const float* __restrict__ row_scale, void* __restrict__ dst,
                        int c_out, int c_in, int taps, int rows_pad, int k_pad_per_tap) {
+  pdl_enter();
   const int total = rows_pad * k_pad_per_tap;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int n = i / k_pad_per_tap;
@@ -140,6 +146,7 @@ pack_weight_fwd_kernel(const float* __restrict__ w, const float* __restrict__ ro
 __global__ void stream_advance_kernel(long long* step, int n_rings, const int* ring_len, const int* ring_dil,
                                       const int* ring_taps, int rows_per_slot, int* table, int n_launch,
                                       const int* launch_desc, int* launch_table) {
+  pdl_enter();
   __shared__ int ring[64][4];
   const long long t = *step;          // frame index of the step being issued
   const int i = threadIdx.x;
@@ -169,6 +176,7 @@ template <int DT>
 __global__ void __launch_bounds__(256)
 ring_write_kernel(const float* __restrict__ src, void* __restrict__ ring, const int* __restrict__ entry, long long rows,
                   int c, int c_pad) {
+  pdl_enter();
   const long long r_hi = entry[2], r_lo = entry[3];
   const long long total = rows * c_pad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -183,7 +191,7 @@ ring_write_kernel(const float* __restrict__ src, void* __restrict__ ring, const 
 cudaError_t launch_stream_advance(long long* step, int n_rings, const int* ring_len, const int* ring_dil,
                                   const int* ring_taps, int rows_per_slot, int* table, int n_launch,
                                   const int* launch_desc, int* launch_table, cudaStream_t stream) {
-  stream_advance_kernel<<<1, 64, 0, stream>>>(step, n_rings, ring_len, ring_dil, ring_taps, rows_per_slot, table,
+  launch_k(stream_advance_kernel, dim3(1), dim3(64), 0, stream, step, n_rings, ring_len, ring_dil, ring_taps, rows_per_slot, table,
                                               n_launch, launch_desc, launch_table);
   return cudaGetLastError();
 }
@@ -192,8 +200,8 @@ static int ew_grid(long long total, int sm_count);
 cudaError_t launch_ring_write(int dtype, const float* src, void* ring, const int* table, long long rows, int c, int c_pad,
                               int sm_count, cudaStream_t stream) {
   const int grid = ew_grid(rows * c_pad, sm_count);
-  if (dtype == VP3D_F16) ring_write_kernel<VP3D_F16><<<grid, 256, 0, stream>>>(src, ring, table, rows, c, c_pad);
-  else if (dtype == VP3D_BF16) ring_write_kernel<VP3D_BF16><<<grid, 256, 0, stream>>>(src, ring, table, rows, c, c_pad);
+  if (dtype == VP3D_F16) launch_k(ring_write_kernel<VP3D_F16>, dim3(grid), dim3(256), 0, stream, src, ring, table, rows, c, c_pad);
+  else if (dtype == VP3D_BF16) launch_k(ring_write_kernel<VP3D_BF16>, dim3(grid), dim3(256), 0, stream, src, ring, table, rows, c, c_pad);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
@@ -214,9 +222,9 @@ cudaError_t launch_pack_rows(int dtype, const float* src, void* dst, long long r
     const int groups = c_pad / 8;
     const int g = ew_grid(rows * groups, sm_count);
     if (dtype == VP3D_F16)
-      pack_rows_vec8_kernel<VP3D_F16><<<g, 256, 0, stream>>>(src, static_cast<uint4*>(dst), rows, c, groups, ones_col);
+      launch_k(pack_rows_vec8_kernel<VP3D_F16>, dim3(g), dim3(256), 0, stream, src, static_cast<uint4*>(dst), rows, c, groups, ones_col);
     else
-      pack_rows_vec8_kernel<VP3D_BF16><<<g, 256, 0, stream>>>(src, static_cast<uint4*>(dst), rows, c, groups, ones_col);
+      launch_k(pack_rows_vec8_kernel<VP3D_BF16>, dim3(g), dim3(256), 0, stream, src, static_cast<uint4*>(dst), rows, c, groups, ones_col);
     return cudaGetLastError();
   }
   if (ones_col >= 0) return cudaErrorInvalidValue;
@@ -226,9 +234,9 @@ cudaError_t launch_pack_rows(int dtype, const float* src, void* dst, long long r
   if (gx > (long long)sm_count * 16) gx = (long long)sm_count * 16;
   if (gx < 1) gx = 1;
   const int grid = (int)gx;
-  if (dtype == VP3D_F16) pack_rows_kernel<VP3D_F16><<<grid, block, 0, stream>>>(src, dst, rows, c, c_pad);
-  else if (dtype == VP3D_BF16) pack_rows_kernel<VP3D_BF16><<<grid, block, 0, stream>>>(src, dst, rows, c, c_pad);
-  else if (dtype == VP3D_TF32) pack_rows_kernel<VP3D_TF32><<<grid, block, 0, stream>>>(src, dst, rows, c, c_pad);
+  if (dtype == VP3D_F16) launch_k(pack_rows_kernel<VP3D_F16>, dim3(grid), dim3(block), 0, stream, src, dst, rows, c, c_pad);
+  else if (dtype == VP3D_BF16) launch_k(pack_rows_kernel<VP3D_BF16>, dim3(grid), dim3(block), 0, stream, src, dst, rows, c, c_pad);
+  else if (dtype == VP3D_TF32) launch_k(pack_rows_kernel<VP3D_TF32>, dim3(grid), dim3(block), 0, stream, src, dst, rows, c, c_pad);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
@@ -240,22 +248,22 @@ cudaError_t launch_pack_weight(int dtype, const float* w, void* dst, int c_out, 
   if (transpose == 0 && (long long)rows_pad * k_pad_per_tap < (1LL << 31)) {
     const int g = ew_grid((long long)rows_pad * k_pad_per_tap, sm_count);
     if (dtype == VP3D_F16)
-      pack_weight_fwd_kernel<VP3D_F16><<<g, 256, 0, stream>>>(w, row_scale, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap);
+      launch_k(pack_weight_fwd_kernel<VP3D_F16>, dim3(g), dim3(256), 0, stream, w, row_scale, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap);
     else if (dtype == VP3D_BF16)
-      pack_weight_fwd_kernel<VP3D_BF16><<<g, 256, 0, stream>>>(w, row_scale, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap);
+      launch_k(pack_weight_fwd_kernel<VP3D_BF16>, dim3(g), dim3(256), 0, stream, w, row_scale, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap);
     else if (dtype == VP3D_TF32)
-      pack_weight_fwd_kernel<VP3D_TF32><<<g, 256, 0, stream>>>(w, row_scale, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap);
+      launch_k(pack_weight_fwd_kernel<VP3D_TF32>, dim3(g), dim3(256), 0, stream, w, row_scale, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap);
     else
       return cudaErrorInvalidValue;
     return cudaGetLastError();
   }
   const int grid = ew_grid((long long)rows_pad * k_total, sm_count);
   if (dtype == VP3D_F16)
-    pack_weight_kernel<VP3D_F16><<<grid, 256, 0, stream>>>(w, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap, transpose);
+    launch_k(pack_weight_kernel<VP3D_F16>, dim3(grid), dim3(256), 0, stream, w, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap, transpose);
   else if (dtype == VP3D_BF16)
-    pack_weight_kernel<VP3D_BF16><<<grid, 256, 0, stream>>>(w, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap, transpose);
+    launch_k(pack_weight_kernel<VP3D_BF16>, dim3(grid), dim3(256), 0, stream, w, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap, transpose);
   else if (dtype == VP3D_TF32)
-    pack_weight_kernel<VP3D_TF32><<<grid, 256, 0, stream>>>(w, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap, transpose);
+    launch_k(pack_weight_kernel<VP3D_TF32>, dim3(grid), dim3(256), 0, stream, w, dst, c_out, c_in, taps, rows_pad, k_pad_per_tap, transpose);
   else
     return cudaErrorInvalidValue;
   return cudaGetLastError();
@@ -263,7 +271,7 @@ cudaError_t launch_pack_weight(int dtype, const float* w, void* dst, int c_out, 
 
 cudaError_t launch_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                            float* scale, float* shift, int c, int c_pad, cudaStream_t stream) {
-  bn_fold_kernel<<<(c_pad + 255) / 256, 256, 0, stream>>>(gamma, beta, mean, var, eps, scale, shift, c, c_pad);
+  launch_k(bn_fold_kernel, dim3((c_pad + 255) / 256), dim3(256), 0, stream, gamma, beta, mean, var, eps, scale, shift, c, c_pad);
   return cudaGetLastError();
 }
 

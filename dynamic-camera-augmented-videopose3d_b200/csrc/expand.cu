@@ -22,6 +22,7 @@
 #include <cuda_fp16.h>
 
 #include "kernels.h"
+#include "pdl.cuh"
 
 namespace vp3d {
 
@@ -67,6 +68,7 @@ expand_bn_stats_kernel(const float* __restrict__ G, const void* __restrict__ w, 
                        float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ nbt,
                        float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                        float* __restrict__ invstd_out, float* __restrict__ wg, int c, int tick_inline) {
+  pdl_enter();
   // weights of the block's 8 channels, [column][channel]: the inner loop below reads one column's 8 weights as two
   // broadcast LDS.128 (a [channel][column] layout needs 8 scalar LDS per column, and the kernel was bound by the LSU's
   // instruction rate: 30 us)
@@ -145,7 +147,10 @@ expand_bn_stats_kernel(const float* __restrict__ G, const void* __restrict__ w, 
   }
 }
 
-__global__ void counter_tick_kernel(long long* nbt) { *nbt += 1; }
+__global__ void counter_tick_kernel(long long* nbt) {
+  pdl_enter();
+  *nbt += 1;
+}
 
 // grid = c_pad / kExCh blocks, thread = column k. P: fp32 [c_pad][256] = gm^T X (scaled by gscale), wg from the forward.
 // dw: nn.Conv1d layout (c_out, c_in, taps); column k = tap * c_in_pad + ci.
@@ -156,6 +161,7 @@ expand_bwd_finish_kernel(const float* __restrict__ P, const float* __restrict__ 
                          const float* __restrict__ mean, const float* __restrict__ invstd,
                          const float* __restrict__ gscale_buf, int c, int c_in, int c_in_pad, int taps,
                          float* __restrict__ dw, float* __restrict__ d_gamma, float* __restrict__ d_beta) {
+  pdl_enter();
   __shared__ float red[kExCh][8];
   const int k = threadIdx.x;
   const int c0 = blockIdx.x * kExCh;
@@ -200,16 +206,16 @@ cudaError_t launch_expand_bn_stats(int dtype, const float* G, const void* w, int
   const int grid = c_pad / kExCh;
   const int tick_inline = momentum >= 0.f ? 1 : 0;
   if (dtype == VP3D_F16)
-    expand_bn_stats_kernel<VP3D_F16><<<grid, kExThreads, 0, stream>>>(G, w, k_total, ones_col, gamma, beta, eps, momentum,
+    launch_k(expand_bn_stats_kernel<VP3D_F16>, dim3(grid), dim3(kExThreads), 0, stream, G, w, k_total, ones_col, gamma, beta, eps, momentum,
                                                                       running_mean, running_var, nbt, scale, shift, mean,
                                                                       invstd, wg, c, tick_inline);
   else if (dtype == VP3D_BF16)
-    expand_bn_stats_kernel<VP3D_BF16><<<grid, kExThreads, 0, stream>>>(G, w, k_total, ones_col, gamma, beta, eps, momentum,
+    launch_k(expand_bn_stats_kernel<VP3D_BF16>, dim3(grid), dim3(kExThreads), 0, stream, G, w, k_total, ones_col, gamma, beta, eps, momentum,
                                                                        running_mean, running_var, nbt, scale, shift, mean,
                                                                        invstd, wg, c, tick_inline);
   else
     return cudaErrorInvalidValue;
-  if (nbt != nullptr && !tick_inline) counter_tick_kernel<<<1, 1, 0, stream>>>(nbt);   // after every block has read the old count
+  if (nbt != nullptr && !tick_inline) launch_k(counter_tick_kernel, dim3(1), dim3(1), 0, stream, nbt);   // after every block has read the old count
   return cudaGetLastError();
 }
 
@@ -219,11 +225,11 @@ cudaError_t launch_expand_bwd_finish(int dtype, const float* P, const float* wg,
                                      float* d_gamma, float* d_beta, cudaStream_t stream) {
   const int grid = c_pad / kExCh;
   if (dtype == VP3D_F16)
-    expand_bwd_finish_kernel<VP3D_F16><<<grid, kExThreads, 0, stream>>>(P, wg, G, w, k_total, ones_col, scale, mean, invstd,
+    launch_k(expand_bwd_finish_kernel<VP3D_F16>, dim3(grid), dim3(kExThreads), 0, stream, P, wg, G, w, k_total, ones_col, scale, mean, invstd,
                                                                         gscale_buf, c, c_in, c_in_pad, taps, dw, d_gamma,
                                                                         d_beta);
   else if (dtype == VP3D_BF16)
-    expand_bwd_finish_kernel<VP3D_BF16><<<grid, kExThreads, 0, stream>>>(P, wg, G, w, k_total, ones_col, scale, mean,
+    launch_k(expand_bwd_finish_kernel<VP3D_BF16>, dim3(grid), dim3(kExThreads), 0, stream, P, wg, G, w, k_total, ones_col, scale, mean,
                                                                          invstd, gscale_buf, c, c_in, c_in_pad, taps, dw,
                                                                          d_gamma, d_beta);
   else

@@ -8,6 +8,7 @@
 // does not depend on atomics ordering. Backward writes d loss / d pred = g/n * w * (pred - target) / ||pred - target||
 // (zero where the distance is zero, as torch.linalg.norm's backward does).
 #include "kernels.h"
+#include "pdl.cuh"
 
 namespace vp3d {
 
@@ -51,6 +52,7 @@ __device__ __forceinline__ float dist3(float px, float py, float pz, float tx, f
 __global__ void __launch_bounds__(kLossThreads)
 mpjpe_partial_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, long long n_joints, WeightView wv,
                      int vec_ok, double* __restrict__ partial) {
+  pdl_enter();
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long n_quads = vec_ok ? (n_joints >> 2) : 0;
   double acc = 0.0;
@@ -80,6 +82,7 @@ mpjpe_partial_kernel(const float* __restrict__ pred, const float* __restrict__ t
 
 __global__ void __launch_bounds__(kLossThreads)
 mean_finish_kernel(const double* __restrict__ partial, int n_partial, double inv_count, float* __restrict__ out) {
+  pdl_enter();
   double acc = 0.0;
   for (int i = threadIdx.x; i < n_partial; i += blockDim.x) acc += partial[i];
   const double s = block_sum(acc);
@@ -89,6 +92,7 @@ mean_finish_kernel(const double* __restrict__ partial, int n_partial, double inv
 __global__ void __launch_bounds__(kLossThreads)
 mpjpe_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, const float* __restrict__ grad_out,
                  float inv_count, long long n_joints, WeightView wv, int vec_ok, float* __restrict__ grad_pred) {
+  pdl_enter();
   const float g0 = __ldg(grad_out) * inv_count;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long n_quads = vec_ok ? (n_joints >> 2) : 0;
@@ -126,6 +130,7 @@ mpjpe_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, 
 __global__ void __launch_bounds__(kLossThreads)
 n_mpjpe_partial_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, long long n_poses, int J,
                        double* __restrict__ partial) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -160,6 +165,7 @@ n_mpjpe_partial_kernel(const float* __restrict__ pred, const float* __restrict__
 __global__ void __launch_bounds__(kLossThreads)
 mpjpe_nd_partial_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, long long n_pts, int D,
                         WeightView wv, double* __restrict__ partial) {
+  pdl_enter();
   const long long stride = (long long)gridDim.x * blockDim.x;
   double acc = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += stride) {
@@ -177,6 +183,7 @@ mpjpe_nd_partial_kernel(const float* __restrict__ pred, const float* __restrict_
 __global__ void __launch_bounds__(kLossThreads)
 mpjpe_nd_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, const float* __restrict__ grad_out,
                     float inv_count, long long n_pts, int D, WeightView wv, float* __restrict__ grad_pred) {
+  pdl_enter();
   const float g0 = __ldg(grad_out) * inv_count;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += stride) {
@@ -198,6 +205,7 @@ mpjpe_nd_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tg
 __global__ void __launch_bounds__(kLossThreads)
 n_mpjpe_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, const float* __restrict__ grad_out,
                    float inv_count, long long n_poses, int J, float* __restrict__ grad_pred) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -279,6 +287,7 @@ __device__ void jacobi_eig3(double A[3][3], double V[3][3], double w[3]) {
 __global__ void __launch_bounds__(kLossThreads)
 p_mpjpe_partial_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, long long n_poses, int J,
                        double* __restrict__ partial) {
+  pdl_enter();
   const long long stride = (long long)gridDim.x * blockDim.x;
   double acc = 0.0;
   for (long long pose = (long long)blockIdx.x * blockDim.x + threadIdx.x; pose < n_poses; pose += stride) {
@@ -376,6 +385,7 @@ p_mpjpe_partial_kernel(const float* __restrict__ pred, const float* __restrict__
 __global__ void __launch_bounds__(kLossThreads)
 velocity_partial_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, long long T, long long inner, int D,
                         double* __restrict__ partial) {
+  pdl_enter();
   const long long n = (T - 1) * inner;
   const long long stride = (long long)gridDim.x * blockDim.x;
   double acc = 0.0;
@@ -408,8 +418,8 @@ cudaError_t launch_mpjpe_fwd(const float* pred, const float* tgt, long long n_jo
   WeightView wv{w, T > 0 ? T : 1, J > 0 ? J : 1, s_n, s_t, s_j};
   const int grid = loss_grid(n_joints, sm_count);
   const int vec_ok = aligned16(pred) && aligned16(tgt);
-  mpjpe_partial_kernel<<<grid, kLossThreads, 0, stream>>>(pred, tgt, n_joints, wv, vec_ok, partial);
-  mean_finish_kernel<<<1, kLossThreads, 0, stream>>>(partial, grid, n_joints > 0 ? 1.0 / (double)n_joints : 0.0, out);
+  launch_k(mpjpe_partial_kernel, dim3(grid), dim3(kLossThreads), 0, stream, pred, tgt, n_joints, wv, vec_ok, partial);
+  launch_k(mean_finish_kernel, dim3(1), dim3(kLossThreads), 0, stream, partial, grid, n_joints > 0 ? 1.0 / (double)n_joints : 0.0, out);
   return cudaGetLastError();
 }
 
@@ -420,7 +430,7 @@ cudaError_t launch_mpjpe_bwd(const float* pred, const float* tgt, const float* g
   WeightView wv{w, T > 0 ? T : 1, J > 0 ? J : 1, s_n, s_t, s_j};
   const int grid = loss_grid(n_joints, sm_count);
   const int vec_ok = aligned16(pred) && aligned16(tgt) && aligned16(grad_pred);
-  mpjpe_bwd_kernel<<<grid, kLossThreads, 0, stream>>>(pred, tgt, grad_out, 1.f / (float)n_joints, n_joints, wv, vec_ok,
+  launch_k(mpjpe_bwd_kernel, dim3(grid), dim3(kLossThreads), 0, stream, pred, tgt, grad_out, 1.f / (float)n_joints, n_joints, wv, vec_ok,
                                                       grad_pred);
   return cudaGetLastError();
 }
@@ -430,8 +440,8 @@ cudaError_t launch_mpjpe_nd_fwd(const float* pred, const float* tgt, long long n
                                 int sm_count, cudaStream_t stream) {
   WeightView wv{w, T > 0 ? T : 1, J > 0 ? J : 1, s_n, s_t, s_j};
   const int grid = loss_grid(n_pts * 4, sm_count);
-  mpjpe_nd_partial_kernel<<<grid, kLossThreads, 0, stream>>>(pred, tgt, n_pts, D, wv, partial);
-  mean_finish_kernel<<<1, kLossThreads, 0, stream>>>(partial, grid, n_pts > 0 ? 1.0 / (double)n_pts : 0.0, out);
+  launch_k(mpjpe_nd_partial_kernel, dim3(grid), dim3(kLossThreads), 0, stream, pred, tgt, n_pts, D, wv, partial);
+  launch_k(mean_finish_kernel, dim3(1), dim3(kLossThreads), 0, stream, partial, grid, n_pts > 0 ? 1.0 / (double)n_pts : 0.0, out);
   return cudaGetLastError();
 }
 
@@ -440,7 +450,7 @@ cudaError_t launch_mpjpe_nd_bwd(const float* pred, const float* tgt, const float
                                 float* grad_pred, int sm_count, cudaStream_t stream) {
   if (n_pts <= 0) return cudaSuccess;
   WeightView wv{w, T > 0 ? T : 1, J > 0 ? J : 1, s_n, s_t, s_j};
-  mpjpe_nd_bwd_kernel<<<loss_grid(n_pts * 4, sm_count), kLossThreads, 0, stream>>>(pred, tgt, grad_out,
+  launch_k(mpjpe_nd_bwd_kernel, dim3(loss_grid(n_pts * 4, sm_count)), dim3(kLossThreads), 0, stream, pred, tgt, grad_out,
                                                                                    1.f / (float)n_pts, n_pts, D, wv,
                                                                                    grad_pred);
   return cudaGetLastError();
@@ -452,9 +462,9 @@ cudaError_t launch_n_mpjpe_fwd(const float* pred, const float* tgt, long long n_
   const long long cap = (long long)sm_count * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  n_mpjpe_partial_kernel<<<(int)blocks, kLossThreads, 0, stream>>>(pred, tgt, n_poses, J, partial);
+  launch_k(n_mpjpe_partial_kernel, dim3((int)blocks), dim3(kLossThreads), 0, stream, pred, tgt, n_poses, J, partial);
   const double cnt = (double)n_poses * (double)J;
-  mean_finish_kernel<<<1, kLossThreads, 0, stream>>>(partial, (int)blocks, cnt > 0 ? 1.0 / cnt : 0.0, out);
+  launch_k(mean_finish_kernel, dim3(1), dim3(kLossThreads), 0, stream, partial, (int)blocks, cnt > 0 ? 1.0 / cnt : 0.0, out);
   return cudaGetLastError();
 }
 
@@ -464,8 +474,8 @@ cudaError_t launch_p_mpjpe_fwd(const float* pred, const float* tgt, long long n_
   const long long cap = (long long)sm_count * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  p_mpjpe_partial_kernel<<<(int)blocks, kLossThreads, 0, stream>>>(pred, tgt, n_poses, J, partial);
-  mean_finish_kernel<<<1, kLossThreads, 0, stream>>>(partial, (int)blocks, 1.0 / ((double)n_poses * J), out);
+  launch_k(p_mpjpe_partial_kernel, dim3((int)blocks), dim3(kLossThreads), 0, stream, pred, tgt, n_poses, J, partial);
+  launch_k(mean_finish_kernel, dim3(1), dim3(kLossThreads), 0, stream, partial, (int)blocks, 1.0 / ((double)n_poses * J), out);
   return cudaGetLastError();
 }
 
@@ -473,8 +483,8 @@ cudaError_t launch_velocity_error(const float* pred, const float* tgt, long long
                                   double* partial, float* out, int sm_count, cudaStream_t stream) {
   const long long n = (T - 1) * inner;
   const int grid = loss_grid(n * 4, sm_count);
-  velocity_partial_kernel<<<grid, kLossThreads, 0, stream>>>(pred, tgt, T, inner, D, partial);
-  mean_finish_kernel<<<1, kLossThreads, 0, stream>>>(partial, grid, n > 0 ? 1.0 / (double)n : 0.0, out);
+  launch_k(velocity_partial_kernel, dim3(grid), dim3(kLossThreads), 0, stream, pred, tgt, T, inner, D, partial);
+  launch_k(mean_finish_kernel, dim3(1), dim3(kLossThreads), 0, stream, partial, grid, n > 0 ? 1.0 / (double)n : 0.0, out);
   return cudaGetLastError();
 }
 
@@ -485,7 +495,7 @@ cudaError_t launch_n_mpjpe_bwd(const float* pred, const float* tgt, const float*
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   const double cnt = (double)n_poses * (double)J;
-  n_mpjpe_bwd_kernel<<<(int)blocks, kLossThreads, 0, stream>>>(pred, tgt, grad_out, (float)(1.0 / cnt), n_poses, J,
+  launch_k(n_mpjpe_bwd_kernel, dim3((int)blocks), dim3(kLossThreads), 0, stream, pred, tgt, grad_out, (float)(1.0 / cnt), n_poses, J,
                                                                grad_pred);
   return cudaGetLastError();
 }
@@ -547,6 +557,7 @@ __device__ __forceinline__ Reproj reproject(const ReprojArgs& a, long long i, co
 
 __global__ void __launch_bounds__(kLossThreads)
 reproj_partial_kernel(const ReprojArgs a, double* __restrict__ partial) {
+  pdl_enter();
   const long long stride = (long long)gridDim.x * blockDim.x;
   double acc = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_pts; i += stride) {
@@ -564,6 +575,7 @@ reproj_partial_kernel(const ReprojArgs a, double* __restrict__ partial) {
 __global__ void __launch_bounds__(kLossThreads)
 reproj_bwd_kernel(const ReprojArgs a, const float* __restrict__ grad_out, float inv_count, float* __restrict__ grad_pose,
                   float* __restrict__ grad_traj) {
+  pdl_enter();
   const float g0 = __ldg(grad_out) * inv_count;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_pts; i += stride) {
@@ -609,8 +621,8 @@ cudaError_t launch_reproj_fwd(const float* pose, const float* traj, long long n_
   const ReprojArgs a{pose, traj, cam, tgt, n_pts, pts_per_traj > 0 ? pts_per_traj : 1, pts_per_cam > 0 ? pts_per_cam : 1,
                      linear};
   const int grid = loss_grid(n_pts * 4, sm_count);
-  reproj_partial_kernel<<<grid, kLossThreads, 0, stream>>>(a, partial);
-  mean_finish_kernel<<<1, kLossThreads, 0, stream>>>(partial, grid, n_pts > 0 ? 1.0 / (double)n_pts : 0.0, out);
+  launch_k(reproj_partial_kernel, dim3(grid), dim3(kLossThreads), 0, stream, a, partial);
+  launch_k(mean_finish_kernel, dim3(1), dim3(kLossThreads), 0, stream, partial, grid, n_pts > 0 ? 1.0 / (double)n_pts : 0.0, out);
   return cudaGetLastError();
 }
 
@@ -621,7 +633,7 @@ cudaError_t launch_reproj_bwd(const float* pose, const float* traj, long long n_
   const ReprojArgs a{pose, traj, cam, tgt, n_pts, pts_per_traj > 0 ? pts_per_traj : 1, pts_per_cam > 0 ? pts_per_cam : 1,
                      linear};
   const int grid = loss_grid(n_pts * 4, sm_count);
-  reproj_bwd_kernel<<<grid, kLossThreads, 0, stream>>>(a, grad_out, 1.f / (float)n_pts, grad_pose, grad_traj);
+  launch_k(reproj_bwd_kernel, dim3(grid), dim3(kLossThreads), 0, stream, a, grad_out, 1.f / (float)n_pts, grad_pose, grad_traj);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,44 @@
+// Programmatic dependent launch (PDL): every kernel of the library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel on the stream may become resident -- and run its
+// prologue: barrier init, tensor-memory allocation, descriptor prefetch -- while this one drains its last CTAs, instead
+// of being launched after the last CTA has retired. Each kernel therefore
+//   * calls pdl_wait() (griddepcontrol.wait: the prerequisite grids have completed and their memory is visible) before
+//     its first access to global memory, in EVERY thread and before any early return -- a grid none of whose threads
+//     waited could complete before its predecessor and let ITS successor start too early;
+//   * calls pdl_trigger() (griddepcontrol.launch_dependents) right after: the dependent grid may be scheduled as soon as
+//     every CTA of this one has started (it still waits for this grid's completion in its own pdl_wait()).
+// A step of the training loop is ~80 dependent launches of 3-150 us, most of them back to back on one stream (also as
+// programmatic edges of the captured CUDA graph). vp3d_set_pdl(0) / VP3D_PDL=0 launches everything with the attribute
+// off (plain stream order); the device-side instructions are then no-ops.
+#pragma once
+
+#include <cuda_runtime.h>
+
+namespace vp3d {
+
+extern int g_pdl;   // api.cu
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_wait();
+  pdl_trigger();
+}
+
+// kernel<<<grid, block, smem, stream>>>(args...) with the PDL attribute (and optionally a cluster shape)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+}  // namespace vp3d

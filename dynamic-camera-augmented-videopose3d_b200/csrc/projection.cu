@@ -18,6 +18,7 @@
 #include <cstdlib>
 
 #include "kernels.h"
+#include "pdl.cuh"
 #include "ptx.cuh"
 
 namespace vp3d {
@@ -241,6 +242,7 @@ template <typename IndexT, bool FAST>
 __global__ void __launch_bounds__(256, 4)
 project_points_kernel(const float* __restrict__ X, float* __restrict__ out3, float* __restrict__ out2, long long n_pts,
                       PointOps o, int vec_ok) {
+  pdl_enter();
   const long long n_quads = vec_ok ? (n_pts >> 2) : 0;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const bool has_pose = (o.mode & 7) != 0, has_proj = (o.mode & 16) != 0;
@@ -339,6 +341,7 @@ __device__ __forceinline__ float3 to_camera(const WindowParams& w, long long f, 
 
 __global__ void __launch_bounds__(256)
 project_windows_kernel(WindowParams w, float* __restrict__ out2) {
+  pdl_enter();
   const unsigned total = (unsigned)w.batch * w.window * w.joints;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const unsigned j = i % w.joints;
@@ -355,6 +358,7 @@ project_windows_kernel(WindowParams w, float* __restrict__ out2) {
 
 __global__ void __launch_bounds__(256)
 window_targets_kernel(WindowParams w, float* __restrict__ target3) {
+  pdl_enter();
   const unsigned total = (unsigned)w.batch * w.chunk * w.joints;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const unsigned j = i % w.joints;
@@ -377,6 +381,7 @@ window_targets_kernel(WindowParams w, float* __restrict__ target3) {
 // K @ [R | -R c] per window frame: R = rotation of conj(q) (world -> camera), c = camera position t
 __global__ void __launch_bounds__(256)
 window_cameras_kernel(WindowParams w, float* __restrict__ cam3x4) {
+  pdl_enter();
   const unsigned total = (unsigned)w.batch * w.window;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const unsigned k = i % w.window;
@@ -415,10 +420,10 @@ cudaError_t launch_project_windows(const float* x, const float* q, const float* 
     if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
     return (unsigned)(blocks < 1 ? 1 : blocks);
   };
-  project_windows_kernel<<<grid_for((long long)batch * w.window * joints), 256, 0, stream>>>(w, out2);
+  launch_k(project_windows_kernel, dim3(grid_for((long long)batch * w.window * joints)), dim3(256), 0, stream, w, out2);
   if (target3 != nullptr)
-    window_targets_kernel<<<grid_for((long long)batch * chunk * joints), 256, 0, stream>>>(w, target3);
-  if (cam3x4 != nullptr) window_cameras_kernel<<<grid_for((long long)batch * w.window), 256, 0, stream>>>(w, cam3x4);
+    launch_k(window_targets_kernel, dim3(grid_for((long long)batch * chunk * joints)), dim3(256), 0, stream, w, target3);
+  if (cam3x4 != nullptr) launch_k(window_cameras_kernel, dim3(grid_for((long long)batch * w.window)), dim3(256), 0, stream, w, cam3x4);
   return cudaGetLastError();
 }
 
@@ -427,6 +432,7 @@ cudaError_t launch_project_windows(const float* x, const float* q, const float* 
 __global__ void __launch_bounds__(256)
 project_bwd_kernel(const float* __restrict__ X, const float* __restrict__ cam, const float* __restrict__ g,
                    long long n_pts, long long pts_per_cam, int linear, float* __restrict__ gx) {
+  pdl_enter();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += stride) {
     const float* c = cam + 9 * (i / pts_per_cam);
@@ -458,7 +464,7 @@ cudaError_t launch_project_bwd(const float* X, const float* cam, const float* g,
   long long blocks = (n_pts + 255) / 256;
   if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
   if (blocks < 1) blocks = 1;
-  project_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(X, cam, g, n_pts, pts_per_cam > 0 ? pts_per_cam : 1, linear, gx);
+  launch_k(project_bwd_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, X, cam, g, n_pts, pts_per_cam > 0 ? pts_per_cam : 1, linear, gx);
   return cudaGetLastError();
 }
 
@@ -509,6 +515,7 @@ __device__ __forceinline__ float clamp_unit_nan(float x) {
 template <int STAGES, bool HAS3>
 __global__ void __launch_bounds__(kFrameThreads, 3)
 project_frames_kernel(const FrameParams p) {
+  pdl_enter();
   extern __shared__ __align__(128) unsigned char frame_smem[];
   const unsigned F = p.tile_frames, J = p.joints;
   const unsigned x_bytes = F * J * 12, q_bytes = F * 16, t_bytes = F * 12;   // all multiples of 16 (F % 4 == 0)
@@ -690,7 +697,7 @@ static cudaError_t try_launch_project_frames(const float* X, float* out3, float*
   }();
   if (configured != cudaSuccess) return configured;
   auto launch = [&](auto kernel) {
-    kernel<<<grid, kFrameThreads, smem, stream>>>(p);
+    launch_k(kernel, dim3(grid), dim3(kFrameThreads), smem, stream, p);
     return cudaGetLastError();
   };
   if (out3 != nullptr) return tune.stages == 2 ? launch(project_frames_kernel<2, true>) : launch(project_frames_kernel<3, true>);
@@ -717,10 +724,10 @@ cudaError_t launch_project_points(const float* X, float* out3, float* out2, long
   if (blocks < 1) blocks = 1;
   const bool fast = (mode & 64) != 0;   // VP3D_PT_FAST
   if (n_pts < (1LL << 31)) {
-    if (fast) project_points_kernel<unsigned int, true><<<(unsigned)blocks, 256, 0, stream>>>(X, out3, out2, n_pts, o, vec_ok);
-    else project_points_kernel<unsigned int, false><<<(unsigned)blocks, 256, 0, stream>>>(X, out3, out2, n_pts, o, vec_ok);
+    if (fast) launch_k(project_points_kernel<unsigned int, true>, dim3((unsigned)blocks), dim3(256), 0, stream, X, out3, out2, n_pts, o, vec_ok);
+    else launch_k(project_points_kernel<unsigned int, false>, dim3((unsigned)blocks), dim3(256), 0, stream, X, out3, out2, n_pts, o, vec_ok);
   } else {
-    project_points_kernel<long long, false><<<(unsigned)blocks, 256, 0, stream>>>(X, out3, out2, n_pts, o, vec_ok);
+    launch_k(project_points_kernel<long long, false>, dim3((unsigned)blocks), dim3(256), 0, stream, X, out3, out2, n_pts, o, vec_ok);
   }
   return cudaGetLastError();
 }

@@ -15,6 +15,7 @@
 #include <cuda_fp16.h>
 
 #include "kernels.h"
+#include "pdl.cuh"
 #include "dropout.cuh"
 #include "bn_tail.cuh"
 
@@ -61,6 +62,7 @@ bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sq
                    float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ nbt,
                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                    float* __restrict__ invstd_out, int c, int c_pad) {
+  pdl_enter();
   BnFinalizeParams f;
   f.sum = sum; f.sqsum = sqsum; f.inv_n = inv_n; f.unbias = unbias; f.gamma = gamma; f.beta = beta; f.eps = eps;
   f.momentum = momentum; f.running_mean = running_mean; f.running_var = running_var; f.nbt = nbt;
@@ -112,6 +114,7 @@ bn_act_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, 
                   const uint4* __restrict__ res, long long rows, long long rows_per_seq, long long res_seq_rows,
                   int res_row_mul, int res_row_off, int groups, DropoutParams dp, uint4* __restrict__ a,
                   const BnFinalizeParams fin) {
+  pdl_enter();
   const RowWalk w;
   if (w.grp >= groups) return;
   const DropCtx drop = make_drop(dp);
@@ -226,6 +229,7 @@ template <int DT>
 __global__ void __launch_bounds__(kEwGroups * kRedLanes)
 col_stats_kernel(const uint4* __restrict__ z, long long rows, int groups, double* __restrict__ sum,
                  double* __restrict__ sqsum) {
+  pdl_enter();
   constexpr int kU = 8;  // rows in flight per thread; a block reads kRedLanes * kU adjacent rows per iteration
   const int gl = threadIdx.x % kEwGroups, lane = threadIdx.x / kEwGroups;
   const int grp = blockIdx.y * kEwGroups + gl;
@@ -285,6 +289,7 @@ bn_act_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* __restrict__ 
                          const float* __restrict__ shift, const float* __restrict__ mean,
                          const float* __restrict__ invstd, long long rows, int groups, DropoutParams dp,
                          double* __restrict__ sum_dy, double* __restrict__ sum_dy_xhat) {
+  pdl_enter();
   const RowWalkT<kRedLanes> w;
   float a1[8], a2[8];
 #pragma unroll
@@ -340,6 +345,7 @@ bn_act_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z
                         DropoutParams dp, const double* __restrict__ sum_dy, const double* __restrict__ sum_dy_xhat,
                         const float* __restrict__ gscale_buf, uint4* __restrict__ dz, float* __restrict__ d_gamma,
                         float* __restrict__ d_beta) {
+  pdl_enter();
   const RowWalk w;
   if (w.grp >= groups) return;
   const DropCtx drop = make_drop(dp);
@@ -402,6 +408,7 @@ bn_act_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z
 // ---------------------------------------------------------------------------------------------- gradient scale
 __global__ void __launch_bounds__(256)
 grad_absmax_kernel(const float* __restrict__ dy, long long n, float* __restrict__ gscale_buf) {
+  pdl_enter();
   float m = 0.f;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -413,6 +420,7 @@ grad_absmax_kernel(const float* __restrict__ dy, long long n, float* __restrict_
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(gscale_buf + 2), __float_as_uint(m));
 }
 __global__ void grad_scale_finish_kernel(float* __restrict__ gscale_buf) {
+  pdl_enter();
   const float m = gscale_buf[2];
   float s = 1.f;
   if (m > 0.f && m < 3.0e38f) {
@@ -431,6 +439,7 @@ template <int DT>
 __global__ void __launch_bounds__(256)
 grad_pack_rows_kernel(const float* __restrict__ src, void* __restrict__ dst, long long rows, int c, int c_pad,
                       const float* __restrict__ gscale_buf, float* __restrict__ col_sum) {
+  pdl_enter();
   const float gs = gscale_buf != nullptr ? gscale_buf[0] : 1.f;
   // thread = column (blockDim.x >= c_pad handled by stride), rows strided over blocks: coalesced in both src and dst
   for (int k = threadIdx.x; k < c_pad; k += blockDim.x) {
@@ -521,12 +530,14 @@ __device__ __forceinline__ void adam_pack_body(const AdamParams& a, const long l
 template <int DT>
 __global__ void __launch_bounds__(256)
 adam_pack_kernel(AdamParams a) {
+  pdl_enter();
   adam_pack_body<DT>(a, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
 }
 
 template <int DT>
 __global__ void __launch_bounds__(256)
 adam_multi_kernel(const __grid_constant__ AdamMultiParams mp) {
+  pdl_enter();
   int i = 0;
   while (i + 1 < mp.count && (int)blockIdx.x >= mp.block_start[i + 1]) ++i;   // <= 32 entries, uniform per block
   const AdamTensor& T = mp.t[i];
@@ -544,8 +555,8 @@ adam_multi_kernel(const __grid_constant__ AdamMultiParams mp) {
 cudaError_t launch_adam_multi(int dtype, const AdamMultiParams& a, cudaStream_t stream) {
   const int blocks = a.block_start[a.count];
   if (blocks <= 0) return cudaSuccess;
-  if (dtype == VP3D_BF16) adam_multi_kernel<VP3D_BF16><<<blocks, 256, 0, stream>>>(a);
-  else adam_multi_kernel<VP3D_F16><<<blocks, 256, 0, stream>>>(a);
+  if (dtype == VP3D_BF16) launch_k(adam_multi_kernel<VP3D_BF16>, dim3(blocks), dim3(256), 0, stream, a);
+  else launch_k(adam_multi_kernel<VP3D_F16>, dim3(blocks), dim3(256), 0, stream, a);
   return cudaGetLastError();
 }
 
@@ -553,14 +564,17 @@ cudaError_t launch_adam_pack(int dtype, const AdamParams& a, int sm_count, cudaS
   long long blocks = ((a.n + 3) / 4 + 255) / 256;
   if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
   if (blocks < 1) blocks = 1;
-  if (dtype == VP3D_BF16) adam_pack_kernel<VP3D_BF16><<<(int)blocks, 256, 0, stream>>>(a);
-  else adam_pack_kernel<VP3D_F16><<<(int)blocks, 256, 0, stream>>>(a);
+  if (dtype == VP3D_BF16) launch_k(adam_pack_kernel<VP3D_BF16>, dim3((int)blocks), dim3(256), 0, stream, a);
+  else launch_k(adam_pack_kernel<VP3D_F16>, dim3((int)blocks), dim3(256), 0, stream, a);
   return cudaGetLastError();
 }
 
-__global__ void counter_add_kernel(unsigned long long* counter, unsigned long long inc) { *counter += inc; }
+__global__ void counter_add_kernel(unsigned long long* counter, unsigned long long inc) {
+  pdl_enter();
+  *counter += inc;
+}
 cudaError_t launch_counter_add(unsigned long long* counter, unsigned long long inc, cudaStream_t stream) {
-  counter_add_kernel<<<1, 1, 0, stream>>>(counter, inc);
+  launch_k(counter_add_kernel, dim3(1), dim3(1), 0, stream, counter, inc);
   return cudaGetLastError();
 }
 
@@ -590,7 +604,7 @@ cudaError_t launch_bn_finalize(const double* sum, const double* sqsum, long long
                                long long* nbt, float* scale, float* shift, float* mean, float* invstd, int c, int c_pad,
                                cudaStream_t stream) {
   const double n = (double)count;
-  bn_finalize_kernel<<<1, c_pad >= 1024 ? 1024 : ((c_pad + 31) / 32) * 32, 0, stream>>>(sum, sqsum, 1.0 / n,
+  launch_k(bn_finalize_kernel, dim3(1), dim3(c_pad >= 1024 ? 1024 : ((c_pad + 31) / 32) * 32), 0, stream, sum, sqsum, 1.0 / n,
                                                               count > 1 ? (float)(n / (n - 1.0)) : 1.f, gamma, beta, eps, momentum,
                                                               running_mean, running_var, nbt, scale, shift, mean,
                                                               invstd, c, c_pad);
@@ -598,8 +612,8 @@ cudaError_t launch_bn_finalize(const double* sum, const double* sqsum, long long
 }
 
 #define VP3D_DISPATCH_16(KERNEL, ...)                                                              \
-  if (dtype == VP3D_F16) KERNEL<VP3D_F16><<<grid, block, 0, stream>>>(__VA_ARGS__);                 \
-  else if (dtype == VP3D_BF16) KERNEL<VP3D_BF16><<<grid, block, 0, stream>>>(__VA_ARGS__);          \
+  if (dtype == VP3D_F16) launch_k(KERNEL<VP3D_F16>, dim3(grid), dim3(block), 0, stream, __VA_ARGS__);                 \
+  else if (dtype == VP3D_BF16) launch_k(KERNEL<VP3D_BF16>, dim3(grid), dim3(block), 0, stream, __VA_ARGS__);          \
   else return cudaErrorInvalidValue;                                                                \
   return cudaGetLastError();
 
@@ -653,8 +667,8 @@ cudaError_t launch_grad_scale(const float* dy, long long n, float* gscale_buf, i
   long long blocks = (n + 255) / 256;
   if (blocks > sm_count * 4) blocks = sm_count * 4;
   if (blocks < 1) blocks = 1;
-  grad_absmax_kernel<<<(int)blocks, 256, 0, stream>>>(dy, n, gscale_buf);
-  grad_scale_finish_kernel<<<1, 1, 0, stream>>>(gscale_buf);
+  launch_k(grad_absmax_kernel, dim3((int)blocks), dim3(256), 0, stream, dy, n, gscale_buf);
+  launch_k(grad_scale_finish_kernel, dim3(1), dim3(1), 0, stream, gscale_buf);
   return cudaGetLastError();
 }
 
@@ -665,9 +679,9 @@ cudaError_t launch_grad_pack_rows(int dtype, const float* src, void* dst, long l
   if (blocks < 1) blocks = 1;
   const int threads = c_pad < 256 ? ((c_pad + 31) / 32) * 32 : 256;
   if (dtype == VP3D_F16)
-    grad_pack_rows_kernel<VP3D_F16><<<(int)blocks, threads, 0, stream>>>(src, dst, rows, c, c_pad, gscale_buf, col_sum);
+    launch_k(grad_pack_rows_kernel<VP3D_F16>, dim3((int)blocks), dim3(threads), 0, stream, src, dst, rows, c, c_pad, gscale_buf, col_sum);
   else if (dtype == VP3D_BF16)
-    grad_pack_rows_kernel<VP3D_BF16><<<(int)blocks, threads, 0, stream>>>(src, dst, rows, c, c_pad, gscale_buf, col_sum);
+    launch_k(grad_pack_rows_kernel<VP3D_BF16>, dim3((int)blocks), dim3(threads), 0, stream, src, dst, rows, c, c_pad, gscale_buf, col_sum);
   else
     return cudaErrorInvalidValue;
   return cudaGetLastError();

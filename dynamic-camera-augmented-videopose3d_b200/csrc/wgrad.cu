@@ -22,6 +22,8 @@
 // two TMEM accumulator buffers so that the reduction of run i overlaps the MMAs of run i + 1.
 #include "ptx.cuh"
 #include "kernels.h"
+#include "pdl.cuh"
+#include "pdl.cuh"
 
 namespace vp3d {
 
@@ -152,6 +154,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  // everything above touched only this CTA's shared / tensor memory: it overlaps the tail of the previous kernel (pdl.cuh)
+  pdl_enter();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -318,7 +322,7 @@ static cudaError_t launch_wg(const CUtensorMap& tmA, const CUtensorMap& tmB, con
   if (cudaError_t e = set_max_smem_once(reinterpret_cast<const void*>(wgrad_gemm_kernel<DT, BN, BM>), Cfg::kSmemBytes,
                                         attr_done))
     return e;
-  wgrad_gemm_kernel<DT, BN, BM><<<grid, kWgThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  launch_k(wgrad_gemm_kernel<DT, BN, BM>, dim3(grid), dim3(kWgThreads), Cfg::kSmemBytes, stream, tmA, tmB, p);
   return cudaGetLastError();
 }
 
@@ -342,6 +346,7 @@ cudaError_t launch_wgrad(int dtype, int block_n, int block_m, const CUtensorMap&
 __global__ void __launch_bounds__(256)
 wgrad_finish_kernel(const float* __restrict__ packed, float* __restrict__ dw, int c_out, int c_in, int taps,
                     long long tap_stride, long long row_stride, const float* __restrict__ gscale_buf) {
+  pdl_enter();
   const float inv = gscale_buf != nullptr ? gscale_buf[1] : 1.f;
   const int total = c_out * c_in;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -359,7 +364,7 @@ cudaError_t launch_wgrad_finish(const float* packed, float* dw, int c_out, int c
   long long blocks = (total + 255) / 256;
   if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
   if (blocks < 1) blocks = 1;
-  wgrad_finish_kernel<<<(int)blocks, 256, 0, stream>>>(packed, dw, c_out, c_in, taps, tap_stride, row_stride,
+  launch_k(wgrad_finish_kernel, dim3((int)blocks), dim3(256), 0, stream, packed, dw, c_out, c_in, taps, tap_stride, row_stride,
                                                        gscale_buf);
   return cudaGetLastError();
 }

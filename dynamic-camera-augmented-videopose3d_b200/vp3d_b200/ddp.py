@@ -252,6 +252,10 @@ def enable_grad_sync(group=None, reserve_sms=0, dynamic_schedule=None, compress=
             training.grad_finish_hook = _active.finish
             training.grad_begin_hook = _active.begin
             training.grad_alloc = _active.alloc
+            # an optimiser update inside the backward (FusedAdam.update_in_backward) follows the exchange of its gradient
+            # on the communication stream; the small tensors are exchanged at the end and left to optimizer.step()
+            training.update_stream = lambda sync=_active: sync.comm
+            training.update_filter = lambda q, sync=_active: id(q) in sync.large_ids
             return _active
     if reserve_sms > 0 and torch.cuda.is_available():
         from . import native
@@ -269,6 +273,8 @@ def enable_grad_sync(group=None, reserve_sms=0, dynamic_schedule=None, compress=
     training.grad_finish_hook = _active.finish
     training.grad_begin_hook = None
     training.grad_alloc = None
+    training.update_stream = None
+    training.update_filter = (lambda q: False) if _active.world > 1 else None   # NCCL: updates wait for finish()
     return _active
 
 
@@ -283,6 +289,8 @@ def disable_grad_sync():
     training.grad_finish_hook = None
     training.grad_begin_hook = None
     training.grad_alloc = None
+    training.update_stream = None
+    training.update_filter = None
 
 
 def enable_sync_bn(group=None, on=True):

@@ -98,6 +98,7 @@ _SIGNATURES = {
     'vp3d_device_info': (C.c_int, [C.POINTER(C.c_int)] * 3),
     'vp3d_set_sm_limit': (C.c_int, [C.c_int]),
     'vp3d_set_pair_mode': (C.c_int, [C.c_int]),
+    'vp3d_set_pdl': (C.c_int, [C.c_int]),
     'vp3d_set_sched_mode': (C.c_int, [C.c_int]),
     'vp3d_conv_block_fwd': (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     'vp3d_pack_rows': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),

@@ -27,6 +27,16 @@ grad_finish_hook = None  # ... and once at the end of the backward (waits for th
 grad_begin_hook = None   # ... and once at its start
 grad_alloc = None        # set by vp3d_b200.ddp (peer exchange): grad_alloc(parameter) -> flat fp32 buffer the gradient of
                          # that parameter is to be written into (a slot of the exchange buffer), or None
+# Optimiser update inside the backward (vp3d_b200.optim.FusedAdam.update_in_backward): param_update_hook([(parameter,
+# gradient), ...]) applies the update of those parameters NOW, on the current stream. The backward calls it on a third
+# stream the moment a gradient is final and nothing of this backward reads the parameter (or its packed operand) again, so
+# the HBM-bound update runs beside the tensor-bound weight-gradient GEMMs of the earlier layers instead of after the
+# backward. `update_stream` / `update_filter` are set by the data-parallel exchange (the update of an exchanged gradient
+# must follow its all-reduce: same stream; gradients exchanged at the end of the backward are left to optimizer.step()).
+param_update_hook = None
+update_stream = None     # callable -> torch.cuda.Stream, or None (a private stream per device)
+update_filter = None     # callable(parameter) -> bool, or None (every parameter)
+_update_streams = {}
 sync_bn_group = None     # process group over which train-mode BatchNorm statistics are summed (None: per replica)
 # vp3d_bn_finalize_act_fwd (statistics -> scale/shift inside the apply pass, one launch less per layer) is available but
 # off: same-box A/B at batch 1024 gave 2.01-2.03 ms per step with it against 1.97 without -- every block of the apply pass
@@ -44,6 +54,12 @@ fused_expand = os.environ.get('VP3D_FUSED_EXPAND', '1') != '0'
 # vp3d_bn_finalize in the tail of the producing GEMM (last CTA done; vp3d_conv_args.fin): 8 launches and their dependent-
 # launch gaps less per training forward. VP3D_FIN_IN_GEMM=0 restores the stand-alone finalize launch.
 finalize_in_gemm = os.environ.get('VP3D_FIN_IN_GEMM', '1') != '0'
+# Issue order of a layer's two backward GEMMs. Both become ready when the layer's dz exists and cannot share an SM (each
+# is a persistent kernel with ~200 KB of shared memory), so one runs after the other whatever the streams say. 'after':
+# the weight-gradient GEMM is made to wait for the data-gradient GEMM -- it then runs on the side stream BESIDE the HBM-bound
+# BatchNorm backward of the layer below (which needs the data gradient and is what the critical path continues with);
+# 'before': both are released together and the hardware picks (VP3D_WGRAD_ORDER).
+wgrad_after_dgrad = os.environ.get('VP3D_WGRAD_ORDER', 'after') != 'before'
 debug_keep_saved = False  # tests: keep the last forward's saved per-layer tensors in `debug_last_saved`
 debug_last_saved = None
 
@@ -380,6 +396,39 @@ class _StackTrainFn(torch.autograd.Function):
             if hook is not None:
                 hook(param, g)
 
+        upd = None
+        if param_update_hook is not None:
+            if update_stream is not None:
+                upd = update_stream()
+            else:
+                upd = _update_streams.get(dy.device.index)
+                if upd is None:
+                    upd = _update_streams[dy.device.index] = torch.cuda.Stream(dy.device)
+        early = []      # parameters whose gradient has been issued and which this backward does not read again
+
+        def release(*params):
+            if upd is not None:
+                early.extend(q for q in params if update_filter is None or update_filter(q))
+
+        def flush_early():
+            """Optimiser update of the released parameters on the update stream, after everything issued so far on the
+            main and the side stream (the gradient's producer; the last reader of the packed weights)."""
+            if upd is None or not early:
+                return
+            pairs = [(q, grads[id(q)]) for q in early if id(q) in grads]
+            early[:] = [q for q in early if id(q) not in grads]
+            if not pairs:
+                return
+            evs = [torch.cuda.Event()]
+            evs[0].record(main)
+            if side is not None:
+                evs.append(torch.cuda.Event())
+                evs[1].record(side)
+            with torch.cuda.stream(upd):
+                for ev in evs:
+                    upd.wait_event(ev)
+                param_update_hook(pairs)
+
         def on_side(fn, *tensors):
             """Runs fn() on the side stream after everything issued so far on the main stream."""
             if side is None:
@@ -403,6 +452,7 @@ class _StackTrainFn(torch.autograd.Function):
         dzs, dbias = ops.grad_pack_rows(dt, dy2, SHRINK_PAD, gscale, want_col_sum=True,
                                         col_sum_out=_slot(model.shrink.bias))
         done(model.shrink.bias, dbias)
+        release(model.shrink.bias)
         rows = n * ctx.t_last
 
         def shrink_wgrad():
@@ -413,11 +463,15 @@ class _StackTrainFn(torch.autograd.Function):
             done(model.shrink.weight,
                  ops.wgrad_finish(packed, n_out, model.shrink.in_channels, 1, SHRINK_PAD, c_pad, gscale,
                                   out=_slot(model.shrink.weight)))
-        on_side(shrink_wgrad, dzs, gscale)
+        if not wgrad_after_dgrad:
+            on_side(shrink_wgrad, dzs, gscale)
         g = torch.empty((n, ctx.t_last, c_pad), dtype=dzs.dtype, device=dy.device)
         k_shrink = ctx.w_shrink.shape[0]      # forward-packed [n_out_pad][c_pad], read as W^T
         ops.conv_block(dt, dzs, (1, rows, SHRINK_PAD, SHRINK_PAD, rows * SHRINK_PAD), ctx.w_shrink, 1, 0, k_shrink, rows,
                        g, (c_pad, rows * c_pad), w_mn_major=(c_pad, 0))
+        if wgrad_after_dgrad:
+            on_side(shrink_wgrad, dzs, gscale)
+        release(model.shrink.weight)
 
         # ---- blocks and the expand layer, last to first. `g` is the gradient wrt the current layer's output.
         for idx in range(len(layers) - 1, -1, -1):
@@ -442,14 +496,19 @@ class _StackTrainFn(torch.autograd.Function):
                     done(L.bn.bias, dbeta)
                     done(L.conv.weight, dw)
                 on_side(expand_grads, g)
+                release(L.bn.weight, L.bn.bias, L.conv.weight)
                 break
             dz, dgamma, dbeta = ops.bn_act_bwd(dt, g, L.z, L.scale, L.shift, L.mean, L.invstd, rows, L.bn.num_features,
                                                L.drop, gscale, count=L.count, group=sync_bn_group, sums=sums_all[idx],
                                                out=(_slot(L.bn.weight), _slot(L.bn.bias)))
             done(L.bn.weight, dgamma)
             done(L.bn.bias, dbeta)
-            on_side(lambda L=L, dz=dz: done(L.conv.weight, _weight_grad(dt, L, dz, n, c_pad, gscale, keep, arena)), dz)
+            release(L.bn.weight, L.bn.bias)
+            wgrad = lambda L=L, dz=dz: done(L.conv.weight, _weight_grad(dt, L, dz, n, c_pad, gscale, keep, arena))
+            if idx == 0 or not wgrad_after_dgrad:
+                on_side(wgrad, dz)
             if idx == 0:
+                release(L.conv.weight)
                 break  # no gradient wrt the 2-D keypoints (the reference never asks for one, run.py:458-485)
             if L.res_of is not None:
                 # second convolution of a block: its output gradient g also feeds the residual source; that fan-in is
@@ -462,8 +521,16 @@ class _StackTrainFn(torch.autograd.Function):
                 gate = (below['a'], below['keep_scale']) if below is not None else None
                 g = _data_grad(dt, L, dz, n, c_pad, fan_in=g_block, fan_rows=fan_rows, fan_off=fan_off, fan_mul=fan_mul,
                                gate=gate)
+            if wgrad_after_dgrad:
+                on_side(wgrad, dz)
+            # the data gradient was the last reader of this layer's packed weights
+            release(L.conv.weight)
+            flush_early()
+        flush_early()
         if side is not None:
             main.wait_stream(side)
+        if upd is not None:
+            main.wait_stream(upd)
         if grad_finish_hook is not None:
             grads.update(grad_finish_hook() or {})
         keep.clear()

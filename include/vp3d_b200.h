@@ -44,6 +44,11 @@ int vp3d_set_sm_limit(int sms);
  * environment variable VP3D_SCHED ("dynamic"). Mode 2 ("dynamic-all") applies it to every pair-kernel launch without
  * statistics whatever its size (tests). Results are identical in all modes. */
 int vp3d_set_sched_mode(int mode);
+/* Programmatic dependent launch: 1 (default; environment variable VP3D_PDL=0 turns it off) launches every kernel of the
+ * library with cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel on the stream becomes resident and
+ * runs its prologue while this one drains (each kernel orders its own global-memory accesses with griddepcontrol.wait);
+ * 0 = plain stream order. Results are identical. No reference counterpart. */
+int vp3d_set_pdl(int on);
 /* Which K1 kernel vp3d_conv_block_fwd launches: 0 = always the single-CTA kernel, 1 = the CTA-pair kernel
  * (tcgen05.mma.cta_group::2) for supported launches of at least two waves of tiles (default), 2 = for every supported
  * launch. Initial value from the environment variable VP3D_K1_2CTA ("0", "force"). */

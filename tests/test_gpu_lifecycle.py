@@ -137,7 +137,8 @@ def test_train_eval_checkpoint_resume_like_run_py(tmp_path):
         if a.dtype.is_floating_point:
             # in norm, not element by element: where a gradient is ~0 Adam's update is +-lr whatever its size, so the
             # order of the fp32 atomics moves single weights by a few lr (1e-3) between two runs
-            assert (a - b).norm().item() <= 2e-2 * max(a.norm().item(), 1e-3), k
+            # (tensors that start at 0 -- BatchNorm biases -- consist of nothing but such +-lr steps: RMS allowance 0.5 lr)
+            assert (a - b).norm().item() <= 2e-2 * a.norm().item() + 0.5 * LR * a.numel() ** 0.5, k
             assert (a - b).abs().max().item() <= 8 * LR + 2e-2 * a.abs().max().item(), k
         else:
             assert int(a) == int(b), k

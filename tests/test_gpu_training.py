@@ -446,6 +446,52 @@ def test_fused_adam_matches_torch_adam_and_refreshes_packed_operands():
         assert (sa[idx]['max_exp_avg_sq'] - sc[idx]['max_exp_avg_sq']).abs().max().item() < 1e-9
 
 
+@pytest.mark.parametrize('cls,T', [(TemporalModelOptimized1f, 27), (TemporalModel, 33)])
+def test_update_in_backward_gives_the_same_parameters(cls, T):
+    """FusedAdam.update_in_backward(): every parameter of the stack is updated INSIDE the backward (on its own stream,
+    beside the weight-gradient GEMMs); the values after step() must be bit-identical to the ordinary step() fed with the
+    same gradients, and the packed operands must have followed."""
+    from vp3d_b200.optim import FusedAdam
+    fw = [3, 3, 3]
+    sd = otm.init_state(17, 2, 17, fw, channels=1024, seed=61)
+    g = torch.Generator().manual_seed(62)
+    x = (torch.rand(64, T, 17, 2, generator=g) * 2 - 1).cuda()
+    tgt = (torch.randn(64, T - 26, 17, 3, generator=g) * 0.3).cuda()
+    ma = _build(cls, sd, fw, 1024, 'fp16')
+    mb = _build(cls, sd, fw, 1024, 'fp16')
+    oa = FusedAdam(ma.parameters(), lr=1e-3, amsgrad=True)
+    ob = FusedAdam(mb.parameters(), lr=1e-3, amsgrad=True)
+    for step in range(3):
+        oa.zero_grad()
+        mpjpe(ma(x), tgt).backward()
+        ob.update_in_backward()
+        try:
+            ob.zero_grad()
+            loss = mpjpe(mb(x), tgt)
+            before = [q.detach().clone() for q in mb.parameters()]
+            loss.backward()
+            torch.cuda.synchronize()
+            moved = [not torch.equal(q, b) for q, b in zip(mb.parameters(), before)]
+            assert all(moved), 'parameters the backward did not update: %s' % [
+                k for (k, _), m in zip(mb.named_parameters(), moved) if not m]
+            after_backward = [q.detach().clone() for q in mb.parameters()]
+            ob.step()
+            for q, b in zip(mb.parameters(), after_backward):
+                assert torch.equal(q, b), 'step() updated a parameter a second time'
+        finally:
+            ob.update_in_backward(False)
+        for pa, pb in zip(ma.parameters(), mb.parameters()):
+            pa.grad.copy_(pb.grad)           # the same gradients through the ordinary step
+        oa.step()
+        for (k, pa), pb in zip(ma.named_parameters(), mb.parameters()):
+            assert torch.equal(pa, pb), (step, k)
+    for w in (mb.expand_conv.weight, mb.layers_conv[0].weight, mb.shrink.weight):
+        (key, (packed, version)), = w.__dict__['_vp3d_packed'].items()
+        assert version == w._version
+        assert torch.equal(packed, ops.pack_conv_weight(key[0], w, key[1], key[2]))
+    assert float(ob.state[mb.expand_conv.weight]['step']) == 3
+
+
 @pytest.mark.parametrize('kw', [dict(causal=True), dict(dense=True)])
 def test_dilated_variants_train_step_against_emulation(kw):
     """Causal and dense (ablation) TemporalModel in train mode: the residual slice moves (pad + shift) and the dense
