@@ -194,7 +194,7 @@ def infer_parity(model, x_host, x_dev, picks):
     tiles = x_dev.shape[0] * ((x_dev.shape[1] - 8 + 127) // 128) * 4      # block-1 launch: rows / 128 x 1024 / 256
     return {'rel_fro': rel_fro(y, ref), 'mpjpe_delta_mm': d_mm, 'within_tolerance': bool(rel_fro(y, ref) <= 1e-3 and d_mm <= 1e-2), 'max_abs': float((y - ref).abs().max()),
             'n_frames': int(y.shape[0] * y.shape[1]), 'sequences': list(picks), 'frames_per_sequence': int(x_dev.shape[1]),
-            'kernel': 'conv_gemm_pair_kernel (cta_group::2)' if tiles >= 2 * sm and os.environ.get('VP3D_K1_2CTA') != '0'
+            'kernel': 'conv_gemm_pair_kernel (cta_group::2)' if 2 * tiles >= sm and os.environ.get('VP3D_K1_2CTA') != '0'
                       else 'conv_gemm_kernel',
             'oracle': 'oracle/temporal_model.py forward (fp32 torch CPU), pinned to the reference by tests/golden',
             'tolerance': {'rel_fro': 1e-3, 'mpjpe_delta_mm': 1e-2},

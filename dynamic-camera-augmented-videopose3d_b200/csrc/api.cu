@@ -86,7 +86,7 @@ struct DeviceInfo {
 // Upper bound on the SMs the persistent kernels size their grids for (0: all). Data-parallel training sets it a few
 // SMs below the device's count so that NCCL's all-reduce CTAs find free SMs next to a running GEMM instead of queueing
 // behind it (or, worse, a statically scheduled persistent GEMM queueing behind them).
-// K1 on CTA pairs: 0 = never, 1 = launches of at least two waves of tiles (default), 2 = whenever the launch is
+// K1 on CTA pairs: 0 = never, 1 = launches of at least half a wave of tiles (default), 2 = whenever the launch is
 // supported (tests on small shapes). Initial value from VP3D_K1_2CTA ("0" / "force").
 int g_pair_mode = [] {
   const char* e = std::getenv("VP3D_K1_2CTA");
@@ -391,7 +391,10 @@ int vp3d_conv_block_fwd(const vp3d_conv_args* a, void* stream) {
   if (want_epi && !(use_pairs && pair_ok))
     return fail(VP3D_ERR_UNSUPPORTED, "fused dropout / side input need the CTA-pair kernel (16-bit operands and output, "
                 "block_n 256, no dyn_offsets, cluster launches available on this device)");
-  if (use_pairs && pair_ok && (use_pairs == 2 || total_tiles >= 2LL * dev->sm_count)) {
+  // (mode 1: from half a wave of tiles on. Measured on the training step, where the layers of 96 - 288 tiles moved from
+  // the single-CTA kernel to pairs: 1.766 -> 1.752 ms -- a pair reads each weight tile once for two row tiles, and
+  // launches of this size are bound by L2 -> shared-memory traffic, not by the tensor pipe)
+  if (use_pairs && pair_ok && (use_pairs == 2 || 2 * total_tiles >= (long long)dev->sm_count)) {
     p.dyn_sched = (a->stat_sum == nullptr &&
                    (g_sched_mode == 2 || (g_sched_mode == 1 && total_tiles >= 2LL * dev->sm_count))) ? 1 : 0;
     CUtensorMap tmBh = tmB;    // MN-major: the same [64 k-rows][64 columns] boxes, two per CTA

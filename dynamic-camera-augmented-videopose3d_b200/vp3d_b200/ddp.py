@@ -117,7 +117,10 @@ class PeerGradSync:
         params = [p for p in params if p.requires_grad]
         assert params and all(p.is_cuda and p.dtype == torch.float32 for p in params), 'fp32 CUDA parameters'
         dev = params[0].device
-        self.ctas = int(ctas if ctas is not None else os.environ.get('VP3D_DDP_CTAS', 8))
+        # CTAs of the exchange kernel (= SMs the backward's GEMM grids leave free). Measured (profiles/README.md): through
+        # the switch 4 CTAs already move 67.8 MB in 0.16 ms at 8 GPUs (a rank reduces 1/8 of a slice) and the step is
+        # 1.91 ms with 4 against 1.97 with 8; at 2 GPUs a rank reduces half of every slice and 8 CTAs are worth their SMs
+        self.ctas = int(ctas if ctas is not None else os.environ.get('VP3D_DDP_CTAS', 8 if self.world <= 2 else 4))
         assert 2 <= self.ctas <= 64 and self.ctas % 2 == 0
         self.reserve = int(reserve_sms if reserve_sms is not None else os.environ.get('VP3D_DDP_RESERVE', self.ctas))
         up = lambda n: (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN

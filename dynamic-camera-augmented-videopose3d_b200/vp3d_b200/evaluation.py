@@ -92,3 +92,31 @@ def run_evaluation(model, generators_by_action, reference_quirk=False):
     if infos_all and all(k in infos_all[0] for k in CAM_KEYS):
         out['pmcc'] = camera_motion_pmcc(torch.cat(e1_all), infos_all, torch.cat(motion_all), reference_quirk)
     return out
+
+
+@torch.no_grad()
+def sliding_window(model, inputs_2d, inputs_cam, window_size, max_windows=None):
+    """The sliding-window evaluator of the camera-aware sibling models (CamLSTM.py:33-44, CamTransformer.py:72-91; called
+    from run.py:511-512,518-519) for ANY model with their `model(win_2d, win_cam) -> (n, J_out, F_out)` protocol: every
+    window of `window_size` consecutive frames of the ONE sequence in `inputs_2d` (1, T, J, F) / `inputs_cam` (1, T, 3, 4)
+    becomes a batch element, in frame order. Returns (1, T - window_size + 1, J_out, F_out).
+    The windows are overlapping strided views of the sequence (no gather kernel: frame i of window w is frame w + i);
+    `max_windows` bounds how many are materialised per model call (the reference materialises all of them at once)."""
+    _, t, j, _ = inputs_2d.shape
+    n_windows = t - window_size + 1
+    if n_windows <= 0:
+        raise ValueError("window_size larger than sequence length")        # CamLSTM.py:36-37
+
+    def windows(x, lo, hi):
+        seq = x[0]
+        s = seq.stride()
+        return seq.as_strided((hi - lo, window_size) + tuple(seq.shape[1:]), (s[0], s[0]) + tuple(s[1:]),
+                              seq.storage_offset() + lo * s[0])
+
+    step = n_windows if not max_windows else int(max_windows)
+    outs = []
+    for lo in range(0, n_windows, step):
+        hi = min(lo + step, n_windows)
+        outs.append(model(windows(inputs_2d, lo, hi), windows(inputs_cam, lo, hi)))
+    out = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+    return out.reshape(1, n_windows, out.shape[-2], out.shape[-1])

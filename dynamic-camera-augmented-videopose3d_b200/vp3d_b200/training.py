@@ -405,6 +405,7 @@ class _StackTrainFn(torch.autograd.Function):
                 if upd is None:
                     upd = _update_streams[dy.device.index] = torch.cuda.Stream(dy.device)
         early = []      # parameters whose gradient has been issued and which this backward does not read again
+        upd_used = []   # something was issued on the update stream (only then is it joined: it may be outside a capture)
 
         def release(*params):
             if upd is not None:
@@ -428,6 +429,7 @@ class _StackTrainFn(torch.autograd.Function):
                 for ev in evs:
                     upd.wait_event(ev)
                 param_update_hook(pairs)
+            upd_used.append(True)
 
         def on_side(fn, *tensors):
             """Runs fn() on the side stream after everything issued so far on the main stream."""
@@ -529,7 +531,7 @@ class _StackTrainFn(torch.autograd.Function):
         flush_early()
         if side is not None:
             main.wait_stream(side)
-        if upd is not None:
+        if upd is not None and upd_used:
             main.wait_stream(upd)
         if grad_finish_hook is not None:
             grads.update(grad_finish_hook() or {})

@@ -50,7 +50,7 @@ int vp3d_set_sched_mode(int mode);
  * 0 = plain stream order. Results are identical. No reference counterpart. */
 int vp3d_set_pdl(int on);
 /* Which K1 kernel vp3d_conv_block_fwd launches: 0 = always the single-CTA kernel, 1 = the CTA-pair kernel
- * (tcgen05.mma.cta_group::2) for supported launches of at least two waves of tiles (default), 2 = for every supported
+ * (tcgen05.mma.cta_group::2) for supported launches of at least half a wave of tiles (default), 2 = for every supported
  * launch. Initial value from the environment variable VP3D_K1_2CTA ("0", "force"). */
 int vp3d_set_pair_mode(int mode);
 

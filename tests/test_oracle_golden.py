@@ -154,3 +154,34 @@ def test_unchunked_generator_composition_against_reference_generator():
             np.testing.assert_allclose(want2[None], z['b2d_%s_%d' % (tag, i)], atol=2e-6)
             np.testing.assert_allclose((xc - xc[:, :1])[None], z['b3d_%s_%d' % (tag, i)], atol=2e-6)
             assert z['cam_%s_%d' % (tag, i)].shape == (1, X.shape[0] + 2 * pad, 3, 4)
+
+
+def test_lifter_oracle_matches_the_reference_fixture():
+    """oracle/lifter.py (StackedPoseLifter.py:37-56, CamLSTM.py:33-44) against tests/golden/lifter.npz, which
+    tests/golden/make_golden_lifter.py produced by importing the real reference."""
+    from oracle import lifter as ol
+    z = load_golden('lifter.npz')
+    J, F = 17, 3
+    sd = {k: v.clone().requires_grad_(True) for k, v in ol.init_state(J, F, 3, 256, seed=21).items()}
+    assert sorted(sd) == list(z['state_keys'])
+    a, b, tgt = (torch.from_numpy(z[k]) for k in ('a', 'b', 'tgt'))
+    y = ol.forward(sd, a, b, J, F)
+    assert torch.equal(y.detach(), torch.from_numpy(z['y']))
+    assert torch.equal(ol.forward(sd, a.squeeze(), b.squeeze(), J, F).detach(), torch.from_numpy(z['y_squeezed']))
+    loss = torch.mean(torch.linalg.norm(y - tgt, dim=3))
+    loss.backward()
+    assert abs(loss.item() - float(z['loss'])) < 1e-6
+    for k, p in sd.items():
+        if 'grad/' + k in z.files:
+            np.testing.assert_allclose(p.grad.numpy(), z['grad/' + k], rtol=1e-4, atol=1e-7)
+        else:
+            np.testing.assert_allclose(p.grad.numpy()[::8, ::8], z['grad_sample/' + k], rtol=1e-4, atol=1e-7)
+
+    def probe(win_2d, win_cam):
+        w = torch.arange(1, win_2d.shape[1] + 1, dtype=win_2d.dtype).view(1, -1, 1, 1)
+        s2 = (win_2d * w).sum(dim=(1, 3))
+        sc = (win_cam * w).sum(dim=(1, 2, 3)).view(-1, 1)
+        return torch.stack([s2, s2 + sc, s2 - sc], dim=-1)
+    x2, cam = torch.from_numpy(z['sw_x2']), torch.from_numpy(z['sw_cam'])
+    np.testing.assert_allclose(ol.sliding_window(probe, x2, cam, 9, J, 3).numpy(), z['sw_out_w9'], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(ol.sliding_window(probe, x2, cam, 39, J, 3).numpy(), z['sw_out_w40'], rtol=1e-5, atol=1e-5)
