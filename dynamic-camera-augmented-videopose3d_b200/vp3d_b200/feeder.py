@@ -67,6 +67,23 @@ class DeviceWindowFeeder:
         self._idx_dev = [torch.empty((batch_size, 2), dtype=torch.int64, device=dev) for _ in range(2)]
         self._idx_copied = [None, None]   # event recorded behind the H2D copy that last read each pinned buffer
         self._flip = 0
+        self._bound = None       # (batch_2d, batch_3d) buffers every full batch is written into (bind_outputs)
+
+    def bind_outputs(self, batch_2d=None, batch_3d=None):
+        """Write every full batch into these caller-owned buffers instead of fresh tensors -- e.g. the static inputs of a
+        captured training step (vp3d_b200.graphs.GraphedTrainStep), so that the kernel's output IS the graph's input and
+        no device-to-device copy sits between the feeder and the step. Shapes (batch_size, window, J, 2) and
+        (batch_size, chunk_length, J, 3), fp32, contiguous, on the feeder's device; None unbinds."""
+        if batch_2d is None:
+            self._bound = None
+            return self
+        J = self.joints
+        want2, want3 = (self.batch_size, self.window, J, 2), (self.batch_size, self.chunk_length, J, 3)
+        for t, want in ((batch_2d, want2), (batch_3d, want3)):
+            assert tuple(t.shape) == want and t.dtype == torch.float32 and t.is_contiguous() and t.device == torch.device(
+                self.dev), 'bind_outputs: expected a contiguous fp32 %s on %s' % (want, self.dev)
+        self._bound = (batch_2d, batch_3d)
+        return self
 
     # -- generator protocol of the reference ------------------------------------------------------------------
     def num_frames(self):
@@ -105,8 +122,11 @@ class DeviceWindowFeeder:
         seq32 = idx[:n, 0].to(torch.int32).contiguous()
         start = idx[:n, 1].contiguous()
         J = self.joints
-        x2d = torch.empty((n, self.window, J, 2), dtype=torch.float32, device=self.dev)
-        tgt = torch.empty((n, self.chunk_length, J, 3), dtype=torch.float32, device=self.dev)
+        if self._bound is not None and n == self.batch_size:
+            x2d, tgt = self._bound
+        else:
+            x2d = torch.empty((n, self.window, J, 2), dtype=torch.float32, device=self.dev)
+            tgt = torch.empty((n, self.chunk_length, J, 3), dtype=torch.float32, device=self.dev)
         cams = torch.empty((n, self.window, 3, 4), dtype=torch.float32, device=self.dev) if self.want_cameras else None
         a = native.WindowArgs()
         a.x_world, a.q, a.t, a.cam = self.x.data_ptr(), self.q.data_ptr(), self.t.data_ptr(), self.cam.data_ptr()

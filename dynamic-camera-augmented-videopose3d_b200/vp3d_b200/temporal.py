@@ -18,6 +18,13 @@ N_TILE_NARROW = 64
 # eval-mode residual of the dilated model through the TMA side input of the pair kernel (A/B switch; measured in
 # profiles/README.md)
 RES_VIA_TMA = os.environ.get('VP3D_RES_TMA', '0') == '1'
+# fp16 activations saturate at 65,504: a checkpoint whose residual stream exceeds that (huge BatchNorm scales) would yield
+# inf / NaN without a word. The guard looks at the OUTPUT (an overflow anywhere in the stack propagates to it as inf / NaN)
+# of an eval forward with fp16 operands and finite input -- one device-to-host read, so by default only on the first
+# forward after the operands of a model were (re)packed, never inside a stream capture:
+#   'first' (default) raise FloatingPointError    'always' check every forward    'bf16' switch the model to bf16 operands
+#   (8 more exponent bits, 3 fewer mantissa bits) with a warning and run again    'off'
+FP16_GUARD = os.environ.get('VP3D_FP16_GUARD', 'first')
 
 
 def _round_up(v, m):
@@ -65,6 +72,7 @@ class PackedStack:
         self.shrink_scale = None
         self.shrink_shift = torch.zeros(self.n_out_pad, dtype=torch.float32, device=dev)
         self.shrink_shift[:self.n_out] = model.shrink.bias.detach().float()
+        self.range_checked = False     # FP16_GUARD: the output of these operands has been looked at once
 
 
 def _param_versions(model):
@@ -175,4 +183,18 @@ def forward_eval(model, x, dt=None):
 
     y, t = _run_layer(dt, h, n, t, pk.c_pad, pk.w_shrink, LayerPlan(1), pk.shrink_scale, pk.shrink_shift, False,
                       out_f32=True, n_valid=pk.n_out, block_n=N_TILE_NARROW)
+    if dt == native.F16 and FP16_GUARD != 'off' and (FP16_GUARD == 'always' or not pk.range_checked):
+        if not torch.cuda.is_current_stream_capturing():
+            pk.range_checked = True
+            if not bool(torch.isfinite(y).all()) and bool(torch.isfinite(x).all()):
+                if FP16_GUARD == 'bf16':
+                    import warnings
+                    warnings.warn('vp3d_b200: fp16 activations overflowed (|x| > 65504) in this model; switching it to '
+                                  'bf16 operands (model.operand_dtype = "bf16")')
+                    model.operand_dtype = 'bf16'
+                    return forward_eval(model, x, native.BF16)
+                raise FloatingPointError(
+                    'vp3d_b200: the forward produced inf / NaN from finite input with fp16 operands -- an activation '
+                    'exceeded the fp16 range (65504). Set model.operand_dtype = "bf16" (or "tf32"), or VP3D_FP16_GUARD=bf16 '
+                    'to switch automatically; VP3D_FP16_GUARD=off disables this check.')
     return y

@@ -231,3 +231,36 @@ def test_host_pipelines_return_what_the_model_returns():
         ev.synchronize()
         assert torch.equal(y, w)
     assert torch.equal(pipe.infer(batches[1]), want[1])
+
+
+def test_fp16_saturation_is_reported_not_silent(monkeypatch):
+    """A checkpoint whose BatchNorm scales push the residual stream past the fp16 range (65504): the first eval forward
+    must raise (default guard) or, with the bf16 fallback, switch the model to bf16 operands and return finite values
+    that agree with the fp32 oracle."""
+    from vp3d_b200 import temporal
+    fw = [3, 3, 3]
+    sd = otm.init_state(17, 2, 17, fw, channels=256, seed=91)
+    for k in list(sd):
+        if k.endswith('_bn.weight') or '_bn.' in k and k.endswith('.weight'):
+            sd[k] = sd[k] * 400.0
+    g = torch.Generator().manual_seed(92)
+    x = (torch.rand(2, 60, 17, 2, generator=g) * 2 - 1)
+    ref = otm.forward(sd, x, fw)
+    assert torch.isfinite(ref).all() and ref.abs().max() > 1e5      # far outside fp16, fine in fp32
+
+    def build():
+        m = TemporalModel(17, 2, 17, fw, channels=256)
+        m.load_state_dict(sd)
+        m.operand_dtype = 'fp16'
+        return m.cuda().eval()
+    monkeypatch.setattr(temporal, 'FP16_GUARD', 'first')
+    with pytest.raises(FloatingPointError):
+        with torch.no_grad():
+            build()(x.cuda())
+    monkeypatch.setattr(temporal, 'FP16_GUARD', 'bf16')
+    m = build()
+    with pytest.warns(UserWarning, match='bf16'):
+        with torch.no_grad():
+            y = m(x.cuda())
+    assert m.operand_dtype == 'bf16' and torch.isfinite(y).all()
+    assert ((y.cpu() - ref).norm() / ref.norm()).item() < 3e-2
