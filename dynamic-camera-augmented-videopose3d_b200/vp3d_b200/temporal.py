@@ -25,6 +25,7 @@ RES_VIA_TMA = os.environ.get('VP3D_RES_TMA', '0') == '1'
 #   'first' (default) raise FloatingPointError    'always' check every forward    'bf16' switch the model to bf16 operands
 #   (8 more exponent bits, 3 fewer mantissa bits) with a warning and run again    'off'
 FP16_GUARD = os.environ.get('VP3D_FP16_GUARD', 'first')
+NARROW_TILES = os.environ.get('VP3D_NARROW', '1') != '0'    # A/B switch of the 64-column tiles for launches of few tiles
 
 
 def _round_up(v, m):
@@ -131,7 +132,7 @@ def _run_layer(dt, x, n, t_in, c_in_pad, w, plan, scale, shift, relu, res=None, 
         # few output tiles (the 1f model's last blocks: 3 or 1 frames per sample): 64-wide column tiles give 4x more
         # CTAs than SMs would otherwise be left idle by 128 x 256 tiles
         tiles = a_view[0] * ((rows_out + 127) // 128) * (n_pad // N_TILE)
-        if tiles * 4 <= native.sm_count(x.device):          # the narrow tiles still fit in one wave
+        if NARROW_TILES and tiles * 4 <= native.sm_count(x.device):          # the narrow tiles still fit in one wave
             block_n = N_TILE_NARROW
     side_kw = {}
     if (RES_VIA_TMA and res is not None and plan.res_mul == 1 and block_n == N_TILE and not out_f32 and

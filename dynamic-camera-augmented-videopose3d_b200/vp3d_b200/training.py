@@ -18,7 +18,7 @@ import os
 import torch
 
 from . import native, ops
-from .temporal import K_ALIGN, N_TILE, LayerPlan, _round_up, _run_layer, resolve_dtype
+from .temporal import K_ALIGN, N_TILE, NARROW_TILES, LayerPlan, _round_up, _run_layer, resolve_dtype
 
 SHRINK_PAD = 128      # shrink-layer output channels are padded to one 128-row MMA tile for its weight gradient
 grad_ready_hook = None   # set by vp3d_b200.ddp: called as hook(parameter, gradient) as soon as a gradient is issued
@@ -315,7 +315,8 @@ def _data_grad(dt, L, dz, n, c_pad, fan_in=None, fan_rows=0, fan_off=0, fan_mul=
     block_n = 256 if cin_pad % 256 == 0 else 64
     if gate is not None:
         assert block_n == 256
-    elif block_n == 256 and ((n * L.t_out + 127) // 128) * (taps * cin_pad // 256) * 4 <= native.sm_count(dz.device):
+    elif NARROW_TILES and block_n == 256 and ((n * L.t_out + 127) // 128) * (taps * cin_pad // 256) * 4 <= native.sm_count(
+            dz.device):
         block_n = 64    # few tiles: narrower column tiles keep all SMs busy (while they still fit in one wave)
     if s > 1 or taps == 1:
         if s > 1 and L.t_in != taps * L.t_out:

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, 'dynamic-camera-augmented-videopose3d_b200'))
 from vp3d_b200 import native, ops
 dev = torch.device('cuda')
-rows, C = 82944, 1024
+rows, C = (int(sys.argv[1]) if len(sys.argv) > 1 else 82944), 1024
 z = torch.randn(rows, C, device=dev).half()
 g = torch.randn(rows, C, device=dev).half()
 one = torch.rand(C, device=dev) + 0.5
