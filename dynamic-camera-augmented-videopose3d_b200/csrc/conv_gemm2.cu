@@ -15,6 +15,8 @@
 // mode statistics, at most 1024 output channels when a scale / shift is applied (the whole per-channel table sits in
 // shared memory because a pair changes column tile from tile to tile). fp32 output (shrink layer), streaming offsets
 // and TF32 stay on conv_gemm_kernel, as do launches of less than two waves.
+#include <cstdlib>
+
 #include "ptx.cuh"
 #include "kernels.h"
 #include "pdl.cuh"
@@ -44,7 +46,7 @@ constexpr int kOutBufBytes = kEpi * 32 * 64;      // one 32 x 32 staging tile (6
 // fetched INTO the staging buffer its result is later written over, two chunks ahead of its use.
 template <int EPI>
 struct EpiCfg {
-  static constexpr int kOutBufs = EPI ? 3 : VP3D_PAIR_OUTBUFS;
+  static constexpr int kOutBufs = EPI == 1 ? 3 : VP3D_PAIR_OUTBUFS;
   static constexpr int kOutStageBytes = kOutBufs * kOutBufBytes;
 };
 constexpr int kBarBytes = 512;
@@ -64,6 +66,10 @@ struct Fmt<VP3D_F16> {
     return *reinterpret_cast<uint32_t*>(&h);
   }
   static __device__ __forceinline__ float2 unpack(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
+  // 0xFFFF in every 16-bit lane whose value is > 0
+  static __device__ __forceinline__ uint32_t gt0_mask(uint32_t u) {
+    return __hgt2_mask(*reinterpret_cast<__half2*>(&u), __half2(__ushort_as_half(0), __ushort_as_half(0)));
+  }
 };
 template <>
 struct Fmt<VP3D_BF16> {
@@ -75,7 +81,91 @@ struct Fmt<VP3D_BF16> {
   static __device__ __forceinline__ float2 unpack(uint32_t u) {
     return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
   }
+  static __device__ __forceinline__ uint32_t gt0_mask(uint32_t u) {
+    return __hgt2_mask(*reinterpret_cast<__nv_bfloat162*>(&u),
+                       __nv_bfloat162(__ushort_as_bfloat16(0), __ushort_as_bfloat16(0)));
+  }
 };
+
+// fp32 pair -> packed 16-bit pair with the ReLU inside the conversion (cvt.rn.relu: negative results become +0)
+template <int DT>
+__device__ __forceinline__ uint32_t pack_relu(float a, float b);
+template <>
+__device__ __forceinline__ uint32_t pack_relu<VP3D_F16>(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+template <>
+__device__ __forceinline__ uint32_t pack_relu<VP3D_BF16>(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// Random bytes of one epilogue chunk (this thread's row `grow`, 32 columns from col0 = four 8-channel groups): lo[j] /
+// hi[j] hold the bytes of channels 8j .. 8j+3 / 8j+4 .. 8j+7 -- the mask of train.cu's passes, where one Philox block per
+// (row pair, 8-channel group) holds the bits of both rows of the pair. Adjacent lanes own the two rows of a pair whenever
+// the warp's first row is even: each of them then draws TWO of the chunk's four blocks and hands the partner its half
+// (4 shuffles instead of 2 blocks).
+__device__ __forceinline__ void drop_chunk_bits(const DropCtx& drop, long long grow, int lane, int col0, uint32_t (&lo)[4],
+                                                uint32_t (&hi)[4]) {
+  const bool h = (grow & 1) != 0;
+  if (((grow - lane) & 1) == 0) {
+    const int jg = (lane & 1) * 2;
+    const uint4 b0 = drop_bits(drop, grow >> 1, (col0 >> 3) + jg);
+    const uint4 b1 = drop_bits(drop, grow >> 1, (col0 >> 3) + jg + 1);
+    const uint32_t m0 = h ? b0.z : b0.x, m1 = h ? b0.w : b0.y, m2 = h ? b1.z : b1.x, m3 = h ? b1.w : b1.y;
+    const uint32_t r0 = __shfl_xor_sync(0xffffffffu, h ? b0.x : b0.z, 1);
+    const uint32_t r1 = __shfl_xor_sync(0xffffffffu, h ? b0.y : b0.w, 1);
+    const uint32_t r2 = __shfl_xor_sync(0xffffffffu, h ? b1.x : b1.z, 1);
+    const uint32_t r3 = __shfl_xor_sync(0xffffffffu, h ? b1.y : b1.w, 1);
+    const bool even = jg == 0;   // even lane drew groups 0, 1 and received 2, 3; odd lane the other way round
+    lo[0] = even ? m0 : r0; hi[0] = even ? m1 : r1;
+    lo[1] = even ? m2 : r2; hi[1] = even ? m3 : r3;
+    lo[2] = even ? r0 : m0; hi[2] = even ? r1 : m1;
+    lo[3] = even ? r2 : m2; hi[3] = even ? r3 : m3;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 bits = drop_bits(drop, grow >> 1, (col0 >> 3) + j);
+      lo[j] = h ? bits.z : bits.x;
+      hi[j] = h ? bits.w : bits.y;
+    }
+  }
+}
+
+// Lean epilogue (EPI = 2), affine + activation + conversion of one 32-column chunk: AFF 0 none, 1 + shift, 2 * scale + shift
+// (tables in shared memory, read as broadcast LDS.128); the ReLU costs nothing (it is a modifier of the conversion).
+template <int DT, bool RELU, int AFF>
+__device__ __forceinline__ void lean_pack(const uint32_t (&x)[32], const float* sc, const float* sh, uint32_t (&pk)[16]) {
+  using F = Fmt<DT>;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float a0 = __uint_as_float(x[4 * j + 0]), a1 = __uint_as_float(x[4 * j + 1]);
+    float a2 = __uint_as_float(x[4 * j + 2]), a3 = __uint_as_float(x[4 * j + 3]);
+    if (AFF == 2) {
+      const float4 s4 = reinterpret_cast<const float4*>(sc)[j];
+      const float4 h4 = reinterpret_cast<const float4*>(sh)[j];
+      a0 = fmaf(a0, s4.x, h4.x); a1 = fmaf(a1, s4.y, h4.y); a2 = fmaf(a2, s4.z, h4.z); a3 = fmaf(a3, s4.w, h4.w);
+    } else if (AFF == 1) {
+      const float4 h4 = reinterpret_cast<const float4*>(sh)[j];
+      a0 += h4.x; a1 += h4.y; a2 += h4.z; a3 += h4.w;
+    }
+    pk[2 * j + 0] = RELU ? pack_relu<DT>(a0, a1) : F::pack(a0, a1);
+    pk[2 * j + 1] = RELU ? pack_relu<DT>(a2, a3) : F::pack(a2, a3);
+  }
+}
 
 struct PairTile {
   int seq, t0, n0;
@@ -201,7 +291,17 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
   // everything above touched only this CTA's shared / tensor memory: it overlaps the tail of the previous kernel (pdl.cuh)
   pdl_enter();
-  if (p.shift != nullptr) {
+  if (EPI == 2) {
+    // lean epilogue: the keep scale of the dropout is folded into the tables (relu(x) * k == relu(x * k) for k > 0)
+    const float ks = p.drop.p > 0.f ? make_drop(p.drop).keep_scale : 1.f;
+    if (p.shift != nullptr || p.scale != nullptr || p.drop.p > 0.f) {
+      const int n_cols = p.n_tiles * kBN;
+      for (int j = threadIdx.x; j < n_cols; j += kThreads) {
+        affine_smem[j] = (p.scale != nullptr ? __ldg(p.scale + j) : 1.f) * ks;
+        affine_smem[kAffineCols + j] = (p.shift != nullptr ? __ldg(p.shift + j) : 0.f) * ks;
+      }
+    }
+  } else if (p.shift != nullptr) {
     const int n_cols = p.n_tiles * kBN;
     for (int j = threadIdx.x; j < n_cols; j += kThreads) {
       affine_smem[j] = p.scale != nullptr ? __ldg(p.scale + j) : 1.f;
@@ -307,6 +407,100 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
     __syncwarp();
+  } else if (EPI == 2) {
+    // ------------------------------------------------------------------ lean epilogue (warps 2..9, both CTAs)
+    // Launches without residual, statistics or side input -- the expand layer (K = 192: the whole launch is epilogue
+    // bound), the 3-tap inference layers, data gradients without fan-in, the lifter's Linear layers: TMEM -> (affine) ->
+    // conversion with the ReLU inside -> dropout as an AND on the packed pairs -> staged tile -> TMA store. The next
+    // chunk's tcgen05.ld is in flight during the math of the current one, and the accumulator is handed back to the MMA
+    // thread as soon as the tile's last chunk has left tensor memory (before its math).
+    constexpr int kChunks = kBN / 64;
+    const int quad = warp & 3;
+    const int epi = warp - 2;
+    const int half = epi >> 2;
+    const int row = quad * 32 + lane;
+    unsigned out_buf = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    DropCtx drop;
+    drop.on = false;
+    if (p.drop.p > 0.f) drop = make_drop(p.drop);
+    // keep iff byte >= thresh  <=>  byte + (256 - thresh) carries out of its byte: bit 7 of maj(x, y, (x & 7f..) + (y & 7f..))
+    const uint32_t kadd = ((256u - drop.thresh) & 0xFFu) * 0x01010101u;
+    const uint32_t kadd7 = kadd & 0x7F7F7F7Fu;
+    const int aff = (p.scale != nullptr || drop.on) ? 2 : (p.shift != nullptr ? 1 : 0);
+    const uint32_t empty_leader0 = map_to_cta(smem_u32(&tmem_empty_bar[0]), 0);
+    const uint32_t empty_leader1 = map_to_cta(smem_u32(&tmem_empty_bar[1]), 0);
+    TileFeed tf;
+    for (int pt = first_pair; pt >= 0; pt = next_tile(tf, pt, lane == 0, true)) {
+      const PairTile tc = decode_pair(pt, p, pairs_per_seq, rank);
+      const long long grow = (long long)tc.seq * p.rows_out + tc.t0 + row;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + acc * kBN + half * kChunks * 32 + (static_cast<uint32_t>(quad * 32) << 16);
+      uint32_t v[2][32];
+      tmem_ld_32x32b_x32(taddr, v[0]);
+#pragma unroll
+      for (int cq = 0; cq < kChunks; ++cq) {
+        tmem_wait_ld();
+        if (cq + 1 < kChunks) {
+          tmem_ld_32x32b_x32(taddr + (cq + 1) * 32, v[(cq + 1) & 1]);
+        } else {
+          // this warp has read its share of the accumulator buffer: one arrival per warp on the LEADER's barrier
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (rank == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            else mbar_arrive_cluster(acc ? empty_leader1 : empty_leader0);
+          }
+        }
+        const int c = half * kChunks + cq;
+        const int col0 = tc.n0 * kBN + c * 32;
+        const float* sc = affine_smem + col0;
+        const float* sh = affine_smem + kAffineCols + col0;
+        uint32_t pk[16];
+        if (p.relu) {
+          if (aff == 2) lean_pack<DT, true, 2>(v[cq & 1], sc, sh, pk);
+          else if (aff == 1) lean_pack<DT, true, 1>(v[cq & 1], sc, sh, pk);
+          else lean_pack<DT, true, 0>(v[cq & 1], sc, sh, pk);
+        } else {
+          if (aff == 2) lean_pack<DT, false, 2>(v[cq & 1], sc, sh, pk);
+          else if (aff == 1) lean_pack<DT, false, 1>(v[cq & 1], sc, sh, pk);
+          else lean_pack<DT, false, 0>(v[cq & 1], sc, sh, pk);
+        }
+        if (drop.on) {
+          uint32_t lo[4], hi[4];
+          drop_chunk_bits(drop, grow, lane, col0, lo, hi);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t ml = maj3(lo[j], kadd, (lo[j] & 0x7F7F7F7Fu) + kadd7);   // bit 7 of byte i: keep channel 8j + i
+            const uint32_t mh = maj3(hi[j], kadd, (hi[j] & 0x7F7F7F7Fu) + kadd7);
+            pk[4 * j + 0] &= prmt(ml, 0u, 0x9988u);   // sign of byte 0 over the low half, of byte 1 over the high half
+            pk[4 * j + 1] &= prmt(ml, 0u, 0xBBAAu);
+            pk[4 * j + 2] &= prmt(mh, 0u, 0x9988u);
+            pk[4 * j + 3] &= prmt(mh, 0u, 0xBBAAu);
+          }
+        }
+        const unsigned b = out_buf;
+        out_buf = out_buf + 1 == kOutBufs ? 0 : out_buf + 1;
+        uint8_t* my_stage = out_stage + b * kOutBufBytes + epi * (32 * 64);
+        if (lane == 0) tma_store_wait_read<kOutBufs - 1>();   // the store that last used this buffer has drained it
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          st_shared_v4(my_stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), pk[4 * j + 0], pk[4 * j + 1], pk[4 * j + 2],
+                       pk[4 * j + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmC, my_stage, col0, tc.t0 + quad * 32, tc.seq);
+          tma_store_commit();
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) tma_store_wait_all<0>();
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
     constexpr int kChunks = kBN / 64;   // 32-column chunks per epilogue warp
@@ -434,34 +628,9 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
         if (EPI && drop.on) {
-          // the mask of train.cu's passes: one Philox block per (row pair, 8-channel group) holds the bits of both rows
-          // of the pair. Adjacent lanes own the two rows of a pair whenever the warp's first row is even: each of them
-          // then draws TWO of the chunk's four blocks and hands the partner its half (4 shuffles instead of 2 blocks).
           const long long grow = (long long)tc.seq * p.rows_out + t;
-          const bool h = (grow & 1) != 0;
           uint32_t lo[4], hi[4];
-          if (((grow - lane) & 1) == 0) {
-            const int jg = (lane & 1) * 2;
-            const uint4 b0 = drop_bits(drop, grow >> 1, (col0 >> 3) + jg);
-            const uint4 b1 = drop_bits(drop, grow >> 1, (col0 >> 3) + jg + 1);
-            const uint32_t m0 = h ? b0.z : b0.x, m1 = h ? b0.w : b0.y, m2 = h ? b1.z : b1.x, m3 = h ? b1.w : b1.y;
-            const uint32_t r0 = __shfl_xor_sync(0xffffffffu, h ? b0.x : b0.z, 1);
-            const uint32_t r1 = __shfl_xor_sync(0xffffffffu, h ? b0.y : b0.w, 1);
-            const uint32_t r2 = __shfl_xor_sync(0xffffffffu, h ? b1.x : b1.z, 1);
-            const uint32_t r3 = __shfl_xor_sync(0xffffffffu, h ? b1.y : b1.w, 1);
-            const bool even = jg == 0;   // even lane drew groups 0, 1 and received 2, 3; odd lane the other way round
-            lo[0] = even ? m0 : r0; hi[0] = even ? m1 : r1;
-            lo[1] = even ? m2 : r2; hi[1] = even ? m3 : r3;
-            lo[2] = even ? r0 : m0; hi[2] = even ? r1 : m1;
-            lo[3] = even ? r2 : m2; hi[3] = even ? r3 : m3;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 bits = drop_bits(drop, grow >> 1, (col0 >> 3) + j);
-              lo[j] = h ? bits.z : bits.x;
-              hi[j] = h ? bits.w : bits.y;
-            }
-          }
+          drop_chunk_bits(drop, grow, lane, col0, lo, hi);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float m[8];
@@ -490,21 +659,22 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (side_on) {
           // the side tile of this chunk sits in the staging buffer (same SWIZZLE_64B box as the store): thread = row
           mbar_wait(&side_bar[epi * kOutBufs + b], (uint32_t)(gc / kOutBufs) & 1u);
+          if (p.side_mode == 1) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 r = *reinterpret_cast<const uint4*>(my_stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
-            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+            for (int j = 0; j < 4; ++j) {
+              const uint4 r = *reinterpret_cast<const uint4*>(my_stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
+              const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 x = F::unpack(rr[e]);
-              if (p.side_mode == 1) {
+              for (int e = 0; e < 4; ++e) {
+                const float2 x = F::unpack(rr[e]);
                 f[8 * j + 2 * e + 0] += x.x;
                 f[8 * j + 2 * e + 1] += x.y;
-              } else {
-                f[8 * j + 2 * e + 0] = x.x > 0.f ? f[8 * j + 2 * e + 0] * p.side_scale : 0.f;
-                f[8 * j + 2 * e + 1] = x.y > 0.f ? f[8 * j + 2 * e + 1] * p.side_scale : 0.f;
               }
             }
+          } else {
+            // gate: the comparison side > 0 happens on the packed pairs when the result is staged (below)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= p.side_scale;
           }
         } else {
           if (lane == 0) tma_store_wait_read<kOutBufs - 1>();   // the store that last used this buffer has drained it
@@ -512,9 +682,18 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          st_shared_v4(my_stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), F::pack(f[8 * j + 0], f[8 * j + 1]),
-                       F::pack(f[8 * j + 2], f[8 * j + 3]), F::pack(f[8 * j + 4], f[8 * j + 5]),
-                       F::pack(f[8 * j + 6], f[8 * j + 7]));
+          uint8_t* dst = my_stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4);
+          uint32_t w0 = F::pack(f[8 * j + 0], f[8 * j + 1]), w1 = F::pack(f[8 * j + 2], f[8 * j + 3]);
+          uint32_t w2 = F::pack(f[8 * j + 4], f[8 * j + 5]), w3 = F::pack(f[8 * j + 6], f[8 * j + 7]);
+          if (side_on && p.side_mode == 2) {
+            // out = side > 0 ? out : 0 as one compare-to-mask + AND per pair; the side values sit where the result goes
+            const uint4 r = *reinterpret_cast<const uint4*>(dst);
+            w0 &= F::gt0_mask(r.x);
+            w1 &= F::gt0_mask(r.y);
+            w2 &= F::gt0_mask(r.z);
+            w3 &= F::gt0_mask(r.w);
+          }
+          st_shared_v4(dst, w0, w1, w2, w3);
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -609,6 +788,13 @@ cudaError_t launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
 template <int DT, bool BMN>
 cudaError_t launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmS,
                             const ConvGemmParams& p, int clusters, cudaStream_t stream) {
+  // lean epilogue whenever nothing but affine / ReLU / dropout happens to the accumulator (VP3D_LEAN_EPI=0: A/B switch)
+  static const bool lean_on = [] {
+    const char* e = std::getenv("VP3D_LEAN_EPI");
+    return e == nullptr || e[0] != '0';
+  }();
+  if (lean_on && p.side_mode == 0 && p.res == nullptr && p.stat_sum == nullptr)
+    return launch_pair<DT, BMN, 2>(tmA, tmB, tmC, tmS, p, clusters, stream);
   if (p.side_mode != 0 || p.drop.p > 0.f) return launch_pair<DT, BMN, 1>(tmA, tmB, tmC, tmS, p, clusters, stream);
   return launch_pair<DT, BMN, 0>(tmA, tmB, tmC, tmS, p, clusters, stream);
 }
@@ -619,7 +805,7 @@ bool conv_gemm_pair_supported(int dtype, int block_n, int /*w_mn_major: both wei
                               const ConvGemmParams& p) {
   if (dtype != VP3D_F16 && dtype != VP3D_BF16) return false;
   if (block_n != kBN || p.out_f32 || p.dyn != nullptr) return false;
-  if (p.shift != nullptr && p.n_tiles * kBN > kAffineCols) return false;
+  if ((p.shift != nullptr || p.drop.p > 0.f) && p.n_tiles * kBN > kAffineCols) return false;
   return true;
 }
 

@@ -103,6 +103,28 @@ def test_batched_long_sequences_against_oracle():
         assert rel_err(m(x.cuda()).cpu(), ref) < 1e-2
 
 
+def test_benchmark_geometry_against_oracle():
+    """The launches bench.py times (BASELINE configs[1]: 64 sequences x 4338 frames -> persistent CTA-pair kernel, lean
+    epilogue on the expand / 3-tap layers, residual epilogue on the 1x1 layers) against the CPU oracle: two of the 64
+    sequences at their full length, fp16 and tf32 operands within the north-star tolerance, bf16 within its documented one."""
+    fw = [3, 3, 3, 3, 3]
+    sd = otm.init_state(17, 2, 17, fw, channels=1024, seed=1234)
+    g = torch.Generator().manual_seed(77)
+    x = torch.rand(64, 4096 + 242, 17, 2, generator=g) * 2 - 1
+    picks = [5, 63]
+    with torch.no_grad():
+        ref = otm.forward(sd, x[picks], fw)
+    m = build(TemporalModel, sd, 17, 17, fw, 1024)
+    xd = x.cuda()
+    for dtype, tol, mtol in (('fp16', REL_TOL, MPJPE_TOL), ('tf32', REL_TOL, MPJPE_TOL), ('bf16', 1e-2, 1e-4)):
+        m.operand_dtype = dtype
+        with torch.no_grad():
+            y = m(xd)[picks].float().cpu()
+        assert y.shape == ref.shape == (2, 4096, 17, 3)
+        assert rel_err(y, ref) < tol, (dtype, rel_err(y, ref))
+        assert mpjpe_delta(y, ref) < mtol, (dtype, mpjpe_delta(y, ref))
+
+
 def test_full_size_properties_config2():
     """BASELINE config 2 at full size (64 x 4338 frames): size-independent properties instead of the CPU oracle.
     (i) every sequence of a batch equals the same sequence run alone; (ii) a time-shifted input gives the

@@ -344,6 +344,63 @@ def test_train_step_with_dropout_runs_and_learns():
     assert torch.isfinite(y).all()
 
 
+def test_training_run_follows_the_oracle_loss_trajectory():
+    """run.py:457-487 as a RUN, not a step: 30 optimiser steps (Adam amsgrad, dropout 0, a new batch every step) of the
+    27-frame 1f model on the CUDA path and of the fp32 CPU oracle from the same initial state on the same batches. The
+    two loss curves must stay together (16-bit operands perturb every step by ~1e-3; the run must not drift), the loss
+    must fall, and the two trained models must agree in eval mode on held-out input."""
+    fw = [3, 3, 3]
+    steps, batch, lr = 30, 128, 1e-3
+    sd0 = otm.init_state(17, 2, 17, fw, channels=1024, seed=41)
+    g = torch.Generator().manual_seed(42)
+    # a learnable synthetic task: the target is a fixed random linear map of the centre frame's keypoints
+    proj = torch.randn(34, 51, generator=g) * 0.3
+    xs = torch.rand(steps, batch, 27, 17, 2, generator=g) * 2 - 1
+    tg = (xs[:, :, 13].reshape(steps, batch, 34) @ proj).reshape(steps, batch, 1, 17, 3)
+
+    # ---- oracle run (fp32 CPU autograd + torch.optim.Adam)
+    sd = {k: v.clone() for k, v in sd0.items()}
+    names = [k for k, v in sd.items() if v.dtype.is_floating_point and 'running_' not in k]
+    plist = [sd[k] for k in names]
+    opt_o = torch.optim.Adam(plist, lr=lr, amsgrad=True)
+    loss_o = []
+    for i in range(steps):
+        loss, _, grads, new_stats = otm.train_step_grads(sd, xs[i], tg[i], fw, strided=True)
+        for k, p in zip(names, plist):
+            p.grad = grads[k]
+        opt_o.step()
+        sd.update(new_stats)
+        loss_o.append(float(loss))
+
+    # ---- CUDA run through the drop-in module and FusedAdam
+    from vp3d_b200.optim import FusedAdam
+    m = TemporalModelOptimized1f(17, 2, 17, fw, dropout=0.0, channels=1024)
+    m.load_state_dict(sd0)
+    m = m.cuda().train()
+    opt = FusedAdam(m.parameters(), lr=lr, amsgrad=True)
+    loss_g = []
+    for i in range(steps):
+        opt.zero_grad()
+        loss = mpjpe(m(xs[i].cuda()), tg[i].cuda())
+        loss.backward()
+        opt.step()
+        loss_g.append(loss.item())
+
+    rel = [abs(a - b) / b for a, b in zip(loss_g, loss_o)]
+    print('loss trajectory (gpu, oracle):', [(round(a, 5), round(b, 5)) for a, b in zip(loss_g, loss_o)][::5],
+          'max rel', max(rel))
+    assert loss_o[-1] < 0.6 * loss_o[0], loss_o
+    assert max(rel) < 2e-2, rel
+    assert rel[-1] < 2e-2
+    # the trained models agree in eval mode (running statistics included) on held-out input
+    xe = torch.rand(64, 27, 17, 2, generator=g) * 2 - 1
+    m.eval()
+    with torch.no_grad():
+        ye = m(xe.cuda()).cpu()
+        ref = otm.forward(sd, xe, fw, strided=True)
+    assert rel_err(ye, ref) < 3e-2, rel_err(ye, ref)
+
+
 def test_j31_pose_and_trajectory_heads_with_reprojection_loss():
     """BASELINE configs[4] primitives: 31-joint skeleton (62 input channels, 93 / 3 output channels), a pose model and a
     trajectory model (num_joints_out = 1) trained jointly with mpjpe + weighted_mpjpe + a reprojection term through the
