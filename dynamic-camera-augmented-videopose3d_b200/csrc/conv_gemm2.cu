@@ -29,31 +29,45 @@ namespace {
 constexpr int kBM = 128;                  // rows per CTA (256 per pair)
 constexpr int kBN = 256;                  // output channels per pair tile
 constexpr int kKBytes = 128;              // one swizzle span of K per stage row
-constexpr int kStages = 5;
-constexpr int kEpi = 8;                   // epilogue warps, two per TMEM lane quadrant
-constexpr int kSchedWarp = 2 + kEpi;      // last warp: tile scheduler (cluster launch control), leader CTA only
-constexpr int kThreads = 64 + 32 * kEpi + 32;
 constexpr int kClcSlots = 3;              // responses in flight: the producer may be 3 tiles ahead of the slowest epilogue warp
-constexpr int kClcConsumers = 2 + 1 + 2 * kEpi;   // both producers, the MMA thread, the epilogue warps of both CTAs
 constexpr int kABytes = kBM * kKBytes;            // 16 KB
 constexpr int kBHalfBytes = (kBN / 2) * kKBytes;  // 16 KB: this CTA's half of the weight tile
 constexpr int kStageBytes = kABytes + kBHalfBytes;
-constexpr int kOutBufBytes = kEpi * 32 * 64;      // one 32 x 32 staging tile (64 B rows) per epilogue warp
 #ifndef VP3D_PAIR_OUTBUFS
 #define VP3D_PAIR_OUTBUFS 2
 #endif
-// ring of TMA-store staging buffers per epilogue warp. EPI = 1 (side input / fused dropout) uses three: a side tile is
-// fetched INTO the staging buffer its result is later written over, two chunks ahead of its use.
-template <int EPI>
-struct EpiCfg {
-  static constexpr int kOutBufs = EPI == 1 ? 3 : VP3D_PAIR_OUTBUFS;
-  static constexpr int kOutStageBytes = kOutBufs * kOutBufBytes;
-};
 constexpr int kBarBytes = 512;
 constexpr int kAffineCols = 1024;
 constexpr int kAffineBytes = 2 * kAffineCols * 4;
+// Warp / shared-memory configuration per epilogue variant:
+//   EPI 0  generic epilogue (residual through registers, train-mode statistics)   8 epilogue warps, 5 stages
+//   EPI 1  + side input by TMA / fused dropout: three staging buffers per epilogue warp -- a side tile is fetched INTO
+//          the staging buffer its result is later written over, two chunks ahead of its use
+//   EPI 2  lean epilogue (affine, ReLU, dropout only)                               8 epilogue warps, 5 stages
+//   EPI 3  lean epilogue for SHORT contractions (the expand layer, K = 192: the launch is bound by the epilogue, which is a
+//          chain of dependent steps per 32-column chunk -- TMEM read, math, staging, fence, store -- so what it needs is
+//          more chains in flight): 16 epilogue warps, four per TMEM lane quadrant, and 4 stages to make room for their
+//          staging buffers
 template <int EPI>
-constexpr int smem_bytes() { return kStages * kStageBytes + EpiCfg<EPI>::kOutStageBytes + kBarBytes + kAffineBytes; }
+struct EpiCfg {
+  static constexpr int kEpi = EPI == 3 ? 16 : 8;           // epilogue warps, kEpi / 4 per TMEM lane quadrant
+  static constexpr int kParts = kEpi / 4;                  // column parts of a tile, one per warp of a quadrant
+  static constexpr int kChunks = kBN / 32 / kParts;        // 32-column chunks per epilogue warp per tile
+  static constexpr int kStages = EPI == 3 ? 4 : 5;
+  static constexpr int kSchedWarp = 2 + kEpi;              // last warp: tile scheduler (cluster launch control), leader only
+  static constexpr int kThreads = 64 + 32 * kEpi + 32;
+  static constexpr int kClcConsumers = 2 + 1 + 2 * kEpi;   // both producers, the MMA thread, the epilogue warps of both CTAs
+  static constexpr int kOutBufBytes = kEpi * 32 * 64;      // one 32 x 32 staging tile (64 B rows) per epilogue warp
+  static constexpr int kOutBufs = EPI == 1 ? 3 : VP3D_PAIR_OUTBUFS;
+  static constexpr int kOutStageBytes = kOutBufs * kOutBufBytes;
+  static constexpr int kSideBars = EPI == 1 ? kEpi * kOutBufs : 0;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutStageBytes + kBarBytes + kAffineBytes;
+  static_assert(2 * kStages + 4 + 2 + kSideBars <= 40 && (40 + 2 * kClcSlots) * 8 <= 384 && 384 + 16 * kClcSlots <= kBarBytes - 4,
+                "barrier area layout");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory");
+};
+template <int EPI>
+constexpr int smem_bytes() { return EpiCfg<EPI>::kSmemBytes; }
 constexpr int kTmemCols = 2 * kBN;                // two accumulator buffers
 
 template <int DT>
@@ -199,13 +213,16 @@ __device__ __forceinline__ uint64_t mnmajor_sw128_desc(uint32_t smem_addr, uint3
 //     side_mode 1 adds it (residual rows without a register round trip), side_mode 2 gates the result by side > 0
 //     (the ReLU / dropout mask of a layer recovered from its stored activation: dropped and clipped elements are 0).
 template <int DT, bool BMN, int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(EpiCfg<EPI>::kThreads, 1)
 conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmS,
                       const ConvGemmParams p) {
   using F = Fmt<DT>;
-  constexpr int kOutBufs = EpiCfg<EPI>::kOutBufs;
-  constexpr int kOutStageBytes = EpiCfg<EPI>::kOutStageBytes;
+  using Cfg = EpiCfg<EPI>;
+  constexpr int kEpi = Cfg::kEpi, kStages = Cfg::kStages, kThreads = Cfg::kThreads, kSchedWarp = Cfg::kSchedWarp;
+  constexpr int kClcConsumers = Cfg::kClcConsumers, kOutBufBytes = Cfg::kOutBufBytes;
+  constexpr int kOutBufs = Cfg::kOutBufs;
+  constexpr int kOutStageBytes = Cfg::kOutStageBytes;
   constexpr int kElemsPerKBlock = kKBytes / 2;
   constexpr uint32_t kIdesc = make_instr_desc(F::kFormat, 2 * kBM, kBN) | (BMN ? (1u << 16) : 0u);
 
@@ -225,8 +242,6 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint64_t* clc_full = bars + 40;                  // dynamic schedule: response landed (per CTA, multicast complete_tx)
   uint64_t* clc_empty = bars + 40 + kClcSlots;     // leader only: every consumer of both CTAs has read the response
   uint8_t* clc_resp = reinterpret_cast<uint8_t*>(bars) + 384;   // kClcSlots x 16 bytes
-  static_assert(2 * kStages + 4 + 2 + kEpi * 3 <= 40 && (40 + 2 * kClcSlots) * 8 <= 384 && 384 + 16 * kClcSlots <= kBarBytes - 4,
-                "barrier area layout");
   float* affine_smem = reinterpret_cast<float*>(out_stage + kOutStageBytes + kBarBytes);   // scale[1024] | shift[1024]
 
   const int warp = threadIdx.x >> 5;
@@ -275,9 +290,9 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], 2 * kEpi);
     }
-    if (EPI) {
+    if (EPI == 1) {
       tma_prefetch_desc(&tmS);
-      for (int s = 0; s < kEpi * kOutBufs; ++s) mbar_init(&side_bar[s], 1);
+      for (int s = 0; s < Cfg::kSideBars; ++s) mbar_init(&side_bar[s], 1);
     }
     for (int s = 0; s < kClcSlots; ++s) {
       mbar_init(&clc_full[s], 1);
@@ -291,7 +306,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
   // everything above touched only this CTA's shared / tensor memory: it overlaps the tail of the previous kernel (pdl.cuh)
   pdl_enter();
-  if (EPI == 2) {
+  if (EPI >= 2) {
     // lean epilogue: the keep scale of the dropout is folded into the tables (relu(x) * k == relu(x * k) for k > 0)
     const float ks = p.drop.p > 0.f ? make_drop(p.drop).keep_scale : 1.f;
     if (p.shift != nullptr || p.scale != nullptr || p.drop.p > 0.f) {
@@ -407,17 +422,18 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
     __syncwarp();
-  } else if (EPI == 2) {
-    // ------------------------------------------------------------------ lean epilogue (warps 2..9, both CTAs)
+  } else if (EPI >= 2) {
+    // ------------------------------------------------------------------ lean epilogue (warps 2.., both CTAs)
     // Launches without residual, statistics or side input -- the expand layer (K = 192: the whole launch is epilogue
     // bound), the 3-tap inference layers, data gradients without fan-in, the lifter's Linear layers: TMEM -> (affine) ->
-    // conversion with the ReLU inside -> dropout as an AND on the packed pairs -> staged tile -> TMA store. The next
-    // chunk's tcgen05.ld is in flight during the math of the current one, and the accumulator is handed back to the MMA
-    // thread as soon as the tile's last chunk has left tensor memory (before its math).
-    constexpr int kChunks = kBN / 64;
+    // conversion with the ReLU inside -> dropout as an AND on the packed pairs -> staged tile -> TMA store. With 8 warps
+    // the next chunk's tcgen05.ld is in flight during the math of the current one; the accumulator is handed back to the
+    // MMA thread as soon as the tile's last chunk has left tensor memory (before its math).
+    constexpr int kChunks = Cfg::kChunks;
+    constexpr bool kPipeLd = EPI == 2;      // 16 warps: one chunk's registers per thread (102-register budget)
     const int quad = warp & 3;
     const int epi = warp - 2;
-    const int half = epi >> 2;
+    const int half = epi >> 2;              // column part of the tile this warp owns (0 .. kParts - 1)
     const int row = quad * 32 + lane;
     unsigned out_buf = 0;
     int acc = 0;
@@ -438,14 +454,17 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + acc * kBN + half * kChunks * 32 + (static_cast<uint32_t>(quad * 32) << 16);
-      uint32_t v[2][32];
-      tmem_ld_32x32b_x32(taddr, v[0]);
+      // (8 warps, 168 registers: two chunks' registers per thread, the next load in flight across the math; 16 warps, 96
+      // registers: one chunk's registers, load and wait adjacent -- four warps per scheduler cover the TMEM latency)
+      uint32_t v[kPipeLd ? 2 : 1][32];
+      if (kPipeLd) tmem_ld_32x32b_x32(taddr, v[0]);
 #pragma unroll
       for (int cq = 0; cq < kChunks; ++cq) {
+        uint32_t (&x)[32] = v[kPipeLd ? (cq & 1) : 0];
+        if (!kPipeLd) tmem_ld_32x32b_x32(taddr + cq * 32, v[0]);
         tmem_wait_ld();
-        if (cq + 1 < kChunks) {
-          tmem_ld_32x32b_x32(taddr + (cq + 1) * 32, v[(cq + 1) & 1]);
-        } else {
+        if (kPipeLd && cq + 1 < kChunks) tmem_ld_32x32b_x32(taddr + (cq + 1) * 32, v[kPipeLd ? ((cq + 1) & 1) : 0]);
+        if (cq + 1 == kChunks) {
           // this warp has read its share of the accumulator buffer: one arrival per warp on the LEADER's barrier
           tcgen05_fence_before();
           __syncwarp();
@@ -460,13 +479,13 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const float* sh = affine_smem + kAffineCols + col0;
         uint32_t pk[16];
         if (p.relu) {
-          if (aff == 2) lean_pack<DT, true, 2>(v[cq & 1], sc, sh, pk);
-          else if (aff == 1) lean_pack<DT, true, 1>(v[cq & 1], sc, sh, pk);
-          else lean_pack<DT, true, 0>(v[cq & 1], sc, sh, pk);
+          if (aff == 2) lean_pack<DT, true, 2>(x, sc, sh, pk);
+          else if (aff == 1) lean_pack<DT, true, 1>(x, sc, sh, pk);
+          else lean_pack<DT, true, 0>(x, sc, sh, pk);
         } else {
-          if (aff == 2) lean_pack<DT, false, 2>(v[cq & 1], sc, sh, pk);
-          else if (aff == 1) lean_pack<DT, false, 1>(v[cq & 1], sc, sh, pk);
-          else lean_pack<DT, false, 0>(v[cq & 1], sc, sh, pk);
+          if (aff == 2) lean_pack<DT, false, 2>(x, sc, sh, pk);
+          else if (aff == 1) lean_pack<DT, false, 1>(x, sc, sh, pk);
+          else lean_pack<DT, false, 0>(x, sc, sh, pk);
         }
         if (drop.on) {
           uint32_t lo[4], hi[4];
@@ -770,7 +789,7 @@ cudaError_t launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(EpiCfg<EPI>::kThreads);
   cfg.dynamicSmemBytes = smem_bytes<EPI>();
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -793,8 +812,15 @@ cudaError_t launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
     const char* e = std::getenv("VP3D_LEAN_EPI");
     return e == nullptr || e[0] != '0';
   }();
-  if (lean_on && p.side_mode == 0 && p.res == nullptr && p.stat_sum == nullptr)
+  if (lean_on && p.side_mode == 0 && p.res == nullptr && p.stat_sum == nullptr) {
+    static const bool lean16_on = [] {
+      const char* e = std::getenv("VP3D_LEAN16");
+      return e == nullptr || e[0] != '0';
+    }();
+    if (lean16_on && p.taps * p.kblocks_per_tap <= 6)   // short contraction: epilogue bound, 16 epilogue warps
+      return launch_pair<DT, BMN, 3>(tmA, tmB, tmC, tmS, p, clusters, stream);
     return launch_pair<DT, BMN, 2>(tmA, tmB, tmC, tmS, p, clusters, stream);
+  }
   if (p.side_mode != 0 || p.drop.p > 0.f) return launch_pair<DT, BMN, 1>(tmA, tmB, tmC, tmS, p, clusters, stream);
   return launch_pair<DT, BMN, 0>(tmA, tmB, tmC, tmS, p, clusters, stream);
 }

