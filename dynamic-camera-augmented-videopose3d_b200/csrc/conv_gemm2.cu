@@ -121,6 +121,12 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
   return d;
 }
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                             uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e),
+               "r"(f), "r"(g), "r"(h)
+               : "memory");
+}
 __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t d;
   asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
@@ -500,6 +506,18 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             pk[4 * j + 3] &= prmt(mh, 0u, 0xBBAAu);
           }
         }
+        if (p.direct_out) {
+          // Straight from registers: a thread holds 64 contiguous bytes of its output row = two 32-byte (one sector each)
+          // stores. No staging tile, proxy fence, warp barrier or TMA store -- and no epilogue traffic through the shared
+          // memory the tensor pipe reads its operands from.
+          if (tc.t0 + row < p.rows_out) {
+            uint16_t* o = static_cast<uint16_t*>(p.out) + (long long)tc.seq * p.out_seq_stride +
+                          (long long)(tc.t0 + row) * p.out_row_stride + col0;
+            st_global_v8(o, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+            st_global_v8(o + 16, pk[8], pk[9], pk[10], pk[11], pk[12], pk[13], pk[14], pk[15]);
+          }
+          continue;
+        }
         const unsigned b = out_buf;
         out_buf = out_buf + 1 == kOutBufs ? 0 : out_buf + 1;
         uint8_t* my_stage = out_stage + b * kOutBufBytes + epi * (32 * 64);
@@ -671,6 +689,24 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             }
           }
         }
+        if (EPI == 0 && p.direct_out) {
+          // (launcher: no statistics) straight from registers, as in the lean epilogue
+          if (row_ok) {
+            uint16_t* o = static_cast<uint16_t*>(p.out) + (long long)tc.seq * p.out_seq_stride +
+                          (long long)t * p.out_row_stride + col0;
+            st_global_v8(o, F::pack(f[0], f[1]), F::pack(f[2], f[3]), F::pack(f[4], f[5]), F::pack(f[6], f[7]),
+                         F::pack(f[8], f[9]), F::pack(f[10], f[11]), F::pack(f[12], f[13]), F::pack(f[14], f[15]));
+            st_global_v8(o + 16, F::pack(f[16], f[17]), F::pack(f[18], f[19]), F::pack(f[20], f[21]), F::pack(f[22], f[23]),
+                         F::pack(f[24], f[25]), F::pack(f[26], f[27]), F::pack(f[28], f[29]), F::pack(f[30], f[31]));
+          }
+          ++gc;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            rcur[j] = rnext[j];
+            rnext[j] = rnext2[j];
+          }
+          continue;
+        }
         // staged SWIZZLE_64B tile -> one TMA store per warp per 32 columns (rows past the sequence end are clipped)
         const unsigned b = out_buf;
         out_buf = out_buf + 1 == kOutBufs ? 0 : out_buf + 1;
@@ -805,6 +841,18 @@ cudaError_t launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
 }
 
 template <int DT, bool BMN>
+cudaError_t launch_lean(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmS,
+                        const ConvGemmParams& p, int clusters, cudaStream_t stream) {
+  static const bool lean16_on = [] {
+    const char* e = std::getenv("VP3D_LEAN16");
+    return e == nullptr || e[0] != '0';
+  }();
+  if (lean16_on && p.taps * p.kblocks_per_tap <= 6)   // short contraction: epilogue bound, 16 epilogue warps
+    return launch_pair<DT, BMN, 3>(tmA, tmB, tmC, tmS, p, clusters, stream);
+  return launch_pair<DT, BMN, 2>(tmA, tmB, tmC, tmS, p, clusters, stream);
+}
+
+template <int DT, bool BMN>
 cudaError_t launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmS,
                             const ConvGemmParams& p, int clusters, cudaStream_t stream) {
   // lean epilogue whenever nothing but affine / ReLU / dropout happens to the accumulator (VP3D_LEAN_EPI=0: A/B switch)
@@ -813,16 +861,31 @@ cudaError_t launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
     return e == nullptr || e[0] != '0';
   }();
   if (lean_on && p.side_mode == 0 && p.res == nullptr && p.stat_sum == nullptr) {
-    static const bool lean16_on = [] {
-      const char* e = std::getenv("VP3D_LEAN16");
-      return e == nullptr || e[0] != '0';
+    static const bool direct_on = [] {
+      const char* e = std::getenv("VP3D_DIRECT_OUT");
+      return e != nullptr && (e[0] == '1' || e[0] == '2');     // off by default, see below
     }();
-    if (lean16_on && p.taps * p.kblocks_per_tap <= 6)   // short contraction: epilogue bound, 16 epilogue warps
-      return launch_pair<DT, BMN, 3>(tmA, tmB, tmC, tmS, p, clusters, stream);
-    return launch_pair<DT, BMN, 2>(tmA, tmB, tmC, tmS, p, clusters, stream);
+    ConvGemmParams q = p;
+    // Measured per launch (ncu, 64 x 4338-frame inference): 3-tap layers 1159 / 1193 / 1207 / 1153 us with staged TMA
+    // stores, 1136 / 1167 / 1178 / 1130 us with direct stores (the tensor pipe no longer shares the shared-memory
+    // bandwidth with the staging traffic); the write-bound expand layer 128 -> 184 us (32-byte sector stores scattered
+    // over 32 rows per instruction lose to TMA's 64-byte row segments when the launch is nothing but output). But the
+    // whole inference step, where the chip sits at its power cap, does not follow the isolated launches: 7.80 ms with
+    // direct stores on the MMA-bound launches against 7.75 ms with TMA stores (4 alternating runs each, same box). The
+    // path stays as an experiment switch (VP3D_DIRECT_OUT=1; =2 extends it to the residual epilogue).
+    q.direct_out = (direct_on && p.taps * p.kblocks_per_tap > 6 && (reinterpret_cast<uintptr_t>(p.out) & 31) == 0 &&
+                    p.out_row_stride % 16 == 0 && p.out_seq_stride % 16 == 0) ? 1 : 0;
+    return launch_lean<DT, BMN>(tmA, tmB, tmC, tmS, q, clusters, stream);
   }
   if (p.side_mode != 0 || p.drop.p > 0.f) return launch_pair<DT, BMN, 1>(tmA, tmB, tmC, tmS, p, clusters, stream);
-  return launch_pair<DT, BMN, 0>(tmA, tmB, tmC, tmS, p, clusters, stream);
+  static const bool direct_generic = [] {
+    const char* e = std::getenv("VP3D_DIRECT_OUT");
+    return e != nullptr && e[0] == '2';      // the residual epilogue with direct stores: off by default (see the lean path)
+  }();
+  ConvGemmParams q = p;
+  q.direct_out = (direct_generic && p.stat_sum == nullptr && (reinterpret_cast<uintptr_t>(p.out) & 31) == 0 &&
+                  p.out_row_stride % 16 == 0 && p.out_seq_stride % 16 == 0) ? 1 : 0;
+  return launch_pair<DT, BMN, 0>(tmA, tmB, tmC, tmS, q, clusters, stream);
 }
 
 }  // namespace

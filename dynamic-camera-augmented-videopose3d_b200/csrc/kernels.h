@@ -96,6 +96,8 @@ struct ConvGemmParams {
                         // 1: out += side[seq][t + side_row_off][n]   2: out = side[seq][t][n] > 0 ? out * side_scale : 0
   int side_row_off;
   float side_scale;
+  int direct_out;       // lean epilogue: 32-byte global stores straight from registers instead of staged TMA stores (set
+                        // by the launcher when `out` and its strides are 32-byte aligned)
 };
 
 cudaError_t launch_conv_gemm(int dtype, int block_n, int w_mn_major, const CUtensorMap& tmA, const CUtensorMap& tmB,
