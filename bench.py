@@ -919,7 +919,7 @@ def bench_stream(args, rank, world, dev):
     model = model.to(dev).eval()
     model.operand_dtype = args.dtype if args.dtype != 'tf32' else 'fp16'
     out = {}
-    for S, steps in ((1024, 200), (1, 200)):
+    for S, steps in ((1024, 200), (8, 400), (1, 400)):
         g = torch.Generator().manual_seed(99 + rank)
         X = (torch.randn(S, 17, 3, generator=g) * 0.3 + torch.tensor([0.0, 0.0, 4.0])).to(dev)
         q = torch.tensor([1.0, 0, 0, 0]).repeat(S, 1).to(dev)
@@ -937,10 +937,13 @@ def bench_stream(args, rank, world, dev):
             e1.record()
             torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
-        out['streams_%d' % S] = {'ms_per_step': ms, 'frames_per_s': S / (ms * 1e-3)}
+        out['streams_%d' % S] = {'ms_per_step': ms, 'frames_per_s': S / (ms * 1e-3),
+                                 'path': 'vp3d_stream_step_fused (one cooperative kernel per frame)' if st.fused
+                                 else 'GEMM launches replayed as one CUDA graph'}
     out['config'] = ('TemporalModel(causal=True) 3,3,3,3,3, per-layer ring buffers, one frame per step, per-frame camera '
-                     'projection with distortion on the device (BASELINE configs[3]); ring offsets on the device, the 12 GEMM / '
-                     'bookkeeping launches of a frame replayed as one CUDA graph')
+                     'projection with distortion on the device (BASELINE configs[3]); ring offsets on the device; 1024 streams: the '
+                     '12 GEMM / bookkeeping launches of a frame replayed as one CUDA graph; <= 8 streams: one cooperative '
+                     'kernel per frame (matrix-vector layers, grid barriers); ms_per_step includes the host side of step_world()')
     return out
 
 

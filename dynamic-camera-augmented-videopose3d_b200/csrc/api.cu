@@ -997,6 +997,46 @@ int vp3d_ring_write(int dtype, const float* src, void* ring, const int* table_en
   return VP3D_OK;
 }
 
+int vp3d_stream_step_fused(int dtype, long long* step, unsigned long long* barrier_counter, int n_rings, const int* ring_len,
+                           const int* ring_dil, const int* ring_taps, int rows_per_slot, const float* x_in, int c_in,
+                           int c_in_pad, void* ring0, int n_streams, const vp3d_stream_layer* layers, int n_layers,
+                           void* stream) {
+  if (dtype != VP3D_F16 && dtype != VP3D_BF16) return fail(VP3D_ERR_INVALID, "stream_step_fused: dtype must be F16 or BF16");
+  if (!step || !barrier_counter || !ring_len || !ring_dil || !ring_taps || !x_in || !ring0 || !layers)
+    return fail(VP3D_ERR_INVALID, "stream_step_fused: null pointer");
+  if (n_rings <= 0 || n_rings > 16 || rows_per_slot <= 0 || c_in <= 0 || c_in_pad < c_in)
+    return fail(VP3D_ERR_INVALID, "stream_step_fused: ring / input geometry");
+  if (n_streams <= 0 || n_streams > vp3d::stream_step_max_streams())
+    return fail(VP3D_ERR_UNSUPPORTED, "stream_step_fused serves 1..%d streams (got %d); larger batches take the GEMM path",
+                vp3d::stream_step_max_streams(), n_streams);
+  if (n_layers <= 0 || n_layers > vp3d::kStreamMaxLayers) return fail(VP3D_ERR_INVALID, "stream_step_fused: 1..12 layers");
+  vp3d::StreamStepParams p;
+  memset(&p, 0, sizeof(p));
+  p.step = step;
+  p.barrier = barrier_counter;
+  p.ring_len = ring_len; p.ring_dil = ring_dil; p.ring_taps = ring_taps;
+  p.n_rings = n_rings; p.rows_per_slot = rows_per_slot;
+  p.x_in = x_in; p.ring0 = ring0; p.c_in = c_in; p.c_in_pad = c_in_pad; p.n_streams = n_streams; p.n_layers = n_layers;
+  for (int l = 0; l < n_layers; ++l) {
+    const vp3d_stream_layer& s = layers[l];
+    if (!s.a || !s.w || !s.out || s.taps <= 0 || s.k_per_tap <= 0 || s.k_per_tap % 8 != 0 ||
+        (long long)s.taps * s.k_per_tap > vp3d::stream_step_max_k() || s.n <= 0 || s.a_ring >= n_rings ||
+        s.res_ring >= n_rings || s.out_ring >= n_rings || (s.res != nullptr && s.res_ring < 0))
+      return fail(VP3D_ERR_INVALID, "stream_step_fused: layer %d", l);
+    vp3d::StreamLayer& d = p.layers[l];
+    d.a = s.a; d.w = s.w; d.shift = s.shift; d.res = s.res; d.out = s.out;
+    d.a_ring = s.a_ring; d.res_ring = s.res_ring; d.out_ring = s.out_ring;
+    d.k_per_tap = s.k_per_tap; d.taps = s.taps; d.tap_row_step = s.tap_row_step;
+    d.n = s.n; d.n_valid = s.n_valid; d.relu = s.relu; d.out_f32 = s.out_f32;
+    d.res_row_stride = s.res_row_stride; d.out_row_stride = s.out_row_stride;
+  }
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_stream_step(dtype, p, dev->sm_count, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "stream_step_fused launch");
+  return VP3D_OK;
+}
+
 static int check_adam_args(const vp3d_adam_args* a) {
   if (!a->p || !a->g || !a->m || !a->v || !a->step || a->n <= 0)
     return fail(VP3D_ERR_INVALID, "adam_step: null pointer or empty tensor");

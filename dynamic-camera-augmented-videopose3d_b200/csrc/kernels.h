@@ -132,6 +132,33 @@ cudaError_t launch_wgrad(int dtype, int block_n, int block_m, const CUtensorMap&
 cudaError_t launch_wgrad_finish(const float* packed, float* dw, int c_out, int c_in, int taps, long long tap_stride,
                                 long long row_stride, const float* gscale_buf, int sm_count, cudaStream_t stream);
 
+// Fused low-latency streaming step (stream.cu): one cooperative kernel per frame for a few concurrent streams.
+struct StreamLayer {
+  const void* a;        // layer input: flat [rows][k_per_tap] view of a ring (or a plain buffer)
+  const void* w;        // K-major weights [n][taps * k_per_tap] (BatchNorm scale folded in)
+  const float* shift;   // [n] or nullptr
+  const void* res;      // residual ring (16-bit, row stride res_row_stride) or nullptr
+  void* out;            // 16-bit ring / buffer, or fp32 [streams][out_row_stride]
+  int a_ring, res_ring, out_ring;   // ring indices whose positions apply (-1: rows start at 0 / no mirror copy)
+  int k_per_tap, taps, tap_row_step;
+  int n, n_valid, relu, out_f32;
+  int res_row_stride, out_row_stride;
+};
+constexpr int kStreamMaxLayers = 12;
+struct StreamStepParams {
+  long long* step;                  // device frame counter (read at the start, incremented at the end)
+  unsigned long long* barrier;      // 128 device words of grid-barrier counters: 0 when *step == 0, never reset in between
+  const int* ring_len; const int* ring_dil; const int* ring_taps;
+  int n_rings, rows_per_slot;
+  const float* x_in;                // [n_streams][c_in] new frame
+  void* ring0;
+  int c_in, c_in_pad, n_streams, n_layers;
+  StreamLayer layers[kStreamMaxLayers];
+};
+int stream_step_max_streams();
+int stream_step_max_k();
+cudaError_t launch_stream_step(int dtype, const StreamStepParams& p, int sm_count, cudaStream_t stream);
+
 cudaError_t launch_counter_add(unsigned long long* counter, unsigned long long inc, cudaStream_t stream);
 struct AdamParams {
   float* p; const float* g; float* m; float* v; float* vmax;

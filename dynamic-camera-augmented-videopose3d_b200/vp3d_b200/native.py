@@ -87,6 +87,15 @@ class AllReduceArgs(C.Structure):
                 ('scale', C.c_float), ('ctas', C.c_int), ('timeout_s', C.c_double)]
 
 
+class StreamLayer(C.Structure):
+    """struct vp3d_stream_layer (include/vp3d_b200.h)"""
+    _fields_ = [('a', C.c_void_p), ('w', C.c_void_p), ('shift', C.c_void_p), ('res', C.c_void_p), ('out', C.c_void_p),
+                ('a_ring', C.c_int), ('res_ring', C.c_int), ('out_ring', C.c_int),
+                ('k_per_tap', C.c_int), ('taps', C.c_int), ('tap_row_step', C.c_int),
+                ('n', C.c_int), ('n_valid', C.c_int), ('relu', C.c_int), ('out_f32', C.c_int),
+                ('res_row_stride', C.c_int), ('out_row_stride', C.c_int)]
+
+
 class Dropout(C.Structure):
     """struct vp3d_dropout (include/vp3d_b200.h)"""
     _fields_ = [('p', C.c_float), ('seed', C.c_ulonglong), ('stream', C.c_ulonglong), ('step_counter', C.c_void_p)]
@@ -152,6 +161,9 @@ _SIGNATURES = {
                                                                       C.POINTER(Dropout)] + [C.c_void_p] * 7),
     'vp3d_stream_advance': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                       C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'vp3d_stream_step_fused': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                         C.POINTER(StreamLayer), C.c_int, C.c_void_p]),
     'vp3d_ring_write': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int,
                                   C.c_void_p]),
     'vp3d_adam_step': (C.c_int, [C.POINTER(AdamArgs), C.c_void_p]),

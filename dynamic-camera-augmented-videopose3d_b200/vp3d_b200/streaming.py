@@ -15,14 +15,23 @@ The ring positions live on the DEVICE: vp3d_stream_advance ticks a frame counter
 that the GEMM launches read (vp3d_conv_args.dyn_offsets), so the ~15 launches of a step never change and are captured
 once as a CUDA graph; a frame then costs one graph launch instead of ~20 Python-issued launches.
 
+Few streams (S <= 8): a frame is ten matrix-vector products, and twelve dependent launches cost 0.13 ms whatever S is.
+`vp3d_stream_step_fused` (csrc/stream.cu) runs the whole frame -- ring bookkeeping, ring write, all layers -- as ONE
+cooperative kernel with grid barriers between the layers (one warp per output channel, weights streamed from L2), on the
+same rings and packed operands; VP3D_STREAM_FUSED=0 keeps the GEMM launches.
+
 Per-frame camera: `step_world()` takes world-space joints plus this frame's camera (quaternion, translation, intrinsics
 with distortion) per stream and projects on the device (vp3d_project_points) before the stack.
 """
+import ctypes as C
+import os
 
 import torch
 
 from . import native, ops
 from .temporal import N_TILE, packed_for, resolve_dtype
+
+FUSED_MAX_STREAMS = 8     # vp3d_stream_step_fused serves 1..8 streams
 
 
 class CausalStream:
@@ -68,6 +77,11 @@ class CausalStream:
         self.use_graph = use_graph
         self.graph = None
         self._warm = 0
+        # few streams: the whole frame as one cooperative kernel (no graph needed: it is a single launch)
+        self.fused = (self.S <= FUSED_MAX_STREAMS and os.environ.get('VP3D_STREAM_FUSED', '1') != '0' and
+                      max(self.taps[i] * widths[i] for i in range(nb + 1)) <= 3072 and nb + 2 + nb <= 12)
+        self.barrier = torch.zeros(128, dtype=torch.int64, device=dev)    # grid-barrier counters, 0 whenever step_dev is 0
+        self._fused_layers = None
 
     def refresh_weights(self):
         """Re-resolves the packed eval operands (folded BatchNorm) from the module's CURRENT parameters and buffers. The
@@ -79,12 +93,14 @@ class CausalStream:
             self.pk = pk
             self.graph = None
             self._warm = 0
+            self._fused_layers = None
 
     def reset(self):
         self.refresh_weights()
         for r in self.rings:
             r.zero_()
         self.step_dev.zero_()
+        self.barrier.zero_()
         
     def prime(self, x0):
         """Left edge padding of the reference's generator (generators.py:193-195 replicates the first frame over the
@@ -136,11 +152,55 @@ class CausalStream:
                        (pk.n_out, S * pk.n_out), block_n=64, scale=None, shift=pk.shrink_shift, relu=False, out_f32=True,
                        n_valid=pk.n_out)
 
+    def _fused_desc(self):
+        """vp3d_stream_layer array of one frame: the launches of _issue() as layer descriptions (built once per pack)."""
+        if self._fused_layers is not None:
+            return self._fused_layers
+        pk, Sp = self.pk, self.S_pad
+        nb = len(self.model.filter_widths) - 1
+        C_ = pk.c_pad
+        layers = []
+
+        def layer(a, a_ring, k_pad, w, taps, dil, shift, out, out_ring, res=None, res_ring=-1, relu=True, out_f32=False,
+                  n=C_, n_valid=C_, out_stride=C_):
+            layers.append(native.StreamLayer(
+                a=a.data_ptr(), w=w.data_ptr(), shift=shift.data_ptr(), res=res.data_ptr() if res is not None else None,
+                out=out.data_ptr(), a_ring=a_ring, res_ring=res_ring, out_ring=out_ring, k_per_tap=k_pad, taps=taps,
+                tap_row_step=dil * Sp, n=n, n_valid=n_valid, relu=1 if relu else 0, out_f32=1 if out_f32 else 0,
+                res_row_stride=C_, out_row_stride=out_stride))
+
+        layer(self.rings[0], 0, pk.c_in_pad, pk.w_expand, self.taps[0], self.dil[0], pk.bn_expand[1],
+              self.rings[1] if nb else self.h_last, 1 if nb else -1)
+        for i in range(1, nb + 1):
+            layer(self.rings[i], i, C_, pk.w_layers[2 * (i - 1)], self.taps[i], self.dil[i], pk.bn_layers[2 * (i - 1)][1],
+                  self.y1, -1)
+            last = i == nb
+            layer(self.y1, -1, C_, pk.w_layers[2 * (i - 1) + 1], 1, 0, pk.bn_layers[2 * (i - 1) + 1][1],
+                  self.h_last if last else self.rings[i + 1], -1 if last else i + 1, res=self.rings[i], res_ring=i)
+        layer(self.h_last, -1, C_, pk.w_shrink, 1, 0, pk.shrink_shift, self.y, -1, relu=False, out_f32=True,
+              n=pk.w_shrink.shape[0], n_valid=pk.n_out, out_stride=pk.n_out)
+        arr = (native.StreamLayer * len(layers))(*layers)
+        self._fused_layers = (arr, len(layers))
+        return self._fused_layers
+
+    def _issue_fused(self, x_in):
+        """One cooperative kernel for the whole frame (S <= 8). x_in: (S, c_in) fp32 contiguous CUDA."""
+        pk = self.pk
+        arr, n_layers = self._fused_desc()
+        with torch.cuda.device(self.dev):
+            native.check(native.lib().vp3d_stream_step_fused(
+                self.dt, self.step_dev.data_ptr(), self.barrier.data_ptr(), len(self.rings), self.ring_len.data_ptr(),
+                self.ring_dil.data_ptr(), self.ring_taps.data_ptr(), self.S_pad, x_in.data_ptr(), pk.c_in, pk.c_in_pad,
+                self.rings[0].data_ptr(), self.S, arr, n_layers, ops._stream()), 'stream_step_fused')
+
     def step(self, x_t):
         """x_t: (S, J, F) fp32 CUDA, the frame every stream has just received -> (S, J_out, 3) fp32 (a fresh tensor)."""
         ops.require_cuda(x_t)
         m, pk, S = self.model, self.pk, self.S
         assert x_t.shape[0] == S and x_t.numel() == S * pk.c_in
+        if self.fused:
+            self._issue_fused(ops.f32c(x_t).reshape(S, pk.c_in))
+            return self.y.view(S, m.num_joints_out, 3).clone()
         self.x_in.copy_(x_t.reshape(S, pk.c_in))
         if not self.use_graph:
             self._issue()

@@ -432,6 +432,29 @@ int vp3d_stream_advance(long long* step, int n_rings, const int* ring_len, const
 int vp3d_ring_write(int dtype, const float* src, void* ring, const int* table_entry, long long rows, int c, int c_pad,
                     void* stream);
 
+/* Low-latency streaming step for a FEW concurrent streams (n_streams <= 8; BASELINE configs[3]): the whole frame -- ring
+ * bookkeeping (what vp3d_stream_advance computes), the write of the new 2-D keypoints into ring 0 (vp3d_ring_write) and
+ * every layer of the causal TemporalModel (TemporalModel.py:126-138 one frame at a time) -- as ONE cooperative kernel
+ * with grid barriers between the layers: with so few rows a layer is a matrix-vector product whose only cost is streaming
+ * the weights out of L2, so one warp owns one output channel and nothing is launched between layers. Layer l computes
+ *   out[s][c] = act(sum_k w[c][k] * a[a_pos + tap * tap_row_step + s][k mod k_per_tap] + shift[c]) (+ res[res_pos + s][c])
+ * for s < n_streams, c < n, with a_pos / res_pos / out positions taken from the rings a_ring / res_ring / out_ring (-1: a
+ * plain buffer starting at row 0; 16-bit outputs into a ring are stored in its slot AND its mirror). Same operands and
+ * rounding points as the vp3d_conv_block_fwd launches it replaces (16-bit activations between layers, fp32 accumulate).
+ * `layers` is a HOST array (n_layers <= 12, taps * k_per_tap <= 3072, k_per_tap % 8 == 0). `barrier_counter` points at
+ * 128 device words (1 KB) that must be 0 when *step is 0 and are otherwise owned by this call. */
+typedef struct vp3d_stream_layer {
+  const void* a; const void* w; const float* shift; const void* res; void* out;
+  int a_ring, res_ring, out_ring;
+  int k_per_tap, taps, tap_row_step;
+  int n, n_valid, relu, out_f32;
+  int res_row_stride, out_row_stride;
+} vp3d_stream_layer;
+int vp3d_stream_step_fused(int dtype, long long* step, unsigned long long* barrier_counter, int n_rings, const int* ring_len,
+                           const int* ring_dil, const int* ring_taps, int rows_per_slot, const float* x_in, int c_in,
+                           int c_in_pad, void* ring0, int n_streams, const vp3d_stream_layer* layers, int n_layers,
+                           void* stream);
+
 /* Fused optimiser step for one convolution weight: torch.optim.Adam(amsgrad) as run.py:662 uses it, in
  * the arithmetic of torch's capturable implementation, plus the re-pack of the updated fp32 weight (c_out, c_in, taps)
  * into the 16-bit K-major operand packed[c_out_pad][taps][k_pad] the next forward reads (padding entries are left

@@ -190,17 +190,28 @@ def test_streaming_equals_full_causal_forward(fw, ch):
         full = m(xpad.cuda()).cpu()                                  # (S, T, 17, 3)
         ref = otm.forward(sd, xpad, fw, causal=True)
     assert rel_err(full, ref) < REL_TOL
-    st = CausalStream(m, S)
     xc = x.cuda()
-    st.prime(xc[:, 0])
-    outs = []
-    with torch.no_grad():
-        for t in range(T):
-            outs.append(st.step(xc[:, t]).cpu())
-    stream = torch.stack(outs, dim=1)
-    assert stream.shape == full.shape
-    assert rel_err(stream, ref) < REL_TOL
-    assert rel_err(stream, full) < 5e-4      # same kernels, same operands: only tile shapes / summation order differ
+    for fused in (True, False):      # one cooperative kernel per frame (S <= 8) / the GEMM launches as a CUDA graph
+        st = CausalStream(m, S)
+        assert st.fused
+        st.fused = fused
+        st.prime(xc[:, 0])
+        outs = []
+        with torch.no_grad():
+            for t in range(T):
+                outs.append(st.step(xc[:, t]).cpu())
+        stream = torch.stack(outs, dim=1)
+        assert stream.shape == full.shape
+        assert rel_err(stream, ref) < REL_TOL, fused
+        assert rel_err(stream, full) < 5e-4, fused      # same operands and rounding points: only the summation order differs
+    # a single stream, and a reset in the middle of a run (frame counter and grid-barrier counter restart together)
+    st1 = CausalStream(m, 1)
+    for rep in range(2):
+        st1.reset()
+        st1.prime(xc[2:3, 0])
+        with torch.no_grad():
+            one = torch.stack([st1.step(xc[2:3, t]).cpu() for t in range(T)], dim=1)
+        assert rel_err(one, full[2:3]) < 5e-4, rep
 
 
 def test_streaming_with_per_frame_camera():
