@@ -50,10 +50,11 @@ H36M_CAM0 = [2.2900989, 2.2875624, 0.025083065, 0.028902981, -0.20709892, 0.2477
 
 def load_traffic():
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full capture of
-    this workload (profiles/r01_traffic.json, written by tools/ncu_summary.py --traffic); {} when absent."""
-    path = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-    if os.path.exists(path):
-        with open(path) as f:
+    this workload (profiles/rNN_traffic.json of the newest round, written by tools/ncu_metrics_table.py); {} when absent."""
+    import glob
+    paths = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r[0-9][0-9]_traffic.json')))   # newest round last
+    if paths:
+        with open(paths[-1]) as f:
             return json.load(f)
     return {}
 

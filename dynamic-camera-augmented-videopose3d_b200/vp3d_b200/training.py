@@ -60,6 +60,7 @@ finalize_in_gemm = os.environ.get('VP3D_FIN_IN_GEMM', '1') != '0'
 # BatchNorm backward of the layer below (which needs the data gradient and is what the critical path continues with);
 # 'before': both are released together and the hardware picks (VP3D_WGRAD_ORDER).
 wgrad_after_dgrad = os.environ.get('VP3D_WGRAD_ORDER', 'after') != 'before'
+prefill_arena = os.environ.get('VP3D_PREFILL_ARENA', '1') != '0'   # zero arena of the backward filled during the forward
 debug_keep_saved = False  # tests: keep the last forward's saved per-layer tensors in `debug_last_saved`
 debug_last_saved = None
 
@@ -345,10 +346,48 @@ def _data_grad(dt, L, dz, n, c_pad, fan_in=None, fan_rows=0, fan_off=0, fan_mul=
     return g_in
 
 
+def _side_stream(device, main):
+    key = (device.index, main.cuda_stream)
+    side = _side_streams.get(key)
+    if side is None:
+        side = _side_streams[key] = torch.cuda.Stream(device)
+    return side
+
+
+def _arena_floats(model, c_in, n_layers):
+    """Upper bound of the fp32 words the backward takes from its zero arena (_ZeroArena): BatchNorm-backward sums, the
+    split-K accumulators of every weight gradient, slack for 16-byte alignment."""
+    ch = model.expand_conv.out_channels
+    c_pad = _round_up(ch, N_TILE)
+    c_in_pad = _round_up(c_in, K_ALIGN)
+    taps0 = model.expand_conv.kernel_size[0]
+    total = 4 * n_layers * c_pad + SHRINK_PAD * c_pad + 8 * (n_layers + 2) + 256
+    total += max(c_pad * 256, taps0 * c_pad * c_in_pad)
+    for conv in model.layers_conv:
+        total += conv.kernel_size[0] * c_pad * c_pad
+    return total
+
+
 class _StackTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, dt, x, *params):
+        # The backward's zero-filled accumulators (68 MB at 1024 channels: one fill launch of ~11 us at HBM speed) depend on
+        # nothing, so the fill is issued NOW on the side stream and runs beside the forward's first kernels instead of at
+        # the head of the backward's critical path; forked from and joined to the current stream inside this call, so the
+        # step stays capturable.
+        arena = None
+        if overlap_wgrad and prefill_arena:
+            main = torch.cuda.current_stream(x.device)
+            side = _side_stream(x.device, main)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                arena = _ZeroArena(_arena_floats(model, x.shape[-1], 2 * len(model.filter_widths) - 1), x.device)
         y, layers, a_last, t_last, c_pad, w_shrink = _forward_stack(model, x, dt)
+        if arena is not None:
+            main.wait_stream(side)
+        ctx.arena = arena
         ctx.w_shrink = w_shrink
         if debug_keep_saved:
             global debug_last_saved
@@ -384,12 +423,7 @@ class _StackTrainFn(torch.autograd.Function):
         # kernel leaves enough registers for one BN-backward block per SM. Every tensor the side stream touches is kept
         # alive in `keep` until the streams have joined (no reliance on record_stream, so the step stays capturable).
         main = torch.cuda.current_stream(dy.device)
-        side = None
-        if overlap_wgrad:
-            key = (dy.device.index, main.cuda_stream)
-            side = _side_streams.get(key)
-            if side is None:
-                side = _side_streams[key] = torch.cuda.Stream(dy.device)
+        side = _side_stream(dy.device, main) if overlap_wgrad else None
         keep = []
 
         def done(param, g):
@@ -444,8 +478,10 @@ class _StackTrainFn(torch.autograd.Function):
                 return fn()
 
         # every zero-initialised accumulator of this backward in one fill
-        arena = _ZeroArena(4 * len(layers) * c_pad + SHRINK_PAD * c_pad + sum(_packed_floats(L, c_pad) for L in layers) +
-                           8 * (len(layers) + 2), dy.device)
+        arena = ctx.arena      # filled during the forward (side stream, joined there)
+        if arena is None:
+            arena = _ZeroArena(4 * len(layers) * c_pad + SHRINK_PAD * c_pad + sum(_packed_floats(L, c_pad) for L in layers) +
+                               8 * (len(layers) + 2), dy.device)
         sums_all = arena.take((len(layers), 2, c_pad), torch.float64)
 
         # ---- shrink layer: y = a_last W^T + b
@@ -538,7 +574,7 @@ class _StackTrainFn(torch.autograd.Function):
             grads.update(grad_finish_hook() or {})
         keep.clear()
         out = [grads.get(id(p)) for p in ctx.params]
-        ctx.layers = ctx.a_last = None
+        ctx.layers = ctx.a_last = ctx.arena = None
         return (None, None, None) + tuple(out)
 
 

@@ -25,6 +25,12 @@ ncu --metrics $M --clock-control none -k regex:"conv_gemm|wgrad_gemm|project_|ex
 echo "== ncu metric table, one inference step"
 ncu --metrics $M --clock-control none -k regex:"conv_gemm|pack_rows" -s 33 -c 11 --csv --log-file $O/${TAG}_metrics_infer.csv \
   python bench.py --mode infer --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_infer.log 2>&1
+echo "== streaming latency probe"; python tools/stream_probe.py > $O/${TAG}_stream_probe.json 2> $O/${TAG}_stream_probe.err
+echo "== ncu --set full + source, expand-layer GEMM (lean epilogue, 16 epilogue warps): inference and training"
+ncu --set full --clock-control none --import-source on -k regex:"conv_gemm_pair_kernel" -c 1 -f -o $O/${TAG}_prof_expand_infer \
+  python bench.py --mode infer --steps 1 --warmup 1 --no-cpu-baseline --no-parity > $O/ncu_expand_infer.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"conv_gemm_pair_kernel" -c 1 -f -o $O/${TAG}_prof_expand_train \
+  python bench.py --mode train --steps 1 --warmup 1 --no-graph --no-cpu-baseline --no-parity > $O/ncu_expand_train.log 2>&1
 echo "== ncu --set full, projection kernel"
 ncu --set full --import-source on --clock-control none -k regex:project_frames -s 2 -c 1 -f -o $O/${TAG}_prof_proj \
   python tools/proj_probe.py > $O/ncu_proj.log 2>&1
