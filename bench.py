@@ -762,7 +762,7 @@ def bench_train_multi(args, rank, world, dev, model, opt, loss_fn, steps, world_
     ddp.enable_sync_bn(on=False)
     glob = local.detach().clone()
     dist.all_reduce(glob, op=dist.ReduceOp.AVG)
-    out['syncbn'] = {'global_batch': per * world, 'loss_one_gpu': float(single), 'loss_syncbn': float(glob),
+    out['syncbn'] = {'global_batch': per * world, 'loss_one_gpu': float(single.detach()), 'loss_syncbn': float(glob.detach()),
                      'loss_rel_delta': abs(float(glob) - float(single)) / abs(float(single)),
                      'expand_bn_weight_grad_rel': rel_fro(g_sync, g_single),
                      'collectives_per_step': sync.collectives, 'tolerance': {'loss_rel_delta': 1e-3}}

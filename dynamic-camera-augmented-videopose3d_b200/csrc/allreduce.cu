@@ -98,7 +98,12 @@ __device__ __forceinline__ void peer_st(float* ptr, float4 v) {
 template <bool MC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kArThreads, 1)
 peer_allreduce_kernel(const AllReduceParams p) {
-  pdl_enter();
+  // Programmatic dependent launch: wait for the producer of the slice, but do NOT release the dependents early. This
+  // kernel blocks on OTHER ranks; a dependent released at its start -- the optimiser update of the slice, ~1200 blocks
+  // -- would sit resident in griddepcontrol.wait on every SM for as long as the slowest rank takes, and the backward's
+  // persistent GEMMs (one CTA per SM, 59 k registers) could not be scheduled beside it (see pdl_enter_long in pdl.cuh for
+  // the measurement that located the effect in the GEMMs' own dependents).
+  pdl_wait();
   rank_barrier(p);
   const long long vecs = p.n >> 2;
   const long long lo = vecs * p.rank / p.world, hi = vecs * (p.rank + 1) / p.world;

@@ -24,6 +24,21 @@ __device__ __forceinline__ void pdl_enter() {
   pdl_wait();
   pdl_trigger();
 }
+// Long-running persistent kernels (LEVEL 1: the weight-gradient GEMM, 2: also the convolution GEMMs) do NOT release their
+// dependents early. A dependent released at their start sits resident in griddepcontrol.wait for the whole launch; when it
+// is a big grid of small blocks (the weight-gradient layout pass, Adam, a BatchNorm pass) it holds registers and thread
+// slots that kernels of OTHER streams need -- the exchange kernel and the optimiser updates of a data-parallel backward,
+// the BatchNorm passes meant to run beside the weight-gradient GEMM. Measured with A/B builds (VP3D_PDL_LATE_TRIGGER = 0 /
+// 1 / 2, same box): one GPU 1.700 / 1.698 / 1.698 ms per training step (the gain of PDL comes from the chains of small
+// kernels), two GPUs 1.971 / 1.896 / 1.808 ms. Default 2.
+#ifndef VP3D_PDL_LATE_TRIGGER
+#define VP3D_PDL_LATE_TRIGGER 2
+#endif
+template <int LEVEL>
+__device__ __forceinline__ void pdl_enter_long() {
+  pdl_wait();
+  if (VP3D_PDL_LATE_TRIGGER < LEVEL) pdl_trigger();
+}
 
 // kernel<<<grid, block, smem, stream>>>(args...) with the PDL attribute (and optionally a cluster shape)
 template <typename... KArgs, typename... Args>
