@@ -311,7 +311,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tmem_relinquish_2cta();
   }
   // everything above touched only this CTA's shared / tensor memory: it overlaps the tail of the previous kernel (pdl.cuh)
-  pdl_enter_long<2>();
+  pdl_enter_long<2>(total_pairs <= pair_step);
   if (EPI >= 2) {
     // lean epilogue: the keep scale of the dropout is folded into the tables (relu(x) * k == relu(x * k) for k > 0)
     const float ks = p.drop.p > 0.f ? make_drop(p.drop).keep_scale : 1.f;

@@ -155,7 +155,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
   // everything above touched only this CTA's shared / tensor memory: it overlaps the tail of the previous kernel (pdl.cuh)
-  pdl_enter_long<1>();
+  pdl_enter_long<1>(false);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer

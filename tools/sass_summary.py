@@ -35,7 +35,7 @@ def main():
         for label, pat in PATTERNS:
             if pat.search(line):
                 counts[name][label] += 1
-        counts[name]['instructions'] += 1 if re.match(r'\s+/\*[0-9a-f]{4}\*/', line) else 0
+        counts[name]['instructions'] += 1 if re.match(r'\s+/\*[0-9a-f]{4,}\*/', line) else 0
     labels = [l for l, _ in PATTERNS]
     print('# cuobjdump -sass %s | per-kernel mnemonic counts (tools/sass_summary.py)' % os.path.relpath(LIB, ROOT))
     print('kernel | ' + ' | '.join(labels) + ' | instructions')
