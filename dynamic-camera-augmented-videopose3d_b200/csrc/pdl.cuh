@@ -30,7 +30,8 @@ __device__ __forceinline__ void pdl_enter() {
 // slots that kernels of OTHER streams need -- the exchange kernel and the optimiser updates of a data-parallel backward,
 // the BatchNorm passes meant to run beside the weight-gradient GEMM. Measured with A/B builds (VP3D_PDL_LATE_TRIGGER = 0 /
 // 1 / 2, same box): one GPU 1.700 / 1.698 / 1.698 ms per training step (the gain of PDL comes from the chains of small
-// kernels), two GPUs 1.971 / 1.896 / 1.808 ms. Default 2.
+// kernels), two GPUs 1.971 / 1.896 / 1.808 ms. Level 3 (the HBM-bound passes -- BatchNorm, weight-gradient layout, Adam --
+// keep their dependents back as well) loses that gain: 1.723-1.732 against 1.685-1.698 ms on one GPU. Default 2.
 #ifndef VP3D_PDL_LATE_TRIGGER
 #define VP3D_PDL_LATE_TRIGGER 2
 #endif

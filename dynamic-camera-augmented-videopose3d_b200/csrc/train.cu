@@ -114,7 +114,7 @@ bn_act_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, 
                   const uint4* __restrict__ res, long long rows, long long rows_per_seq, long long res_seq_rows,
                   int res_row_mul, int res_row_off, int groups, DropoutParams dp, uint4* __restrict__ a,
                   const BnFinalizeParams fin) {
-  pdl_enter();
+  pdl_enter_long<3>(false);   // level 3 (A/B builds): the HBM-bound passes keep their dependents back too
   const RowWalk w;
   if (w.grp >= groups) return;
   const DropCtx drop = make_drop(dp);
@@ -289,7 +289,7 @@ bn_act_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* __restrict__ 
                          const float* __restrict__ shift, const float* __restrict__ mean,
                          const float* __restrict__ invstd, long long rows, int groups, DropoutParams dp,
                          double* __restrict__ sum_dy, double* __restrict__ sum_dy_xhat) {
-  pdl_enter();
+  pdl_enter_long<3>(false);   // level 3 (A/B builds): the HBM-bound passes keep their dependents back too
   const RowWalkT<kRedLanes> w;
   float a1[8], a2[8];
 #pragma unroll
@@ -345,7 +345,7 @@ bn_act_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z
                         DropoutParams dp, const double* __restrict__ sum_dy, const double* __restrict__ sum_dy_xhat,
                         const float* __restrict__ gscale_buf, uint4* __restrict__ dz, float* __restrict__ d_gamma,
                         float* __restrict__ d_beta) {
-  pdl_enter();
+  pdl_enter_long<3>(false);   // level 3 (A/B builds): the HBM-bound passes keep their dependents back too
   const RowWalk w;
   if (w.grp >= groups) return;
   const DropCtx drop = make_drop(dp);
@@ -530,14 +530,14 @@ __device__ __forceinline__ void adam_pack_body(const AdamParams& a, const long l
 template <int DT>
 __global__ void __launch_bounds__(256)
 adam_pack_kernel(AdamParams a) {
-  pdl_enter();
+  pdl_enter_long<3>(false);   // level 3 (A/B builds): the HBM-bound passes keep their dependents back too
   adam_pack_body<DT>(a, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
 }
 
 template <int DT>
 __global__ void __launch_bounds__(256)
 adam_multi_kernel(const __grid_constant__ AdamMultiParams mp) {
-  pdl_enter();
+  pdl_enter_long<3>(false);   // level 3 (A/B builds): the HBM-bound passes keep their dependents back too
   int i = 0;
   while (i + 1 < mp.count && (int)blockIdx.x >= mp.block_start[i + 1]) ++i;   // <= 32 entries, uniform per block
   const AdamTensor& T = mp.t[i];

@@ -346,7 +346,7 @@ cudaError_t launch_wgrad(int dtype, int block_n, int block_m, const CUtensorMap&
 __global__ void __launch_bounds__(256)
 wgrad_finish_kernel(const float* __restrict__ packed, float* __restrict__ dw, int c_out, int c_in, int taps,
                     long long tap_stride, long long row_stride, const float* __restrict__ gscale_buf) {
-  pdl_enter();
+  pdl_enter_long<3>(false);
   const float inv = gscale_buf != nullptr ? gscale_buf[1] : 1.f;
   const int total = c_out * c_in;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
