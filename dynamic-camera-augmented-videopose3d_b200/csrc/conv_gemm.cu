@@ -481,6 +481,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) tma_store_wait_all<0>();  // every output tile of this warp has reached global memory
   }
 
+  pdl_tail_trigger(total_tiles <= (int)gridDim.x);
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {

@@ -803,6 +803,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (lane == 0) tma_store_wait_all<0>();
   }
 
+  pdl_tail_trigger(total_pairs <= pair_step);
   // nobody leaves (or frees tensor memory) while the peer may still read this CTA's shared memory or signal its barriers
   tcgen05_fence_before();
   __syncthreads();

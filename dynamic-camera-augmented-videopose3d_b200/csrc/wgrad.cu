@@ -306,6 +306,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   }
 
+  pdl_tail_trigger(false);
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
