@@ -72,6 +72,7 @@ __device__ __forceinline__ uint4 ldcg16(const void* p) { return __ldcg(reinterpr
 // total once this barrier is complete (monotonic counters, never reset between frames).
 constexpr int kBarWords = 8;
 constexpr int kBarStride = 16;   // u64 words between counters (128 bytes)
+constexpr int kBarEpochWord = 120;   // frames this barrier buffer has served (its own 128-byte line)
 __device__ void grid_barrier(unsigned long long* counters, unsigned long long arrivals) {
   __syncthreads();
   if (threadIdx.x < 32) {
@@ -115,7 +116,11 @@ __global__ void __launch_bounds__(kStThreads, 1) stream_step_kernel(const Stream
     ring[i][3] = (q - L) * p.rows_per_slot;
   }
   __syncthreads();
-  const unsigned long long bar_base = static_cast<unsigned long long>(t) * p.n_layers;   // n_layers barriers per frame
+  // The barrier counters are monotonic; how many frames they have seen is kept beside them (word kBarEpochWord), not taken
+  // from the frame counter, so frames advanced by the GEMM path (vp3d_stream_advance) in between do no harm. Read here by
+  // every CTA, written by CTA 0 after the frame's first barrier.
+  const unsigned long long epoch = p.barrier[kBarEpochWord];
+  const unsigned long long bar_base = epoch * p.n_layers;   // n_layers barriers per frame
   int bar = 0;
 
   // weight rows (and the epilogue's shift / residual values) of the first layer while phase 0 runs
@@ -248,7 +253,10 @@ __global__ void __launch_bounds__(kStThreads, 1) stream_step_kernel(const Stream
     }
   }
   // every CTA read *step before it arrived at the frame's first barrier, which this thread has passed
-  if (blockIdx.x == 0 && threadIdx.x == 0) *p.step = t + 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *p.step = t + 1;
+    p.barrier[kBarEpochWord] = epoch + 1;
+  }
 }
 
 template <int DT, int S, int CH>

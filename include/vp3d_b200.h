@@ -442,7 +442,8 @@ int vp3d_ring_write(int dtype, const float* src, void* ring, const int* table_en
  * plain buffer starting at row 0; 16-bit outputs into a ring are stored in its slot AND its mirror). Same operands and
  * rounding points as the vp3d_conv_block_fwd launches it replaces (16-bit activations between layers, fp32 accumulate).
  * `layers` is a HOST array (n_layers <= 12, taps * k_per_tap <= 3072, k_per_tap % 8 == 0). `barrier_counter` points at
- * 128 device words (1 KB) that must be 0 when *step is 0 and are otherwise owned by this call. */
+ * 128 device words (1 KB), zero-filled once by the caller and owned by this call from then on (barrier counters and the
+ * number of frames they have served; independent of *step, which vp3d_stream_advance may advance in between). */
 typedef struct vp3d_stream_layer {
   const void* a; const void* w; const float* shift; const void* res; void* out;
   int a_ring, res_ring, out_ring;

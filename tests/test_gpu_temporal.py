@@ -204,6 +204,15 @@ def test_streaming_equals_full_causal_forward(fw, ch):
         assert stream.shape == full.shape
         assert rel_err(stream, ref) < REL_TOL, fused
         assert rel_err(stream, full) < 5e-4, fused      # same operands and rounding points: only the summation order differs
+    # the two paths may alternate on one object (the fused kernel keeps its own barrier epoch)
+    st = CausalStream(m, S)
+    st.prime(xc[:, 0])
+    outs = []
+    with torch.no_grad():
+        for t in range(T):
+            st.fused = (t // 3) % 2 == 0
+            outs.append(st.step(xc[:, t]).cpu())
+    assert rel_err(torch.stack(outs, dim=1), full) < 5e-4
     # a single stream, and a reset in the middle of a run (frame counter and grid-barrier counter restart together)
     st1 = CausalStream(m, 1)
     for rep in range(2):
