@@ -32,6 +32,29 @@ def test_library_exports_every_declared_symbol():
     assert native.lib().vp3d_loss_workspace_bytes() > 0
 
 
+def test_integration_doc_names_every_entry_point_and_knob():
+    """INTEGRATION.md is the maintainer's map of the boundary: every exported function and every VP3D_* environment
+    variable the package reads must appear in it (families may be written `vp3d_x_fwd/bwd`, `vp3d_x_fwd` / `vp3d_x_bwd`)."""
+    doc = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    doc = re.sub(r'(vp3d_[a-z0-9_]+?)_fwd/bwd', r'\1_fwd \1_bwd', doc)
+    missing = [s for s in _header_symbols() if s not in doc]
+    assert not missing, missing
+    pkg = os.path.join(ROOT, 'dynamic-camera-augmented-videopose3d_b200')
+    knobs = set()
+    for sub in ('vp3d_b200', 'csrc', 'common'):
+        for dirpath, _, files in os.walk(os.path.join(pkg, sub)):
+            if 'build' in dirpath:
+                continue
+            for f in files:
+                if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                    src = open(os.path.join(dirpath, f)).read()
+                    knobs.update(re.findall(r"environ\.get\(\s*'(VP3D_[A-Z0-9_]+)'", src))
+                    knobs.update(re.findall(r'getenv\("(VP3D_[A-Z0-9_]+)"\)', src))
+    assert len(knobs) >= 10
+    undocumented = sorted(k for k in knobs if k not in doc)
+    assert not undocumented, undocumented
+
+
 def test_conv_args_struct_matches_header_field_order():
     text = open(os.path.join(ROOT, 'include', 'vp3d_b200.h')).read()
     body = text[text.index('typedef struct vp3d_conv_args {'):text.index('} vp3d_conv_args;')]
