@@ -871,6 +871,59 @@ int vp3d_bn_act_fwd(int dtype, const void* z, const float* scale, const float* s
   return VP3D_OK;
 }
 
+int vp3d_bn_act_fwd_mask(int dtype, const void* z, const float* scale, const float* shift, const void* res,
+                         long long seqs, long long rows_per_seq, long long res_seq_rows, int res_row_mul, int res_row_off,
+                         int c_pad, const vp3d_dropout* drop, void* a, unsigned char* keep_mask, void* stream) {
+  if (int rc = check_ew(dtype, c_pad, "bn_act_fwd_mask")) return rc;
+  if (!z || !scale || !shift || !a || !keep_mask || seqs <= 0 || rows_per_seq <= 0)
+    return fail(VP3D_ERR_INVALID, "bn_act_fwd_mask args");
+  if (drop && (drop->p < 0.f || drop->p >= 1.f)) return fail(VP3D_ERR_INVALID, "dropout p must be in [0, 1)");
+  if (res != nullptr &&
+      (res_row_off < 0 || (rows_per_seq - 1) * (long long)res_row_mul + res_row_off >= res_seq_rows))
+    return fail(VP3D_ERR_INVALID, "bn_act_fwd_mask: residual rows out of range");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  vp3d::BnFinalizeParams fin;
+  memset(&fin, 0, sizeof(fin));
+  cudaError_t e = vp3d::launch_bn_act_fwd(dtype, z, scale, shift, res, seqs, rows_per_seq, res_seq_rows, res_row_mul,
+                                          res_row_off, c_pad, drop_of(drop), a, fin, dev->sm_count,
+                                          static_cast<cudaStream_t>(stream), keep_mask);
+  if (e != cudaSuccess) return cuda_fail(e, "bn_act_fwd_mask launch");
+  return VP3D_OK;
+}
+
+int vp3d_bn_act_bwd_reduce_mask(int dtype, const void* g, const void* z, const unsigned char* keep_mask, const float* mean,
+                                const float* invstd, float keep_scale, long long rows, int c_pad, double* sum_dy,
+                                double* sum_dy_xhat, void* stream) {
+  if (int rc = check_ew(dtype, c_pad, "bn_act_bwd_reduce_mask")) return rc;
+  if (!g || !z || !keep_mask || !mean || !invstd || !sum_dy || !sum_dy_xhat || rows <= 0 || !(keep_scale >= 1.f))
+    return fail(VP3D_ERR_INVALID, "bn_act_bwd_reduce_mask args");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_bn_act_bwd_reduce_mask(dtype, g, z, keep_mask, mean, invstd, keep_scale, rows, c_pad, sum_dy,
+                                                      sum_dy_xhat, dev->sm_count, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "bn_act_bwd_reduce_mask launch");
+  return VP3D_OK;
+}
+
+int vp3d_bn_act_bwd_apply_mask(int dtype, const void* g, const void* z, const unsigned char* keep_mask, const float* scale,
+                               const float* mean, const float* invstd, float keep_scale, long long rows, long long count,
+                               int c, int c_pad, const double* sum_dy, const double* sum_dy_xhat, const float* gscale_buf,
+                               void* dz, float* d_gamma, float* d_beta, void* stream) {
+  if (int rc = check_ew(dtype, c_pad, "bn_act_bwd_apply_mask")) return rc;
+  if (!g || !z || !keep_mask || !scale || !mean || !invstd || !sum_dy || !sum_dy_xhat || !dz || rows <= 0 || c <= 0 ||
+      c > c_pad || count < rows || !(keep_scale >= 1.f))
+    return fail(VP3D_ERR_INVALID, "bn_act_bwd_apply_mask args");
+  if ((d_gamma == nullptr) != (d_beta == nullptr)) return fail(VP3D_ERR_INVALID, "bn_act_bwd_apply_mask d_gamma / d_beta");
+  DeviceInfo* dev = nullptr;
+  if (int rc = device_info(&dev)) return rc;
+  cudaError_t e = vp3d::launch_bn_act_bwd_apply_mask(dtype, g, z, keep_mask, scale, mean, invstd, keep_scale, rows, count, c,
+                                                     c_pad, sum_dy, sum_dy_xhat, gscale_buf, dz, d_gamma, d_beta,
+                                                     dev->sm_count, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return cuda_fail(e, "bn_act_bwd_apply_mask launch");
+  return VP3D_OK;
+}
+
 int vp3d_bn_finalize_act_fwd(int dtype, const void* z, const double* stat_sum, const double* stat_sqsum, long long count,
                              const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
                              float* running_var, long long* num_batches_tracked, float* scale, float* shift, float* mean,

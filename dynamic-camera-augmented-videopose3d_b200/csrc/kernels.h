@@ -203,7 +203,18 @@ cudaError_t launch_bn_finalize(const double* sum, const double* sqsum, long long
 cudaError_t launch_bn_act_fwd(int dtype, const void* z, const float* scale, const float* shift, const void* res,
                               long long seqs, long long rows_per_seq, long long res_seq_rows, int res_row_mul,
                               int res_row_off, int c_pad, const DropoutParams& dp, void* a,
-                              const BnFinalizeParams& fin, int sm_count, cudaStream_t stream);
+                              const BnFinalizeParams& fin, int sm_count, cudaStream_t stream,
+                              unsigned char* keep_mask = nullptr);
+// backward passes that read the keep bits the forward stored (train.cu)
+cudaError_t launch_bn_act_bwd_reduce_mask(int dtype, const void* g, const void* z, const unsigned char* keep,
+                                          const float* mean, const float* invstd, float keep_scale, long long rows,
+                                          int c_pad, double* sum_dy, double* sum_dy_xhat, int sm_count,
+                                          cudaStream_t stream);
+cudaError_t launch_bn_act_bwd_apply_mask(int dtype, const void* g, const void* z, const unsigned char* keep,
+                                         const float* scale, const float* mean, const float* invstd, float keep_scale,
+                                         long long rows, long long count, int c, int c_pad, const double* sum_dy,
+                                         const double* sum_dy_xhat, const float* gscale_buf, void* dz, float* d_gamma,
+                                         float* d_beta, int sm_count, cudaStream_t stream);
 cudaError_t launch_col_stats(int dtype, const void* z, long long rows, int c_pad, double* sum, double* sqsum,
                              int sm_count, cudaStream_t stream);
 cudaError_t launch_bn_act_bwd_reduce(int dtype, const void* g, const void* z, const float* scale, const float* shift,

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kEwGroups * kEwLanes, 3)
 bn_act_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                   const uint4* __restrict__ res, long long rows, long long rows_per_seq, long long res_seq_rows,
                   int res_row_mul, int res_row_off, int groups, DropoutParams dp, uint4* __restrict__ a,
-                  const BnFinalizeParams fin) {
+                  const BnFinalizeParams fin, uint8_t* __restrict__ keep_mask) {
   pdl_enter_long<3>(false);   // level 3 (A/B builds): the HBM-bound passes keep their dependents back too
   const RowWalk w;
   if (w.grp >= groups) return;
@@ -183,6 +183,13 @@ bn_act_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, 
           } else {
 #pragma unroll
             for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f);
+          }
+          if (keep_mask != nullptr) {
+            // bit k: channel 8 grp + k of this row passed the ReLU and the dropout (v >= 0 here, so v != 0 <=> kept)
+            uint32_t kb = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) kb |= min(__float_as_uint(v[k]), 1u) << k;
+            keep_mask[row * groups + w.grp] = (uint8_t)kb;
           }
           if (res != nullptr) {
             float r[8];
@@ -405,6 +412,146 @@ bn_act_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z
   }
 }
 
+// ---------------------------------------------------------------------------------------------- backward, stored mask
+// The forward can store the keep decision (ReLU passed AND not dropped) as one bit per element (vp3d_bn_act_fwd_mask:
+// 1/16 of the 16-bit activation). With it the two backward passes need neither the Philox stream nor the affine
+// comparison, and the rest folds into per-channel constants:
+//   reduce   gm = keep ? g : 0;   S1 += gm,  S2 += gm * (z - mean)        sum_dy = ks S1, sum_dy_xhat = ks invstd S2
+//   apply    dz = A gm + C z + B  with A = scale ks, C = -scale invstd m2, B = -scale m1 - C mean
+//            (= scale * (ks gm - m1 - (z - mean) invstd m2), m1 / m2 = the batch means of dy / dy xhat)
+// The mask is applied to the PACKED gradient: byte -> two words whose byte sign bits are the 8 keep bits (one multiply
+// each), prmt with sign replication -> 16-bit lane masks, one AND per pair. ~7 instructions per element instead of 22-26
+// (ncu: the recomputing kernels are issue bound at 40 % of the HBM peak), so both passes run at memory speed.
+__device__ __forceinline__ uint32_t prmt_sign(uint32_t a, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, 0, %2;" : "=r"(d) : "r"(a), "r"(sel));
+  return d;
+}
+template <int DT>
+__device__ __forceinline__ void masked_unpack8(const uint4& gu, uint32_t keep_byte, float (&gm)[8]) {
+  // bit i of the low / high nibble -> bit 8 i + 7 (the sign bit of byte i); the four shifted copies do not overlap
+  const uint32_t lo = (keep_byte & 0xFu) * 0x10204080u, hi = (keep_byte >> 4) * 0x10204080u;
+  const uint4 m = make_uint4(gu.x & prmt_sign(lo, 0x9988u), gu.y & prmt_sign(lo, 0xBBAAu), gu.z & prmt_sign(hi, 0x9988u),
+                             gu.w & prmt_sign(hi, 0xBBAAu));
+  unpack8<DT>(m, gm);
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kEwGroups * kRedLanes, 1)
+bn_act_bwd_reduce_mask_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z, const uint8_t* __restrict__ keep,
+                              const float* __restrict__ mean, const float* __restrict__ invstd, float keep_scale,
+                              long long rows, int groups, double* __restrict__ sum_dy,
+                              double* __restrict__ sum_dy_xhat) {
+  pdl_enter_long<3>(false);
+  const RowWalkT<kRedLanes> w;
+  float a1[8], a2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a1[k] = a2[k] = 0.f;
+  if (w.grp < groups) {
+    float mu[8], is[8];
+    load8(mean, w.grp, mu);
+    load8(invstd, w.grp, is);
+    const long long iters = (rows + (long long)gridDim.x * (2 * kRedLanes * kPairUnroll) - 1) / ((long long)gridDim.x * (2 * kRedLanes * kPairUnroll));
+    for (long long it = 0; it < iters; ++it) {
+      uint4 gv[2 * kPairUnroll], zv[2 * kPairUnroll];
+      uint32_t kb[2 * kPairUnroll];
+#pragma unroll
+      for (int u = 0; u < 2 * kPairUnroll; ++u) {
+        const long long row = 2 * w.pair(it, u >> 1) + (u & 1);
+        if (row < rows) {
+          gv[u] = __ldg(g + row * groups + w.grp);
+          zv[u] = __ldg(z + row * groups + w.grp);
+          kb[u] = __ldg(keep + row * groups + w.grp);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2 * kPairUnroll; ++u) {
+        const long long row = 2 * w.pair(it, u >> 1) + (u & 1);
+        if (row < rows) {
+          float gm[8], zf[8];
+          masked_unpack8<DT>(gv[u], kb[u], gm);
+          unpack8<DT>(zv[u], zf);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            a1[k] += gm[k];
+            a2[k] = fmaf(gm[k], zf[k] - mu[k], a2[k]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      a1[k] *= keep_scale;
+      a2[k] *= keep_scale * is[k];
+    }
+  }
+  block_combine_and_add(a1, a2, w.gl, w.lane, w.grp, groups, sum_dy, sum_dy_xhat);
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kEwGroups * kEwLanes, 2)
+bn_act_bwd_apply_mask_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z, const uint8_t* __restrict__ keep,
+                             const float* __restrict__ scale, const float* __restrict__ mean,
+                             const float* __restrict__ invstd, float keep_scale, long long rows, long long count, int c,
+                             int groups, const double* __restrict__ sum_dy, const double* __restrict__ sum_dy_xhat,
+                             const float* __restrict__ gscale_buf, uint4* __restrict__ dz, float* __restrict__ d_gamma,
+                             float* __restrict__ d_beta) {
+  pdl_enter_long<3>(false);
+  const RowWalk w;
+  if (w.grp >= groups) return;
+  const double inv_n = 1.0 / (double)count;
+  float sc[8], mu[8], is[8], A[8], B[8], Cc[8];
+  load8(scale, w.grp, sc);
+  load8(mean, w.grp, mu);
+  load8(invstd, w.grp, is);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float m1 = (float)(sum_dy[w.grp * 8 + k] * inv_n);
+    const float m2 = (float)(sum_dy_xhat[w.grp * 8 + k] * inv_n);
+    A[k] = sc[k] * keep_scale;
+    Cc[k] = -sc[k] * is[k] * m2;
+    B[k] = -sc[k] * m1 - Cc[k] * mu[k];
+  }
+  // BatchNorm parameter gradients (un-scaled): written once, by pair lane 0 of the blocks of grid row 0
+  if (blockIdx.x == 0 && w.lane == 0 && d_gamma != nullptr) {
+    const double inv = gscale_buf != nullptr ? (double)gscale_buf[1] : 1.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = w.grp * 8 + k;
+      if (ch < c) {
+        d_gamma[ch] = (float)(sum_dy_xhat[ch] * inv);
+        d_beta[ch] = (float)(sum_dy[ch] * inv);
+      }
+    }
+  }
+  const long long iters = (rows + (long long)gridDim.x * kRowsPerIter - 1) / ((long long)gridDim.x * kRowsPerIter);
+  for (long long it = 0; it < iters; ++it) {
+    uint4 gv[2 * kPairUnroll], zv[2 * kPairUnroll];
+    uint32_t kb[2 * kPairUnroll];
+#pragma unroll
+    for (int u = 0; u < 2 * kPairUnroll; ++u) {
+      const long long row = 2 * w.pair(it, u >> 1) + (u & 1);
+      if (row < rows) {
+        gv[u] = __ldg(g + row * groups + w.grp);
+        zv[u] = __ldg(z + row * groups + w.grp);
+        kb[u] = __ldg(keep + row * groups + w.grp);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2 * kPairUnroll; ++u) {
+      const long long row = 2 * w.pair(it, u >> 1) + (u & 1);
+      if (row < rows) {
+        float gm[8], zf[8], o[8];
+        masked_unpack8<DT>(gv[u], kb[u], gm);
+        unpack8<DT>(zv[u], zf);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = fmaf(A[k], gm[k], fmaf(Cc[k], zf[k], B[k]));
+        dz[row * groups + w.grp] = pack8<DT>(o);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- gradient scale
 __global__ void __launch_bounds__(256)
 grad_absmax_kernel(const float* __restrict__ dy, long long n, float* __restrict__ gscale_buf) {
@@ -620,13 +767,13 @@ cudaError_t launch_bn_finalize(const double* sum, const double* sqsum, long long
 cudaError_t launch_bn_act_fwd(int dtype, const void* z, const float* scale, const float* shift, const void* res,
                               long long seqs, long long rows_per_seq, long long res_seq_rows, int res_row_mul,
                               int res_row_off, int c_pad, const DropoutParams& dp, void* a,
-                              const BnFinalizeParams& fin, int sm_count, cudaStream_t stream) {
+                              const BnFinalizeParams& fin, int sm_count, cudaStream_t stream, unsigned char* keep_mask) {
   const long long rows = seqs * rows_per_seq;
   const int groups = c_pad / 8;
   const dim3 grid = row_walk_grid(rows, groups, sm_count, 8);
   const int block = kEwGroups * kEwLanes;
   VP3D_DISPATCH_16(bn_act_fwd_kernel, static_cast<const uint4*>(z), scale, shift, static_cast<const uint4*>(res), rows,
-                   rows_per_seq, res_seq_rows, res_row_mul, res_row_off, groups, dp, static_cast<uint4*>(a), fin)
+                   rows_per_seq, res_seq_rows, res_row_mul, res_row_off, groups, dp, static_cast<uint4*>(a), fin, keep_mask)
 }
 
 cudaError_t launch_col_stats(int dtype, const void* z, long long rows, int c_pad, double* sum, double* sqsum,
@@ -659,6 +806,30 @@ cudaError_t launch_bn_act_bwd_apply(int dtype, const void* g, const void* z, con
   VP3D_DISPATCH_16(bn_act_bwd_apply_kernel, static_cast<const uint4*>(g), static_cast<const uint4*>(z), scale, shift,
                    mean, invstd, rows, count, c, groups, dp, sum_dy, sum_dy_xhat, gscale_buf, static_cast<uint4*>(dz),
                    d_gamma, d_beta)
+}
+
+cudaError_t launch_bn_act_bwd_reduce_mask(int dtype, const void* g, const void* z, const unsigned char* keep,
+                                          const float* mean, const float* invstd, float keep_scale, long long rows,
+                                          int c_pad, double* sum_dy, double* sum_dy_xhat, int sm_count,
+                                          cudaStream_t stream) {
+  const int groups = c_pad / 8;
+  const dim3 grid = reduce_grid(rows, 2 * kRedLanes * kPairUnroll, groups, sm_count);
+  const int block = kEwGroups * kRedLanes;
+  VP3D_DISPATCH_16(bn_act_bwd_reduce_mask_kernel, static_cast<const uint4*>(g), static_cast<const uint4*>(z), keep, mean,
+                   invstd, keep_scale, rows, groups, sum_dy, sum_dy_xhat)
+}
+
+cudaError_t launch_bn_act_bwd_apply_mask(int dtype, const void* g, const void* z, const unsigned char* keep,
+                                         const float* scale, const float* mean, const float* invstd, float keep_scale,
+                                         long long rows, long long count, int c, int c_pad, const double* sum_dy,
+                                         const double* sum_dy_xhat, const float* gscale_buf, void* dz, float* d_gamma,
+                                         float* d_beta, int sm_count, cudaStream_t stream) {
+  const int groups = c_pad / 8;
+  const dim3 grid = row_walk_grid(rows, groups, sm_count, 8);
+  const int block = kEwGroups * kEwLanes;
+  VP3D_DISPATCH_16(bn_act_bwd_apply_mask_kernel, static_cast<const uint4*>(g), static_cast<const uint4*>(z), keep, scale,
+                   mean, invstd, keep_scale, rows, count, c, groups, sum_dy, sum_dy_xhat, gscale_buf,
+                   static_cast<uint4*>(dz), d_gamma, d_beta)
 }
 
 cudaError_t launch_grad_scale(const float* dy, long long n, float* gscale_buf, int sm_count, cudaStream_t stream) {

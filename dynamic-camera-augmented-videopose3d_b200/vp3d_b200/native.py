@@ -151,6 +151,12 @@ _SIGNATURES = {
                          [C.c_void_p] * 7 + [C.c_int, C.c_int, C.c_void_p]),
     'vp3d_bn_act_fwd': (C.c_int, [C.c_int] + [C.c_void_p] * 4 + [C.c_longlong] * 3 + [C.c_int] * 3 +
                         [C.POINTER(Dropout), C.c_void_p, C.c_void_p]),
+    'vp3d_bn_act_fwd_mask': (C.c_int, [C.c_int] + [C.c_void_p] * 4 + [C.c_longlong] * 3 + [C.c_int] * 3 +
+                             [C.POINTER(Dropout), C.c_void_p, C.c_void_p, C.c_void_p]),
+    'vp3d_bn_act_bwd_reduce_mask': (C.c_int, [C.c_int] + [C.c_void_p] * 5 + [C.c_float, C.c_longlong, C.c_int] +
+                                    [C.c_void_p] * 3),
+    'vp3d_bn_act_bwd_apply_mask': (C.c_int, [C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_longlong, C.c_longlong, C.c_int,
+                                                                           C.c_int] + [C.c_void_p] * 7),
     'vp3d_bn_finalize_act_fwd': (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
                                            C.c_float, C.c_float] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p] +
                                  [C.c_longlong] * 3 + [C.c_int] * 3 + [C.POINTER(Dropout), C.c_void_p, C.c_void_p]),

@@ -539,10 +539,19 @@ def expand_bwd_finish(dt, p_packed, wg, gram, w, k_total, ones_col, scale, mean,
     return dw, dgb[0], dgb[1]
 
 
-def bn_act_fwd(dt, z, scale, shift, seqs, rows_per_seq, drop, res=None, res_seq_rows=0, res_row_mul=1, res_row_off=0):
+def bn_act_fwd(dt, z, scale, shift, seqs, rows_per_seq, drop, res=None, res_seq_rows=0, res_row_mul=1, res_row_off=0,
+               want_mask=False):
+    """-> a, or (a, keep_mask uint8 [rows][c_pad / 8]) with want_mask: the keep bits the backward reads instead of
+    recomputing the dropout stream and the ReLU decision (vp3d_bn_act_fwd_mask)."""
     c_pad = z.shape[-1]
     a = torch.empty_like(z)
     with torch.cuda.device(z.device):
+        if want_mask:
+            mask = torch.empty((seqs * rows_per_seq, c_pad // 8), dtype=torch.uint8, device=z.device)
+            check(lib().vp3d_bn_act_fwd_mask(dt, _ptr(z), _ptr(scale), _ptr(shift), _ptr(res), seqs, rows_per_seq,
+                                             res_seq_rows, res_row_mul, res_row_off, c_pad, C.byref(drop), _ptr(a),
+                                             _ptr(mask), _stream()), 'bn_act_fwd_mask')
+            return a, mask
         check(lib().vp3d_bn_act_fwd(dt, _ptr(z), _ptr(scale), _ptr(shift), _ptr(res), seqs, rows_per_seq, res_seq_rows,
                                     res_row_mul, res_row_off, c_pad, C.byref(drop), _ptr(a), _stream()), 'bn_act_fwd')
     return a
@@ -574,7 +583,7 @@ def bn_finalize_act_fwd(dt, z, stat, count, bn, seqs, rows_per_seq, drop, res=No
 
 
 def bn_act_bwd(dt, g, z, scale, shift, mean, invstd, rows, c, drop, gscale_buf, count=None, group=None, sums=None,
-               out=(None, None)):
+               out=(None, None), mask=None):
     """-> (dz operand-typed [rows][c_pad], d_gamma [c], d_beta [c]). `count` (>= rows) is the number of rows the
     batch statistics were taken over; with `group` the per-channel sums are all-reduced first (SyncBN). The kernel
     then writes the GLOBAL sums as d_gamma / d_beta; they are divided by the group size here so that the gradient
@@ -587,16 +596,29 @@ def bn_act_bwd(dt, g, z, scale, shift, mean, invstd, rows, c, drop, gscale_buf, 
     dz = torch.empty_like(z)
     dgb = (_grad_out(out[0], (c,), dev), _grad_out(out[1], (c,), dev))
     with torch.cuda.device(dev):
-        check(lib().vp3d_bn_act_bwd_reduce(dt, _ptr(g), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd),
-                                           rows, c_pad, C.byref(drop), _ptr(sums[0]), _ptr(sums[1]), _stream()),
-              'bn_act_bwd_reduce')
+        if mask is not None:
+            # the forward stored the keep bits: no dropout stream, no affine comparison (vp3d_bn_act_bwd_*_mask)
+            ks = float(keep_scale(drop.p))
+            check(lib().vp3d_bn_act_bwd_reduce_mask(dt, _ptr(g), _ptr(z), _ptr(mask), _ptr(mean), _ptr(invstd), ks, rows,
+                                                    c_pad, _ptr(sums[0]), _ptr(sums[1]), _stream()),
+                  'bn_act_bwd_reduce_mask')
+        else:
+            check(lib().vp3d_bn_act_bwd_reduce(dt, _ptr(g), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd),
+                                               rows, c_pad, C.byref(drop), _ptr(sums[0]), _ptr(sums[1]), _stream()),
+                  'bn_act_bwd_reduce')
         if group is not None:
             import torch.distributed as dist
             dist.all_reduce(sums, group=group)
-        check(lib().vp3d_bn_act_bwd_apply(dt, _ptr(g), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd),
-                                          rows, int(count or rows), c, c_pad, C.byref(drop), _ptr(sums[0]), _ptr(sums[1]),
-                                          _ptr(gscale_buf), _ptr(dz), _ptr(dgb[0]), _ptr(dgb[1]), _stream()),
-              'bn_act_bwd_apply')
+        if mask is not None:
+            check(lib().vp3d_bn_act_bwd_apply_mask(dt, _ptr(g), _ptr(z), _ptr(mask), _ptr(scale), _ptr(mean),
+                                                   _ptr(invstd), ks, rows, int(count or rows), c, c_pad, _ptr(sums[0]),
+                                                   _ptr(sums[1]), _ptr(gscale_buf), _ptr(dz), _ptr(dgb[0]),
+                                                   _ptr(dgb[1]), _stream()), 'bn_act_bwd_apply_mask')
+        else:
+            check(lib().vp3d_bn_act_bwd_apply(dt, _ptr(g), _ptr(z), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd),
+                                              rows, int(count or rows), c, c_pad, C.byref(drop), _ptr(sums[0]),
+                                              _ptr(sums[1]), _ptr(gscale_buf), _ptr(dz), _ptr(dgb[0]), _ptr(dgb[1]),
+                                              _stream()), 'bn_act_bwd_apply')
         if group is not None:
             import torch.distributed as dist
             torch._foreach_mul_(list(dgb), 1.0 / dist.get_world_size(group))

@@ -60,6 +60,13 @@ finalize_in_gemm = os.environ.get('VP3D_FIN_IN_GEMM', '1') != '0'
 # BatchNorm backward of the layer below (which needs the data gradient and is what the critical path continues with);
 # 'before': both are released together and the hardware picks (VP3D_WGRAD_ORDER).
 wgrad_after_dgrad = os.environ.get('VP3D_WGRAD_ORDER', 'after') != 'before'
+# The forward's BatchNorm apply pass stores the keep decision (ReLU passed and not dropped) as one bit per element; the two
+# backward passes read it instead of recomputing the Philox stream and the affine comparison and run at memory speed
+# (vp3d_bn_act_fwd_mask / vp3d_bn_act_bwd_*_mask). Measured (ncu, serialised): backward passes 327 -> 271 us per step, the
+# forward pass 119 -> 133 us (building and storing the bits); the backward passes run beside the weight-gradient GEMMs
+# while the forward pass is on the critical path, so the STEP does not gain: 1.684-1.725 ms with the mask against
+# 1.670-1.693 without (three alternating runs, same box). Off by default; VP3D_BN_MASK=1 turns it on.
+store_keep_mask = os.environ.get('VP3D_BN_MASK', '0') == '1'
 prefill_arena = os.environ.get('VP3D_PREFILL_ARENA', '1') != '0'   # zero arena of the backward filled during the forward
 debug_keep_saved = False  # tests: keep the last forward's saved per-layer tensors in `debug_last_saved`
 debug_last_saved = None
@@ -68,7 +75,7 @@ debug_last_saved = None
 class _Layer:
     """Everything the backward needs about one convolution + BatchNorm + activation of the stack."""
     __slots__ = ('conv', 'bn', 'taps', 'dilation', 'stride', 't_in', 't_out', 'c_in', 'c_in_pad', 'a_in', 'z', 'scale',
-                 'shift', 'mean', 'invstd', 'drop', 'res_of', 'res_mul', 'res_off', 'res_t', 'w_fwd', 'count', 'fused')
+                 'shift', 'mean', 'invstd', 'drop', 'res_of', 'res_mul', 'res_off', 'res_t', 'w_fwd', 'count', 'fused', 'mask')
 
 
 def _conv_w(dt, conv, rows_pad, k_pad):
@@ -102,7 +109,7 @@ def _dropout_for(model, layer_idx, counter):
     return ops.make_dropout(p, torch.initial_seed(), layer_idx, counter)
 
 
-def _forward_stack(model, x, dt):
+def _forward_stack(model, x, dt, keep_masks=False):
     """-> (y fp32 (N, T', 3*J_out), saved layers). x: (N, T, C_in) fp32 CUDA."""
     n, t_in, c_in = x.shape
     strided = model._strided
@@ -122,6 +129,7 @@ def _forward_stack(model, x, dt):
     def conv_bn_act(idx, conv, bn, a_in, t, cin, cin_pad, plan, res=None, res_t=0, res_mul=1, res_off=0):
         L = _Layer()
         L.fused = None
+        L.mask = None
         L.conv, L.bn = conv, bn
         L.taps, L.dilation, L.stride = plan.taps, plan.dilation, plan.stride
         L.c_in, L.c_in_pad, L.t_in, L.a_in = cin, cin_pad, t, a_in
@@ -146,10 +154,11 @@ def _forward_stack(model, x, dt):
         L.count = count
         L.drop = _dropout_for(model, idx, step)
         L.res_of, L.res_t, L.res_mul, L.res_off = res, res_t, res_mul, res_off
+        want_mask = store_keep_mask and keep_masks     # only a forward that will be differentiated stores them
         if fin is not None:
             L.scale, L.shift, L.mean, L.invstd = fin_out
             a = ops.bn_act_fwd(dt, z, L.scale, L.shift, n, t_out, L.drop, res=res, res_seq_rows=res_t,
-                               res_row_mul=res_mul, res_row_off=res_off)
+                               res_row_mul=res_mul, res_row_off=res_off, want_mask=want_mask)
         elif fuse_bn_finalize and bn.momentum is not None:
             a, L.scale, L.shift, L.mean, L.invstd = ops.bn_finalize_act_fwd(
                 dt, z, stats, count, bn, n, t_out, L.drop, res=res, res_seq_rows=res_t, res_row_mul=res_mul,
@@ -157,7 +166,9 @@ def _forward_stack(model, x, dt):
         else:
             L.scale, L.shift, L.mean, L.invstd = ops.bn_finalize(stats, count, bn, c_pad)
             a = ops.bn_act_fwd(dt, z, L.scale, L.shift, n, t_out, L.drop, res=res, res_seq_rows=res_t,
-                               res_row_mul=res_mul, res_row_off=res_off)
+                               res_row_mul=res_mul, res_row_off=res_off, want_mask=want_mask)
+        if isinstance(a, tuple):
+            a, L.mask = a
         layers.append(L)
         return a, t_out
 
@@ -218,6 +229,7 @@ def _expand_fused(model, dt, x, n, t_in, c_in, c_in_pad, c_pad, plan, drop, laye
     ops.wgrad(dt, h, xv, h, av, 256, 256, 1, gram, block_n=256, dz_cols=k_total)
     w = _conv_w(dt, conv, c_pad, c_in_pad)
     L = _Layer()
+    L.mask = None
     L.conv, L.bn, L.w_fwd = conv, bn, w
     L.taps, L.dilation, L.stride = plan.taps, plan.dilation, plan.stride
     L.c_in, L.c_in_pad, L.t_in, L.a_in = c_in, c_in_pad, t_in, h
@@ -384,7 +396,7 @@ class _StackTrainFn(torch.autograd.Function):
             with torch.cuda.stream(side):
                 side.wait_event(ev)
                 arena = _ZeroArena(_arena_floats(model, x.shape[-1], 2 * len(model.filter_widths) - 1), x.device)
-        y, layers, a_last, t_last, c_pad, w_shrink = _forward_stack(model, x, dt)
+        y, layers, a_last, t_last, c_pad, w_shrink = _forward_stack(model, x, dt, keep_masks=True)
         if arena is not None:
             main.wait_stream(side)
         ctx.arena = arena
@@ -539,7 +551,7 @@ class _StackTrainFn(torch.autograd.Function):
                 break
             dz, dgamma, dbeta = ops.bn_act_bwd(dt, g, L.z, L.scale, L.shift, L.mean, L.invstd, rows, L.bn.num_features,
                                                L.drop, gscale, count=L.count, group=sync_bn_group, sums=sums_all[idx],
-                                               out=(_slot(L.bn.weight), _slot(L.bn.bias)))
+                                               out=(_slot(L.bn.weight), _slot(L.bn.bias)), mask=L.mask)
             done(L.bn.weight, dgamma)
             done(L.bn.bias, dbeta)
             release(L.bn.weight, L.bn.bias)

@@ -409,6 +409,26 @@ int vp3d_bn_act_bwd_apply(int dtype, const void* g, const void* z, const float* 
                           const vp3d_dropout* drop, const double* sum_dy, const double* sum_dy_xhat,
                           const float* gscale_buf, void* dz, float* d_gamma, float* d_beta, void* stream);
 
+/* The same three passes with the keep decision STORED instead of recomputed. vp3d_bn_act_fwd_mask also writes
+ * keep_mask[r][c_pad / 8] (one byte per row and 8-channel group, bit k = channel 8 group + k passed the ReLU and was not
+ * dropped: 1/16 of the 16-bit activation). The backward passes then need neither the dropout stream nor the affine
+ * comparison and run at memory speed (~7 instead of 22-26 instructions per element): with gm = keep ? g : 0,
+ *   reduce: sum_dy[c] += keep_scale * sum_rows gm,  sum_dy_xhat[c] += keep_scale * invstd[c] * sum_rows gm * (z - mean[c])
+ *   apply:  dz = scale * (keep_scale * gm - sum_dy / count - (z - mean) * invstd * sum_dy_xhat / count), d_gamma / d_beta as
+ *           vp3d_bn_act_bwd_apply.
+ * keep_scale = 1 / (1 - p) as quantised by the dropout (256 / (256 - round(256 p)); 1 without dropout). Same results as
+ * the recomputing passes up to fp32 rounding of the folded constants. */
+int vp3d_bn_act_fwd_mask(int dtype, const void* z, const float* scale, const float* shift, const void* res,
+                         long long seqs, long long rows_per_seq, long long res_seq_rows, int res_row_mul, int res_row_off,
+                         int c_pad, const vp3d_dropout* drop, void* a, unsigned char* keep_mask, void* stream);
+int vp3d_bn_act_bwd_reduce_mask(int dtype, const void* g, const void* z, const unsigned char* keep_mask, const float* mean,
+                                const float* invstd, float keep_scale, long long rows, int c_pad, double* sum_dy,
+                                double* sum_dy_xhat, void* stream);
+int vp3d_bn_act_bwd_apply_mask(int dtype, const void* g, const void* z, const unsigned char* keep_mask, const float* scale,
+                               const float* mean, const float* invstd, float keep_scale, long long rows, long long count,
+                               int c, int c_pad, const double* sum_dy, const double* sum_dy_xhat, const float* gscale_buf,
+                               void* dz, float* d_gamma, float* d_beta, void* stream);
+
 /* gscale_buf[0] = 2^floor(log2(64 / max|dy|)) (1 if dy == 0), gscale_buf[1] = 1 / gscale_buf[0]; gscale_buf[2] is
  * scratch (max|dy|). dy: n fp32 values. */
 int vp3d_grad_scale(const float* dy, long long n, float* gscale_buf, void* stream);

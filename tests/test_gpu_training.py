@@ -320,6 +320,48 @@ def test_dropout_mask_statistics_and_consistency():
     assert sums[1].abs().max().item() == 0
 
 
+@pytest.mark.parametrize('dtype,p', [('fp16', 0.25), ('bf16', 0.25), ('fp16', 0.0)])
+def test_backward_with_stored_keep_mask_matches_the_recomputing_passes(dtype, p):
+    """vp3d_bn_act_fwd_mask stores one keep bit per element; vp3d_bn_act_bwd_reduce_mask / _apply_mask must give what the
+    passes that recompute the dropout stream and the ReLU decision give: the same per-channel sums (fp32 summation order
+    aside), the same dz up to the rounding of the folded per-channel constants, the same BatchNorm gradients. Ragged row
+    count, a residual in the forward (the mask must describe the value BEFORE the residual is added)."""
+    dt = native.DTYPE_NAMES[dtype]
+    td = ops.torch_dtype(dt)
+    g_ = torch.Generator().manual_seed(11)
+    seqs, rows_per_seq, C = 3, 333, 512
+    rows = seqs * rows_per_seq
+    z = torch.randn(rows, C, generator=g_).to(td).cuda()
+    g = (torch.randn(rows, C, generator=g_) * 3).to(td).cuda()
+    res = torch.randn(rows, C, generator=g_).to(td).cuda()
+    gamma = (torch.rand(C, generator=g_) + 0.5).cuda()
+    mean = (torch.randn(C, generator=g_) * 0.3).cuda()
+    invstd = (torch.rand(C, generator=g_) + 0.5).cuda()
+    scale = gamma * invstd
+    shift = (torch.randn(C, generator=g_) * 0.2).cuda() - mean * scale
+    d = ops.make_dropout(p, 77, 5)
+    gsb = torch.tensor([4.0, 0.25, 0.0, 0.0], device='cuda')
+    a_ref = ops.bn_act_fwd(dt, z, scale, shift, seqs, rows_per_seq, d, res=res.view(seqs, rows_per_seq, C),
+                           res_seq_rows=rows_per_seq)
+    a, mask = ops.bn_act_fwd(dt, z, scale, shift, seqs, rows_per_seq, d, res=res.view(seqs, rows_per_seq, C),
+                             res_seq_rows=rows_per_seq, want_mask=True)
+    assert torch.equal(a, a_ref) and mask.shape == (rows, C // 8) and mask.dtype == torch.uint8
+    bits = ((mask.unsqueeze(-1) >> torch.arange(8, device='cuda', dtype=torch.uint8)) & 1).reshape(rows, C).bool()
+    pre_drop = (a.float() - res.float())            # = dropout(relu(.)) up to the rounding of the sum
+    assert torch.equal(bits & (pre_drop.abs() > 1e-2), pre_drop.abs() > 1e-2)
+    kept = bits.float().mean().item()
+    assert abs(kept - 0.5 * (1 - p)) < 0.03          # about half pass the ReLU, 1 - p of those the dropout
+    s_ref = torch.zeros((2, C), dtype=torch.float64, device='cuda')
+    s_new = torch.zeros((2, C), dtype=torch.float64, device='cuda')
+    dz_ref, dg_ref, db_ref = ops.bn_act_bwd(dt, g, z, scale, shift, mean, invstd, rows, C, d, gsb, sums=s_ref)
+    dz_new, dg_new, db_new = ops.bn_act_bwd(dt, g, z, scale, shift, mean, invstd, rows, C, d, gsb, sums=s_new, mask=mask)
+    torch.cuda.synchronize()
+    assert rel_err(s_new, s_ref) < 1e-5
+    assert rel_err(dg_new, dg_ref) < 1e-5 and rel_err(db_new, db_ref) < 1e-5
+    assert rel_err(dz_new, dz_ref) < (2e-3 if dtype == 'fp16' else 1.2e-2)
+    assert (dz_new.float() - dz_ref.float()).abs().max().item() <= (0.03 if dtype == 'fp16' else 0.25)   # ~1-2 output ulps
+
+
 def test_train_step_with_dropout_runs_and_learns():
     fw = [3, 3, 3]
     torch.manual_seed(0)
