@@ -52,6 +52,30 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// helpers of the lean forward pass / the stored-mask backward passes
+__device__ __forceinline__ uint32_t prmt_sign(uint32_t a, uint32_t sel) {   // prmt with zero as the second source
+  uint32_t d;
+  asm("prmt.b32 %0, %1, 0, %2;" : "=r"(d) : "r"(a), "r"(sel));
+  return d;
+}
+__device__ __forceinline__ uint32_t prmt2(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+template <int DT>
+__device__ __forceinline__ uint32_t pack2_relu(float a, float b) {   // {lo = relu(a), hi = relu(b)} in the operand type
+  uint32_t d;
+  if (DT == VP3D_F16) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+
 // ---------------------------------------------------------------------------------------------- bn_finalize
 // One block walks all channels (c_pad <= a few thousand): the step counter is read by every thread BEFORE thread 0 ticks
 // it, which the cumulative-average mode (momentum < 0: nn.BatchNorm1d(momentum=None), factor 1 / num_batches_tracked
@@ -149,6 +173,19 @@ bn_act_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, 
     load8(scale, w.grp, sc);
     load8(shift, w.grp, sh);
   }
+  // Lean arithmetic (the pass was issue bound at ~18 instructions per element and 30 % of the HBM peak): the keep scale of
+  // the dropout is folded into the affine (relu(x) k == relu(x k), k > 0); the dropout decision is a byte-wise carry test on
+  // the Philox words (bit 7 of byte i: channel i kept); without a residual the ReLU is a modifier of the 16-bit conversion
+  // and the mask an AND on the packed pairs, with a residual the fp32 value is masked by a sign-replicating prmt before the
+  // add (one rounding, as before). The keep bits (ReLU passed AND kept) for the backward are the byte sign bits gathered
+  // by a multiply.
+  const float ks = drop.on ? drop.keep_scale : 1.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sc[k] *= ks;
+    sh[k] *= ks;
+  }
+  const uint32_t kadd = ((256u - drop.thresh) & 0xFFu) * 0x01010101u, kadd7 = kadd & 0x7F7F7F7Fu;
   const long long iters = (rows + (long long)gridDim.x * kRowsPerIter - 1) / ((long long)gridDim.x * kRowsPerIter);
   for (long long it = 0; it < iters; ++it) {
     uint4 zv[2 * kPairUnroll], rv[2 * kPairUnroll];
@@ -174,30 +211,45 @@ bn_act_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, 
       for (int h = 0; h < 2; ++h) {
         const long long row = 2 * P + h;
         if (row < rows) {
-          float v[8], m[8];
+          float v[8];
           unpack8<DT>(zv[2 * pu + h], v);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], sc[k], sh[k]);
+          // bit 7 of byte i of kl / kh: channel i / 4 + i kept by the dropout (byte >= thresh <=> byte + 256 - thresh carries)
+          uint32_t kl = 0x80808080u, kh = 0x80808080u;
           if (drop.on) {
-            drop_mult8(drop, h ? bits.z : bits.x, h ? bits.w : bits.y, m);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f) * m[k];
+            const uint32_t w0 = h ? bits.z : bits.x, w1 = h ? bits.w : bits.y;
+            kl = lop3_maj(w0, kadd, (w0 & 0x7F7F7F7Fu) + kadd7);
+            kh = lop3_maj(w1, kadd, (w1 & 0x7F7F7F7Fu) + kadd7);
+          }
+          uint4 out;
+          if (res == nullptr) {
+            out.x = pack2_relu<DT>(v[0], v[1]) & prmt_sign(kl, 0x9988u);
+            out.y = pack2_relu<DT>(v[2], v[3]) & prmt_sign(kl, 0xBBAAu);
+            out.z = pack2_relu<DT>(v[4], v[5]) & prmt_sign(kh, 0x9988u);
+            out.w = pack2_relu<DT>(v[6], v[7]) & prmt_sign(kh, 0xBBAAu);
           } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f);
-          }
-          if (keep_mask != nullptr) {
-            // bit k: channel 8 grp + k of this row passed the ReLU and the dropout (v >= 0 here, so v != 0 <=> kept)
-            uint32_t kb = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) kb |= min(__float_as_uint(v[k]), 1u) << k;
-            keep_mask[row * groups + w.grp] = (uint8_t)kb;
-          }
-          if (res != nullptr) {
             float r[8];
             unpack8<DT>(rv[2 * pu + h], r);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] += r[k];
+            for (int k = 0; k < 8; ++k) {
+              // sign of byte (k & 3) replicated over the word: all ones where the channel is kept
+              const uint32_t m = prmt_sign(k < 4 ? kl : kh, 0x8888u + 0x1111u * (k & 3));
+              r[k] += __uint_as_float(__float_as_uint(fmaxf(v[k], 0.f)) & m);
+            }
+            out = pack8<DT>(r);
           }
-          a[row * groups + w.grp] = pack8<DT>(v);
+          if (keep_mask != nullptr) {
+            // ReLU passed <=> sign bit of the pre-activation clear (and not -0): top bytes of the 8 values gathered into two
+            // words, cleared from the dropout keep bits, then the four byte sign bits of each word -> one nibble
+            const uint32_t sl = prmt2(prmt2(__float_as_uint(v[0]), __float_as_uint(v[1]), 0x0073u),
+                                      prmt2(__float_as_uint(v[2]), __float_as_uint(v[3]), 0x0073u), 0x5410u);
+            const uint32_t sh_ = prmt2(prmt2(__float_as_uint(v[4]), __float_as_uint(v[5]), 0x0073u),
+                                       prmt2(__float_as_uint(v[6]), __float_as_uint(v[7]), 0x0073u), 0x5410u);
+            const uint32_t fl = kl & ~sl & 0x80808080u, fh = kh & ~sh_ & 0x80808080u;
+            keep_mask[row * groups + w.grp] = (uint8_t)(((fl * 0x00204081u) >> 28) | (((fh * 0x00204081u) >> 28) << 4));
+          }
+          a[row * groups + w.grp] = out;
         }
       }
     }
@@ -422,11 +474,6 @@ bn_act_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ z
 // The mask is applied to the PACKED gradient: byte -> two words whose byte sign bits are the 8 keep bits (one multiply
 // each), prmt with sign replication -> 16-bit lane masks, one AND per pair. ~7 instructions per element instead of 22-26
 // (ncu: the recomputing kernels are issue bound at 40 % of the HBM peak), so both passes run at memory speed.
-__device__ __forceinline__ uint32_t prmt_sign(uint32_t a, uint32_t sel) {
-  uint32_t d;
-  asm("prmt.b32 %0, %1, 0, %2;" : "=r"(d) : "r"(a), "r"(sel));
-  return d;
-}
 template <int DT>
 __device__ __forceinline__ void masked_unpack8(const uint4& gu, uint32_t keep_byte, float (&gm)[8]) {
   // bit i of the low / high nibble -> bit 8 i + 7 (the sign bit of byte i); the four shifted copies do not overlap
