@@ -142,6 +142,7 @@ bn_act_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, 
   const RowWalk w;
   if (w.grp >= groups) return;
   const DropCtx drop = make_drop(dp);
+  const bool res_flat = res_seq_rows == rows_per_seq * res_row_mul;
   float sc[8], sh[8];
   if (fin.sum != nullptr) {
     const bool publish = blockIdx.x == 0 && w.lane == 0;
@@ -195,9 +196,21 @@ bn_act_fwd_kernel(const uint4* __restrict__ z, const float* __restrict__ scale, 
       if (row < rows) {
         zv[u] = __ldg(z + row * groups + w.grp);
         if (res != nullptr) {
-          const long long seq = row / rows_per_seq;
-          const long long t = row - seq * rows_per_seq;
-          rv[u] = __ldg(res + (seq * res_seq_rows + t * res_row_mul + res_row_off) * groups + w.grp);
+          // residual row of output row (seq, t): seq * res_seq_rows + t * res_row_mul + res_row_off. When a residual
+          // sequence is exactly res_row_mul x an output sequence (the strided 1f blocks) that is row * res_row_mul +
+          // res_row_off -- no 64-bit division per row (it was ~6 instructions per element of this pass)
+          long long rrow;
+          if (res_flat) {
+            rrow = row * res_row_mul + res_row_off;
+          } else if (rows <= 0xFFFFFFFFll) {
+            const unsigned int seq = (unsigned int)row / (unsigned int)rows_per_seq;
+            const unsigned int t = (unsigned int)row - seq * (unsigned int)rows_per_seq;
+            rrow = (long long)seq * res_seq_rows + (long long)t * res_row_mul + res_row_off;
+          } else {
+            const long long seq = row / rows_per_seq;
+            rrow = seq * res_seq_rows + (row - seq * rows_per_seq) * res_row_mul + res_row_off;
+          }
+          rv[u] = __ldg(res + rrow * groups + w.grp);
         }
       }
     }
