@@ -119,3 +119,26 @@ def test_numpy_metrics_against_golden():
     np.testing.assert_array_equal(cam.image_coordinates(ns, w=1000, h=1002), c['img_sc'])
     from common.utils import deterministic_random
     assert deterministic_random(0, 100, 'S1/Walking') == deterministic_random(0, 100, 'S1/Walking')
+
+
+@pytest.mark.parametrize('fw,j,ch,cls', [([3, 3, 3, 3, 3], 17, 1024, '1f'), ([3, 3, 3], 31, 256, '1f'),
+                                         ([3, 3, 3, 3], 17, 512, 'dilated'), ([5, 3], 17, 1024, 'dilated'),
+                                         ([3], 17, 256, '1f')])
+def test_backward_arena_bound_covers_every_accumulator(fw, j, ch, cls):
+    """training._arena_floats (the zero arena of the backward is allocated during the forward, before the saved layers
+    exist) must not be smaller than what the backward takes: BatchNorm sums, one split-K accumulator per convolution in
+    either of its two layouts, the shrink layer's, 16-byte alignment slack."""
+    from common.models.TemporalModel import TemporalModel, TemporalModelOptimized1f
+    from vp3d_b200 import training
+    from vp3d_b200.temporal import K_ALIGN, N_TILE, _round_up
+    model = (TemporalModelOptimized1f if cls == '1f' else TemporalModel)(j, 2, j, fw, channels=ch)
+    c_in = 2 * j
+    n_layers = 2 * len(fw) - 1
+    c_pad, c_in_pad = _round_up(ch, N_TILE), _round_up(c_in, K_ALIGN)
+    takes = [n_layers * 2 * c_pad * 2]                                        # sums_all: [layers][2][c_pad] doubles
+    takes.append(training.SHRINK_PAD * c_pad)                                  # shrink weight gradient
+    takes.append(max(c_pad * 256, fw[0] * c_pad * c_in_pad))                   # expand: fused / narrow or generic layout
+    for conv in model.layers_conv:
+        takes.append(conv.kernel_size[0] * c_pad * c_pad)
+    need = sum((t + 3) // 4 * 4 for t in takes)
+    assert training._arena_floats(model, c_in, n_layers) >= need
